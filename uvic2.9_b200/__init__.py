@@ -1,0 +1,2 @@
+"""uvic2.9_b200 -- B200-native ocean tracer step for the UVic ESCM 2.9 (load as uvic29_b200)."""
+from . import synthetic  # noqa: F401
