@@ -1,0 +1,163 @@
+/*
+ * uvic_b200.h -- C ABI of the B200-native ocean tracer step for the UVic ESCM 2.9.
+ *
+ * This is the drop-in boundary.  The reference has no FFI: its
+ * boundary is a set of Fortran subroutine call sites inside `mom` plus the COMMON blocks
+ * they share.  Each entry point below replaces one of those call sites; the Fortran side
+ * binds them with ISO_C_BINDING from an overlay tracer.F / isopyc.F / vmixc.F
+ * (INTEGRATION.md shows the shim).  Plain pointers and sizes only; no exceptions cross
+ * the ABI; every function returns 0 on success and non-zero on error, with a message
+ * retrievable through uvic_b200_last_error (the reference convention is a message on
+ * stdout followed by `stop '=>routine'`, e.g. 09/mom/tracer.F:1248-1250; the Fortran
+ * wrapper prints the message and stops).
+ *
+ * Layout: every field is the reference's Fortran column-major array, unchanged:
+ * (i,k,j[,n]) with i fastest (09/mom/mw.h:76-77).  Arrays documented "0:km" carry km+1
+ * levels (09/mom/mw.h:249,302,309).  All reals are FP64 (the reference builds with -r8,
+ * run/mk.ver:39-43).
+ *
+ * Latitude slabs: a context owns the rows jrow_lo..jrow_hi of the global grid (2..jmt-1
+ * for a single GPU) and keeps a 2-row halo on each side resident, so every array argument
+ * with a j extent covers the `jl` rows jbase..jbase+jl-1, jbase = max(1, jrow_lo-2),
+ * jbase+jl-1 = min(jmt, jrow_hi+2).  With one GPU that is simply rows 1..jmt.
+ * Paths are relative to /root/reference; "09/" = updates/09/source/.
+ */
+#ifndef UVIC_B200_H
+#define UVIC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct uvic_b200_ctx uvic_b200_ctx;
+
+/* sizes: 09/common/size.h:27-144 */
+typedef struct uvic_b200_dims {
+  int32_t imt, jmt, km;     /* global grid incl. the boundary columns/rows */
+  int32_t nt, nsrc;         /* tracers, tracers with sources */
+  int32_t jrow_lo, jrow_hi; /* first / last global row this context computes */
+} uvic_b200_dims;
+
+/* grid metrics: source/common/grdvar.h:64-86, coord.h, accel.h (host pointers, copied) */
+typedef struct uvic_b200_grid {
+  const double *dxt, *dxtr, *dxt2r, *dxt4r, *dxu, *dxur;                 /* (imt) */
+  const double *dyt, *dytr, *dyt2r, *dyt4r, *dyu, *dyur;                 /* (jmt) global */
+  const double *cst, *cstr, *csu, *csur, *cstdytr, *cstdyt2r, *csu_dyur; /* (jmt) global */
+  const double *dzt, *dztr, *dzt2r, *dztur, *dztlr, *zt, *zw;            /* (km) */
+  const double *dzw, *dzwr;                                              /* (0:km) */
+  const double *dtxcel, *dtxsqr, *dztxcl, *dzwxcl;                       /* (km) */
+  const double *tlat;                                                    /* (imt,jl) */
+  const double *duw, *due;                                               /* (imt) adv_vel */
+  const double *dus, *dun;                                               /* (jmt) adv_vel */
+  const double *eosc;                                                    /* c(km,9) source/mom/state.h:15-16 */
+  const double *to, *so;                                                 /* (km) */
+} uvic_b200_grid;
+
+/* run-time parameters: &mixing / &isopyc of run/control.in, 09/mom/setmom.F:80-82,
+ * and the cpp options of run/mk.in that select code paths */
+typedef struct uvic_b200_params {
+  double aidif, kappa_h;        /* run/control.in:8 */
+  double ahisop, athkdf, slmxr; /* 09/mom/isopyc.F:70-110 */
+  double diff_cet, diff_cnt;    /* 09/mom/hmixc.F:192-200 */
+  double zetar, ogamma, gravrho0r;
+  int32_t fct;                  /* O_fct */
+  int32_t isopycmix;            /* O_isopycmix + O_gent_mcwilliams */
+  int32_t tidal_kv;             /* O_tidal_kv */
+  int32_t fullconvect;          /* O_fullconvect */
+  int32_t mobi;                 /* O_mobi (+ the O_mobi_* / O_carbon* set of run/mk.in) */
+  int32_t fourfil;              /* O_fourfil */
+  const int32_t *itrc;          /* (nt) source slot per tracer, 0 = none (09/mom/mw.h:125-221) */
+  const int32_t *mobi_index;    /* tracer / source index maps for MOBI, see uvic_b200_mobi.h; may be NULL */
+  const double *mobi_par;       /* MOBI parameter block after mobi_init's unit conversion; may be NULL */
+  int32_t n_mobi_index, n_mobi_par;
+} uvic_b200_params;
+
+/* time-invariant 2-D / 3-D inputs (host pointers, copied at create) */
+typedef struct uvic_b200_static {
+  const int32_t *kmt;     /* (imt,jl)  09/common/levind.h */
+  const int32_t *mskhr;   /* (imt,jl)  horizontal regions for basin means, may be NULL */
+  const double *fisop;    /* (imt,jl,km)  note (i,j,k)  09/common/isopyc.h:42 */
+  const double *addisop;  /* (imt,km,jl) */
+  const double *edrm2, *edrs2, *edrk1, *edro1; /* (imt,km,jl) 09/mom/tidal_kv.h */
+  const double *sg_bathy; /* (imt,jl,km) may be NULL without MOBI */
+  const double *fe_hydr;  /* (imt,jl,km) */
+  const double *fe_atmdep;/* (imt,jl,12) */
+} uvic_b200_static;
+
+/* per-step switches and scalars (source/mom/mom.F:111-146, 09/common/switch.F:217-224) */
+typedef struct uvic_b200_stepinfo {
+  double dtts;       /* tracer time step (s) */
+  int32_t leapfrog;  /* 1: leapfrog (c2dtts = 2 dtts); 0: forward mixing step (tau-1 := tau) */
+  int32_t diag;      /* 1: also form tbar / sumbk inventories (tsiperts .and. eots) */
+  double relyr;      /* model time in years (MOBI light / month index) */
+  double co2ccn;     /* atmospheric CO2 (ppmv) for co2calc */
+} uvic_b200_stepinfo;
+
+/* ---- life cycle ---------------------------------------------------------------- */
+int uvic_b200_create(const uvic_b200_dims *dims, const uvic_b200_grid *grid, const uvic_b200_params *par,
+                     const uvic_b200_static *st, int device, uvic_b200_ctx **out);
+int uvic_b200_destroy(uvic_b200_ctx *ctx);
+const char *uvic_b200_last_error(const uvic_b200_ctx *ctx); /* ctx may be NULL: last create error */
+int uvic_b200_set_stream(uvic_b200_ctx *ctx, void *cuda_stream);
+int uvic_b200_synchronize(uvic_b200_ctx *ctx);
+
+/* ---- state movement (replaces loadmw / putmw, 09/mom/loadmw.F:102-117,717-744) ---- */
+/* level: -1 = tau-1, 0 = tau, +1 = tau+1.  host arrays are t(imt,km,jl,nt). */
+int uvic_b200_upload_t(uvic_b200_ctx *ctx, int level, const double *t_host);
+int uvic_b200_download_t(uvic_b200_ctx *ctx, int level, double *t_host);
+int uvic_b200_download_tracer(uvic_b200_ctx *ctx, int level, int n, double *field_host); /* lazy D2H of one tracer (1-based n) */
+/* advective velocities from adv_vel (source/mom/adv_vel.F:60-131): (imt,km,jl),(imt,km,jl),(imt,0:km,jl) */
+int uvic_b200_upload_adv_vel(uvic_b200_ctx *ctx, const double *adv_vet, const double *adv_vnt, const double *adv_vbt);
+/* or: B-grid velocity u(imt,km,jl,2) at tau, and adv_vel on the device */
+int uvic_b200_upload_u(uvic_b200_ctx *ctx, const double *u_host);
+int uvic_b200_adv_vel(uvic_b200_ctx *ctx);
+/* surface / bottom tracer fluxes from setvbc (09/mom/setvbc.F): stf, btf (imt,jl,nt) */
+int uvic_b200_upload_vbc(uvic_b200_ctx *ctx, const double *stf, const double *btf);
+/* MOBI 2-D forcing: dnswr, aice, hice, hsno (imt,jl) (09/mom/tracer.F:370-390) */
+int uvic_b200_upload_forcing(uvic_b200_ctx *ctx, const double *dnswr, const double *aice, const double *hice, const double *hsno);
+/* rotate time levels after a step: tau-1 <- tau <- tau+1 (source/mom/mom.F:210-212) */
+int uvic_b200_rotate(uvic_b200_ctx *ctx);
+
+/* ---- the hot path, one entry per reference call site (device resident) ------------ */
+int uvic_b200_isopyc(uvic_b200_ctx *ctx);                              /* call isopyc  source/mom/mom.F:340 */
+int uvic_b200_vmixc(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si); /* call vmixc   source/mom/mom.F:347 */
+int uvic_b200_tracer(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si);/* call tracer  source/mom/mom.F:389 */
+/* isopyc + vmixc + tracer in one call */
+int uvic_b200_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si);
+
+/* one synchronous step with HOST buffers (what the Fortran shim calls): uploads
+ * t(tau-1), t(tau), the advective velocities and the vertical b.c., runs the step and
+ * returns t(tau+1).  NULL inputs keep the resident copy. */
+int uvic_b200_tracer_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si, const double *t_taum1, const double *t_tau,
+                          const double *adv_vet, const double *adv_vnt, const double *adv_vbt, const double *stf,
+                          const double *btf, double *t_taup1);
+
+/* ---- diagnostics (09/mom/tracer.F:1516-1565) ---------------------------------------- */
+/* volume-weighted inventories sum(t*dV) of every tracer at one time level over the rows
+ * this context owns, deterministic fixed-order reduction; out(nt) */
+int uvic_b200_inventory(uvic_b200_ctx *ctx, int level, double *out_nt);
+/* tbar(km,nt,jl): sum_i t(tau)*dzt*dxt*cst*dyt*tmask per level, tracer and row */
+int uvic_b200_tbar(uvic_b200_ctx *ctx, double *tbar_host);
+/* basin sums sumbk(3,km,nt) by mskhr */
+int uvic_b200_sumbk(uvic_b200_ctx *ctx, double *sumbk_host);
+
+/* ---- introspection (tests, halo exchange, profiling) ---------------------------------- */
+/* copy a named device array to the host; returns the element count through *nelem when
+ * host == NULL.  Names follow the reference's COMMON variables (alphai, K11, diff_cbt ...) */
+int uvic_b200_fetch(uvic_b200_ctx *ctx, const char *name, double *host, size_t *nelem);
+/* raw device pointer of a named array (for NCCL halo exchange driven by the host) */
+void *uvic_b200_device_ptr(uvic_b200_ctx *ctx, const char *name, size_t *nelem);
+/* device pointer of t at a time level: t(imt,km,jl,nt) */
+void *uvic_b200_t_ptr(uvic_b200_ctx *ctx, int level);
+/* number of kernels this context has launched so far */
+int64_t uvic_b200_kernel_launches(const uvic_b200_ctx *ctx);
+int uvic_b200_local_rows(const uvic_b200_ctx *ctx, int32_t *jbase, int32_t *jl);
+const char *uvic_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,2 +1,5 @@
 """uvic2.9_b200 -- B200-native ocean tracer step for the UVic ESCM 2.9 (load as uvic29_b200)."""
 from . import synthetic  # noqa: F401
+from . import timestep  # noqa: F401
+from . import api  # noqa: F401
+from .api import TracerContext, UvicError, load_library  # noqa: F401

@@ -1,0 +1,326 @@
+"""Host-side mirror of the reference's tracer-step call sites, over the C ABI.
+
+The reference's interface for this path is a set of Fortran subroutine calls inside `mom`
+(source/mom/mom.F:340-389): ``call isopyc``, ``call vmixc``, ``call tracer``.  `TracerContext`
+exposes the same three calls (plus `step`, which sequences them as `mom` does) on top of
+libuvic_b200.so (include/uvic_b200.h).  There is no CPU fallback: if the CUDA library is
+missing or no device is present, construction fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libuvic_b200.so")
+
+_c_double_p = C.POINTER(C.c_double)
+_c_int_p = C.POINTER(C.c_int32)
+
+
+class Dims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("imt", "jmt", "km", "nt", "nsrc", "jrow_lo", "jrow_hi")]
+
+
+_GRID_FIELDS = (
+    "dxt dxtr dxt2r dxt4r dxu dxur dyt dytr dyt2r dyt4r dyu dyur cst cstr csu csur cstdytr cstdyt2r csu_dyur "
+    "dzt dztr dzt2r dztur dztlr zt zw dzw dzwr dtxcel dtxsqr dztxcl dzwxcl tlat duw due dus dun eosc to so"
+).split()
+
+
+class Grid(C.Structure):
+    _fields_ = [(n, _c_double_p) for n in _GRID_FIELDS]
+
+
+class Params(C.Structure):
+    _fields_ = (
+        [(n, C.c_double) for n in ("aidif", "kappa_h", "ahisop", "athkdf", "slmxr", "diff_cet", "diff_cnt",
+                                   "zetar", "ogamma", "gravrho0r")]
+        + [(n, C.c_int32) for n in ("fct", "isopycmix", "tidal_kv", "fullconvect", "mobi", "fourfil")]
+        + [("itrc", _c_int_p), ("mobi_index", _c_int_p), ("mobi_par", _c_double_p),
+           ("n_mobi_index", C.c_int32), ("n_mobi_par", C.c_int32)]
+    )
+
+
+class Static(C.Structure):
+    _fields_ = [("kmt", _c_int_p), ("mskhr", _c_int_p)] + [
+        (n, _c_double_p) for n in ("fisop", "addisop", "edrm2", "edrs2", "edrk1", "edro1", "sg_bathy", "fe_hydr", "fe_atmdep")]
+
+
+class StepInfo(C.Structure):
+    _fields_ = [("dtts", C.c_double), ("leapfrog", C.c_int32), ("diag", C.c_int32), ("relyr", C.c_double),
+                ("co2ccn", C.c_double)]
+
+
+# every symbol include/uvic_b200.h declares
+ABI_SYMBOLS = [
+    "uvic_b200_create", "uvic_b200_destroy", "uvic_b200_last_error", "uvic_b200_set_stream", "uvic_b200_synchronize",
+    "uvic_b200_upload_t", "uvic_b200_download_t", "uvic_b200_download_tracer", "uvic_b200_upload_adv_vel",
+    "uvic_b200_upload_u", "uvic_b200_adv_vel", "uvic_b200_upload_vbc", "uvic_b200_upload_forcing", "uvic_b200_rotate",
+    "uvic_b200_isopyc", "uvic_b200_vmixc", "uvic_b200_tracer", "uvic_b200_step", "uvic_b200_tracer_step",
+    "uvic_b200_inventory", "uvic_b200_tbar", "uvic_b200_sumbk", "uvic_b200_fetch", "uvic_b200_device_ptr",
+    "uvic_b200_t_ptr", "uvic_b200_kernel_launches", "uvic_b200_local_rows", "uvic_b200_version",
+]
+
+_lib = None
+
+
+def load_library():
+    """dlopen libuvic_b200.so and declare the prototypes.  Fails loudly when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` (nvcc, sm_100a). "
+            "There is no CPU fallback for the tracer step.")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.uvic_b200_create.argtypes = [C.POINTER(Dims), C.POINTER(Grid), C.POINTER(Params), C.POINTER(Static), C.c_int, C.POINTER(vp)]
+    L.uvic_b200_last_error.restype = C.c_char_p
+    L.uvic_b200_last_error.argtypes = [vp]
+    L.uvic_b200_version.restype = C.c_char_p
+    for fn in ("destroy", "synchronize", "adv_vel", "rotate", "isopyc"):
+        getattr(L, "uvic_b200_" + fn).argtypes = [vp]
+    L.uvic_b200_set_stream.argtypes = [vp, vp]
+    L.uvic_b200_upload_t.argtypes = [vp, C.c_int, vp]
+    L.uvic_b200_download_t.argtypes = [vp, C.c_int, vp]
+    L.uvic_b200_download_tracer.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.uvic_b200_upload_adv_vel.argtypes = [vp, vp, vp, vp]
+    L.uvic_b200_upload_u.argtypes = [vp, vp]
+    L.uvic_b200_upload_vbc.argtypes = [vp, vp, vp]
+    L.uvic_b200_upload_forcing.argtypes = [vp, vp, vp, vp, vp]
+    for fn in ("vmixc", "tracer", "step"):
+        getattr(L, "uvic_b200_" + fn).argtypes = [vp, C.POINTER(StepInfo)]
+    L.uvic_b200_tracer_step.argtypes = [vp, C.POINTER(StepInfo)] + [vp] * 8
+    L.uvic_b200_inventory.argtypes = [vp, C.c_int, vp]
+    L.uvic_b200_tbar.argtypes = [vp, vp]
+    L.uvic_b200_sumbk.argtypes = [vp, vp]
+    L.uvic_b200_fetch.argtypes = [vp, C.c_char_p, vp, C.POINTER(C.c_size_t)]
+    L.uvic_b200_device_ptr.restype = vp
+    L.uvic_b200_device_ptr.argtypes = [vp, C.c_char_p, C.POINTER(C.c_size_t)]
+    L.uvic_b200_t_ptr.restype = vp
+    L.uvic_b200_t_ptr.argtypes = [vp, C.c_int]
+    L.uvic_b200_kernel_launches.restype = C.c_int64
+    L.uvic_b200_kernel_launches.argtypes = [vp]
+    L.uvic_b200_local_rows.argtypes = [vp, _c_int_p, _c_int_p]
+    _lib = L
+    return L
+
+
+class UvicError(RuntimeError):
+    pass
+
+
+def _dp(a):
+    return a.ctypes.data_as(_c_double_p)
+
+
+def _vp(a):
+    return None if a is None else C.c_void_p(a.ctypes.data if isinstance(a, np.ndarray) else int(a))
+
+
+# j axis (counted from the front of the C-ordered numpy array) of every array with a j extent
+_JAXIS = {
+    "kmt": 0, "mskhr": 0, "tlat": 0, "fisop": 1, "sg_bathy": 1, "fe_hydr": 1, "fe_atmdep": 1,
+    "addisop": 0, "edrm2": 0, "edrs2": 0, "edrk1": 0, "edro1": 0,
+    "adv_vet": 0, "adv_vnt": 0, "adv_vbt": 0, "stf": 1, "btf": 1, "u": 1, "t": 2,
+    "dnswr": 0, "aice": 0, "hice": 0, "hsno": 0,
+}
+
+
+def slab_rows(jmt, jlo, jhi):
+    jbase = max(1, jlo - 2)
+    jtop = min(jmt, jhi + 2)
+    return jbase, jtop - jbase + 1
+
+
+def slab_slice(name, arr, jbase, jl):
+    """Rows jbase..jbase+jl-1 (global, 1-based) of a global array."""
+    ax = _JAXIS[name]
+    sl = [slice(None)] * arr.ndim
+    sl[ax] = slice(jbase - 1, jbase - 1 + jl)
+    return np.ascontiguousarray(arr[tuple(sl)])
+
+
+class TracerContext:
+    """Device-resident tracer step for one latitude slab (rows jlo..jhi of the global grid)."""
+
+    def __init__(self, case, jlo=None, jhi=None, device=0, fct=1, isopycmix=1, tidal_kv=1, fullconvect=1, mobi=0,
+                 fourfil=0):
+        self.L = load_library()
+        self.case = case
+        imt, jmt, km, nt, nsrc = case.imt, case.jmt, case.km, case.nt, case.nsrc
+        self.jlo = 2 if jlo is None else jlo
+        self.jhi = jmt - 1 if jhi is None else jhi
+        self.jbase, self.jl = slab_rows(jmt, self.jlo, self.jhi)
+        self.imt, self.jmt, self.km, self.nt, self.nsrc = imt, jmt, km, nt, nsrc
+        a, s = case.arrays, case.scalars
+        self._keep = []
+
+        def f64(x):
+            x = np.ascontiguousarray(x, dtype=np.float64)
+            self._keep.append(x)
+            return x
+
+        def loc(name):
+            return f64(slab_slice(name, a[name], self.jbase, self.jl))
+
+        d = Dims(imt, jmt, km, nt, max(nsrc, 0), self.jlo, self.jhi)
+        g = Grid()
+        for n in _GRID_FIELDS:
+            arr = loc(n) if n == "tlat" else f64(a[n])
+            setattr(g, n, _dp(arr))
+        p = Params()
+        for n in ("aidif", "kappa_h", "ahisop", "athkdf", "slmxr", "diff_cet", "diff_cnt", "zetar", "ogamma", "gravrho0r"):
+            setattr(p, n, float(s[n]))
+        p.fct, p.isopycmix, p.tidal_kv, p.fullconvect, p.mobi, p.fourfil = fct, isopycmix, tidal_kv, fullconvect, mobi, fourfil
+        itrc = np.ascontiguousarray(a["itrc"], dtype=np.int32)
+        self._keep.append(itrc)
+        p.itrc = itrc.ctypes.data_as(_c_int_p)
+        st = Static()
+        kmt = np.ascontiguousarray(slab_slice("kmt", a["kmt"], self.jbase, self.jl), dtype=np.int32)
+        msk = np.ascontiguousarray(slab_slice("mskhr", a["mskhr"], self.jbase, self.jl), dtype=np.int32)
+        self._keep += [kmt, msk]
+        st.kmt = kmt.ctypes.data_as(_c_int_p)
+        st.mskhr = msk.ctypes.data_as(_c_int_p)
+        for n in ("fisop", "addisop", "edrm2", "edrs2", "edrk1", "edro1", "sg_bathy", "fe_hydr", "fe_atmdep"):
+            if n in a:
+                setattr(st, n, _dp(loc(n)))
+        h = C.c_void_p()
+        rc = self.L.uvic_b200_create(C.byref(d), C.byref(g), C.byref(p), C.byref(st), device, C.byref(h))
+        if rc != 0:
+            raise UvicError(self.L.uvic_b200_last_error(None).decode())
+        self.h = h
+        self.dtts = float(s["dtts"])
+        self.relyr = float(s.get("relyr", 0.0))
+        self.co2ccn = float(s.get("co2ccn", 280.0))
+
+    # ---- plumbing ----------------------------------------------------------------
+    def _ck(self, rc):
+        if rc != 0:
+            raise UvicError(self.L.uvic_b200_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.uvic_b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_handle):
+        self._ck(self.L.uvic_b200_set_stream(self.h, C.c_void_p(int(cuda_stream_handle))))
+
+    def synchronize(self):
+        self._ck(self.L.uvic_b200_synchronize(self.h))
+
+    def stepinfo(self, leapfrog=True, diag=False):
+        return StepInfo(self.dtts, 1 if leapfrog else 0, 1 if diag else 0, self.relyr, self.co2ccn)
+
+    # ---- state movement ------------------------------------------------------------
+    def shape_t(self):
+        return (self.nt, self.jl, self.km, self.imt)
+
+    def upload_t(self, level, t_local):
+        t_local = np.ascontiguousarray(t_local, dtype=np.float64)
+        assert t_local.shape == self.shape_t(), (t_local.shape, self.shape_t())
+        self._ck(self.L.uvic_b200_upload_t(self.h, level, _vp(t_local)))
+        self.synchronize()
+
+    def download_t(self, level, out=None):
+        out = np.empty(self.shape_t()) if out is None else out
+        self._ck(self.L.uvic_b200_download_t(self.h, level, _vp(out)))
+        return out
+
+    def load_state(self, case=None):
+        """Upload t(tau-1), t(tau), velocities and vertical b.c. of a (global) Case."""
+        case = case or self.case
+        a = case.arrays
+        sl = lambda n, x: slab_slice(n, x, self.jbase, self.jl)
+        self.upload_t(-1, sl("t", a["t"])[0])
+        self.upload_t(0, sl("t", a["t"])[1])
+        vet, vnt, vbt = (np.ascontiguousarray(sl(n, a[n])) for n in ("adv_vet", "adv_vnt", "adv_vbt"))
+        self._ck(self.L.uvic_b200_upload_adv_vel(self.h, _vp(vet), _vp(vnt), _vp(vbt)))
+        stf, btf = np.ascontiguousarray(sl("stf", a["stf"])), np.ascontiguousarray(sl("btf", a["btf"]))
+        self._ck(self.L.uvic_b200_upload_vbc(self.h, _vp(stf), _vp(btf)))
+        self.synchronize()
+
+    def upload_u(self, u_local):
+        u_local = np.ascontiguousarray(u_local, dtype=np.float64)
+        self._ck(self.L.uvic_b200_upload_u(self.h, _vp(u_local)))
+        self.synchronize()
+
+    def adv_vel(self):
+        self._ck(self.L.uvic_b200_adv_vel(self.h))
+
+    def rotate(self):
+        self._ck(self.L.uvic_b200_rotate(self.h))
+
+    # ---- the reference's call sites ---------------------------------------------------
+    def isopyc(self):
+        self._ck(self.L.uvic_b200_isopyc(self.h))
+
+    def vmixc(self, leapfrog=True):
+        si = self.stepinfo(leapfrog)
+        self._ck(self.L.uvic_b200_vmixc(self.h, C.byref(si)))
+
+    def tracer(self, leapfrog=True, diag=False):
+        si = self.stepinfo(leapfrog, diag)
+        self._ck(self.L.uvic_b200_tracer(self.h, C.byref(si)))
+
+    def step(self, leapfrog=True, diag=False):
+        si = self.stepinfo(leapfrog, diag)
+        self._ck(self.L.uvic_b200_step(self.h, C.byref(si)))
+
+    def tracer_step_host(self, t_taum1, t_tau, adv_vet, adv_vnt, adv_vbt, stf, btf, t_taup1, leapfrog=True):
+        """One synchronous step with host buffers (the call the Fortran shim makes)."""
+        si = self.stepinfo(leapfrog)
+        self._ck(self.L.uvic_b200_tracer_step(self.h, C.byref(si), _vp(t_taum1), _vp(t_tau), _vp(adv_vet), _vp(adv_vnt),
+                                              _vp(adv_vbt), _vp(stf), _vp(btf), _vp(t_taup1)))
+
+    # ---- diagnostics / introspection ----------------------------------------------------
+    def inventory(self, level):
+        out = np.empty(self.nt)
+        self._ck(self.L.uvic_b200_inventory(self.h, level, _vp(out)))
+        return out
+
+    def tbar(self):
+        out = np.empty((self.jhi - self.jlo + 1, self.nt, self.km))
+        self._ck(self.L.uvic_b200_tbar(self.h, _vp(out)))
+        return out
+
+    def sumbk(self):
+        out = np.empty((self.nt, self.km, 3))
+        self._ck(self.L.uvic_b200_sumbk(self.h, _vp(out)))
+        return out
+
+    def fetch(self, name, shape=None):
+        n = C.c_size_t()
+        self._ck(self.L.uvic_b200_fetch(self.h, name.encode(), None, C.byref(n)))
+        out = np.empty(n.value)
+        self._ck(self.L.uvic_b200_fetch(self.h, name.encode(), _vp(out), C.byref(n)))
+        return out.reshape(shape) if shape is not None else out
+
+    def t_ptr(self, level):
+        return self.L.uvic_b200_t_ptr(self.h, level)
+
+    def device_ptr(self, name):
+        n = C.c_size_t()
+        p = self.L.uvic_b200_device_ptr(self.h, name.encode(), C.byref(n))
+        return p, n.value
+
+    @property
+    def kernel_launches(self):
+        return int(self.L.uvic_b200_kernel_launches(self.h))
+
+    def shape3(self):
+        return (self.jl, self.km, self.imt)
+
+    def shape3z(self):
+        return (self.jl, self.km + 1, self.imt)

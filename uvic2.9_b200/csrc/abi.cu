@@ -1,0 +1,379 @@
+// abi.cu -- the C ABI of include/uvic_b200.h: context life cycle, state movement and the
+// entry points that replace the reference's call sites in `mom` (source/mom/mom.F:340-389).
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include "ctx.h"
+
+static std::string g_create_err;
+
+#define CK(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess) {                                                                      \
+      char b_[512];                                                                               \
+      snprintf(b_, sizeof b_, "%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      if (ctx) ctx->err = b_; else g_create_err = b_;                                             \
+      return 1;                                                                                   \
+    }                                                                                             \
+  } while (0)
+
+static int fail(uvic_b200_ctx *ctx, const std::string &msg) {
+  if (ctx) ctx->err = msg; else g_create_err = msg;
+  return 1;
+}
+
+template <typename T>
+static int dev_alloc(uvic_b200_ctx *ctx, const char *name, T **slot, size_t n, const T *host_init) {
+  T *p = nullptr;
+  CK(cudaMalloc((void **)&p, std::max<size_t>(n, 1) * sizeof(T)));
+  if (host_init) CK(cudaMemcpy(p, host_init, n * sizeof(T), cudaMemcpyHostToDevice));
+  else CK(cudaMemset(p, 0, std::max<size_t>(n, 1) * sizeof(T)));
+  *slot = p;
+  ctx->owned.push_back((void *)p);
+  NamedArr a;
+  a.name = name; a.slot = (void **)slot; a.nelem = n; a.is_int = sizeof(T) == 4;
+  ctx->arrs.push_back(a);
+  return 0;
+}
+#define DALLOC(field, n, init) \
+  if (dev_alloc(ctx, #field, const_cast<double **>(&ctx->v.field), (size_t)(n), (const double *)(init))) return 1
+#define IALLOC(field, n, init) \
+  if (dev_alloc(ctx, #field, const_cast<int **>(&ctx->v.field), (size_t)(n), (const int *)(init))) return 1
+
+static void set_levels(uvic_b200_ctx *c, bool leapfrog) {
+  c->v.t_0 = c->t_slot[c->lev[1]];
+  c->v.t_p1 = c->t_slot[c->lev[2]];
+  // on mixing steps both tau-1 and tau are read from the tau slot (09/mom/loadmw.F:109-111)
+  c->v.t_m1 = leapfrog ? c->t_slot[c->lev[0]] : c->t_slot[c->lev[1]];
+}
+
+extern "C" {
+
+const char *uvic_b200_version(void) { return "uvic_b200 0.1 (sm_100a)"; }
+
+const char *uvic_b200_last_error(const uvic_b200_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int uvic_b200_create(const uvic_b200_dims *d, const uvic_b200_grid *g, const uvic_b200_params *par, const uvic_b200_static *st,
+                     int device, uvic_b200_ctx **out) {
+  uvic_b200_ctx *ctx = nullptr;
+  if (!d || !g || !par || !st || !out) return fail(nullptr, "uvic_b200_create: null argument");
+  if (d->imt < 4 || d->jmt < 4 || d->km < 2 || d->nt < 2) return fail(nullptr, "uvic_b200_create: bad dims");
+  if (d->jrow_lo < 2 || d->jrow_hi > d->jmt - 1 || d->jrow_lo > d->jrow_hi)
+    return fail(nullptr, "uvic_b200_create: rows must satisfy 2 <= jrow_lo <= jrow_hi <= jmt-1");
+  if (!par->fct) return fail(nullptr, "uvic_b200_create: only the O_fct advection scheme of run/mk.in is built");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, "uvic_b200_create: no CUDA device (this library has no CPU fallback)");
+  {
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+  }
+  ctx = new uvic_b200_ctx();
+  ctx->device = device;
+  ctx->stream = 0;
+  ctx->launches = 0;
+  ctx->par = *par;
+  ctx->red_partial = ctx->red_out = nullptr;
+  ctx->pin_buf = nullptr; ctx->pin_bytes = 0;
+  DevView &v = ctx->v;
+  memset(&v, 0, sizeof v);
+  v.imt = d->imt; v.jmt = d->jmt; v.km = d->km; v.nt = d->nt; v.nsrc = d->nsrc;
+  v.jlo = d->jrow_lo; v.jhi = d->jrow_hi;
+  v.jbase = std::max(1, v.jlo - 2);
+  int jtop = std::min(v.jmt, v.jhi + 2);
+  v.jl = jtop - v.jbase + 1;
+  const int imt = v.imt, km = v.km, jl = v.jl, jmt = v.jmt, nt = v.nt;
+  v.n2 = (long long)imt * jl;
+  v.n3 = v.n2 * km;
+  v.n3z = v.n2 * (km + 1);
+  v.aidif = par->aidif; v.kappa_h = par->kappa_h; v.ahisop = par->ahisop; v.athkdf = par->athkdf; v.slmxr = par->slmxr;
+  v.diff_cet = par->diff_cet; v.diff_cnt = par->diff_cnt; v.zetar = par->zetar; v.ogamma = par->ogamma;
+  v.gravrho0r = par->gravrho0r;
+  v.fct = par->fct; v.isopycmix = par->isopycmix; v.tidal_kv = par->tidal_kv;
+
+  // closed walls: rows 1 and jmt must be land (the FCT boundary rules rely on it,
+  // 09/mom/tracer_adv_flx.F:467-482, 554-556)
+  for (int jj = 0; jj < jl; jj++) {
+    int jglob = v.jbase + jj;
+    if (jglob == 1 || jglob == jmt)
+      for (int i = 0; i < imt; i++)
+        if (st->kmt[i + (size_t)imt * jj] != 0) { delete ctx; return fail(nullptr, "uvic_b200_create: rows 1 and jmt must be land (kmt=0)"); }
+  }
+
+  // ---- grid ----
+#define G1(name, n) DALLOC(name, n, g->name)
+  G1(dxt, imt); G1(dxtr, imt); G1(dxt2r, imt); G1(dxt4r, imt); G1(dxu, imt); G1(dxur, imt);
+  G1(dyt, jmt); G1(dytr, jmt); G1(dyt2r, jmt); G1(dyt4r, jmt); G1(dyu, jmt); G1(dyur, jmt);
+  G1(cst, jmt); G1(cstr, jmt); G1(csu, jmt); G1(csur, jmt); G1(cstdytr, jmt); G1(cstdyt2r, jmt); G1(csu_dyur, jmt);
+  G1(dzt, km); G1(dztr, km); G1(dzt2r, km); G1(dztur, km); G1(dztlr, km); G1(zt, km); G1(zw, km);
+  G1(dzw, km + 1); G1(dzwr, km + 1);
+  G1(dtxcel, km); G1(dtxsqr, km); G1(dztxcl, km); G1(dzwxcl, km);
+  G1(duw, imt); G1(due, imt); G1(dus, jmt); G1(dun, jmt);
+  G1(eosc, km * 9); G1(to, km); G1(so, km);
+  G1(tlat, v.n2);
+#undef G1
+  // tidal geometry tables (09/mom/vmixc.F:100-104): host libm exp, time invariant
+  {
+    std::vector<double> e1((size_t)km * km, 0.0), den(km, 1.0);
+    for (int k1 = 1; k1 <= km; k1++) {
+      den[k1 - 1] = 1 - exp(-par->zetar * g->zw[k1 - 1]);
+      for (int k = 1; k <= km; k++) {
+        double hab = g->zw[k - 1] - g->zw[k1 - 1];
+        e1[(k - 1) + (size_t)km * (k1 - 1)] = exp(hab * par->zetar);
+      }
+    }
+    DALLOC(edr_e1, (size_t)km * km, e1.data());
+    DALLOC(edr_den, km, den.data());
+  }
+  // ---- static inputs ----
+  IALLOC(kmt, v.n2, st->kmt);
+  if (st->mskhr) IALLOC(mskhr, v.n2, st->mskhr);
+  ctx->itrc_h.assign(nt, 0);
+  if (par->itrc) for (int n = 0; n < nt; n++) ctx->itrc_h[n] = par->itrc[n];
+  for (int n = 0; n < nt; n++)
+    if (ctx->itrc_h[n] < 0 || ctx->itrc_h[n] > v.nsrc) { delete ctx; return fail(nullptr, "uvic_b200_create: itrc out of range"); }
+  IALLOC(itrc, nt, ctx->itrc_h.data());
+  DALLOC(fisop, v.n3, st->fisop);
+  DALLOC(addisop, v.n3, st->addisop);
+  {
+    // latitude-weighted tidal constituent sum (09/mom/vmixc.F:73-84,101-102)
+    std::vector<double> es((size_t)v.n3, 0.0);
+    if (par->tidal_kv && st->edrm2 && st->edrs2 && st->edrk1 && st->edro1) {
+      for (int jj = 0; jj < jl; jj++)
+        for (int i = 0; i < imt; i++) {
+          double lat = g->tlat[i + (size_t)imt * jj];
+          double qk1, qo1, q2;
+          if (fabs(lat) < 30.) { qk1 = 0.33; qo1 = 0.33; } else { qk1 = 1.; qo1 = 1.; }
+          if (fabs(lat) < 70.) q2 = 0.33; else q2 = 1.;
+          for (int k = 0; k < km; k++) {
+            size_t x = i + (size_t)imt * (k + (size_t)km * jj);
+            es[x] = (q2 * (st->edrm2[x] + st->edrs2[x]) + qk1 * st->edrk1[x] + qo1 * st->edro1[x]);
+          }
+        }
+    }
+    DALLOC(edrsum, v.n3, es.data());
+  }
+  // ---- state and work arrays ----
+  for (int s = 0; s < 3; s++) {
+    double *p = nullptr;
+    CK(cudaMalloc((void **)&p, (size_t)v.n3 * nt * sizeof(double)));
+    CK(cudaMemset(p, 0, (size_t)v.n3 * nt * sizeof(double)));
+    ctx->t_slot[s] = p;
+    ctx->owned.push_back(p);
+    ctx->lev[s] = s;
+  }
+  set_levels(ctx, true);
+  DALLOC(u, v.n3 * 2, nullptr);
+  DALLOC(adv_vet, v.n3, nullptr); DALLOC(adv_vnt, v.n3, nullptr); DALLOC(adv_vbt, v.n3z, nullptr);
+  DALLOC(ue, v.n3, nullptr); DALLOC(vn, v.n3, nullptr); DALLOC(wb, v.n3z, nullptr);
+  DALLOC(adv_vetiso, v.n3, nullptr); DALLOC(adv_vntiso, v.n3, nullptr); DALLOC(adv_vbtiso, v.n3z, nullptr);
+  DALLOC(alphai, v.n3, nullptr); DALLOC(betai, v.n3, nullptr);
+  DALLOC(ddxt, v.n3 * 2, nullptr); DALLOC(ddyt, v.n3 * 2, nullptr); DALLOC(ddzt, v.n3z * 2, nullptr);
+  DALLOC(ce, v.n3 * 4, nullptr); DALLOC(cn, v.n3 * 4, nullptr); DALLOC(cbx, v.n3 * 4, nullptr); DALLOC(cby, v.n3 * 4, nullptr);
+  DALLOC(K11, v.n3, nullptr); DALLOC(K22, v.n3, nullptr); DALLOC(K33, v.n3, nullptr);
+  DALLOC(diff_cbt, v.n3, nullptr); DALLOC(tri_a, v.n3, nullptr); DALLOC(tri_e, v.n3, nullptr); DALLOC(tri_bet, v.n3, nullptr);
+  DALLOC(stf, v.n2 * nt, nullptr); DALLOC(btf, v.n2 * nt, nullptr);
+  DALLOC(src, v.n3 * std::max(v.nsrc, 1), nullptr);
+  {
+    // FCT scratch: t_lo + six ratios per tracer of a group; keep the group within ~2 GiB
+    size_t per = (size_t)v.n3 * 7 * sizeof(double);
+    size_t cap = (size_t)2 << 30;
+    v.ngroup = (int)std::max<size_t>(1, std::min<size_t>((size_t)nt, cap / per));
+    DALLOC(t_lo, (size_t)v.n3 * v.ngroup, nullptr);
+    DALLOC(Rfac, (size_t)v.n3 * 6 * v.ngroup, nullptr);
+  }
+  {
+    size_t ntb = (size_t)km * nt * jl;
+    CK(cudaMalloc((void **)&ctx->tbar, ntb * sizeof(double)));
+    CK(cudaMemset(ctx->tbar, 0, ntb * sizeof(double)));
+    ctx->owned.push_back(ctx->tbar);
+    CK(cudaMalloc((void **)&ctx->sumbk, (size_t)3 * km * nt * sizeof(double)));
+    ctx->owned.push_back(ctx->sumbk);
+    CK(cudaMalloc((void **)&ctx->red_out, (size_t)nt * sizeof(double)));
+    ctx->owned.push_back(ctx->red_out);
+  }
+  CK(cudaDeviceSynchronize());
+  *out = ctx;
+  return 0;
+}
+
+int uvic_b200_destroy(uvic_b200_ctx *ctx) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (void *p : ctx->owned) cudaFree(p);
+  delete ctx;
+  return 0;
+}
+
+int uvic_b200_set_stream(uvic_b200_ctx *ctx, void *s) {
+  if (!ctx) return 1;
+  ctx->stream = (cudaStream_t)s;
+  return 0;
+}
+int uvic_b200_synchronize(uvic_b200_ctx *ctx) {
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static int lev_index(int level) { return level + 1; }
+
+int uvic_b200_upload_t(uvic_b200_ctx *ctx, int level, const double *h) {
+  if (level < -1 || level > 1) return fail(ctx, "upload_t: level must be -1, 0 or 1");
+  CK(cudaMemcpyAsync(ctx->t_slot[ctx->lev[lev_index(level)]], h, (size_t)ctx->v.n3 * ctx->v.nt * sizeof(double),
+                     cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+int uvic_b200_download_t(uvic_b200_ctx *ctx, int level, double *h) {
+  if (level < -1 || level > 1) return fail(ctx, "download_t: level must be -1, 0 or 1");
+  CK(cudaMemcpyAsync(h, ctx->t_slot[ctx->lev[lev_index(level)]], (size_t)ctx->v.n3 * ctx->v.nt * sizeof(double),
+                     cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int uvic_b200_download_tracer(uvic_b200_ctx *ctx, int level, int n, double *h) {
+  if (level < -1 || level > 1 || n < 1 || n > ctx->v.nt) return fail(ctx, "download_tracer: bad level or tracer index");
+  CK(cudaMemcpyAsync(h, ctx->t_slot[ctx->lev[lev_index(level)]] + (size_t)(n - 1) * ctx->v.n3, (size_t)ctx->v.n3 * sizeof(double),
+                     cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int uvic_b200_upload_adv_vel(uvic_b200_ctx *ctx, const double *vet, const double *vnt, const double *vbt) {
+  DevView &v = ctx->v;
+  if (vet) CK(cudaMemcpyAsync(v.adv_vet, vet, (size_t)v.n3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (vnt) CK(cudaMemcpyAsync(v.adv_vnt, vnt, (size_t)v.n3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (vbt) CK(cudaMemcpyAsync(v.adv_vbt, vbt, (size_t)v.n3z * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+int uvic_b200_upload_u(uvic_b200_ctx *ctx, const double *u) {
+  CK(cudaMemcpyAsync(ctx->v.u, u, (size_t)ctx->v.n3 * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+int uvic_b200_adv_vel(uvic_b200_ctx *ctx) {
+  launch_adv_vel(ctx);
+  CK(cudaGetLastError());
+  return 0;
+}
+int uvic_b200_upload_vbc(uvic_b200_ctx *ctx, const double *stf, const double *btf) {
+  DevView &v = ctx->v;
+  if (stf) CK(cudaMemcpyAsync(v.stf, stf, (size_t)v.n2 * v.nt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (btf) CK(cudaMemcpyAsync(v.btf, btf, (size_t)v.n2 * v.nt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+int uvic_b200_upload_forcing(uvic_b200_ctx *ctx, const double *, const double *, const double *, const double *) {
+  return fail(ctx, "upload_forcing: MOBI is not built into this library yet");
+}
+int uvic_b200_rotate(uvic_b200_ctx *ctx) {
+  // tau+1 overwrites the old tau-1 slot next step (source/mom/mom.F:210-212)
+  int old_m1 = ctx->lev[0];
+  ctx->lev[0] = ctx->lev[1];
+  ctx->lev[1] = ctx->lev[2];
+  ctx->lev[2] = old_m1;
+  set_levels(ctx, true);
+  return 0;
+}
+
+static void set_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
+  ctx->v.dtts = si->dtts;
+  ctx->v.c2dtts = si->leapfrog ? 2.0 * si->dtts : si->dtts;  // source/mom/mom.F:111-146
+  set_levels(ctx, si->leapfrog != 0);
+}
+
+int uvic_b200_isopyc(uvic_b200_ctx *ctx) {
+  launch_isopyc(ctx);
+  CK(cudaGetLastError());
+  return 0;
+}
+int uvic_b200_vmixc(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
+  set_step(ctx, si);
+  launch_vmixc(ctx);
+  CK(cudaGetLastError());
+  return 0;
+}
+int uvic_b200_tracer(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
+  set_step(ctx, si);
+  if (ctx->par.mobi) return fail(ctx, "tracer: MOBI is not built into this library yet");
+  launch_tracer(ctx, si);
+  CK(cudaGetLastError());
+  if (si->diag) {
+    launch_tbar(ctx);
+    if (ctx->v.mskhr) launch_sumbk(ctx);
+    CK(cudaGetLastError());
+  }
+  return 0;
+}
+int uvic_b200_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
+  set_step(ctx, si);
+  if (uvic_b200_isopyc(ctx)) return 1;
+  if (uvic_b200_vmixc(ctx, si)) return 1;
+  return uvic_b200_tracer(ctx, si);
+}
+
+int uvic_b200_tracer_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si, const double *t_taum1, const double *t_tau,
+                          const double *adv_vet, const double *adv_vnt, const double *adv_vbt, const double *stf,
+                          const double *btf, double *t_taup1) {
+  if (t_taum1 && uvic_b200_upload_t(ctx, -1, t_taum1)) return 1;
+  if (t_tau && uvic_b200_upload_t(ctx, 0, t_tau)) return 1;
+  if (uvic_b200_upload_adv_vel(ctx, adv_vet, adv_vnt, adv_vbt)) return 1;
+  if (uvic_b200_upload_vbc(ctx, stf, btf)) return 1;
+  if (uvic_b200_step(ctx, si)) return 1;
+  if (t_taup1) return uvic_b200_download_t(ctx, 1, t_taup1);
+  return uvic_b200_synchronize(ctx);
+}
+
+int uvic_b200_inventory(uvic_b200_ctx *ctx, int level, double *out) {
+  if (level < -1 || level > 1) return fail(ctx, "inventory: bad level");
+  launch_inventory(ctx, ctx->t_slot[ctx->lev[lev_index(level)]], ctx->red_out);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, ctx->red_out, (size_t)ctx->v.nt * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int uvic_b200_tbar(uvic_b200_ctx *ctx, double *h) {
+  size_t n = (size_t)ctx->v.km * ctx->v.nt * (ctx->v.jhi - ctx->v.jlo + 1);
+  CK(cudaMemcpyAsync(h, ctx->tbar, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int uvic_b200_sumbk(uvic_b200_ctx *ctx, double *h) {
+  CK(cudaMemcpyAsync(h, ctx->sumbk, (size_t)3 * ctx->v.km * ctx->v.nt * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+void *uvic_b200_device_ptr(uvic_b200_ctx *ctx, const char *name, size_t *nelem) {
+  for (auto &a : ctx->arrs)
+    if (a.name == name) {
+      if (nelem) *nelem = a.nelem;
+      return *a.slot;
+    }
+  return nullptr;
+}
+int uvic_b200_fetch(uvic_b200_ctx *ctx, const char *name, double *host, size_t *nelem) {
+  size_t n = 0;
+  void *p = uvic_b200_device_ptr(ctx, name, &n);
+  if (!p) return fail(ctx, std::string("fetch: unknown array ") + name);
+  if (nelem) *nelem = n;
+  if (!host) return 0;
+  for (auto &a : ctx->arrs)
+    if (a.name == name && a.is_int) return fail(ctx, "fetch: integer arrays are not fetchable as double");
+  CK(cudaMemcpyAsync(host, p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+void *uvic_b200_t_ptr(uvic_b200_ctx *ctx, int level) {
+  if (level < -1 || level > 1) return nullptr;
+  return ctx->t_slot[ctx->lev[lev_index(level)]];
+}
+int64_t uvic_b200_kernel_launches(const uvic_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int uvic_b200_local_rows(const uvic_b200_ctx *ctx, int32_t *jbase, int32_t *jl) {
+  if (!ctx) return 1;
+  if (jbase) *jbase = ctx->v.jbase;
+  if (jl) *jl = ctx->v.jl;
+  return 0;
+}
+
+}  // extern "C"

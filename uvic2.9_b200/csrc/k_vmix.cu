@@ -1,0 +1,79 @@
+// k_vmix.cu -- vertical diffusivity and the tracer-independent part of the implicit solve.
+//
+// Replaces `call vmixc` (source/mom/mom.F:347 -> 09/mom/vmixc.F:68-188):
+//   diff_cbt = max(kappa_h, min(100, kappa_h + ogamma*edr/N2)) + K33
+// with edr the Simmons et al. tidal sum over all levels below k.  The geometry factors
+// exp(hab*zetar) and 1-exp(-zetar*zw(k1)) of 09/mom/vmixc.F:103 are time invariant and
+// come from host tables (edr_e1, edr_den), as does the latitude-weighted constituent sum
+// q2*(edrm2+edrs2)+qk1*edrk1+qo1*edro1 (edrsum), so the step itself evaluates no exp.
+//
+// The same column pass factorises the tridiagonal matrix of invtri
+// (source/mom/invtri.F:55-100): a, c, b, e and bet depend only on diff_cbt, the masks,
+// tdt and aidif, not on the tracer, so they are built once per step (the reference
+// rebuilds them for each of the nt tracers) and the per-tracer solve is two sweeps.
+#include "ctx.h"
+
+__global__ void __launch_bounds__(128) k_vmix_column(const DevView v) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int ni = v.imt - 2;
+  int nrow = v.jhi - v.jlo + 1;
+  if (idx >= (long long)ni * nrow) return;
+  int i = (int)(idx % ni) + 2;
+  int j = (int)(idx / ni) + v.jlo;
+  const int km = v.km;
+  const int kb = v.kmt[X2(i, j)];
+
+  // ---- diff_cbt (09/mom/vmixc.F:68-124, 182-188) ----
+  for (int k = 1; k <= km; k++) {
+    double d = 0.0;  // diff_cbt(i,k>=kmt,j) is never assigned in the reference: zero COMMON
+    if (k <= kb - 1) {
+      if (v.tidal_kv) {
+        double drodzb = v.alphai[X3(i, k, j)] * v.ddzt[X3Z(i, k, j)] + v.betai[X3(i, k, j)] * v.ddzt[X3Z(i, k, j) + v.n3z];
+        double zn2 = fmax(-v.gravrho0r * drodzb, 1e-8);
+        double edr = 0.;
+        for (int k1 = k + 1; k1 <= kb; k1++)
+          edr = edr + v.edrsum[X3(i, k1, j)] * v.edr_e1[(k - 1) + km * (k1 - 1)] / v.edr_den[k1 - 1];
+        double zkappa = v.ogamma * edr / zn2;
+        d = fmax(v.kappa_h, fmin(100., zkappa + v.kappa_h));
+      } else {
+        d = v.kappa_h;
+      }
+    }
+    if (v.isopycmix) d = d + v.K33[X3(i, k, j)];
+    v.diff_cbt[X3(i, k, j)] = d;
+  }
+
+  // ---- invtri factorisation (source/mom/invtri.F:55-100) ----
+  const double eps = 1.e-30;
+  double bet = 0.0, cprev = 0.0;
+  for (int k = 1; k <= km; k++) {
+    int km1 = max(1, k - 1), kp1 = min(k + 1, km);
+    double tdt = v.c2dtts * v.dtxcel[k - 1];
+    double factu = v.dztur[k - 1] * tdt * v.aidif;
+    double factl = v.dztlr[k - 1] * tdt * v.aidif;
+    double mk = (kb >= k) ? 1.0 : 0.0, mkp1 = (kb >= kp1) ? 1.0 : 0.0;
+    double a = -v.diff_cbt[X3(i, km1, j)] * factu * mk;
+    double cc = -v.diff_cbt[X3(i, k, j)] * factl * mkp1;
+    if (k == 1) a = 0.0;
+    if (k == km) cc = 0.0;
+    double b = 1.0 - a - cc;
+    double e = 0.0;
+    if (k == 1) {
+      bet = mk / (b + eps);
+    } else {
+      e = cprev * bet;
+      bet = mk / (b - a * e + eps);
+    }
+    v.tri_a[X3(i, k, j)] = a;
+    v.tri_e[X3(i, k, j)] = e;
+    v.tri_bet[X3(i, k, j)] = bet;
+    cprev = cc;
+  }
+}
+
+void launch_vmixc(uvic_b200_ctx *c) {
+  DevView &v = c->v;
+  long long ncol = (long long)(v.imt - 2) * (v.jhi - v.jlo + 1);
+  k_vmix_column<<<cdiv(ncol, 128), 128, 0, c->stream>>>(v);
+  c->launches += 1;
+}
