@@ -180,6 +180,16 @@ class TracerContext:
         itrc = np.ascontiguousarray(a["itrc"], dtype=np.int32)
         self._keep.append(itrc)
         p.itrc = itrc.ctypes.data_as(_c_int_p)
+        if mobi:
+            if not getattr(case, "has_mobi", False):
+                raise UvicError("O_mobi needs the full MOBI tracer set (see mobi_params.mobi_index_maps)")
+            midx = np.ascontiguousarray(a["mobi_idx"], dtype=np.int32)
+            mpar = f64(a["mobi_par"])
+            self._keep.append(midx)
+            p.mobi_index = midx.ctypes.data_as(_c_int_p)
+            p.mobi_par = _dp(mpar)
+            p.n_mobi_index, p.n_mobi_par = midx.size, mpar.size
+        self.mobi = bool(mobi)
         st = Static()
         kmt = np.ascontiguousarray(slab_slice("kmt", a["kmt"], self.jbase, self.jl), dtype=np.int32)
         msk = np.ascontiguousarray(slab_slice("mskhr", a["mskhr"], self.jbase, self.jl), dtype=np.int32)
@@ -249,6 +259,9 @@ class TracerContext:
         self._ck(self.L.uvic_b200_upload_adv_vel(self.h, _vp(vet), _vp(vnt), _vp(vbt)))
         stf, btf = np.ascontiguousarray(sl("stf", a["stf"])), np.ascontiguousarray(sl("btf", a["btf"]))
         self._ck(self.L.uvic_b200_upload_vbc(self.h, _vp(stf), _vp(btf)))
+        if self.mobi:
+            f = [np.ascontiguousarray(sl(n, a[n]), dtype=np.float64) for n in ("dnswr", "aice", "hice", "hsno")]
+            self._ck(self.L.uvic_b200_upload_forcing(self.h, *[_vp(x) for x in f]))
         self.synchronize()
 
     def upload_u(self, u_local):

@@ -176,6 +176,30 @@ int uvic_b200_create(const uvic_b200_dims *d, const uvic_b200_grid *g, const uvi
   DALLOC(diff_cbt, v.n3, nullptr); DALLOC(tri_a, v.n3, nullptr); DALLOC(tri_e, v.n3, nullptr); DALLOC(tri_bet, v.n3, nullptr);
   DALLOC(stf, v.n2 * nt, nullptr); DALLOC(btf, v.n2 * nt, nullptr);
   DALLOC(src, v.n3 * std::max(v.nsrc, 1), nullptr);
+  if (par->mobi) {
+    if (!par->mobi_par || !par->mobi_index || par->n_mobi_par < (int)(sizeof(MobiPar) / sizeof(double)) || par->n_mobi_index < IX_N ||
+        !st->sg_bathy || !st->fe_hydr || !st->fe_atmdep) {
+      delete ctx;
+      return fail(nullptr, "uvic_b200_create: O_mobi needs mobi_par, mobi_index, sg_bathy, fe_hydr and fe_atmdep");
+    }
+    if (km > MOBI_KMAX) { delete ctx; return fail(nullptr, "uvic_b200_create: km exceeds MOBI_KMAX"); }
+    for (int m = 0; m < IX_N; m++) {
+      int x = par->mobi_index[m];
+      bool is_src = (m >= IX_SRC && m < IX_SRC + MOBI_NVAR) || m >= IX_ISALK;
+      if (x < 1 || x > (is_src ? v.nsrc : nt)) { delete ctx; return fail(nullptr, "uvic_b200_create: MOBI index map out of range"); }
+    }
+    double *mp = nullptr;
+    if (dev_alloc(ctx, "mobi_par", &mp, sizeof(MobiPar) / sizeof(double), par->mobi_par)) return 1;
+    v.mobi_par = (const MobiPar *)mp;
+    ctx->mobi_dtnpzd = ((const MobiPar *)par->mobi_par)->dtnpzd;
+    IALLOC(mobi_idx, MOBI_NIDX, nullptr);
+    CK(cudaMemcpy(const_cast<int *>(v.mobi_idx), par->mobi_index, sizeof(int) * std::min(par->n_mobi_index, MOBI_NIDX), cudaMemcpyHostToDevice));
+    DALLOC(sg_bathy, v.n3, st->sg_bathy);
+    DALLOC(fe_hydr, v.n3, st->fe_hydr);
+    DALLOC(fe_atmdep, v.n2 * 12, st->fe_atmdep);
+    DALLOC(dnswr, v.n2, nullptr); DALLOC(aice, v.n2, nullptr); DALLOC(hice, v.n2, nullptr); DALLOC(hsno, v.n2, nullptr);
+    DALLOC(co2_star, v.n3, nullptr); DALLOC(co2_omega, v.n3, nullptr);
+  }
   {
     // FCT scratch: t_lo + six ratios per tracer of a group; keep the group within ~2 GiB
     size_t per = (size_t)v.n3 * 7 * sizeof(double);
@@ -263,8 +287,15 @@ int uvic_b200_upload_vbc(uvic_b200_ctx *ctx, const double *stf, const double *bt
   if (btf) CK(cudaMemcpyAsync(v.btf, btf, (size_t)v.n2 * v.nt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   return 0;
 }
-int uvic_b200_upload_forcing(uvic_b200_ctx *ctx, const double *, const double *, const double *, const double *) {
-  return fail(ctx, "upload_forcing: MOBI is not built into this library yet");
+int uvic_b200_upload_forcing(uvic_b200_ctx *ctx, const double *dnswr, const double *aice, const double *hice, const double *hsno) {
+  DevView &v = ctx->v;
+  if (!ctx->par.mobi) return fail(ctx, "upload_forcing: context was created without O_mobi");
+  size_t nb = (size_t)v.n2 * sizeof(double);
+  if (dnswr) CK(cudaMemcpyAsync(v.dnswr, dnswr, nb, cudaMemcpyHostToDevice, ctx->stream));
+  if (aice) CK(cudaMemcpyAsync(v.aice, aice, nb, cudaMemcpyHostToDevice, ctx->stream));
+  if (hice) CK(cudaMemcpyAsync(v.hice, hice, nb, cudaMemcpyHostToDevice, ctx->stream));
+  if (hsno) CK(cudaMemcpyAsync(v.hsno, hsno, nb, cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
 }
 int uvic_b200_rotate(uvic_b200_ctx *ctx) {
   // tau+1 overwrites the old tau-1 slot next step (source/mom/mom.F:210-212)
@@ -295,7 +326,7 @@ int uvic_b200_vmixc(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
 }
 int uvic_b200_tracer(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
   set_step(ctx, si);
-  if (ctx->par.mobi) return fail(ctx, "tracer: MOBI is not built into this library yet");
+  if (ctx->par.mobi) launch_mobi(ctx, si);
   launch_tracer(ctx, si);
   CK(cudaGetLastError());
   if (si->diag) {

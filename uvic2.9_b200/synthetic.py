@@ -51,6 +51,7 @@ class Case:
     scalars: dict = field(default_factory=dict)
     arrays: dict = field(default_factory=dict)
     tracer_names: list = field(default_factory=list)
+    has_mobi: bool = False
 
     def __getitem__(self, k):
         return self.arrays[k]
@@ -294,6 +295,11 @@ def make_tracers(imt, jmt, km, nt, names, arrays, seed, noise=1.0):
             f = mag * ratio * vert * np.exp(0.35 * sm + 0.15 * sm2 + noise * 0.05 * wn)
         if name.startswith("passive"):
             f = 1.0 + 0.5 * sm + 0.2 * sm2 + noise * 0.05 * wn
+        if name == "alk" and "dic" in names:
+            # keep the carbonate system realistic: alkalinity tracks DIC with a positive excess,
+            # so calcite stays near saturation (Omega_c ~ 1-6) instead of wandering through the
+            # singularity of the PIC:POC formula at Omega_c = 1 - kcapr (09/mom/mobi.F:786)
+            f = t[0, names.index("dic")] + 0.22 + 0.04 * sm - 0.08 * (1.0 - prof) + noise * 0.003 * wn
         f = f * tmask
         f[..., 0] = f[..., -2]
         f[..., -1] = f[..., 1]
@@ -388,4 +394,13 @@ def make_case(imt=102, jmt=102, km=19, nt=2, seed=SEED, names=None, dtts=None, n
             nsrc += 1
             itrc[n] = nsrc
     arrays["itrc"] = itrc
-    return Case(imt=imt, jmt=jmt, km=km, nt=nt, nsrc=nsrc, scalars=scalars, arrays=arrays, tracer_names=names)
+    case = Case(imt=imt, jmt=jmt, km=km, nt=nt, nsrc=nsrc, scalars=scalars, arrays=arrays, tracer_names=names)
+    from . import mobi_params as mp
+    if all(s in names for s in mp.MOBI_STATE + ["alk", "o2", "c14"]):
+        # full MOBI tracer set: source slots in tracer_init's order, gather/scatter maps, parameters
+        itrc, idx, nsrc = mp.mobi_index_maps(names)
+        arrays["itrc"], arrays["mobi_idx"] = itrc, idx
+        case.nsrc = nsrc
+        arrays["mobi_par"] = mp.mobi_par_block(case)
+        case.has_mobi = True
+    return case
