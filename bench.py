@@ -1,0 +1,429 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native UVic ESCM 2.9 ocean tracer step.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+
+One "step" = one pass of the hot path (isopyc -> vmixc -> MOBI -> tracer, as `mom` sequences
+it, source/mom/mom.F:340-389) over one batch of synthetic fields, followed by the halo
+exchange (N > 1) and the time-level rotation.  The default workload is the configuration
+BASELINE.json quotes its metric on: the 100x100x19 ocean (imt=102, jmt=102, km=19) with
+isopycnal mixing + GM + FCT advection and the full MOBI tracer set of run/mk.in (nt=37,
+nsrc=35).  With N GPUs the global grid grows to 100*N interior rows (weak scaling): every rank
+owns a 100-row latitude slab of the same shape and exchanges 2-row halos over NCCL.
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle (a restatement of the
+reference Fortran, which cannot be built here -- no Fortran compiler, no netCDF, no input
+data) on the host cores, one serial replica per core, on the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib.util
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (imt, rows per GPU, km, nt, mobi)
+    "uvic100_mobi37": dict(imt=102, rows=100, km=19, nt=37, mobi=1,
+                           desc="UVic 2.9 100x100x19, isopycnal mixing + GM + FCT + full MOBI tracer set (run/mk.in), nt=37"),
+    "uvic100_ts": dict(imt=102, rows=100, km=19, nt=2, mobi=0, desc="UVic 2.9 100x100x19, T,S only, isopyc + GM + FCT"),
+    "half_deg_40": dict(imt=722, rows=360, km=40, nt=40, mobi=1,
+                        desc="synthetic 0.5 deg 720x360x40, 40 tracers (37 MOBI + 3 passive), isopyc + FCT + invtri"),
+    "tenth_deg_slab_40": dict(imt=3602, rows=225, km=60, nt=40, mobi=1,
+                              desc="synthetic 0.1 deg 3600x(225 rows per GPU)x60 latitude slab, 40 tracers"),
+}
+
+
+def load_pkg():
+    if "uvic29_b200" in sys.modules:
+        return sys.modules["uvic29_b200"]
+    path = os.path.join(ROOT, "uvic2.9_b200", "__init__.py")
+    spec = importlib.util.spec_from_file_location("uvic29_b200", path, submodule_search_locations=[os.path.dirname(path)])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["uvic29_b200"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def make_case(pkg, wl, world):
+    w = WORKLOADS[wl]
+    jmt = 2 + w["rows"] * world
+    return pkg.synthetic.make_case(imt=w["imt"], jmt=jmt, km=w["km"], nt=w["nt"])
+
+
+def units_per_step(case):
+    # tracer cell-updates per step: land cells count
+    return (case.imt - 2) * (case.jmt - 2) * case.km * case.nt
+
+
+def algorithmic_step_bytes(case, mobi):
+    """B_step = N*[24 nt + 16 nsrc + 8 n_mobi_in + 2*8*C], C = 24 shared fields."""
+    n = case.imt * case.km * case.jmt
+    nsrc = case.nsrc if mobi else 0
+    n_mobi_in = 37 if mobi else 0
+    return n * (24 * case.nt + 16 * nsrc + 8 * n_mobi_in + 384)
+
+
+def kernel_bytes_per_launch(name, case, ctx, ngroup_launch):
+    """Compulsory bytes of one launch of each kernel as designed: every
+    distinct field it reads once + every field it writes once, for the cells it covers."""
+    cells = (case.imt - 2) * case.km * (ctx.jhi - ctx.jlo + 1)
+    cells_r = (case.imt - 2) * case.km * (min(case.jmt - 1, ctx.jhi + 1) - max(2, ctx.jlo - 1) + 1)
+    g = ngroup_launch
+    ocean = float((case["kmt"][ctx.jlo - 1:ctx.jhi, 1:-1]).sum())  # ocean cells in the owned rows
+    table = {
+        "k_fct_tlo": cells_r * (16 * g + 24),          # t(tau-1) in, t_lo out per tracer; 3 face velocities
+        "k_fct_rfac": cells_r * (72 * g + 24),         # t_lo, t(tau-1), t(tau) in; 6 ratios out; velocities
+        "k_update": cells * (80 * g + 176),            # 6 ratios, t(tau-1), t(tau), src in; t(tau+1) out; 22 shared fields
+        "k_invtri": cells * (16 * g + 24),             # t(tau+1) in/out; a, e, bet
+        "k_convect": cells * (16 * case.nt),           # worst case: every tracer read + written
+        "k_mobi_column": ocean * 8 * (37 + 2 + 35),    # 37 tracers + CO2*, Omega in; 35 sources out
+        "k_mobi_co2": ocean * 8 * (4 + 2),
+        "k_elements": cells * 8 * (2 + 8),
+        "k_isocoef": cells * 8 * (10 + 19),
+        "k_gm_faces": cells * 8 * (8 + 2),
+        "k_gm_column": cells * 8 * (5 + 4),
+        "k_vmix_column": cells * 8 * (5 + 4),
+    }
+    return table.get(name)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_step_time(pkg, case, mobi, nsteps, warm=1):
+    """Seconds per step of the CPU oracle (single thread) on this case."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import make_oracle, oracle_rotate, oracle_set_step
+
+    o = make_oracle(case, do_mobi=mobi)
+    itt = 0
+    times = []
+    for s in range(warm + nsteps):
+        itt += 1
+        lf = pkg.timestep.is_leapfrog(itt, 16)
+        oracle_set_step(o, case, lf)
+        t0 = time.perf_counter()
+        o.call("ora_step")
+        dt = time.perf_counter() - t0
+        oracle_rotate(o)
+        if s >= warm:
+            times.append(dt)
+    o.close()
+    return sum(times) / len(times)
+
+
+def _replica(args):
+    wl, nsteps, warm = args
+    pkg = load_pkg()
+    case = make_case(pkg, wl, 1)
+    return oracle_step_time(pkg, case, WORKLOADS[wl]["mobi"], nsteps, warm)
+
+
+def run_reference(a):
+    """--impl reference: the CPU restatement of the reference on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+
+    pkg = load_pkg()
+    case = make_case(pkg, a.workload, 1)
+    cores = os.cpu_count() or 1
+    nrep = max(1, min(cores, 64))
+    # each replica times `steps` serial steps of the same workload after `warmup` untimed ones;
+    # bounded so the whole arm ends within a few minutes
+    nsteps = max(1, min(a.steps, 8))
+    warm = max(1, min(a.warmup, 1))
+    t0 = time.perf_counter()
+    with mp.get_context("spawn").Pool(nrep) as pool:
+        per = pool.map(_replica, [(a.workload, nsteps, warm)] * nrep)
+    wall = time.perf_counter() - t0
+    tmax = max(per)
+    units = units_per_step(case)
+    value = nrep * units / tmax / 1e9
+    w = WORKLOADS[a.workload]
+    line = {
+        "impl": "reference", "metric": "tracer cell-updates/sec", "value": value, "unit": "G cell*tracer/s", "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tmax / nrep, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": a.workload, "desc": w["desc"], "grid": [case.imt, case.jmt, case.km], "nt": case.nt},
+        "cpu_baseline": {"value": value, "unit": "G cell*tracer/s", "cores": nrep, "kind": "port",
+                         "sample": f"{nrep} independent serial replicas (the reference is a serial code) x {nsteps} full steps of the "
+                                   f"workload after {warm} warm-up; oracle/ C restatement, gcc -O2 -ffp-contract=off; "
+                                   f"single-replica step {1e3 * min(per):.0f}-{1e3 * tmax:.0f} ms; wall {wall:.0f} s"},
+        "e2e": {"value": value, "unit": "G cell*tracer/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="uvic100_mobi37", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        return run_reference(a)
+
+    import numpy as np
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the tracer step has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    pkg = load_pkg()
+    w = WORKLOADS[a.workload]
+    warmup = max(a.warmup, 3)
+    case = make_case(pkg, a.workload, world)
+    parts = pkg.slab.partition_rows(case.jmt, world)
+    jlo, jhi = parts[rank]
+    ctx = pkg.TracerContext(case, jlo=jlo, jhi=jhi, device=local, mobi=w["mobi"])
+    ctx.load_state()
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    halo = pkg.slab.HaloExchanger(case.jmt, rank, world, dist)
+    tviews = {}
+
+    def tp1_tensor():
+        p = ctx.t_ptr(+1)
+        if p not in tviews:
+            tviews[p] = pkg.slab.device_tensor(p, ctx.shape_t(), local)
+        return tviews[p]
+
+    state = {"itt": 0}
+
+    def one_step():
+        state["itt"] += 1
+        ctx.step(leapfrog=pkg.timestep.is_leapfrog(state["itt"], 16))
+        if world > 1:
+            halo.exchange(tp1_tensor())
+        ctx.rotate()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        one_step()
+    # ---- timed region: device resident -------------------------------------------------
+    barrier()
+    ctx.profile_reset()
+    ctx.profile_enable(True)
+    l0 = ctx.kernel_launches
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(a.steps):
+        one_step()
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop() if rank == 0 else None
+    launches = ctx.kernel_launches - l0
+    ctx.profile_enable(False)
+    prof = ctx.profile()
+    if world > 1:
+        tt = torch.tensor([ms], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    units = units_per_step(case)
+    ms_step = ms / a.steps
+    value = units / (ms_step * 1e-3) / 1e9
+
+    # ---- end to end: host buffers through the reference-facing C ABI call ---------------
+    e2e = None
+    if not a.no_e2e:
+        sl = lambda n: np.ascontiguousarray(pkg.api.slab_slice(n, case[n], ctx.jbase, ctx.jl))
+
+        def pinned(x):
+            t = torch.empty(x.shape, dtype=torch.float64, pin_memory=True)
+            t.numpy()[...] = x
+            return t
+
+        h_vet, h_vnt, h_vbt = pinned(sl("adv_vet")), pinned(sl("adv_vnt")), pinned(sl("adv_vbt"))
+        h_stf, h_btf = pinned(sl("stf")), pinned(sl("btf"))
+        h_out = torch.empty(ctx.shape_t(), dtype=torch.float64, pin_memory=True)
+        h2d = sum(x.numel() * 8 for x in (h_vet, h_vnt, h_vbt, h_stf, h_btf))
+        d2h = h_out.numel() * 8
+
+        def e2e_step():
+            state["itt"] += 1
+            lf = pkg.timestep.is_leapfrog(state["itt"], 16)
+            # t(tau-1), t(tau) stay resident (NULL = keep); velocities and vertical b.c. come from the host,
+            # t(tau+1) goes back to the host: what the Fortran shim moves every step
+            ctx.tracer_step_host(None, None, h_vet.numpy(), h_vnt.numpy(), h_vbt.numpy(), h_stf.numpy(), h_btf.numpy(),
+                                 h_out.numpy(), leapfrog=lf)
+            if world > 1:
+                halo.exchange(tp1_tensor())
+            ctx.rotate()
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        ev0.record(stream)
+        for _ in range(a.steps):
+            e2e_step()
+        ev1.record(stream)
+        barrier()
+        ms_e = ev0.elapsed_time(ev1)
+        wall_e = (time.perf_counter() - t0) * 1e3
+        ms_e = max(ms_e, wall_e)   # the call is synchronous: host wall clock bounds it
+        if world > 1:
+            tt = torch.tensor([ms_e], device=f"cuda:{local}", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms_e = float(tt.item())
+        e2e = {"value": units / (ms_e / a.steps * 1e-3) / 1e9, "unit": "G cell*tracer/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e / a.steps,
+               "note": "uvic_b200_tracer_step: adv velocities + stf/btf H2D from pinned memory, t(tau+1) D2H every step"}
+
+    # ---- conservation check on the state the timed steps produced -----------------------
+    inv = ctx.inventory(0)
+
+    if rank != 0:
+        ctx.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ------------------------------------------------
+    peaks = {}
+    pth = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pth):
+        peaks = json.load(open(pth))
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    tot_ms = sum(v[0] for v in prof.values()) or 1.0
+    kern = []
+    for name, (kms, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+        per_launch_ms = kms / max(cnt, 1)
+        groups = max(1, cnt // a.steps)
+        ng = -(-case.nt // groups) if name in ("k_fct_tlo", "k_fct_rfac", "k_update", "k_invtri") else case.nt
+        b = kernel_bytes_per_launch(name, case, ctx, ng)
+        kern.append({"kernel": name, "launches": cnt, "ms_total": round(kms, 4), "share": round(kms / tot_ms, 4),
+                     "us_per_launch": round(1e3 * per_launch_ms, 2),
+                     "gbs": round(b / (per_launch_ms * 1e-3) / 1e9, 1) if b else None})
+    top = kern[0]
+    top_bytes = kernel_bytes_per_launch(top["kernel"], case, ctx, -(-case.nt // max(1, top["launches"] // a.steps)))
+    achieved = top_bytes / (top["us_per_launch"] * 1e-6) / 1e9 if top_bytes else None
+    roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                "bytes_per_launch": top_bytes, "us_per_launch": top["us_per_launch"],
+                "note": "compulsory bytes of the launch as designed / CUDA-event time; see profiles/ for the ncu capture"}
+    step_bytes = algorithmic_step_bytes(case, w["mobi"]) / world
+    step_hbm = {"algorithmic_bytes_per_step": step_bytes, "achieved": step_bytes / (ms_step * 1e-3) / 1e9, "peak": peak,
+                "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak, "unit": "GB/s",
+                "note": "SURVEY 8(d) B_step per GPU / step time"}
+
+    cpu = None
+    if world == 1 and not a.no_cpu_baseline:
+        # bounded sample of the same workload on one host core (about 10-30 s)
+        t_est = 2.5 * units / 7.3e6
+        ns = max(1, min(5, int(20.0 / max(t_est, 0.1))))
+        sub = case
+        sample = f"{ns} full steps of the same workload after 1 warm-up"
+        if t_est > 60:
+            # large synthetic grids: time a latitude sub-slab and scale
+            rows = max(8, int((case.jmt - 2) * 20.0 / t_est))
+            sub = pkg.synthetic.make_case(imt=case.imt, jmt=rows + 2, km=case.km, nt=case.nt)
+            ns = 1
+            sample = f"1 full step of a {rows}-row latitude sub-slab of the workload, throughput per cell"
+        tstep = oracle_step_time(pkg, sub, w["mobi"], ns, 1)
+        cpu = {"value": units_per_step(sub) / tstep / 1e9, "unit": "G cell*tracer/s", "cores": 1, "kind": "port",
+               "sample": sample + "; oracle/ C restatement (gcc -O2 -ffp-contract=off), single thread",
+               "ms_per_step": 1e3 * tstep}
+
+    line = {
+        "metric": "tracer cell-updates/sec", "value": value, "unit": "G cell*tracer/s", "n_gpus": world, "steps": a.steps,
+        "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": a.workload, "desc": w["desc"], "grid": [case.imt, case.jmt, case.km], "nt": case.nt,
+                   "nsrc": case.nsrc, "rows_per_gpu": w["rows"], "parallelism": f"latitude slabs x{world}, 2-row NCCL halos",
+                   "l2": "per-step working set (3 time levels + sources + coefficients + FCT scratch) exceeds the 126 MB L2; no explicit flush",
+                   "time_stepping": "leapfrog with a forward mixing step every 16th (run/control.in nmix=16)"},
+        "sim_years_per_day": 86400.0 / (292.0 * ms_step * 1e-3),
+        "roofline": roofline, "step_hbm": step_hbm, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+        "clocks": clk, "kernels": kern, "inventory_check": {"finite": bool(np.isfinite(inv).all())},
+    }
+    print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -154,6 +154,11 @@ void *uvic_b200_device_ptr(uvic_b200_ctx *ctx, const char *name, size_t *nelem);
 void *uvic_b200_t_ptr(uvic_b200_ctx *ctx, int level);
 /* number of kernels this context has launched so far */
 int64_t uvic_b200_kernel_launches(const uvic_b200_ctx *ctx);
+/* per-kernel device time, measured with CUDA events on the launch stream while enabled */
+int uvic_b200_profile_enable(uvic_b200_ctx *ctx, int on);
+int uvic_b200_profile_count(uvic_b200_ctx *ctx); /* synchronises; number of distinct kernels seen */
+int uvic_b200_profile_get(uvic_b200_ctx *ctx, int idx, char *name, int name_len, double *total_ms, int64_t *count);
+int uvic_b200_profile_reset(uvic_b200_ctx *ctx);
 int uvic_b200_local_rows(const uvic_b200_ctx *ctx, int32_t *jbase, int32_t *jl);
 const char *uvic_b200_version(void);
 

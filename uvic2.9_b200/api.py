@@ -62,6 +62,7 @@ ABI_SYMBOLS = [
     "uvic_b200_isopyc", "uvic_b200_vmixc", "uvic_b200_tracer", "uvic_b200_step", "uvic_b200_tracer_step",
     "uvic_b200_inventory", "uvic_b200_tbar", "uvic_b200_sumbk", "uvic_b200_fetch", "uvic_b200_device_ptr",
     "uvic_b200_t_ptr", "uvic_b200_kernel_launches", "uvic_b200_local_rows", "uvic_b200_version",
+    "uvic_b200_profile_enable", "uvic_b200_profile_count", "uvic_b200_profile_get", "uvic_b200_profile_reset",
 ]
 
 _lib = None
@@ -106,6 +107,10 @@ def load_library():
     L.uvic_b200_kernel_launches.restype = C.c_int64
     L.uvic_b200_kernel_launches.argtypes = [vp]
     L.uvic_b200_local_rows.argtypes = [vp, _c_int_p, _c_int_p]
+    L.uvic_b200_profile_enable.argtypes = [vp, C.c_int]
+    L.uvic_b200_profile_count.argtypes = [vp]
+    L.uvic_b200_profile_get.argtypes = [vp, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    L.uvic_b200_profile_reset.argtypes = [vp]
     _lib = L
     return L
 
@@ -327,6 +332,23 @@ class TracerContext:
         n = C.c_size_t()
         p = self.L.uvic_b200_device_ptr(self.h, name.encode(), C.byref(n))
         return p, n.value
+
+    def profile_enable(self, on=True):
+        self._ck(self.L.uvic_b200_profile_enable(self.h, 1 if on else 0))
+
+    def profile_reset(self):
+        self._ck(self.L.uvic_b200_profile_reset(self.h))
+
+    def profile(self):
+        """{kernel name: (total ms, launches)} accumulated since the last reset (CUDA events)."""
+        n = self.L.uvic_b200_profile_count(self.h)
+        out = {}
+        for q in range(max(n, 0)):
+            name = C.create_string_buffer(64)
+            ms, cnt = C.c_double(), C.c_int64()
+            self._ck(self.L.uvic_b200_profile_get(self.h, q, name, 64, C.byref(ms), C.byref(cnt)))
+            out[name.value.decode()] = (ms.value, cnt.value)
+        return out
 
     @property
     def kernel_launches(self):

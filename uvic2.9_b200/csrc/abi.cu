@@ -77,6 +77,8 @@ int uvic_b200_create(const uvic_b200_dims *d, const uvic_b200_grid *g, const uvi
   ctx->par = *par;
   ctx->red_partial = ctx->red_out = nullptr;
   ctx->pin_buf = nullptr; ctx->pin_bytes = 0;
+  ctx->prof_on = false;
+  ctx->mobi_dtnpzd = 0.0;
   DevView &v = ctx->v;
   memset(&v, 0, sizeof v);
   v.imt = d->imt; v.jmt = d->jmt; v.km = d->km; v.nt = d->nt; v.nsrc = d->nsrc;
@@ -400,6 +402,46 @@ void *uvic_b200_t_ptr(uvic_b200_ctx *ctx, int level) {
   return ctx->t_slot[ctx->lev[lev_index(level)]];
 }
 int64_t uvic_b200_kernel_launches(const uvic_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int uvic_b200_profile_enable(uvic_b200_ctx *ctx, int on) {
+  if (!ctx) return 1;
+  ctx->prof_on = on != 0;
+  return 0;
+}
+// drain pending event pairs into the per-kernel totals
+static int prof_drain(uvic_b200_ctx *ctx) {
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (auto &r : ctx->prof_pending) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, r.a, r.b));
+    ctx->prof_ms[r.id] += ms;
+    ctx->prof_count[r.id] += 1;
+    ctx->prof_free.push_back(r.a);
+    ctx->prof_free.push_back(r.b);
+  }
+  ctx->prof_pending.clear();
+  return 0;
+}
+int uvic_b200_profile_count(uvic_b200_ctx *ctx) {
+  if (!ctx || prof_drain(ctx)) return -1;
+  return (int)ctx->prof_names.size();
+}
+int uvic_b200_profile_get(uvic_b200_ctx *ctx, int idx, char *name, int name_len, double *total_ms, int64_t *count) {
+  if (!ctx || idx < 0 || idx >= (int)ctx->prof_names.size()) return 1;
+  if (name && name_len > 0) {
+    strncpy(name, ctx->prof_names[idx].c_str(), name_len - 1);
+    name[name_len - 1] = 0;
+  }
+  if (total_ms) *total_ms = ctx->prof_ms[idx];
+  if (count) *count = ctx->prof_count[idx];
+  return 0;
+}
+int uvic_b200_profile_reset(uvic_b200_ctx *ctx) {
+  if (!ctx || prof_drain(ctx)) return 1;
+  for (auto &x : ctx->prof_ms) x = 0.0;
+  for (auto &x : ctx->prof_count) x = 0;
+  return 0;
+}
 int uvic_b200_local_rows(const uvic_b200_ctx *ctx, int32_t *jbase, int32_t *jl) {
   if (!ctx) return 1;
   if (jbase) *jbase = ctx->v.jbase;

@@ -53,8 +53,7 @@ __global__ void __launch_bounds__(128) k_advvel_column(const DevView v) {
 void launch_adv_vel(uvic_b200_ctx *c) {
   DevView &v = c->v;
   long long tot = (long long)v.imt * v.km * v.jl;
-  k_advvel_faces<<<cdiv(tot, 256), 256, 0, c->stream>>>(v);
+  KLAUNCH("k_advvel_faces", k_advvel_faces, cdiv(tot, 256), 256, v);
   long long ncol = (long long)(v.imt - 2) * v.jl;
-  k_advvel_column<<<cdiv(ncol, 128), 128, 0, c->stream>>>(v);
-  c->launches += 2;
+  KLAUNCH("k_advvel_column", k_advvel_column, cdiv(ncol, 128), 128, v);
 }

@@ -368,12 +368,10 @@ void launch_isopyc(uvic_b200_ctx *c) {
   DevView &v = c->v;
   long long ncell = (long long)(v.imt - 2) * v.km * v.jl;
   if (v.isopycmix) {
-    k_elements<<<cdiv(ncell, 256), 256, 0, c->stream>>>(v);
-    k_isocoef<<<cdiv(ncell, 256), 256, 0, c->stream>>>(v);
-    k_gm_faces<<<cdiv(ncell, 256), 256, 0, c->stream>>>(v);
-    c->launches += 3;
+    KLAUNCH("k_elements", k_elements, cdiv(ncell, 256), 256, v);
+    KLAUNCH("k_isocoef", k_isocoef, cdiv(ncell, 256), 256, v);
+    KLAUNCH("k_gm_faces", k_gm_faces, cdiv(ncell, 256), 256, v);
   }
   long long ncol = (long long)(v.imt - 2) * v.jl;
-  k_gm_column<<<cdiv(ncol, 128), 128, 0, c->stream>>>(v);
-  c->launches += 1;
+  KLAUNCH("k_gm_column", k_gm_column, cdiv(ncol, 128), 128, v);
 }

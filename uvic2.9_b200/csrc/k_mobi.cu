@@ -743,7 +743,6 @@ void launch_mobi(uvic_b200_ctx *c, const uvic_b200_stepinfo *si) {
   double rnbio = 1. / nbio;
   long long ncell = (long long)(v.imt - 2) * v.km * (v.jhi - v.jlo + 1);
   long long ncol = (long long)(v.imt - 2) * (v.jhi - v.jlo + 1);
-  k_mobi_co2<<<cdiv(ncell, 128), 128, 0, c->stream>>>(v);
-  k_mobi_column<<<cdiv(ncol, 64), 64, 0, c->stream>>>(v, mi, declin, nbio, dtbio, rdtts, rnbio);
-  c->launches += 2;
+  KLAUNCH("k_mobi_co2", k_mobi_co2, cdiv(ncell, 128), 128, v);
+  KLAUNCH("k_mobi_column", k_mobi_column, cdiv(ncol, 64), 64, v, mi, declin, nbio, dtbio, rdtts, rnbio);
 }

@@ -87,18 +87,15 @@ __global__ void __launch_bounds__(256) k_sumbk(const DevView v, const double *t,
 void launch_inventory(uvic_b200_ctx *c, const double *t, double *out_dev) {
   DevView &v = c->v;
   long long nline = (long long)v.km * v.nt * (v.jhi - v.jlo + 1);
-  k_tbar<<<cdiv(nline * 32, 256), 256, 0, c->stream>>>(v, t, c->tbar);
-  k_inventory<<<v.nt, 256, 0, c->stream>>>(v, c->tbar, out_dev);
-  c->launches += 2;
+  KLAUNCH("k_tbar", k_tbar, cdiv(nline * 32, 256), 256, v, t, c->tbar);
+  KLAUNCH("k_inventory", k_inventory, v.nt, 256, v, c->tbar, out_dev);
 }
 void launch_tbar(uvic_b200_ctx *c) {
   DevView &v = c->v;
   long long nline = (long long)v.km * v.nt * (v.jhi - v.jlo + 1);
-  k_tbar<<<cdiv(nline * 32, 256), 256, 0, c->stream>>>(v, v.t_0, c->tbar);
-  c->launches += 1;
+  KLAUNCH("k_tbar", k_tbar, cdiv(nline * 32, 256), 256, v, v.t_0, c->tbar);
 }
 void launch_sumbk(uvic_b200_ctx *c) {
   DevView &v = c->v;
-  k_sumbk<<<v.km * v.nt, 256, 0, c->stream>>>(v, v.t_0, c->sumbk);
-  c->launches += 1;
+  KLAUNCH("k_sumbk", k_sumbk, v.km * v.nt, 256, v, v.t_0, c->sumbk);
 }

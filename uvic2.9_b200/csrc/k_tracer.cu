@@ -463,18 +463,15 @@ void launch_tracer(uvic_b200_ctx *c, const uvic_b200_stepinfo *si) {
     int ng = min(v.ngroup, v.nt - nbase);
     if (v.fct) {
       dim3 gr(cdiv(ncell_r, 256), ng);
-      k_fct_tlo<<<gr, 256, 0, c->stream>>>(v, nbase, jf_r, nrow_r);
-      k_fct_rfac<<<gr, 256, 0, c->stream>>>(v, nbase, jf_r, nrow_r);
-      c->launches += 2;
+      KLAUNCH("k_fct_tlo", k_fct_tlo, gr, 256, v, nbase, jf_r, nrow_r);
+      KLAUNCH("k_fct_rfac", k_fct_rfac, gr, 256, v, nbase, jf_r, nrow_r);
     }
     dim3 gc(cdiv(ncell_c, 256), ng);
-    k_update<<<gc, 256, 0, c->stream>>>(v, nbase, v.jlo, nrow_c);
+    KLAUNCH("k_update", k_update, gc, 256, v, nbase, v.jlo, nrow_c);
     dim3 gi(cdiv(ncol, 128), ng);
-    k_invtri<<<gi, 128, 0, c->stream>>>(v, nbase);
-    c->launches += 2;
+    KLAUNCH("k_invtri", k_invtri, gi, 128, v, nbase);
   }
   if (c->par.fullconvect) {
-    k_convect<<<cdiv(ncol, 128), 128, 0, c->stream>>>(v);
-    c->launches += 1;
+    KLAUNCH("k_convect", k_convect, cdiv(ncol, 128), 128, v);
   }
 }

@@ -74,6 +74,5 @@ __global__ void __launch_bounds__(128) k_vmix_column(const DevView v) {
 void launch_vmixc(uvic_b200_ctx *c) {
   DevView &v = c->v;
   long long ncol = (long long)(v.imt - 2) * (v.jhi - v.jlo + 1);
-  k_vmix_column<<<cdiv(ncol, 128), 128, 0, c->stream>>>(v);
-  c->launches += 1;
+  KLAUNCH("k_vmix_column", k_vmix_column, cdiv(ncol, 128), 128, v);
 }
