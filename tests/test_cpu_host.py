@@ -1,0 +1,137 @@
+"""CPU tests of the host-side logic: C-ABI library exports, time stepping, slab partition,
+synthetic inputs, MOBI parameter block, and the 2-rank halo exchange over gloo."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_pkg
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    return load_pkg()
+
+
+def test_abi_library_exports_every_declared_symbol(pkg):
+    hdr = open(os.path.join(ROOT, "include", "uvic_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(uvic_b200_[a-z_0-9]+)\s*\(", hdr)))
+    assert len(declared) >= 30
+    L = ctypes.CDLL(pkg.api.LIB_PATH)       # loads without a GPU; no compute call is made
+    for s in declared:
+        assert hasattr(L, s), s
+    assert sorted(pkg.api.ABI_SYMBOLS) == declared
+    L.uvic_b200_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in L.uvic_b200_version()
+
+
+def test_library_is_sm100a_only():
+    lib = os.path.join(ROOT, "uvic2.9_b200", "libuvic_b200.so")
+    out = subprocess.run(["cuobjdump", "-lelf", lib], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and "sm_90" not in out
+
+
+def test_create_fails_loudly_without_gpu(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    case = pkg.synthetic.make_case(imt=14, jmt=12, km=5, nt=2)
+    with pytest.raises(pkg.UvicError, match="no CUDA device"):
+        pkg.TracerContext(case)
+
+
+def test_leapfrog_switch_matches_switch_F(pkg):
+    # 09/common/switch.F:217-224 with nmix=16: mixing step when mod(itt,16) == 1
+    f = pkg.timestep.is_leapfrog
+    assert [f(i, 16) for i in (1, 2, 16, 17, 18, 33)] == [False, True, True, False, True, False]
+    assert all(f(i, 0) for i in range(1, 40)) and all(f(i, 1) for i in range(1, 40))
+
+
+def test_partition_and_halo_plan(pkg):
+    parts = pkg.slab.partition_rows(102, 8)
+    assert parts[0][0] == 2 and parts[-1][1] == 101
+    assert all(b[0] == a[1] + 1 for a, b in zip(parts, parts[1:]))
+    assert sum(hi - lo + 1 for lo, hi in parts) == 100
+    with pytest.raises(ValueError):
+        pkg.slab.partition_rows(10, 8)
+    p0, p1 = pkg.slab.halo_plan(102, 2, 0), pkg.slab.halo_plan(102, 2, 1)
+    assert p0["send_dn"] is None and p1["send_up"] is None
+    # rows sent up by rank 0 are the rows rank 1 receives from below
+    g = lambda p, s: [p["jbase"] + q for q in range(s.start, s.stop)]
+    assert g(p0, p0["send_up"]) == g(p1, p1["recv_dn"]) == [50, 51]
+    assert g(p1, p1["send_dn"]) == g(p0, p0["recv_up"]) == [52, 53]
+
+
+def test_synthetic_case_is_consistent(pkg):
+    c = pkg.synthetic.make_case(imt=34, jmt=30, km=8, nt=37, seed=5)
+    a = c.arrays
+    kmt = a["kmt"]
+    assert (kmt[0] == 0).all() and (kmt[-1] == 0).all()
+    assert (kmt[:, 0] == kmt[:, -2]).all() and (kmt[:, -1] == kmt[:, 1]).all()
+    assert set(np.unique(kmt)) <= {0, *range(2, c.km + 1)}
+    t = a["t"]
+    assert np.array_equal(t[..., 0], t[..., -2]) and np.array_equal(t[..., -1], t[..., 1])
+    assert (t[:2][:, :, a["tmask"] == 0] == 0).all()
+    # adv_vbt from continuity closes at the bottom of every column (to round-off)
+    jj, ii = np.nonzero(kmt > 0)
+    assert np.abs(a["adv_vbt"][jj, kmt[jj, ii], ii]).max() <= 1e-12 * np.abs(a["adv_vbt"]).max()
+    # MOBI maps: every state variable has a tracer and a source slot; T,S have no source
+    assert c.has_mobi and c.nsrc == 35
+    assert a["itrc"][0] == 0 and a["itrc"][1] == 0 and sorted(a["itrc"][2:]) == list(range(1, 36))
+    # same seed -> same bytes
+    c2 = pkg.synthetic.make_case(imt=34, jmt=30, km=8, nt=37, seed=5)
+    assert np.array_equal(c2["t"], t) and np.array_equal(c2["kmt"], kmt)
+
+
+def test_mobi_parameter_block(pkg):
+    mp = pkg.mobi_params
+    c = pkg.synthetic.make_case(imt=14, jmt=12, km=5, nt=37)
+    p = dict(zip(mp.PAR_ORDER, c["mobi_par"]))
+    # unit conversions of mobi_init (09/mom/mobi.F:191-245) on the run/control.in values
+    assert p["redctn"] == 7 * 1.e-3 and p["redntp"] == 16.0 and p["diazptn"] == 1. / 32.
+    assert p["abio_P"] == 0.4 / 86400.0 and p["kw"] == 0.04 * 1.e-2 and p["tap"] == 2. * 0.43
+    assert p["dtnpzd"] == 27000.0
+    # grazing preferences renormalised by the reference's (quirky) sum = 0.80
+    assert abs(p["zprefP"] - 0.29 / 0.8) < 1e-15 and abs(p["zprefDiat"] - 0.24 / 0.8) < 1e-15
+    assert len(mp.MOBI_STATE) == 32 and len(mp.SOURCE_ORDER) == 35 and c["mobi_par"].size == mp.N_PAR
+
+
+_GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import numpy as np, torch, torch.distributed as dist
+from conftest import load_pkg
+pkg = load_pkg()
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+jmt, nt, km, imt = 26, 3, 4, 10
+glob = np.arange(nt * jmt * km * imt, dtype=np.float64).reshape(nt, jmt, km, imt)
+plan = pkg.slab.halo_plan(jmt, world, rank)
+jbase, jl = pkg.api.slab_rows(jmt, plan["jlo"], plan["jhi"])
+loc = torch.from_numpy(glob[:, jbase - 1: jbase - 1 + jl].copy())
+# poison the halos, then exchange
+for key in ("recv_up", "recv_dn"):
+    if plan[key] is not None:
+        loc[:, plan[key]] = -1.0
+pkg.slab.HaloExchanger(jmt, rank, world).exchange(loc)
+ok = np.array_equal(loc.numpy(), glob[:, jbase - 1: jbase - 1 + jl])
+inv = pkg.slab.combine_inventories(np.array([float(rank + 1), 2.0 * (rank + 1)]))
+ok = ok and np.array_equal(inv, np.array([3.0, 6.0]))
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if ok else 3)
+'''
+
+
+def test_halo_exchange_two_ranks_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29731", str(script), ROOT], capture_output=True, text=True, env=env,
+                       timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -1,0 +1,239 @@
+"""CPU tests of the oracle (the parity pin): the reference ships no golden vectors, so the
+oracle is checked against the invariants the reference's own diagnostics define
+ and against independent numpy restatements of the simplest routines."""
+import numpy as np
+import pytest
+
+from conftest import load_pkg
+from helpers import make_oracle, oracle_set_step, relerr
+from oracle_ffi import Oracle
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    return load_pkg()
+
+
+@pytest.fixture(scope="module")
+def small(pkg):
+    names = ["temp", "salt", "passive0", "passive1"]
+    return pkg.synthetic.make_case(imt=34, jmt=30, km=8, nt=4, names=names, seed=21)
+
+
+def _volume(case):
+    a = case.arrays
+    dv = (a["dzt"][None, :, None] * a["dxt"][None, None, :] * (a["cst"] * a["dyt"])[:, None, None]) * a["tmask"]
+    dv[..., 0] = 0
+    dv[..., -1] = 0
+    dv[0] = 0
+    dv[-1] = 0
+    return dv
+
+
+def test_mask_rule_bit_exact(pkg, small):
+    """09/mom/loadmw.F:60-77: tmask = 1 where kmt >= k."""
+    o = make_oracle(small)
+    o.arr("tmask")[:] = -1
+    o.call("ora_make_masks")
+    k = np.arange(1, small.km + 1)[None, :, None]
+    ref = (small["kmt"][:, None, :] >= k).astype(np.float64)
+    assert np.array_equal(o.arr("tmask", ref.shape), ref)
+    o.close()
+
+
+def test_inventory_conserved_by_full_step(pkg, small):
+    """tbar-style inventory (09/mom/tracer.F:1516-1539) is conserved by advection (FCT),
+    isopycnal + vertical diffusion, the implicit solve and convection with zero b.c. fluxes."""
+    o = make_oracle(small)
+    oracle_set_step(o, small, True)
+    o.call("ora_step")
+    t = o.t()
+    dv = _volume(small)
+    for n in range(small.nt):
+        a, b = (t[0, n] * dv).sum(), (t[2, n] * dv).sum()
+        assert abs(b - a) <= 2e-14 * abs(a), (n, a, b)
+    o.close()
+
+
+def test_uniform_tracer_stays_uniform(pkg, small):
+    """A spatially uniform passive tracer is (almost) untouched by FCT + GM + Redi + invtri: the
+    resolved velocity is non-divergent by construction of adv_vbt.  "Almost": the reference's
+    isoflux differences the tracer across the sea floor (land value 0, 09/mom/isopyc.F:960-971)
+    with a heavily tapered coefficient, and zeroes adv_vbtiso at kmt (:1521-1525); both leave an
+    O(1e-8) relative signal in bottom cells, so the bound here is 1e-6, and exactly zero change
+    is required away from the bottom."""
+    case = pkg.synthetic.make_case(imt=34, jmt=30, km=8, nt=4, names=["temp", "salt", "passive0", "passive1"], seed=21)
+    case["t"][:, 2] = 3.25 * case["tmask"]
+    o = make_oracle(case, do_convect=0)
+    oracle_set_step(o, case, True)
+    o.call("ora_step")
+    t = o.t()
+    ocean = case["tmask"][1:-1, :, 1:-1] > 0
+    dev = np.abs(t[2, 2][1:-1, :, 1:-1] - 3.25)
+    assert dev[ocean].max() <= 3.25 * 1e-6
+    # cells whose whole 3x3 horizontal neighbourhood is at least two levels above the sea floor
+    kmt = case["kmt"]
+    kmin = np.minimum.reduce([np.roll(np.roll(kmt, a, 0), b, 1) for a in (-1, 0, 1) for b in (-1, 0, 1)])
+    k = np.arange(1, case.km + 1)[None, :, None]
+    interior = (k <= (kmin[:, None, :] - 2))[1:-1, :, 1:-1]
+    assert interior.sum() > 50 and dev[interior].max() <= 3.25 * 1e-13
+    o.close()
+
+
+def test_invtri_against_dense_solve(pkg, small):
+    """source/mom/invtri.F against numpy.linalg.solve of the same tridiagonal system."""
+    o = make_oracle(small)
+    oracle_set_step(o, small, True)
+    o.call("ora_isopyc")
+    o.call("ora_vmixc")
+    a = small.arrays
+    km, imt, jmt = small.km, small.imt, small.jmt
+    dcb = o.arr("diff_cbt", (jmt, km, imt)).copy()
+    rng = np.random.default_rng(4)
+    z0 = rng.standard_normal((jmt, km, imt)) * a["tmask"]
+    stf = rng.standard_normal((jmt, imt)) * 1e-3
+    btf = rng.standard_normal((jmt, imt)) * 1e-3
+    t = o.t()
+    t[2, 0] = z0
+    o.arr("stf", (small.nt, jmt, imt))[0] = stf
+    o.arr("btf", (small.nt, jmt, imt))[0] = btf
+    import ctypes
+    L = o.L
+    L.ora_invtri.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 5
+    tdt = np.full(km, small.scalars["c2dtts"]) * a["dtxcel"]
+    zp = t[2, 0]
+    L.ora_invtri(o.h, zp.ctypes.data, o.arr("stf").ctypes.data, o.arr("btf").ctypes.data, o.arr("diff_cbt").ctypes.data,
+                 tdt.ctypes.data)
+    aidif = small.scalars["aidif"]
+    checked = 0
+    for j in range(1, jmt - 1):
+        for i in range(1, imt - 1, 3):
+            kb = int(a["kmt"][j, i])
+            if kb < 2:
+                continue
+            A = np.zeros((kb, kb))
+            f = z0[j, :kb, i].copy()
+            for k in range(kb):
+                lo = -dcb[j, k - 1, i] * a["dztur"][k] * tdt[k] * aidif if k > 0 else 0.0
+                up = -dcb[j, k, i] * a["dztlr"][k] * tdt[k] * aidif if k < kb - 1 else 0.0
+                A[k, k] = 1.0 - lo - up
+                if k > 0:
+                    A[k, k - 1] = lo
+                if k < kb - 1:
+                    A[k, k + 1] = up
+            f[0] += stf[j, i] * tdt[0] * a["dztr"][0] * aidif
+            f[kb - 1] -= btf[j, i] * tdt[kb - 1] * a["dztr"][kb - 1] * aidif
+            ref = np.linalg.solve(A, f)
+            got = zp[j, :kb, i]
+            assert np.abs(got - ref).max() <= 1e-10 * max(1.0, np.abs(ref).max())
+            checked += 1
+    assert checked > 20
+    o.close()
+
+
+def test_zero_slope_reduces_redi_to_laplacian(pkg):
+    """With horizontally uniform T,S the isopycnals are flat: the off-diagonal Redi terms
+    vanish, K33 = 0 and K11 = K22 = Ai0-weighted column means."""
+    case = pkg.synthetic.make_case(imt=26, jmt=22, km=6, nt=3, names=["temp", "salt", "passive0"], seed=2)
+    prof = np.linspace(20.0, 2.0, case.km)[None, :, None]
+    case["t"][:, 0] = prof * case["tmask"]
+    case["t"][:, 1] = -3.0e-4 * case["tmask"]
+    # flat bottom so the uniform state has no masked gradients
+    case["kmt"][1:-1, :] = case.km
+    case.arrays["tmask"] = (case["kmt"][:, None, :] >= np.arange(1, case.km + 1)[None, :, None]).astype(np.float64)
+    case["t"][:, 0] = prof * case["tmask"]
+    case["t"][:, 1] = -3.0e-4 * case["tmask"]
+    o = make_oracle(case)
+    oracle_set_step(o, case, True)
+    o.call("ora_isopyc")
+    s3 = (case.jmt, case.km, case.imt)
+    assert np.abs(o.arr("K33", s3)).max() == 0.0
+    assert np.abs(o.arr("adv_vetiso", s3)).max() == 0.0
+    assert np.abs(o.arr("adv_vntiso", s3)).max() == 0.0
+    o.close()
+
+
+def test_fct_monotone_on_step_profile(pkg):
+    """FCT creates no new extrema: a passive tracer bounded by [0,1] stays within [0,1]
+    after advection alone (diffusion switched off through ahisop = 0, kappa_h = 0)."""
+    case = pkg.synthetic.make_case(imt=42, jmt=30, km=6, nt=3, names=["temp", "salt", "passive0"], seed=9)
+    x = np.zeros_like(case["t"][0, 2])
+    x[:, :, 10:22] = 1.0
+    x *= case["tmask"]
+    x[..., 0] = x[..., -2]
+    x[..., -1] = x[..., 1]
+    case["t"][0, 2] = x
+    case["t"][1, 2] = x
+    case.scalars.update(ahisop=0.0, athkdf=0.0, kappa_h=0.0)
+    for nm in ("edrm2", "edrs2", "edrk1", "edro1", "addisop"):
+        case[nm][:] = 0.0
+    o = make_oracle(case, do_convect=0)
+    oracle_set_step(o, case, False)    # forward step: low-order solution is monotone
+    o.call("ora_step")
+    y = o.t()[2, 2][1:-1, :, 1:-1]
+    assert y.min() >= -1e-12 and y.max() <= 1.0 + 1e-12
+    o.close()
+
+
+def test_convct2_removes_instability_and_conserves(pkg, small):
+    a = small.arrays
+    o = make_oracle(small)
+    oracle_set_step(o, small, True)
+    t = o.t()
+    # make the top of every column heavy: cold and salty on top
+    t[2] = t[0]
+    t[2, 0, :, 0, :] -= 15.0 * a["tmask"][:, 0, :]
+    before = t[2].copy()
+    o.L.ora_convct2.argtypes = [__import__("ctypes").c_void_p] * 2
+    o.L.ora_convct2(o.h, t[2].ctypes.data)
+    after = t[2]
+    w = a["dztxcl"][None, :, None] * a["tmask"]
+    for n in range(small.nt):
+        col0 = (before[n] * w).sum(axis=1)[1:-1, 1:-1]
+        col1 = (after[n] * w).sum(axis=1)[1:-1, 1:-1]
+        assert np.abs(col1 - col0).max() <= 1e-12 * max(1.0, np.abs(col0).max())
+    assert np.abs(after - before).max() > 0          # something was mixed
+    o.close()
+
+
+def test_mobi_column_closure(pkg):
+    """sg_bathy(kmt)=1 closes the sinking fluxes (09/common/topog.F:276-282): with the dust,
+    hydrothermal and sediment iron sources removed, MOBI conserves column phosphorus
+    (PO4 + DOP + P in phytoplankton, detritus, zooplankton, diatoms, diazotrophs)."""
+    case = pkg.synthetic.make_case(imt=22, jmt=18, km=8, nt=37, seed=3)
+    o = make_oracle(case, do_mobi=1)
+    oracle_set_step(o, case, True)
+    o.call("ora_mobi_columns")
+    from uvic29_b200 import mobi_params as mp
+    src = o.arr("src", (case.nsrc, case.jmt, case.km, case.imt))
+    assert np.isfinite(src).all()
+    s = {nm: src[q] for q, nm in enumerate(mp.SOURCE_ORDER)}
+    par = dict(zip(mp.PAR_ORDER, case["mobi_par"]))
+    redptn, diazptn = par["redptn"], par["diazptn"]
+    ptot = (s["po4"] + s["dop"] + s["phyt_phos"] + s["detr_phos"] + redptn * (s["zoop"] + s["diat"]) + diazptn * s["diaz"])
+    w = case["dzt"][None, :, None] * case["tmask"]
+    col = (ptot * w).sum(axis=1)[1:-1, 1:-1]
+    scale = (np.abs(s["po4"]) * w).sum(axis=1)[1:-1, 1:-1].max()
+    assert np.abs(col).max() <= 1e-9 * scale, (np.abs(col).max(), scale)
+    # silicon: o_sil + o_opl is conserved (updates/README.md)
+    sicol = ((s["sil"] + s["opl"]) * w).sum(axis=1)[1:-1, 1:-1]
+    sscale = (np.abs(s["opl"]) * w).sum(axis=1)[1:-1, 1:-1].max()
+    assert np.abs(sicol).max() <= 1e-9 * sscale
+    o.close()
+
+
+def test_co2calc_known_state(pkg):
+    """co2calc_SWS at a standard surface state: pH ~ 8.1, Omega_calcite ~ 4-6 (OCMIP-2 ballpark)."""
+    import ctypes as C
+    from oracle_ffi import lib
+    L = lib()
+    L.ora_co2calc_SWS.argtypes = [C.c_double] * 7 + [C.POINTER(C.c_double)] * 8
+    out = [C.c_double() for _ in range(8)]
+    L.ora_co2calc_SWS(20.0, 35.0, 2.05, 2.35, 280.0, 1.0, 5.0, *[C.byref(x) for x in out])
+    ph, co2star, dco2, pco2, dpco2, co3, om_c, om_a = [x.value for x in out]
+    assert 7.9 < ph < 8.4
+    assert 3.0 < om_c < 8.0 and om_a < om_c
+    assert 150.0 < pco2 < 450.0
+    # deeper water is less saturated
+    L.ora_co2calc_SWS(2.0, 34.7, 2.3, 2.4, 280.0, 1.0, 4000.0, *[C.byref(x) for x in out])
+    assert out[6].value < om_c
