@@ -83,7 +83,8 @@ def kernel_bytes_per_launch(name, case, ctx, ngroup_launch):
         "k_fct_rfac": cells_r * (72 * g + 24),         # t_lo, t(tau-1), t(tau) in; 6 ratios out; velocities
         "k_update": cells * (80 * g + 176),            # 6 ratios, t(tau-1), t(tau), src in; t(tau+1) out; 22 shared fields
         "k_invtri": cells * (16 * g + 24),             # t(tau+1) in/out; a, e, bet
-        "k_convect": cells * (16 * case.nt),           # worst case: every tracer read + written
+        "k_convect_ts": cells * 32,                    # T,S read + written (worst case)
+        "k_convect_tr": cells * 16 * (case.nt - 2),    # worst case: every other tracer read + written
         "k_mobi_column": ocean * 8 * (37 + 2 + 35),    # 37 tracers + CO2*, Omega in; 35 sources out
         "k_mobi_co2": ocean * 8 * (4 + 2),
         "k_elements": cells * 8 * (2 + 8),

@@ -78,6 +78,7 @@ int uvic_b200_create(const uvic_b200_dims *d, const uvic_b200_grid *g, const uvi
   ctx->red_partial = ctx->red_out = nullptr;
   ctx->pin_buf = nullptr; ctx->pin_bytes = 0;
   ctx->prof_on = false;
+  ctx->stream2 = nullptr; ctx->fork_event = nullptr; ctx->mobi_event = nullptr; ctx->mobi_inflight = false;
   ctx->mobi_dtnpzd = 0.0;
   DevView &v = ctx->v;
   memset(&v, 0, sizeof v);
@@ -201,11 +202,22 @@ int uvic_b200_create(const uvic_b200_dims *d, const uvic_b200_grid *g, const uvi
     DALLOC(fe_atmdep, v.n2 * 12, st->fe_atmdep);
     DALLOC(dnswr, v.n2, nullptr); DALLOC(aice, v.n2, nullptr); DALLOC(hice, v.n2, nullptr); DALLOC(hsno, v.n2, nullptr);
     DALLOC(co2_star, v.n3, nullptr); DALLOC(co2_omega, v.n3, nullptr);
+    CK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->mobi_event, cudaEventDisableTiming));
   }
   {
-    // FCT scratch: t_lo + six ratios per tracer of a group; keep the group within ~2 GiB
+    int *ip = nullptr;
+    if (dev_alloc(ctx, "conv_n", &ip, (size_t)v.n2, (const int *)nullptr)) return 1;
+    v.conv_n = ip;
+    if (dev_alloc(ctx, "conv_kt", &ip, (size_t)v.n2 * (km / 2 + 1), (const int *)nullptr)) return 1;
+    v.conv_kt = ip;
+    DALLOC(conv_zsm, (size_t)v.n2 * (km / 2 + 1), nullptr);
+  }
+  {
+    // FCT scratch: t_lo + six ratios per tracer of a group; keep the group within ~12 GiB
     size_t per = (size_t)v.n3 * 7 * sizeof(double);
-    size_t cap = (size_t)2 << 30;
+    size_t cap = (size_t)12 << 30;
     v.ngroup = (int)std::max<size_t>(1, std::min<size_t>((size_t)nt, cap / per));
     DALLOC(t_lo, (size_t)v.n3 * v.ngroup, nullptr);
     DALLOC(Rfac, (size_t)v.n3 * 6 * v.ngroup, nullptr);
@@ -230,6 +242,9 @@ int uvic_b200_destroy(uvic_b200_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   for (void *p : ctx->owned) cudaFree(p);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+  if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
+  if (ctx->mobi_event) cudaEventDestroy(ctx->mobi_event);
   delete ctx;
   return 0;
 }
@@ -309,6 +324,19 @@ int uvic_b200_rotate(uvic_b200_ctx *ctx) {
   return 0;
 }
 
+// launch MOBI on the side stream; the main stream waits for it right before k_update
+static void fork_mobi(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
+  if (!ctx->par.mobi || ctx->mobi_inflight) return;
+  cudaEventRecord(ctx->fork_event, ctx->stream);
+  cudaStreamWaitEvent(ctx->stream2, ctx->fork_event, 0);
+  cudaStream_t main_stream = ctx->stream;
+  ctx->stream = ctx->stream2;
+  launch_mobi(ctx, si);
+  ctx->stream = main_stream;
+  cudaEventRecord(ctx->mobi_event, ctx->stream2);
+  ctx->mobi_inflight = true;
+}
+
 static void set_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
   ctx->v.dtts = si->dtts;
   ctx->v.c2dtts = si->leapfrog ? 2.0 * si->dtts : si->dtts;  // source/mom/mom.F:111-146
@@ -328,8 +356,9 @@ int uvic_b200_vmixc(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
 }
 int uvic_b200_tracer(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
   set_step(ctx, si);
-  if (ctx->par.mobi) launch_mobi(ctx, si);
+  fork_mobi(ctx, si);
   launch_tracer(ctx, si);
+  ctx->mobi_inflight = false;
   CK(cudaGetLastError());
   if (si->diag) {
     launch_tbar(ctx);
@@ -340,6 +369,7 @@ int uvic_b200_tracer(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
 }
 int uvic_b200_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
   set_step(ctx, si);
+  fork_mobi(ctx, si);
   if (uvic_b200_isopyc(ctx)) return 1;
   if (uvic_b200_vmixc(ctx, si)) return 1;
   return uvic_b200_tracer(ctx, si);

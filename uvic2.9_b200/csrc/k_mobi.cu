@@ -210,17 +210,19 @@ struct SrcIO {
 #define CL15(x) fmax(fmin((x), 2. * RN15STD / (1 + RN15STD)), RN15STD / (1 + RN15STD) / 2.)
 #define CL13(x) fmax(fmin((x), 2. * RC13STD / (1 + RC13STD)), 0.5 * RC13STD / (1 + RC13STD))
 
-__device__ __noinline__ void mobi_src(const MobiPar *__restrict__ P, int nbio, double dtbio, double *b, double *clip, SrcIO &io) {
+__device__ __forceinline__ void mobi_src(const MobiPar *__restrict__ P, int nbio, double dtbio, double (&b)[MOBI_NVAR], double (&clip)[MOBI_NVAR], SrcIO &io) {
   const double gamma1 = P->gamma1, redptn = P->redptn, redctn = P->redctn, redntp = P->redntp, diazntp = P->diazntp;
   const double diazptn = P->diazptn, dfr = P->dfr, pfr = P->pfr, dfrt = P->dfrt, geZ = P->geZ, rfeton = P->rfeton;
   const double bct = io.bct, dzt = io.dzt, gl = io.gl;
   // ratios from the raw inputs (:1781-1784)
   double ptn_P = b[V_PHYT_PHOS] / b[V_PHYT];
   double ptn_detr = b[V_DETR_PHOS] / b[V_DETR];
-  // flags from the raw inputs (:1814-1890); bit m of fl = flag of state m is 1
-  double fl[MOBI_NVAR];
+  // flags from the raw inputs (:1814-1890), kept as a bit mask: bit m set <=> flag of state m is 1
+  unsigned flm = 0u;
 #pragma unroll
-  for (int m = 0; m < MOBI_NVAR; m++) fl[m] = tflag(b[m]);
+  for (int m = 0; m < MOBI_NVAR; m++)
+    if (b[m] - TRCMIN >= 0.0) flm |= (1u << m);
+#define fl(m) (((flm >> (m)) & 1u) ? 1.0 : 0.0)
   const double sf_P_phosflag = 0.5 + fsign(0.5, ptn_P - gamma1 * redptn);
   const double sf_detr_phosflag = 0.5 + fsign(0.5, ptn_detr - gamma1 * redptn);
   // limit tracers to positive values; the clipped inputs are what the caller sees afterwards (:1893-1926)
@@ -353,37 +355,37 @@ __device__ __noinline__ void mobi_src(const MobiPar *__restrict__ P, int nbio, d
     double ligand = fmax(aou8 / 66. + pow(biodon, 0.8) / 4.8, 0.5) / 1000.;
     double fepa = (1.0 + P->kfeleq * (ligand - biodfe)) * o2flag;
     double feprime = ((-fepa + sqrt(fepa * fepa + 4.0 * P->kfeleq * biodfe)) / (2.0 * P->kfeleq)) * o2flag;
-    double feorgads = (P->kfeorg * (pow(((biodetr * fl[V_DETR]) * P->mc * redctn), 0.58)) * feprime) * o2flag;
+    double feorgads = (P->kfeorg * (pow(((biodetr * fl(V_DETR)) * P->mc * redctn), 0.58)) * feprime) * o2flag;
     double fecol = P->kfecol * (feprime * feprime) * o2flag;
     double expofe = io.wwd * biodetrfe;
     // flags switch outgoing fluxes off when a pool is exhausted (:2284-2334)
-    graz = graz * fl[V_PHYT] * fl[V_PHYT_PHOS] * sf_P_phosflag * fl[V_PHYTN15];
-    graz_Z = graz_Z * fl[V_ZOOP] * fl[V_ZOOPN15];
-    graz_Det = graz_Det * fl[V_DETR] * fl[V_DETR_PHOS] * sf_detr_phosflag * fl[V_DETRN15];
-    morp = morp * fl[V_PHYT] * fl[V_PHYT_PHOS] * fl[V_PHYTN15];
-    morpt = morpt * fl[V_PHYT] * fl[V_PHYT_PHOS] * fl[V_PHYTN15];
-    morz = morz * fl[V_ZOOP] * fl[V_ZOOPN15];
-    remi = remi * fl[V_DETR] * fl[V_DETR_PHOS] * fl[V_DETRN15];
-    expo = expo * fl[V_DETR] * fl[V_DETRN15];
-    expo_phos = expo_phos * fl[V_DETR_PHOS];
-    recy_dop = recy_dop * fl[V_DOP];
-    npp = npp * fl[V_NO3] * (dopupt_flag * fl[V_DOP] + (1. - dopupt_flag) * fl[V_PO4]) * fl[V_DIN15];
-    npp_Diat = npp_Diat * fl[V_NO3] * (dopupt_Diat_flag * fl[V_DOP] + (1. - dopupt_Diat_flag) * fl[V_PO4]) * fl[V_DIN15];
-    npp_D = npp_D * (dopupt_D_flag * fl[V_DOP] + (1. - dopupt_D_flag) * fl[V_PO4]) * fl[V_DIN15];
-    graz_D = graz_D * fl[V_DIAZ] * fl[V_DIAZN15];
-    morpt_D = morpt_D * fl[V_DIAZ] * fl[V_DIAZN15];
-    morp_D = morp_D * fl[V_DIAZ] * fl[V_DIAZN15];
-    no3upt_D = no3upt_D * fl[V_NO3] * fl[V_DIN15];
-    recy_don = recy_don * fl[V_DON] * fl[V_DON15];
-    dissl = dissl * fl[V_CACO3];
-    expocaco3 = expocaco3 * fl[V_CACO3];
-    graz_Diat = graz_Diat * fl[V_DIAT];
-    morp_Diat = morp_Diat * fl[V_DIAT];
-    morpt_Diat = morpt_Diat * fl[V_DIAT];
-    remife = remife * fl[V_DETRFE];
-    feorgads = feorgads * fl[V_DFE];
-    expofe = expofe * fl[V_DETRFE];
-    fecol = fecol * fl[V_DFE];
+    graz = graz * fl(V_PHYT) * fl(V_PHYT_PHOS) * sf_P_phosflag * fl(V_PHYTN15);
+    graz_Z = graz_Z * fl(V_ZOOP) * fl(V_ZOOPN15);
+    graz_Det = graz_Det * fl(V_DETR) * fl(V_DETR_PHOS) * sf_detr_phosflag * fl(V_DETRN15);
+    morp = morp * fl(V_PHYT) * fl(V_PHYT_PHOS) * fl(V_PHYTN15);
+    morpt = morpt * fl(V_PHYT) * fl(V_PHYT_PHOS) * fl(V_PHYTN15);
+    morz = morz * fl(V_ZOOP) * fl(V_ZOOPN15);
+    remi = remi * fl(V_DETR) * fl(V_DETR_PHOS) * fl(V_DETRN15);
+    expo = expo * fl(V_DETR) * fl(V_DETRN15);
+    expo_phos = expo_phos * fl(V_DETR_PHOS);
+    recy_dop = recy_dop * fl(V_DOP);
+    npp = npp * fl(V_NO3) * (dopupt_flag * fl(V_DOP) + (1. - dopupt_flag) * fl(V_PO4)) * fl(V_DIN15);
+    npp_Diat = npp_Diat * fl(V_NO3) * (dopupt_Diat_flag * fl(V_DOP) + (1. - dopupt_Diat_flag) * fl(V_PO4)) * fl(V_DIN15);
+    npp_D = npp_D * (dopupt_D_flag * fl(V_DOP) + (1. - dopupt_D_flag) * fl(V_PO4)) * fl(V_DIN15);
+    graz_D = graz_D * fl(V_DIAZ) * fl(V_DIAZN15);
+    morpt_D = morpt_D * fl(V_DIAZ) * fl(V_DIAZN15);
+    morp_D = morp_D * fl(V_DIAZ) * fl(V_DIAZN15);
+    no3upt_D = no3upt_D * fl(V_NO3) * fl(V_DIN15);
+    recy_don = recy_don * fl(V_DON) * fl(V_DON15);
+    dissl = dissl * fl(V_CACO3);
+    expocaco3 = expocaco3 * fl(V_CACO3);
+    graz_Diat = graz_Diat * fl(V_DIAT);
+    morp_Diat = morp_Diat * fl(V_DIAT);
+    morpt_Diat = morpt_Diat * fl(V_DIAT);
+    remife = remife * fl(V_DETRFE);
+    feorgads = feorgads * fl(V_DFE);
+    expofe = expofe * fl(V_DETRFE);
+    fecol = fecol * fl(V_DFE);
     // digestion, excretion, sloppy feeding (:2335-2440)
     double dig_P = gamma1 * graz, dig_Z = gamma1 * graz_Z, dig_Det = gamma1 * graz_Det, dig_Diat = gamma1 * graz_Diat;
     double dig = dig_Z + dig_P + dig_Det + dig_Diat;
@@ -435,9 +437,9 @@ __device__ __noinline__ void mobi_src(const MobiPar *__restrict__ P, int nbio, d
     // CaCO3 and opal production (:2532-2548)
     double calpro = ((sf_Z + morz) * io.capr + (sf_P + morp) * io.capr) * redctn * 1.e3;
     double sipr0 = (-0.46204044117647 * tanh(6.9 * biodfe * 1.e3 + -3.673092) + 1.60266544117647);
-    double oplpro = (morp_Diat + sf_Diat) * sipr0 * fl[V_SIL] * (1.e-3);
-    opldis = opldis * fl[V_OPL];
-    expoopl = expoopl * fl[V_OPL];
+    double oplpro = (morp_Diat + sf_Diat) * sipr0 * fl(V_SIL) * (1.e-3);
+    opldis = opldis * fl(V_OPL);
+    expoopl = expoopl * fl(V_OPL);
     double GM15ptc = 0.0060 + 0.0069 * biopo4;
     double GM15ptn = GM15ptc * redctn * 1.e3;
     const double rnd = redntp / diazntp;
@@ -524,7 +526,7 @@ __device__ __noinline__ void mobi_src(const MobiPar *__restrict__ P, int nbio, d
     // a flag that is still 1 is re-evaluated on the updated pool; once 0 it stays 0 (:3175-3251)
 #pragma unroll
     for (int m = 0; m < MOBI_NVAR; m++)
-      if (fl[m] == 1) fl[m] = tflag(b[m]);
+      if (b[m] - TRCMIN < 0.0) flm &= ~(1u << m);
   }
   // increments relative to the clipped inputs (:3254-3311)
 #pragma unroll
@@ -532,9 +534,10 @@ __device__ __noinline__ void mobi_src(const MobiPar *__restrict__ P, int nbio, d
   io.nfix = nfixout; io.expo = expoout; io.expo_phos = expo_phosout; io.calpro = calproout; io.dissl = disslout;
   io.expocaco3 = expocaco3out; io.expoopl = expooplout; io.rn15expo = rn15expoout; io.rc13expo = rc13expoout;
   io.rcaco3c13expo = rcaco3c13expoout; io.expofe = expofeout;
+#undef fl
 }
 
-__global__ void __launch_bounds__(64) k_mobi_column(const DevView v, int mi, double declin, int nbio, double dtbio, double rdtts,
+__global__ void __launch_bounds__(32) k_mobi_column(const DevView v, int mi, double declin, int nbio, double dtbio, double rdtts,
                                                      double rnbio) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int ni = v.imt - 2, nrow = v.jhi - v.jlo + 1;
@@ -608,7 +611,7 @@ __global__ void __launch_bounds__(64) k_mobi_column(const DevView v, int mi, dou
     io.impofe = expofe * dztrk;
     io.bct = pow(P->bbio, (P->cbio * t_in));
     io.impoopl = expoopl * dztrk;
-    io.bctz = (0.5 * (tanh(o2_in - 8.) + 1)) * pow(P->bbio, (P->cbio * t_in));
+    io.bctz = (0.5 * (tanh(o2_in - 8.) + 1)) * io.bct;   // same bbio**(cbio*t) value (:830-835)
     io.nud = P->nud0 * (0.6 + 0.4 * tanh(0.22 * fmax(o2_in, 0.)));
     io.nudon = P->nudon0;
     io.nudop = P->nudop0;
@@ -744,5 +747,5 @@ void launch_mobi(uvic_b200_ctx *c, const uvic_b200_stepinfo *si) {
   long long ncell = (long long)(v.imt - 2) * v.km * (v.jhi - v.jlo + 1);
   long long ncol = (long long)(v.imt - 2) * (v.jhi - v.jlo + 1);
   KLAUNCH("k_mobi_co2", k_mobi_co2, cdiv(ncell, 128), 128, v);
-  KLAUNCH("k_mobi_column", k_mobi_column, cdiv(ncol, 64), 64, v, mi, declin, nbio, dtbio, rdtts, rnbio);
+  KLAUNCH("k_mobi_column", k_mobi_column, cdiv(ncol, 32), 32, v, mi, declin, nbio, dtbio, rdtts, rnbio);
 }

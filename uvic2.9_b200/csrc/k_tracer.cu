@@ -1,5 +1,5 @@
 // k_tracer.cu -- the per-tracer part of `call tracer` (source/mom/mom.F:389 ->
-// 09/mom/tracer.F:902-1203) on the device, all nt tracers batched per launch:
+// 09/mom/tracer.F:902-1203) on the device:
 //
 //   k_fct_tlo     low-order (upstream) fluxes and the low-order solution t_lo
 //                 09/mom/tracer_adv_flx.F:496-580
@@ -13,7 +13,16 @@
 //   k_invtri      implicit vertical diffusion, per-tracer sweeps of the Thomas solve
 //                 (source/mom/invtri.F:75-110) using the factors from k_vmix_column,
 //                 then the cyclic boundary (setbcx, tracer.F:1153-1155)
-//   k_convect     convct2 full convective adjustment (source/mom/convect.F:99-311)
+//   k_convect_ts / k_convect_tr   convct2 full convective adjustment
+//                 (source/mom/convect.F:99-311): region search on T,S per column, then
+//                 the mixing of the other tracers in parallel over (column, tracer)
+//
+// Thread mapping of the three flux kernels: one thread per cell (i fastest, so a warp
+// reads 32 consecutive i), and each thread loops over a chunk of tracers.  Everything
+// that does not depend on the tracer -- the face velocities, the 38 Redi / vertical
+// coefficients of the six faces, masks and metric factors -- is loaded once into
+// registers and reused for every tracer of the chunk; per tracer a thread reads its
+// 15-point t(tau-1) neighbourhood, 7 points of t(tau), 18 ratios and the source.
 //
 // The reference's j loop in adv_flux looks sequential (iteration j limits anti_fn(j) with
 // R+-Y(j) from the previous iteration) but is algebraically parallel; what must be kept
@@ -22,88 +31,66 @@
 // ratios are zero because tmask(row jmt)=0 -- and the cyclic wrap of R+-x (:693-694).
 #include "ctx.h"
 
-struct TrPtr {
-  const double *tm1;  // t(tau-1) of this tracer
-  const double *t0;   // t(tau)
-  double *tp1;        // t(tau+1)
+// decoded cell: 1-based i,k, global j, and 32-bit offsets inside one 3-D field
+struct Cell {
+  int i, k, j;
+  int c;        // (i,k,j) in an (imt,km,jl) field
+  int cz;       // (i,k,j) in an (imt,0:km,jl) field
+  int sk, sj;   // strides of k and j in an (imt,km,jl) field
+  int c2;       // (i,j) in an (imt,jl) field
 };
 
-__device__ __forceinline__ double tmk(const DevView &v, int i, int k, int j) { return (v.kmt[X2(i, j)] >= k) ? 1.0 : 0.0; }
-__device__ __forceinline__ int wrap_i(const DevView &v, int i) {
-  if (i < 2) return i + (v.imt - 2);
-  if (i > v.imt - 1) return i - (v.imt - 2);
-  return i;
-}
-
-// ---- low-order (upstream) fluxes, 09/mom/tracer_adv_flx.F:496-548 ----
-__device__ __forceinline__ double lowfe(const DevView &v, const double *tm1, int i, int k, int j) {
-  double totadv = v.ue[X3(i, k, j)];
-  double a = tm1[X3(i, k, j)], b = tm1[X3(i + 1, k, j)];
-  return totadv * (a + b) + fabs(totadv) * (a - b);
-}
-__device__ __forceinline__ double lowfn(const DevView &v, const double *tm1, int i, int k, int j) {
-  double totadv = v.vn[X3(i, k, j)];
-  double a = tm1[X3(i, k, j)], b = tm1[X3(i, k, j + 1)];
-  return totadv * (a + b) + fabs(totadv) * (a - b);
-}
-__device__ __forceinline__ double lowfb(const DevView &v, const double *tm1, int i, int k, int j) {
-  if (k == 0) return v.wb[X3Z(i, 0, j)] * 2.0 * tm1[X3(i, 1, j)];
-  if (k >= v.km) return 0.0;
-  double totadv = v.wb[X3Z(i, k, j)];
-  double a = tm1[X3(i, k + 1, j)], b = tm1[X3(i, k, j)];
-  return totadv * (a + b) + fabs(totadv) * (a - b);
-}
-// ---- raw antidiffusive fluxes, :582-620 ----
-__device__ __forceinline__ double antife(const DevView &v, const TrPtr &p, int i, int k, int j) {
-  return v.ue[X3(i, k, j)] * (p.t0[X3(i, k, j)] + p.t0[X3(i + 1, k, j)]) - lowfe(v, p.tm1, i, k, j);
-}
-__device__ __forceinline__ double antifn(const DevView &v, const TrPtr &p, int i, int k, int j) {
-  if (j < 2) return 0.0;  // anti_fn(i,k,1,n) = c0 (:475)
-  return v.vn[X3(i, k, j)] * (p.t0[X3(i, k, j)] + p.t0[X3(i, k, j + 1)]) - lowfn(v, p.tm1, i, k, j);
-}
-__device__ __forceinline__ double antifb(const DevView &v, const TrPtr &p, int i, int k, int j) {
-  if (k == 0) return v.wb[X3Z(i, 0, j)] * 2.0 * p.tm1[X3(i, 1, j)];
-  if (k >= v.km) return 0.0;
-  return v.wb[X3Z(i, k, j)] * (p.t0[X3(i, k, j)] + p.t0[X3(i, k + 1, j)]) - lowfb(v, p.tm1, i, k, j) * tmk(v, i, k, j);
-}
-
-__device__ __forceinline__ bool decode_cell(const DevView &v, long long idx, int jfirst, int nrow, int &i, int &k, int &j) {
-  int ni = v.imt - 2;
-  long long tot = (long long)ni * v.km * nrow;
-  if (idx >= tot) return false;
-  i = (int)(idx % ni) + 2;
-  long long r = idx / ni;
-  k = (int)(r % v.km) + 1;
-  j = (int)(r / v.km) + jfirst;
+__device__ __forceinline__ bool decode_cell(const DevView &v, long long idx, int jfirst, int nrow, Cell &q) {
+  const int ni = v.imt - 2;
+  if (idx >= (long long)ni * v.km * nrow) return false;
+  unsigned u = (unsigned)idx;
+  unsigned r = u / (unsigned)ni;
+  q.i = (int)(u - r * (unsigned)ni) + 2;
+  unsigned jj = r / (unsigned)v.km;
+  q.k = (int)(r - jj * (unsigned)v.km) + 1;
+  q.j = (int)jj + jfirst;
+  const int jloc = q.j - v.jbase;
+  q.sk = v.imt;
+  q.sj = v.imt * v.km;
+  q.c = (q.i - 1) + v.imt * ((q.k - 1) + v.km * jloc);
+  q.cz = q.c + v.imt * (jloc + 1);
+  q.c2 = (q.i - 1) + v.imt * jloc;
   return true;
 }
 
-__device__ __forceinline__ TrPtr tracer_ptr(const DevView &v, int n0) {
-  TrPtr p;
-  p.tm1 = v.t_m1 + (long long)n0 * v.n3;
-  p.t0 = v.t_0 + (long long)n0 * v.n3;
-  p.tp1 = v.t_p1 + (long long)n0 * v.n3;
-  return p;
-}
+// upstream flux 2*(v*T)_face, 09/mom/tracer_adv_flx.F:500-503: totadv*(a+b) + |totadv|*(a-b)
+__device__ __forceinline__ double upw(double totadv, double a, double b) { return totadv * (a + b) + fabs(totadv) * (a - b); }
 
-// rows of t_lo / R: max(2,jlo-1) .. min(jmt-1,jhi+1)
-__global__ void __launch_bounds__(256) k_fct_tlo(const DevView v, int nbase, int jfirst, int nrow) {
-  int i, k, j;
-  if (!decode_cell(v, (long long)blockIdx.x * blockDim.x + threadIdx.x, jfirst, nrow, i, k, j)) return;
-  const int g = blockIdx.y;
-  const TrPtr p = tracer_ptr(v, nbase + g);
-  double *t_lo = v.t_lo + (long long)g * v.n3;
-  // ADV_Tx, ADV_Ty, ADV_Tz of source/mom/fdift.h:25-39 on the low-order fluxes
-  double cstdxt2r = v.cstr[j - 1] * v.dxtr[i - 1] * 0.5;  // 09/mom/tracer.F:240
-  double tx = (lowfe(v, p.tm1, i, k, j) - lowfe(v, p.tm1, i - 1, k, j)) * cstdxt2r;
-  double ty = (lowfn(v, p.tm1, i, k, j) - lowfn(v, p.tm1, i, k, j - 1)) * v.cstdyt2r[j - 1];
-  double tz = (lowfb(v, p.tm1, i, k - 1, j) - lowfb(v, p.tm1, i, k, j)) * v.dzt2r[k - 1];
-  double twodt = v.c2dtts * v.dtxcel[k - 1];
-  double val = p.tm1[X3(i, k, j)] - twodt * (tx + ty + tz) * tmk(v, i, k, j);
-  long long line = X3(1, k, j);
-  t_lo[line + i - 1] = val;
-  if (i == 2) t_lo[line + v.imt - 1] = val;
-  if (i == v.imt - 1) t_lo[line] = val;
+// ------------------------------------------------------------------------------------
+// t_lo, rows max(2,jlo-1) .. min(jmt-1,jhi+1)
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fct_tlo(const DevView v, int nbase, int ng, int tch, int jfirst, int nrow) {
+  Cell q;
+  if (!decode_cell(v, (long long)blockIdx.x * blockDim.x + threadIdx.x, jfirst, nrow, q)) return;
+  const int km = v.km, k = q.k, c = q.c;
+  const double ue_c = v.ue[c], ue_w = v.ue[c - 1], vn_c = v.vn[c], vn_s = v.vn[c - q.sj];
+  const double wb_d = v.wb[q.cz], wb_u = v.wb[q.cz - q.sk];
+  const double m = (v.kmt[q.c2] >= k) ? 1.0 : 0.0;
+  const double cstdxt2r = v.cstr[q.j - 1] * v.dxtr[q.i - 1] * 0.5;  // 09/mom/tracer.F:240
+  const double cstdyt2r = v.cstdyt2r[q.j - 1], dzt2r = v.dzt2r[k - 1];
+  const double twodt = v.c2dtts * v.dtxcel[k - 1];
+  const int cu = (k > 1) ? c - q.sk : c, cd = (k < km) ? c + q.sk : c;
+  const int g0 = blockIdx.y * tch, g1 = min(g0 + tch, ng);
+  for (int g = g0; g < g1; g++) {
+    const double *__restrict__ T = v.t_m1 + (long long)(nbase + g) * v.n3;
+    double *__restrict__ t_lo = v.t_lo + (long long)g * v.n3;
+    const double Tc = T[c], Te = T[c + 1], Tw = T[c - 1], Tn = T[c + q.sj], Ts = T[c - q.sj], Tu = T[cu], Td = T[cd];
+    // ADV_Tx, ADV_Ty, ADV_Tz of source/mom/fdift.h:25-39 on the low-order fluxes
+    double tx = (upw(ue_c, Tc, Te) - upw(ue_w, Tw, Tc)) * cstdxt2r;
+    double ty = (upw(vn_c, Tc, Tn) - upw(vn_s, Ts, Tc)) * cstdyt2r;
+    double fb_u = (k == 1) ? wb_u * 2.0 * Tc : upw(wb_u, Tc, Tu);   // adv_fb(i,0,j) = adv_vbt(i,0,j)*c2*t(i,1,j) (:543)
+    double fb_d = (k == km) ? 0.0 : upw(wb_d, Td, Tc);              // adv_fb(i,km,j) = c0 (:544)
+    double tz = (fb_u - fb_d) * dzt2r;
+    double val = Tc - twodt * (tx + ty + tz) * m;
+    t_lo[c] = val;
+    if (q.i == 2) t_lo[c + v.imt - 2] = val;       // setbcx(t_lo) (:580)
+    if (q.i == v.imt - 1) t_lo[c - (v.imt - 2)] = val;
+  }
 }
 
 __device__ __forceinline__ void ratio(double c2dtts, double dcf, double flxlft, double flxrgt, double fxa, double fxb, double tlo,
@@ -118,58 +105,61 @@ __device__ __forceinline__ void ratio(double c2dtts, double dcf, double flxlft, 
   rmn = fmin(1., m * qminus / (pminus + UVIC_EPSLN));
 }
 
-__global__ void __launch_bounds__(256) k_fct_rfac(const DevView v, int nbase, int jfirst, int nrow) {
-  int i, k, j;
-  if (!decode_cell(v, (long long)blockIdx.x * blockDim.x + threadIdx.x, jfirst, nrow, i, k, j)) return;
-  const int g = blockIdx.y;
-  const TrPtr p = tracer_ptr(v, nbase + g);
-  const double *t_lo = v.t_lo + (long long)g * v.n3;
-  double *R = v.Rfac + (long long)g * 6 * v.n3;
-  const long long c = X3(i, k, j);
-  const double m = tmk(v, i, k, j);
-  const double tlo = t_lo[c];
-  const double t0c = p.t0[c];
-  double rpl, rmn;
-
-  // ---- x (:635-694) ----
-  {
-    double mw = tmk(v, i - 1, k, j), me = tmk(v, i + 1, k, j);
-    double fxa = mw * (0.5 * (p.t0[X3(i - 1, k, j)] + t0c)) + (1.0 - mw) * tlo;
-    double fxb = me * (0.5 * (t0c + p.t0[X3(i + 1, k, j)])) + (1.0 - me) * tlo;
-    double dcf = v.cstr[j - 1] * v.dxtr[i - 1] * 0.5;
-    ratio(v.c2dtts, dcf, antife(v, p, i - 1, k, j), antife(v, p, i, k, j), fxa, fxb, tlo, m, rpl, rmn);
-    R[c] = rpl;
-    R[c + v.n3] = rmn;
-  }
-  // ---- y (:714-770) ----
-  {
-    int jp2 = min(j + 1, v.jmt);
-    double ms = tmk(v, i, k, j - 1), mn = tmk(v, i, k, jp2);
-    double fxa = 0.5 * ms * (p.t0[X3(i, k, j - 1)] + t0c) + (1.0 - ms) * tlo;
-    double fxb = 0.5 * mn * (t0c + p.t0[X3(i, k, jp2)]) + (1.0 - mn) * tlo;
-    ratio(v.c2dtts, v.cstdyt2r[j - 1], antifn(v, p, i, k, j - 1), antifn(v, p, i, k, j), fxa, fxb, tlo, m, rpl, rmn);
-    R[c + 2 * v.n3] = rpl;
-    R[c + 3 * v.n3] = rmn;
-  }
-  // ---- z (:786-958) ----
-  {
-    double fxa, fxb;
-    if (k > 1) {
-      double mu = tmk(v, i, k - 1, j);
-      fxa = 0.5 * mu * (p.t0[X3(i, k - 1, j)] + t0c) + (1.0 - mu) * tlo;
-    } else {
-      fxa = tlo;
+// ------------------------------------------------------------------------------------
+// R+-x, R+-y, R+-z, same rows as t_lo
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fct_rfac(const DevView v, int nbase, int ng, int tch, int jfirst, int nrow) {
+  Cell q;
+  if (!decode_cell(v, (long long)blockIdx.x * blockDim.x + threadIdx.x, jfirst, nrow, q)) return;
+  const int km = v.km, k = q.k, c = q.c, j = q.j;
+  const double ue_c = v.ue[c], ue_w = v.ue[c - 1], vn_c = v.vn[c], vn_s = v.vn[c - q.sj];
+  const double wb_d = v.wb[q.cz], wb_u = v.wb[q.cz - q.sk];
+  const int kmc = v.kmt[q.c2];
+  const double m = (kmc >= k) ? 1.0 : 0.0, mu = (kmc >= k - 1) ? 1.0 : 0.0, md = (kmc >= k + 1) ? 1.0 : 0.0;
+  const double mw = (v.kmt[q.c2 - 1] >= k) ? 1.0 : 0.0, me = (v.kmt[q.c2 + 1] >= k) ? 1.0 : 0.0;
+  const double ms = (v.kmt[q.c2 - v.imt] >= k) ? 1.0 : 0.0, mn = (v.kmt[q.c2 + v.imt] >= k) ? 1.0 : 0.0;  // jp2 = j+1 <= jmt
+  const double dcfx = v.cstr[j - 1] * v.dxtr[q.i - 1] * 0.5, dcfy = v.cstdyt2r[j - 1], dcfz = v.dzt2r[k - 1];
+  const int cu = (k > 1) ? c - q.sk : c, cd = (k < km) ? c + q.sk : c;
+  const int g0 = blockIdx.y * tch, g1 = min(g0 + tch, ng);
+  for (int g = g0; g < g1; g++) {
+    const double *__restrict__ T = v.t_m1 + (long long)(nbase + g) * v.n3;
+    const double *__restrict__ U = v.t_0 + (long long)(nbase + g) * v.n3;
+    double *__restrict__ R = v.Rfac + (long long)g * 6 * v.n3;
+    const double tlo = v.t_lo[(long long)g * v.n3 + c];
+    const double Tc = T[c], Te = T[c + 1], Tw = T[c - 1], Tn = T[c + q.sj], Ts = T[c - q.sj], Tu = T[cu], Td = T[cd];
+    const double Uc = U[c], Ue = U[c + 1], Uw = U[c - 1], Un = U[c + q.sj], Us = U[c - q.sj], Uu = U[cu], Ud = U[cd];
+    double rpl, rmn;
+    // ---- x (:635-694): flxlft = anti_fe(i-1), flxrgt = anti_fe(i) ----
+    {
+      double fxa = mw * (0.5 * (Uw + Uc)) + (1.0 - mw) * tlo;
+      double fxb = me * (0.5 * (Uc + Ue)) + (1.0 - me) * tlo;
+      double a_w = ue_w * (Uw + Uc) - upw(ue_w, Tw, Tc);
+      double a_e = ue_c * (Uc + Ue) - upw(ue_c, Tc, Te);
+      ratio(v.c2dtts, dcfx, a_w, a_e, fxa, fxb, tlo, m, rpl, rmn);
+      R[c] = rpl;
+      R[c + v.n3] = rmn;
     }
-    if (k < v.km) {
-      double md = tmk(v, i, k + 1, j);
-      fxb = 0.5 * md * (t0c + p.t0[X3(i, k + 1, j)]) + (1.0 - md) * tlo;
-    } else {
-      fxb = tlo;
+    // ---- y (:714-770): flxlft = anti_fn(j-1) (= 0 for row 1, :475), flxrgt = anti_fn(j) ----
+    {
+      double fxa = 0.5 * ms * (Us + Uc) + (1.0 - ms) * tlo;
+      double fxb = 0.5 * mn * (Uc + Un) + (1.0 - mn) * tlo;
+      double a_s = (j - 1 < 2) ? 0.0 : vn_s * (Us + Uc) - upw(vn_s, Ts, Tc);
+      double a_n = vn_c * (Uc + Un) - upw(vn_c, Tc, Tn);
+      ratio(v.c2dtts, dcfy, a_s, a_n, fxa, fxb, tlo, m, rpl, rmn);
+      R[c + 2 * v.n3] = rpl;
+      R[c + 3 * v.n3] = rmn;
     }
-    // flxlft = anti_fb(k), flxrgt = anti_fb(k-1)  (:792-793)
-    ratio(v.c2dtts, v.dzt2r[k - 1], antifb(v, p, i, k, j), antifb(v, p, i, k - 1, j), fxa, fxb, tlo, m, rpl, rmn);
-    R[c + 4 * v.n3] = rpl;
-    R[c + 5 * v.n3] = rmn;
+    // ---- z (:786-958): flxlft = anti_fb(k), flxrgt = anti_fb(k-1) ----
+    {
+      double fxa = (k > 1) ? 0.5 * mu * (Uu + Uc) + (1.0 - mu) * tlo : tlo;
+      double fxb = (k < km) ? 0.5 * md * (Uc + Ud) + (1.0 - md) * tlo : tlo;
+      // anti_fb(i,0,j) = adv_vbt(i,0,j)*c2*t(i,1,j,taum1) (:617); anti_fb(i,km,j) = 0
+      double a_d = (k == km) ? 0.0 : wb_d * (Uc + Ud) - upw(wb_d, Td, Tc) * m;
+      double a_u = (k == 1) ? wb_u * 2.0 * Tc : wb_u * (Uu + Uc) - upw(wb_u, Tc, Tu) * mu;
+      ratio(v.c2dtts, dcfz, a_d, a_u, fxa, fxb, tlo, m, rpl, rmn);
+      R[c + 4 * v.n3] = rpl;
+      R[c + 5 * v.n3] = rmn;
+    }
   }
 }
 
@@ -178,133 +168,224 @@ __device__ __forceinline__ double delimit(double cpos, double cneg, double a) {
   return 0.5 * ((cpos + cneg) * a + (cpos - cneg) * fabs(a));
 }
 
-// corrected 2*advective flux through the east face of cell column f (f = 1..imt-1)
-__device__ __forceinline__ double advfe(const DevView &v, const TrPtr &p, const double *R, int f, int k, int j) {
-  long long cl = X3(wrap_i(v, f), k, j), cr = X3(wrap_i(v, f + 1), k, j);
-  double cpos = fmin(R[cr], R[cl + v.n3]);   // Cpos(i) = min(Rpl(i+1),Rmn(i))  (:698-701)
-  double cneg = fmin(R[cl], R[cr + v.n3]);   // Cneg(i) = min(Rpl(i),Rmn(i+1))
-  return delimit(cpos, cneg, antife(v, p, f, k, j)) + lowfe(v, p.tm1, f, k, j);
-}
-__device__ __forceinline__ double advfn(const DevView &v, const TrPtr &p, const double *R, int i, int k, int g) {
-  // rows 1 and jmt carry zero ratios (row 1: :477-478; row jmt: tmask = 0)
-  double rpl_s = 0.0, rmn_s = 0.0, rpl_n = 0.0, rmn_n = 0.0;
-  if (g >= 2) { rpl_s = R[X3(i, k, g) + 2 * v.n3]; rmn_s = R[X3(i, k, g) + 3 * v.n3]; }
-  if (g + 1 <= v.jmt - 1) { rpl_n = R[X3(i, k, g + 1) + 2 * v.n3]; rmn_n = R[X3(i, k, g + 1) + 3 * v.n3]; }
-  double cpos = fmin(rpl_n, rmn_s);  // min(R_plusY(j+1),R_minusY(j))  (:772-775)
-  double cneg = fmin(rpl_s, rmn_n);
-  return (delimit(cpos, cneg, antifn(v, p, i, k, g)) + lowfn(v, p.tm1, i, k, g)) * tmk(v, i, k, g);
-}
-__device__ __forceinline__ double advfb(const DevView &v, const TrPtr &p, const double *R, int i, int h, int j) {
-  if (h == 0) {
-    double t1 = p.t0[X3(i, 1, j)];
-    return v.adv_vbt[X3Z(i, 0, j)] * (t1 + t1);  // 09/mom/tracer.F:1063-1064
+// ------------------------------------------------------------------------------------
+// fluxes + explicit update, rows jlo..jhi
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_update(const DevView v, int nbase, int ng, int tch, int jfirst, int nrow) {
+  Cell q;
+  if (!decode_cell(v, (long long)blockIdx.x * blockDim.x + threadIdx.x, jfirst, nrow, q)) return;
+  const int km = v.km, k = q.k, c = q.c, i = q.i, j = q.j, sk = q.sk, sj = q.sj;
+  const long long n3 = v.n3;
+  const bool iso = v.isopycmix != 0;
+  // cyclic neighbours in i for quantities stored on i = 2..imt-1 only (ratios, Redi coefficients)
+  const int cwr = (i == 2) ? c + (v.imt - 3) : c - 1;           // cell/face i-1 -> imt-1
+  const int cer = (i == v.imt - 1) ? c - (v.imt - 3) : c + 1;   // cell i+1 -> 2
+  // masks (09/mom/loadmw.F:60-77)
+  const int kb = v.kmt[q.c2];
+  const double m = (kb >= k) ? 1.0 : 0.0, mu = (kb >= k - 1) ? 1.0 : 0.0;
+  const double mw = (v.kmt[q.c2 - 1] >= k) ? 1.0 : 0.0, me = (v.kmt[q.c2 + 1] >= k) ? 1.0 : 0.0;
+  const double ms = (v.kmt[q.c2 - v.imt] >= k) ? 1.0 : 0.0, mn = (v.kmt[q.c2 + v.imt] >= k) ? 1.0 : 0.0;
+  // face velocities
+  const double ue_c = v.ue[c], ue_w = v.ue[c - 1], vn_c = v.vn[c], vn_s = v.vn[c - sj];
+  const double wb_d = v.wb[q.cz], wb_u = v.wb[q.cz - sk];
+  // metric factors (09/mom/tracer.F:234-249, source/mom/fdift.h)
+  const double cstr = v.cstr[j - 1];
+  const double cstdxtr = cstr * v.dxtr[i - 1];
+  const double cstdxt2r = cstr * v.dxtr[i - 1] * 0.5;
+  const int iw = (i == 2) ? v.imt - 1 : i - 1;
+  const double cstdxur_e = cstr * v.dxur[i - 1], cstdxur_w = cstr * v.dxur[iw - 1];
+  const double ah_e = v.diff_cet * cstr * v.dxur[i - 1], ah_w = v.diff_cet * cstr * v.dxur[iw - 1];
+  const double cstdyt2r = v.cstdyt2r[j - 1], cstdytr = v.cstdytr[j - 1];
+  const double csu_dyur_n = v.csu_dyur[j - 1], csu_dyur_s = v.csu_dyur[j - 2];
+  const double dzt2r = v.dzt2r[k - 1], dztr = v.dztr[k - 1], dzt4r = 0.5 * v.dzt2r[k - 1];
+  const double csu_dzt4r_n = v.csu[j - 1] * 0.5 * v.dzt2r[k - 1], csu_dzt4r_s = v.csu[j - 2] * 0.5 * v.dzt2r[k - 1];
+  const double dxt4r = v.dxt4r[i - 1], dyt4r_cstr = v.dyt4r[j - 1] * cstr;
+  const double twodt = v.c2dtts * v.dtxcel[k - 1];
+  const double one_m_aidif = 1.0 - v.aidif;
+  // tracer-independent coefficients of the six faces
+  double ce_e[4], ce_w[4], cn_n[4], cn_s[4], cbx_d[4], cby_d[4], cbx_u[4], cby_u[4];
+  double K11_e = 0.0, K11_w = 0.0, K22_n = 0.0, K22_s = 0.0;
+  const bool has_d = (k <= km - 1), has_u = (k >= 2);   // diff_fbiso exists on faces 1..km-1
+  if (iso) {
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      ce_e[a] = v.ce[c + a * n3];
+      ce_w[a] = v.ce[cwr + a * n3];
+      cn_n[a] = v.cn[c + a * n3];
+      cn_s[a] = v.cn[c - sj + a * n3];
+      cbx_d[a] = has_d ? v.cbx[c + a * n3] : 0.0;
+      cby_d[a] = has_d ? v.cby[c + a * n3] : 0.0;
+      cbx_u[a] = has_u ? v.cbx[c - sk + a * n3] : 0.0;
+      cby_u[a] = has_u ? v.cby[c - sk + a * n3] : 0.0;
+    }
+    K11_e = v.K11[c];
+    K11_w = v.K11[cwr];
+    K22_n = v.K22[c];
+    K22_s = v.K22[c - sj];
   }
-  if (h == v.km) return v.adv_vbt[X3Z(i, v.km, j)] * p.t0[X3(i, v.km, j)];  // :1065
-  long long cu = X3(i, h, j), cd = X3(i, h + 1, j);
-  double cneg = fmin(R[cd + 4 * v.n3], R[cu + 5 * v.n3]);  // min(Rpl(k+1),Rmn(k))  (:966-969)
-  double cpos = fmin(R[cu + 4 * v.n3], R[cd + 5 * v.n3]);
-  return (delimit(cpos, cneg, antifb(v, p, i, h, j)) + lowfb(v, p.tm1, i, h, j)) * tmk(v, i, h, j);
-}
+  // diff_cbt*dzwr on faces k and k-1 (09/mom/tracer.F:1025-1032)
+  const double dcb_d = has_d ? v.diff_cbt[c] : 0.0, dcb_u = has_u ? v.diff_cbt[c - sk] : 0.0;
+  const double dzwr_d = v.dzwr[k], dzwr_u = v.dzwr[k - 1];
+  const int cu = has_u ? c - sk : c, cd = has_d ? c + sk : c;   // clamped k-1, k+1 (km1kr / kpkr of isoflux)
+  const bool row_s_has_R = (j - 1 >= 2), row_n_has_R = (j + 1 <= v.jmt - 1);
 
-// total diffusive flux through the east face of column f (f in 2..imt-1 after wrap):
-// background (tracer.F:930-940) + K11 + off-diagonal Redi terms (isopyc.F:950-1002)
-__device__ __forceinline__ double difffe(const DevView &v, const double *tm1, int f, int k, int j) {
-  f = wrap_i(v, f);
-  long long c = X3(f, k, j);
-  double d = tm1[X3(f + 1, k, j)] - tm1[c];
-  double cstdxur = v.cstr[j - 1] * v.dxur[f - 1];
-  double fe = v.diff_cet * v.cstr[j - 1] * v.dxur[f - 1] * d;
-  if (!v.isopycmix) return fe;
-  double dzt4r = 0.5 * v.dzt2r[k - 1];
-  double sumz = 0.0;
-#pragma unroll
-  for (int kr = 0; kr <= 1; kr++) {
-    int km1kr = max(k - 1 + kr, 1), kpkr = min(k + kr, v.km);
-#pragma unroll
-    for (int ip = 0; ip <= 1; ip++)
-      sumz = sumz - v.ce[c + (ip + 2 * kr) * v.n3] * (tm1[X3(f + ip, km1kr, j)] - tm1[X3(f + ip, kpkr, j)]);
+  const int g0 = blockIdx.y * tch, g1 = min(g0 + tch, ng);
+  for (int g = g0; g < g1; g++) {
+    const int n0 = nbase + g;
+    const double *__restrict__ T = v.t_m1 + (long long)n0 * n3;
+    const double *__restrict__ U = v.t_0 + (long long)n0 * n3;
+    const double *__restrict__ R = v.Rfac + (long long)g * 6 * n3;
+    // t(tau-1): the 15-point neighbourhood
+    const double Tc = T[c], Te = T[c + 1], Tw = T[c - 1], Tn = T[c + sj], Ts = T[c - sj], Tu = T[cu], Td = T[cd];
+    const double Teu = T[cu + 1], Twu = T[cu - 1], Tnu = T[cu + sj], Tsu = T[cu - sj];
+    const double Ted = T[cd + 1], Twd = T[cd - 1], Tnd = T[cd + sj], Tsd = T[cd - sj];
+    // t(tau)
+    const double Uc = U[c], Ue = U[c + 1], Uw = U[c - 1], Un = U[c + sj], Us = U[c - sj], Uu = U[cu], Ud = U[cd];
+
+    // ---------------- advective fluxes (FCT) ----------------
+    // east / west faces: Cpos(f) = min(Rpl(f+1),Rmn(f)), Cneg(f) = min(Rpl(f),Rmn(f+1)) (:698-701); no mask (:987)
+    const double rplx_c = R[c], rmnx_c = R[c + n3];
+    double adv_fe_e, adv_fe_w;
+    {
+      double lo = upw(ue_c, Tc, Te);
+      double a = ue_c * (Uc + Ue) - lo;
+      adv_fe_e = delimit(fmin(R[cer], rmnx_c), fmin(rplx_c, R[cer + n3]), a) + lo;
+      lo = upw(ue_w, Tw, Tc);
+      a = ue_w * (Uw + Uc) - lo;
+      adv_fe_w = delimit(fmin(rplx_c, R[cwr + n3]), fmin(R[cwr], rmnx_c), a) + lo;
+    }
+    // north / south faces: Cpos(g) = min(R_plusY(g+1),R_minusY(g)), Cneg(g) = min(R_plusY(g),R_minusY(g+1)) (:772-775)
+    const double rply_c = R[c + 2 * n3], rmny_c = R[c + 3 * n3];
+    double adv_fn_n, adv_fn_s;
+    {
+      double rpl_n = 0.0, rmn_n = 0.0, rpl_s = 0.0, rmn_s = 0.0;   // rows 1 and jmt carry zero ratios
+      if (row_n_has_R) { rpl_n = R[c + sj + 2 * n3]; rmn_n = R[c + sj + 3 * n3]; }
+      if (row_s_has_R) { rpl_s = R[c - sj + 2 * n3]; rmn_s = R[c - sj + 3 * n3]; }
+      double lo = upw(vn_c, Tc, Tn);
+      double a = vn_c * (Uc + Un) - lo;
+      adv_fn_n = (delimit(fmin(rpl_n, rmny_c), fmin(rply_c, rmn_n), a) + lo) * m;
+      lo = upw(vn_s, Ts, Tc);
+      a = row_s_has_R ? vn_s * (Us + Uc) - lo : 0.0;                // anti_fn(i,k,1,n) = c0 (:475)
+      adv_fn_s = (delimit(fmin(rply_c, rmn_s), fmin(rpl_s, rmny_c), a) + lo) * ms;
+    }
+    // bottom / top faces: Cneg(h) = min(Rpl(h+1),Rmn(h)), Cpos(h) = min(Rpl(h),Rmn(h+1)) (:966-969);
+    // adv_fb(0), adv_fb(km) are overwritten in tracer (09/mom/tracer.F:1063-1065)
+    const double rplz_c = R[c + 4 * n3], rmnz_c = R[c + 5 * n3];
+    double adv_fb_d, adv_fb_u;
+    if (k == km) {
+      adv_fb_d = wb_d * Uc;
+    } else {
+      double lo = upw(wb_d, Td, Tc);
+      double a = wb_d * (Uc + Ud) - lo * m;
+      adv_fb_d = (delimit(fmin(rplz_c, R[c + sk + 5 * n3]), fmin(R[c + sk + 4 * n3], rmnz_c), a) + lo) * m;
+    }
+    if (k == 1) {
+      adv_fb_u = wb_u * (Uc + Uc);
+    } else {
+      double lo = upw(wb_u, Tc, Tu);
+      double a = wb_u * (Uu + Uc) - lo * mu;
+      adv_fb_u = (delimit(fmin(R[c - sk + 4 * n3], rmnz_c), fmin(rplz_c, R[c - sk + 5 * n3]), a) + lo) * mu;
+    }
+    const double adv_tx = (adv_fe_e - adv_fe_w) * cstdxt2r;
+    const double adv_ty = (adv_fn_n - adv_fn_s) * cstdyt2r;
+    const double adv_tz = (adv_fb_u - adv_fb_d) * dzt2r;
+
+    // ---------------- diffusive fluxes ----------------
+    // east / west (09/mom/tracer.F:930-940 + isoflux 09/mom/isopyc.F:950-1002)
+    double diff_fe_e, diff_fe_w;
+    {
+      double d = Te - Tc;
+      diff_fe_e = ah_e * d;
+      if (iso) {
+        double sumz = 0.0;
+        sumz = sumz - ce_e[0] * (Tu - Tc);
+        sumz = sumz - ce_e[1] * (Teu - Te);
+        sumz = sumz - ce_e[2] * (Tc - Td);
+        sumz = sumz - ce_e[3] * (Te - Ted);
+        diff_fe_e = diff_fe_e + K11_e * cstdxur_e * d + dzt4r * sumz;
+      }
+      d = Tc - Tw;
+      diff_fe_w = ah_w * d;
+      if (iso) {
+        double sumz = 0.0;
+        sumz = sumz - ce_w[0] * (Twu - Tw);
+        sumz = sumz - ce_w[1] * (Tu - Tc);
+        sumz = sumz - ce_w[2] * (Tw - Twd);
+        sumz = sumz - ce_w[3] * (Tc - Td);
+        diff_fe_w = diff_fe_w + K11_w * cstdxur_w * d + dzt4r * sumz;
+      }
+    }
+    // north / south (09/mom/tracer.F:945-961 + isoflux :1007-1053)
+    double diff_fn_n, diff_fn_s;
+    {
+      double d = Tn - Tc;
+      diff_fn_n = v.diff_cnt * csu_dyur_n * d;
+      if (iso) {
+        double sumz = 0.0;
+        sumz = sumz - cn_n[0] * (Tu - Tc);
+        sumz = sumz - cn_n[1] * (Tnu - Tn);
+        sumz = sumz - cn_n[2] * (Tc - Td);
+        sumz = sumz - cn_n[3] * (Tn - Tnd);
+        diff_fn_n = diff_fn_n + K22_n * csu_dyur_n * d + csu_dzt4r_n * sumz;
+      }
+      d = Tc - Ts;
+      diff_fn_s = v.diff_cnt * csu_dyur_s * d;
+      if (iso) {
+        double sumz = 0.0;
+        sumz = sumz - cn_s[0] * (Tsu - Ts);
+        sumz = sumz - cn_s[1] * (Tu - Tc);
+        sumz = sumz - cn_s[2] * (Ts - Tsd);
+        sumz = sumz - cn_s[3] * (Tc - Td);
+        diff_fn_s = diff_fn_s + K22_s * csu_dyur_s * d + csu_dzt4r_s * sumz;
+      }
+    }
+    // vertical with the b.c. of tracer.F:1053-1062: diff_fb(0)=stf, then diff_fb(kmt)=btf
+    double fb_d, fb_u;
+    {
+      const double stf = v.stf[q.c2 + (long long)n0 * v.n2], btf = v.btf[q.c2 + (long long)n0 * v.n2];
+      fb_d = (k == kb) ? btf : (has_d ? dcb_d * dzwr_d * (Tc - Td) : 0.0);
+      fb_u = (k - 1 == kb) ? btf : ((k == 1) ? stf : dcb_u * dzwr_u * (Tu - Tc));
+    }
+    double diff_tz;
+    if (iso) {
+      // K31, K32 part solved explicitly (09/mom/isopyc.F:1062-1108)
+      double fbiso_d = 0.0, fbiso_u = 0.0;
+      if (has_d) {
+        double sumx = 0.0, sumy = 0.0;
+        sumx = sumx - cbx_d[0] * (Tc - Tw);
+        sumx = sumx - cbx_d[2] * (Td - Twd);
+        sumx = sumx - cbx_d[1] * (Te - Tc);
+        sumx = sumx - cbx_d[3] * (Ted - Td);
+        sumy = sumy - cby_d[0] * (Tc - Ts);
+        sumy = sumy - cby_d[2] * (Td - Tsd);
+        sumy = sumy - cby_d[1] * (Tn - Tc);
+        sumy = sumy - cby_d[3] * (Tnd - Td);
+        fbiso_d = dxt4r * sumx + dyt4r_cstr * sumy;
+      }
+      if (has_u) {
+        double sumx = 0.0, sumy = 0.0;
+        sumx = sumx - cbx_u[0] * (Tu - Twu);
+        sumx = sumx - cbx_u[2] * (Tc - Tw);
+        sumx = sumx - cbx_u[1] * (Teu - Tu);
+        sumx = sumx - cbx_u[3] * (Te - Tc);
+        sumy = sumy - cby_u[0] * (Tu - Tsu);
+        sumy = sumy - cby_u[2] * (Tc - Ts);
+        sumy = sumy - cby_u[1] * (Tnu - Tu);
+        sumy = sumy - cby_u[3] * (Tn - Tc);
+        fbiso_u = dxt4r * sumx + dyt4r_cstr * sumy;
+      }
+      diff_tz = (fb_u - fb_d) * dztr * one_m_aidif + (fbiso_u - fbiso_d) * dztr;
+    } else {
+      diff_tz = (fb_u - fb_d) * dztr;
+    }
+    const double diff_tx = (diff_fe_e * me - diff_fe_w * mw) * cstdxtr;
+    const double diff_ty = (diff_fn_n * mn - diff_fn_s * ms) * cstdytr;
+
+    // The source term is added in k_invtri (same operation order as 09/mom/tracer.F:1114-1127:
+    // t(tau-1) + twodt*(DIFF - ADV + source)*tmask), so the MOBI kernels, which run on a side
+    // stream, only have to finish before the implicit solve.
+    v.t_p1[(long long)n0 * n3 + c] = diff_tx + diff_ty + diff_tz - adv_tx - adv_ty - adv_tz;
   }
-  double flux_x = dzt4r * sumz;
-  return fe + v.K11[c] * cstdxur * d + flux_x;
-}
-__device__ __forceinline__ double difffn(const DevView &v, const double *tm1, int i, int k, int g) {
-  long long c = X3(i, k, g);
-  double d = tm1[X3(i, k, g + 1)] - tm1[c];
-  double fn = v.diff_cnt * v.csu_dyur[g - 1] * d;
-  if (!v.isopycmix) return fn;
-  double csu_dzt4r = v.csu[g - 1] * 0.5 * v.dzt2r[k - 1];
-  double sumz = 0.0;
-#pragma unroll
-  for (int kr = 0; kr <= 1; kr++) {
-    int km1kr = max(k - 1 + kr, 1), kpkr = min(k + kr, v.km);
-#pragma unroll
-    for (int jq = 0; jq <= 1; jq++)
-      sumz = sumz - v.cn[c + (jq + 2 * kr) * v.n3] * (tm1[X3(i, km1kr, g + jq)] - tm1[X3(i, kpkr, g + jq)]);
-  }
-  double flux_y = csu_dzt4r * sumz;
-  return fn + v.K22[c] * v.csu_dyur[g - 1] * d + flux_y;
-}
-// vertical diffusive flux with the b.c. of tracer.F:1053-1062
-__device__ __forceinline__ double difffb(const DevView &v, const double *tm1, int n0, int i, int h, int j, int kb) {
-  if (h == kb) return v.btf[X2(i, j) + (long long)n0 * v.n2];
-  if (h == 0) return v.stf[X2(i, j) + (long long)n0 * v.n2];
-  if (h >= v.km) return 0.0;
-  return v.diff_cbt[X3(i, h, j)] * v.dzwr[h] * (tm1[X3(i, h, j)] - tm1[X3(i, h + 1, j)]);
-}
-// K31, K32 part, solved explicitly (isopyc.F:1062-1108)
-__device__ __forceinline__ double difffbiso(const DevView &v, const double *tm1, int i, int h, int j) {
-  if (h == 0 || h >= v.km) return 0.0;
-  long long c = X3(i, h, j);
-  double sumx = 0.0, sumy = 0.0;
-#pragma unroll
-  for (int ip = 0; ip <= 1; ip++)
-#pragma unroll
-    for (int kr = 0; kr <= 1; kr++)
-      sumx = sumx - v.cbx[c + (ip + 2 * kr) * v.n3] * (tm1[X3(i + ip, h + kr, j)] - tm1[X3(i - 1 + ip, h + kr, j)]);
-#pragma unroll
-  for (int jq = 0; jq <= 1; jq++)
-#pragma unroll
-    for (int kr = 0; kr <= 1; kr++)
-      sumy = sumy - v.cby[c + (jq + 2 * kr) * v.n3] * (tm1[X3(i, h + kr, j + jq)] - tm1[X3(i, h + kr, j - 1 + jq)]);
-  return v.dxt4r[i - 1] * sumx + v.dyt4r[j - 1] * v.cstr[j - 1] * sumy;
-}
-
-__global__ void __launch_bounds__(256) k_update(const DevView v, int nbase, int jfirst, int nrow) {
-  int i, k, j;
-  if (!decode_cell(v, (long long)blockIdx.x * blockDim.x + threadIdx.x, jfirst, nrow, i, k, j)) return;
-  const int g = blockIdx.y;
-  const int n0 = nbase + g;
-  const TrPtr p = tracer_ptr(v, n0);
-  const double *R = v.Rfac + (long long)g * 6 * v.n3;
-  const long long c = X3(i, k, j);
-  const int kb = v.kmt[X2(i, j)];
-  const double m = (kb >= k) ? 1.0 : 0.0;
-
-  // advective flux divergences (source/mom/fdift.h:25-39)
-  double cstdxt2r = v.cstr[j - 1] * v.dxtr[i - 1] * 0.5;
-  double cstdxtr = v.cstr[j - 1] * v.dxtr[i - 1];
-  double adv_tx = (advfe(v, p, R, i, k, j) - advfe(v, p, R, i - 1, k, j)) * cstdxt2r;
-  double adv_ty = (advfn(v, p, R, i, k, j) - advfn(v, p, R, i, k, j - 1)) * v.cstdyt2r[j - 1];
-  double adv_tz = (advfb(v, p, R, i, k - 1, j) - advfb(v, p, R, i, k, j)) * v.dzt2r[k - 1];
-
-  // diffusive flux divergences (fdift.h:61-88)
-  double diff_tx = (difffe(v, p.tm1, i, k, j) * tmk(v, i + 1, k, j) - difffe(v, p.tm1, i - 1, k, j) * tmk(v, i - 1, k, j)) * cstdxtr;
-  double diff_ty = (difffn(v, p.tm1, i, k, j) * tmk(v, i, k, j + 1) - difffn(v, p.tm1, i, k, j - 1) * tmk(v, i, k, j - 1)) * v.cstdytr[j - 1];
-  double diff_tz;
-  {
-    double fb_u = difffb(v, p.tm1, n0, i, k - 1, j, kb), fb_d = difffb(v, p.tm1, n0, i, k, j, kb);
-    if (v.isopycmix)
-      diff_tz = (fb_u - fb_d) * v.dztr[k - 1] * (1.0 - v.aidif) +
-                (difffbiso(v, p.tm1, i, k - 1, j) - difffbiso(v, p.tm1, i, k, j)) * v.dztr[k - 1];
-    else
-      diff_tz = (fb_u - fb_d) * v.dztr[k - 1];
-  }
-  double source = 0.0;
-  int is = v.itrc[n0];
-  if (is != 0) source = v.src[c + (long long)(is - 1) * v.n3];
-
-  double twodt = v.c2dtts * v.dtxcel[k - 1];
-  p.tp1[c] = p.tm1[c] + twodt * (diff_tx + diff_ty + diff_tz - adv_tx - adv_ty - adv_tz + source) * m;
 }
 
 // one thread per (column, tracer): source/mom/invtri.F:75-110 with precomputed a, e, bet
@@ -317,19 +398,25 @@ __global__ void __launch_bounds__(128) k_invtri(const DevView v, int nbase) {
   int j = (int)(idx / ni) + v.jlo;
   const int n0 = nbase + blockIdx.y;
   double *z = v.t_p1 + (long long)n0 * v.n3;
+  const double *__restrict__ tm1 = v.t_m1 + (long long)n0 * v.n3;
+  const int isrc = v.itrc[n0];
+  const double *__restrict__ srcp = (isrc != 0) ? v.src + (long long)(isrc - 1) * v.n3 : nullptr;
   const int km = v.km;
   const int kb = v.kmt[X2(i, j)];
   const int kbot = max(2, kb);
   double topbc = v.stf[X2(i, j) + (long long)n0 * v.n2];
   double botbc = v.btf[X2(i, j) + (long long)n0 * v.n2];
   double zprev = 0.0;
+  const int c1 = (int)X3(i, 1, j), sk = v.imt;
   for (int k = 1; k <= km; k++) {
-    long long c = X3(i, k, j);
+    int c = c1 + (k - 1) * sk;
     double mk = (kb >= k) ? 1.0 : 0.0;
     double tdt = v.c2dtts * v.dtxcel[k - 1];
-    double f = z[c] * mk;
-    if (k == 1) f = z[c] + topbc * tdt * v.dztr[0] * v.aidif * mk;
-    if (k == kbot) f = z[c] - botbc * tdt * v.dztr[k - 1] * v.aidif * mk;
+    // explicit update (09/mom/tracer.F:1114-1127) from the partial tendency left by k_update
+    const double zc = tm1[c] + tdt * (z[c] + (srcp ? srcp[c] : 0.0)) * mk;
+    double f = zc * mk;
+    if (k == 1) f = zc + topbc * tdt * v.dztr[0] * v.aidif * mk;
+    if (k == kbot) f = zc - botbc * tdt * v.dztr[k - 1] * v.aidif * mk;
     double zk;
     if (k == 1)
       zk = f * v.tri_bet[c];
@@ -341,18 +428,17 @@ __global__ void __launch_bounds__(128) k_invtri(const DevView v, int nbase) {
   // back substitution + cyclic boundary
   double znext = zprev;
   {
-    long long line = X3(1, km, j);
-    if (i == 2) z[line + v.imt - 1] = znext;
-    if (i == v.imt - 1) z[line] = znext;
+    int c = c1 + (km - 1) * sk;
+    if (i == 2) z[c + v.imt - 2] = znext;
+    if (i == v.imt - 1) z[c - (v.imt - 2)] = znext;
   }
   for (int k = km - 1; k >= 1; k--) {
-    long long c = X3(i, k, j);
-    double zk = z[c] - v.tri_e[X3(i, k + 1, j)] * znext;
+    int c = c1 + (k - 1) * sk;
+    double zk = z[c] - v.tri_e[c + sk] * znext;
     z[c] = zk;
     znext = zk;
-    long long line = X3(1, k, j);
-    if (i == 2) z[line + v.imt - 1] = zk;
-    if (i == v.imt - 1) z[line] = zk;
+    if (i == 2) z[c + v.imt - 2] = zk;
+    if (i == v.imt - 1) z[c - (v.imt - 2)] = zk;
   }
 }
 
@@ -363,8 +449,11 @@ __device__ __forceinline__ double dens_f(const DevView &v, double tq, double sq,
          (ECC(k, 2) + (ECC(k, 5) + ECC(k, 9) * sq) * sq) * sq;
 }
 
-// one thread per column: convct2 (source/mom/convect.F:99-311), all nt tracers
-__global__ void __launch_bounds__(128) k_convect(const DevView v) {
+// convct2 phase 1 (source/mom/convect.F:193-268): one thread per column finds the unstable
+// regions from T and S, mixes T and S, and records (kt, kb, zsm) of every region so that the
+// other tracers can be mixed in parallel.  zsm is recorded, not recomputed, because it is
+// accumulated in the order the levels were discovered.
+__global__ void __launch_bounds__(128) k_convect_ts(const DevView v) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int ni = v.imt - 2;
   int nrow = v.jhi - v.jlo + 1;
@@ -374,7 +463,11 @@ __global__ void __launch_bounds__(128) k_convect(const DevView v) {
   const int kbo = v.kmt[X2(i, j)];
   double *T = v.t_p1, *S = v.t_p1 + v.n3;
   const double *dz = v.dztxcl;
-#define TSV(a, k) a[X3(i, k, j)]
+  const int c1 = (int)X3(i, 1, j), sk = v.imt;
+  const long long col = X2(i, j);
+  const int maxreg = v.km / 2 + 1;
+#define TSV(a, k) a[c1 + ((k)-1) * sk]
+  int nreg = 0;
   int kt = 1, kb = 2;
   while (kt < kbo) {
     double ru = dens_f(v, TSV(T, kt) - v.to[kb - 1], TSV(S, kt) - v.so[kb - 1], kb);
@@ -426,27 +519,57 @@ __global__ void __launch_bounds__(128) k_convect(const DevView v) {
         TSV(T, k) = tmx1;
         TSV(S, k) = tmx2;
       }
-      for (int n = 3; n <= v.nt; n++) {
-        double *X = v.t_p1 + (long long)(n - 1) * v.n3;
-        double tsm3 = 0.0;
-        for (int k = kt; k <= kb; k++) tsm3 = tsm3 + TSV(X, k) * dz[k - 1];
-        double tmx3 = tsm3 / zsm;
-        for (int k = kt; k <= kb; k++) TSV(X, k) = tmx3;
+      if (nreg < maxreg) {
+        v.conv_kt[col + (long long)nreg * v.n2] = kt | (kb << 16);
+        v.conv_zsm[col + (long long)nreg * v.n2] = zsm;
       }
+      nreg++;
       kt = kb + 1;
     } else {
       kt = kb;
     }
     kb = kt + 1;
   }
-#undef TSV
-  // cyclic boundary of every tracer (09/mom/tracer.F:1199-1203)
+  v.conv_n[col] = nreg;
+  // cyclic boundary of T and S (09/mom/tracer.F:1199-1203)
   if (i == 2 || i == v.imt - 1) {
-    int iw = (i == 2) ? v.imt : 1;
-    for (int n = 0; n < v.nt; n++) {
-      double *X = v.t_p1 + (long long)n * v.n3;
-      for (int k = 1; k <= v.km; k++) X[X3(iw, k, j)] = X[X3(i, k, j)];
+    int off = (i == 2) ? (v.imt - 2) : -(v.imt - 2);
+    for (int k = 1; k <= v.km; k++) {
+      T[c1 + (k - 1) * sk + off] = TSV(T, k);
+      S[c1 + (k - 1) * sk + off] = TSV(S, k);
     }
+  }
+#undef TSV
+}
+
+// convct2 phase 2 (source/mom/convect.F:269-277): one thread per (column, tracer n >= 3)
+__global__ void __launch_bounds__(128) k_convect_tr(const DevView v) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int ni = v.imt - 2;
+  int nrow = v.jhi - v.jlo + 1;
+  if (idx >= (long long)ni * nrow) return;
+  int i = (int)(idx % ni) + 2;
+  int j = (int)(idx / ni) + v.jlo;
+  const int n0 = blockIdx.y + 2;
+  const long long col = X2(i, j);
+  const int nreg = v.conv_n[col];
+  const bool edge = (i == 2 || i == v.imt - 1);
+  if (nreg == 0 && !edge) return;
+  double *X = v.t_p1 + (long long)n0 * v.n3;
+  const double *dz = v.dztxcl;
+  const int c1 = (int)X3(i, 1, j), sk = v.imt;
+  for (int r = 0; r < nreg; r++) {
+    int pk = v.conv_kt[col + (long long)r * v.n2];
+    int kt = pk & 0xffff, kb = pk >> 16;
+    double zsm = v.conv_zsm[col + (long long)r * v.n2];
+    double tsm3 = 0.0;
+    for (int k = kt; k <= kb; k++) tsm3 = tsm3 + X[c1 + (k - 1) * sk] * dz[k - 1];
+    double tmx3 = tsm3 / zsm;
+    for (int k = kt; k <= kb; k++) X[c1 + (k - 1) * sk] = tmx3;
+  }
+  if (edge) {
+    int off = (i == 2) ? (v.imt - 2) : -(v.imt - 2);
+    for (int k = 1; k <= v.km; k++) X[c1 + (k - 1) * sk + off] = X[c1 + (k - 1) * sk];
   }
 }
 
@@ -461,17 +584,27 @@ void launch_tracer(uvic_b200_ctx *c, const uvic_b200_stepinfo *si) {
   const long long ncol = (long long)(v.imt - 2) * nrow_c;
   for (int nbase = 0; nbase < v.nt; nbase += v.ngroup) {
     int ng = min(v.ngroup, v.nt - nbase);
+    // tracers per thread: keep at least ~4 CTAs-worth of threads per SM in flight, then amortise the
+    // tracer-independent loads over as many tracers as possible
+    int nchunk = (int)min((long long)ng, max(1LL, (148LL * 2048 * 2 + ncell_c - 1) / ncell_c));
+    int tch = (ng + nchunk - 1) / nchunk;
+    nchunk = (ng + tch - 1) / tch;
     if (v.fct) {
-      dim3 gr(cdiv(ncell_r, 256), ng);
-      KLAUNCH("k_fct_tlo", k_fct_tlo, gr, 256, v, nbase, jf_r, nrow_r);
-      KLAUNCH("k_fct_rfac", k_fct_rfac, gr, 256, v, nbase, jf_r, nrow_r);
+      dim3 gr(cdiv(ncell_r, 256), nchunk);
+      KLAUNCH("k_fct_tlo", k_fct_tlo, gr, 256, v, nbase, ng, tch, jf_r, nrow_r);
+      KLAUNCH("k_fct_rfac", k_fct_rfac, gr, 256, v, nbase, ng, tch, jf_r, nrow_r);
     }
-    dim3 gc(cdiv(ncell_c, 256), ng);
-    KLAUNCH("k_update", k_update, gc, 256, v, nbase, v.jlo, nrow_c);
+    dim3 gc(cdiv(ncell_c, 256), nchunk);
+    KLAUNCH("k_update", k_update, gc, 256, v, nbase, ng, tch, v.jlo, nrow_c);
+    if (nbase == 0 && c->mobi_event) cudaStreamWaitEvent(c->stream, c->mobi_event, 0);
     dim3 gi(cdiv(ncol, 128), ng);
     KLAUNCH("k_invtri", k_invtri, gi, 128, v, nbase);
   }
   if (c->par.fullconvect) {
-    KLAUNCH("k_convect", k_convect, cdiv(ncol, 128), 128, v);
+    KLAUNCH("k_convect_ts", k_convect_ts, cdiv(ncol, 128), 128, v);
+    if (v.nt > 2) {
+      dim3 gt(cdiv(ncol, 128), v.nt - 2);
+      KLAUNCH("k_convect_tr", k_convect_tr, gt, 128, v);
+    }
   }
 }
