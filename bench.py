@@ -34,6 +34,8 @@ WORKLOADS = {
     "uvic100_mobi37": dict(imt=102, rows=100, km=19, nt=37, mobi=1,
                            desc="UVic 2.9 100x100x19, isopycnal mixing + GM + FCT + full MOBI tracer set (run/mk.in), nt=37"),
     "uvic100_ts": dict(imt=102, rows=100, km=19, nt=2, mobi=0, desc="UVic 2.9 100x100x19, T,S only, isopyc + GM + FCT"),
+    "one_deg_37": dict(imt=362, rows=180, km=30, nt=37, mobi=1,
+                       desc="synthetic 1 deg 360x180x30, full MOBI tracer set (profiling size)"),
     "half_deg_40": dict(imt=722, rows=360, km=40, nt=40, mobi=1,
                         desc="synthetic 0.5 deg 720x360x40, 40 tracers (37 MOBI + 3 passive), isopyc + FCT + invtri"),
     "tenth_deg_slab_40": dict(imt=3602, rows=225, km=60, nt=40, mobi=1,

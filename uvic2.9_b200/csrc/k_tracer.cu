@@ -61,6 +61,10 @@ __device__ __forceinline__ bool decode_cell(const DevView &v, long long idx, int
 // upstream flux 2*(v*T)_face, 09/mom/tracer_adv_flx.F:500-503: totadv*(a+b) + |totadv|*(a-b)
 __device__ __forceinline__ double upw(double totadv, double a, double b) { return totadv * (a + b) + fabs(totadv) * (a - b); }
 
+// Fortran max/min on finite operands: one DSETP + two selects (CUDA's fmax/fmin add NaN handling)
+__device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
+__device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
+
 // ------------------------------------------------------------------------------------
 // t_lo, rows max(2,jlo-1) .. min(jmt-1,jhi+1)
 // ------------------------------------------------------------------------------------
@@ -95,14 +99,14 @@ __global__ void __launch_bounds__(256) k_fct_tlo(const DevView v, int nbase, int
 
 __device__ __forceinline__ void ratio(double c2dtts, double dcf, double flxlft, double flxrgt, double fxa, double fxb, double tlo,
                                       double m, double &rpl, double &rmn) {
-  double trmax = fmax(fmax(fxa, fxb), tlo);
-  double trmin = fmin(fmin(fxa, fxb), tlo);
-  double pplus = c2dtts * dcf * (fmax(0.0, flxlft) - fmin(0.0, flxrgt));
-  double pminus = c2dtts * dcf * (fmax(0.0, flxrgt) - fmin(0.0, flxlft));
+  double trmax = dmax(dmax(fxa, fxb), tlo);
+  double trmin = dmin(dmin(fxa, fxb), tlo);
+  double pplus = c2dtts * dcf * (dmax(0.0, flxlft) - dmin(0.0, flxrgt));
+  double pminus = c2dtts * dcf * (dmax(0.0, flxrgt) - dmin(0.0, flxlft));
   double qplus = trmax - tlo;
   double qminus = tlo - trmin;
-  rpl = fmin(1., m * qplus / (pplus + UVIC_EPSLN));
-  rmn = fmin(1., m * qminus / (pminus + UVIC_EPSLN));
+  rpl = dmin(1., div0(m * qplus, pplus + UVIC_EPSLN));
+  rmn = dmin(1., div0(m * qminus, pminus + UVIC_EPSLN));
 }
 
 // ------------------------------------------------------------------------------------
@@ -171,9 +175,21 @@ __device__ __forceinline__ double delimit(double cpos, double cneg, double a) {
 // ------------------------------------------------------------------------------------
 // fluxes + explicit update, rows jlo..jhi
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_update(const DevView v, int nbase, int ng, int tch, int jfirst, int nrow) {
+#define UPD_T 128   // threads per CTA of k_update
+// per-thread column of the shared-memory coefficient table: element a lives at p[a*UPD_T]
+struct SmCol {
+  double *p;
+  __device__ __forceinline__ double &operator[](int a) const { return p[a * UPD_T]; }
+};
+
+__global__ void __launch_bounds__(UPD_T) k_update(const DevView v, int nbase, int ng, int tch, int jfirst, int nrow) {
+  // The 36 tracer-independent Redi coefficients of a cell's six faces are parked in shared
+  // memory (thread-private slots, conflict free) instead of registers: 36 KB per 128-thread CTA
+  // buys ~70 registers per thread, i.e. three CTAs per SM instead of one 256-thread CTA.
+  __shared__ double sco[36][UPD_T];
   Cell q;
   if (!decode_cell(v, (long long)blockIdx.x * blockDim.x + threadIdx.x, jfirst, nrow, q)) return;
+  const int tid = threadIdx.x;
   const int km = v.km, k = q.k, c = q.c, i = q.i, j = q.j, sk = q.sk, sj = q.sj;
   const long long n3 = v.n3;
   const bool iso = v.isopycmix != 0;
@@ -203,8 +219,9 @@ __global__ void __launch_bounds__(256) k_update(const DevView v, int nbase, int 
   const double twodt = v.c2dtts * v.dtxcel[k - 1];
   const double one_m_aidif = 1.0 - v.aidif;
   // tracer-independent coefficients of the six faces
-  double ce_e[4], ce_w[4], cn_n[4], cn_s[4], cbx_d[4], cby_d[4], cbx_u[4], cby_u[4];
-  double K11_e = 0.0, K11_w = 0.0, K22_n = 0.0, K22_s = 0.0;
+  const SmCol ce_e{&sco[0][tid]}, ce_w{&sco[4][tid]}, cn_n{&sco[8][tid]}, cn_s{&sco[12][tid]};
+  const SmCol cbx_d{&sco[16][tid]}, cby_d{&sco[20][tid]}, cbx_u{&sco[24][tid]}, cby_u{&sco[28][tid]};
+  double &K11_e = sco[32][tid], &K11_w = sco[33][tid], &K22_n = sco[34][tid], &K22_s = sco[35][tid];
   const bool has_d = (k <= km - 1), has_u = (k >= 2);   // diff_fbiso exists on faces 1..km-1
   if (iso) {
 #pragma unroll
@@ -249,10 +266,10 @@ __global__ void __launch_bounds__(256) k_update(const DevView v, int nbase, int 
     {
       double lo = upw(ue_c, Tc, Te);
       double a = ue_c * (Uc + Ue) - lo;
-      adv_fe_e = delimit(fmin(R[cer], rmnx_c), fmin(rplx_c, R[cer + n3]), a) + lo;
+      adv_fe_e = delimit(dmin(R[cer], rmnx_c), dmin(rplx_c, R[cer + n3]), a) + lo;
       lo = upw(ue_w, Tw, Tc);
       a = ue_w * (Uw + Uc) - lo;
-      adv_fe_w = delimit(fmin(rplx_c, R[cwr + n3]), fmin(R[cwr], rmnx_c), a) + lo;
+      adv_fe_w = delimit(dmin(rplx_c, R[cwr + n3]), dmin(R[cwr], rmnx_c), a) + lo;
     }
     // north / south faces: Cpos(g) = min(R_plusY(g+1),R_minusY(g)), Cneg(g) = min(R_plusY(g),R_minusY(g+1)) (:772-775)
     const double rply_c = R[c + 2 * n3], rmny_c = R[c + 3 * n3];
@@ -263,10 +280,10 @@ __global__ void __launch_bounds__(256) k_update(const DevView v, int nbase, int 
       if (row_s_has_R) { rpl_s = R[c - sj + 2 * n3]; rmn_s = R[c - sj + 3 * n3]; }
       double lo = upw(vn_c, Tc, Tn);
       double a = vn_c * (Uc + Un) - lo;
-      adv_fn_n = (delimit(fmin(rpl_n, rmny_c), fmin(rply_c, rmn_n), a) + lo) * m;
+      adv_fn_n = (delimit(dmin(rpl_n, rmny_c), dmin(rply_c, rmn_n), a) + lo) * m;
       lo = upw(vn_s, Ts, Tc);
       a = row_s_has_R ? vn_s * (Us + Uc) - lo : 0.0;                // anti_fn(i,k,1,n) = c0 (:475)
-      adv_fn_s = (delimit(fmin(rply_c, rmn_s), fmin(rpl_s, rmny_c), a) + lo) * ms;
+      adv_fn_s = (delimit(dmin(rply_c, rmn_s), dmin(rpl_s, rmny_c), a) + lo) * ms;
     }
     // bottom / top faces: Cneg(h) = min(Rpl(h+1),Rmn(h)), Cpos(h) = min(Rpl(h),Rmn(h+1)) (:966-969);
     // adv_fb(0), adv_fb(km) are overwritten in tracer (09/mom/tracer.F:1063-1065)
@@ -277,14 +294,14 @@ __global__ void __launch_bounds__(256) k_update(const DevView v, int nbase, int 
     } else {
       double lo = upw(wb_d, Td, Tc);
       double a = wb_d * (Uc + Ud) - lo * m;
-      adv_fb_d = (delimit(fmin(rplz_c, R[c + sk + 5 * n3]), fmin(R[c + sk + 4 * n3], rmnz_c), a) + lo) * m;
+      adv_fb_d = (delimit(dmin(rplz_c, R[c + sk + 5 * n3]), dmin(R[c + sk + 4 * n3], rmnz_c), a) + lo) * m;
     }
     if (k == 1) {
       adv_fb_u = wb_u * (Uc + Uc);
     } else {
       double lo = upw(wb_u, Tc, Tu);
       double a = wb_u * (Uu + Uc) - lo * mu;
-      adv_fb_u = (delimit(fmin(R[c - sk + 4 * n3], rmnz_c), fmin(rplz_c, R[c - sk + 5 * n3]), a) + lo) * mu;
+      adv_fb_u = (delimit(dmin(R[c - sk + 4 * n3], rmnz_c), dmin(rplz_c, R[c - sk + 5 * n3]), a) + lo) * mu;
     }
     const double adv_tx = (adv_fe_e - adv_fe_w) * cstdxt2r;
     const double adv_ty = (adv_fn_n - adv_fn_s) * cstdyt2r;
@@ -594,8 +611,8 @@ void launch_tracer(uvic_b200_ctx *c, const uvic_b200_stepinfo *si) {
       KLAUNCH("k_fct_tlo", k_fct_tlo, gr, 256, v, nbase, ng, tch, jf_r, nrow_r);
       KLAUNCH("k_fct_rfac", k_fct_rfac, gr, 256, v, nbase, ng, tch, jf_r, nrow_r);
     }
-    dim3 gc(cdiv(ncell_c, 256), nchunk);
-    KLAUNCH("k_update", k_update, gc, 256, v, nbase, ng, tch, v.jlo, nrow_c);
+    dim3 gc(cdiv(ncell_c, UPD_T), nchunk);
+    KLAUNCH("k_update", k_update, gc, UPD_T, v, nbase, ng, tch, v.jlo, nrow_c);
     if (nbase == 0 && c->mobi_event) cudaStreamWaitEvent(c->stream, c->mobi_event, 0);
     dim3 gi(cdiv(ncol, 128), ng);
     KLAUNCH("k_invtri", k_invtri, gi, 128, v, nbase);
