@@ -43,6 +43,15 @@ WORKLOADS = {
 }
 
 
+_JSON_OUT = None
+
+
+def _emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def load_pkg():
     if "uvic29_b200" in sys.modules:
         return sys.modules["uvic29_b200"]
@@ -214,7 +223,7 @@ def run_reference(a):
                                    f"single-replica step {1e3 * min(per):.0f}-{1e3 * tmax:.0f} ms; wall {wall:.0f} s"},
         "e2e": {"value": value, "unit": "G cell*tracer/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def main():
@@ -227,6 +236,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     a = ap.parse_args()
+    # Keep stdout clean for the ONE JSON line: libraries (NCCL prints its version banner there)
+    # get stderr as their fd 1; the JSON goes to the saved descriptor.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if a.impl == "reference":
         return run_reference(a)
 
@@ -422,7 +437,7 @@ def main():
         "roofline": roofline, "step_hbm": step_hbm, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": clk, "kernels": kern, "inventory_check": {"finite": bool(np.isfinite(inv).all())},
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

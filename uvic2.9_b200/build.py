@@ -17,8 +17,11 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # the operation order was kept.  The kernels are bandwidth / FP64-issue bound, not FMA bound.
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-fmad=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
 ]
+# Per-file override of -fmad.  FMA contraction was measured on k_mobi.cu (the FP64-issue bound
+# kernel): 5-6 % faster only, so every translation unit keeps -fmad=false.
+FMAD = {}
 
 
 def sources():
@@ -41,7 +44,7 @@ def build(force=False, verbose=False, extra=()):
 
     def cc(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [NVCC, *FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [NVCC, *FLAGS, f"-fmad={FMAD.get(src, 'false')}", *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
