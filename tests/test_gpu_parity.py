@@ -198,3 +198,61 @@ def test_slab_decomposition_matches_single_context(pkg):
             c.rotate()
     for c in (one, lo, hi):
         c.close()
+
+
+@pytest.mark.parametrize("opts", [dict(fct=0), dict(tidal_kv=0), dict(fullconvect=0), dict(fct=0, tidal_kv=0, fullconvect=0)])
+def test_option_switches(pkg, opts):
+    """cpp options of run/mk.in as run-time switches: O_fct off (2nd-order centred advection +
+    explicit GM advective terms, 09/mom/tracer_adv_flx.F:1030-1082), O_tidal_kv off, O_fullconvect off."""
+    case = _case(pkg, imt=42, jmt=34, km=9, nt=3, seed=17)
+    o = make_oracle(case, do_convect=opts.get("fullconvect", 1))
+    o.set_scalar("fct", opts.get("fct", 1))
+    o.set_scalar("tidal_kv", opts.get("tidal_kv", 1))
+    ctx = pkg.TracerContext(case, **opts)
+    ctx.load_state()
+    for step in range(2):
+        oracle_set_step(o, case, True)
+        o.call("ora_step")
+        ctx.step(True)
+        got, ref = ctx.download_t(+1), o.t()[2]
+        for n in range(case.nt):
+            assert relerr(got[n, 1:-1], ref[n, 1:-1]) <= TOL, (opts, step, n)
+        oracle_rotate(o)
+        ctx.rotate()
+    ctx.close()
+    o.close()
+
+
+def test_adv_vel_bit_exact(pkg):
+    """adv_vel (tracer part, source/mom/adv_vel.F:60-131) on the device against the oracle."""
+    case = _case(pkg, imt=42, jmt=34, km=9, nt=3, seed=19)
+    o = make_oracle(case)
+    o.call("ora_adv_vel")
+    ctx = pkg.TracerContext(case)
+    ctx.upload_u(case["u"])
+    ctx.adv_vel()
+    ctx.synchronize()
+    s3, s3z = ctx.shape3(), ctx.shape3z()
+    got_e, got_n, got_b = ctx.fetch("adv_vet", s3), ctx.fetch("adv_vnt", s3), ctx.fetch("adv_vbt", s3z)
+    assert np.array_equal(got_n, o.arr("adv_vnt", s3))
+    assert np.array_equal(got_e[1:], o.arr("adv_vet", s3)[1:])
+    assert np.array_equal(got_b[1:], o.arr("adv_vbt", s3z)[1:])
+    # and they agree with the numpy generator used for the synthetic inputs to round-off
+    assert np.allclose(got_n, case["adv_vnt"], rtol=0, atol=1e-13 * np.abs(case["adv_vnt"]).max())
+    ctx.close()
+    o.close()
+
+
+def test_host_buffer_step_matches_resident_step(pkg):
+    """uvic_b200_tracer_step (host buffers, what the Fortran shim calls) == resident step."""
+    case = _case(pkg, imt=34, jmt=26, km=8, nt=3, seed=23)
+    a = _ctx(pkg, case)
+    b = pkg.TracerContext(case)
+    t = case["t"]
+    out = np.empty(b.shape_t())
+    b.tracer_step_host(np.ascontiguousarray(t[0]), np.ascontiguousarray(t[1]), case["adv_vet"], case["adv_vnt"], case["adv_vbt"],
+                       case["stf"], case["btf"], out, leapfrog=True)
+    a.step(True)
+    assert np.array_equal(out, a.download_t(+1))
+    a.close()
+    b.close()

@@ -62,7 +62,6 @@ int uvic_b200_create(const uvic_b200_dims *d, const uvic_b200_grid *g, const uvi
   if (d->imt < 4 || d->jmt < 4 || d->km < 2 || d->nt < 2) return fail(nullptr, "uvic_b200_create: bad dims");
   if (d->jrow_lo < 2 || d->jrow_hi > d->jmt - 1 || d->jrow_lo > d->jrow_hi)
     return fail(nullptr, "uvic_b200_create: rows must satisfy 2 <= jrow_lo <= jrow_hi <= jmt-1");
-  if (!par->fct) return fail(nullptr, "uvic_b200_create: only the O_fct advection scheme of run/mk.in is built");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(nullptr, "uvic_b200_create: no CUDA device (this library has no CPU fallback)");

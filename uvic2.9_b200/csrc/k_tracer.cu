@@ -182,6 +182,7 @@ struct SmCol {
   __device__ __forceinline__ double &operator[](int a) const { return p[a * UPD_T]; }
 };
 
+template <bool FCT>
 __global__ void __launch_bounds__(UPD_T) k_update(const DevView v, int nbase, int ng, int tch, int jfirst, int nrow) {
   // The 36 tracer-independent Redi coefficients of a cell's six faces are parked in shared
   // memory (thread-private slots, conflict free) instead of registers: 36 KB per 128-thread CTA
@@ -259,53 +260,78 @@ __global__ void __launch_bounds__(UPD_T) k_update(const DevView v, int nbase, in
     // t(tau)
     const double Uc = U[c], Ue = U[c + 1], Uw = U[c - 1], Un = U[c + sj], Us = U[c - sj], Uu = U[cu], Ud = U[cd];
 
-    // ---------------- advective fluxes (FCT) ----------------
-    // east / west faces: Cpos(f) = min(Rpl(f+1),Rmn(f)), Cneg(f) = min(Rpl(f),Rmn(f+1)) (:698-701); no mask (:987)
-    const double rplx_c = R[c], rmnx_c = R[c + n3];
-    double adv_fe_e, adv_fe_w;
-    {
-      double lo = upw(ue_c, Tc, Te);
-      double a = ue_c * (Uc + Ue) - lo;
-      adv_fe_e = delimit(dmin(R[cer], rmnx_c), dmin(rplx_c, R[cer + n3]), a) + lo;
-      lo = upw(ue_w, Tw, Tc);
-      a = ue_w * (Uw + Uc) - lo;
-      adv_fe_w = delimit(dmin(rplx_c, R[cwr + n3]), dmin(R[cwr], rmnx_c), a) + lo;
-    }
-    // north / south faces: Cpos(g) = min(R_plusY(g+1),R_minusY(g)), Cneg(g) = min(R_plusY(g),R_minusY(g+1)) (:772-775)
-    const double rply_c = R[c + 2 * n3], rmny_c = R[c + 3 * n3];
-    double adv_fn_n, adv_fn_s;
-    {
-      double rpl_n = 0.0, rmn_n = 0.0, rpl_s = 0.0, rmn_s = 0.0;   // rows 1 and jmt carry zero ratios
-      if (row_n_has_R) { rpl_n = R[c + sj + 2 * n3]; rmn_n = R[c + sj + 3 * n3]; }
-      if (row_s_has_R) { rpl_s = R[c - sj + 2 * n3]; rmn_s = R[c - sj + 3 * n3]; }
-      double lo = upw(vn_c, Tc, Tn);
-      double a = vn_c * (Uc + Un) - lo;
-      adv_fn_n = (delimit(dmin(rpl_n, rmny_c), dmin(rply_c, rmn_n), a) + lo) * m;
-      lo = upw(vn_s, Ts, Tc);
-      a = row_s_has_R ? vn_s * (Us + Uc) - lo : 0.0;                // anti_fn(i,k,1,n) = c0 (:475)
-      adv_fn_s = (delimit(dmin(rply_c, rmn_s), dmin(rpl_s, rmny_c), a) + lo) * ms;
-    }
-    // bottom / top faces: Cneg(h) = min(Rpl(h+1),Rmn(h)), Cpos(h) = min(Rpl(h),Rmn(h+1)) (:966-969);
-    // adv_fb(0), adv_fb(km) are overwritten in tracer (09/mom/tracer.F:1063-1065)
-    const double rplz_c = R[c + 4 * n3], rmnz_c = R[c + 5 * n3];
-    double adv_fb_d, adv_fb_u;
-    if (k == km) {
-      adv_fb_d = wb_d * Uc;
+    // ---------------- advective fluxes ----------------
+    double adv_tx, adv_ty, adv_tz, adv_tz_iso[3] = {0.0, 0.0, 0.0};
+    bool adv_iso = false;
+    if constexpr (FCT) {
+      // east / west faces: Cpos(f) = min(Rpl(f+1),Rmn(f)), Cneg(f) = min(Rpl(f),Rmn(f+1)) (:698-701); no mask (:987)
+      const double rplx_c = R[c], rmnx_c = R[c + n3];
+      double adv_fe_e, adv_fe_w;
+      {
+        double lo = upw(ue_c, Tc, Te);
+        double a = ue_c * (Uc + Ue) - lo;
+        adv_fe_e = delimit(dmin(R[cer], rmnx_c), dmin(rplx_c, R[cer + n3]), a) + lo;
+        lo = upw(ue_w, Tw, Tc);
+        a = ue_w * (Uw + Uc) - lo;
+        adv_fe_w = delimit(dmin(rplx_c, R[cwr + n3]), dmin(R[cwr], rmnx_c), a) + lo;
+      }
+      // north / south faces: Cpos(g) = min(R_plusY(g+1),R_minusY(g)), Cneg(g) = min(R_plusY(g),R_minusY(g+1)) (:772-775)
+      const double rply_c = R[c + 2 * n3], rmny_c = R[c + 3 * n3];
+      double adv_fn_n, adv_fn_s;
+      {
+        double rpl_n = 0.0, rmn_n = 0.0, rpl_s = 0.0, rmn_s = 0.0;   // rows 1 and jmt carry zero ratios
+        if (row_n_has_R) { rpl_n = R[c + sj + 2 * n3]; rmn_n = R[c + sj + 3 * n3]; }
+        if (row_s_has_R) { rpl_s = R[c - sj + 2 * n3]; rmn_s = R[c - sj + 3 * n3]; }
+        double lo = upw(vn_c, Tc, Tn);
+        double a = vn_c * (Uc + Un) - lo;
+        adv_fn_n = (delimit(dmin(rpl_n, rmny_c), dmin(rply_c, rmn_n), a) + lo) * m;
+        lo = upw(vn_s, Ts, Tc);
+        a = row_s_has_R ? vn_s * (Us + Uc) - lo : 0.0;                // anti_fn(i,k,1,n) = c0 (:475)
+        adv_fn_s = (delimit(dmin(rply_c, rmn_s), dmin(rpl_s, rmny_c), a) + lo) * ms;
+      }
+      // bottom / top faces: Cneg(h) = min(Rpl(h+1),Rmn(h)), Cpos(h) = min(Rpl(h),Rmn(h+1)) (:966-969);
+      // adv_fb(0), adv_fb(km) are overwritten in tracer (09/mom/tracer.F:1063-1065)
+      const double rplz_c = R[c + 4 * n3], rmnz_c = R[c + 5 * n3];
+      double adv_fb_d, adv_fb_u;
+      if (k == km) {
+        adv_fb_d = wb_d * Uc;
+      } else {
+        double lo = upw(wb_d, Td, Tc);
+        double a = wb_d * (Uc + Ud) - lo * m;
+        adv_fb_d = (delimit(dmin(rplz_c, R[c + sk + 5 * n3]), dmin(R[c + sk + 4 * n3], rmnz_c), a) + lo) * m;
+      }
+      if (k == 1) {
+        adv_fb_u = wb_u * (Uc + Uc);
+      } else {
+        double lo = upw(wb_u, Tc, Tu);
+        double a = wb_u * (Uu + Uc) - lo * mu;
+        adv_fb_u = (delimit(dmin(R[c - sk + 4 * n3], rmnz_c), dmin(rplz_c, R[c - sk + 5 * n3]), a) + lo) * mu;
+      }
+      adv_tx = (adv_fe_e - adv_fe_w) * cstdxt2r;
+      adv_ty = (adv_fn_n - adv_fn_s) * cstdyt2r;
+      adv_tz = (adv_fb_u - adv_fb_d) * dzt2r;
     } else {
-      double lo = upw(wb_d, Td, Tc);
-      double a = wb_d * (Uc + Ud) - lo * m;
-      adv_fb_d = (delimit(dmin(rplz_c, R[c + sk + 5 * n3]), dmin(R[c + sk + 4 * n3], rmnz_c), a) + lo) * m;
+      // 2nd-order centred (09/mom/tracer_adv_flx.F:1030-1082, source/mom/fdift.h:25-39) plus the
+      // Gent-McWilliams advective terms ADV_Txiso/Tyiso/Tziso (fdift.h:44-52, isoflux :1110-1134)
+      const double vet_c = v.adv_vet[c], vet_w = v.adv_vet[c - 1], vnt_c = v.adv_vnt[c], vnt_s = v.adv_vnt[c - sj];
+      const double vbt_d = v.adv_vbt[q.cz], vbt_u = v.adv_vbt[q.cz - sk];
+      adv_tx = (vet_c * (Uc + Ue) - vet_w * (Uw + Uc)) * cstdxt2r;
+      adv_ty = (vnt_c * (Uc + Un) - vnt_s * (Us + Uc)) * cstdyt2r;
+      const double fb_dn = (k == km) ? vbt_d * Uc : vbt_d * (Uc + Ud);
+      const double fb_up = (k == 1) ? vbt_u * (Uc + Uc) : vbt_u * (Uu + Uc);
+      adv_tz = (fb_up - fb_dn) * dzt2r;
+      if (iso) {
+        const double ve_c = v.adv_vetiso[c], ve_w = v.adv_vetiso[c - 1], vn_c2 = v.adv_vntiso[c], vn_s2 = v.adv_vntiso[c - sj];
+        const double txi = cstdxt2r * (ve_c * (Te + Tc) - ve_w * (Tc + Tw));
+        const double tyi = cstdyt2r * (vn_c2 * (Tn + Tc) - vn_s2 * (Tc + Ts));
+        const double fbi_d = (k == km) ? 0.0 : v.adv_vbtiso[q.cz] * (Tc + Td);
+        const double fbi_u = (k == 1) ? 0.0 : v.adv_vbtiso[q.cz - sk] * (Tu + Tc);
+        const double tzi = dzt2r * (fbi_u - fbi_d);
+        adv_iso = true;
+        // subtracted in the reference's order: ... - ADV_Tz - ADV_Txiso - ADV_Tyiso - ADV_Tziso
+        adv_tz_iso[0] = txi; adv_tz_iso[1] = tyi; adv_tz_iso[2] = tzi;
+      }
     }
-    if (k == 1) {
-      adv_fb_u = wb_u * (Uc + Uc);
-    } else {
-      double lo = upw(wb_u, Tc, Tu);
-      double a = wb_u * (Uu + Uc) - lo * mu;
-      adv_fb_u = (delimit(dmin(R[c - sk + 4 * n3], rmnz_c), dmin(rplz_c, R[c - sk + 5 * n3]), a) + lo) * mu;
-    }
-    const double adv_tx = (adv_fe_e - adv_fe_w) * cstdxt2r;
-    const double adv_ty = (adv_fn_n - adv_fn_s) * cstdyt2r;
-    const double adv_tz = (adv_fb_u - adv_fb_d) * dzt2r;
 
     // ---------------- diffusive fluxes ----------------
     // east / west (09/mom/tracer.F:930-940 + isoflux 09/mom/isopyc.F:950-1002)
@@ -401,7 +427,9 @@ __global__ void __launch_bounds__(UPD_T) k_update(const DevView v, int nbase, in
     // The source term is added in k_invtri (same operation order as 09/mom/tracer.F:1114-1127:
     // t(tau-1) + twodt*(DIFF - ADV + source)*tmask), so the MOBI kernels, which run on a side
     // stream, only have to finish before the implicit solve.
-    v.t_p1[(long long)n0 * n3 + c] = diff_tx + diff_ty + diff_tz - adv_tx - adv_ty - adv_tz;
+    double P = diff_tx + diff_ty + diff_tz - adv_tx - adv_ty - adv_tz;
+    if (!FCT && adv_iso) P = P - adv_tz_iso[0] - adv_tz_iso[1] - adv_tz_iso[2];
+    v.t_p1[(long long)n0 * n3 + c] = P;
   }
 }
 
@@ -612,7 +640,10 @@ void launch_tracer(uvic_b200_ctx *c, const uvic_b200_stepinfo *si) {
       KLAUNCH("k_fct_rfac", k_fct_rfac, gr, 256, v, nbase, ng, tch, jf_r, nrow_r);
     }
     dim3 gc(cdiv(ncell_c, UPD_T), nchunk);
-    KLAUNCH("k_update", k_update, gc, UPD_T, v, nbase, ng, tch, v.jlo, nrow_c);
+    if (v.fct)
+      KLAUNCH("k_update", k_update<true>, gc, UPD_T, v, nbase, ng, tch, v.jlo, nrow_c);
+    else
+      KLAUNCH("k_update", k_update<false>, gc, UPD_T, v, nbase, ng, tch, v.jlo, nrow_c);
     if (nbase == 0 && c->mobi_event) cudaStreamWaitEvent(c->stream, c->mobi_event, 0);
     dim3 gi(cdiv(ncol, 128), ng);
     KLAUNCH("k_invtri", k_invtri, gi, 128, v, nbase);
