@@ -264,7 +264,10 @@ def main():
     case = make_case(pkg, a.workload, world)
     parts = pkg.slab.partition_rows(case.jmt, world)
     jlo, jhi = parts[rank]
-    ctx = pkg.TracerContext(case, jlo=jlo, jhi=jhi, device=local, mobi=w["mobi"])
+    # O_fourfil is on in run/mk.in; the synthetic fine grids skip it (the reference's filter
+    # tables are fixed-size, source/common/index.h:34)
+    fourfil = 1 if a.workload.startswith("uvic100") else 0
+    ctx = pkg.TracerContext(case, jlo=jlo, jhi=jhi, device=local, mobi=w["mobi"], fourfil=fourfil)
     ctx.load_state()
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)

@@ -69,6 +69,7 @@ typedef struct uvic_b200_params {
   int32_t fullconvect;          /* O_fullconvect */
   int32_t mobi;                 /* O_mobi (+ the O_mobi_* / O_carbon* set of run/mk.in) */
   int32_t fourfil;              /* O_fourfil */
+  int32_t jfrst, jft0, jft1, jft2; /* Fourier-filter rows (global), source/common/setcom.F:37-40,75-85 */
   const int32_t *itrc;          /* (nt) source slot per tracer, 0 = none (09/mom/mw.h:125-221) */
   const int32_t *mobi_index;    /* tracer / source index maps for MOBI, see uvic_b200_mobi.h; may be NULL */
   const double *mobi_par;       /* MOBI parameter block after mobi_init's unit conversion; may be NULL */

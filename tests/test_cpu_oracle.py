@@ -237,3 +237,43 @@ def test_co2calc_known_state(pkg):
     # deeper water is less saturated
     L.ora_co2calc_SWS(2.0, 34.7, 2.3, 2.4, 280.0, 1.0, 4000.0, *[C.byref(x) for x in out])
     assert out[6].value < om_c
+
+
+def _filter_case(pkg, **kw):
+    # ocean up to 86 degrees so that many rows poleward of 69.3 degrees are filtered
+    return pkg.synthetic.make_case(imt=42, jmt=48, km=6, nt=3, names=["temp", "salt", "passive0"], seed=31, land_lat=86.0, **kw)
+
+
+def test_fourier_filter_properties(pkg):
+    """filt/filtr (source/common/filt.F, filtr.F): only rows poleward of 69.3 degrees change, every
+    ocean strip keeps its sum (filtr.F:411-420), and grid-scale noise along a polar row is damped."""
+    case = _filter_case(pkg)
+    s = case.scalars
+    assert 1 <= s["jfrst"] <= s["jft1"] < s["jft2"] <= case.jmt
+    o = make_oracle(case)
+    o.set_scalar("do_filter", 1)
+    t = o.t()
+    rng = np.random.default_rng(0)
+    noisy = case["t"][0] + 0.3 * rng.standard_normal(case["t"][0].shape) * case["tmask"]
+    noisy[..., 0] = noisy[..., -2]
+    noisy[..., -1] = noisy[..., 1]
+    t[2] = noisy
+    before = t[2].copy()
+    o.call("ora_filt")
+    after = t[2]
+    yt = case["_yt"]
+    unfiltered = (np.arange(1, case.jmt + 1) > s["jft1"]) & (np.arange(1, case.jmt + 1) < s["jft2"])
+    assert np.array_equal(after[:, unfiltered], before[:, unfiltered])
+    polar = ~unfiltered
+    polar[0] = polar[-1] = False
+    assert np.abs(after[:, polar] - before[:, polar]).max() > 1e-3
+    # row sums over i = 2..imt-1 are preserved strip by strip, hence per (row, level)
+    sb = before[:, :, :, 1:-1].sum(axis=-1)
+    sa = after[:, :, :, 1:-1].sum(axis=-1)
+    assert np.abs(sa - sb).max() <= 1e-11 * np.abs(sb).max()
+    # roughness (sum of squared i-differences) of the polar ocean rows drops
+    def rough(x):
+        d = np.diff(x[:, polar][..., 1:-1], axis=-1) * (case["tmask"][polar][..., 1:-2] * case["tmask"][polar][..., 2:-1])[None]
+        return (d ** 2).sum()
+    assert rough(after) < 0.7 * rough(before)
+    o.close()

@@ -38,7 +38,8 @@ class Params(C.Structure):
     _fields_ = (
         [(n, C.c_double) for n in ("aidif", "kappa_h", "ahisop", "athkdf", "slmxr", "diff_cet", "diff_cnt",
                                    "zetar", "ogamma", "gravrho0r")]
-        + [(n, C.c_int32) for n in ("fct", "isopycmix", "tidal_kv", "fullconvect", "mobi", "fourfil")]
+        + [(n, C.c_int32) for n in ("fct", "isopycmix", "tidal_kv", "fullconvect", "mobi", "fourfil",
+                                    "jfrst", "jft0", "jft1", "jft2")]
         + [("itrc", _c_int_p), ("mobi_index", _c_int_p), ("mobi_par", _c_double_p),
            ("n_mobi_index", C.c_int32), ("n_mobi_par", C.c_int32)]
     )
@@ -182,6 +183,8 @@ class TracerContext:
         for n in ("aidif", "kappa_h", "ahisop", "athkdf", "slmxr", "diff_cet", "diff_cnt", "zetar", "ogamma", "gravrho0r"):
             setattr(p, n, float(s[n]))
         p.fct, p.isopycmix, p.tidal_kv, p.fullconvect, p.mobi, p.fourfil = fct, isopycmix, tidal_kv, fullconvect, mobi, fourfil
+        if fourfil:
+            p.jfrst, p.jft0, p.jft1, p.jft2 = (int(s[n]) for n in ("jfrst", "jft0", "jft1", "jft2"))
         itrc = np.ascontiguousarray(a["itrc"], dtype=np.int32)
         self._keep.append(itrc)
         p.itrc = itrc.ctypes.data_as(_c_int_p)

@@ -231,6 +231,14 @@ int uvic_b200_create(const uvic_b200_dims *d, const uvic_b200_grid *g, const uvi
     CK(cudaMalloc((void **)&ctx->red_out, (size_t)nt * sizeof(double)));
     ctx->owned.push_back(ctx->red_out);
   }
+  ctx->filt_items = nullptr; ctx->filt_mats = nullptr; ctx->filt_nitems = 0; ctx->filt_maxim = 0;
+  if (par->fourfil) {
+    if (par->jfrst < 1 || par->jft0 < 1 || par->jft0 > jmt || par->jft1 < par->jfrst || par->jft2 <= par->jft1 || par->jft2 > jmt) {
+      delete ctx;
+      return fail(nullptr, "uvic_b200_create: O_fourfil needs 1 <= jfrst <= jft1 < jft2 <= jmt and a valid jft0");
+    }
+    if (filter_setup(ctx, st->kmt, g->cst, g->cstr)) return fail(ctx, "uvic_b200_create: filter set-up failed");
+  }
   CK(cudaDeviceSynchronize());
   *out = ctx;
   return 0;

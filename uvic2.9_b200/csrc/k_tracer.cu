@@ -655,4 +655,6 @@ void launch_tracer(uvic_b200_ctx *c, const uvic_b200_stepinfo *si) {
       KLAUNCH("k_convect_tr", k_convect_tr, gt, 128, v);
     }
   }
+  // Fourier filter of the polar rows + cyclic boundary (09/mom/tracer.F:1245-1262)
+  launch_filter(c);
 }

@@ -321,15 +321,25 @@ def default_tracer_names(nt):
     return names
 
 
+def indp(value, array):
+    """index (1-based) of the array element nearest to value (source/common/util.F `indp`)."""
+    return int(np.argmin(np.abs(np.asarray(array) - value))) + 1
+
+
+def filter_rows(yt):
+    """Fourier-filter rows as setcom derives them (source/common/setcom.F:37-40,75-85)."""
+    return dict(jfrst=indp(-87.3, yt), jft0=indp(-67.5, yt), jft1=indp(-69.3, yt), jft2=indp(69.3, yt))
+
+
 def make_case(imt=102, jmt=102, km=19, nt=2, seed=SEED, names=None, dtts=None, noise=1.0,
-              with_static_mobi=True) -> Case:
+              with_static_mobi=True, land_lat=72.0) -> Case:
     """Build one complete synthetic configuration."""
     names = list(names) if names is not None else default_tracer_names(nt)
     assert len(names) == nt
     arrays: dict = {}
     scalars: dict = {}
     make_grid(imt, jmt, km, arrays, scalars)
-    make_bathymetry(imt, jmt, km, arrays, seed)
+    make_bathymetry(imt, jmt, km, arrays, seed, land_lat=land_lat)
     make_eos(km, arrays)
     make_velocity(imt, jmt, km, arrays, seed)
     vet, vnt, vbt = adv_vel_numpy(imt, jmt, km, arrays)
@@ -386,6 +396,7 @@ def make_case(imt=102, jmt=102, km=19, nt=2, seed=SEED, names=None, dtts=None, n
         diff_cet=0.0, diff_cnt=0.0,                                  # ah=ahbkg=0 with O_isopycmix
         zetar=zetar, ogamma=0.2 * (1.0 / rho0) * zetar, gravrho0r=grav * (1.0 / rho0),
         relyr=0.37, co2ccn=280.0,
+        **filter_rows(arrays["_yt"]),
     )
     itrc = np.zeros(nt, dtype=np.int32)
     nsrc = 0
