@@ -96,8 +96,10 @@ def kernel_bytes_per_launch(name, case, ctx, ngroup_launch):
         "k_invtri": cells * (16 * g + 24),             # t(tau+1) in/out; a, e, bet
         "k_convect_ts": cells * 32,                    # T,S read + written (worst case)
         "k_convect_tr": cells * 16 * (case.nt - 2),    # worst case: every other tracer read + written
-        "k_mobi_column": ocean * 8 * (37 + 2 + 35),    # 37 tracers + CO2*, Omega in; 35 sources out
-        "k_mobi_co2": ocean * 8 * (4 + 2),
+        "k_mobi_column": ocean * 8 * (37 + 15 + 35),   # 37 tracers + 15 pre-pass fields in; 35 sources out
+        "k_mobi_ws": ocean * 8 * (37 + 15 + 35),
+        "k_mobi_cell": ocean * 8 * (11 + 1 + 15),      # 11 tracers + light in; 15 pre-pass fields out
+        "k_mobi_light": ocean * 8 * (4 + 1),
         "k_elements": cells * 8 * (2 + 8),
         "k_isocoef": cells * 8 * (10 + 19),
         "k_gm_faces": cells * 8 * (8 + 2),
@@ -297,10 +299,8 @@ def main():
 
     for _ in range(warmup):
         one_step()
-    # ---- timed region: device resident -------------------------------------------------
+    # ---- timed region: device resident (production path: MOBI overlapped on its side stream) ----
     barrier()
-    ctx.profile_reset()
-    ctx.profile_enable(True)
     l0 = ctx.kernel_launches
     clocks = ClockSampler(local)
     if rank == 0:
@@ -313,8 +313,21 @@ def main():
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
-    clk = clocks.stop() if rank == 0 else None
     launches = ctx.kernel_launches - l0
+    # ---- the same K steps again with per-kernel CUDA events (library hooks).  In this pass the
+    # library runs MOBI in line on the launch stream, so that no two kernels share the SMs and
+    # every event interval is the duration of exactly one kernel; its total is NOT the bench value.
+    ctx.profile_reset()
+    ctx.profile_enable(True)
+    barrier()
+    evp0, evp1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evp0.record(stream)
+    for _ in range(a.steps):
+        one_step()
+    evp1.record(stream)
+    barrier()
+    ms_prof = evp0.elapsed_time(evp1)
+    clk = clocks.stop() if rank == 0 else None
     ctx.profile_enable(False)
     prof = ctx.profile()
     if world > 1:
@@ -438,7 +451,7 @@ def main():
                    "time_stepping": "leapfrog with a forward mixing step every 16th (run/control.in nmix=16)"},
         "sim_years_per_day": 86400.0 / (292.0 * ms_step * 1e-3),
         "roofline": roofline, "step_hbm": step_hbm, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-        "clocks": clk, "kernels": kern, "inventory_check": {"finite": bool(np.isfinite(inv).all())},
+        "clocks": clk, "ms_per_step_serialised_profile_pass": ms_prof / a.steps, "kernels": kern, "inventory_check": {"finite": bool(np.isfinite(inv).all())},
     }
     _emit(line)
     ctx.close()

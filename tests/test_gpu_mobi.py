@@ -21,7 +21,10 @@ def _mobi_pair(pkg, **kw):
     return case, o, ctx
 
 
-def test_mobi_sources_parity(pkg):
+@pytest.mark.parametrize("ws", ["0", "1"])
+def test_mobi_sources_parity(pkg, ws, monkeypatch):
+    # both column kernels: one thread per column ("0") and warp specialised ("1")
+    monkeypatch.setenv("UVIC_B200_MOBI_WS", ws)
     case, o, ctx = _mobi_pair(pkg)
     oracle_set_step(o, case, True)
     o.call("ora_step")
@@ -40,7 +43,9 @@ def test_mobi_sources_parity(pkg):
     o.close()
 
 
-def test_mobi_multi_step_with_mixing(pkg):
+@pytest.mark.parametrize("ws", ["0", "1"])
+def test_mobi_multi_step_with_mixing(pkg, ws, monkeypatch):
+    monkeypatch.setenv("UVIC_B200_MOBI_WS", ws)
     case, o, ctx = _mobi_pair(pkg, imt=42, jmt=34, km=10, seed=5)
     itt = 0
     for _ in range(6):
@@ -57,3 +62,19 @@ def test_mobi_multi_step_with_mixing(pkg):
         ctx.rotate()
     ctx.close()
     o.close()
+
+
+def test_mobi_kernels_agree_bitwise(pkg, monkeypatch):
+    """The warp-specialised kernel evaluates the same expressions in the same order as the
+    one-thread-per-column kernel: the source fields must be identical to the last bit."""
+    case = pkg.synthetic.make_case(nt=37, imt=50, jmt=40, km=12, seed=11)
+    out = []
+    for ws in ("0", "1"):
+        monkeypatch.setenv("UVIC_B200_MOBI_WS", ws)
+        ctx = pkg.TracerContext(case, mobi=1)
+        ctx.load_state()
+        ctx.step(True)
+        out.append((ctx.fetch("src", (case.nsrc, case.jmt, case.km, case.imt)).copy(), ctx.download_t(+1).copy()))
+        ctx.close()
+    assert np.array_equal(out[0][0], out[1][0])
+    assert np.array_equal(out[0][1], out[1][1])

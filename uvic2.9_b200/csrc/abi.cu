@@ -200,7 +200,22 @@ int uvic_b200_create(const uvic_b200_dims *d, const uvic_b200_grid *g, const uvi
     DALLOC(fe_hydr, v.n3, st->fe_hydr);
     DALLOC(fe_atmdep, v.n2 * 12, st->fe_atmdep);
     DALLOC(dnswr, v.n2, nullptr); DALLOC(aice, v.n2, nullptr); DALLOC(hice, v.n2, nullptr); DALLOC(hsno, v.n2, nullptr);
-    DALLOC(co2_star, v.n3, nullptr); DALLOC(co2_omega, v.n3, nullptr);
+    DALLOC(mobi_pre, (size_t)v.n3 * MOBI_NPRE, nullptr);
+    DALLOC(mobi_day, v.n2, nullptr);
+    {
+      // depth dependence of the benthic denitrification fractionation (09/mom/mobi.F:1062): host libm exp, time invariant
+      std::vector<double> eb(km);
+      for (int k = 0; k < km; k++) eb[k] = ((const MobiPar *)par->mobi_par)->eps_bdeni0 * exp(-2.5e-6 * g->zt[k]);
+      DALLOC(mobi_epsbd, km, eb.data());
+      // water columns of the owned rows, deepest first (stable, so equal depths keep the i-fastest order)
+      std::vector<int> cols;
+      for (int jj = v.jlo - v.jbase; jj <= v.jhi - v.jbase; jj++)
+        for (int i = 1; i < imt - 1; i++)
+          if (st->kmt[i + (size_t)imt * jj] > 0) cols.push_back(i + imt * jj);
+      std::stable_sort(cols.begin(), cols.end(), [&](int a, int b) { return st->kmt[a] > st->kmt[b]; });
+      v.mobi_ncols = (int)cols.size();
+      IALLOC(mobi_cols, cols.size(), cols.data());
+    }
     CK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->mobi_event, cudaEventDisableTiming));
@@ -334,6 +349,14 @@ int uvic_b200_rotate(uvic_b200_ctx *ctx) {
 // launch MOBI on the side stream; the main stream waits for it right before k_update
 static void fork_mobi(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
   if (!ctx->par.mobi || ctx->mobi_inflight) return;
+  if (ctx->prof_on) {
+    // per-kernel timing: run MOBI in line so that no two kernels share the SMs and every
+    // CUDA-event interval is the duration of exactly one kernel
+    launch_mobi(ctx, si);
+    cudaEventRecord(ctx->mobi_event, ctx->stream);
+    ctx->mobi_inflight = true;
+    return;
+  }
   cudaEventRecord(ctx->fork_event, ctx->stream);
   cudaStreamWaitEvent(ctx->stream2, ctx->fork_event, 0);
   cudaStream_t main_stream = ctx->stream;

@@ -2,14 +2,14 @@
 // O_mobi, O_mobi_alk/_caco3/_o2/_nitrogen/_nitrogen_15/_silicon/_iron, O_carbon,
 // O_carbon_13, O_carbon_14).
 //
-//   k_mobi_co2     co2calc_SWS + drtsafe + ta_iter_SWS (09/common/co2calc.F), one thread
-//                  per ocean cell.  The carbonate solve depends only on T, S, DIC, ALK of
-//                  the cell, so it is lifted out of the column loop of mobi_driver
-//                  (09/mom/mobi.F:768-772) and run at full cell parallelism; it hands
-//                  CO2* and Omega_calcite to the column kernel.
-//   k_mobi_column  the column prologue of tracer (09/mom/tracer.F:310-545), mobi_driver
-//                  (09/mom/mobi.F:519-1483) and mobi_src (:1485-3313), one thread per
-//                  water column, i fastest so the 37 tracer reads of a level coalesce.
+//   k_mobi_light   day fraction, incoming solar and the light at the top of every level
+//                  (09/mom/tracer.F:370-390, 09/mom/mobi.F:795-812), one thread per column.
+//   k_mobi_cell    everything per cell that does not depend on the sinking chain, one thread
+//                  per ocean cell: co2calc_SWS + drtsafe + ta_iter_SWS (09/common/co2calc.F),
+//                  AOU, rate factors, the Evans-Parslow integrals, denitrification switches.
+//   k_mobi_column  mobi_driver (09/mom/mobi.F:519-1483) and the Euler sub-steps of mobi_src
+//                  (:2148-3313), one thread per water column (columns sorted by depth).
+//   k_mobi_ws      the same, warp specialised: 8 warps share 32 columns (small grids).
 //                  The reference's three k-loops are fused: loops 2 and 3 of mobi_driver
 //                  (:1301-1400) only touch level-k quantities, so running them directly
 //                  after level k of loop 1 performs the same operations in the same order
@@ -20,6 +20,7 @@
 // and the nbio Euler sub-steps are serial in time, so the parallel axis is the column.
 #include "ctx.h"
 #include "mobi_par.h"
+#include <stdlib.h>
 
 #define TRCMIN 5e-12        // 09/mom/mobi.h:199
 #define RN15STD 0.0036765   // 09/mom/mobi.h
@@ -173,7 +174,71 @@ __device__ void co2calc_sws(double t, double s, double dic_in, double ta_in, dou
   co2star_out = co2star / permil;
 }
 
-__global__ void __launch_bounds__(128) k_mobi_co2(const DevView v) {
+// ------------------------------------------------------------------------------------
+// Pre-pass.  Everything mobi_driver / mobi_src evaluate per level that does NOT depend
+// on the sinking chain (the export of the level above) is a function of the tau-1 inputs
+// alone and is computed here at full parallelism, leaving only the nbio Euler sub-steps
+// and the export chain to the column kernels.
+// ------------------------------------------------------------------------------------
+enum MobiPre {
+  PR_AC13B = 0, PR_DISSK1, PR_CAPR, PR_BCT, PR_BCTZ, PR_NUD, PR_AOU8, PR_O2FLAG, PR_AVEJ, PR_AVEJ_D, PR_AVEJ_DIAT,
+  PR_FO2, PR_P099, PR_LNO3A, PR_LNO3B, PR_GL, PR_N
+};
+static_assert(PR_N == MOBI_NPRE, "mobi_pre field count");
+
+// k_mobi_light: one thread per water column.  Day fraction and incoming solar
+// (09/mom/tracer.F:370-390), then the light at the top of every level: the attenuation by the
+// plankton and calcite of the levels above uses their tau-1 inputs only (09/mom/mobi.F:795-812).
+__global__ void __launch_bounds__(128) k_mobi_light(const DevView v, double declin) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int ni = v.imt - 2, nrow = v.jhi - v.jlo + 1;
+  if (idx >= (long long)ni * nrow) return;
+  int i = (int)(idx % ni) + 2;
+  int j = (int)(idx / ni) + v.jlo;
+  const int kmx = v.kmt[X2(i, j)];
+  if (kmx <= 0) return;
+  const MobiPar *__restrict__ P = v.mobi_par;
+  const int *__restrict__ ix = v.mobi_idx;
+  const double pi = 3.14159265358979323846;  // atan(1.0)*4.0 in FP64
+  const double radian = 360. / (2. * pi);
+  double lat = v.tlat[X2(i, j)];
+  double rctheta = fmax(-1.5, fmin(1.5, lat / radian - declin));
+  double cr = cos(rctheta);
+  rctheta = P->kw / sqrt(1. - (1. - cr * cr) / (1.33 * 1.33));
+  double dayfrac = fmin(1., -tan(lat / radian) * tan(declin));
+  dayfrac = fmax(1e-12, acos(fmax(-1., dayfrac)) / pi);
+  double swr = P->tap * v.dnswr[X2(i, j)] * 1e-3 * (1. + v.aice[X2(i, j)] * (exp(-P->ki * (v.hice[X2(i, j)] + v.hsno[X2(i, j)])) - 1.));
+  v.mobi_day[X2(i, j)] = dayfrac;
+  const long long n3 = v.n3;
+  const double *__restrict__ phyt = v.t_m1 + (long long)(ix[IX_TR + V_PHYT] - 1) * n3;
+  const double *__restrict__ diaz = v.t_m1 + (long long)(ix[IX_TR + V_DIAZ] - 1) * n3;
+  const double *__restrict__ diat = v.t_m1 + (long long)(ix[IX_TR + V_DIAT] - 1) * n3;
+  const double *__restrict__ caco3 = v.t_m1 + (long long)(ix[IX_TR + V_CACO3] - 1) * n3;
+  double phin = 0.0, caco3in = 0.0;
+  for (int k = 1; k <= kmx; k++) {
+    const long long c = X3(i, k, j);
+    const double dztk = v.dzt[k - 1];
+    swr = swr * exp(-P->kc * phin - P->kc_c * caco3in);
+    phin = fmax(phyt[c], TRCMIN) * dztk + fmax(diaz[c], TRCMIN) * dztk + fmax(diat[c], TRCMIN) * dztk;
+    caco3in = caco3in + caco3[c] * dztk;
+    v.mobi_pre[(long long)PR_GL * n3 + c] = swr * exp(P->ztt[k - 1] * rctheta);
+  }
+}
+
+// Evans & Parslow daily-mean light-limited growth (09/mom/mobi.F:1984-2003), one species
+__device__ __forceinline__ double evans_parslow(double gl_x, double gd, double f1, double kirr, double dzt) {
+  double u1 = fmax(gl_x / gd, 1.e-6), u2 = u1 * f1;
+  double phi1 = log(u1 + sqrt(1. + u1 * u1)) - (sqrt(1. + u1 * u1) - 1.) / u1;
+  double phi2 = log(u2 + sqrt(1. + u2 * u2)) - (sqrt(1. + u2 * u2) - 1.) / u2;
+  return gd * (phi1 - phi2) / (-kirr * dzt);
+}
+
+// k_mobi_cell: one thread per ocean cell.  co2calc_SWS (09/common/co2calc.F, called from
+// mobi_driver :768-772), O2 saturation -> AOU (09/mom/tracer.F:457-476), the temperature and
+// oxygen dependent rate factors (09/mom/mobi.F:775-835), the pre-loop light harvesting and
+// Evans-Parslow integrals of mobi_src (:1928-2003), and the oxygen / nitrate switches of
+// the denitrification terms (:1035-1046, 1301-1322).
+__global__ void __launch_bounds__(128) k_mobi_cell(const DevView v) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int ni = v.imt - 2, nrow = v.jhi - v.jlo + 1;
   if (idx >= (long long)ni * v.km * nrow) return;
@@ -182,17 +247,79 @@ __global__ void __launch_bounds__(128) k_mobi_co2(const DevView v) {
   int k = (int)(r % v.km) + 1;
   int j = (int)(r / v.km) + v.jlo;
   if (k > v.kmt[X2(i, j)]) return;
+  const MobiPar *__restrict__ P = v.mobi_par;
   const int *ix = v.mobi_idx;
-  long long c = X3(i, k, j);
-  double t_in = v.t_m1[c + (long long)(ix[IX_ITEMP] - 1) * v.n3];
-  double s_in = 1.e3 * v.t_m1[c + (long long)(ix[IX_ISALT] - 1) * v.n3] + 35.0;
-  double dic_in = v.t_m1[c + (long long)(ix[IX_TR + V_DIC] - 1) * v.n3];
-  double alk_in = v.t_m1[c + (long long)(ix[IX_IALK] - 1) * v.n3];
-  double depth = v.zt[k - 1] / 100.;
-  double co2star, omega_c;
-  co2calc_sws(t_in, s_in, dic_in, alk_in, depth, co2star, omega_c);
-  v.co2_star[c] = co2star;
-  v.co2_omega[c] = omega_c;
+  const long long n3 = v.n3;
+  const long long c = X3(i, k, j);
+#define TIN(slot) v.t_m1[c + (long long)(ix[slot] - 1) * n3]
+  const double t_in = TIN(IX_ITEMP);
+  const double s_in = 1.e3 * TIN(IX_ISALT) + 35.0;
+  const double dic_in = TIN(IX_TR + V_DIC);
+  const double alk_in = TIN(IX_IALK);
+  const double o2_in = TIN(IX_IO2) * 1000.;
+  double *__restrict__ pre = v.mobi_pre + c;
+  double co2star, Omega_c;
+  co2calc_sws(t_in, s_in, dic_in, alk_in, v.zt[k - 1] / 100., co2star, Omega_c);
+  {
+    double ac13_DIC_aq = -1.0512994e-4 * t_in + 1.011765;
+    double ac13_aq_POC = -0.017 * log10(fmin(fmax(co2star * 1000., 2.), 74.)) + 1.0034;
+    pre[(long long)PR_AC13B * n3] = ac13_aq_POC / ac13_DIC_aq;
+    pre[(long long)PR_DISSK1 * n3] = P->dissk0 * fmax(0., (1. - Omega_c));
+    pre[(long long)PR_CAPR * n3] = P->caprmax * fmax(0., (Omega_c - 1.) / (P->kcapr + Omega_c - 1.));
+  }
+  // oxygen saturation -> AOU for the ligand parameterisation
+  double aou_in;
+  {
+    double f1 = log((298.15 - t_in) / (273.15 + t_in));
+    double f2 = f1 * f1, f3 = f2 * f1, f4 = f3 * f1, f5 = f4 * f1;
+    double o2sat = exp(2.00907 + 3.22014 * f1 + 4.05010 * f2 + 4.94457 * f3 - 2.56847E-1 * f4 + 3.88767 * f5 +
+                       s_in * (-6.24523e-3 - 7.37614e-3 * f1 - 1.03410e-2 * f2 - 8.17083E-3 * f3) - 4.88682E-7 * s_in * s_in);
+    o2sat = o2sat / 22391.6 * 1000.0 * 1000.;
+    aou_in = o2sat - o2_in;
+  }
+  const double bct = pow(P->bbio, (P->cbio * t_in));
+  const double fo2 = tanh(0.22 * fmax(o2_in, 0.));
+  pre[(long long)PR_BCT * n3] = bct;
+  pre[(long long)PR_BCTZ * n3] = (0.5 * (tanh(o2_in - 8.) + 1)) * bct;   // same bbio**(cbio*t) value (:830-835)
+  pre[(long long)PR_NUD * n3] = P->nud0 * (0.6 + 0.4 * fo2);
+  pre[(long long)PR_FO2 * n3] = fo2;
+  pre[(long long)PR_AOU8 * n3] = pow(fmax(aou_in, 40.), 0.8);
+  pre[(long long)PR_O2FLAG * n3] = tanh(fmax(o2_in, 0.));
+  {
+    const double tno3 = fmax(TIN(IX_TR + V_NO3), TRCMIN);   // tnpzd(k,ino3) after the clip of mobi_src
+    pre[(long long)PR_P099 * n3] = pow(0.99, (fmax(o2_in, TRCMIN) - fmax(tno3, TRCMIN)));
+    pre[(long long)PR_LNO3A * n3] = 0.5 * tanh(tno3 * 10 - 5.0);
+    pre[(long long)PR_LNO3B * n3] = 0.5 * tanh(tno3 - 2.5);
+  }
+  // light harvesting and daily growth integrals on the clipped inputs
+  {
+    const double bphyt = fmax(TIN(IX_TR + V_PHYT), TRCMIN), bdiaz = fmax(TIN(IX_TR + V_DIAZ), TRCMIN);
+    const double bdiat = fmax(TIN(IX_TR + V_DIAT), TRCMIN), bcaco3 = fmax(TIN(IX_TR + V_CACO3), TRCMIN);
+    const double bdfe = fmax(TIN(IX_TR + V_DFE), TRCMIN);
+    const double gl = pre[(long long)PR_GL * n3], dayfrac = v.mobi_day[X2(i, j)], dzt = v.dzt[k - 1];
+    double p1 = fmin(bphyt, P->pmax), p2 = fmax(0.0, bphyt - P->pmax);
+    double kfevar = (P->kfemin * p1 + P->kfemax * p2) / (p1 + p2);
+    double deffe = bdfe / (kfevar + bdfe);
+    double thetamax = P->thetamaxlo + (P->thetamaxhi - P->thetamaxlo) * deffe;
+    double alpha_O = P->alphamin + (P->alphamax - P->alphamin) * deffe;
+    double gl_O = gl * thetamax * alpha_O;
+    p1 = fmin(bdiat, P->pmax_Diat);
+    p2 = fmax(0.0, bdiat - P->pmax_Diat);
+    double kfevar_Diat = (P->kfemin_Diat * p1 + P->kfemax_Diat * p2) / (p1 + p2);
+    double deffe_Diat = bdfe / (kfevar_Diat + bdfe);
+    double gl_Diat = gl * (P->thetamaxlo + (P->thetamaxhi - P->thetamaxlo) * deffe_Diat) * (P->alphamin + (P->alphamax - P->alphamin) * deffe_Diat);
+    double deffe_D = bdfe / (P->kfe_D + bdfe);
+    double gl_D = gl * (P->thetamaxlo + (P->thetamaxhi - P->thetamaxlo) * deffe_D) * (P->alphamin + (P->alphamax - P->alphamin) * deffe_D);
+    double kirr = -P->kw - P->kc * (bphyt + bdiaz + bdiat) - P->kc_c * bcaco3;
+    double f1 = exp(kirr * dzt);
+    double jmax = P->abio_P * bct * deffe;
+    pre[(long long)PR_AVEJ * n3] = evans_parslow(gl_O, jmax * dayfrac, f1, kirr, dzt);
+    double jmax_D = fmax(0., P->abio_P * (bct - P->dbct_D) * deffe_D) * P->jdiar;
+    pre[(long long)PR_AVEJ_D * n3] = evans_parslow(gl_D, fmax(1.e-14, jmax_D * dayfrac), f1, kirr, dzt);
+    double jmax_Diat = P->abiodiat * bct * deffe_Diat;
+    pre[(long long)PR_AVEJ_DIAT * n3] = evans_parslow(gl_Diat, jmax_Diat * dayfrac, f1, kirr, dzt);
+  }
+#undef TIN
 }
 
 // ------------------------------------------------------------------------------------
@@ -201,19 +328,18 @@ __global__ void __launch_bounds__(128) k_mobi_co2(const DevView v) {
 // ------------------------------------------------------------------------------------
 struct SrcIO {
   // in
-  double gl, bct, impo, dzt, impo_phos, dayfrac, wwd, nud, impocaco3, wwc, dissk1, impoopl, wwo, opl_disk1, nudop, nudon, bctz;
-  double rn15impo, rc13impo, ac13b, rcaco3c13impo, impofe, o2, aou, capr;
+  double bct, impo, impo_phos, wwd, nud, impocaco3, wwc, dissk1, impoopl, wwo, opl_disk1, nudop, nudon, bctz;
+  double rn15impo, rc13impo, ac13b, rcaco3c13impo, impofe, capr, avej, avej_D, avej_Diat, o2flag, aou8;
   // out
   double nfix, expo, expo_phos, calpro, dissl, expocaco3, expoopl, rn15expo, rc13expo, rcaco3c13expo, expofe;
 };
 
 #define CL15(x) fmax(fmin((x), 2. * RN15STD / (1 + RN15STD)), RN15STD / (1 + RN15STD) / 2.)
 #define CL13(x) fmax(fmin((x), 2. * RC13STD / (1 + RC13STD)), 0.5 * RC13STD / (1 + RC13STD))
-
 __device__ __forceinline__ void mobi_src(const MobiPar *__restrict__ P, int nbio, double dtbio, double (&b)[MOBI_NVAR], double (&clip)[MOBI_NVAR], SrcIO &io) {
   const double gamma1 = P->gamma1, redptn = P->redptn, redctn = P->redctn, redntp = P->redntp, diazntp = P->diazntp;
   const double diazptn = P->diazptn, dfr = P->dfr, pfr = P->pfr, dfrt = P->dfrt, geZ = P->geZ, rfeton = P->rfeton;
-  const double bct = io.bct, dzt = io.dzt, gl = io.gl;
+  const double bct = io.bct;
   // ratios from the raw inputs (:1781-1784)
   double ptn_P = b[V_PHYT_PHOS] / b[V_PHYT];
   double ptn_detr = b[V_DETR_PHOS] / b[V_DETR];
@@ -231,52 +357,15 @@ __device__ __forceinline__ void mobi_src(const MobiPar *__restrict__ P, int nbio
     b[m] = fmax(b[m], TRCMIN);
     clip[m] = b[m];
   }
-  // iron-dependent light harvesting, pre-loop values (:1928-1952)
-  double p1 = fmin(b[V_PHYT], P->pmax), p2 = fmax(0.0, b[V_PHYT] - P->pmax);
-  double kfevar = (P->kfemin * p1 + P->kfemax * p2) / (p1 + p2);
-  double deffe = b[V_DFE] / (kfevar + b[V_DFE]);
-  double thetamax = P->thetamaxlo + (P->thetamaxhi - P->thetamaxlo) * deffe;
-  double alpha_O = P->alphamin + (P->alphamax - P->alphamin) * deffe;
-  double gl_O = gl * thetamax * alpha_O;
-  p1 = fmin(b[V_DIAT], P->pmax_Diat);
-  p2 = fmax(0.0, b[V_DIAT] - P->pmax_Diat);
-  double kfevar_Diat = (P->kfemin_Diat * p1 + P->kfemax_Diat * p2) / (p1 + p2);
-  double deffe_Diat = b[V_DFE] / (kfevar_Diat + b[V_DFE]);
-  double gl_Diat = gl * (P->thetamaxlo + (P->thetamaxhi - P->thetamaxlo) * deffe_Diat) * (P->alphamin + (P->alphamax - P->alphamin) * deffe_Diat);
-  double deffe_D = b[V_DFE] / (P->kfe_D + b[V_DFE]);
-  double gl_D = gl * (P->thetamaxlo + (P->thetamaxhi - P->thetamaxlo) * deffe_D) * (P->alphamin + (P->alphamax - P->alphamin) * deffe_D);
-  // photosynthesis after Evans & Parslow (:1954-2003)
-  double kirr = -P->kw - P->kc * (b[V_PHYT] + b[V_DIAZ] + b[V_DIAT]) - P->kc_c * b[V_CACO3];
-  double f1 = exp(kirr * dzt);
-  double avej, avej_D, avej_Diat;
-  {
-    double jmax = P->abio_P * bct * deffe;
-    double gd = jmax * io.dayfrac;
-    double u1 = fmax(gl_O / gd, 1.e-6), u2 = u1 * f1;
-    double phi1 = log(u1 + sqrt(1. + u1 * u1)) - (sqrt(1. + u1 * u1) - 1.) / u1;
-    double phi2 = log(u2 + sqrt(1. + u2 * u2)) - (sqrt(1. + u2 * u2) - 1.) / u2;
-    avej = gd * (phi1 - phi2) / (-kirr * dzt);
-    double jmax_D = fmax(0., P->abio_P * (bct - P->dbct_D) * deffe_D) * P->jdiar;
-    double gd_D = fmax(1.e-14, jmax_D * io.dayfrac);
-    u1 = fmax(gl_D / gd_D, 1.e-6);
-    u2 = u1 * f1;
-    phi1 = log(u1 + sqrt(1. + u1 * u1)) - (sqrt(1. + u1 * u1) - 1.) / u1;
-    phi2 = log(u2 + sqrt(1. + u2 * u2)) - (sqrt(1. + u2 * u2) - 1.) / u2;
-    avej_D = gd_D * (phi1 - phi2) / (-kirr * dzt);
-    double jmax_Diat = P->abiodiat * bct * deffe_Diat;
-    double gd_Diat = jmax_Diat * io.dayfrac;
-    u1 = fmax(gl_Diat / gd_Diat, 1.e-6);
-    u2 = u1 * f1;
-    phi1 = log(u1 + sqrt(1. + u1 * u1)) - (sqrt(1. + u1 * u1) - 1.) / u1;
-    phi2 = log(u2 + sqrt(1. + u2 * u2)) - (sqrt(1. + u2 * u2) - 1.) / u2;
-    avej_Diat = gd_Diat * (phi1 - phi2) / (-kirr * dzt);
-  }
+  // the pre-loop light harvesting and Evans-Parslow integrals (:1928-2003) come from k_mobi_cell
+  const double avej = io.avej, avej_D = io.avej_D, avej_Diat = io.avej_Diat;
+  double p1, p2, kfevar, deffe, kfevar_Diat, deffe_Diat, deffe_D;
   const double gmax = P->gbio * io.bctz;
   const double nupt = P->nupt0 * bct, nupt_D = P->nupt0_D * bct, nudt = P->nudt0 * bct;
   double nfixout = 0.0, expoout = 0.0, expo_phosout = 0.0, rn15expoout = 0.0, rc13expoout = 0.0, rcaco3c13expoout = 0.0;
   double calproout = 0.0, disslout = 0.0, expocaco3out = 0.0, expooplout = 0.0, expofeout = 0.0;
-  const double o2flag = tanh(fmax(io.o2, 0.));  // (:2267) loop invariant
-  const double aou8 = pow(fmax(io.aou, 40.), 0.8);
+  const double o2flag = io.o2flag;  // tanh(max(o2,0)) (:2267) and max(aou,40)**0.8 (:2263): loop invariant, from k_mobi_cell
+  const double aou8 = io.aou8;
 
   for (int n = 1; n <= nbio; n++) {
     const double biopo4 = b[V_PO4], biophyt = b[V_PHYT], biophyt_phos = b[V_PHYT_PHOS], biozoop = b[V_ZOOP], biodetr = b[V_DETR];
@@ -537,32 +626,20 @@ __device__ __forceinline__ void mobi_src(const MobiPar *__restrict__ P, int nbio
 #undef fl
 }
 
-__global__ void __launch_bounds__(32) k_mobi_column(const DevView v, int mi, double declin, int nbio, double dtbio, double rdtts,
-                                                     double rnbio) {
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  int ni = v.imt - 2, nrow = v.jhi - v.jlo + 1;
-  if (idx >= (long long)ni * nrow) return;
-  int i = (int)(idx % ni) + 2;
-  int j = (int)(idx / ni) + v.jlo;
-  const int kmx = v.kmt[X2(i, j)];
-  if (kmx <= 0) return;
+__global__ void __launch_bounds__(32) k_mobi_column(const DevView v, int mi, int nbio, double dtbio, double rdtts, double rnbio) {
+  // ocean columns of the owned rows, sorted by depth so that the 32 columns of a warp run
+  // the same number of levels
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= v.mobi_ncols) return;
+  const int col = v.mobi_cols[idx];
+  const int i = col % v.imt + 1, j = col / v.imt + v.jbase;
+  const int kmx = v.kmt[col];
   const MobiPar *__restrict__ P = v.mobi_par;
   const int *__restrict__ ix = v.mobi_idx;
   const double redctn = P->redctn;
-  const double pi = 3.14159265358979323846;  // atan(1.0)*4.0 in FP64
-  const double radian = 360. / (2. * pi);
 
-  // day fraction and incoming solar (09/mom/tracer.F:370-390)
-  double lat = v.tlat[X2(i, j)];
-  double rctheta = fmax(-1.5, fmin(1.5, lat / radian - declin));
-  double cr = cos(rctheta);
-  rctheta = P->kw / sqrt(1. - (1. - cr * cr) / (1.33 * 1.33));
-  double dayfrac = fmin(1., -tan(lat / radian) * tan(declin));
-  dayfrac = fmax(1e-12, acos(fmax(-1., dayfrac)) / pi);
-  double swr = P->tap * v.dnswr[X2(i, j)] * 1e-3 * (1. + v.aice[X2(i, j)] * (exp(-P->ki * (v.hice[X2(i, j)] + v.hsno[X2(i, j)])) - 1.));
-
-  double expo = 0.0, expo_phos = 0.0, phin = 0.0, rn15expo = 0.0, rc13expo = 0.0, rcaco3c13expo = 0.0;
-  double expofe = 0.0, caco3in = 0.0, expocaco3 = 0.0, expoopl = 0.0;
+  double expo = 0.0, expo_phos = 0.0, rn15expo = 0.0, rc13expo = 0.0, rcaco3c13expo = 0.0;
+  double expofe = 0.0, expocaco3 = 0.0, expoopl = 0.0;
   const long long n3 = v.n3;
   double b[MOBI_NVAR], clip[MOBI_NVAR];
   const int s_alk = ix[IX_ISALK], s_o2 = ix[IX_ISO2], s_c14 = ix[IX_ISC14];
@@ -573,55 +650,38 @@ __global__ void __launch_bounds__(32) k_mobi_column(const DevView v, int mi, dou
     // gather (tracer.F:393-503)
 #pragma unroll
     for (int m = 0; m < MOBI_NVAR; m++) b[m] = v.t_m1[c + (long long)(ix[IX_TR + m] - 1) * n3];
-    const double t_in = v.t_m1[c + (long long)(ix[IX_ITEMP] - 1) * n3];
     const double o2_in = v.t_m1[c + (long long)(ix[IX_IO2] - 1) * n3] * 1000.;
-    const double s_in = 1.e3 * v.t_m1[c + (long long)(ix[IX_ISALT] - 1) * n3] + 35.0;
     const double dic_in = b[V_DIC];
     const double c14_in = v.t_m1[c + (long long)(ix[IX_IC14] - 1) * n3];
     const double sgb = v.sg_bathy[XIJK(i, j, k)];
-    // oxygen saturation -> AOU for the ligand parameterisation (tracer.F:457-476)
-    double aou_in;
-    {
-      double f1 = log((298.15 - t_in) / (273.15 + t_in));
-      double f2 = f1 * f1, f3 = f2 * f1, f4 = f3 * f1, f5 = f4 * f1;
-      double o2sat = exp(2.00907 + 3.22014 * f1 + 4.05010 * f2 + 4.94457 * f3 - 2.56847E-1 * f4 + 3.88767 * f5 +
-                         s_in * (-6.24523e-3 - 7.37614e-3 * f1 - 1.03410e-2 * f2 - 8.17083E-3 * f3) - 4.88682E-7 * s_in * s_in);
-      o2sat = o2sat / 22391.6 * 1000.0 * 1000.;
-      aou_in = o2sat - o2_in;
-    }
+    const double *__restrict__ pre = v.mobi_pre + c;
     // ---- mobi_driver, level k of loop 1 (mobi.F:763-1289) ----
     SrcIO io;
     io.rn15impo = rn15expo;
-    const double co2star = v.co2_star[c], Omega_c = v.co2_omega[c];
-    double ac13_DIC_aq = -1.0512994e-4 * t_in + 1.011765;
-    double ac13_aq_POC = -0.017 * log10(fmin(fmax(co2star * 1000., 2.), 74.)) + 1.0034;
-    io.ac13b = ac13_aq_POC / ac13_DIC_aq;
+    io.ac13b = pre[(long long)PR_AC13B * n3];
     io.rc13impo = rc13expo * dztrk;
     io.rcaco3c13impo = rcaco3c13expo * dztrk;
-    io.dissk1 = P->dissk0 * fmax(0., (1. - Omega_c));
-    io.capr = P->caprmax * fmax(0., (Omega_c - 1.) / (P->kcapr + Omega_c - 1.));
+    io.dissk1 = pre[(long long)PR_DISSK1 * n3];
+    io.capr = pre[(long long)PR_CAPR * n3];
     io.opl_disk1 = P->opl_disk0;
-    swr = swr * exp(-P->kc * phin - P->kc_c * caco3in);
-    phin = fmax(b[V_PHYT], TRCMIN) * dztk + fmax(b[V_DIAZ], TRCMIN) * dztk + fmax(b[V_DIAT], TRCMIN) * dztk;
-    caco3in = caco3in + b[V_CACO3] * dztk;
     io.impocaco3 = expocaco3 * dztrk;
-    io.gl = swr * exp(P->ztt[k - 1] * rctheta);
     io.impo = expo * dztrk;
     io.impo_phos = expo_phos * dztrk;
     io.impofe = expofe * dztrk;
-    io.bct = pow(P->bbio, (P->cbio * t_in));
+    io.bct = pre[(long long)PR_BCT * n3];
     io.impoopl = expoopl * dztrk;
-    io.bctz = (0.5 * (tanh(o2_in - 8.) + 1)) * io.bct;   // same bbio**(cbio*t) value (:830-835)
-    io.nud = P->nud0 * (0.6 + 0.4 * tanh(0.22 * fmax(o2_in, 0.)));
+    io.bctz = pre[(long long)PR_BCTZ * n3];
+    io.nud = pre[(long long)PR_NUD * n3];
     io.nudon = P->nudon0;
     io.nudop = P->nudop0;
-    io.dzt = dztk;
-    io.dayfrac = dayfrac;
     io.wwd = P->wd[k - 1];
     io.wwc = P->wc[k - 1];
     io.wwo = P->wo[k - 1];
-    io.o2 = o2_in;
-    io.aou = aou_in;
+    io.avej = pre[(long long)PR_AVEJ * n3];
+    io.avej_D = pre[(long long)PR_AVEJ_D * n3];
+    io.avej_Diat = pre[(long long)PR_AVEJ_DIAT * n3];
+    io.o2flag = pre[(long long)PR_O2FLAG * n3];
+    io.aou8 = pre[(long long)PR_AOU8 * n3];
     mobi_src(P, nbio, dtbio, b, clip, io);   // b: increments; clip: the clipped tnpzd(k,:)
     // rates (mobi.F:880-895)
 #pragma unroll
@@ -643,8 +703,8 @@ __global__ void __launch_bounds__(32) k_mobi_column(const DevView v, int mi, dou
     const double tno3 = clip[V_NO3], tdin15 = clip[V_DIN15];
     double no3flag = 0.5 + fsign(0.5, tno3 - TRCMIN);
     double din15flag = 0.5 + fsign(0.5, tdin15 - TRCMIN);
-    double lno3 = 0.5 * tanh(tno3 * 10 - 5.0);
-    double sg_bdeni = (0.06 + 0.19 * pow(0.99, (fmax(o2_in, TRCMIN) - fmax(tno3, TRCMIN)))) * fmax(expo * sgb, TRCMIN) * redctn * 1.e3;
+    double lno3 = pre[(long long)PR_LNO3A * n3];
+    double sg_bdeni = (0.06 + 0.19 * pre[(long long)PR_P099 * n3]) * fmax(expo * sgb, TRCMIN) * redctn * 1.e3;
     sg_bdeni = fmin(sg_bdeni, sgb * expo);
     sg_bdeni = fmax(sg_bdeni, 0.);
     sg_bdeni = sg_bdeni * (0.5 + lno3) * no3flag * din15flag;
@@ -653,7 +713,7 @@ __global__ void __launch_bounds__(32) k_mobi_column(const DevView v, int mi, dou
     double rno3 = fmax(tdin15, TRCMIN * RN15STD / (1 + RN15STD)) / fmax(tno3 - tdin15, TRCMIN * RN15STD / (1 + RN15STD));
     rno3 = fmin(rno3, 2. * RN15STD);
     rno3 = fmax(rno3, RN15STD / 2.);
-    double eps_bdeni = P->eps_bdeni0 * exp(-2.5e-6 * (v.zt[k - 1]));
+    double eps_bdeni = v.mobi_epsbd[k - 1];
     double bbdeni = rno3 - eps_bdeni * rno3 / 1000.;
     b[V_DIN15] = b[V_DIN15] + rn15expo * sgb * expo - bbdeni / (1 + bbdeni) * sg_bdeni;
     // sediment carbon oxidation (Flogel 2011 / Somes 2021) and iron release (Dale 2015) (:1076-1110)
@@ -690,9 +750,9 @@ __global__ void __launch_bounds__(32) k_mobi_column(const DevView v, int mi, dou
     expoopl = expoopl * dztk;
 
     // ---- level k of loop 2: O2, water-column denitrification, ALK (:1301-1366) ----
-    double fo2 = tanh(0.22 * fmax(o2_in, 0.));
+    double fo2 = pre[(long long)PR_FO2 * n3];
     double so2 = dic_npzd_sms * P->redotc + nfix * rnbio * 1.25e-3;
-    lno3 = 0.5 * tanh(tno3 - 2.5);
+    lno3 = pre[(long long)PR_LNO3B * n3];
     double wcdeni = 800. * no3flag * so2 * (1.0 - fo2) * (0.5 + lno3) * din15flag;
     wcdeni = fmax(wcdeni, 0.);
     b[V_NO3] = b[V_NO3] - wcdeni;
@@ -731,6 +791,690 @@ __global__ void __launch_bounds__(32) k_mobi_column(const DevView v, int mi, dou
   }
 }
 
+
+// ------------------------------------------------------------------------------------
+// k_mobi_ws: the same column physics, warp specialised.  With few water columns (the
+// 100x100 grid has ~7000) one thread per column leaves the SMs almost empty and the
+// kernel time is the latency of one column's serial instruction chain.  Here a CTA of
+// 8 warps owns 32 columns (lane = column) and every warp executes a different slice of
+// the Euler sub-step for those columns -- no divergence inside a warp -- exchanging the
+// rates through shared memory:
+//   stage 1  every warp derives its share of the process rates / isotope factors from the
+//            state at the start of the sub-step                 (09/mom/mobi.F:2150-2548)
+//   stage 2  every warp advances the state variables it owns and re-evaluates their
+//            flags                                             (:2552-2777, 3175-3251)
+// Each expression is evaluated exactly as in mobi_src above (same operands, same order), so
+// the two kernels agree bit for bit.  The level epilogue of mobi_driver (:880-1400) is split
+// the same way.  The export chain (expo -> impo of the next level) stays serial in k.
+// ------------------------------------------------------------------------------------
+enum WsRate {
+  R_npp = 0, R_dopupt, R_npp_D, R_no3upt_D, R_dopupt_D, R_fcassim, R_npp_Diat, R_dopupt_Diat, R_sipr0, R_recy_don, R_fcrecy,
+  R_graz, R_graz_Z, R_graz_Det, R_graz_D, R_graz_Diat, R_morp, R_morpt, R_morp_D, R_morpt_D, R_morp_Diat, R_morpt_Diat, R_morz,
+  R_remi, R_expo, R_expo_phos, R_recy_dop, R_dissl, R_expocaco3, R_opldis, R_expoopl, R_remife, R_expofe, R_dig, R_dig_P, R_dig_Z,
+  R_dig_Det, R_dig_Diat, R_dig_D, R_excr, R_sf, R_sf_P, R_sf_Z, R_sf_Det, R_sf_Diat, R_sf_D, R_sf_phos, R_nr_excr_D, R_calpro,
+  R_feprime, R_fecol, R_pw58, R_fcexcr, R_fcnfix, R_rtdic13, R_rtcaco3c13, R_GM15ptn, R_rtphytn15, R_rtdiatn15, R_rtzoopn15,
+  R_rtdetrn15, R_rtdiazn15, R_fcnpp, R_rtphytc13, R_rtdiatc13, R_rtzoopc13, R_rtdetrc13, R_rtdoc13, R_rtdiazc13, R_N
+};
+enum WsLev {
+  // export chain carried from level to level (09/mom/mobi.F:1280-1288)
+  X_expo = 0, X_expo_phos, X_rn15expo, X_rc13expo, X_rcaco3c13expo, X_expofe, X_expocaco3, X_expoopl,
+  // per-level sums over the sub-steps (the *out arguments of mobi_src, :2762-2777)
+  S_expo, S_expo_phos, S_rn15expo, S_rc13expo, S_rcaco3c13expo, S_expofe, S_expocaco3, S_expoopl, S_calpro, S_dissl, S_nfix,
+  // phytoplankton / detritus P:N ratios, double buffered over the sub-steps, and their flags (:1781-1784, 1814-1890)
+  L_ptn_P0, L_ptn_P1, L_ptn_detr0, L_ptn_detr1, L_sf_P_phosflag, L_sf_detr_phosflag,
+  // epilogue exchange
+  L_wcdeni, L_bwfrac, L_N
+};
+struct WsSm {
+  double B[MOBI_NVAR][32];   // state at the start of the sub-step
+  double F[MOBI_NVAR][32];   // flags (1.0 / 0.0)
+  double C[MOBI_NVAR][32];   // clipped inputs tnpzd(k,:)
+  double R[R_N][32];
+  double L[L_N][32];
+};
+#define WS_WARPS 8
+
+__global__ void __launch_bounds__(32 * WS_WARPS) k_mobi_ws(const DevView v, int mi, int nbio, double dtbio, double rdtts, double rnbio) {
+  extern __shared__ __align__(16) unsigned char ws_raw[];
+  WsSm &sm = *reinterpret_cast<WsSm *>(ws_raw);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int cidx = blockIdx.x * 32 + lane;
+  const bool valid = cidx < v.mobi_ncols;
+  const int col = valid ? v.mobi_cols[cidx] : 0;
+  const int i = col % v.imt + 1, j = col / v.imt + v.jbase;
+  const int kmx = valid ? v.kmt[col] : 0;
+  const int kmax = v.kmt[v.mobi_cols[blockIdx.x * 32]];   // columns are sorted by depth, deepest first
+  const MobiPar *__restrict__ P = v.mobi_par;
+  const int *__restrict__ ix = v.mobi_idx;
+  const long long n3 = v.n3;
+  const double gamma1 = P->gamma1, redptn = P->redptn, redctn = P->redctn, redntp = P->redntp, diazntp = P->diazntp;
+  const double diazptn = P->diazptn, dfr = P->dfr, pfr = P->pfr, dfrt = P->dfrt, geZ = P->geZ, rfeton = P->rfeton;
+  const double rnd = redntp / diazntp;
+#define SB(m) sm.B[m][lane]
+#define SF(m) sm.F[m][lane]
+#define SC(m) sm.C[m][lane]
+#define SR(x) sm.R[R_##x][lane]
+#define SL(x) sm.L[x][lane]
+  if (w == 0) {
+#pragma unroll
+    for (int q = X_expo; q <= X_expoopl; q++) SL(q) = 0.0;
+  }
+  // per-warp accumulators of the *out sums
+  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0, acc4 = 0.0, acc5 = 0.0, acc6 = 0.0;
+  // epilogue carry of warp 1 (finished after the barrier, see E3)
+  double e3_no3 = 0.0, e3_din15 = 0.0;
+  bool e3_pending = false;
+  long long e3_c = 0;
+
+  for (int k = 1; k <= kmax; k++) {
+    const bool act = k <= kmx;
+    const long long c = X3(i, k, j);
+    const double dztk = v.dzt[k - 1], dztrk = v.dztr[k - 1];
+    const double *__restrict__ pre = v.mobi_pre + c;
+#define PRE(f) (act ? pre[(long long)(f) * n3] : 1.0)
+    // ---- E3 of the previous level (warp 1): water-column denitrification closes NO3, DIN15 and ALK ----
+    if (w == 1 && e3_pending) {
+      const double wcdeni = SL(L_wcdeni), bwfrac = SL(L_bwfrac);
+      v.src[e3_c + (long long)(ix[IX_SRC + V_NO3] - 1) * n3] = e3_no3 - wcdeni;
+      v.src[e3_c + (long long)(ix[IX_SRC + V_DIN15] - 1) * n3] = e3_din15 - bwfrac * wcdeni;
+      e3_pending = false;
+    }
+    // ---- P1: gather, flags from the raw inputs, clip (09/mom/tracer.F:393-503, mobi.F:1781-1926) ----
+    {
+      double raw[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int m = 4 * w + q;
+        raw[q] = act ? v.t_m1[c + (long long)(ix[IX_TR + m] - 1) * n3] : 1.0;
+        SF(m) = (raw[q] - TRCMIN >= 0.0) ? 1.0 : 0.0;
+        const double cl = fmax(raw[q], TRCMIN);
+        SB(m) = cl;
+        SC(m) = cl;
+      }
+      if (w == 0) {   // states 0..3: PO4, PHYT, PHYT_PHOS, ZOOP
+        const double ptn_P = raw[V_PHYT_PHOS] / raw[V_PHYT];
+        SL(L_ptn_P0) = ptn_P;
+        SL(L_sf_P_phosflag) = 0.5 + fsign(0.5, ptn_P - gamma1 * redptn);
+      }
+      if (w == 1) {   // states 4..7: DETR, DETR_PHOS, DIC, DIC13
+        const double ptn_detr = raw[V_DETR_PHOS - 4] / raw[V_DETR - 4];
+        SL(L_ptn_detr0) = ptn_detr;
+        SL(L_sf_detr_phosflag) = 0.5 + fsign(0.5, ptn_detr - gamma1 * redptn);
+      }
+    }
+    // level constants of this warp's role
+    const double bct = PRE(PR_BCT);
+    double lc0 = 0.0, lc1 = 0.0, lc2 = 0.0, lc3 = 0.0, lc4 = 0.0, lc5 = 0.0, lc6 = 0.0;
+    switch (w) {
+      case 0: lc0 = PRE(PR_AVEJ); break;
+      case 1: lc0 = PRE(PR_AVEJ_DIAT); break;
+      case 2: lc0 = P->gbio * PRE(PR_BCTZ); lc1 = PRE(PR_NUD); lc2 = PRE(PR_DISSK1); lc3 = PRE(PR_CAPR);
+              lc4 = P->wd[k - 1]; lc5 = P->wc[k - 1]; lc6 = P->wo[k - 1]; break;
+      case 3: lc0 = PRE(PR_AOU8); lc1 = PRE(PR_O2FLAG); break;
+      case 6: lc0 = PRE(PR_AC13B); break;
+      case 7: lc0 = PRE(PR_AVEJ_D); break;
+      default: break;
+    }
+    acc0 = acc1 = acc2 = acc3 = acc4 = acc5 = acc6 = 0.0;
+    __syncthreads();
+
+    for (int n = 1; n <= nbio; n++) {
+      const int par = (n - 1) & 1;
+      const double ptn_P = SL(L_ptn_P0 + par), ptn_detr = SL(L_ptn_detr0 + par);
+      // ================= stage 1: rates from the state at the start of the sub-step =================
+      switch (w) {
+        case 0: {
+          // phytoplankton growth (:2150-2206), NO3 assimilation fractionation (:2441-2452)
+          const double biophyt = SB(V_PHYT), biodfe = SB(V_DFE), biodop = SB(V_DOP), biopo4 = SB(V_PO4), biono3 = SB(V_NO3);
+          double p1 = fmin(biophyt, P->pmax), p2 = fmax(0.0, biophyt - P->pmax);
+          double k1n = (P->knmin * p1 + P->knmax * p2) / (p1 + p2);
+          double k1p_P = k1n * ptn_P;
+          double kfevar = (P->kfemin * p1 + P->kfemax * p2) / (p1 + p2);
+          double deffe = biodfe / (kfevar + biodfe);
+          double jmax = P->abio_P * bct * deffe;
+          double limP_dop = P->hdop * biodop / (k1p_P + biodop);
+          double limP_po4 = biopo4 / (k1p_P + biopo4);
+          double dopupt_flag = 0.5 + fsign(0.5, limP_dop - limP_po4);
+          double limP = limP_dop * dopupt_flag + limP_po4 * (1. - dopupt_flag);
+          double u_P = fmin(lc0, jmax * limP);
+          u_P = fmin(u_P, jmax * biono3 / (k1n + biono3));
+          double npp = u_P * biophyt;
+          SR(dopupt) = npp * dopupt_flag;
+          npp = npp * SF(V_NO3) * (dopupt_flag * SF(V_DOP) + (1. - dopupt_flag) * SF(V_PO4)) * SF(V_DIN15);
+          SR(npp) = npp;
+          double uno3 = fmax(fmin(npp * dtbio / biono3, 0.999), TRCMIN);
+          double rno3 = fmax(fmin(SB(V_DIN15) / (biono3 - SB(V_DIN15)), 2 * RN15STD), RN15STD / 2.);
+          double bassim = rno3 + P->eps_assim * (1 - uno3) / uno3 * log(1 - uno3) * rno3 / 1000.;
+          SR(fcassim) = bassim / (1 + bassim);
+        } break;
+        case 1: {
+          // diatom growth (:2160-2200), opal production ratio (:2540)
+          const double biodiat = SB(V_DIAT), biodfe = SB(V_DFE), biosil = SB(V_SIL), biodop = SB(V_DOP), biopo4 = SB(V_PO4);
+          const double biono3 = SB(V_NO3);
+          double p1 = fmin(biodiat, P->pmax_Diat), p2 = fmax(0.0, biodiat - P->pmax_Diat);
+          double kfevar_Diat = (P->kfemin_Diat * p1 + P->kfemax_Diat * p2) / (p1 + p2);
+          double k1n_Diat = (P->knmin_Diat * p1 + P->knmax_Diat * p2) / (p1 + p2);
+          double k1p_Diat = k1n_Diat * redptn;
+          double deffe_Diat = biodfe / (kfevar_Diat + biodfe);
+          double jmax_Diat = P->abiodiat * bct * deffe_Diat;
+          double limSi = biosil / (5.e-3 + biosil);  // k1si = 5.e-3 (:2181)
+          double limP_dop = P->hdop * biodop / (k1p_Diat + biodop);
+          double limP_po4 = biopo4 / (k1p_Diat + biopo4);
+          double dopupt_Diat_flag = 0.5 + fsign(0.5, limP_dop - limP_po4);
+          double limP_Diat = limP_dop * dopupt_Diat_flag + limP_po4 * (1. - dopupt_Diat_flag);
+          double u_Diat = fmin(lc0, jmax_Diat * limSi);
+          u_Diat = fmin(u_Diat, jmax_Diat * limP_Diat);
+          u_Diat = fmin(u_Diat, jmax_Diat * biono3 / (k1n_Diat + biono3));
+          double npp_Diat = u_Diat * biodiat;
+          SR(dopupt_Diat) = npp_Diat * dopupt_Diat_flag;
+          SR(npp_Diat) = npp_Diat * SF(V_NO3) * (dopupt_Diat_flag * SF(V_DOP) + (1. - dopupt_Diat_flag) * SF(V_PO4)) * SF(V_DIN15);
+          SR(sipr0) = (-0.46204044117647 * tanh(6.9 * biodfe * 1.e3 + -3.673092) + 1.60266544117647);
+        } break;
+        case 2: {
+          // grazing, mortality, remineralisation, sinking (:2208-2260), flags (:2284-2334), digestion / sloppy feeding (:2335-2440)
+          const double biophyt = SB(V_PHYT), biodetr = SB(V_DETR), biozoop = SB(V_ZOOP), biodiaz = SB(V_DIAZ), biodiat = SB(V_DIAT);
+          const double gmax = lc0, nud = lc1;
+          const double nupt = P->nupt0 * bct, nupt_D = P->nupt0_D * bct, nudt = P->nudt0 * bct;
+          double thetaZ = P->zprefP * biophyt + P->zprefDet * biodetr + P->zprefZ * biozoop + P->zprefDiaz * biodiaz + P->kzoo +
+                          P->zprefDiat * biodiat;
+          double ing_P = P->zprefP / thetaZ, ing_Det = P->zprefDet / thetaZ, ing_Z = P->zprefZ / thetaZ;
+          double ing_D = P->zprefDiaz / thetaZ, ing_Diat = P->zprefDiat / thetaZ;
+          double graz_D = gmax * ing_D * biodiaz * biozoop;
+          double morpt_D = nupt_D * biodiaz;
+          double morp_D = P->nup_D * biodiaz * biodiaz;
+          double graz = gmax * ing_P * biophyt * biozoop;
+          double graz_Z = gmax * ing_Z * biozoop * biozoop;
+          double graz_Det = gmax * ing_Det * biodetr * biozoop;
+          double morp = P->nup * biophyt;
+          double morpt = nupt * biophyt;
+          double recy_dop = P->nudop0 * bct * SB(V_DOP);
+          double morz = P->nuz * biozoop * biozoop;
+          double remi = nud * bct * biodetr;
+          double expo = lc4 * biodetr;
+          double expo_phos = lc4 * SB(V_DETR_PHOS);
+          double dissl = SB(V_CACO3) * lc2;
+          double expocaco3 = lc5 * SB(V_CACO3);
+          double graz_Diat = gmax * ing_Diat * biodiat * biozoop;
+          double morp_Diat = P->nu_diat * biodiat;
+          double morpt_Diat = nudt * biodiat;
+          double opldis = SB(V_OPL) * P->opl_disk0;
+          double expoopl = lc6 * SB(V_OPL);
+          double remife = nud * bct * SB(V_DETRFE);
+          double expofe = lc4 * SB(V_DETRFE);
+          graz = graz * SF(V_PHYT) * SF(V_PHYT_PHOS) * SL(L_sf_P_phosflag) * SF(V_PHYTN15);
+          graz_Z = graz_Z * SF(V_ZOOP) * SF(V_ZOOPN15);
+          graz_Det = graz_Det * SF(V_DETR) * SF(V_DETR_PHOS) * SL(L_sf_detr_phosflag) * SF(V_DETRN15);
+          morp = morp * SF(V_PHYT) * SF(V_PHYT_PHOS) * SF(V_PHYTN15);
+          morpt = morpt * SF(V_PHYT) * SF(V_PHYT_PHOS) * SF(V_PHYTN15);
+          morz = morz * SF(V_ZOOP) * SF(V_ZOOPN15);
+          remi = remi * SF(V_DETR) * SF(V_DETR_PHOS) * SF(V_DETRN15);
+          expo = expo * SF(V_DETR) * SF(V_DETRN15);
+          expo_phos = expo_phos * SF(V_DETR_PHOS);
+          recy_dop = recy_dop * SF(V_DOP);
+          graz_D = graz_D * SF(V_DIAZ) * SF(V_DIAZN15);
+          morpt_D = morpt_D * SF(V_DIAZ) * SF(V_DIAZN15);
+          morp_D = morp_D * SF(V_DIAZ) * SF(V_DIAZN15);
+          dissl = dissl * SF(V_CACO3);
+          expocaco3 = expocaco3 * SF(V_CACO3);
+          graz_Diat = graz_Diat * SF(V_DIAT);
+          morp_Diat = morp_Diat * SF(V_DIAT);
+          morpt_Diat = morpt_Diat * SF(V_DIAT);
+          remife = remife * SF(V_DETRFE);
+          expofe = expofe * SF(V_DETRFE);
+          double dig_P = gamma1 * graz, dig_Z = gamma1 * graz_Z, dig_Det = gamma1 * graz_Det, dig_Diat = gamma1 * graz_Diat;
+          double dig = dig_Z + dig_P + dig_Det + dig_Diat;
+          double excr = gamma1 * (1 - geZ) * graz_Z + gamma1 * (1 - geZ) * graz + gamma1 * (1 - geZ) * graz_Det + gamma1 * (1 - geZ) * graz_Diat;
+          double sf_P = (1. - gamma1) * graz, sf_Z = (1. - gamma1) * graz_Z, sf_Det = (1. - gamma1) * graz_Det;
+          double sf_Diat = (1. - gamma1) * graz_Diat;
+          double sf = sf_P + sf_Z + sf_Det + sf_Diat;
+          double sf_P_phos = (graz * ptn_P - dig_P * redptn);
+          double sf_Det_phos = (graz_Det * ptn_detr - dig_Det * redptn);
+          double sf_phos = sf_P_phos + sf_Z * redptn + sf_Det_phos + sf_Diat * redptn;
+          double dig_D = gamma1 * graz_D * (redntp / diazntp);
+          dig = dig + dig_D;
+          excr = excr + gamma1 * (1 - geZ) * graz_D * (redntp / diazntp);
+          double nr_excr_D = gamma1 * graz_D * (1 - (redntp / diazntp)) + (1 - gamma1) * graz_D * (1 - (redntp / diazntp));
+          double sf_D = (1 - gamma1) * graz_D * (redntp / diazntp);
+          sf = sf + sf_D;
+          sf_phos = sf_phos + sf_D * redptn;
+          double calpro = ((sf_Z + morz) * lc3 + (sf_P + morp) * lc3) * redctn * 1.e3;
+          opldis = opldis * SF(V_OPL);
+          expoopl = expoopl * SF(V_OPL);
+          SR(graz) = graz; SR(graz_Z) = graz_Z; SR(graz_Det) = graz_Det; SR(graz_D) = graz_D; SR(graz_Diat) = graz_Diat;
+          SR(morp) = morp; SR(morpt) = morpt; SR(morp_D) = morp_D; SR(morpt_D) = morpt_D; SR(morp_Diat) = morp_Diat;
+          SR(morpt_Diat) = morpt_Diat; SR(morz) = morz; SR(remi) = remi; SR(expo) = expo; SR(expo_phos) = expo_phos;
+          SR(recy_dop) = recy_dop; SR(dissl) = dissl; SR(expocaco3) = expocaco3; SR(opldis) = opldis; SR(expoopl) = expoopl;
+          SR(remife) = remife; SR(expofe) = expofe; SR(dig) = dig; SR(dig_P) = dig_P; SR(dig_Z) = dig_Z; SR(dig_Det) = dig_Det;
+          SR(dig_Diat) = dig_Diat; SR(dig_D) = dig_D; SR(excr) = excr; SR(sf) = sf; SR(sf_P) = sf_P; SR(sf_Z) = sf_Z;
+          SR(sf_Det) = sf_Det; SR(sf_Diat) = sf_Diat; SR(sf_D) = sf_D; SR(sf_phos) = sf_phos; SR(nr_excr_D) = nr_excr_D;
+          SR(calpro) = calpro;
+          // *out sums (:2762-2777)
+          acc0 = acc0 + expo; acc1 = acc1 + expo_phos; acc2 = acc2 + calpro; acc3 = acc3 + dissl; acc4 = acc4 + expocaco3;
+          acc5 = acc5 + expoopl; acc6 = acc6 + expofe;
+        } break;
+        case 3: {
+          // iron speciation and scavenging (:2262-2283)
+          const double biodon = SB(V_DON), biodfe = SB(V_DFE), aou8 = lc0, o2flag = lc1;
+          double ligand = fmax(aou8 / 66. + pow(biodon, 0.8) / 4.8, 0.5) / 1000.;
+          double fepa = (1.0 + P->kfeleq * (ligand - biodfe)) * o2flag;
+          double feprime = ((-fepa + sqrt(fepa * fepa + 4.0 * P->kfeleq * biodfe)) / (2.0 * P->kfeleq)) * o2flag;
+          double fecol = P->kfecol * (feprime * feprime) * o2flag;
+          SR(feprime) = feprime;
+          SR(fecol) = fecol * SF(V_DFE);
+        } break;
+        case 4: {
+          // organic iron adsorption exponent (:2278), excretion / N2-fixation fractionation (:2466-2478), calcite 13C ratios
+          const double biozoop = SB(V_ZOOP);
+          SR(pw58) = pow(((SB(V_DETR) * SF(V_DETR)) * P->mc * redctn), 0.58);
+          double rzoop = fmax(fmin(SB(V_ZOOPN15) / (biozoop - SB(V_ZOOPN15)), 2. * RN15STD), RN15STD / 2.);
+          double bexcr = rzoop - P->eps_excr * rzoop / 1000.;
+          SR(fcexcr) = bexcr / (1 + bexcr);
+          double bnfix = RN15STD - P->eps_nfix * RN15STD / 1000.;
+          SR(fcnfix) = bnfix / (1 + bnfix);
+          SR(rtdic13) = CL13(SB(V_DIC13) / SB(V_DIC));
+          SR(rtcaco3c13) = CL13(SB(V_CACO3C13) / SB(V_CACO3));
+          double GM15ptc = 0.0060 + 0.0069 * SB(V_PO4);
+          SR(GM15ptn) = GM15ptc * redctn * 1.e3;
+        } break;
+        case 5: {
+          // DON recycling and its fractionation (:2453-2465), 15N ratios of the organic pools (:2479-2500)
+          const double biodon = SB(V_DON);
+          double recy_don = P->nudon0 * bct * biodon;
+          recy_don = recy_don * SF(V_DON) * SF(V_DON15);
+          SR(recy_don) = recy_don;
+          double udon = fmax(fmin(recy_don * dtbio / biodon, 0.999), TRCMIN);
+          double rdon = fmax(fmin(SB(V_DON15) / (biodon - SB(V_DON15)), 2 * RN15STD), RN15STD / 2.);
+          double brecy = rdon + P->eps_recy * (1 - udon) / udon * log(1 - udon) * rdon / 1000.;
+          SR(fcrecy) = brecy / (1 + brecy);
+          SR(rtphytn15) = CL15(SB(V_PHYTN15) / SB(V_PHYT));
+          SR(rtdiatn15) = CL15(SB(V_DIATN15) / SB(V_DIAT));
+          SR(rtzoopn15) = CL15(SB(V_ZOOPN15) / SB(V_ZOOP));
+          const double rtdetrn15 = CL15(SB(V_DETRN15) / SB(V_DETR));
+          SR(rtdetrn15) = rtdetrn15;
+          SR(rtdiazn15) = CL15(SB(V_DIAZN15) / SB(V_DIAZ));
+          acc0 = acc0 + rtdetrn15;   // rn15expoout
+        } break;
+        case 6: {
+          // 13C fractionation of primary production and ratios of the living pools (:2501-2530)
+          const double biodic = SB(V_DIC);
+          double rdic13 = fmax(fmin(SB(V_DIC13) / (biodic - SB(V_DIC13)), 2. * RC13STD), 0.5 * RC13STD);
+          double bc13npp = lc0 * rdic13;
+          SR(fcnpp) = bc13npp / (1 + bc13npp);
+          SR(rtphytc13) = CL13(SB(V_PHYTC13) / (SB(V_PHYT) * redctn));
+          SR(rtdiatc13) = CL13(SB(V_DIATC13) / (SB(V_DIAT) * redctn));
+          SR(rtzoopc13) = CL13(SB(V_ZOOPC13) / (SB(V_ZOOP) * redctn));
+          SR(rtdetrc13) = CL13(SB(V_DETRC13) / (SB(V_DETR) * redctn));
+        } break;
+        case 7: {
+          // diazotroph growth and N2 fixation (:2164-2166, 2200-2206, 2226-2232); the phosphorus limitation of the
+          // ordinary phytoplankton is re-derived here (same expressions as warp 0)
+          const double biophyt = SB(V_PHYT), biodfe = SB(V_DFE), biodop = SB(V_DOP), biopo4 = SB(V_PO4), biono3 = SB(V_NO3);
+          const double biodiaz = SB(V_DIAZ);
+          double p1 = fmin(biophyt, P->pmax), p2 = fmax(0.0, biophyt - P->pmax);
+          double k1n = (P->knmin * p1 + P->knmax * p2) / (p1 + p2);
+          double k1p_P = k1n * ptn_P;
+          double deffe_D = biodfe / (P->kfe_D + biodfe);
+          double jmax_D = fmax(0., P->abio_P * (bct - P->dbct_D) * deffe_D) * P->jdiar;
+          double limP_dop = P->hdop * biodop / (k1p_P + biodop);
+          double limP_po4 = biopo4 / (k1p_P + biopo4);
+          double dopupt_flag = 0.5 + fsign(0.5, limP_dop - limP_po4);
+          double limP = limP_dop * dopupt_flag + limP_po4 * (1. - dopupt_flag);
+          double u_D = fmin(lc0, jmax_D * limP);
+          double npp_D = fmax(0., u_D * biodiaz);
+          double no3upt_D = (0.5 + 0.5 * tanh(biono3 - 5.)) * npp_D;
+          SR(dopupt_D) = npp_D * dopupt_flag;
+          npp_D = npp_D * (dopupt_flag * SF(V_DOP) + (1. - dopupt_flag) * SF(V_PO4)) * SF(V_DIN15);
+          no3upt_D = no3upt_D * SF(V_NO3) * SF(V_DIN15);
+          SR(npp_D) = npp_D;
+          SR(no3upt_D) = no3upt_D;
+          acc0 = acc0 + npp_D - no3upt_D;   // nfixout
+          SR(rtdoc13) = CL13(SB(V_DOC13) / (SB(V_DON) * redctn));
+          SR(rtdiazc13) = CL13(SB(V_DIAZC13) / (biodiaz * redctn));
+        } break;
+      }
+      __syncthreads();
+      // ================= stage 2: forward Euler on the owned state variables (:2552-2760) =================
+#define UPD(m, expr)                                   \
+  do {                                                 \
+    const double nv_ = (expr);                         \
+    SB(m) = nv_;                                       \
+    if (nv_ - TRCMIN < 0.0) SF(m) = 0.0;               \
+  } while (0)
+      switch (w) {
+        case 0: {
+          const double npp = SR(npp), dopupt = SR(dopupt), morp = SR(morp), morpt = SR(morpt), graz = SR(graz), remi = SR(remi);
+          const double morpt_D = SR(morpt_D), npp_D = SR(npp_D), dopupt_D = SR(dopupt_D), recy_dop = SR(recy_dop), excr = SR(excr);
+          const double morpt_Diat = SR(morpt_Diat), npp_Diat = SR(npp_Diat), dopupt_Diat = SR(dopupt_Diat), morp_Diat = SR(morp_Diat);
+          const double GM15ptn = SR(GM15ptn);
+          const double biophyt = SB(V_PHYT), biophyt_phos = SB(V_PHYT_PHOS);
+          UPD(V_PO4, SB(V_PO4) + dtbio * (dopupt * ptn_P - GM15ptn * npp + (1. - dfrt) * morpt * ptn_P + (1. - pfr) * remi * ptn_detr +
+                                         diazptn * (morpt_D - (npp_D - dopupt_D)) + recy_dop +
+                                         redptn * (excr + (1. - dfrt) * morpt_Diat - (npp_Diat - dopupt_Diat))));
+          UPD(V_DOP, SB(V_DOP) + dtbio * (dfr * morp * ptn_P + redptn * (dfr * morp_Diat + dfrt * morpt_Diat - dopupt_Diat) +
+                                         dfrt * morpt * ptn_P + pfr * remi * ptn_detr - ptn_P * dopupt - diazptn * dopupt_D - recy_dop));
+          const double nphyt = biophyt + dtbio * (npp - morp - graz - morpt);
+          const double nphos = biophyt_phos + dtbio * (npp * GM15ptn - morp * ptn_P - graz * ptn_P - morpt * ptn_P);
+          UPD(V_PHYT, nphyt);
+          UPD(V_PHYT_PHOS, nphos);
+          SL(L_ptn_P0 + (par ^ 1)) = nphos / nphyt;
+        } break;
+        case 1: {
+          const double morp = SR(morp), sf = SR(sf), morz = SR(morz), remi = SR(remi), graz_Det = SR(graz_Det), expo = SR(expo);
+          const double morp_D = SR(morp_D), morp_Diat = SR(morp_Diat), sf_phos = SR(sf_phos), expo_phos = SR(expo_phos);
+          const double impo = SL(X_expo) * dztrk, impo_phos = SL(X_expo_phos) * dztrk;
+          const double ndetr = SB(V_DETR) + dtbio * ((1. - dfr) * morp + sf + morz - remi - graz_Det - expo + impo + morp_D * rnd +
+                                                     (1. - dfr) * morp_Diat);
+          const double ndphos = SB(V_DETR_PHOS) + dtbio * ((1. - dfr) * morp * ptn_P + sf_phos + morz * redptn - remi * ptn_detr -
+                                                           graz_Det * ptn_detr - expo_phos + impo_phos + morp_D * rnd * redptn +
+                                                           (1. - dfr) * morp_Diat * redptn);
+          UPD(V_DETR, ndetr);
+          UPD(V_DETR_PHOS, ndphos);
+          SL(L_ptn_detr0 + (par ^ 1)) = ndphos / ndetr;
+          UPD(V_ZOOP, SB(V_ZOOP) + dtbio * (SR(dig) - morz - SR(graz_Z) - SR(excr)));
+          UPD(V_DIAZ, SB(V_DIAZ) + dtbio * (SR(npp_D) - morp_D - SR(morpt_D) - SR(graz_D)));
+          UPD(V_DIAT, SB(V_DIAT) + dtbio * (SR(npp_Diat) - morp_Diat - SR(graz_Diat) - SR(morpt_Diat)));
+        } break;
+        case 2: {
+          const double excr = SR(excr), remi = SR(remi), morpt = SR(morpt), npp = SR(npp), morpt_Diat = SR(morpt_Diat);
+          const double npp_Diat = SR(npp_Diat), morpt_D = SR(morpt_D), npp_D = SR(npp_D), recy_don = SR(recy_don);
+          const double nr_excr_D = SR(nr_excr_D), morp_D = SR(morp_D), no3upt_D = SR(no3upt_D), morp = SR(morp);
+          const double morp_Diat = SR(morp_Diat);
+          const double nr_excr_P = 0.0, nr_excr_detr = 0.0;
+          UPD(V_DIC, SB(V_DIC) + dtbio * redctn *
+                                     (excr + (1. - pfr) * remi + (1. - dfrt) * morpt - npp + (1. - dfrt) * morpt_Diat - npp_Diat + morpt_D -
+                                      npp_D + recy_don + nr_excr_D + nr_excr_P + nr_excr_detr + morp_D * (1. - rnd)));
+          UPD(V_NO3, SB(V_NO3) + dtbio * (excr + (1. - pfr) * remi + (1. - dfrt) * morpt - npp + (1. - dfrt) * morpt_Diat - npp_Diat +
+                                         morpt_D - no3upt_D + recy_don + nr_excr_D + nr_excr_P + nr_excr_detr + morp_D * (1. - rnd)));
+          UPD(V_DON, SB(V_DON) + dtbio * (dfr * morp + dfrt * morpt + pfr * remi - recy_don + dfr * morp_Diat + dfrt * morpt_Diat));
+          UPD(V_CACO3, SB(V_CACO3) + dtbio * (SR(calpro) - SR(dissl) - SR(expocaco3) + SL(X_expocaco3) * dztrk));
+        } break;
+        case 3: {
+          const double excr = SR(excr), morpt = SR(morpt), npp = SR(npp), morpt_D = SR(morpt_D), npp_D = SR(npp_D);
+          const double recy_don = SR(recy_don), nr_excr_D = SR(nr_excr_D), morp_D = SR(morp_D), remife = SR(remife), fecol = SR(fecol);
+          const double morpt_Diat = SR(morpt_Diat), npp_Diat = SR(npp_Diat), sf = SR(sf), morp = SR(morp), morz = SR(morz);
+          const double graz_Det = SR(graz_Det), expofe = SR(expofe), morp_Diat = SR(morp_Diat), sf_Diat = SR(sf_Diat);
+          const double nr_excr_P = 0.0, nr_excr_detr = 0.0;
+          const double o2flag = lc1;
+          double feorgads = (P->kfeorg * SR(pw58) * SR(feprime)) * o2flag;
+          feorgads = feorgads * SF(V_DFE);
+          const double opldis = SR(opldis);
+          const double oplpro = (morp_Diat + sf_Diat) * SR(sipr0) * SF(V_SIL) * (1.e-3);
+          UPD(V_DFE, SB(V_DFE) + dtbio * (rfeton * (excr + (1. - dfrt) * morpt - npp + morpt_D - npp_D + recy_don + nr_excr_D + nr_excr_P +
+                                                    nr_excr_detr + morp_D * (1. - rnd)) -
+                                          feorgads + remife - fecol + rfeton * ((1. - dfrt) * morpt_Diat - npp_Diat)));
+          UPD(V_DETRFE, SB(V_DETRFE) + dtbio * (rfeton * (sf + (1. - dfr) * morp + morp_D * rnd + morz - graz_Det) + feorgads +
+                                                P->iscr * fecol - remife - expofe + SL(X_expofe) * dztrk +
+                                                rfeton * (1. - dfr) * morp_Diat));
+          UPD(V_SIL, SB(V_SIL) + dtbio * (opldis - oplpro));
+          UPD(V_OPL, SB(V_OPL) + dtbio * (oplpro - opldis - SR(expoopl) + SL(X_expoopl) * dztrk));
+        } break;
+        case 4: {
+          const double rtphytn15 = SR(rtphytn15), rtdiatn15 = SR(rtdiatn15), rtdiazn15 = SR(rtdiazn15), rtdetrn15 = SR(rtdetrn15);
+          const double fcassim = SR(fcassim), fcexcr = SR(fcexcr), fcrecy = SR(fcrecy);
+          const double morpt = SR(morpt), morpt_Diat = SR(morpt_Diat), npp_Diat = SR(npp_Diat), excr = SR(excr), morpt_D = SR(morpt_D);
+          const double nr_excr_D = SR(nr_excr_D), morp_D = SR(morp_D), remi = SR(remi), recy_don = SR(recy_don), npp = SR(npp);
+          const double no3upt_D = SR(no3upt_D), morp = SR(morp), morp_Diat = SR(morp_Diat);
+          const double nr_excr_P = 0.0, nr_excr_detr = 0.0;
+          UPD(V_DIN15, SB(V_DIN15) + dtbio * (rtphytn15 * (1. - dfrt) * morpt + rtphytn15 * nr_excr_P + rtdiatn15 * (1. - dfrt) * morpt_Diat -
+                                             fcassim * npp_Diat + fcexcr * excr + rtdiazn15 * morpt_D + rtdiazn15 * nr_excr_D +
+                                             rtdiazn15 * morp_D * (1. - rnd) + rtdetrn15 * (1. - pfr) * remi + rtdetrn15 * nr_excr_detr +
+                                             fcrecy * recy_don - fcassim * npp - fcassim * no3upt_D));
+          UPD(V_DON15, SB(V_DON15) + dtbio * (dfr * rtphytn15 * morp + dfr * rtdiatn15 * morp_Diat + dfrt * rtdiatn15 * morpt_Diat +
+                                             dfrt * rtphytn15 * morpt + rtdetrn15 * pfr * remi - fcrecy * recy_don));
+        } break;
+        case 5: {
+          const double rtphytn15 = SR(rtphytn15), rtdiatn15 = SR(rtdiatn15), rtdiazn15 = SR(rtdiazn15), rtdetrn15 = SR(rtdetrn15);
+          const double rtzoopn15 = SR(rtzoopn15), fcassim = SR(fcassim), fcexcr = SR(fcexcr), fcnfix = SR(fcnfix);
+          const double npp = SR(npp), morp = SR(morp), graz = SR(graz), morpt = SR(morpt), npp_Diat = SR(npp_Diat);
+          const double morp_Diat = SR(morp_Diat), graz_Diat = SR(graz_Diat), morpt_Diat = SR(morpt_Diat), morz = SR(morz);
+          const double graz_Z = SR(graz_Z), excr = SR(excr), npp_D = SR(npp_D), no3upt_D = SR(no3upt_D), morp_D = SR(morp_D);
+          const double graz_D = SR(graz_D), morpt_D = SR(morpt_D);
+          UPD(V_PHYTN15, SB(V_PHYTN15) + dtbio * (fcassim * npp - rtphytn15 * morp - rtphytn15 * graz - rtphytn15 * morpt));
+          UPD(V_DIATN15, SB(V_DIATN15) + dtbio * (fcassim * npp_Diat - rtdiatn15 * morp_Diat - rtdiatn15 * graz_Diat - rtdiatn15 * morpt_Diat));
+          UPD(V_ZOOPN15, SB(V_ZOOPN15) + dtbio * (rtphytn15 * SR(dig_P) + rtdiatn15 * SR(dig_Diat) + rtzoopn15 * SR(dig_Z) +
+                                                 rtdetrn15 * SR(dig_Det) + rtdiazn15 * SR(dig_D) - rtzoopn15 * morz - rtzoopn15 * graz_Z -
+                                                 fcexcr * excr));
+          UPD(V_DIAZN15, SB(V_DIAZN15) + dtbio * (fcnfix * (npp_D - no3upt_D) + fcassim * no3upt_D - rtdiazn15 * morp_D - rtdiazn15 * graz_D -
+                                                 rtdiazn15 * morpt_D));
+        } break;
+        case 6: {
+          const double rtphytn15 = SR(rtphytn15), rtdiatn15 = SR(rtdiatn15), rtdiazn15 = SR(rtdiazn15), rtdetrn15 = SR(rtdetrn15);
+          const double rtzoopn15 = SR(rtzoopn15);
+          const double morp = SR(morp), morp_Diat = SR(morp_Diat), sf_Diat = SR(sf_Diat), sf_P = SR(sf_P), sf_Z = SR(sf_Z);
+          const double sf_Det = SR(sf_Det), sf_D = SR(sf_D), morz = SR(morz), remi = SR(remi), graz_Det = SR(graz_Det), expo = SR(expo);
+          const double morp_D = SR(morp_D);
+          const double impo = SL(X_expo) * dztrk, rn15impo = SL(X_rn15expo);
+          UPD(V_DETRN15, SB(V_DETRN15) + dtbio * (rtphytn15 * (1. - dfr) * morp + rtdiatn15 * (1. - dfr) * morp_Diat + rtdiatn15 * sf_Diat +
+                                                 rtphytn15 * sf_P + rtzoopn15 * sf_Z + rtdetrn15 * sf_Det + rtdiazn15 * sf_D +
+                                                 rtzoopn15 * morz - rtdetrn15 * remi - rtdetrn15 * graz_Det - rtdetrn15 * expo +
+                                                 rn15impo * impo + rtdiazn15 * morp_D * rnd));
+          const double rtphytc13 = SR(rtphytc13), rtzoopc13 = SR(rtzoopc13), rtdiazc13 = SR(rtdiazc13), rtdetrc13 = SR(rtdetrc13);
+          const double rtdiatc13 = SR(rtdiatc13), rtdoc13 = SR(rtdoc13), fcnpp = SR(fcnpp);
+          const double morpt = SR(morpt), excr = SR(excr), morpt_D = SR(morpt_D), nr_excr_D = SR(nr_excr_D);
+          const double morpt_Diat = SR(morpt_Diat), npp_Diat = SR(npp_Diat), recy_don = SR(recy_don), npp = SR(npp), npp_D = SR(npp_D);
+          const double nr_excr_P = 0.0, nr_excr_detr = 0.0;
+          UPD(V_DIC13, SB(V_DIC13) + dtbio * redctn *
+                                         (rtphytc13 * (1. - dfrt) * morpt + rtphytc13 * nr_excr_P + rtzoopc13 * excr + rtdiazc13 * morpt_D +
+                                          rtdiazc13 * nr_excr_D + rtdiazc13 * morp_D * (1 - rnd) + rtdetrc13 * (1. - pfr) * remi +
+                                          rtdetrc13 * nr_excr_detr + rtdiatc13 * (1. - dfrt) * morpt_Diat - fcnpp * npp_Diat +
+                                          rtdoc13 * recy_don - fcnpp * npp - fcnpp * npp_D));
+        } break;
+        case 7: {
+          const double rtphytc13 = SR(rtphytc13), rtzoopc13 = SR(rtzoopc13), rtdiazc13 = SR(rtdiazc13), rtdetrc13 = SR(rtdetrc13);
+          const double rtdiatc13 = SR(rtdiatc13), rtdoc13 = SR(rtdoc13), fcnpp = SR(fcnpp), rtdic13 = SR(rtdic13);
+          const double rtcaco3c13 = SR(rtcaco3c13);
+          const double morp = SR(morp), morp_Diat = SR(morp_Diat), morpt_Diat = SR(morpt_Diat), morpt = SR(morpt), remi = SR(remi);
+          const double recy_don = SR(recy_don), npp = SR(npp), graz = SR(graz), morz = SR(morz), graz_Z = SR(graz_Z), excr = SR(excr);
+          const double sf_Diat = SR(sf_Diat), sf_P = SR(sf_P), sf_Z = SR(sf_Z), sf_Det = SR(sf_Det), sf_D = SR(sf_D);
+          const double graz_Det = SR(graz_Det), expo = SR(expo), morp_D = SR(morp_D), npp_D = SR(npp_D), graz_D = SR(graz_D);
+          const double morpt_D = SR(morpt_D), calpro = SR(calpro), dissl = SR(dissl), expocaco3 = SR(expocaco3);
+          const double npp_Diat = SR(npp_Diat), graz_Diat = SR(graz_Diat);
+          const double rc13impo = SL(X_rc13expo) * dztrk, rcaco3c13impo = SL(X_rcaco3c13expo) * dztrk;
+          UPD(V_DOC13, SB(V_DOC13) + dtbio * redctn *
+                                         (dfr * rtphytc13 * morp + rtdiatc13 * (dfr * morp_Diat + dfrt * morpt_Diat) + rtphytc13 * dfrt * morpt +
+                                          rtdetrc13 * pfr * remi - rtdoc13 * recy_don));
+          UPD(V_PHYTC13, SB(V_PHYTC13) + dtbio * redctn * (fcnpp * npp - rtphytc13 * morp - rtphytc13 * graz - rtphytc13 * morpt));
+          UPD(V_ZOOPC13, SB(V_ZOOPC13) + dtbio * redctn *
+                                             (rtphytc13 * SR(dig_P) + rtdiatc13 * SR(dig_Diat) + rtzoopc13 * SR(dig_Z) + rtdetrc13 * SR(dig_Det) +
+                                              rtdiazc13 * SR(dig_D) - rtzoopc13 * morz - rtzoopc13 * graz_Z - rtzoopc13 * excr));
+          UPD(V_DETRC13, SB(V_DETRC13) + dtbio * redctn *
+                                             (rtphytc13 * (1. - dfr) * morp + rtdiatc13 * (1. - dfr) * morp_Diat + rtdiatc13 * sf_Diat +
+                                              rtphytc13 * sf_P + rtzoopc13 * sf_Z + rtdetrc13 * sf_Det + rtdiazc13 * sf_D + rtzoopc13 * morz -
+                                              rtdetrc13 * remi - rtdetrc13 * graz_Det - rtdetrc13 * expo + rc13impo + rtdiazc13 * morp_D * rnd));
+          UPD(V_DIAZC13, SB(V_DIAZC13) + dtbio * redctn * (fcnpp * npp_D - rtdiazc13 * (morp_D + graz_D + morpt_D)));
+          UPD(V_CACO3C13, SB(V_CACO3C13) + dtbio * (rtdic13 * calpro - rtcaco3c13 * dissl - rtcaco3c13 * expocaco3 + rcaco3c13impo));
+          UPD(V_DIATC13, SB(V_DIATC13) + dtbio * redctn * (fcnpp * npp_Diat - rtdiatc13 * (morp_Diat + graz_Diat + morpt_Diat)));
+          acc1 = acc1 + rtdetrc13 * expo;            // rc13expoout
+          acc2 = acc2 + rtcaco3c13 * expocaco3;      // rcaco3c13expoout
+        } break;
+      }
+      __syncthreads();
+    }  // sub-steps
+
+    // ================= E1: increments as rates (:880-895); publish the sums =================
+    // States the driver does not touch afterwards go straight to src; the others stay in B.
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int m = 4 * w + q;
+      const double inc = (SB(m) - SC(m)) * rdtts;
+      SB(m) = inc;
+      const bool later = (m == V_NO3 || m == V_DIN15 || m == V_DFE || m == V_PO4 || m == V_DIC || m == V_DIC13 || m == V_SIL);
+      if (!later && act) v.src[c + (long long)(ix[IX_SRC + m] - 1) * n3] = inc;
+    }
+    switch (w) {
+      case 2: SL(S_expo) = acc0; SL(S_expo_phos) = acc1; SL(S_calpro) = acc2; SL(S_dissl) = acc3; SL(S_expocaco3) = acc4;
+              SL(S_expoopl) = acc5; SL(S_expofe) = acc6; break;
+      case 5: SL(S_rn15expo) = acc0; break;
+      case 7: SL(S_nfix) = acc0; SL(S_rc13expo) = acc1; SL(S_rcaco3c13expo) = acc2; break;
+      default: break;
+    }
+    __syncthreads();
+
+    // ================= E2: mobi_driver after mobi_src (:896-1400) =================
+    {
+      const double sgb = act ? v.sg_bathy[XIJK(i, j, k)] : 0.0;
+      const double expo = SL(S_expo) * rnbio;   // export of this level before the sea-floor share is removed
+      switch (w) {
+        case 0: {
+          // export chain -> import of the next level (:1000-1010, 1112-1120, 1280-1288); sea-floor phosphorus
+          double expofe = SL(S_expofe) * rnbio, expocaco3 = SL(S_expocaco3) * rnbio, expoopl = SL(S_expoopl) * rnbio;
+          double expo_phos = SL(S_expo_phos) * rnbio, rn15expo = SL(S_rn15expo) * rnbio, rc13expo = SL(S_rc13expo) * rnbio;
+          double rcaco3c13expo = SL(S_rcaco3c13expo) * rnbio;
+          double ex = expo;
+          const double po4 = SB(V_PO4) + sgb * expo_phos;
+          if (act) v.src[c + (long long)(ix[IX_SRC + V_PO4] - 1) * n3] = po4;
+          rc13expo = rc13expo - sgb * rc13expo;
+          ex = ex - sgb * ex;
+          expo_phos = expo_phos - sgb * expo_phos;
+          SL(X_expo) = ex * dztk;
+          SL(X_expo_phos) = expo_phos * dztk;
+          SL(X_rn15expo) = rn15expo;
+          SL(X_rc13expo) = rc13expo * dztk;
+          SL(X_rcaco3c13expo) = rcaco3c13expo * dztk;
+          SL(X_expofe) = expofe * dztk;
+          SL(X_expocaco3) = expocaco3 * dztk;
+          SL(X_expoopl) = expoopl * dztk;
+        } break;
+        case 1: {
+          // benthic denitrification, Bohlen et al. 2012 (:1035-1075); NO3 / DIN15 / ALK are closed in E3
+          const double tno3 = SC(V_NO3), tdin15 = SC(V_DIN15);
+          const double rn15expo = SL(S_rn15expo) * rnbio;
+          double no3flag = 0.5 + fsign(0.5, tno3 - TRCMIN);
+          double din15flag = 0.5 + fsign(0.5, tdin15 - TRCMIN);
+          double lno3 = PRE(PR_LNO3A);
+          double sg_bdeni = (0.06 + 0.19 * PRE(PR_P099)) * fmax(expo * sgb, TRCMIN) * redctn * 1.e3;
+          sg_bdeni = fmin(sg_bdeni, sgb * expo);
+          sg_bdeni = fmax(sg_bdeni, 0.);
+          sg_bdeni = sg_bdeni * (0.5 + lno3) * no3flag * din15flag;
+          double rno3 = fmax(tdin15, TRCMIN * RN15STD / (1 + RN15STD)) / fmax(tno3 - tdin15, TRCMIN * RN15STD / (1 + RN15STD));
+          rno3 = fmin(rno3, 2. * RN15STD);
+          rno3 = fmax(rno3, RN15STD / 2.);
+          double eps_bdeni = v.mobi_epsbd[k - 1];
+          double bbdeni = rno3 - eps_bdeni * rno3 / 1000.;
+          e3_no3 = SB(V_NO3) + sgb * expo - sg_bdeni;
+          e3_din15 = SB(V_DIN15) + rn15expo * sgb * expo - bbdeni / (1 + bbdeni) * sg_bdeni;
+          e3_c = c;
+          e3_pending = act;
+        } break;
+        case 2: {
+          // sea-floor carbon, O2, water-column denitrification, ALK (:1100-1110, 1301-1366), calcite (:1372-1400), c14 (tracer.F:848-867)
+          const double tno3 = SC(V_NO3), tdin15 = SC(V_DIN15);
+          const double nfix = SL(S_nfix), rdissl = SL(S_dissl) * rnbio, rcalpro = SL(S_calpro) * rnbio;
+          const double rexpocaco3 = SL(S_expocaco3) * rnbio;
+          double no3flag = 0.5 + fsign(0.5, tno3 - TRCMIN);
+          double din15flag = 0.5 + fsign(0.5, tdin15 - TRCMIN);
+          double dic = SB(V_DIC) + sgb * expo * redctn;
+          const double dic_npzd_sms = dic;
+          double src_alk = -dic * P->redntc * 1.e-3;
+          // the benthic term of warp 1 enters ALK: same expressions as there
+          double bdeni;
+          {
+            double lno3a = PRE(PR_LNO3A);
+            double sg_bdeni = (0.06 + 0.19 * PRE(PR_P099)) * fmax(expo * sgb, TRCMIN) * redctn * 1.e3;
+            sg_bdeni = fmin(sg_bdeni, sgb * expo);
+            sg_bdeni = fmax(sg_bdeni, 0.);
+            bdeni = sg_bdeni * (0.5 + lno3a) * no3flag * din15flag;
+          }
+          double rno3 = fmax(tdin15, TRCMIN * RN15STD / (1 + RN15STD)) / fmax(tno3 - tdin15, TRCMIN * RN15STD / (1 + RN15STD));
+          rno3 = fmin(rno3, 2. * RN15STD);
+          rno3 = fmax(rno3, RN15STD / 2.);
+          const double fo2 = PRE(PR_FO2);
+          double so2 = dic_npzd_sms * P->redotc + nfix * rnbio * 1.25e-3;
+          double lno3 = PRE(PR_LNO3B);
+          double wcdeni = 800. * no3flag * so2 * (1.0 - fo2) * (0.5 + lno3) * din15flag;
+          wcdeni = fmax(wcdeni, 0.);
+          double uno3 = wcdeni * v.c2dtts / tno3;
+          uno3 = fmin(uno3, 0.999);
+          uno3 = fmax(uno3, TRCMIN);
+          double bwcdeni = rno3 + P->eps_wcdeni * (1 - uno3) / uno3 * log(1 - uno3) * rno3 / 1000.;
+          SL(L_wcdeni) = wcdeni;
+          SL(L_bwfrac) = (bwcdeni / (1 + bwcdeni));
+          src_alk = src_alk + wcdeni * 1.e-3;
+          src_alk = src_alk + bdeni * 1.e-3;
+          src_alk = src_alk - nfix * rnbio * 1.e-3;
+          const double src_o2 = -so2 * fo2;
+          if (k < kmx) {
+            dic = dic + rdissl * 1.e-3 - rcalpro * 1.e-3;
+            src_alk = src_alk + 2. * rdissl * 1.e-3 - 2. * rcalpro * 1.e-3;
+          } else {
+            dic = dic + rdissl * 1.e-3 - rcalpro * 1.e-3 + rexpocaco3 * 1.e-3;
+            src_alk = src_alk + 2. * rdissl * 1.e-3 - 2. * rcalpro * 1.e-3 + 2. * rexpocaco3 * 1.e-3;
+          }
+          if (act) {
+            const double c14_in = v.t_m1[c + (long long)(ix[IX_IC14] - 1) * n3];
+            v.src[c + (long long)(ix[IX_SRC + V_DIC] - 1) * n3] = dic;
+            v.src[c + (long long)(ix[IX_ISALK] - 1) * n3] = src_alk;
+            v.src[c + (long long)(ix[IX_ISO2] - 1) * n3] = src_o2;
+            v.src[c + (long long)(ix[IX_ISC14] - 1) * n3] = dic * RC14STD - 3.836e-12 * c14_in;
+          }
+        } break;
+        case 3: {
+          // sediment carbon oxidation (Flogel 2011 / Somes 2021), iron release (Dale 2015) (:1076-1099); dust and
+          // hydrothermal iron (tracer.F:536-545)
+          const double o2_in = act ? v.t_m1[c + (long long)(ix[IX_IO2] - 1) * n3] * 1000. : 1.0;
+          double coxdepth = fmin(fmax(v.zt[k - 1], 50000.), 150000.);
+          double oblinc = -1.26e-6 * coxdepth + 0.203;
+          double obexpc = -6.e-7 * coxdepth + 1.14;
+          double nburial = (oblinc * pow((expo * sgb * dztk / 100 * 86400. * 365. * redctn * 1000.), obexpc)) /
+                           (86400. * 365. * dztk / 100 * redctn * 1000.);
+          double coxsed = expo * sgb - nburial;
+          double fesed = 85. * tanh(coxsed * redctn * 1000 * dztk / 100 * 86400. / o2_in) / (dztk / 100 * 86400 * 1000);
+          double dfe = SB(V_DFE) + fesed;
+          if (act) {
+            if (k == 1) dfe = dfe + v.fe_atmdep[X2(i, j) + (long long)(mi - 1) * v.n2] * 1000 / (v.dzt[0] / 100.);
+            dfe = dfe + v.fe_hydr[XIJK(i, j, k)];
+            v.src[c + (long long)(ix[IX_SRC + V_DFE] - 1) * n3] = dfe;
+          }
+        } break;
+        case 4: {
+          // 13C of the sea-floor remineralisation and of calcite dissolution / production (:1104, 1258-1276, 1372-1400)
+          const double rc13expo = SL(S_rc13expo) * rnbio, rdissl = SL(S_dissl) * rnbio, rcalpro = SL(S_calpro) * rnbio;
+          const double rexpocaco3 = SL(S_expocaco3) * rnbio;
+          const double dic_in = act ? v.t_m1[c + (long long)(ix[IX_TR + V_DIC] - 1) * n3] : 1.0;
+          double dic13 = SB(V_DIC13) + rc13expo * sgb * redctn;
+          double rtdic13 = fmax(SC(V_DIC13), TRCMIN * RC13STD / (1 + RC13STD)) / fmax(dic_in, TRCMIN);
+          rtdic13 = fmin(rtdic13, 2. * RC13STD / (1 + RC13STD));
+          rtdic13 = fmax(rtdic13, 0.5 * RC13STD / (1 + RC13STD));
+          double rtcaco3c13 = fmax(SC(V_CACO3C13), TRCMIN * RC13STD / (1 + RC13STD)) / fmax(SC(V_CACO3), TRCMIN);
+          rtcaco3c13 = fmin(rtcaco3c13, 2. * RC13STD / (1 + RC13STD));
+          rtcaco3c13 = fmax(rtcaco3c13, 0.5 * RC13STD / (1 + RC13STD));
+          if (k < kmx)
+            dic13 = dic13 + rdissl * 1.e-3 * rtcaco3c13 - rcalpro * 1.e-3 * rtdic13;
+          else
+            dic13 = dic13 + rdissl * 1.e-3 * rtcaco3c13 - rcalpro * 1.e-3 * rtdic13 + rexpocaco3 * 1.e-3 * rtcaco3c13;
+          if (act) v.src[c + (long long)(ix[IX_SRC + V_DIC13] - 1) * n3] = dic13;
+        } break;
+        case 5: {
+          // opal reaching the sea floor dissolves there (:1478)
+          double sil = SB(V_SIL);
+          if (k >= kmx) sil = sil + SL(S_expoopl) * rnbio;
+          if (act) v.src[c + (long long)(ix[IX_SRC + V_SIL] - 1) * n3] = sil;
+        } break;
+        default: break;
+      }
+    }
+    __syncthreads();
+#undef PRE
+  }  // levels
+  if (w == 1 && e3_pending) {
+    const double wcdeni = SL(L_wcdeni), bwfrac = SL(L_bwfrac);
+    v.src[e3_c + (long long)(ix[IX_SRC + V_NO3] - 1) * n3] = e3_no3 - wcdeni;
+    v.src[e3_c + (long long)(ix[IX_SRC + V_DIN15] - 1) * n3] = e3_din15 - bwfrac * wcdeni;
+  }
+#undef SB
+#undef SF
+#undef SC
+#undef SR
+#undef SL
+#undef UPD
+}
+
+static int mobi_ws_mode() {
+  // UVIC_B200_MOBI_WS = 0 (one thread per column), 1 (warp specialised), unset = by column count
+  const char *e = getenv("UVIC_B200_MOBI_WS");
+  return e ? atoi(e) : -1;
+}
+
 void launch_mobi(uvic_b200_ctx *c, const uvic_b200_stepinfo *si) {
   DevView &v = c->v;
   // month index and declination (09/mom/tracer.F:310-343)
@@ -746,6 +1490,23 @@ void launch_mobi(uvic_b200_ctx *c, const uvic_b200_stepinfo *si) {
   double rnbio = 1. / nbio;
   long long ncell = (long long)(v.imt - 2) * v.km * (v.jhi - v.jlo + 1);
   long long ncol = (long long)(v.imt - 2) * (v.jhi - v.jlo + 1);
-  KLAUNCH("k_mobi_co2", k_mobi_co2, cdiv(ncell, 128), 128, v);
-  KLAUNCH("k_mobi_column", k_mobi_column, cdiv(ncol, 32), 32, v, mi, declin, nbio, dtbio, rdtts, rnbio);
+  if (v.mobi_ncols <= 0) return;
+  KLAUNCH("k_mobi_light", k_mobi_light, cdiv(ncol, 128), 128, v, declin);
+  KLAUNCH("k_mobi_cell", k_mobi_cell, cdiv(ncell, 128), 128, v);
+  const int ngroups = (v.mobi_ncols + 31) / 32;
+  int mode = mobi_ws_mode();
+  // Few column groups: the chain latency of a column dominates and the warp-specialised kernel wins; many groups
+  // fill the machine either way and the one-thread-per-column kernel issues fewer instructions in total.
+  bool ws = (mode < 0) ? (ngroups <= 148 * 8) : (mode != 0);
+  if (ws) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(k_mobi_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WsSm));
+      attr_set = true;
+    }
+    ProfScope ps_(c, "k_mobi_ws");
+    k_mobi_ws<<<ngroups, 32 * WS_WARPS, sizeof(WsSm), c->stream>>>(v, mi, nbio, dtbio, rdtts, rnbio);
+  } else {
+    KLAUNCH("k_mobi_column", k_mobi_column, ngroups, 32, v, mi, nbio, dtbio, rdtts, rnbio);
+  }
 }

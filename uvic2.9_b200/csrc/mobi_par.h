@@ -6,6 +6,7 @@
 #define MOBI_NVAR 32   // ntnpzd with the options of run/mk.in (09/mom/mobi.h:104-142)
 #define MOBI_KMAX 128
 #define MOBI_NIDX 128
+#define MOBI_NPRE 16   // per-cell fields of the MOBI pre-pass (k_mobi.cu, enum MobiPre)
 
 // MOBI-internal state order = mobi_init's setimobi sequence (09/mom/mobi.F:440-497)
 enum MobiVar {
