@@ -104,7 +104,9 @@ def kernel_bytes_per_launch(name, case, ctx, ngroup_launch):
         "k_isocoef": cells * 8 * (10 + 19),
         "k_gm_faces": cells * 8 * (8 + 2),
         "k_gm_column": cells * 8 * (5 + 4),
-        "k_vmix_column": cells * 8 * (5 + 4),
+        "k_vmix_cbt": cells * 8 * (6 + 1),
+        "k_vmix_factor": cells * 8 * (1 + 3),
+        "k_gm_total": cells * 8 * (4 + 2),
     }
     return table.get(name)
 
@@ -286,7 +288,8 @@ def main():
 
     def one_step():
         state["itt"] += 1
-        ctx.step(leapfrog=pkg.timestep.is_leapfrog(state["itt"], 16))
+        # the host knows its schedule (mixing step every nmix-th itt, source/mom/mom.F:111-146) and says so: MOBI look-ahead
+        ctx.step(leapfrog=pkg.timestep.is_leapfrog(state["itt"], 16), next_leapfrog=pkg.timestep.is_leapfrog(state["itt"] + 1, 16))
         if world > 1:
             halo.exchange(tp1_tensor())
         ctx.rotate()
@@ -360,7 +363,7 @@ def main():
             # t(tau-1), t(tau) stay resident (NULL = keep); velocities and vertical b.c. come from the host,
             # t(tau+1) goes back to the host: what the Fortran shim moves every step
             ctx.tracer_step_host(None, None, h_vet.numpy(), h_vnt.numpy(), h_vbt.numpy(), h_stf.numpy(), h_btf.numpy(),
-                                 h_out.numpy(), leapfrog=lf)
+                                 h_out.numpy(), leapfrog=lf, next_leapfrog=pkg.timestep.is_leapfrog(state["itt"] + 1, 16))
             if world > 1:
                 halo.exchange(tp1_tensor())
             ctx.rotate()
@@ -383,7 +386,8 @@ def main():
             ms_e = float(tt.item())
         e2e = {"value": units / (ms_e / a.steps * 1e-3) / 1e9, "unit": "G cell*tracer/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e / a.steps,
-               "note": "uvic_b200_tracer_step: adv velocities + stf/btf H2D from pinned memory, t(tau+1) D2H every step"}
+               "note": "uvic_b200_tracer_step: adv velocities + stf/btf H2D from pinned memory and the whole t(tau+1) D2H every step, "
+                       "copies on their own streams under the kernels; MOBI of step n+1 runs while t(tau+1) of step n travels"}
 
     # ---- conservation check on the state the timed steps produced -----------------------
     inv = ctx.inventory(0)

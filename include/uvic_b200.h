@@ -129,9 +129,22 @@ int uvic_b200_tracer(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si);/* call t
 /* isopyc + vmixc + tracer in one call */
 int uvic_b200_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si);
 
+/* Optional look-ahead: the stepinfo of the step AFTER the next call of uvic_b200_tracer / _step / _tracer_step.  The
+ * MOBI source terms of a step depend only on t(tau-1) of that step and the 2-D forcing, all of which are final once
+ * the current step's kernels have run (source/mom/mom.F:111-146 fixes the schedule: mixing steps every nmix-th itt),
+ * so with a hint the library computes them on a side stream while the current t(tau+1) travels to the host.  The
+ * result is used only if the next call's stepinfo equals the hint bit for bit and no upload_t / upload_forcing came
+ * in between; otherwise it is discarded and recomputed.  Results are identical with and without hints. */
+int uvic_b200_hint_next_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *next);
+
+/* page-lock / release a host array passed every step (the Fortran COMMON storage), so H2D / D2H copies overlap kernels */
+int uvic_b200_pin_host(void *host, size_t bytes);
+int uvic_b200_unpin_host(void *host);
+
 /* one synchronous step with HOST buffers (what the Fortran shim calls): uploads
  * t(tau-1), t(tau), the advective velocities and the vertical b.c., runs the step and
- * returns t(tau+1).  NULL inputs keep the resident copy. */
+ * returns t(tau+1).  NULL inputs keep the resident copy.  Velocities and b.c. are copied on a separate stream under
+ * the kernels that do not need them, and t(tau+1) leaves in tracer batches (T,S first) as soon as each is final. */
 int uvic_b200_tracer_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si, const double *t_taum1, const double *t_tau,
                           const double *adv_vet, const double *adv_vnt, const double *adv_vbt, const double *stf,
                           const double *btf, double *t_taup1);

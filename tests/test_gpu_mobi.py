@@ -78,3 +78,50 @@ def test_mobi_kernels_agree_bitwise(pkg, monkeypatch):
         ctx.close()
     assert np.array_equal(out[0][0], out[1][0])
     assert np.array_equal(out[0][1], out[1][1])
+
+
+def test_mobi_lookahead_is_bitwise_neutral(pkg):
+    """Hints (right and wrong ones) never change results: a mispredicted look-ahead is discarded."""
+    case = pkg.synthetic.make_case(nt=37, imt=42, jmt=34, km=10, seed=7)
+    sched = [True, True, False, True, True]
+    runs = []
+    for hints in (None, "right", "wrong"):
+        ctx = pkg.TracerContext(case, mobi=1)
+        ctx.load_state()
+        out = []
+        for s, lf in enumerate(sched):
+            nxt = None
+            if hints is not None and s + 1 < len(sched):
+                nxt = sched[s + 1] if hints == "right" else (not sched[s + 1])
+            ctx.step(leapfrog=lf, next_leapfrog=nxt)
+            out.append(ctx.download_t(+1).copy())
+            ctx.rotate()
+        runs.append(out)
+        ctx.close()
+    for other in runs[1:]:
+        for a, b in zip(runs[0], other):
+            assert np.array_equal(a, b)
+
+
+def test_host_buffer_step_with_lookahead_matches_resident_step(pkg):
+    """uvic_b200_tracer_step (copy streams, batched D2H, look-ahead) against the resident call sequence."""
+    case = pkg.synthetic.make_case(nt=37, imt=42, jmt=34, km=10, seed=9)
+    a = case.arrays
+    ref = pkg.TracerContext(case, mobi=1)
+    ref.load_state()
+    ctx = pkg.TracerContext(case, mobi=1)
+    ctx.load_state()
+    sched = [True, True, False, True]
+    vet, vnt, vbt = (np.ascontiguousarray(a[n]) for n in ("adv_vet", "adv_vnt", "adv_vbt"))
+    stf, btf = np.ascontiguousarray(a["stf"]), np.ascontiguousarray(a["btf"])
+    out = np.empty(ctx.shape_t())
+    for s, lf in enumerate(sched):
+        ref.step(leapfrog=lf)
+        want = ref.download_t(+1)
+        nxt = sched[s + 1] if s + 1 < len(sched) else None
+        ctx.tracer_step_host(None, None, vet, vnt, vbt, stf, btf, out, leapfrog=lf, next_leapfrog=nxt)
+        assert np.array_equal(out[:, 1:-1], want[:, 1:-1])
+        ref.rotate()
+        ctx.rotate()
+    ref.close()
+    ctx.close()

@@ -288,3 +288,25 @@ def test_fourier_filter_parity(pkg):
     for c in (a, b, ctx):
         c.close()
     o.close()
+
+
+@pytest.mark.parametrize("shape", [dict(imt=34, jmt=26, km=8), dict(imt=70, jmt=37, km=19), dict(imt=23, jmt=50, km=33)])
+def test_split_fct_update_matches_merged_kernel_bitwise(pkg, shape, monkeypatch):
+    """k_update<2> (diffusion) followed by k_update<3> (FCT fluxes) performs the operations of the
+    merged k_update<1> in the same order; t(tau+1) must be identical to the last bit (leapfrog
+    and mixing steps)."""
+    case = pkg.synthetic.make_case(nt=4, names=["temp", "salt", "p0", "p1"], seed=3, **shape)
+    out = []
+    for mode in ("merged", "split"):
+        monkeypatch.setenv("UVIC_B200_FCT", mode)
+        ctx = pkg.TracerContext(case)
+        ctx.load_state()
+        res = []
+        for lf in (True, False, True):
+            ctx.step(leapfrog=lf)
+            res.append(ctx.download_t(+1).copy())
+            ctx.rotate()
+        out.append(res)
+        ctx.close()
+    for a, b in zip(*out):
+        assert np.array_equal(a, b)

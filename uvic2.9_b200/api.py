@@ -64,6 +64,7 @@ ABI_SYMBOLS = [
     "uvic_b200_inventory", "uvic_b200_tbar", "uvic_b200_sumbk", "uvic_b200_fetch", "uvic_b200_device_ptr",
     "uvic_b200_t_ptr", "uvic_b200_kernel_launches", "uvic_b200_local_rows", "uvic_b200_version",
     "uvic_b200_profile_enable", "uvic_b200_profile_count", "uvic_b200_profile_get", "uvic_b200_profile_reset",
+    "uvic_b200_hint_next_step", "uvic_b200_pin_host", "uvic_b200_unpin_host",
 ]
 
 _lib = None
@@ -97,6 +98,9 @@ def load_library():
     for fn in ("vmixc", "tracer", "step"):
         getattr(L, "uvic_b200_" + fn).argtypes = [vp, C.POINTER(StepInfo)]
     L.uvic_b200_tracer_step.argtypes = [vp, C.POINTER(StepInfo)] + [vp] * 8
+    L.uvic_b200_hint_next_step.argtypes = [vp, C.POINTER(StepInfo)]
+    L.uvic_b200_pin_host.argtypes = [vp, C.c_size_t]
+    L.uvic_b200_unpin_host.argtypes = [vp]
     L.uvic_b200_inventory.argtypes = [vp, C.c_int, vp]
     L.uvic_b200_tbar.argtypes = [vp, vp]
     L.uvic_b200_sumbk.argtypes = [vp, vp]
@@ -295,12 +299,21 @@ class TracerContext:
         si = self.stepinfo(leapfrog, diag)
         self._ck(self.L.uvic_b200_tracer(self.h, C.byref(si)))
 
-    def step(self, leapfrog=True, diag=False):
+    def hint_next_step(self, leapfrog=True):
+        """Tell the library what the step after the next one looks like (MOBI look-ahead); None-safe."""
+        si = self.stepinfo(leapfrog)
+        self._ck(self.L.uvic_b200_hint_next_step(self.h, C.byref(si)))
+
+    def step(self, leapfrog=True, diag=False, next_leapfrog=None):
+        if next_leapfrog is not None:
+            self.hint_next_step(next_leapfrog)
         si = self.stepinfo(leapfrog, diag)
         self._ck(self.L.uvic_b200_step(self.h, C.byref(si)))
 
-    def tracer_step_host(self, t_taum1, t_tau, adv_vet, adv_vnt, adv_vbt, stf, btf, t_taup1, leapfrog=True):
+    def tracer_step_host(self, t_taum1, t_tau, adv_vet, adv_vnt, adv_vbt, stf, btf, t_taup1, leapfrog=True, next_leapfrog=None):
         """One synchronous step with host buffers (the call the Fortran shim makes)."""
+        if next_leapfrog is not None:
+            self.hint_next_step(next_leapfrog)
         si = self.stepinfo(leapfrog)
         self._ck(self.L.uvic_b200_tracer_step(self.h, C.byref(si), _vp(t_taum1), _vp(t_tau), _vp(adv_vet), _vp(adv_vnt),
                                               _vp(adv_vbt), _vp(stf), _vp(btf), _vp(t_taup1)))

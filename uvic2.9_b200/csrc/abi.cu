@@ -79,6 +79,9 @@ int uvic_b200_create(const uvic_b200_dims *d, const uvic_b200_grid *g, const uvi
   ctx->prof_on = false;
   ctx->stream2 = nullptr; ctx->fork_event = nullptr; ctx->mobi_event = nullptr; ctx->mobi_inflight = false;
   ctx->mobi_dtnpzd = 0.0;
+  ctx->src_buf[0] = ctx->src_buf[1] = nullptr; ctx->src_cur = 0;
+  ctx->hint_valid = ctx->ahead_valid = false; ctx->ahead_tm1 = nullptr; ctx->ahead_buf = 0;
+  ctx->main_done_event = nullptr; ctx->copy_in = ctx->copy_out = nullptr; ctx->h2d_event = nullptr; ctx->d2h_dst = nullptr;
   DevView &v = ctx->v;
   memset(&v, 0, sizeof v);
   v.imt = d->imt; v.jmt = d->jmt; v.km = d->km; v.nt = d->nt; v.nsrc = d->nsrc;
@@ -178,6 +181,7 @@ int uvic_b200_create(const uvic_b200_dims *d, const uvic_b200_grid *g, const uvi
   DALLOC(diff_cbt, v.n3, nullptr); DALLOC(tri_a, v.n3, nullptr); DALLOC(tri_e, v.n3, nullptr); DALLOC(tri_bet, v.n3, nullptr);
   DALLOC(stf, v.n2 * nt, nullptr); DALLOC(btf, v.n2 * nt, nullptr);
   DALLOC(src, v.n3 * std::max(v.nsrc, 1), nullptr);
+  ctx->src_buf[0] = v.src;
   if (par->mobi) {
     if (!par->mobi_par || !par->mobi_index || par->n_mobi_par < (int)(sizeof(MobiPar) / sizeof(double)) || par->n_mobi_index < IX_N ||
         !st->sg_bathy || !st->fe_hydr || !st->fe_atmdep) {
@@ -217,9 +221,13 @@ int uvic_b200_create(const uvic_b200_dims *d, const uvic_b200_grid *g, const uvi
       IALLOC(mobi_cols, cols.size(), cols.data());
     }
     CK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->mobi_event, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->main_done_event, cudaEventDisableTiming));
   }
+  CK(cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&ctx->h2d_event, cudaEventDisableTiming));
+  CK(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
   {
     int *ip = nullptr;
     if (dev_alloc(ctx, "conv_n", &ip, (size_t)v.n2, (const int *)nullptr)) return 1;
@@ -229,11 +237,10 @@ int uvic_b200_create(const uvic_b200_dims *d, const uvic_b200_grid *g, const uvi
     DALLOC(conv_zsm, (size_t)v.n2 * (km / 2 + 1), nullptr);
   }
   {
-    // FCT scratch: t_lo + six ratios per tracer of a group; keep the group within ~12 GiB
-    size_t per = (size_t)v.n3 * 7 * sizeof(double);
+    // FCT scratch: six ratios per tracer of a group; keep the group within ~12 GiB
+    size_t per = (size_t)v.n3 * 6 * sizeof(double);
     size_t cap = (size_t)12 << 30;
     v.ngroup = (int)std::max<size_t>(1, std::min<size_t>((size_t)nt, cap / per));
-    DALLOC(t_lo, (size_t)v.n3 * v.ngroup, nullptr);
     DALLOC(Rfac, (size_t)v.n3 * 6 * v.ngroup, nullptr);
   }
   {
@@ -267,6 +274,11 @@ int uvic_b200_destroy(uvic_b200_ctx *ctx) {
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
   if (ctx->mobi_event) cudaEventDestroy(ctx->mobi_event);
+  if (ctx->main_done_event) cudaEventDestroy(ctx->main_done_event);
+  if (ctx->h2d_event) cudaEventDestroy(ctx->h2d_event);
+  if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+  if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
+  for (auto e : ctx->ev_batch) cudaEventDestroy(e);
   delete ctx;
   return 0;
 }
@@ -286,6 +298,10 @@ static int lev_index(int level) { return level + 1; }
 
 int uvic_b200_upload_t(uvic_b200_ctx *ctx, int level, const double *h) {
   if (level < -1 || level > 1) return fail(ctx, "upload_t: level must be -1, 0 or 1");
+  if (ctx->ahead_valid) {   // a look-ahead MOBI may be reading this slot; its result is void now
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->mobi_event, 0));
+    ctx->ahead_valid = false;
+  }
   CK(cudaMemcpyAsync(ctx->t_slot[ctx->lev[lev_index(level)]], h, (size_t)ctx->v.n3 * ctx->v.nt * sizeof(double),
                      cudaMemcpyHostToDevice, ctx->stream));
   return 0;
@@ -329,6 +345,10 @@ int uvic_b200_upload_vbc(uvic_b200_ctx *ctx, const double *stf, const double *bt
 int uvic_b200_upload_forcing(uvic_b200_ctx *ctx, const double *dnswr, const double *aice, const double *hice, const double *hsno) {
   DevView &v = ctx->v;
   if (!ctx->par.mobi) return fail(ctx, "upload_forcing: context was created without O_mobi");
+  if (ctx->ahead_valid) {
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->mobi_event, 0));
+    ctx->ahead_valid = false;
+  }
   size_t nb = (size_t)v.n2 * sizeof(double);
   if (dnswr) CK(cudaMemcpyAsync(v.dnswr, dnswr, nb, cudaMemcpyHostToDevice, ctx->stream));
   if (aice) CK(cudaMemcpyAsync(v.aice, aice, nb, cudaMemcpyHostToDevice, ctx->stream));
@@ -346,13 +366,31 @@ int uvic_b200_rotate(uvic_b200_ctx *ctx) {
   return 0;
 }
 
-// launch MOBI on the side stream; the main stream waits for it right before k_update
-static void fork_mobi(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
+static bool same_step(const uvic_b200_stepinfo &a, const uvic_b200_stepinfo &b) {
+  return a.dtts == b.dtts && a.leapfrog == b.leapfrog && a.relyr == b.relyr && a.co2ccn == b.co2ccn;
+}
+
+// MOBI of this step.  If the look-ahead of the previous step already produced the sources for exactly this step
+// (same stepinfo, same t(tau-1) slot, nothing uploaded in between) they are adopted; otherwise MOBI is launched on the
+// side stream now.  Either way the main stream waits for mobi_event right before the first sourced k_invtri.
+static void begin_mobi(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
   if (!ctx->par.mobi || ctx->mobi_inflight) return;
+  if (ctx->ahead_valid) {
+    const bool hit = !ctx->prof_on && same_step(*si, ctx->ahead_si) && ctx->ahead_tm1 == ctx->v.t_m1;
+    ctx->ahead_valid = false;
+    if (hit) {
+      ctx->src_cur = ctx->ahead_buf;
+      ctx->v.src = ctx->src_buf[ctx->src_cur];
+      ctx->mobi_inflight = true;
+      return;
+    }
+    // mispredicted: the side stream may still be writing the other buffer; order this step's MOBI behind it (same stream)
+  }
   if (ctx->prof_on) {
     // per-kernel timing: run MOBI in line so that no two kernels share the SMs and every
     // CUDA-event interval is the duration of exactly one kernel
-    launch_mobi(ctx, si);
+    cudaStreamWaitEvent(ctx->stream, ctx->mobi_event, 0);   // a look-ahead still in flight uses the same scratch
+    launch_mobi(ctx, ctx->v, si);
     cudaEventRecord(ctx->mobi_event, ctx->stream);
     ctx->mobi_inflight = true;
     return;
@@ -361,16 +399,57 @@ static void fork_mobi(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
   cudaStreamWaitEvent(ctx->stream2, ctx->fork_event, 0);
   cudaStream_t main_stream = ctx->stream;
   ctx->stream = ctx->stream2;
-  launch_mobi(ctx, si);
+  launch_mobi(ctx, ctx->v, si);
   ctx->stream = main_stream;
   cudaEventRecord(ctx->mobi_event, ctx->stream2);
   ctx->mobi_inflight = true;
+}
+
+// MOBI of the NEXT step (hinted), queued behind this step's kernels on the side stream
+static int lookahead_mobi(uvic_b200_ctx *ctx) {
+  if (!ctx->hint_valid) return 0;
+  ctx->hint_valid = false;
+  if (!ctx->par.mobi || ctx->prof_on) return 0;
+  if (!ctx->src_buf[1]) {
+    double *p = nullptr;
+    CK(cudaMalloc((void **)&p, (size_t)ctx->v.n3 * std::max(ctx->v.nsrc, 1) * sizeof(double)));
+    CK(cudaMemsetAsync(p, 0, (size_t)ctx->v.n3 * std::max(ctx->v.nsrc, 1) * sizeof(double), ctx->stream2));
+    ctx->src_buf[1] = p;
+    ctx->owned.push_back(p);
+  }
+  const uvic_b200_stepinfo &h = ctx->hint_si;
+  DevView vv = ctx->v;
+  vv.dtts = h.dtts;
+  vv.c2dtts = h.leapfrog ? 2.0 * h.dtts : h.dtts;
+  // after the rotation tau-1 of the next step is today's tau; a mixing step reads today's tau+1 instead
+  vv.t_m1 = h.leapfrog ? ctx->t_slot[ctx->lev[1]] : ctx->t_slot[ctx->lev[2]];
+  const int other = ctx->src_cur ^ 1;
+  vv.src = ctx->src_buf[other];
+  CK(cudaEventRecord(ctx->main_done_event, ctx->stream));
+  CK(cudaStreamWaitEvent(ctx->stream2, ctx->main_done_event, 0));
+  cudaStream_t main_stream = ctx->stream;
+  ctx->stream = ctx->stream2;
+  launch_mobi(ctx, vv, &h);
+  ctx->stream = main_stream;
+  CK(cudaEventRecord(ctx->mobi_event, ctx->stream2));
+  ctx->ahead_valid = true;
+  ctx->ahead_si = h;
+  ctx->ahead_tm1 = vv.t_m1;
+  ctx->ahead_buf = other;
+  return 0;
 }
 
 static void set_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
   ctx->v.dtts = si->dtts;
   ctx->v.c2dtts = si->leapfrog ? 2.0 * si->dtts : si->dtts;  // source/mom/mom.F:111-146
   set_levels(ctx, si->leapfrog != 0);
+}
+
+int uvic_b200_hint_next_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *next) {
+  if (!ctx) return 1;
+  ctx->hint_valid = next != nullptr;
+  if (next) ctx->hint_si = *next;
+  return 0;
 }
 
 int uvic_b200_isopyc(uvic_b200_ctx *ctx) {
@@ -386,7 +465,7 @@ int uvic_b200_vmixc(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
 }
 int uvic_b200_tracer(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
   set_step(ctx, si);
-  fork_mobi(ctx, si);
+  begin_mobi(ctx, si);
   launch_tracer(ctx, si);
   ctx->mobi_inflight = false;
   CK(cudaGetLastError());
@@ -395,11 +474,11 @@ int uvic_b200_tracer(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
     if (ctx->v.mskhr) launch_sumbk(ctx);
     CK(cudaGetLastError());
   }
-  return 0;
+  return lookahead_mobi(ctx);
 }
 int uvic_b200_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
   set_step(ctx, si);
-  fork_mobi(ctx, si);
+  begin_mobi(ctx, si);
   if (uvic_b200_isopyc(ctx)) return 1;
   if (uvic_b200_vmixc(ctx, si)) return 1;
   return uvic_b200_tracer(ctx, si);
@@ -408,14 +487,46 @@ int uvic_b200_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
 int uvic_b200_tracer_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si, const double *t_taum1, const double *t_tau,
                           const double *adv_vet, const double *adv_vnt, const double *adv_vbt, const double *stf,
                           const double *btf, double *t_taup1) {
+  DevView &v = ctx->v;
   if (t_taum1 && uvic_b200_upload_t(ctx, -1, t_taum1)) return 1;
   if (t_tau && uvic_b200_upload_t(ctx, 0, t_tau)) return 1;
-  if (uvic_b200_upload_adv_vel(ctx, adv_vet, adv_vnt, adv_vbt)) return 1;
-  if (uvic_b200_upload_vbc(ctx, stf, btf)) return 1;
-  if (uvic_b200_step(ctx, si)) return 1;
-  if (t_taup1) return uvic_b200_download_t(ctx, 1, t_taup1);
-  return uvic_b200_synchronize(ctx);
+  // velocities and vertical b.c. travel on the input copy stream while the kernels that do not need them
+  // (MOBI, Redi / GM coefficients, vmixc) already run; the copy stream first waits for everything queued so far
+  // on the main stream (the previous step still reads these arrays)
+  CK(cudaEventRecord(ctx->fork_event, ctx->stream));
+  CK(cudaStreamWaitEvent(ctx->copy_in, ctx->fork_event, 0));
+  if (adv_vet) CK(cudaMemcpyAsync(v.adv_vet, adv_vet, (size_t)v.n3 * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
+  if (adv_vnt) CK(cudaMemcpyAsync(v.adv_vnt, adv_vnt, (size_t)v.n3 * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
+  if (adv_vbt) CK(cudaMemcpyAsync(v.adv_vbt, adv_vbt, (size_t)v.n3z * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
+  if (stf) CK(cudaMemcpyAsync(v.stf, stf, (size_t)v.n2 * v.nt * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
+  if (btf) CK(cudaMemcpyAsync(v.btf, btf, (size_t)v.n2 * v.nt * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
+  CK(cudaEventRecord(ctx->h2d_event, ctx->copy_in));
+  set_step(ctx, si);
+  begin_mobi(ctx, si);
+  launch_isopyc_coef(ctx);
+  launch_vmixc(ctx);
+  CK(cudaStreamWaitEvent(ctx->stream, ctx->h2d_event, 0));
+  launch_isopyc_vel(ctx);
+  CK(cudaGetLastError());
+  // finished tracer batches stream to the host while the next batch computes (launch_tracer)
+  ctx->d2h_dst = t_taup1;
+  int rc = uvic_b200_tracer(ctx, si);
+  ctx->d2h_dst = nullptr;
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->copy_out));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  return 0;
 }
+
+int uvic_b200_pin_host(void *host, size_t bytes) {
+  // page-lock a host array (e.g. the COMMON block the Fortran shim passes every step) so that the copies above are
+  // truly asynchronous; returns 0 when the range is already registered
+  cudaError_t e = cudaHostRegister(host, bytes, cudaHostRegisterPortable);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return 0; }
+  return e == cudaSuccess ? 0 : 1;
+}
+int uvic_b200_unpin_host(void *host) { return cudaHostUnregister(host) == cudaSuccess ? 0 : 1; }
 
 int uvic_b200_inventory(uvic_b200_ctx *ctx, int level, double *out) {
   if (level < -1 || level > 1) return fail(ctx, "inventory: bad level");

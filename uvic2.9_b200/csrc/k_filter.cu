@@ -193,12 +193,12 @@ int filter_setup(uvic_b200_ctx *c, const int *kmt_h, const double *cst, const do
 }
 
 // one CTA per (item, tracer); dynamic smem: s[im], sprime[im], 2 scalars
-__global__ void __launch_bounds__(128) k_filter(const DevView v, const FiltItem *items, const double *mats) {
+__global__ void __launch_bounds__(128) k_filter(const DevView v, const FiltItem *items, const double *mats, int nbase) {
   extern __shared__ double sh[];
   const FiltItem it = items[blockIdx.x];
   const int im = it.im;
   double *s = sh, *sp = sh + im, *sc = sh + 2 * im;
-  double *X = v.t_p1 + (long long)blockIdx.y * v.n3;
+  double *X = v.t_p1 + (long long)(nbase + blockIdx.y) * v.n3;
   const long long line = X3(1, it.k, it.j);
   // gather the strip (filt.F:84-95): elements past the seam continue at i = 2
   for (int p = threadIdx.x; p < im; p += blockDim.x) {
@@ -246,11 +246,11 @@ __global__ void __launch_bounds__(128) k_filter(const DevView v, const FiltItem 
   }
 }
 
-void launch_filter(uvic_b200_ctx *c) {
+void launch_filter(uvic_b200_ctx *c, int nbase, int ng) {
   if (!c->par.fourfil || c->filt_nitems == 0) return;
   DevView &v = c->v;
-  dim3 grid(c->filt_nitems, v.nt);
+  dim3 grid(c->filt_nitems, ng);
   size_t smem = (size_t)(2 * c->filt_maxim + 4) * sizeof(double);
   ProfScope ps(c, "k_filter");
-  k_filter<<<grid, 128, smem, c->stream>>>(v, (const FiltItem *)c->filt_items, c->filt_mats);
+  k_filter<<<grid, 128, smem, c->stream>>>(v, (const FiltItem *)c->filt_items, c->filt_mats, nbase);
 }

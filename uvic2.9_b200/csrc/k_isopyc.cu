@@ -314,38 +314,35 @@ __global__ void __launch_bounds__(256) k_gm_faces(const DevView v) {
   }
 }
 
+// total (resolved + GM) velocities on the east and north faces used by the FCT kernels
+// (totadv = adv_v*t + adv_v*tiso, 09/mom/tracer_adv_flx.F:498-499,512-513), one thread per cell
+__global__ void __launch_bounds__(256) k_gm_total(const DevView v) {
+  int i, k, j;
+  if (!decode_ikj(v, (long long)blockIdx.x * blockDim.x + threadIdx.x, i, k, j)) return;
+  const int jtop = v.jbase + v.jl - 1;
+  const bool gm = v.isopycmix != 0;
+  const long long line = X3(1, k, j);
+  if (j <= v.jmt - 1 && j + 1 <= jtop)   // north face, rows 1..jmt-1
+    store_cyc(v, v.vn, line, i, v.adv_vnt[line + i - 1] + (gm ? v.adv_vntiso[line + i - 1] : 0.0));
+  if (j >= 2 && j <= v.jmt - 1)
+    store_cyc(v, v.ue, line, i, v.adv_vet[line + i - 1] + (gm ? v.adv_vetiso[line + i - 1] : 0.0));
+}
+
 // one thread per column: vertical GM velocity by continuity + downward cumulative sum
-// (09/mom/isopyc.F:1496-1531), then the total face velocities used by the FCT kernels
-// (totadv = adv_v*t + adv_v*tiso, 09/mom/tracer_adv_flx.F:498-499,512-513,524-525).
+// (09/mom/isopyc.F:1496-1531) and the total vertical velocity (09/mom/tracer_adv_flx.F:524-525)
 __global__ void __launch_bounds__(128) k_gm_column(const DevView v) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int ni = v.imt - 2;
   if (idx >= (long long)ni * v.jl) return;
   int i = (int)(idx % ni) + 2;
   int j = (int)(idx / ni) + v.jbase;
-  const int jtop = v.jbase + v.jl - 1;
   const bool gm = v.isopycmix != 0;
-  // north-face total velocity, rows 1..jmt-1
-  if (j <= v.jmt - 1 && j + 1 <= jtop) {
-    for (int k = 1; k <= v.km; k++) {
-      long long line = X3(1, k, j);
-      double val = v.adv_vnt[line + i - 1] + (gm ? v.adv_vntiso[line + i - 1] : 0.0);
-      store_cyc(v, v.vn, line, i, val);
-    }
-  }
-  if (j >= 2 && j <= v.jmt - 1) {
-    for (int k = 1; k <= v.km; k++) {
-      long long line = X3(1, k, j);
-      double val = v.adv_vet[line + i - 1] + (gm ? v.adv_vetiso[line + i - 1] : 0.0);
-      store_cyc(v, v.ue, line, i, val);
-    }
-  }
   if (j >= 2 && j <= v.jmt - 1 && j - 1 >= v.jbase) {
     int kb = v.kmt[X2(i, j)];
     double acc = 0.0;  // adv_vbtiso(i,0,j) = 0
     {
       long long l0 = X3Z(1, 0, j);
-      if (gm) store_cyc(v, v.adv_vbtiso, l0, i, (kb == 0) ? 0.0 : 0.0);
+      if (gm) store_cyc(v, v.adv_vbtiso, l0, i, 0.0);
       store_cyc(v, v.wb, l0, i, v.adv_vbt[l0 + i - 1] + 0.0);
     }
     for (int k = 1; k <= v.km; k++) {
@@ -364,7 +361,8 @@ __global__ void __launch_bounds__(128) k_gm_column(const DevView v) {
   }
 }
 
-void launch_isopyc(uvic_b200_ctx *c) {
+// the part of isopyc that depends on t(tau-1) only
+void launch_isopyc_coef(uvic_b200_ctx *c) {
   DevView &v = c->v;
   long long ncell = (long long)(v.imt - 2) * v.km * v.jl;
   if (v.isopycmix) {
@@ -372,6 +370,15 @@ void launch_isopyc(uvic_b200_ctx *c) {
     KLAUNCH("k_isocoef", k_isocoef, cdiv(ncell, 256), 256, v);
     KLAUNCH("k_gm_faces", k_gm_faces, cdiv(ncell, 256), 256, v);
   }
+}
+// the part that also needs the resolved advective velocities of this step
+void launch_isopyc_vel(uvic_b200_ctx *c) {
+  DevView &v = c->v;
   long long ncol = (long long)(v.imt - 2) * v.jl;
+  KLAUNCH("k_gm_total", k_gm_total, cdiv(ncol * v.km, 256), 256, v);
   KLAUNCH("k_gm_column", k_gm_column, cdiv(ncol, 128), 128, v);
+}
+void launch_isopyc(uvic_b200_ctx *c) {
+  launch_isopyc_coef(c);
+  launch_isopyc_vel(c);
 }

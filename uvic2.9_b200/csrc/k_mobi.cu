@@ -238,7 +238,7 @@ __device__ __forceinline__ double evans_parslow(double gl_x, double gd, double f
 // oxygen dependent rate factors (09/mom/mobi.F:775-835), the pre-loop light harvesting and
 // Evans-Parslow integrals of mobi_src (:1928-2003), and the oxygen / nitrate switches of
 // the denitrification terms (:1035-1046, 1301-1322).
-__global__ void __launch_bounds__(128) k_mobi_cell(const DevView v) {
+__global__ void __launch_bounds__(128, 5) k_mobi_cell(const DevView v) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int ni = v.imt - 2, nrow = v.jhi - v.jlo + 1;
   if (idx >= (long long)ni * v.km * nrow) return;
@@ -832,18 +832,27 @@ struct WsSm {
   double R[R_N][32];
   double L[L_N][32];
 };
-#define WS_WARPS 8
+#define WS_WARPS 4
+// barrier of one column group: named barrier 1 + group, WS_WARPS warps
+#define WS_BAR() asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(32 * WS_WARPS) : "memory")
+#define WS_ROLES 8   // every warp runs roles w and w + WS_WARPS one after the other
 
-__global__ void __launch_bounds__(32 * WS_WARPS) k_mobi_ws(const DevView v, int mi, int nbio, double dtbio, double rdtts, double rnbio) {
+// G column groups per CTA: the groups of a CTA are independent (own shared-memory block, own named barrier) but run
+// the same instruction stream, so an SM fetches the (instruction-cache sized) sub-step code once for G groups.
+template <int G>
+__global__ void __launch_bounds__(32 * WS_WARPS * G) k_mobi_ws(const DevView v, int mi, int nbio, double dtbio, double rdtts, double rnbio) {
   extern __shared__ __align__(16) unsigned char ws_raw[];
-  WsSm &sm = *reinterpret_cast<WsSm *>(ws_raw);
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int cidx = blockIdx.x * 32 + lane;
+  const int grp = threadIdx.x / (32 * WS_WARPS);
+  const int gidx = blockIdx.x * G + grp;                    // column group of these WS_WARPS warps
+  if (gidx * 32 >= v.mobi_ncols) return;                    // whole group idle (its barrier has no other users)
+  WsSm &sm = *reinterpret_cast<WsSm *>(ws_raw + (size_t)grp * sizeof(WsSm));
+  const int lane = threadIdx.x & 31, w = (threadIdx.x >> 5) % WS_WARPS;
+  const int cidx = gidx * 32 + lane;
   const bool valid = cidx < v.mobi_ncols;
   const int col = valid ? v.mobi_cols[cidx] : 0;
   const int i = col % v.imt + 1, j = col / v.imt + v.jbase;
   const int kmx = valid ? v.kmt[col] : 0;
-  const int kmax = v.kmt[v.mobi_cols[blockIdx.x * 32]];   // columns are sorted by depth, deepest first
+  const int kmax = v.kmt[v.mobi_cols[gidx * 32]];   // columns are sorted by depth, deepest first
   const MobiPar *__restrict__ P = v.mobi_par;
   const int *__restrict__ ix = v.mobi_idx;
   const long long n3 = v.n3;
@@ -881,49 +890,59 @@ __global__ void __launch_bounds__(32 * WS_WARPS) k_mobi_ws(const DevView v, int 
     }
     // ---- P1: gather, flags from the raw inputs, clip (09/mom/tracer.F:393-503, mobi.F:1781-1926) ----
     {
-      double raw[4];
+      double raw[8];
 #pragma unroll
-      for (int q = 0; q < 4; q++) {
-        const int m = 4 * w + q;
+      for (int q = 0; q < 8; q++) {
+        const int m = 8 * w + q;
         raw[q] = act ? v.t_m1[c + (long long)(ix[IX_TR + m] - 1) * n3] : 1.0;
         SF(m) = (raw[q] - TRCMIN >= 0.0) ? 1.0 : 0.0;
         const double cl = fmax(raw[q], TRCMIN);
         SB(m) = cl;
         SC(m) = cl;
       }
-      if (w == 0) {   // states 0..3: PO4, PHYT, PHYT_PHOS, ZOOP
+      if (w == 0) {   // states 0..7 include PHYT, PHYT_PHOS, DETR, DETR_PHOS
         const double ptn_P = raw[V_PHYT_PHOS] / raw[V_PHYT];
         SL(L_ptn_P0) = ptn_P;
         SL(L_sf_P_phosflag) = 0.5 + fsign(0.5, ptn_P - gamma1 * redptn);
-      }
-      if (w == 1) {   // states 4..7: DETR, DETR_PHOS, DIC, DIC13
-        const double ptn_detr = raw[V_DETR_PHOS - 4] / raw[V_DETR - 4];
+        const double ptn_detr = raw[V_DETR_PHOS] / raw[V_DETR];
         SL(L_ptn_detr0) = ptn_detr;
         SL(L_sf_detr_phosflag) = 0.5 + fsign(0.5, ptn_detr - gamma1 * redptn);
       }
     }
     // level constants of this warp's role
     const double bct = PRE(PR_BCT);
-    double lc0 = 0.0, lc1 = 0.0, lc2 = 0.0, lc3 = 0.0, lc4 = 0.0, lc5 = 0.0, lc6 = 0.0;
+    double lc0 = 0.0, lc1 = 0.0, lc2 = 0.0, lc3 = 0.0, lc4 = 0.0, lc5 = 0.0, lc6 = 0.0, lc7 = 0.0;
     switch (w) {
       case 0: lc0 = PRE(PR_AVEJ); break;
       case 1: lc0 = PRE(PR_AVEJ_DIAT); break;
       case 2: lc0 = P->gbio * PRE(PR_BCTZ); lc1 = PRE(PR_NUD); lc2 = PRE(PR_DISSK1); lc3 = PRE(PR_CAPR);
-              lc4 = P->wd[k - 1]; lc5 = P->wc[k - 1]; lc6 = P->wo[k - 1]; break;
-      case 3: lc0 = PRE(PR_AOU8); lc1 = PRE(PR_O2FLAG); break;
-      case 6: lc0 = PRE(PR_AC13B); break;
-      case 7: lc0 = PRE(PR_AVEJ_D); break;
+              lc4 = P->wd[k - 1]; lc5 = P->wc[k - 1]; lc6 = P->wo[k - 1];
+              lc7 = PRE(PR_AC13B); break;                                             // role 6
+      case 3: lc0 = PRE(PR_AOU8); lc1 = PRE(PR_O2FLAG); lc2 = PRE(PR_AVEJ_D); break;   // roles 3 and 7
       default: break;
     }
     acc0 = acc1 = acc2 = acc3 = acc4 = acc5 = acc6 = 0.0;
-    __syncthreads();
+    WS_BAR();
 
-    for (int n = 1; n <= nbio; n++) {
-      const int par = (n - 1) & 1;
-      const double ptn_P = SL(L_ptn_P0 + par), ptn_detr = SL(L_ptn_detr0 + par);
-      // ================= stage 1: rates from the state at the start of the sub-step =================
-      switch (w) {
-        case 0: {
+#define UPD(m, expr)                                   \
+  do {                                                 \
+    const double nv_ = (expr);                         \
+    SB(m) = nv_;                                       \
+    if (nv_ - TRCMIN < 0.0) SF(m) = 0.0;               \
+  } while (0)
+    // Role-major loops: every warp runs its own compact sub-step loop (stage 1, barrier, stage 2, barrier), so its
+    // instruction stream is a short predictable loop instead of two indirect branches per sub-step into a kernel-sized
+    // switch.  All warps execute the same number of barriers.
+
+#define WS_LOOP_HEAD                          \
+    for (int n = 1; n <= nbio; n++) {         \
+      const int par = (n - 1) & 1;            \
+      const double ptn_P = SL(L_ptn_P0 + par), ptn_detr = SL(L_ptn_detr0 + par); \
+      (void)ptn_P; (void)ptn_detr;
+    switch (w) {
+      case 0: {   // roles 0 and 4
+        WS_LOOP_HEAD
+        {
           // phytoplankton growth (:2150-2206), NO3 assimilation fractionation (:2441-2452)
           const double biophyt = SB(V_PHYT), biodfe = SB(V_DFE), biodop = SB(V_DOP), biopo4 = SB(V_PO4), biono3 = SB(V_NO3);
           double p1 = fmin(biophyt, P->pmax), p2 = fmax(0.0, biophyt - P->pmax);
@@ -946,8 +965,59 @@ __global__ void __launch_bounds__(32 * WS_WARPS) k_mobi_ws(const DevView v, int 
           double rno3 = fmax(fmin(SB(V_DIN15) / (biono3 - SB(V_DIN15)), 2 * RN15STD), RN15STD / 2.);
           double bassim = rno3 + P->eps_assim * (1 - uno3) / uno3 * log(1 - uno3) * rno3 / 1000.;
           SR(fcassim) = bassim / (1 + bassim);
-        } break;
-        case 1: {
+        }
+        {
+          // organic iron adsorption exponent (:2278), excretion / N2-fixation fractionation (:2466-2478), calcite 13C ratios
+          const double biozoop = SB(V_ZOOP);
+          SR(pw58) = pow(((SB(V_DETR) * SF(V_DETR)) * P->mc * redctn), 0.58);
+          double rzoop = fmax(fmin(SB(V_ZOOPN15) / (biozoop - SB(V_ZOOPN15)), 2. * RN15STD), RN15STD / 2.);
+          double bexcr = rzoop - P->eps_excr * rzoop / 1000.;
+          SR(fcexcr) = bexcr / (1 + bexcr);
+          double bnfix = RN15STD - P->eps_nfix * RN15STD / 1000.;
+          SR(fcnfix) = bnfix / (1 + bnfix);
+          SR(rtdic13) = CL13(SB(V_DIC13) / SB(V_DIC));
+          SR(rtcaco3c13) = CL13(SB(V_CACO3C13) / SB(V_CACO3));
+          double GM15ptc = 0.0060 + 0.0069 * SB(V_PO4);
+          SR(GM15ptn) = GM15ptc * redctn * 1.e3;
+        }
+        WS_BAR();
+        {
+          const double npp = SR(npp), dopupt = SR(dopupt), morp = SR(morp), morpt = SR(morpt), graz = SR(graz), remi = SR(remi);
+          const double morpt_D = SR(morpt_D), npp_D = SR(npp_D), dopupt_D = SR(dopupt_D), recy_dop = SR(recy_dop), excr = SR(excr);
+          const double morpt_Diat = SR(morpt_Diat), npp_Diat = SR(npp_Diat), dopupt_Diat = SR(dopupt_Diat), morp_Diat = SR(morp_Diat);
+          const double GM15ptn = SR(GM15ptn);
+          const double biophyt = SB(V_PHYT), biophyt_phos = SB(V_PHYT_PHOS);
+          UPD(V_PO4, SB(V_PO4) + dtbio * (dopupt * ptn_P - GM15ptn * npp + (1. - dfrt) * morpt * ptn_P + (1. - pfr) * remi * ptn_detr +
+                                         diazptn * (morpt_D - (npp_D - dopupt_D)) + recy_dop +
+                                         redptn * (excr + (1. - dfrt) * morpt_Diat - (npp_Diat - dopupt_Diat))));
+          UPD(V_DOP, SB(V_DOP) + dtbio * (dfr * morp * ptn_P + redptn * (dfr * morp_Diat + dfrt * morpt_Diat - dopupt_Diat) +
+                                         dfrt * morpt * ptn_P + pfr * remi * ptn_detr - ptn_P * dopupt - diazptn * dopupt_D - recy_dop));
+          const double nphyt = biophyt + dtbio * (npp - morp - graz - morpt);
+          const double nphos = biophyt_phos + dtbio * (npp * GM15ptn - morp * ptn_P - graz * ptn_P - morpt * ptn_P);
+          UPD(V_PHYT, nphyt);
+          UPD(V_PHYT_PHOS, nphos);
+          SL(L_ptn_P0 + (par ^ 1)) = nphos / nphyt;
+        }
+        {
+          const double rtphytn15 = SR(rtphytn15), rtdiatn15 = SR(rtdiatn15), rtdiazn15 = SR(rtdiazn15), rtdetrn15 = SR(rtdetrn15);
+          const double fcassim = SR(fcassim), fcexcr = SR(fcexcr), fcrecy = SR(fcrecy);
+          const double morpt = SR(morpt), morpt_Diat = SR(morpt_Diat), npp_Diat = SR(npp_Diat), excr = SR(excr), morpt_D = SR(morpt_D);
+          const double nr_excr_D = SR(nr_excr_D), morp_D = SR(morp_D), remi = SR(remi), recy_don = SR(recy_don), npp = SR(npp);
+          const double no3upt_D = SR(no3upt_D), morp = SR(morp), morp_Diat = SR(morp_Diat);
+          const double nr_excr_P = 0.0, nr_excr_detr = 0.0;
+          UPD(V_DIN15, SB(V_DIN15) + dtbio * (rtphytn15 * (1. - dfrt) * morpt + rtphytn15 * nr_excr_P + rtdiatn15 * (1. - dfrt) * morpt_Diat -
+                                             fcassim * npp_Diat + fcexcr * excr + rtdiazn15 * morpt_D + rtdiazn15 * nr_excr_D +
+                                             rtdiazn15 * morp_D * (1. - rnd) + rtdetrn15 * (1. - pfr) * remi + rtdetrn15 * nr_excr_detr +
+                                             fcrecy * recy_don - fcassim * npp - fcassim * no3upt_D));
+          UPD(V_DON15, SB(V_DON15) + dtbio * (dfr * rtphytn15 * morp + dfr * rtdiatn15 * morp_Diat + dfrt * rtdiatn15 * morpt_Diat +
+                                             dfrt * rtphytn15 * morpt + rtdetrn15 * pfr * remi - fcrecy * recy_don));
+        }
+        WS_BAR();
+        }
+      } break;
+      case 1: {   // roles 1 and 5
+        WS_LOOP_HEAD
+        {
           // diatom growth (:2160-2200), opal production ratio (:2540)
           const double biodiat = SB(V_DIAT), biodfe = SB(V_DFE), biosil = SB(V_SIL), biodop = SB(V_DOP), biopo4 = SB(V_PO4);
           const double biono3 = SB(V_NO3);
@@ -969,8 +1039,63 @@ __global__ void __launch_bounds__(32 * WS_WARPS) k_mobi_ws(const DevView v, int 
           SR(dopupt_Diat) = npp_Diat * dopupt_Diat_flag;
           SR(npp_Diat) = npp_Diat * SF(V_NO3) * (dopupt_Diat_flag * SF(V_DOP) + (1. - dopupt_Diat_flag) * SF(V_PO4)) * SF(V_DIN15);
           SR(sipr0) = (-0.46204044117647 * tanh(6.9 * biodfe * 1.e3 + -3.673092) + 1.60266544117647);
-        } break;
-        case 2: {
+        }
+        {
+          // DON recycling and its fractionation (:2453-2465), 15N ratios of the organic pools (:2479-2500)
+          const double biodon = SB(V_DON);
+          double recy_don = P->nudon0 * bct * biodon;
+          recy_don = recy_don * SF(V_DON) * SF(V_DON15);
+          SR(recy_don) = recy_don;
+          double udon = fmax(fmin(recy_don * dtbio / biodon, 0.999), TRCMIN);
+          double rdon = fmax(fmin(SB(V_DON15) / (biodon - SB(V_DON15)), 2 * RN15STD), RN15STD / 2.);
+          double brecy = rdon + P->eps_recy * (1 - udon) / udon * log(1 - udon) * rdon / 1000.;
+          SR(fcrecy) = brecy / (1 + brecy);
+          SR(rtphytn15) = CL15(SB(V_PHYTN15) / SB(V_PHYT));
+          SR(rtdiatn15) = CL15(SB(V_DIATN15) / SB(V_DIAT));
+          SR(rtzoopn15) = CL15(SB(V_ZOOPN15) / SB(V_ZOOP));
+          const double rtdetrn15 = CL15(SB(V_DETRN15) / SB(V_DETR));
+          SR(rtdetrn15) = rtdetrn15;
+          SR(rtdiazn15) = CL15(SB(V_DIAZN15) / SB(V_DIAZ));
+          acc0 = acc0 + rtdetrn15;   // rn15expoout
+        }
+        WS_BAR();
+        {
+          const double morp = SR(morp), sf = SR(sf), morz = SR(morz), remi = SR(remi), graz_Det = SR(graz_Det), expo = SR(expo);
+          const double morp_D = SR(morp_D), morp_Diat = SR(morp_Diat), sf_phos = SR(sf_phos), expo_phos = SR(expo_phos);
+          const double impo = SL(X_expo) * dztrk, impo_phos = SL(X_expo_phos) * dztrk;
+          const double ndetr = SB(V_DETR) + dtbio * ((1. - dfr) * morp + sf + morz - remi - graz_Det - expo + impo + morp_D * rnd +
+                                                     (1. - dfr) * morp_Diat);
+          const double ndphos = SB(V_DETR_PHOS) + dtbio * ((1. - dfr) * morp * ptn_P + sf_phos + morz * redptn - remi * ptn_detr -
+                                                           graz_Det * ptn_detr - expo_phos + impo_phos + morp_D * rnd * redptn +
+                                                           (1. - dfr) * morp_Diat * redptn);
+          UPD(V_DETR, ndetr);
+          UPD(V_DETR_PHOS, ndphos);
+          SL(L_ptn_detr0 + (par ^ 1)) = ndphos / ndetr;
+          UPD(V_ZOOP, SB(V_ZOOP) + dtbio * (SR(dig) - morz - SR(graz_Z) - SR(excr)));
+          UPD(V_DIAZ, SB(V_DIAZ) + dtbio * (SR(npp_D) - morp_D - SR(morpt_D) - SR(graz_D)));
+          UPD(V_DIAT, SB(V_DIAT) + dtbio * (SR(npp_Diat) - morp_Diat - SR(graz_Diat) - SR(morpt_Diat)));
+        }
+        {
+          const double rtphytn15 = SR(rtphytn15), rtdiatn15 = SR(rtdiatn15), rtdiazn15 = SR(rtdiazn15), rtdetrn15 = SR(rtdetrn15);
+          const double rtzoopn15 = SR(rtzoopn15), fcassim = SR(fcassim), fcexcr = SR(fcexcr), fcnfix = SR(fcnfix);
+          const double npp = SR(npp), morp = SR(morp), graz = SR(graz), morpt = SR(morpt), npp_Diat = SR(npp_Diat);
+          const double morp_Diat = SR(morp_Diat), graz_Diat = SR(graz_Diat), morpt_Diat = SR(morpt_Diat), morz = SR(morz);
+          const double graz_Z = SR(graz_Z), excr = SR(excr), npp_D = SR(npp_D), no3upt_D = SR(no3upt_D), morp_D = SR(morp_D);
+          const double graz_D = SR(graz_D), morpt_D = SR(morpt_D);
+          UPD(V_PHYTN15, SB(V_PHYTN15) + dtbio * (fcassim * npp - rtphytn15 * morp - rtphytn15 * graz - rtphytn15 * morpt));
+          UPD(V_DIATN15, SB(V_DIATN15) + dtbio * (fcassim * npp_Diat - rtdiatn15 * morp_Diat - rtdiatn15 * graz_Diat - rtdiatn15 * morpt_Diat));
+          UPD(V_ZOOPN15, SB(V_ZOOPN15) + dtbio * (rtphytn15 * SR(dig_P) + rtdiatn15 * SR(dig_Diat) + rtzoopn15 * SR(dig_Z) +
+                                                 rtdetrn15 * SR(dig_Det) + rtdiazn15 * SR(dig_D) - rtzoopn15 * morz - rtzoopn15 * graz_Z -
+                                                 fcexcr * excr));
+          UPD(V_DIAZN15, SB(V_DIAZN15) + dtbio * (fcnfix * (npp_D - no3upt_D) + fcassim * no3upt_D - rtdiazn15 * morp_D - rtdiazn15 * graz_D -
+                                                 rtdiazn15 * morpt_D));
+        }
+        WS_BAR();
+        }
+      } break;
+      case 2: {   // roles 2 and 6
+        WS_LOOP_HEAD
+        {
           // grazing, mortality, remineralisation, sinking (:2208-2260), flags (:2284-2334), digestion / sloppy feeding (:2335-2440)
           const double biophyt = SB(V_PHYT), biodetr = SB(V_DETR), biozoop = SB(V_ZOOP), biodiaz = SB(V_DIAZ), biodiat = SB(V_DIAT);
           const double gmax = lc0, nud = lc1;
@@ -1051,130 +1176,20 @@ __global__ void __launch_bounds__(32 * WS_WARPS) k_mobi_ws(const DevView v, int 
           // *out sums (:2762-2777)
           acc0 = acc0 + expo; acc1 = acc1 + expo_phos; acc2 = acc2 + calpro; acc3 = acc3 + dissl; acc4 = acc4 + expocaco3;
           acc5 = acc5 + expoopl; acc6 = acc6 + expofe;
-        } break;
-        case 3: {
-          // iron speciation and scavenging (:2262-2283)
-          const double biodon = SB(V_DON), biodfe = SB(V_DFE), aou8 = lc0, o2flag = lc1;
-          double ligand = fmax(aou8 / 66. + pow(biodon, 0.8) / 4.8, 0.5) / 1000.;
-          double fepa = (1.0 + P->kfeleq * (ligand - biodfe)) * o2flag;
-          double feprime = ((-fepa + sqrt(fepa * fepa + 4.0 * P->kfeleq * biodfe)) / (2.0 * P->kfeleq)) * o2flag;
-          double fecol = P->kfecol * (feprime * feprime) * o2flag;
-          SR(feprime) = feprime;
-          SR(fecol) = fecol * SF(V_DFE);
-        } break;
-        case 4: {
-          // organic iron adsorption exponent (:2278), excretion / N2-fixation fractionation (:2466-2478), calcite 13C ratios
-          const double biozoop = SB(V_ZOOP);
-          SR(pw58) = pow(((SB(V_DETR) * SF(V_DETR)) * P->mc * redctn), 0.58);
-          double rzoop = fmax(fmin(SB(V_ZOOPN15) / (biozoop - SB(V_ZOOPN15)), 2. * RN15STD), RN15STD / 2.);
-          double bexcr = rzoop - P->eps_excr * rzoop / 1000.;
-          SR(fcexcr) = bexcr / (1 + bexcr);
-          double bnfix = RN15STD - P->eps_nfix * RN15STD / 1000.;
-          SR(fcnfix) = bnfix / (1 + bnfix);
-          SR(rtdic13) = CL13(SB(V_DIC13) / SB(V_DIC));
-          SR(rtcaco3c13) = CL13(SB(V_CACO3C13) / SB(V_CACO3));
-          double GM15ptc = 0.0060 + 0.0069 * SB(V_PO4);
-          SR(GM15ptn) = GM15ptc * redctn * 1.e3;
-        } break;
-        case 5: {
-          // DON recycling and its fractionation (:2453-2465), 15N ratios of the organic pools (:2479-2500)
-          const double biodon = SB(V_DON);
-          double recy_don = P->nudon0 * bct * biodon;
-          recy_don = recy_don * SF(V_DON) * SF(V_DON15);
-          SR(recy_don) = recy_don;
-          double udon = fmax(fmin(recy_don * dtbio / biodon, 0.999), TRCMIN);
-          double rdon = fmax(fmin(SB(V_DON15) / (biodon - SB(V_DON15)), 2 * RN15STD), RN15STD / 2.);
-          double brecy = rdon + P->eps_recy * (1 - udon) / udon * log(1 - udon) * rdon / 1000.;
-          SR(fcrecy) = brecy / (1 + brecy);
-          SR(rtphytn15) = CL15(SB(V_PHYTN15) / SB(V_PHYT));
-          SR(rtdiatn15) = CL15(SB(V_DIATN15) / SB(V_DIAT));
-          SR(rtzoopn15) = CL15(SB(V_ZOOPN15) / SB(V_ZOOP));
-          const double rtdetrn15 = CL15(SB(V_DETRN15) / SB(V_DETR));
-          SR(rtdetrn15) = rtdetrn15;
-          SR(rtdiazn15) = CL15(SB(V_DIAZN15) / SB(V_DIAZ));
-          acc0 = acc0 + rtdetrn15;   // rn15expoout
-        } break;
-        case 6: {
+        }
+        {
           // 13C fractionation of primary production and ratios of the living pools (:2501-2530)
           const double biodic = SB(V_DIC);
           double rdic13 = fmax(fmin(SB(V_DIC13) / (biodic - SB(V_DIC13)), 2. * RC13STD), 0.5 * RC13STD);
-          double bc13npp = lc0 * rdic13;
+          double bc13npp = lc7 * rdic13;
           SR(fcnpp) = bc13npp / (1 + bc13npp);
           SR(rtphytc13) = CL13(SB(V_PHYTC13) / (SB(V_PHYT) * redctn));
           SR(rtdiatc13) = CL13(SB(V_DIATC13) / (SB(V_DIAT) * redctn));
           SR(rtzoopc13) = CL13(SB(V_ZOOPC13) / (SB(V_ZOOP) * redctn));
           SR(rtdetrc13) = CL13(SB(V_DETRC13) / (SB(V_DETR) * redctn));
-        } break;
-        case 7: {
-          // diazotroph growth and N2 fixation (:2164-2166, 2200-2206, 2226-2232); the phosphorus limitation of the
-          // ordinary phytoplankton is re-derived here (same expressions as warp 0)
-          const double biophyt = SB(V_PHYT), biodfe = SB(V_DFE), biodop = SB(V_DOP), biopo4 = SB(V_PO4), biono3 = SB(V_NO3);
-          const double biodiaz = SB(V_DIAZ);
-          double p1 = fmin(biophyt, P->pmax), p2 = fmax(0.0, biophyt - P->pmax);
-          double k1n = (P->knmin * p1 + P->knmax * p2) / (p1 + p2);
-          double k1p_P = k1n * ptn_P;
-          double deffe_D = biodfe / (P->kfe_D + biodfe);
-          double jmax_D = fmax(0., P->abio_P * (bct - P->dbct_D) * deffe_D) * P->jdiar;
-          double limP_dop = P->hdop * biodop / (k1p_P + biodop);
-          double limP_po4 = biopo4 / (k1p_P + biopo4);
-          double dopupt_flag = 0.5 + fsign(0.5, limP_dop - limP_po4);
-          double limP = limP_dop * dopupt_flag + limP_po4 * (1. - dopupt_flag);
-          double u_D = fmin(lc0, jmax_D * limP);
-          double npp_D = fmax(0., u_D * biodiaz);
-          double no3upt_D = (0.5 + 0.5 * tanh(biono3 - 5.)) * npp_D;
-          SR(dopupt_D) = npp_D * dopupt_flag;
-          npp_D = npp_D * (dopupt_flag * SF(V_DOP) + (1. - dopupt_flag) * SF(V_PO4)) * SF(V_DIN15);
-          no3upt_D = no3upt_D * SF(V_NO3) * SF(V_DIN15);
-          SR(npp_D) = npp_D;
-          SR(no3upt_D) = no3upt_D;
-          acc0 = acc0 + npp_D - no3upt_D;   // nfixout
-          SR(rtdoc13) = CL13(SB(V_DOC13) / (SB(V_DON) * redctn));
-          SR(rtdiazc13) = CL13(SB(V_DIAZC13) / (biodiaz * redctn));
-        } break;
-      }
-      __syncthreads();
-      // ================= stage 2: forward Euler on the owned state variables (:2552-2760) =================
-#define UPD(m, expr)                                   \
-  do {                                                 \
-    const double nv_ = (expr);                         \
-    SB(m) = nv_;                                       \
-    if (nv_ - TRCMIN < 0.0) SF(m) = 0.0;               \
-  } while (0)
-      switch (w) {
-        case 0: {
-          const double npp = SR(npp), dopupt = SR(dopupt), morp = SR(morp), morpt = SR(morpt), graz = SR(graz), remi = SR(remi);
-          const double morpt_D = SR(morpt_D), npp_D = SR(npp_D), dopupt_D = SR(dopupt_D), recy_dop = SR(recy_dop), excr = SR(excr);
-          const double morpt_Diat = SR(morpt_Diat), npp_Diat = SR(npp_Diat), dopupt_Diat = SR(dopupt_Diat), morp_Diat = SR(morp_Diat);
-          const double GM15ptn = SR(GM15ptn);
-          const double biophyt = SB(V_PHYT), biophyt_phos = SB(V_PHYT_PHOS);
-          UPD(V_PO4, SB(V_PO4) + dtbio * (dopupt * ptn_P - GM15ptn * npp + (1. - dfrt) * morpt * ptn_P + (1. - pfr) * remi * ptn_detr +
-                                         diazptn * (morpt_D - (npp_D - dopupt_D)) + recy_dop +
-                                         redptn * (excr + (1. - dfrt) * morpt_Diat - (npp_Diat - dopupt_Diat))));
-          UPD(V_DOP, SB(V_DOP) + dtbio * (dfr * morp * ptn_P + redptn * (dfr * morp_Diat + dfrt * morpt_Diat - dopupt_Diat) +
-                                         dfrt * morpt * ptn_P + pfr * remi * ptn_detr - ptn_P * dopupt - diazptn * dopupt_D - recy_dop));
-          const double nphyt = biophyt + dtbio * (npp - morp - graz - morpt);
-          const double nphos = biophyt_phos + dtbio * (npp * GM15ptn - morp * ptn_P - graz * ptn_P - morpt * ptn_P);
-          UPD(V_PHYT, nphyt);
-          UPD(V_PHYT_PHOS, nphos);
-          SL(L_ptn_P0 + (par ^ 1)) = nphos / nphyt;
-        } break;
-        case 1: {
-          const double morp = SR(morp), sf = SR(sf), morz = SR(morz), remi = SR(remi), graz_Det = SR(graz_Det), expo = SR(expo);
-          const double morp_D = SR(morp_D), morp_Diat = SR(morp_Diat), sf_phos = SR(sf_phos), expo_phos = SR(expo_phos);
-          const double impo = SL(X_expo) * dztrk, impo_phos = SL(X_expo_phos) * dztrk;
-          const double ndetr = SB(V_DETR) + dtbio * ((1. - dfr) * morp + sf + morz - remi - graz_Det - expo + impo + morp_D * rnd +
-                                                     (1. - dfr) * morp_Diat);
-          const double ndphos = SB(V_DETR_PHOS) + dtbio * ((1. - dfr) * morp * ptn_P + sf_phos + morz * redptn - remi * ptn_detr -
-                                                           graz_Det * ptn_detr - expo_phos + impo_phos + morp_D * rnd * redptn +
-                                                           (1. - dfr) * morp_Diat * redptn);
-          UPD(V_DETR, ndetr);
-          UPD(V_DETR_PHOS, ndphos);
-          SL(L_ptn_detr0 + (par ^ 1)) = ndphos / ndetr;
-          UPD(V_ZOOP, SB(V_ZOOP) + dtbio * (SR(dig) - morz - SR(graz_Z) - SR(excr)));
-          UPD(V_DIAZ, SB(V_DIAZ) + dtbio * (SR(npp_D) - morp_D - SR(morpt_D) - SR(graz_D)));
-          UPD(V_DIAT, SB(V_DIAT) + dtbio * (SR(npp_Diat) - morp_Diat - SR(graz_Diat) - SR(morpt_Diat)));
-        } break;
-        case 2: {
+        }
+        WS_BAR();
+        {
           const double excr = SR(excr), remi = SR(remi), morpt = SR(morpt), npp = SR(npp), morpt_Diat = SR(morpt_Diat);
           const double npp_Diat = SR(npp_Diat), morpt_D = SR(morpt_D), npp_D = SR(npp_D), recy_don = SR(recy_don);
           const double nr_excr_D = SR(nr_excr_D), morp_D = SR(morp_D), no3upt_D = SR(no3upt_D), morp = SR(morp);
@@ -1187,57 +1202,8 @@ __global__ void __launch_bounds__(32 * WS_WARPS) k_mobi_ws(const DevView v, int 
                                          morpt_D - no3upt_D + recy_don + nr_excr_D + nr_excr_P + nr_excr_detr + morp_D * (1. - rnd)));
           UPD(V_DON, SB(V_DON) + dtbio * (dfr * morp + dfrt * morpt + pfr * remi - recy_don + dfr * morp_Diat + dfrt * morpt_Diat));
           UPD(V_CACO3, SB(V_CACO3) + dtbio * (SR(calpro) - SR(dissl) - SR(expocaco3) + SL(X_expocaco3) * dztrk));
-        } break;
-        case 3: {
-          const double excr = SR(excr), morpt = SR(morpt), npp = SR(npp), morpt_D = SR(morpt_D), npp_D = SR(npp_D);
-          const double recy_don = SR(recy_don), nr_excr_D = SR(nr_excr_D), morp_D = SR(morp_D), remife = SR(remife), fecol = SR(fecol);
-          const double morpt_Diat = SR(morpt_Diat), npp_Diat = SR(npp_Diat), sf = SR(sf), morp = SR(morp), morz = SR(morz);
-          const double graz_Det = SR(graz_Det), expofe = SR(expofe), morp_Diat = SR(morp_Diat), sf_Diat = SR(sf_Diat);
-          const double nr_excr_P = 0.0, nr_excr_detr = 0.0;
-          const double o2flag = lc1;
-          double feorgads = (P->kfeorg * SR(pw58) * SR(feprime)) * o2flag;
-          feorgads = feorgads * SF(V_DFE);
-          const double opldis = SR(opldis);
-          const double oplpro = (morp_Diat + sf_Diat) * SR(sipr0) * SF(V_SIL) * (1.e-3);
-          UPD(V_DFE, SB(V_DFE) + dtbio * (rfeton * (excr + (1. - dfrt) * morpt - npp + morpt_D - npp_D + recy_don + nr_excr_D + nr_excr_P +
-                                                    nr_excr_detr + morp_D * (1. - rnd)) -
-                                          feorgads + remife - fecol + rfeton * ((1. - dfrt) * morpt_Diat - npp_Diat)));
-          UPD(V_DETRFE, SB(V_DETRFE) + dtbio * (rfeton * (sf + (1. - dfr) * morp + morp_D * rnd + morz - graz_Det) + feorgads +
-                                                P->iscr * fecol - remife - expofe + SL(X_expofe) * dztrk +
-                                                rfeton * (1. - dfr) * morp_Diat));
-          UPD(V_SIL, SB(V_SIL) + dtbio * (opldis - oplpro));
-          UPD(V_OPL, SB(V_OPL) + dtbio * (oplpro - opldis - SR(expoopl) + SL(X_expoopl) * dztrk));
-        } break;
-        case 4: {
-          const double rtphytn15 = SR(rtphytn15), rtdiatn15 = SR(rtdiatn15), rtdiazn15 = SR(rtdiazn15), rtdetrn15 = SR(rtdetrn15);
-          const double fcassim = SR(fcassim), fcexcr = SR(fcexcr), fcrecy = SR(fcrecy);
-          const double morpt = SR(morpt), morpt_Diat = SR(morpt_Diat), npp_Diat = SR(npp_Diat), excr = SR(excr), morpt_D = SR(morpt_D);
-          const double nr_excr_D = SR(nr_excr_D), morp_D = SR(morp_D), remi = SR(remi), recy_don = SR(recy_don), npp = SR(npp);
-          const double no3upt_D = SR(no3upt_D), morp = SR(morp), morp_Diat = SR(morp_Diat);
-          const double nr_excr_P = 0.0, nr_excr_detr = 0.0;
-          UPD(V_DIN15, SB(V_DIN15) + dtbio * (rtphytn15 * (1. - dfrt) * morpt + rtphytn15 * nr_excr_P + rtdiatn15 * (1. - dfrt) * morpt_Diat -
-                                             fcassim * npp_Diat + fcexcr * excr + rtdiazn15 * morpt_D + rtdiazn15 * nr_excr_D +
-                                             rtdiazn15 * morp_D * (1. - rnd) + rtdetrn15 * (1. - pfr) * remi + rtdetrn15 * nr_excr_detr +
-                                             fcrecy * recy_don - fcassim * npp - fcassim * no3upt_D));
-          UPD(V_DON15, SB(V_DON15) + dtbio * (dfr * rtphytn15 * morp + dfr * rtdiatn15 * morp_Diat + dfrt * rtdiatn15 * morpt_Diat +
-                                             dfrt * rtphytn15 * morpt + rtdetrn15 * pfr * remi - fcrecy * recy_don));
-        } break;
-        case 5: {
-          const double rtphytn15 = SR(rtphytn15), rtdiatn15 = SR(rtdiatn15), rtdiazn15 = SR(rtdiazn15), rtdetrn15 = SR(rtdetrn15);
-          const double rtzoopn15 = SR(rtzoopn15), fcassim = SR(fcassim), fcexcr = SR(fcexcr), fcnfix = SR(fcnfix);
-          const double npp = SR(npp), morp = SR(morp), graz = SR(graz), morpt = SR(morpt), npp_Diat = SR(npp_Diat);
-          const double morp_Diat = SR(morp_Diat), graz_Diat = SR(graz_Diat), morpt_Diat = SR(morpt_Diat), morz = SR(morz);
-          const double graz_Z = SR(graz_Z), excr = SR(excr), npp_D = SR(npp_D), no3upt_D = SR(no3upt_D), morp_D = SR(morp_D);
-          const double graz_D = SR(graz_D), morpt_D = SR(morpt_D);
-          UPD(V_PHYTN15, SB(V_PHYTN15) + dtbio * (fcassim * npp - rtphytn15 * morp - rtphytn15 * graz - rtphytn15 * morpt));
-          UPD(V_DIATN15, SB(V_DIATN15) + dtbio * (fcassim * npp_Diat - rtdiatn15 * morp_Diat - rtdiatn15 * graz_Diat - rtdiatn15 * morpt_Diat));
-          UPD(V_ZOOPN15, SB(V_ZOOPN15) + dtbio * (rtphytn15 * SR(dig_P) + rtdiatn15 * SR(dig_Diat) + rtzoopn15 * SR(dig_Z) +
-                                                 rtdetrn15 * SR(dig_Det) + rtdiazn15 * SR(dig_D) - rtzoopn15 * morz - rtzoopn15 * graz_Z -
-                                                 fcexcr * excr));
-          UPD(V_DIAZN15, SB(V_DIAZN15) + dtbio * (fcnfix * (npp_D - no3upt_D) + fcassim * no3upt_D - rtdiazn15 * morp_D - rtdiazn15 * graz_D -
-                                                 rtdiazn15 * morpt_D));
-        } break;
-        case 6: {
+        }
+        {
           const double rtphytn15 = SR(rtphytn15), rtdiatn15 = SR(rtdiatn15), rtdiazn15 = SR(rtdiazn15), rtdetrn15 = SR(rtdetrn15);
           const double rtzoopn15 = SR(rtzoopn15);
           const double morp = SR(morp), morp_Diat = SR(morp_Diat), sf_Diat = SR(sf_Diat), sf_P = SR(sf_P), sf_Z = SR(sf_Z);
@@ -1258,8 +1224,70 @@ __global__ void __launch_bounds__(32 * WS_WARPS) k_mobi_ws(const DevView v, int 
                                           rtdiazc13 * nr_excr_D + rtdiazc13 * morp_D * (1 - rnd) + rtdetrc13 * (1. - pfr) * remi +
                                           rtdetrc13 * nr_excr_detr + rtdiatc13 * (1. - dfrt) * morpt_Diat - fcnpp * npp_Diat +
                                           rtdoc13 * recy_don - fcnpp * npp - fcnpp * npp_D));
-        } break;
-        case 7: {
+        }
+        WS_BAR();
+        }
+      } break;
+      case 3: {   // roles 3 and 7
+        WS_LOOP_HEAD
+        {
+          // iron speciation and scavenging (:2262-2283)
+          const double biodon = SB(V_DON), biodfe = SB(V_DFE), aou8 = lc0, o2flag = lc1;
+          double ligand = fmax(aou8 / 66. + pow(biodon, 0.8) / 4.8, 0.5) / 1000.;
+          double fepa = (1.0 + P->kfeleq * (ligand - biodfe)) * o2flag;
+          double feprime = ((-fepa + sqrt(fepa * fepa + 4.0 * P->kfeleq * biodfe)) / (2.0 * P->kfeleq)) * o2flag;
+          double fecol = P->kfecol * (feprime * feprime) * o2flag;
+          SR(feprime) = feprime;
+          SR(fecol) = fecol * SF(V_DFE);
+        }
+        {
+          // diazotroph growth and N2 fixation (:2164-2166, 2200-2206, 2226-2232); the phosphorus limitation of the
+          // ordinary phytoplankton is re-derived here (same expressions as warp 0)
+          const double biophyt = SB(V_PHYT), biodfe = SB(V_DFE), biodop = SB(V_DOP), biopo4 = SB(V_PO4), biono3 = SB(V_NO3);
+          const double biodiaz = SB(V_DIAZ);
+          double p1 = fmin(biophyt, P->pmax), p2 = fmax(0.0, biophyt - P->pmax);
+          double k1n = (P->knmin * p1 + P->knmax * p2) / (p1 + p2);
+          double k1p_P = k1n * ptn_P;
+          double deffe_D = biodfe / (P->kfe_D + biodfe);
+          double jmax_D = fmax(0., P->abio_P * (bct - P->dbct_D) * deffe_D) * P->jdiar;
+          double limP_dop = P->hdop * biodop / (k1p_P + biodop);
+          double limP_po4 = biopo4 / (k1p_P + biopo4);
+          double dopupt_flag = 0.5 + fsign(0.5, limP_dop - limP_po4);
+          double limP = limP_dop * dopupt_flag + limP_po4 * (1. - dopupt_flag);
+          double u_D = fmin(lc2, jmax_D * limP);
+          double npp_D = fmax(0., u_D * biodiaz);
+          double no3upt_D = (0.5 + 0.5 * tanh(biono3 - 5.)) * npp_D;
+          SR(dopupt_D) = npp_D * dopupt_flag;
+          npp_D = npp_D * (dopupt_flag * SF(V_DOP) + (1. - dopupt_flag) * SF(V_PO4)) * SF(V_DIN15);
+          no3upt_D = no3upt_D * SF(V_NO3) * SF(V_DIN15);
+          SR(npp_D) = npp_D;
+          SR(no3upt_D) = no3upt_D;
+          acc0 = acc0 + npp_D - no3upt_D;   // nfixout
+          SR(rtdoc13) = CL13(SB(V_DOC13) / (SB(V_DON) * redctn));
+          SR(rtdiazc13) = CL13(SB(V_DIAZC13) / (biodiaz * redctn));
+        }
+        WS_BAR();
+        {
+          const double excr = SR(excr), morpt = SR(morpt), npp = SR(npp), morpt_D = SR(morpt_D), npp_D = SR(npp_D);
+          const double recy_don = SR(recy_don), nr_excr_D = SR(nr_excr_D), morp_D = SR(morp_D), remife = SR(remife), fecol = SR(fecol);
+          const double morpt_Diat = SR(morpt_Diat), npp_Diat = SR(npp_Diat), sf = SR(sf), morp = SR(morp), morz = SR(morz);
+          const double graz_Det = SR(graz_Det), expofe = SR(expofe), morp_Diat = SR(morp_Diat), sf_Diat = SR(sf_Diat);
+          const double nr_excr_P = 0.0, nr_excr_detr = 0.0;
+          const double o2flag = lc1;
+          double feorgads = (P->kfeorg * SR(pw58) * SR(feprime)) * o2flag;
+          feorgads = feorgads * SF(V_DFE);
+          const double opldis = SR(opldis);
+          const double oplpro = (morp_Diat + sf_Diat) * SR(sipr0) * SF(V_SIL) * (1.e-3);
+          UPD(V_DFE, SB(V_DFE) + dtbio * (rfeton * (excr + (1. - dfrt) * morpt - npp + morpt_D - npp_D + recy_don + nr_excr_D + nr_excr_P +
+                                                    nr_excr_detr + morp_D * (1. - rnd)) -
+                                          feorgads + remife - fecol + rfeton * ((1. - dfrt) * morpt_Diat - npp_Diat)));
+          UPD(V_DETRFE, SB(V_DETRFE) + dtbio * (rfeton * (sf + (1. - dfr) * morp + morp_D * rnd + morz - graz_Det) + feorgads +
+                                                P->iscr * fecol - remife - expofe + SL(X_expofe) * dztrk +
+                                                rfeton * (1. - dfr) * morp_Diat));
+          UPD(V_SIL, SB(V_SIL) + dtbio * (opldis - oplpro));
+          UPD(V_OPL, SB(V_OPL) + dtbio * (oplpro - opldis - SR(expoopl) + SL(X_expoopl) * dztrk));
+        }
+        {
           const double rtphytc13 = SR(rtphytc13), rtzoopc13 = SR(rtzoopc13), rtdiazc13 = SR(rtdiazc13), rtdetrc13 = SR(rtdetrc13);
           const double rtdiatc13 = SR(rtdiatc13), rtdoc13 = SR(rtdoc13), fcnpp = SR(fcnpp), rtdic13 = SR(rtdic13);
           const double rtcaco3c13 = SR(rtcaco3c13);
@@ -1286,16 +1314,18 @@ __global__ void __launch_bounds__(32 * WS_WARPS) k_mobi_ws(const DevView v, int 
           UPD(V_DIATC13, SB(V_DIATC13) + dtbio * redctn * (fcnpp * npp_Diat - rtdiatc13 * (morp_Diat + graz_Diat + morpt_Diat)));
           acc1 = acc1 + rtdetrc13 * expo;            // rc13expoout
           acc2 = acc2 + rtcaco3c13 * expocaco3;      // rcaco3c13expoout
-        } break;
-      }
-      __syncthreads();
-    }  // sub-steps
+        }
+        WS_BAR();
+        }
+      } break;
+    }
+#undef WS_LOOP_HEAD
 
     // ================= E1: increments as rates (:880-895); publish the sums =================
     // States the driver does not touch afterwards go straight to src; the others stay in B.
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const int m = 4 * w + q;
+    for (int q = 0; q < 8; q++) {
+      const int m = 8 * w + q;
       const double inc = (SB(m) - SC(m)) * rdtts;
       SB(m) = inc;
       const bool later = (m == V_NO3 || m == V_DIN15 || m == V_DFE || m == V_PO4 || m == V_DIC || m == V_DIC13 || m == V_SIL);
@@ -1304,17 +1334,18 @@ __global__ void __launch_bounds__(32 * WS_WARPS) k_mobi_ws(const DevView v, int 
     switch (w) {
       case 2: SL(S_expo) = acc0; SL(S_expo_phos) = acc1; SL(S_calpro) = acc2; SL(S_dissl) = acc3; SL(S_expocaco3) = acc4;
               SL(S_expoopl) = acc5; SL(S_expofe) = acc6; break;
-      case 5: SL(S_rn15expo) = acc0; break;
-      case 7: SL(S_nfix) = acc0; SL(S_rc13expo) = acc1; SL(S_rcaco3c13expo) = acc2; break;
+      case 1: SL(S_rn15expo) = acc0; break;                                                   // role 5
+      case 3: SL(S_nfix) = acc0; SL(S_rc13expo) = acc1; SL(S_rcaco3c13expo) = acc2; break;   // role 7
       default: break;
     }
-    __syncthreads();
+    WS_BAR();
 
     // ================= E2: mobi_driver after mobi_src (:896-1400) =================
     {
       const double sgb = act ? v.sg_bathy[XIJK(i, j, k)] : 0.0;
       const double expo = SL(S_expo) * rnbio;   // export of this level before the sea-floor share is removed
-      switch (w) {
+      for (int rr = 0; rr < 2; rr++)
+      switch (w + WS_WARPS * rr) {
         case 0: {
           // export chain -> import of the next level (:1000-1010, 1112-1120, 1280-1288); sea-floor phosphorus
           double expofe = SL(S_expofe) * rnbio, expocaco3 = SL(S_expocaco3) * rnbio, expoopl = SL(S_expoopl) * rnbio;
@@ -1453,7 +1484,7 @@ __global__ void __launch_bounds__(32 * WS_WARPS) k_mobi_ws(const DevView v, int 
         default: break;
       }
     }
-    __syncthreads();
+    WS_BAR();
 #undef PRE
   }  // levels
   if (w == 1 && e3_pending) {
@@ -1475,8 +1506,7 @@ static int mobi_ws_mode() {
   return e ? atoi(e) : -1;
 }
 
-void launch_mobi(uvic_b200_ctx *c, const uvic_b200_stepinfo *si) {
-  DevView &v = c->v;
+void launch_mobi(uvic_b200_ctx *c, const DevView &v, const uvic_b200_stepinfo *si) {
   // month index and declination (09/mom/tracer.F:310-343)
   double yrtime = fmod(si->relyr, 1.);
   int mi = 12;
@@ -1501,11 +1531,22 @@ void launch_mobi(uvic_b200_ctx *c, const uvic_b200_stepinfo *si) {
   if (ws) {
     static bool attr_set = false;
     if (!attr_set) {
-      cudaFuncSetAttribute(k_mobi_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WsSm));
+      cudaFuncSetAttribute(k_mobi_ws<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WsSm));
+      cudaFuncSetAttribute(k_mobi_ws<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(WsSm));
+      cudaFuncSetAttribute(k_mobi_ws<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (int)sizeof(WsSm));
       attr_set = true;
     }
+    // G = 4 confines MOBI to a quarter of the SMs it would otherwise touch (48 of 148 on the 100x100 grid), leaving the
+    // rest to the kernels of the main stream it overlaps with; measured best for the whole step.
+    int G = 4;
+    if (const char *e = getenv("UVIC_B200_MOBI_WS_G")) G = atoi(e);
     ProfScope ps_(c, "k_mobi_ws");
-    k_mobi_ws<<<ngroups, 32 * WS_WARPS, sizeof(WsSm), c->stream>>>(v, mi, nbio, dtbio, rdtts, rnbio);
+    if (G >= 4)
+      k_mobi_ws<4><<<(ngroups + 3) / 4, 32 * WS_WARPS * 4, 4 * sizeof(WsSm), c->stream>>>(v, mi, nbio, dtbio, rdtts, rnbio);
+    else if (G == 2)
+      k_mobi_ws<2><<<(ngroups + 1) / 2, 32 * WS_WARPS * 2, 2 * sizeof(WsSm), c->stream>>>(v, mi, nbio, dtbio, rdtts, rnbio);
+    else
+      k_mobi_ws<1><<<ngroups, 32 * WS_WARPS, sizeof(WsSm), c->stream>>>(v, mi, nbio, dtbio, rdtts, rnbio);
   } else {
     KLAUNCH("k_mobi_column", k_mobi_column, ngroups, 32, v, mi, nbio, dtbio, rdtts, rnbio);
   }

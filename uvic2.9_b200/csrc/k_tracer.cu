@@ -1,9 +1,8 @@
 // k_tracer.cu -- the per-tracer part of `call tracer` (source/mom/mom.F:389 ->
 // 09/mom/tracer.F:902-1203) on the device:
 //
-//   k_fct_tlo     low-order (upstream) fluxes and the low-order solution t_lo
-//                 09/mom/tracer_adv_flx.F:496-580
-//   k_fct_rfac    raw antidiffusive fluxes and the one-dimensional Zalesak ratios
+//   k_fct_rfac    low-order (upstream) fluxes and the low-order solution t_lo of the cell
+//                 (09/mom/tracer_adv_flx.F:496-580), raw antidiffusive fluxes and the one-dimensional Zalesak ratios
 //                 R+-x, R+-y, R+-z of every cell            :582-712, 714-770, 786-958
 //   k_update      delimited + low-order advective fluxes (:696-712,772-784,960-1002),
 //                 explicit horizontal/vertical diffusion (09/mom/tracer.F:930-961,
@@ -30,6 +29,12 @@
 // jp1=min(j+1,jmt-1), jp2=min(j+2,jmt) (:554-556) -- which only touch row jmt, whose
 // ratios are zero because tmask(row jmt)=0 -- and the cyclic wrap of R+-x (:693-694).
 #include "ctx.h"
+#include "fct_common.h"
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <utility>
+#include <vector>
 
 // decoded cell: 1-based i,k, global j, and 32-bit offsets inside one 3-D field
 struct Cell {
@@ -58,59 +63,8 @@ __device__ __forceinline__ bool decode_cell(const DevView &v, long long idx, int
   return true;
 }
 
-// upstream flux 2*(v*T)_face, 09/mom/tracer_adv_flx.F:500-503: totadv*(a+b) + |totadv|*(a-b)
-__device__ __forceinline__ double upw(double totadv, double a, double b) { return totadv * (a + b) + fabs(totadv) * (a - b); }
-
-// Fortran max/min on finite operands: one DSETP + two selects (CUDA's fmax/fmin add NaN handling)
-__device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
-__device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
-
 // ------------------------------------------------------------------------------------
-// t_lo, rows max(2,jlo-1) .. min(jmt-1,jhi+1)
-// ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_fct_tlo(const DevView v, int nbase, int ng, int tch, int jfirst, int nrow) {
-  Cell q;
-  if (!decode_cell(v, (long long)blockIdx.x * blockDim.x + threadIdx.x, jfirst, nrow, q)) return;
-  const int km = v.km, k = q.k, c = q.c;
-  const double ue_c = v.ue[c], ue_w = v.ue[c - 1], vn_c = v.vn[c], vn_s = v.vn[c - q.sj];
-  const double wb_d = v.wb[q.cz], wb_u = v.wb[q.cz - q.sk];
-  const double m = (v.kmt[q.c2] >= k) ? 1.0 : 0.0;
-  const double cstdxt2r = v.cstr[q.j - 1] * v.dxtr[q.i - 1] * 0.5;  // 09/mom/tracer.F:240
-  const double cstdyt2r = v.cstdyt2r[q.j - 1], dzt2r = v.dzt2r[k - 1];
-  const double twodt = v.c2dtts * v.dtxcel[k - 1];
-  const int cu = (k > 1) ? c - q.sk : c, cd = (k < km) ? c + q.sk : c;
-  const int g0 = blockIdx.y * tch, g1 = min(g0 + tch, ng);
-  for (int g = g0; g < g1; g++) {
-    const double *__restrict__ T = v.t_m1 + (long long)(nbase + g) * v.n3;
-    double *__restrict__ t_lo = v.t_lo + (long long)g * v.n3;
-    const double Tc = T[c], Te = T[c + 1], Tw = T[c - 1], Tn = T[c + q.sj], Ts = T[c - q.sj], Tu = T[cu], Td = T[cd];
-    // ADV_Tx, ADV_Ty, ADV_Tz of source/mom/fdift.h:25-39 on the low-order fluxes
-    double tx = (upw(ue_c, Tc, Te) - upw(ue_w, Tw, Tc)) * cstdxt2r;
-    double ty = (upw(vn_c, Tc, Tn) - upw(vn_s, Ts, Tc)) * cstdyt2r;
-    double fb_u = (k == 1) ? wb_u * 2.0 * Tc : upw(wb_u, Tc, Tu);   // adv_fb(i,0,j) = adv_vbt(i,0,j)*c2*t(i,1,j) (:543)
-    double fb_d = (k == km) ? 0.0 : upw(wb_d, Td, Tc);              // adv_fb(i,km,j) = c0 (:544)
-    double tz = (fb_u - fb_d) * dzt2r;
-    double val = Tc - twodt * (tx + ty + tz) * m;
-    t_lo[c] = val;
-    if (q.i == 2) t_lo[c + v.imt - 2] = val;       // setbcx(t_lo) (:580)
-    if (q.i == v.imt - 1) t_lo[c - (v.imt - 2)] = val;
-  }
-}
-
-__device__ __forceinline__ void ratio(double c2dtts, double dcf, double flxlft, double flxrgt, double fxa, double fxb, double tlo,
-                                      double m, double &rpl, double &rmn) {
-  double trmax = dmax(dmax(fxa, fxb), tlo);
-  double trmin = dmin(dmin(fxa, fxb), tlo);
-  double pplus = c2dtts * dcf * (dmax(0.0, flxlft) - dmin(0.0, flxrgt));
-  double pminus = c2dtts * dcf * (dmax(0.0, flxrgt) - dmin(0.0, flxlft));
-  double qplus = trmax - tlo;
-  double qminus = tlo - trmin;
-  rpl = dmin(1., div0(m * qplus, pplus + UVIC_EPSLN));
-  rmn = dmin(1., div0(m * qminus, pminus + UVIC_EPSLN));
-}
-
-// ------------------------------------------------------------------------------------
-// R+-x, R+-y, R+-z, same rows as t_lo
+// t_lo and R+-x, R+-y, R+-z, rows max(2,jlo-1) .. min(jmt-1,jhi+1)
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_fct_rfac(const DevView v, int nbase, int ng, int tch, int jfirst, int nrow) {
   Cell q;
@@ -123,15 +77,26 @@ __global__ void __launch_bounds__(256) k_fct_rfac(const DevView v, int nbase, in
   const double mw = (v.kmt[q.c2 - 1] >= k) ? 1.0 : 0.0, me = (v.kmt[q.c2 + 1] >= k) ? 1.0 : 0.0;
   const double ms = (v.kmt[q.c2 - v.imt] >= k) ? 1.0 : 0.0, mn = (v.kmt[q.c2 + v.imt] >= k) ? 1.0 : 0.0;  // jp2 = j+1 <= jmt
   const double dcfx = v.cstr[j - 1] * v.dxtr[q.i - 1] * 0.5, dcfy = v.cstdyt2r[j - 1], dcfz = v.dzt2r[k - 1];
+  const double twodt = v.c2dtts * v.dtxcel[k - 1];
   const int cu = (k > 1) ? c - q.sk : c, cd = (k < km) ? c + q.sk : c;
   const int g0 = blockIdx.y * tch, g1 = min(g0 + tch, ng);
   for (int g = g0; g < g1; g++) {
     const double *__restrict__ T = v.t_m1 + (long long)(nbase + g) * v.n3;
     const double *__restrict__ U = v.t_0 + (long long)(nbase + g) * v.n3;
     double *__restrict__ R = v.Rfac + (long long)g * 6 * v.n3;
-    const double tlo = v.t_lo[(long long)g * v.n3 + c];
     const double Tc = T[c], Te = T[c + 1], Tw = T[c - 1], Tn = T[c + q.sj], Ts = T[c - q.sj], Tu = T[cu], Td = T[cd];
     const double Uc = U[c], Ue = U[c + 1], Uw = U[c - 1], Un = U[c + q.sj], Us = U[c - q.sj], Uu = U[cu], Ud = U[cd];
+    // low-order solution of this cell (:496-580); only the cell's own t_lo enters its ratios, so it is formed here
+    // instead of in a separate pass (its upstream fluxes are the ones the antidiffusive fluxes below need anyway)
+    double tlo;
+    {
+      double tx = (upw(ue_c, Tc, Te) - upw(ue_w, Tw, Tc)) * dcfx;
+      double ty = (upw(vn_c, Tc, Tn) - upw(vn_s, Ts, Tc)) * dcfy;
+      double fb_u = (k == 1) ? wb_u * 2.0 * Tc : upw(wb_u, Tc, Tu);   // adv_fb(i,0,j) = adv_vbt(i,0,j)*c2*t(i,1,j) (:543)
+      double fb_d = (k == km) ? 0.0 : upw(wb_d, Td, Tc);              // adv_fb(i,km,j) = c0 (:544)
+      double tz = (fb_u - fb_d) * dcfz;
+      tlo = Tc - twodt * (tx + ty + tz) * m;
+    }
     double rpl, rmn;
     // ---- x (:635-694): flxlft = anti_fe(i-1), flxrgt = anti_fe(i) ----
     {
@@ -167,11 +132,6 @@ __global__ void __launch_bounds__(256) k_fct_rfac(const DevView v, int nbase, in
   }
 }
 
-__device__ __forceinline__ double delimit(double cpos, double cneg, double a) {
-  // :706-711, 777-782, 972-977
-  return 0.5 * ((cpos + cneg) * a + (cpos - cneg) * fabs(a));
-}
-
 // ------------------------------------------------------------------------------------
 // fluxes + explicit update, rows jlo..jhi
 // ------------------------------------------------------------------------------------
@@ -182,7 +142,10 @@ struct SmCol {
   __device__ __forceinline__ double &operator[](int a) const { return p[a * UPD_T]; }
 };
 
-template <bool FCT>
+// MODE 0: 2nd-order centred advection + diffusion; 1: FCT advection (ratios of k_fct_rfac) + diffusion;
+// 2: diffusive tendency only; 3: FCT advection only, subtracted from the tendency MODE 2 left in t(tau+1).
+// 2 followed by 3 performs the operations of 1 in the same order with half the registers each.
+template <int MODE>
 __global__ void __launch_bounds__(UPD_T) k_update(const DevView v, int nbase, int ng, int tch, int jfirst, int nrow) {
   // The 36 tracer-independent Redi coefficients of a cell's six faces are parked in shared
   // memory (thread-private slots, conflict free) instead of registers: 36 KB per 128-thread CTA
@@ -224,7 +187,7 @@ __global__ void __launch_bounds__(UPD_T) k_update(const DevView v, int nbase, in
   const SmCol cbx_d{&sco[16][tid]}, cby_d{&sco[20][tid]}, cbx_u{&sco[24][tid]}, cby_u{&sco[28][tid]};
   double &K11_e = sco[32][tid], &K11_w = sco[33][tid], &K22_n = sco[34][tid], &K22_s = sco[35][tid];
   const bool has_d = (k <= km - 1), has_u = (k >= 2);   // diff_fbiso exists on faces 1..km-1
-  if (iso) {
+  if (MODE != 3 && iso) {
 #pragma unroll
     for (int a = 0; a < 4; a++) {
       ce_e[a] = v.ce[c + a * n3];
@@ -261,9 +224,9 @@ __global__ void __launch_bounds__(UPD_T) k_update(const DevView v, int nbase, in
     const double Uc = U[c], Ue = U[c + 1], Uw = U[c - 1], Un = U[c + sj], Us = U[c - sj], Uu = U[cu], Ud = U[cd];
 
     // ---------------- advective fluxes ----------------
-    double adv_tx, adv_ty, adv_tz, adv_tz_iso[3] = {0.0, 0.0, 0.0};
+    double adv_tx = 0.0, adv_ty = 0.0, adv_tz = 0.0, adv_tz_iso[3] = {0.0, 0.0, 0.0};
     bool adv_iso = false;
-    if constexpr (FCT) {
+    if constexpr (MODE == 1 || MODE == 3) {
       // east / west faces: Cpos(f) = min(Rpl(f+1),Rmn(f)), Cneg(f) = min(Rpl(f),Rmn(f+1)) (:698-701); no mask (:987)
       const double rplx_c = R[c], rmnx_c = R[c + n3];
       double adv_fe_e, adv_fe_w;
@@ -310,7 +273,7 @@ __global__ void __launch_bounds__(UPD_T) k_update(const DevView v, int nbase, in
       adv_tx = (adv_fe_e - adv_fe_w) * cstdxt2r;
       adv_ty = (adv_fn_n - adv_fn_s) * cstdyt2r;
       adv_tz = (adv_fb_u - adv_fb_d) * dzt2r;
-    } else {
+    } else if constexpr (MODE == 0) {
       // 2nd-order centred (09/mom/tracer_adv_flx.F:1030-1082, source/mom/fdift.h:25-39) plus the
       // Gent-McWilliams advective terms ADV_Txiso/Tyiso/Tziso (fdift.h:44-52, isoflux :1110-1134)
       const double vet_c = v.adv_vet[c], vet_w = v.adv_vet[c - 1], vnt_c = v.adv_vnt[c], vnt_s = v.adv_vnt[c - sj];
@@ -427,8 +390,11 @@ __global__ void __launch_bounds__(UPD_T) k_update(const DevView v, int nbase, in
     // The source term is added in k_invtri (same operation order as 09/mom/tracer.F:1114-1127:
     // t(tau-1) + twodt*(DIFF - ADV + source)*tmask), so the MOBI kernels, which run on a side
     // stream, only have to finish before the implicit solve.
-    double P = diff_tx + diff_ty + diff_tz - adv_tx - adv_ty - adv_tz;
-    if (!FCT && adv_iso) P = P - adv_tz_iso[0] - adv_tz_iso[1] - adv_tz_iso[2];
+    double P;
+    if constexpr (MODE == 3) P = v.t_p1[(long long)n0 * n3 + c];   // the diffusive tendency left by k_update<2>
+    else P = diff_tx + diff_ty + diff_tz;
+    if constexpr (MODE != 2) P = P - adv_tx - adv_ty - adv_tz;
+    if (MODE == 0 && adv_iso) P = P - adv_tz_iso[0] - adv_tz_iso[1] - adv_tz_iso[2];
     v.t_p1[(long long)n0 * n3 + c] = P;
   }
 }
@@ -588,14 +554,14 @@ __global__ void __launch_bounds__(128) k_convect_ts(const DevView v) {
 }
 
 // convct2 phase 2 (source/mom/convect.F:269-277): one thread per (column, tracer n >= 3)
-__global__ void __launch_bounds__(128) k_convect_tr(const DevView v) {
+__global__ void __launch_bounds__(128) k_convect_tr(const DevView v, int nfirst) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int ni = v.imt - 2;
   int nrow = v.jhi - v.jlo + 1;
   if (idx >= (long long)ni * nrow) return;
   int i = (int)(idx % ni) + 2;
   int j = (int)(idx / ni) + v.jlo;
-  const int n0 = blockIdx.y + 2;
+  const int n0 = nfirst + blockIdx.y;
   const long long col = X2(i, j);
   const int nreg = v.conv_n[col];
   const bool edge = (i == 2 || i == v.imt - 1);
@@ -618,6 +584,12 @@ __global__ void __launch_bounds__(128) k_convect_tr(const DevView v) {
   }
 }
 
+// UVIC_B200_FCT=merged runs diffusion and the FCT fluxes in one kernel (k_update<1>); the default splits them
+static bool fct_split() {
+  const char *e = getenv("UVIC_B200_FCT");
+  return !(e && !strcmp(e, "merged"));
+}
+
 void launch_tracer(uvic_b200_ctx *c, const uvic_b200_stepinfo *si) {
   DevView &v = c->v;
   (void)si;
@@ -627,34 +599,73 @@ void launch_tracer(uvic_b200_ctx *c, const uvic_b200_stepinfo *si) {
   const long long ncell_r = (long long)(v.imt - 2) * v.km * nrow_r;
   const long long ncell_c = (long long)(v.imt - 2) * v.km * nrow_c;
   const long long ncol = (long long)(v.imt - 2) * nrow_c;
-  for (int nbase = 0; nbase < v.nt; nbase += v.ngroup) {
-    int ng = min(v.ngroup, v.nt - nbase);
+  // Tracer batches.  Device resident: as many tracers per batch as the FCT scratch holds.  With a host destination
+  // (uvic_b200_tracer_step) T and S go first -- they need no MOBI source and clinic wants them -- and the rest is cut into
+  // a few batches, so that every finished batch streams to the host on the copy stream while the next one computes.
+  std::vector<std::pair<int, int>> batches;
+  if (c->d2h_dst && v.nt > 2) {
+    batches.push_back({0, 2});
+    const int rest = v.nt - 2, nb = std::min(rest, std::max(3, (rest + v.ngroup - 1) / v.ngroup));
+    for (int b = 0; b < nb; b++) {
+      const int lo = 2 + (int)((long long)rest * b / nb), hi = 2 + (int)((long long)rest * (b + 1) / nb);
+      for (int q = lo; q < hi; q += v.ngroup) batches.push_back({q, std::min(v.ngroup, hi - q)});
+    }
+  } else {
+    for (int nbase = 0; nbase < v.nt; nbase += v.ngroup) batches.push_back({nbase, std::min(v.ngroup, v.nt - nbase)});
+  }
+  bool mobi_waited = false;
+  size_t nb_done = 0;
+  for (auto &bt : batches) {
+    const int nbase = bt.first, ng = bt.second;
     // tracers per thread: keep at least ~4 CTAs-worth of threads per SM in flight, then amortise the
     // tracer-independent loads over as many tracers as possible
     int nchunk = (int)min((long long)ng, max(1LL, (148LL * 2048 * 2 + ncell_c - 1) / ncell_c));
     int tch = (ng + nchunk - 1) / nchunk;
     nchunk = (ng + tch - 1) / tch;
+    dim3 gc(cdiv(ncell_c, UPD_T), nchunk);
     if (v.fct) {
       dim3 gr(cdiv(ncell_r, 256), nchunk);
-      KLAUNCH("k_fct_tlo", k_fct_tlo, gr, 256, v, nbase, ng, tch, jf_r, nrow_r);
       KLAUNCH("k_fct_rfac", k_fct_rfac, gr, 256, v, nbase, ng, tch, jf_r, nrow_r);
+      if (fct_split()) {
+        KLAUNCH("k_diffuse", k_update<2>, gc, UPD_T, v, nbase, ng, tch, v.jlo, nrow_c);
+        KLAUNCH("k_fct_apply", k_update<3>, gc, UPD_T, v, nbase, ng, tch, v.jlo, nrow_c);
+      } else {
+        KLAUNCH("k_update", k_update<1>, gc, UPD_T, v, nbase, ng, tch, v.jlo, nrow_c);
+      }
+    } else {
+      KLAUNCH("k_update", k_update<0>, gc, UPD_T, v, nbase, ng, tch, v.jlo, nrow_c);
     }
-    dim3 gc(cdiv(ncell_c, UPD_T), nchunk);
-    if (v.fct)
-      KLAUNCH("k_update", k_update<true>, gc, UPD_T, v, nbase, ng, tch, v.jlo, nrow_c);
-    else
-      KLAUNCH("k_update", k_update<false>, gc, UPD_T, v, nbase, ng, tch, v.jlo, nrow_c);
-    if (nbase == 0 && c->mobi_event) cudaStreamWaitEvent(c->stream, c->mobi_event, 0);
+    // the source term enters in k_invtri: the first batch with a sourced tracer waits for MOBI
+    bool sourced = false;
+    for (int n = nbase; n < nbase + ng; n++) sourced = sourced || c->itrc_h[n] != 0;
+    if (sourced && !mobi_waited && c->mobi_event && c->mobi_inflight) {
+      cudaStreamWaitEvent(c->stream, c->mobi_event, 0);
+      mobi_waited = true;
+    }
     dim3 gi(cdiv(ncol, 128), ng);
     KLAUNCH("k_invtri", k_invtri, gi, 128, v, nbase);
-  }
-  if (c->par.fullconvect) {
-    KLAUNCH("k_convect_ts", k_convect_ts, cdiv(ncol, 128), 128, v);
-    if (v.nt > 2) {
-      dim3 gt(cdiv(ncol, 128), v.nt - 2);
-      KLAUNCH("k_convect_tr", k_convect_tr, gt, 128, v);
+    if (c->par.fullconvect) {
+      if (nbase == 0) KLAUNCH("k_convect_ts", k_convect_ts, cdiv(ncol, 128), 128, v);
+      const int nfirst = max(2, nbase), ntr = nbase + ng - nfirst;
+      if (ntr > 0) {
+        dim3 gt(cdiv(ncol, 128), ntr);
+        KLAUNCH("k_convect_tr", k_convect_tr, gt, 128, v, nfirst);
+      }
+    }
+    // Fourier filter of the polar rows + cyclic boundary (09/mom/tracer.F:1245-1262)
+    launch_filter(c, nbase, ng);
+    if (c->d2h_dst) {
+      // this batch of t(tau+1) is final: hand it to the copy stream
+      if (nb_done >= c->ev_batch.size()) {
+        cudaEvent_t e;
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        c->ev_batch.push_back(e);
+      }
+      cudaEventRecord(c->ev_batch[nb_done], c->stream);
+      cudaStreamWaitEvent(c->copy_out, c->ev_batch[nb_done], 0);
+      cudaMemcpyAsync(c->d2h_dst + (size_t)nbase * v.n3, v.t_p1 + (size_t)nbase * v.n3, (size_t)ng * v.n3 * sizeof(double),
+                      cudaMemcpyDeviceToHost, c->copy_out);
+      nb_done++;
     }
   }
-  // Fourier filter of the polar rows + cyclic boundary (09/mom/tracer.F:1245-1262)
-  launch_filter(c);
 }

@@ -7,13 +7,45 @@
 // come from host tables (edr_e1, edr_den), as does the latitude-weighted constituent sum
 // q2*(edrm2+edrs2)+qk1*edrk1+qo1*edro1 (edrsum), so the step itself evaluates no exp.
 //
-// The same column pass factorises the tridiagonal matrix of invtri
+// A column pass then factorises the tridiagonal matrix of invtri
 // (source/mom/invtri.F:55-100): a, c, b, e and bet depend only on diff_cbt, the masks,
 // tdt and aidif, not on the tracer, so they are built once per step (the reference
 // rebuilds them for each of the nt tracers) and the per-tracer solve is two sweeps.
 #include "ctx.h"
 
-__global__ void __launch_bounds__(128) k_vmix_column(const DevView v) {
+// diff_cbt, one thread per cell: the tidal sum of a cell runs over the levels below it in the reference's order
+__global__ void __launch_bounds__(256) k_vmix_cbt(const DevView v) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int ni = v.imt - 2, km = v.km;
+  const int nrow = v.jhi - v.jlo + 1;
+  if (idx >= (long long)ni * km * nrow) return;
+  const int i = (int)(idx % ni) + 2;
+  const long long r = idx / ni;
+  const int k = (int)(r % km) + 1;
+  const int j = (int)(r / km) + v.jlo;
+  const int kb = v.kmt[X2(i, j)];
+  const long long c = X3(i, k, j);
+  // ---- diff_cbt (09/mom/vmixc.F:68-124, 182-188) ----
+  double d = 0.0;  // diff_cbt(i,k>=kmt,j) is never assigned in the reference: zero COMMON
+  if (k <= kb - 1) {
+    if (v.tidal_kv) {
+      double drodzb = v.alphai[c] * v.ddzt[X3Z(i, k, j)] + v.betai[c] * v.ddzt[X3Z(i, k, j) + v.n3z];
+      double zn2 = fmax(-v.gravrho0r * drodzb, 1e-8);
+      double edr = 0.;
+      for (int k1 = k + 1; k1 <= kb; k1++)
+        edr = edr + v.edrsum[c + (long long)(k1 - k) * v.imt] * v.edr_e1[(k - 1) + km * (k1 - 1)] / v.edr_den[k1 - 1];
+      double zkappa = v.ogamma * edr / zn2;
+      d = fmax(v.kappa_h, fmin(100., zkappa + v.kappa_h));
+    } else {
+      d = v.kappa_h;
+    }
+  }
+  if (v.isopycmix) d = d + v.K33[c];
+  v.diff_cbt[c] = d;
+}
+
+// the tracer-independent Thomas factors, one thread per column
+__global__ void __launch_bounds__(128) k_vmix_factor(const DevView v) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int ni = v.imt - 2;
   int nrow = v.jhi - v.jlo + 1;
@@ -22,26 +54,6 @@ __global__ void __launch_bounds__(128) k_vmix_column(const DevView v) {
   int j = (int)(idx / ni) + v.jlo;
   const int km = v.km;
   const int kb = v.kmt[X2(i, j)];
-
-  // ---- diff_cbt (09/mom/vmixc.F:68-124, 182-188) ----
-  for (int k = 1; k <= km; k++) {
-    double d = 0.0;  // diff_cbt(i,k>=kmt,j) is never assigned in the reference: zero COMMON
-    if (k <= kb - 1) {
-      if (v.tidal_kv) {
-        double drodzb = v.alphai[X3(i, k, j)] * v.ddzt[X3Z(i, k, j)] + v.betai[X3(i, k, j)] * v.ddzt[X3Z(i, k, j) + v.n3z];
-        double zn2 = fmax(-v.gravrho0r * drodzb, 1e-8);
-        double edr = 0.;
-        for (int k1 = k + 1; k1 <= kb; k1++)
-          edr = edr + v.edrsum[X3(i, k1, j)] * v.edr_e1[(k - 1) + km * (k1 - 1)] / v.edr_den[k1 - 1];
-        double zkappa = v.ogamma * edr / zn2;
-        d = fmax(v.kappa_h, fmin(100., zkappa + v.kappa_h));
-      } else {
-        d = v.kappa_h;
-      }
-    }
-    if (v.isopycmix) d = d + v.K33[X3(i, k, j)];
-    v.diff_cbt[X3(i, k, j)] = d;
-  }
 
   // ---- invtri factorisation (source/mom/invtri.F:55-100) ----
   const double eps = 1.e-30;
@@ -74,5 +86,6 @@ __global__ void __launch_bounds__(128) k_vmix_column(const DevView v) {
 void launch_vmixc(uvic_b200_ctx *c) {
   DevView &v = c->v;
   long long ncol = (long long)(v.imt - 2) * (v.jhi - v.jlo + 1);
-  KLAUNCH("k_vmix_column", k_vmix_column, cdiv(ncol, 128), 128, v);
+  KLAUNCH("k_vmix_cbt", k_vmix_cbt, cdiv(ncol * v.km, 256), 256, v);
+  KLAUNCH("k_vmix_factor", k_vmix_factor, cdiv(ncol, 128), 128, v);
 }
