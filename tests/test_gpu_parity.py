@@ -290,14 +290,17 @@ def test_fourier_filter_parity(pkg):
     o.close()
 
 
-@pytest.mark.parametrize("shape", [dict(imt=34, jmt=26, km=8), dict(imt=70, jmt=37, km=19), dict(imt=23, jmt=50, km=33)])
-def test_split_fct_update_matches_merged_kernel_bitwise(pkg, shape, monkeypatch):
-    """k_update<2> (diffusion) followed by k_update<3> (FCT fluxes) performs the operations of the
-    merged k_update<1> in the same order; t(tau+1) must be identical to the last bit (leapfrog
-    and mixing steps)."""
+@pytest.mark.parametrize("shape", [dict(imt=34, jmt=26, km=8), dict(imt=70, jmt=37, km=19), dict(imt=23, jmt=50, km=33),
+                                   dict(imt=95, jmt=21, km=45), dict(imt=12, jmt=90, km=61)])
+def test_fct_variants_agree_bitwise(pkg, shape, monkeypatch):
+    """The marching FCT kernel (k_fct_march: shared-memory staged rows, every face flux formed once),
+    the two-pass version (k_fct_rfac + k_update<3>, ratios through HBM) and the merged k_update<1>
+    evaluate every expression with the same operands in the same order; t(tau+1) must be identical to
+    the last bit on leapfrog and mixing steps, for one and for several k tiles / row chunks, and for a
+    two-slab decomposition of the same grid."""
     case = pkg.synthetic.make_case(nt=4, names=["temp", "salt", "p0", "p1"], seed=3, **shape)
-    out = []
-    for mode in ("merged", "split"):
+    out = {}
+    for mode in ("merged", "split", "march"):
         monkeypatch.setenv("UVIC_B200_FCT", mode)
         ctx = pkg.TracerContext(case)
         ctx.load_state()
@@ -306,7 +309,19 @@ def test_split_fct_update_matches_merged_kernel_bitwise(pkg, shape, monkeypatch)
             ctx.step(leapfrog=lf)
             res.append(ctx.download_t(+1).copy())
             ctx.rotate()
-        out.append(res)
+        out[mode] = res
         ctx.close()
-    for a, b in zip(*out):
+    for a, b, c in zip(out["merged"], out["split"], out["march"]):
         assert np.array_equal(a, b)
+        assert np.array_equal(a, c)
+    # slabs: rows 2..jm and jm+1..jmt-1 computed by two contexts from the same state
+    jm = case.jmt // 2
+    ref = out["march"][0]
+    for jlo, jhi in ((2, jm), (jm + 1, case.jmt - 1)):
+        ctx = pkg.TracerContext(case, jlo=jlo, jhi=jhi)
+        ctx.load_state()
+        ctx.step(leapfrog=True)
+        got = ctx.download_t(+1)
+        lo = jlo - ctx.jbase
+        assert np.array_equal(got[:, lo:lo + (jhi - jlo + 1)], ref[:, jlo - 1:jhi])
+        ctx.close()

@@ -21,7 +21,7 @@ FLAGS = [
 ]
 # Per-file override of -fmad.  FMA contraction was measured on k_mobi.cu (the FP64-issue bound
 # kernel): 5-6 % faster only, so every translation unit keeps -fmad=false.
-FMAD = {}
+FMAD = {f: "true" for f in os.environ.get("UVIC_B200_FMAD", "").split(",") if f}   # experiment switch
 
 
 def sources():

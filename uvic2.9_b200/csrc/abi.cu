@@ -237,11 +237,16 @@ int uvic_b200_create(const uvic_b200_dims *d, const uvic_b200_grid *g, const uvi
     DALLOC(conv_zsm, (size_t)v.n2 * (km / 2 + 1), nullptr);
   }
   {
-    // FCT scratch: six ratios per tracer of a group; keep the group within ~12 GiB
-    size_t per = (size_t)v.n3 * 6 * sizeof(double);
-    size_t cap = (size_t)12 << 30;
-    v.ngroup = (int)std::max<size_t>(1, std::min<size_t>((size_t)nt, cap / per));
-    DALLOC(Rfac, (size_t)v.n3 * 6 * v.ngroup, nullptr);
+    // The marching FCT kernel needs no scratch and takes all tracers in one batch.  The two-pass reference variants
+    // (UVIC_B200_FCT=split|merged) park six ratios per tracer of a group in HBM; keep the group within ~12 GiB.
+    v.ngroup = nt;
+    v.Rfac = nullptr;
+    if (fct_variant() != 0) {
+      size_t per = (size_t)v.n3 * 6 * sizeof(double);
+      size_t cap = (size_t)12 << 30;
+      v.ngroup = (int)std::max<size_t>(1, std::min<size_t>((size_t)nt, cap / per));
+      DALLOC(Rfac, (size_t)v.n3 * 6 * v.ngroup, nullptr);
+    }
   }
   {
     size_t ntb = (size_t)km * nt * jl;

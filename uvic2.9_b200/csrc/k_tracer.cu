@@ -399,57 +399,108 @@ __global__ void __launch_bounds__(UPD_T) k_update(const DevView v, int nbase, in
   }
 }
 
-// one thread per (column, tracer): source/mom/invtri.F:75-110 with precomputed a, e, bet
-__global__ void __launch_bounds__(128) k_invtri(const DevView v, int nbase) {
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  int ni = v.imt - 2;
-  int nrow = v.jhi - v.jlo + 1;
+// Implicit vertical diffusion.  One thread per (column, tracer): source/mom/invtri.F:75-110 with the
+// precomputed factors a, e, bet of k_vmix_factor.  A CTA is 32 consecutive columns x 4 tracers (warp =
+// tracer) and the grid runs the tracer quads of one column block back to back, so the tracer-independent
+// a / bet / e lines are fetched from HBM once and hit L1 / L2 for the other tracers.  The forward sweep
+// parks z(k) in a thread-private shared-memory column instead of writing it to t(tau+1) and reading it
+// back for the substitution: per cell and tracer the kernel moves the tendency, t(tau-1), the source
+// (reads) and t(tau+1) (one write).
+#define INV_T 128
+#define INV_KC 8
+__global__ void __launch_bounds__(INV_T) k_invtri(const DevView v, int nbase, int ng, int ntq) {
+  extern __shared__ double zsm[];   // [km][INV_T]
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int tq = blockIdx.x % ntq, cb = blockIdx.x / ntq;
+  const int g = tq * 4 + w;
+  if (g >= ng) return;
+  const int ni = v.imt - 2;
+  const int nrow = v.jhi - v.jlo + 1;
+  const long long idx = (long long)cb * 32 + lane;
   if (idx >= (long long)ni * nrow) return;
-  int i = (int)(idx % ni) + 2;
-  int j = (int)(idx / ni) + v.jlo;
-  const int n0 = nbase + blockIdx.y;
-  double *z = v.t_p1 + (long long)n0 * v.n3;
+  const int i = (int)(idx % ni) + 2;
+  const int j = (int)(idx / ni) + v.jlo;
+  const int n0 = nbase + g;
+  double *__restrict__ z = v.t_p1 + (long long)n0 * v.n3;
   const double *__restrict__ tm1 = v.t_m1 + (long long)n0 * v.n3;
   const int isrc = v.itrc[n0];
   const double *__restrict__ srcp = (isrc != 0) ? v.src + (long long)(isrc - 1) * v.n3 : nullptr;
+  const double *__restrict__ tri_a = v.tri_a, *__restrict__ tri_bet = v.tri_bet, *__restrict__ tri_e = v.tri_e;
+  double *zc = zsm + threadIdx.x;
   const int km = v.km;
   const int kb = v.kmt[X2(i, j)];
   const int kbot = max(2, kb);
-  double topbc = v.stf[X2(i, j) + (long long)n0 * v.n2];
-  double botbc = v.btf[X2(i, j) + (long long)n0 * v.n2];
+  const double topbc = v.stf[X2(i, j) + (long long)n0 * v.n2];
+  const double botbc = v.btf[X2(i, j) + (long long)n0 * v.n2];
+  const double aidif = v.aidif, c2dtts = v.c2dtts;
   double zprev = 0.0;
   const int c1 = (int)X3(i, 1, j), sk = v.imt;
-  for (int k = 1; k <= km; k++) {
-    int c = c1 + (k - 1) * sk;
-    double mk = (kb >= k) ? 1.0 : 0.0;
-    double tdt = v.c2dtts * v.dtxcel[k - 1];
-    // explicit update (09/mom/tracer.F:1114-1127) from the partial tendency left by k_update
-    const double zc = tm1[c] + tdt * (z[c] + (srcp ? srcp[c] : 0.0)) * mk;
-    double f = zc * mk;
-    if (k == 1) f = zc + topbc * tdt * v.dztr[0] * v.aidif * mk;
-    if (k == kbot) f = zc - botbc * tdt * v.dztr[k - 1] * v.aidif * mk;
-    double zk;
-    if (k == 1)
-      zk = f * v.tri_bet[c];
-    else
-      zk = (f - v.tri_a[c] * zprev) * v.tri_bet[c];
-    z[c] = zk;
-    zprev = zk;
+  // levels are processed in chunks of INV_KC: all loads of a chunk are issued before its (serial) recurrence, so a
+  // thread keeps 5*INV_KC independent 8-byte loads in flight instead of one level's worth
+  const double *__restrict__ dtx = v.dtxcel;
+  const double dztr_top = v.dztr[0], dztr_bot = v.dztr[kbot - 1];
+  for (int k0 = 1; k0 <= km; k0 += INV_KC) {
+    double pp[INV_KC], tt[INV_KC], ss[INV_KC], aa[INV_KC], bb[INV_KC], td[INV_KC];
+#pragma unroll
+    for (int q = 0; q < INV_KC; q++) {
+      const int k = min(k0 + q, km);
+      const int c = c1 + (k - 1) * sk;
+      pp[q] = z[c];
+      tt[q] = tm1[c];
+      ss[q] = srcp ? srcp[c] : 0.0;
+      aa[q] = tri_a[c];
+      bb[q] = tri_bet[c];
+      td[q] = dtx[k - 1];
+    }
+    asm volatile("" ::: "memory");   // keep the chunk's loads together, ahead of the recurrence
+#pragma unroll
+    for (int q = 0; q < INV_KC; q++) {
+      const int k = k0 + q;
+      if (k <= km) {
+        const double mk = (kb >= k) ? 1.0 : 0.0;
+        const double tdt = c2dtts * td[q];
+        // explicit update (09/mom/tracer.F:1114-1127) from the partial tendency left by the flux kernels
+        const double zc0 = tt[q] + tdt * (pp[q] + ss[q]) * mk;
+        double f = zc0 * mk;
+        if (k == 1) f = zc0 + topbc * tdt * dztr_top * aidif * mk;
+        if (k == kbot) f = zc0 - botbc * tdt * dztr_bot * aidif * mk;
+        double zk;
+        if (k == 1)
+          zk = f * bb[q];
+        else
+          zk = (f - aa[q] * zprev) * bb[q];
+        zc[(k - 1) * INV_T] = zk;
+        zprev = zk;
+      }
+    }
   }
-  // back substitution + cyclic boundary
+  // back substitution + cyclic boundary (setbcx, 09/mom/tracer.F:1153-1155)
+  const int wrap = (i == 2) ? (v.imt - 2) : ((i == v.imt - 1) ? -(v.imt - 2) : 0);
   double znext = zprev;
   {
-    int c = c1 + (km - 1) * sk;
-    if (i == 2) z[c + v.imt - 2] = znext;
-    if (i == v.imt - 1) z[c - (v.imt - 2)] = znext;
+    const int c = c1 + (km - 1) * sk;
+    z[c] = znext;
+    if (wrap) z[c + wrap] = znext;
   }
-  for (int k = km - 1; k >= 1; k--) {
-    int c = c1 + (k - 1) * sk;
-    double zk = z[c] - v.tri_e[c + sk] * znext;
-    z[c] = zk;
-    znext = zk;
-    if (i == 2) z[c + v.imt - 2] = zk;
-    if (i == v.imt - 1) z[c - (v.imt - 2)] = zk;
+  for (int k0 = km - 1; k0 >= 1; k0 -= INV_KC) {
+    double ee[INV_KC];
+#pragma unroll
+    for (int q = 0; q < INV_KC; q++) {
+      const int k = max(k0 - q, 1);
+      ee[q] = tri_e[c1 + k * sk];
+    }
+    asm volatile("" ::: "memory");
+#pragma unroll
+    for (int q = 0; q < INV_KC; q++) {
+      const int k = k0 - q;
+      if (k >= 1) {
+        const int c = c1 + (k - 1) * sk;
+        const double zk = zc[(k - 1) * INV_T] - ee[q] * znext;
+        z[c] = zk;
+        znext = zk;
+        if (wrap) z[c + wrap] = zk;
+      }
+    }
   }
 }
 
@@ -584,10 +635,14 @@ __global__ void __launch_bounds__(128) k_convect_tr(const DevView v, int nfirst)
   }
 }
 
-// UVIC_B200_FCT=merged runs diffusion and the FCT fluxes in one kernel (k_update<1>); the default splits them
-static bool fct_split() {
+// FCT variants: the default is the marching kernel of k_fct.cu behind the diffusion pass; UVIC_B200_FCT=split keeps
+// the two-pass version (ratios through HBM: k_fct_rfac, then k_update<3>), =merged runs diffusion and the FCT fluxes
+// of the two-pass version in one kernel (k_update<1>).  All three agree bit for bit (tests/test_gpu_parity.py).
+int fct_variant() {
   const char *e = getenv("UVIC_B200_FCT");
-  return !(e && !strcmp(e, "merged"));
+  if (e && !strcmp(e, "merged")) return 2;
+  if (e && !strcmp(e, "split")) return 1;
+  return 0;
 }
 
 void launch_tracer(uvic_b200_ctx *c, const uvic_b200_stepinfo *si) {
@@ -624,13 +679,19 @@ void launch_tracer(uvic_b200_ctx *c, const uvic_b200_stepinfo *si) {
     nchunk = (ng + tch - 1) / tch;
     dim3 gc(cdiv(ncell_c, UPD_T), nchunk);
     if (v.fct) {
-      dim3 gr(cdiv(ncell_r, 256), nchunk);
-      KLAUNCH("k_fct_rfac", k_fct_rfac, gr, 256, v, nbase, ng, tch, jf_r, nrow_r);
-      if (fct_split()) {
+      const int variant = fct_variant();
+      if (variant == 0) {
         KLAUNCH("k_diffuse", k_update<2>, gc, UPD_T, v, nbase, ng, tch, v.jlo, nrow_c);
-        KLAUNCH("k_fct_apply", k_update<3>, gc, UPD_T, v, nbase, ng, tch, v.jlo, nrow_c);
+        launch_fct_march(c, nbase, ng);
       } else {
-        KLAUNCH("k_update", k_update<1>, gc, UPD_T, v, nbase, ng, tch, v.jlo, nrow_c);
+        dim3 gr(cdiv(ncell_r, 256), nchunk);
+        KLAUNCH("k_fct_rfac", k_fct_rfac, gr, 256, v, nbase, ng, tch, jf_r, nrow_r);
+        if (variant == 1) {
+          KLAUNCH("k_diffuse", k_update<2>, gc, UPD_T, v, nbase, ng, tch, v.jlo, nrow_c);
+          KLAUNCH("k_fct_apply", k_update<3>, gc, UPD_T, v, nbase, ng, tch, v.jlo, nrow_c);
+        } else {
+          KLAUNCH("k_update", k_update<1>, gc, UPD_T, v, nbase, ng, tch, v.jlo, nrow_c);
+        }
       }
     } else {
       KLAUNCH("k_update", k_update<0>, gc, UPD_T, v, nbase, ng, tch, v.jlo, nrow_c);
@@ -642,8 +703,17 @@ void launch_tracer(uvic_b200_ctx *c, const uvic_b200_stepinfo *si) {
       cudaStreamWaitEvent(c->stream, c->mobi_event, 0);
       mobi_waited = true;
     }
-    dim3 gi(cdiv(ncol, 128), ng);
-    KLAUNCH("k_invtri", k_invtri, gi, 128, v, nbase);
+    {
+      const int ntq = (ng + 3) / 4;
+      const size_t shm = (size_t)v.km * INV_T * sizeof(double);
+      static size_t shm_set = 0;
+      if (shm > 48 * 1024 && shm > shm_set) {
+        cudaFuncSetAttribute(k_invtri, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+        shm_set = shm;
+      }
+      ProfScope ps_(c, "k_invtri");
+      k_invtri<<<cdiv(ncol, 32) * ntq, INV_T, shm, c->stream>>>(v, nbase, ng, ntq);
+    }
     if (c->par.fullconvect) {
       if (nbase == 0) KLAUNCH("k_convect_ts", k_convect_ts, cdiv(ncol, 128), 128, v);
       const int nfirst = max(2, nbase), ntr = nbase + ng - nfirst;
