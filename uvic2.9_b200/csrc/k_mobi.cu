@@ -22,6 +22,16 @@
 #include "mobi_par.h"
 #include <stdlib.h>
 
+// k_mobi_cell is long straight-line code (~120 KB of SASS when everything is inlined, most of it copies of exp / log /
+// pow / tanh and of ta_iter's divides) and was stalled on instruction fetch; the pre-pass kernels call one out-of-line
+// body per function.  Same library code, same results.  The sub-step loops of the column kernels keep the inlined
+// versions (measured: out-of-line calls cost them 2-4 %).
+__device__ __noinline__ double m_exp(double x) { return exp(x); }
+__device__ __noinline__ double m_log(double x) { return log(x); }
+__device__ __noinline__ double m_log10(double x) { return log10(x); }
+__device__ __noinline__ double m_pow(double x, double y) { return pow(x, y); }
+__device__ __noinline__ double m_tanh(double x) { return tanh(x); }
+
 #define TRCMIN 5e-12        // 09/mom/mobi.h:199
 #define RN15STD 0.0036765   // 09/mom/mobi.h
 #define RC13STD 0.0112372
@@ -63,23 +73,48 @@ __device__ __forceinline__ void ta_iter(const Carb &q, double x, double &fn, dou
        q.st * (1.0 / (hs * hs)) * (q.ks * c / x2) - q.ft * (1.0 / (hf * hf)) * (q.kf * c / x2) - q.pt * x2 * (3.0 * a - x * da) / a2;
 }
 
-// 09/common/co2calc.F:401-454 (Numerical Recipes rtsafe, error trapping removed)
+// 09/common/co2calc.F:401-454 (Numerical Recipes rtsafe, error trapping removed).  The reference evaluates ta_iter at
+// x1, at x2, at the midpoint and then once per iteration; here all evaluations go through ONE inlined copy of ta_iter
+// (it holds ~30 divides: four copies were a third of k_mobi_cell's code) driven by a small state machine that performs
+// the same evaluations in the same order.
 __device__ double drtsafe(const Carb &q, double x1, double x2, double xacc) {
-  double fl, fh, df, f, xl, xh;
-  ta_iter(q, x1, fl, df);
-  ta_iter(q, x2, fh, df);
-  if (fl < 0.0) {
-    xl = x1;
-    xh = x2;
-  } else {
-    xh = x1;
-    xl = x2;
-  }
-  double r = 0.5 * (x1 + x2);
-  double dxold = fabs(x2 - x1);
-  double dx = dxold;
-  ta_iter(q, r, f, df);
-  for (int it = 1; it <= 100; it++) {
+  double fl = 0.0, f = 0.0, df = 0.0, xl = 0.0, xh = 0.0, r = 0.0, dxold = 0.0, dx = 0.0;
+  double x = x1;
+  int stage = 0, it = 0;
+  while (true) {
+    double fv, dfv;
+    ta_iter(q, x, fv, dfv);
+    if (stage == 0) {          // f(x1)
+      fl = fv;
+      x = x2;
+      stage = 1;
+      continue;
+    }
+    if (stage == 1) {          // f(x2): orient the bracket, start from the midpoint
+      if (fl < 0.0) {
+        xl = x1;
+        xh = x2;
+      } else {
+        xh = x1;
+        xl = x2;
+      }
+      r = 0.5 * (x1 + x2);
+      dxold = fabs(x2 - x1);
+      dx = dxold;
+      x = r;
+      stage = 2;
+      continue;
+    }
+    f = fv;
+    df = dfv;
+    if (stage == 3) {          // evaluation at the end of an iteration: shrink the bracket
+      if (f < 0.0)
+        xl = r;
+      else
+        xh = r;
+    }
+    stage = 3;
+    if (++it > 100) return r;
     if (((r - xh) * df - f) * ((r - xl) * df - f) >= 0. || fabs(2.0 * f) > fabs(dxold * df)) {
       dxold = dx;
       dx = 0.5 * (xh - xl);
@@ -93,13 +128,8 @@ __device__ double drtsafe(const Carb &q, double x1, double x2, double xacc) {
       if (temp == r) return r;
     }
     if (fabs(dx) < xacc) return r;
-    ta_iter(q, r, f, df);
-    if (f < 0.0)
-      xl = r;
-    else
-      xh = r;
+    x = r;
   }
-  return r;
 }
 
 // 09/common/co2calc.F:1-400; returns CO2* (mol m-3) and Omega_calcite, the two outputs MOBI uses
@@ -115,14 +145,14 @@ __device__ void co2calc_sws(double t, double s, double dic_in, double ta_in, dou
   double tk100 = tk / 100.0;
   double tk1002 = tk100 * tk100;
   double invtk = 1.0 / tk;
-  double dlogtk = log(tk);
+  double dlogtk = m_log(tk);
   double is = 19.924 * s / (1000. - 1.005 * s);
   double is2 = is * is;
   double sqrtis = sqrt(is);
   double s2 = s * s;
   double t2 = t * t;
   double sqrts = sqrt(s);
-  double s15 = pow(s, 1.5);
+  double s15 = m_pow(s, 1.5);
   double scl = s / 1.80655;
   double pitkR = pres / tk / 83.15;
   double p2itkR = pres * pitkR;
@@ -131,44 +161,44 @@ __device__ void co2calc_sws(double t, double s, double dic_in, double ta_in, dou
   q.ft = 0.000067 * scl / 18.9984;
   (void)tk1002;
 
-  q.k1 = pow(10., (-1. * (3670.7 * invtk - 62.008 + 9.7944 * dlogtk - 0.0118 * s + 0.000116 * s2))) *
-         exp((25.5 - 0.1271 * t) * pitkR + 0.5 * (-3.08e-3 + 8.77e-5 * t) * p2itkR);
-  q.k2 = pow(10., (-1 * (1394.7 * invtk + 4.777 - 0.0184 * s + 0.000118 * s2))) *
-         exp((15.82 + 0.0219 * t) * pitkR + 0.5 * (1.13e-3 - 1.475e-4 * t) * p2itkR);
-  q.k1p = exp(-4576.752 * invtk + 115.540 - 18.453 * dlogtk + (-106.736 * invtk + 0.69171) * sqrts + (-0.65643 * invtk - 0.01844) * s) *
-          exp((14.51 - 0.1211 * t + 3.21e-4 * t2) * pitkR + 0.5 * (-2.67e-3 + 4.27e-5 * t) * p2itkR);
-  q.k2p = exp(-8814.715 * invtk + 172.1033 - 27.927 * dlogtk + (-160.340 * invtk + 1.3566) * sqrts + (0.37335 * invtk - 0.05778) * s) *
-          exp((23.12 - 0.1758 * t + 2.647e-3 * t2) * pitkR + 0.5 * (-5.15e-3 + 9.0e-5 * t) * p2itkR);
-  q.k3p = exp(-3070.75 * invtk - 18.126 + (17.27039 * invtk + 2.81197) * sqrts + (-44.99486 * invtk - 0.09984) * s) *
-          exp((26.57 - 0.202 * t + 3.042e-3 * t2) * pitkR + 0.5 * (-4.08e-3 + 7.14e-5 * t) * p2itkR);
-  q.ksi = exp(-8904.2 * invtk + 117.400 - 19.334 * dlogtk + (-458.79 * invtk + 3.5913) * sqrtis + (188.74 * invtk - 1.5998) * is +
-              (-12.1652 * invtk + 0.07871) * is2 + log(1.0 - 0.001005 * s)) *
-          exp((29.48 - 0.1622 * t - 2.608e-3 * t2) * pitkR + 0.5 * (-2.84e-3) * p2itkR);
-  q.kw = exp(-13847.26 * invtk + 148.9802 - 23.6521 * dlogtk + (118.67 * invtk - 5.977 + 1.0495 * dlogtk) * sqrts - 0.01615 * s) *
-         exp((20.02 - 0.1119 * t + 1.409e-3 * t2) * pitkR + 0.5 * (-5.13e-3 + 7.94e-5 * t) * p2itkR);
-  q.ks = exp(-4276.1 * invtk + 141.328 - 23.093 * dlogtk + (-13856 * invtk + 324.57 - 47.986 * dlogtk) * sqrtis +
-             (35474 * invtk - 771.54 + 114.723 * dlogtk) * is - 2698 * invtk * pow(is, 1.5) + 1776 * invtk * is2 +
-             log(1.0 - 0.001005 * s)) *
-         exp((18.03 - .0466 * t - 3.16e-4 * t2) * pitkR + 0.5 * (-4.53e-3 + 9.0e-5 * t) * p2itkR);
-  q.kf = exp(1590.2 * invtk - 12.641 + 1.525 * sqrtis + log(1.0 - 0.001005 * s)) *
-         exp((9.78 + 9.0e-3 * t + 9.42e-4 * t2) * pitkR + 0.5 * (-3.91e-3 + 5.4e-5 * t) * p2itkR);
-  q.kb = exp((-8966.90 - 2890.53 * sqrts - 77.942 * s + 1.728 * s15 - 0.0996 * s2) * invtk +
+  q.k1 = m_pow(10., (-1. * (3670.7 * invtk - 62.008 + 9.7944 * dlogtk - 0.0118 * s + 0.000116 * s2))) *
+         m_exp((25.5 - 0.1271 * t) * pitkR + 0.5 * (-3.08e-3 + 8.77e-5 * t) * p2itkR);
+  q.k2 = m_pow(10., (-1 * (1394.7 * invtk + 4.777 - 0.0184 * s + 0.000118 * s2))) *
+         m_exp((15.82 + 0.0219 * t) * pitkR + 0.5 * (1.13e-3 - 1.475e-4 * t) * p2itkR);
+  q.k1p = m_exp(-4576.752 * invtk + 115.540 - 18.453 * dlogtk + (-106.736 * invtk + 0.69171) * sqrts + (-0.65643 * invtk - 0.01844) * s) *
+          m_exp((14.51 - 0.1211 * t + 3.21e-4 * t2) * pitkR + 0.5 * (-2.67e-3 + 4.27e-5 * t) * p2itkR);
+  q.k2p = m_exp(-8814.715 * invtk + 172.1033 - 27.927 * dlogtk + (-160.340 * invtk + 1.3566) * sqrts + (0.37335 * invtk - 0.05778) * s) *
+          m_exp((23.12 - 0.1758 * t + 2.647e-3 * t2) * pitkR + 0.5 * (-5.15e-3 + 9.0e-5 * t) * p2itkR);
+  q.k3p = m_exp(-3070.75 * invtk - 18.126 + (17.27039 * invtk + 2.81197) * sqrts + (-44.99486 * invtk - 0.09984) * s) *
+          m_exp((26.57 - 0.202 * t + 3.042e-3 * t2) * pitkR + 0.5 * (-4.08e-3 + 7.14e-5 * t) * p2itkR);
+  q.ksi = m_exp(-8904.2 * invtk + 117.400 - 19.334 * dlogtk + (-458.79 * invtk + 3.5913) * sqrtis + (188.74 * invtk - 1.5998) * is +
+              (-12.1652 * invtk + 0.07871) * is2 + m_log(1.0 - 0.001005 * s)) *
+          m_exp((29.48 - 0.1622 * t - 2.608e-3 * t2) * pitkR + 0.5 * (-2.84e-3) * p2itkR);
+  q.kw = m_exp(-13847.26 * invtk + 148.9802 - 23.6521 * dlogtk + (118.67 * invtk - 5.977 + 1.0495 * dlogtk) * sqrts - 0.01615 * s) *
+         m_exp((20.02 - 0.1119 * t + 1.409e-3 * t2) * pitkR + 0.5 * (-5.13e-3 + 7.94e-5 * t) * p2itkR);
+  q.ks = m_exp(-4276.1 * invtk + 141.328 - 23.093 * dlogtk + (-13856 * invtk + 324.57 - 47.986 * dlogtk) * sqrtis +
+             (35474 * invtk - 771.54 + 114.723 * dlogtk) * is - 2698 * invtk * m_pow(is, 1.5) + 1776 * invtk * is2 +
+             m_log(1.0 - 0.001005 * s)) *
+         m_exp((18.03 - .0466 * t - 3.16e-4 * t2) * pitkR + 0.5 * (-4.53e-3 + 9.0e-5 * t) * p2itkR);
+  q.kf = m_exp(1590.2 * invtk - 12.641 + 1.525 * sqrtis + m_log(1.0 - 0.001005 * s)) *
+         m_exp((9.78 + 9.0e-3 * t + 9.42e-4 * t2) * pitkR + 0.5 * (-3.91e-3 + 5.4e-5 * t) * p2itkR);
+  q.kb = m_exp((-8966.90 - 2890.53 * sqrts - 77.942 * s + 1.728 * s15 - 0.0996 * s2) * invtk +
              (148.0248 + 137.1942 * sqrts + 1.62142 * s) + (-24.4344 - 25.085 * sqrts - 0.2474 * s) * dlogtk + 0.053105 * sqrts * tk +
-             log((1 + (q.st / q.ks) + (q.ft / q.kf)) / (1 + (q.st / q.ks)))) *
-         exp((29.48 - 0.1622 * t - 2.608e-3 * t2) * pitkR + 0.5 * (-2.84e-3) * p2itkR);
+             m_log((1 + (q.st / q.ks) + (q.ft / q.kf)) / (1 + (q.st / q.ks)))) *
+         m_exp((29.48 - 0.1622 * t - 2.608e-3 * t2) * pitkR + 0.5 * (-2.84e-3) * p2itkR);
 
   // [H+] on the seawater scale in [1e-10, 1e-6], xacc = 1e-10 (:343-346)
-  double x1 = pow(10.0, -6.), x2 = pow(10.0, -10.);
+  double x1 = m_pow(10.0, -6.), x2 = m_pow(10.0, -10.);
   double hSWS = drtsafe(q, x1, x2, 1.e-10);
   double hSWS2 = hSWS * hSWS;
   double co2star = q.dic * hSWS2 / (hSWS2 + q.k1 * hSWS + q.k1 * q.k2);
   double CO3 = q.k1 * q.k2 * co2star / hSWS2;
   // calcite solubility product with pressure dependence (:360-388)
-  double Kspc = exp(-395.8293 + (6537.773 / tk) + 71.595 * log(tk) - 0.17959 * tk +
+  double Kspc = m_exp(-395.8293 + (6537.773 / tk) + 71.595 * m_log(tk) - 0.17959 * tk +
                     (-1.78938 + (410.64 / tk) + 0.0065453 * tk) * sqrt(s) - 0.17755 * s + 0.0094979 * s15);
   double DVc = -65.28 + 0.397 * t - 0.005155 * (t * t) + (19.816 - 0.0441 * t - 0.00017 * (t * t)) * sqrt(s / 35.);
   double DK = 0.01847 + 0.0001956 * t - 0.000002212 * (t * t) + (-0.03217 - 0.0000711 * t + 0.000002212) * sqrt(s / 35.);
-  Kspc = Kspc * exp(-DVc * pitkR + 0.5 * DK * p2itkR);
+  Kspc = Kspc * m_exp(-DVc * pitkR + 0.5 * DK * p2itkR);
   const double Ca = 10.28E-3;
   omega_c = Ca * CO3 / Kspc;
   co2star_out = co2star / permil;
@@ -207,7 +237,7 @@ __global__ void __launch_bounds__(128) k_mobi_light(const DevView v, double decl
   rctheta = P->kw / sqrt(1. - (1. - cr * cr) / (1.33 * 1.33));
   double dayfrac = fmin(1., -tan(lat / radian) * tan(declin));
   dayfrac = fmax(1e-12, acos(fmax(-1., dayfrac)) / pi);
-  double swr = P->tap * v.dnswr[X2(i, j)] * 1e-3 * (1. + v.aice[X2(i, j)] * (exp(-P->ki * (v.hice[X2(i, j)] + v.hsno[X2(i, j)])) - 1.));
+  double swr = P->tap * v.dnswr[X2(i, j)] * 1e-3 * (1. + v.aice[X2(i, j)] * (m_exp(-P->ki * (v.hice[X2(i, j)] + v.hsno[X2(i, j)])) - 1.));
   v.mobi_day[X2(i, j)] = dayfrac;
   const long long n3 = v.n3;
   const double *__restrict__ phyt = v.t_m1 + (long long)(ix[IX_TR + V_PHYT] - 1) * n3;
@@ -218,18 +248,18 @@ __global__ void __launch_bounds__(128) k_mobi_light(const DevView v, double decl
   for (int k = 1; k <= kmx; k++) {
     const long long c = X3(i, k, j);
     const double dztk = v.dzt[k - 1];
-    swr = swr * exp(-P->kc * phin - P->kc_c * caco3in);
+    swr = swr * m_exp(-P->kc * phin - P->kc_c * caco3in);
     phin = fmax(phyt[c], TRCMIN) * dztk + fmax(diaz[c], TRCMIN) * dztk + fmax(diat[c], TRCMIN) * dztk;
     caco3in = caco3in + caco3[c] * dztk;
-    v.mobi_pre[(long long)PR_GL * n3 + c] = swr * exp(P->ztt[k - 1] * rctheta);
+    v.mobi_pre[(long long)PR_GL * n3 + c] = swr * m_exp(P->ztt[k - 1] * rctheta);
   }
 }
 
 // Evans & Parslow daily-mean light-limited growth (09/mom/mobi.F:1984-2003), one species
 __device__ __forceinline__ double evans_parslow(double gl_x, double gd, double f1, double kirr, double dzt) {
   double u1 = fmax(gl_x / gd, 1.e-6), u2 = u1 * f1;
-  double phi1 = log(u1 + sqrt(1. + u1 * u1)) - (sqrt(1. + u1 * u1) - 1.) / u1;
-  double phi2 = log(u2 + sqrt(1. + u2 * u2)) - (sqrt(1. + u2 * u2) - 1.) / u2;
+  double phi1 = m_log(u1 + sqrt(1. + u1 * u1)) - (sqrt(1. + u1 * u1) - 1.) / u1;
+  double phi2 = m_log(u2 + sqrt(1. + u2 * u2)) - (sqrt(1. + u2 * u2) - 1.) / u2;
   return gd * (phi1 - phi2) / (-kirr * dzt);
 }
 
@@ -262,7 +292,7 @@ __global__ void __launch_bounds__(128, 5) k_mobi_cell(const DevView v) {
   co2calc_sws(t_in, s_in, dic_in, alk_in, v.zt[k - 1] / 100., co2star, Omega_c);
   {
     double ac13_DIC_aq = -1.0512994e-4 * t_in + 1.011765;
-    double ac13_aq_POC = -0.017 * log10(fmin(fmax(co2star * 1000., 2.), 74.)) + 1.0034;
+    double ac13_aq_POC = -0.017 * m_log10(fmin(fmax(co2star * 1000., 2.), 74.)) + 1.0034;
     pre[(long long)PR_AC13B * n3] = ac13_aq_POC / ac13_DIC_aq;
     pre[(long long)PR_DISSK1 * n3] = P->dissk0 * fmax(0., (1. - Omega_c));
     pre[(long long)PR_CAPR * n3] = P->caprmax * fmax(0., (Omega_c - 1.) / (P->kcapr + Omega_c - 1.));
@@ -270,26 +300,26 @@ __global__ void __launch_bounds__(128, 5) k_mobi_cell(const DevView v) {
   // oxygen saturation -> AOU for the ligand parameterisation
   double aou_in;
   {
-    double f1 = log((298.15 - t_in) / (273.15 + t_in));
+    double f1 = m_log((298.15 - t_in) / (273.15 + t_in));
     double f2 = f1 * f1, f3 = f2 * f1, f4 = f3 * f1, f5 = f4 * f1;
-    double o2sat = exp(2.00907 + 3.22014 * f1 + 4.05010 * f2 + 4.94457 * f3 - 2.56847E-1 * f4 + 3.88767 * f5 +
+    double o2sat = m_exp(2.00907 + 3.22014 * f1 + 4.05010 * f2 + 4.94457 * f3 - 2.56847E-1 * f4 + 3.88767 * f5 +
                        s_in * (-6.24523e-3 - 7.37614e-3 * f1 - 1.03410e-2 * f2 - 8.17083E-3 * f3) - 4.88682E-7 * s_in * s_in);
     o2sat = o2sat / 22391.6 * 1000.0 * 1000.;
     aou_in = o2sat - o2_in;
   }
-  const double bct = pow(P->bbio, (P->cbio * t_in));
-  const double fo2 = tanh(0.22 * fmax(o2_in, 0.));
+  const double bct = m_pow(P->bbio, (P->cbio * t_in));
+  const double fo2 = m_tanh(0.22 * fmax(o2_in, 0.));
   pre[(long long)PR_BCT * n3] = bct;
-  pre[(long long)PR_BCTZ * n3] = (0.5 * (tanh(o2_in - 8.) + 1)) * bct;   // same bbio**(cbio*t) value (:830-835)
+  pre[(long long)PR_BCTZ * n3] = (0.5 * (m_tanh(o2_in - 8.) + 1)) * bct;   // same bbio**(cbio*t) value (:830-835)
   pre[(long long)PR_NUD * n3] = P->nud0 * (0.6 + 0.4 * fo2);
   pre[(long long)PR_FO2 * n3] = fo2;
-  pre[(long long)PR_AOU8 * n3] = pow(fmax(aou_in, 40.), 0.8);
-  pre[(long long)PR_O2FLAG * n3] = tanh(fmax(o2_in, 0.));
+  pre[(long long)PR_AOU8 * n3] = m_pow(fmax(aou_in, 40.), 0.8);
+  pre[(long long)PR_O2FLAG * n3] = m_tanh(fmax(o2_in, 0.));
   {
     const double tno3 = fmax(TIN(IX_TR + V_NO3), TRCMIN);   // tnpzd(k,ino3) after the clip of mobi_src
-    pre[(long long)PR_P099 * n3] = pow(0.99, (fmax(o2_in, TRCMIN) - fmax(tno3, TRCMIN)));
-    pre[(long long)PR_LNO3A * n3] = 0.5 * tanh(tno3 * 10 - 5.0);
-    pre[(long long)PR_LNO3B * n3] = 0.5 * tanh(tno3 - 2.5);
+    pre[(long long)PR_P099 * n3] = m_pow(0.99, (fmax(o2_in, TRCMIN) - fmax(tno3, TRCMIN)));
+    pre[(long long)PR_LNO3A * n3] = 0.5 * m_tanh(tno3 * 10 - 5.0);
+    pre[(long long)PR_LNO3B * n3] = 0.5 * m_tanh(tno3 - 2.5);
   }
   // light harvesting and daily growth integrals on the clipped inputs
   {
@@ -311,7 +341,7 @@ __global__ void __launch_bounds__(128, 5) k_mobi_cell(const DevView v) {
     double deffe_D = bdfe / (P->kfe_D + bdfe);
     double gl_D = gl * (P->thetamaxlo + (P->thetamaxhi - P->thetamaxlo) * deffe_D) * (P->alphamin + (P->alphamax - P->alphamin) * deffe_D);
     double kirr = -P->kw - P->kc * (bphyt + bdiaz + bdiat) - P->kc_c * bcaco3;
-    double f1 = exp(kirr * dzt);
+    double f1 = m_exp(kirr * dzt);
     double jmax = P->abio_P * bct * deffe;
     pre[(long long)PR_AVEJ * n3] = evans_parslow(gl_O, jmax * dayfrac, f1, kirr, dzt);
     double jmax_D = fmax(0., P->abio_P * (bct - P->dbct_D) * deffe_D) * P->jdiar;
