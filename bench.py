@@ -90,10 +90,13 @@ def kernel_bytes_per_launch(name, case, ctx, ngroup_launch):
     g = ngroup_launch
     ocean = float((case["kmt"][ctx.jlo - 1:ctx.jhi, 1:-1]).sum())  # ocean cells in the owned rows
     table = {
-        "k_fct_tlo": cells_r * (16 * g + 24),          # t(tau-1) in, t_lo out per tracer; 3 face velocities
-        "k_fct_rfac": cells_r * (72 * g + 24),         # t_lo, t(tau-1), t(tau) in; 6 ratios out; velocities
-        "k_update": cells * (80 * g + 176),            # 6 ratios, t(tau-1), t(tau), src in; t(tau+1) out; 22 shared fields
-        "k_invtri": cells * (16 * g + 24),             # t(tau+1) in/out; a, e, bet
+        "k_fct_march": cells * (32 * g + 24),          # t(tau-1), t(tau), tendency in; tendency out per tracer; 3 face velocities
+        "k_diffuse": cells * (16 * g + 176),           # t(tau-1) in, tendency out per tracer; 22 shared coefficient fields
+        "k_fct_tlo": cells_r * (16 * g + 24),          # (two-pass reference variants)
+        "k_fct_rfac": cells_r * (72 * g + 24),
+        "k_fct_apply": cells * (80 * g + 24),
+        "k_update": cells * (80 * g + 176),
+        "k_invtri": cells * (32 * g + 24),             # tendency, t(tau-1), source in; t(tau+1) out; a, e, bet
         "k_convect_ts": cells * 32,                    # T,S read + written (worst case)
         "k_convect_tr": cells * 16 * (case.nt - 2),    # worst case: every other tracer read + written
         "k_mobi_column": ocean * 8 * (37 + 15 + 35),   # 37 tracers + 15 pre-pass fields in; 35 sources out
@@ -109,6 +112,13 @@ def kernel_bytes_per_launch(name, case, ctx, ngroup_launch):
         "k_gm_total": cells * 8 * (4 + 2),
     }
     return table.get(name)
+
+
+PER_TRACER_KERNELS = ("k_fct_march", "k_diffuse", "k_fct_tlo", "k_fct_rfac", "k_fct_apply", "k_update", "k_invtri")
+
+# FP64-pipe instructions per cell*tracer of the flux kernels (thread level; from the committed ncu captures,
+# sm__pipe_fp64_cycles_active x duration: profiles/r01_ncu_*): these kernels are FP64-issue bound, not HBM bound
+DP_INST_PER_UNIT = {"k_fct_march": 309.0, "k_diffuse": 177.0}
 
 
 class ClockSampler:
@@ -410,18 +420,36 @@ def main():
     for name, (kms, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
         per_launch_ms = kms / max(cnt, 1)
         groups = max(1, cnt // a.steps)
-        ng = -(-case.nt // groups) if name in ("k_fct_tlo", "k_fct_rfac", "k_update", "k_invtri") else case.nt
+        ng = -(-case.nt // groups) if name in PER_TRACER_KERNELS else case.nt
         b = kernel_bytes_per_launch(name, case, ctx, ng)
         kern.append({"kernel": name, "launches": cnt, "ms_total": round(kms, 4), "share": round(kms / tot_ms, 4),
                      "us_per_launch": round(1e3 * per_launch_ms, 2),
                      "gbs": round(b / (per_launch_ms * 1e-3) / 1e9, 1) if b else None})
     top = kern[0]
-    top_bytes = kernel_bytes_per_launch(top["kernel"], case, ctx, -(-case.nt // max(1, top["launches"] // a.steps)))
+    top_ng = -(-case.nt // max(1, top["launches"] // a.steps)) if top["kernel"] in PER_TRACER_KERNELS else case.nt
+    top_bytes = kernel_bytes_per_launch(top["kernel"], case, ctx, top_ng)
     achieved = top_bytes / (top["us_per_launch"] * 1e-6) / 1e9 if top_bytes else None
+    # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed `ncu --set full` capture
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if os.path.exists(tpath):
+        traffic = (json.load(open(tpath)).get(a.workload) or {}).get(top["kernel"])
     roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "bytes_per_launch": top_bytes, "us_per_launch": top["us_per_launch"],
-                "note": "compulsory bytes of the launch as designed / CUDA-event time; see profiles/ for the ncu capture"}
+                "note": "compulsory bytes of the launch as designed / CUDA-event time; traffic = ncu dram bytes of one launch "
+                        "(profiles/r01_ncu_traffic.json)"}
+    # the flux kernels are FP64-issue bound: report them against the FP64 pipe as well (148 SMs x 64 lanes x SM clock)
+    sm_mhz = (clk or {}).get("sm_mhz") or 1965.0
+    fp64_peak = 148 * 64 * sm_mhz * 1e6 / 1e12
+    units_rank = (case.imt - 2) * (ctx.jhi - ctx.jlo + 1) * case.km * case.nt
+    for kq in kern:
+        dp = DP_INST_PER_UNIT.get(kq["kernel"])
+        if dp:
+            ms_step_k = kq["ms_total"] / a.steps
+            kq["fp64_tinst_s"] = round(dp * units_rank / (ms_step_k * 1e-3) / 1e12, 3)
+            kq["fp64_frac"] = round(kq["fp64_tinst_s"] / fp64_peak, 4)
+    roofline["fp64_peak_tinst_s"] = round(fp64_peak, 2)
     step_bytes = algorithmic_step_bytes(case, w["mobi"]) / world
     step_hbm = {"algorithmic_bytes_per_step": step_bytes, "achieved": step_bytes / (ms_step * 1e-3) / 1e9, "peak": peak,
                 "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak, "unit": "GB/s",

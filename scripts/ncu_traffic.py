@@ -1,0 +1,35 @@
+#!/usr/bin/env python
+"""Per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of every kernel in .ncu-rep files
+-> profiles/r01_ncu_traffic.json, which bench.py quotes as roofline.traffic.
+
+    python scripts/ncu_traffic.py WORKLOAD=report.ncu-rep [WORKLOAD=report2.ncu-rep ...]
+"""
+import csv
+import json
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+NAMES = {"k_update<2>": "k_diffuse", "k_update<3>": "k_fct_apply", "k_update<1>": "k_update", "k_update<0>": "k_update"}
+
+out = json.load(open(OUT)) if os.path.exists(OUT) else {}
+for arg in sys.argv[1:]:
+    wl, rep = arg.split("=", 1)
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    ix = {h: i for i, h in enumerate(hdr)}
+    for r in rows[2:]:
+        name = r[ix["Kernel Name"]]
+        short = re.sub(r"^void ", "", name).split("(")[0]
+        short = NAMES.get(short, re.sub(r"<.*>", "", short))
+        tot = 0.0
+        for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(r[ix[m]]) * SCALE[units[ix[m]]]
+        out.setdefault(wl, {})[short] = int(tot)
+json.dump(out, open(OUT, "w"), indent=1, sort_keys=True)
+print(json.dumps(out, indent=1, sort_keys=True))

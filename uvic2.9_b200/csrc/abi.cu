@@ -5,6 +5,7 @@
 #include <string.h>
 #include <algorithm>
 #include "ctx.h"
+#include <stdlib.h>
 
 static std::string g_create_err;
 
@@ -77,7 +78,7 @@ int uvic_b200_create(const uvic_b200_dims *d, const uvic_b200_grid *g, const uvi
   ctx->red_partial = ctx->red_out = nullptr;
   ctx->pin_buf = nullptr; ctx->pin_bytes = 0;
   ctx->prof_on = false;
-  ctx->stream2 = nullptr; ctx->fork_event = nullptr; ctx->mobi_event = nullptr; ctx->mobi_inflight = false;
+  ctx->stream2 = nullptr; ctx->fork_event = nullptr; ctx->mobi_event = nullptr; ctx->src_ready[0] = ctx->src_ready[1] = nullptr; ctx->mobi_inflight = false;
   ctx->mobi_dtnpzd = 0.0;
   ctx->src_buf[0] = ctx->src_buf[1] = nullptr; ctx->src_cur = 0;
   ctx->hint_valid = ctx->ahead_valid = false; ctx->ahead_tm1 = nullptr; ctx->ahead_buf = 0;
@@ -222,6 +223,8 @@ int uvic_b200_create(const uvic_b200_dims *d, const uvic_b200_grid *g, const uvi
     }
     CK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ctx->mobi_event, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->src_ready[0], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->src_ready[1], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->main_done_event, cudaEventDisableTiming));
   }
   CK(cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
@@ -279,6 +282,7 @@ int uvic_b200_destroy(uvic_b200_ctx *ctx) {
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
   if (ctx->mobi_event) cudaEventDestroy(ctx->mobi_event);
+  for (auto e : ctx->src_ready) if (e) cudaEventDestroy(e);
   if (ctx->main_done_event) cudaEventDestroy(ctx->main_done_event);
   if (ctx->h2d_event) cudaEventDestroy(ctx->h2d_event);
   if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
@@ -378,8 +382,21 @@ static bool same_step(const uvic_b200_stepinfo &a, const uvic_b200_stepinfo &b) 
 // MOBI of this step.  If the look-ahead of the previous step already produced the sources for exactly this step
 // (same stepinfo, same t(tau-1) slot, nothing uploaded in between) they are adopted; otherwise MOBI is launched on the
 // side stream now.  Either way the main stream waits for mobi_event right before the first sourced k_invtri.
+static int lookahead_mobi(uvic_b200_ctx *ctx);
+static void begin_mobi_now(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si);
+
 static void begin_mobi(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
   if (!ctx->par.mobi || ctx->mobi_inflight) return;
+  begin_mobi_now(ctx, si);
+  // A hinted leapfrog step reads today's t(tau) as its t(tau-1): that field is final already, so its MOBI is queued
+  // right behind this step's MOBI instead of behind this step's tracer kernels (a hinted mixing step needs t(tau+1)
+  // and is launched at the end of the step, uvic_b200_tracer).  The side stream then runs a whole step ahead and the
+  // implicit solve never waits for it.
+  static const bool early = !(getenv("UVIC_B200_MOBI_EARLY") && atoi(getenv("UVIC_B200_MOBI_EARLY")) == 0);   // A/B switch
+  if (early && ctx->hint_valid && ctx->hint_si.leapfrog && !ctx->prof_on) lookahead_mobi(ctx);
+}
+
+static void begin_mobi_now(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
   if (ctx->ahead_valid) {
     const bool hit = !ctx->prof_on && same_step(*si, ctx->ahead_si) && ctx->ahead_tm1 == ctx->v.t_m1;
     ctx->ahead_valid = false;
@@ -397,6 +414,7 @@ static void begin_mobi(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
     cudaStreamWaitEvent(ctx->stream, ctx->mobi_event, 0);   // a look-ahead still in flight uses the same scratch
     launch_mobi(ctx, ctx->v, si);
     cudaEventRecord(ctx->mobi_event, ctx->stream);
+    cudaEventRecord(ctx->src_ready[ctx->src_cur], ctx->stream);
     ctx->mobi_inflight = true;
     return;
   }
@@ -407,10 +425,11 @@ static void begin_mobi(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
   launch_mobi(ctx, ctx->v, si);
   ctx->stream = main_stream;
   cudaEventRecord(ctx->mobi_event, ctx->stream2);
+  cudaEventRecord(ctx->src_ready[ctx->src_cur], ctx->stream2);
   ctx->mobi_inflight = true;
 }
 
-// MOBI of the NEXT step (hinted), queued behind this step's kernels on the side stream
+// MOBI of the NEXT step (hinted), queued on the side stream behind everything the main stream holds at this point
 static int lookahead_mobi(uvic_b200_ctx *ctx) {
   if (!ctx->hint_valid) return 0;
   ctx->hint_valid = false;
@@ -437,6 +456,7 @@ static int lookahead_mobi(uvic_b200_ctx *ctx) {
   launch_mobi(ctx, vv, &h);
   ctx->stream = main_stream;
   CK(cudaEventRecord(ctx->mobi_event, ctx->stream2));
+  CK(cudaEventRecord(ctx->src_ready[other], ctx->stream2));
   ctx->ahead_valid = true;
   ctx->ahead_si = h;
   ctx->ahead_tm1 = vv.t_m1;

@@ -231,9 +231,9 @@ __global__ void __launch_bounds__(32 * MAXW, 1) k_fct_march(const DevView v, int
       const double wb_d = sWb[so + o_c], wb_u = sWb[so + o_c - FM_W];
       kmc = sK[sko];
       const double m = (kmc >= k) ? 1.0 : 0.0;
-      const double mu = (kmc >= k - 1) ? 1.0 : 0.0, md = (kmc >= k + 1) ? 1.0 : 0.0;
-      const double mw = (sK[sko - 1] >= k) ? 1.0 : 0.0, me = (sK[sko + 1] >= k) ? 1.0 : 0.0;
-      const double ms = m_p, mn = (sK[((r + 1) & 3) * FM_W + lane + 1] >= k) ? 1.0 : 0.0;
+      const double mu = (kmc >= k - 1) ? 1.0 : 0.0;
+      const bool mw_b = sK[sko - 1] >= k, me_b = sK[sko + 1] >= k;
+      const bool ms_b = kmc_p >= k, mn_b = sK[((r + 1) & 3) * FM_W + lane + 1] >= k;
       const double dcfx = cstr[r - 1] * dxtr_i * 0.5;
       const double dcfy = cstdyt2r[r - 1];
       // low-order fluxes of the six faces and the low-order solution (:496-580)
@@ -257,14 +257,15 @@ __global__ void __launch_bounds__(32 * MAXW, 1) k_fct_march(const DevView v, int
       const double a_w = ue_w * (Uw + Uc) - lo_w;
       const double a_e = ue_c * (Uc + Ue) - lo_e;
       {
-        const double fxa = mw * (0.5 * (Uw + Uc)) + (1.0 - mw) * tlo;
-        const double fxb = me * (0.5 * (Uc + Ue)) + (1.0 - me) * tlo;
+        // mask*(average) + (1-mask)*t_lo with a 0/1 mask is one of the two terms (up to the sign of a zero): select it
+        const double fxa = mw_b ? 0.5 * (Uw + Uc) : tlo;
+        const double fxb = me_b ? 0.5 * (Uc + Ue) : tlo;
         ratio(c2dtts, dcfx, a_w, a_e, fxa, fxb, tlo, m, rxp, rxm);
       }
       // ---- y (:714-770): flxlft = anti_fn(j-1) (= 0 for row 1, :475), flxrgt = anti_fn(j) ----
       {
-        const double fxa = 0.5 * ms * (Um + Uc) + (1.0 - ms) * tlo;
-        const double fxb = 0.5 * mn * (Uc + Un) + (1.0 - mn) * tlo;
+        const double fxa = ms_b ? 0.5 * (Um + Uc) : tlo;
+        const double fxb = mn_b ? 0.5 * (Uc + Un) : tlo;
         a_n = vn_c * (Uc + Un) - lo_n;
         ratio(c2dtts, dcfy, a_n_p, a_n, fxa, fxb, tlo, m, ryp, rym);
       }
@@ -273,8 +274,8 @@ __global__ void __launch_bounds__(32 * MAXW, 1) k_fct_march(const DevView v, int
       const double a_d = wb_d * (Uc + Ud) - lo_d * m;
       const double a_u = wb_u * (Uu + Uc) - lo_u * mu;
       {
-        const double fxa = (k > 1) ? 0.5 * mu * (Uu + Uc) + (1.0 - mu) * tlo : tlo;
-        const double fxb = (k < km) ? 0.5 * md * (Uc + Ud) + (1.0 - md) * tlo : tlo;
+        const double fxa = (k > 1 && kmc >= k - 1) ? 0.5 * (Uu + Uc) : tlo;
+        const double fxb = (k < km && kmc >= k + 1) ? 0.5 * (Uc + Ud) : tlo;
         ratio(c2dtts, dcfz, (k == km) ? 0.0 : a_d, (k == 1) ? wb_u * 2.0 * Tc : a_u, fxa, fxb, tlo, m, rzp, rzm);
       }
       double *R = sR + (r & 1) * (4 * FM_MAXW * 32);

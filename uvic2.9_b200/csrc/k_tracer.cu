@@ -700,7 +700,7 @@ void launch_tracer(uvic_b200_ctx *c, const uvic_b200_stepinfo *si) {
     bool sourced = false;
     for (int n = nbase; n < nbase + ng; n++) sourced = sourced || c->itrc_h[n] != 0;
     if (sourced && !mobi_waited && c->mobi_event && c->mobi_inflight) {
-      cudaStreamWaitEvent(c->stream, c->mobi_event, 0);
+      cudaStreamWaitEvent(c->stream, c->src_ready[c->src_cur], 0);   // this step's sources, not a look-ahead queued behind them
       mobi_waited = true;
     }
     {
