@@ -175,7 +175,8 @@ class ClockSampler:
 
 
 def oracle_step_time(pkg, case, mobi, nsteps, warm=1):
-    """Seconds per step of the CPU oracle (single thread) on this case."""
+    """Seconds per step of the CPU oracle (single thread) on this case; the -O3 build (the reference's run/mk.ver level)."""
+    os.environ["UVIC_ORACLE_VARIANT"] = "o3"
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from helpers import make_oracle, oracle_rotate, oracle_set_step
 
@@ -233,7 +234,7 @@ def run_reference(a):
         "config": {"workload": a.workload, "desc": w["desc"], "grid": [case.imt, case.jmt, case.km], "nt": case.nt},
         "cpu_baseline": {"value": value, "unit": "G cell*tracer/s", "cores": nrep, "kind": "port",
                          "sample": f"{nrep} independent serial replicas (the reference is a serial code) x {nsteps} full steps of the "
-                                   f"workload after {warm} warm-up; oracle/ C restatement, gcc -O2 -ffp-contract=off; "
+                                   f"workload after {warm} warm-up; oracle/ C restatement, gcc -O3 -march=x86-64-v3 (the reference builds with -O3, run/mk.ver); "
                                    f"single-replica step {1e3 * min(per):.0f}-{1e3 * tmax:.0f} ms; wall {wall:.0f} s"},
         "e2e": {"value": value, "unit": "G cell*tracer/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -470,7 +471,7 @@ def main():
             sample = f"1 full step of a {rows}-row latitude sub-slab of the workload, throughput per cell"
         tstep = oracle_step_time(pkg, sub, w["mobi"], ns, 1)
         cpu = {"value": units_per_step(sub) / tstep / 1e9, "unit": "G cell*tracer/s", "cores": 1, "kind": "port",
-               "sample": sample + "; oracle/ C restatement (gcc -O2 -ffp-contract=off), single thread",
+               "sample": sample + "; oracle/ C restatement (gcc -O3 -march=x86-64-v3, the reference's -O3 level), single thread",
                "ms_per_step": 1e3 * tstep}
 
     line = {

@@ -9,7 +9,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
-LIB = os.path.join(ORACLE_DIR, "_build", "liboracle.so")
+# UVIC_ORACLE_VARIANT=o3 selects the -O3 timing build (bench.py's CPU baseline); the parity tests use the default,
+# which is compiled without FMA contraction
+LIB = os.path.join(ORACLE_DIR, "_build", "liboracle_o3.so" if os.environ.get("UVIC_ORACLE_VARIANT") == "o3" else "liboracle.so")
 
 
 def build_oracle(force=False):
