@@ -400,6 +400,52 @@ def main():
                "note": "uvic_b200_tracer_step: adv velocities + stf/btf H2D from pinned memory and the whole t(tau+1) D2H every step, "
                        "copies on their own streams under the kernels; MOBI of step n+1 runs while t(tau+1) of step n travels"}
 
+        # ---- the same step with setvbc / set_sbc on the device: per step the host sends the advective
+        # velocities and, once per ocean segment, the coupler's sbc array; it receives T and S of t(tau+1) every step (the
+        # density clinic / loadmw need) and the sbc array with the averaged surface accumulators at the end of a segment
+        # (segtim = 5 days, dtts = 1.25 days: ntspos = 4, run/control.in:3-4); the other tracers stay resident
+        nsbc = 2 * case.nt + 4
+        ctx.sbc_setup(nsbc, np.arange(1, case.nt + 1, dtype=np.int32), np.arange(case.nt + 1, 2 * case.nt + 1, dtype=np.int32))
+        h_sbc = pinned(np.zeros((nsbc, ctx.jl, case.imt)))
+        h_bhf = pinned(np.zeros((ctx.jl, case.imt)))
+        h_sbc_out = torch.empty((nsbc, ctx.jl, case.imt), dtype=torch.float64, pin_memory=True)
+        h_ts = torch.empty((2,) + tuple(ctx.shape_t()[1:]), dtype=torch.float64, pin_memory=True)
+        ntspos = 4
+
+        def coupled_step():
+            state["itt"] += 1
+            lf = pkg.timestep.is_leapfrog(state["itt"], 16)
+            p = (state["itt"] - 1) % ntspos
+            ctx.tracer_step_coupled(h_vet.numpy(), h_vnt.numpy(), h_vbt.numpy(), h_sbc.numpy() if p == 0 else None,
+                                    h_bhf.numpy() if p == 0 else None, True, p == 0, p == ntspos - 1, ntspos, h_ts.numpy(),
+                                    h_sbc_out.numpy(), leapfrog=lf, next_leapfrog=pkg.timestep.is_leapfrog(state["itt"] + 1, 16))
+            if world > 1:
+                halo.exchange(tp1_tensor())
+            ctx.rotate()
+
+        nc = ntspos * max(1, a.steps // ntspos)      # whole segments
+        state["itt"] = 0
+        for _ in range(ntspos):
+            coupled_step()
+        barrier()
+        t0 = time.perf_counter()
+        ev0.record(stream)
+        for _ in range(nc):
+            coupled_step()
+        ev1.record(stream)
+        barrier()
+        ms_c = max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3)
+        if world > 1:
+            tt = torch.tensor([ms_c], device=f"cuda:{local}", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms_c = float(tt.item())
+        vel_b = sum(x.numel() * 8 for x in (h_vet, h_vnt, h_vbt))
+        e2e["coupled"] = {"value": units / (ms_c / nc * 1e-3) / 1e9, "unit": "G cell*tracer/s", "ms_per_step": ms_c / nc, "steps": nc,
+                          "h2d_bytes_per_step": int(vel_b + (h_sbc.numel() + h_bhf.numel()) * 8 / ntspos),
+                          "d2h_bytes_per_step": int(h_ts.numel() * 8 + h_sbc_out.numel() * 8 / ntspos),
+                          "note": "uvic_b200_tracer_step_coupled: setvbc / set_sbc on the device; velocities in and T,S out every "
+                                  "step, the sbc array in / out once per 4-step ocean segment; other tracers resident"}
+
     # ---- conservation check on the state the timed steps produced -----------------------
     inv = ctx.inventory(0)
 

@@ -120,6 +120,21 @@ int uvic_b200_upload_vbc(uvic_b200_ctx *ctx, const double *stf, const double *bt
 /* MOBI 2-D forcing: dnswr, aice, hice, hsno (imt,jl) (09/mom/tracer.F:370-390) */
 int uvic_b200_upload_forcing(uvic_b200_ctx *ctx, const double *dnswr, const double *aice, const double *hice, const double *hsno);
 /* rotate time levels after a step: tau-1 <- tau <- tau+1 (source/mom/mom.F:210-212) */
+/* Surface boundary conditions on the device.  sbc(imt,jl,numsbc) is this slab of the coupler's
+ * array (09/common/csbc.h); flx_index[n-1] / acc_index[n-1] are the 1-based sbc slots that hold tracer n's surface flux
+ * (the right-hand sides of the assignment list in 09/mom/setvbc.F:83-126) and its surface accumulator (trsbcindex(n),
+ * 09/mom/tracer.F:1270-1288); 0 = none.  With these the host moves 2-D fields per step: the flux slots in, and the
+ * accumulator slots out at the end of an ocean segment. */
+int uvic_b200_sbc_setup(uvic_b200_ctx *ctx, int numsbc, const int32_t *flx_index, const int32_t *acc_index);
+int uvic_b200_upload_sbc(uvic_b200_ctx *ctx, const double *sbc, const double *bhf);            /* whole array / (imt,jl); NULL = keep */
+int uvic_b200_upload_sbc_slot(uvic_b200_ctx *ctx, int slot, const double *field);              /* one (imt,jl) slot, async */
+int uvic_b200_download_sbc(uvic_b200_ctx *ctx, double *sbc);
+int uvic_b200_download_sbc_slot(uvic_b200_ctx *ctx, int slot, double *field);
+int uvic_b200_setvbc(uvic_b200_ctx *ctx);   /* call setvbc (source/mom/mom.F:360, 09/mom/setvbc.F:60-140): fills stf, btf */
+/* call set_sbc for every tracer with an accumulator slot (09/mom/tracer.F:1270-1288, 09/mom/set_sbc.F:36-83) on the
+ * t(tau+1) the last uvic_b200_tracer produced; eots/osegs/osege/ntspos are the switches of source/common/switch.h */
+int uvic_b200_set_sbc(uvic_b200_ctx *ctx, int eots, int osegs, int osege, int ntspos);
+
 int uvic_b200_rotate(uvic_b200_ctx *ctx);
 
 /* ---- the hot path, one entry per reference call site (device resident) ------------ */
@@ -152,6 +167,16 @@ int uvic_b200_tracer_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si, cons
 /* ---- diagnostics (09/mom/tracer.F:1516-1565) ---------------------------------------- */
 /* volume-weighted inventories sum(t*dV) of every tracer at one time level over the rows
  * this context owns, deterministic fixed-order reduction; out(nt) */
+/* One ocean step with setvbc / set_sbc on the device (needs uvic_b200_sbc_setup).  Host -> device: the advective
+ * velocities (every step) and, when they changed, the coupler's sbc array and the bottom heat flux (NULL = keep).
+ * Device -> host: T and S of t(tau+1), ts_taup1(imt,km,jl,2), for the density in clinic / loadmw (NULL = skip), and the
+ * whole sbc array with the averaged surface accumulators when this step ends an ocean segment (eots && osege).  All
+ * other tracers stay resident; output steps fetch them with uvic_b200_download_tracer.  Synchronous like the call
+ * sites it replaces (setvbc source/mom/mom.F:360, isopyc :340, vmixc :347, tracer :389). */
+int uvic_b200_tracer_step_coupled(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si, const double *adv_vet,
+                                  const double *adv_vnt, const double *adv_vbt, const double *sbc_in, const double *bhf,
+                                  int eots, int osegs, int osege, int ntspos, double *ts_taup1, double *sbc_out);
+
 int uvic_b200_inventory(uvic_b200_ctx *ctx, int level, double *out_nt);
 /* tbar(km,nt,jl): sum_i t(tau)*dzt*dxt*cst*dyt*tmask per level, tracer and row */
 int uvic_b200_tbar(uvic_b200_ctx *ctx, double *tbar_host);

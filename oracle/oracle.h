@@ -133,6 +133,14 @@ typedef struct ora_ctx {
   ora_mobi_par *mobi;
   int32_t *mobi_idx;   /* tracer index maps, see ora_mobi.h */
 
+  /* ---- surface boundary conditions (09/common/csbc.h, 09/mom/setvbc.F, 09/mom/set_sbc.F) ---- */
+  int numsbc;
+  double *sbc;             /* (imt,jmt,numsbc) */
+  double *bhf;             /* (imt,jmt) bottom heat flux */
+  int32_t *sbc_flx_index;  /* (nt) 1-based sbc slot of tracer n's surface flux, 0 = none */
+  int32_t *trsbcindex;     /* (nt) 1-based sbc slot of tracer n's surface accumulator, 0 = none */
+  int eots, osegs, osege, ntspos;   /* source/common/switch.h */
+
   /* ---- Fourier filter (source/common/index.h) ---- */
   int do_filter;
   int jfrst, jft1, jft2, jft0;  /* source/common/setcom.F */
@@ -162,6 +170,8 @@ void ora_tracer(ora_ctx *c);                           /* 09/mom/tracer.F:214-13
 void ora_diag_tbar(ora_ctx *c, int n);                 /* 09/mom/tracer.F:1516-1565 */
 void ora_mobi_columns(ora_ctx *c);                     /* 09/mom/tracer.F:310-545,848-867 */
 void ora_filt(ora_ctx *c);                             /* source/common/filt.F */
+void ora_setvbc(ora_ctx *c);                           /* 09/mom/setvbc.F:60-140 */
+void ora_set_sbc(ora_ctx *c);                          /* 09/mom/set_sbc.F:36-83 via 09/mom/tracer.F:1270-1288 */
 
 /* one full step as mom.F sequences it: isopyc -> vmixc -> tracer (source/mom/mom.F:340-389) */
 void ora_step(ora_ctx *c);

@@ -277,3 +277,57 @@ def test_fourier_filter_properties(pkg):
         return (d ** 2).sum()
     assert rough(after) < 0.7 * rough(before)
     o.close()
+
+
+def test_setvbc_and_set_sbc_semantics(pkg):
+    """09/mom/setvbc.F:60-140 and 09/mom/set_sbc.F:36-83: stf = flux slot * tmask(k=1), btf = 0 except the bottom
+    heat flux on temperature; the surface accumulators are zeroed at the start of an ocean segment and averaged at its
+    end on ocean cells only, while the per-step accumulation also runs over land (the reference's own quirk)."""
+    from helpers import make_oracle
+
+    case = pkg.synthetic.make_case(imt=22, jmt=18, km=6, nt=5, names=["temp", "salt", "p0", "p1", "p2"], seed=5)
+    o = make_oracle(case)
+    o.call("ora_make_masks")
+    imt, jmt, km, nt = case.imt, case.jmt, case.km, case.nt
+    numsbc = 2 * nt + 4
+    rng = np.random.default_rng(7)
+    sbc = o.arr("sbc", (numsbc, jmt, imt))
+    sbc[...] = rng.standard_normal(sbc.shape)
+    o.arr("bhf", (jmt, imt))[...] = rng.standard_normal((jmt, imt))
+    flx = np.array([1, 2, 0, 4, 5], dtype=np.int32)
+    acc = np.array([6, 7, 8, 0, 9], dtype=np.int32)
+    o.set("sbc_flx_index", flx)
+    o.set("trsbcindex", acc)
+    tmask1 = (case["kmt"] >= 1).astype(float)
+    o.call("ora_setvbc")
+    stf, btf = o.arr("stf", (nt, jmt, imt)), o.arr("btf", (nt, jmt, imt))
+    for n in range(nt):
+        want = sbc[flx[n] - 1] * tmask1 if flx[n] else np.zeros((jmt, imt))
+        assert np.array_equal(stf[n][:, 1:-1], want[:, 1:-1])
+        assert np.array_equal(stf[n][:, [0, -1]], np.zeros((jmt, 2)))       # i = 1, imt are not touched
+    assert np.array_equal(btf[0][:, 1:-1], (-o.arr("bhf", (jmt, imt)) * tmask1)[:, 1:-1])
+    assert not btf[1:].any()
+    # a three-step ocean segment
+    t = o.t()
+    ocean = (case["kmt"] != 0)[:, 1:-1]
+    before = sbc.copy()
+    surf = []
+    for step in range(3):
+        t[2, :, :, 0, :] = rng.standard_normal((nt, jmt, imt))
+        surf.append(t[2, :, :, 0, :].copy())
+        o.set_scalar("eots", 1)
+        o.set_scalar("osegs", 1 if step == 0 else 0)
+        o.set_scalar("osege", 1 if step == 2 else 0)
+        o.set_scalar("ntspos", 3)
+        o.call("ora_set_sbc")
+    for n in range(nt):
+        if not acc[n]:
+            continue
+        got = sbc[acc[n] - 1][:, 1:-1]
+        s = [x[n][:, 1:-1] for x in surf]
+        mean = (1.0 / 3.0) * (((0.0 + s[0]) + s[1]) + s[2])
+        land = ((before[acc[n] - 1][:, 1:-1] + s[0]) + s[1]) + s[2]
+        assert np.array_equal(got[ocean], mean[ocean])
+        assert np.array_equal(got[~ocean], land[~ocean])
+    assert np.array_equal(sbc[3 - 1], before[3 - 1])      # a slot nobody owns is untouched
+    o.close()

@@ -325,3 +325,65 @@ def test_fct_variants_agree_bitwise(pkg, shape, monkeypatch):
         lo = jlo - ctx.jbase
         assert np.array_equal(got[:, lo:lo + (jhi - jlo + 1)], ref[:, jlo - 1:jhi])
         ctx.close()
+
+
+def test_setvbc_and_set_sbc_on_device(pkg):
+    """setvbc (09/mom/setvbc.F:60-140) and set_sbc (09/mom/set_sbc.F:36-83 via
+    09/mom/tracer.F:1270-1288) on the device.  stf / btf and the accumulators built from an uploaded t(tau+1) are
+    bit-exact; a three-step ocean segment driven by the device-side fluxes stays within 1e-12 of the oracle."""
+    case = _case(pkg, imt=42, jmt=30, km=8, nt=5, seed=21)
+    nt, jmt, imt = case.nt, case.jmt, case.imt
+    numsbc = 2 * nt + 4
+    rng = np.random.default_rng(3)
+    sbc0 = rng.standard_normal((numsbc, jmt, imt)) * 1e-6
+    bhf = rng.standard_normal((jmt, imt)) * 1e-6
+    flx = np.array([1, 2, 0, 4, 5], dtype=np.int32)
+    acc = np.array([6, 7, 8, 0, 9], dtype=np.int32)
+    o = make_oracle(case)
+    o.call("ora_make_masks")
+    o.arr("sbc", (numsbc, jmt, imt))[...] = sbc0
+    o.arr("bhf", (jmt, imt))[...] = bhf
+    o.set("sbc_flx_index", flx)
+    o.set("trsbcindex", acc)
+    ctx = _ctx(pkg, case)
+    ctx.sbc_setup(numsbc, flx, acc)
+    ctx.upload_sbc(sbc0, bhf)
+    # setvbc: bit-exact
+    o.call("ora_setvbc")
+    ctx.setvbc()
+    for name in ("stf", "btf"):
+        assert np.array_equal(ctx.fetch(name, (nt, jmt, imt)), o.arr(name, (nt, jmt, imt))), name
+    # set_sbc on a given t(tau+1): bit-exact, all switch combinations of a segment
+    tp1 = rng.standard_normal(ctx.shape_t())
+    ctx.upload_t(+1, tp1)
+    o.t()[2] = tp1
+    for eots, osegs, osege in ((1, 1, 0), (1, 0, 0), (0, 0, 0), (1, 0, 1), (1, 1, 1)):
+        for k, v in (("eots", eots), ("osegs", osegs), ("osege", osege), ("ntspos", 3)):
+            o.set_scalar(k, v)
+        o.call("ora_set_sbc")
+        ctx.set_sbc(eots, osegs, osege, 3)
+        got, ref = ctx.download_sbc(), o.arr("sbc", (numsbc, jmt, imt))
+        assert np.array_equal(got[:, 1:-1], ref[:, 1:-1]), (eots, osegs, osege)
+    # a three-step segment with the surface fluxes in play
+    ctx.load_state()
+    o.load_case(case)
+    o.arr("sbc", (numsbc, jmt, imt))[...] = sbc0
+    ctx.upload_sbc(sbc0, bhf)
+    for step in range(3):
+        oracle_set_step(o, case, True)
+        o.call("ora_setvbc")
+        o.call("ora_step")
+        ctx.setvbc()
+        ctx.step(True)
+        for k, v in (("eots", 1), ("osegs", int(step == 0)), ("osege", int(step == 2)), ("ntspos", 3)):
+            o.set_scalar(k, v)
+        o.call("ora_set_sbc")
+        ctx.set_sbc(1, step == 0, step == 2, 3)
+        oracle_rotate(o)
+        ctx.rotate()
+    got, ref = ctx.download_sbc(), o.arr("sbc", (numsbc, jmt, imt))
+    for n in range(nt):
+        if acc[n]:
+            assert relerr(got[acc[n] - 1][1:-1, 1:-1], ref[acc[n] - 1][1:-1, 1:-1]) <= TOL, n
+    ctx.close()
+    o.close()

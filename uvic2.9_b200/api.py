@@ -65,6 +65,8 @@ ABI_SYMBOLS = [
     "uvic_b200_t_ptr", "uvic_b200_kernel_launches", "uvic_b200_local_rows", "uvic_b200_version",
     "uvic_b200_profile_enable", "uvic_b200_profile_count", "uvic_b200_profile_get", "uvic_b200_profile_reset",
     "uvic_b200_hint_next_step", "uvic_b200_pin_host", "uvic_b200_unpin_host",
+    "uvic_b200_sbc_setup", "uvic_b200_upload_sbc", "uvic_b200_upload_sbc_slot", "uvic_b200_download_sbc",
+    "uvic_b200_download_sbc_slot", "uvic_b200_setvbc", "uvic_b200_set_sbc", "uvic_b200_tracer_step_coupled",
 ]
 
 _lib = None
@@ -116,6 +118,14 @@ def load_library():
     L.uvic_b200_profile_count.argtypes = [vp]
     L.uvic_b200_profile_get.argtypes = [vp, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.uvic_b200_profile_reset.argtypes = [vp]
+    L.uvic_b200_sbc_setup.argtypes = [vp, C.c_int, vp, vp]
+    L.uvic_b200_upload_sbc.argtypes = [vp, vp, vp]
+    L.uvic_b200_upload_sbc_slot.argtypes = [vp, C.c_int, vp]
+    L.uvic_b200_download_sbc.argtypes = [vp, vp]
+    L.uvic_b200_download_sbc_slot.argtypes = [vp, C.c_int, vp]
+    L.uvic_b200_setvbc.argtypes = [vp]
+    L.uvic_b200_set_sbc.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.uvic_b200_tracer_step_coupled.argtypes = [vp, C.POINTER(StepInfo)] + [vp] * 5 + [C.c_int] * 4 + [vp, vp]
     _lib = L
     return L
 
@@ -286,6 +296,47 @@ class TracerContext:
 
     def rotate(self):
         self._ck(self.L.uvic_b200_rotate(self.h))
+
+    # ---- surface boundary conditions on the device (09/mom/setvbc.F, 09/mom/set_sbc.F) ----
+    def sbc_setup(self, numsbc, flx_index, acc_index):
+        """flx_index[n] / acc_index[n]: 1-based sbc slot of tracer n's surface flux / accumulator (0 = none)."""
+        self.numsbc = int(numsbc)
+        f = np.ascontiguousarray(flx_index, dtype=np.int32)
+        a = np.ascontiguousarray(acc_index, dtype=np.int32)
+        assert f.shape == (self.nt,) and a.shape == (self.nt,)
+        self._ck(self.L.uvic_b200_sbc_setup(self.h, self.numsbc, _vp(f), _vp(a)))
+
+    def upload_sbc(self, sbc_local=None, bhf_local=None):
+        """sbc_local: (numsbc, jl, imt) slab of the coupler's array; bhf_local: (jl, imt)."""
+        if sbc_local is not None:
+            sbc_local = np.ascontiguousarray(sbc_local, dtype=np.float64)
+            assert sbc_local.shape == (self.numsbc, self.jl, self.imt)
+        if bhf_local is not None:
+            bhf_local = np.ascontiguousarray(bhf_local, dtype=np.float64)
+            assert bhf_local.shape == (self.jl, self.imt)
+        self._ck(self.L.uvic_b200_upload_sbc(self.h, _vp(sbc_local), _vp(bhf_local)))
+        self.synchronize()
+
+    def download_sbc(self):
+        out = np.empty((self.numsbc, self.jl, self.imt))
+        self._ck(self.L.uvic_b200_download_sbc(self.h, _vp(out)))
+        return out
+
+    def setvbc(self):
+        self._ck(self.L.uvic_b200_setvbc(self.h))
+
+    def tracer_step_coupled(self, adv_vet, adv_vnt, adv_vbt, sbc_in, bhf, eots, osegs, osege, ntspos, ts_taup1, sbc_out,
+                            leapfrog=True, next_leapfrog=None):
+        """uvic_b200_tracer_step_coupled with host (ideally pinned) numpy buffers; None = NULL."""
+        if next_leapfrog is not None:
+            self.hint_next_step(next_leapfrog)
+        si = self.stepinfo(leapfrog)
+        self._ck(self.L.uvic_b200_tracer_step_coupled(self.h, C.byref(si), _vp(adv_vet), _vp(adv_vnt), _vp(adv_vbt), _vp(sbc_in),
+                                                      _vp(bhf), int(eots), int(osegs), int(osege), int(ntspos), _vp(ts_taup1),
+                                                      _vp(sbc_out)))
+
+    def set_sbc(self, eots=True, osegs=False, osege=False, ntspos=1):
+        self._ck(self.L.uvic_b200_set_sbc(self.h, int(eots), int(osegs), int(osege), int(ntspos)))
 
     # ---- the reference's call sites ---------------------------------------------------
     def isopyc(self):

@@ -82,7 +82,7 @@ int uvic_b200_create(const uvic_b200_dims *d, const uvic_b200_grid *g, const uvi
   ctx->mobi_dtnpzd = 0.0;
   ctx->src_buf[0] = ctx->src_buf[1] = nullptr; ctx->src_cur = 0;
   ctx->hint_valid = ctx->ahead_valid = false; ctx->ahead_tm1 = nullptr; ctx->ahead_buf = 0;
-  ctx->main_done_event = nullptr; ctx->copy_in = ctx->copy_out = nullptr; ctx->h2d_event = nullptr; ctx->d2h_dst = nullptr;
+  ctx->main_done_event = nullptr; ctx->copy_in = ctx->copy_out = nullptr; ctx->h2d_event = nullptr; ctx->d2h_dst = nullptr; ctx->d2h_ntr = 0;
   DevView &v = ctx->v;
   memset(&v, 0, sizeof v);
   v.imt = d->imt; v.jmt = d->jmt; v.km = d->km; v.nt = d->nt; v.nsrc = d->nsrc;
@@ -365,6 +365,61 @@ int uvic_b200_upload_forcing(uvic_b200_ctx *ctx, const double *dnswr, const doub
   if (hsno) CK(cudaMemcpyAsync(v.hsno, hsno, nb, cudaMemcpyHostToDevice, ctx->stream));
   return 0;
 }
+// ---- surface boundary conditions on the device ----
+int uvic_b200_sbc_setup(uvic_b200_ctx *ctx, int numsbc, const int32_t *flx_index, const int32_t *acc_index) {
+  if (!ctx || numsbc < 1 || !flx_index || !acc_index) return fail(ctx, "sbc_setup: bad argument");
+  if (ctx->v.sbc) return fail(ctx, "sbc_setup: already set up");
+  for (int n = 0; n < ctx->v.nt; n++)
+    if (flx_index[n] < 0 || flx_index[n] > numsbc || acc_index[n] < 0 || acc_index[n] > numsbc)
+      return fail(ctx, "sbc_setup: slot index out of range");
+  ctx->v.numsbc = numsbc;
+  DALLOC(sbc, (size_t)ctx->v.n2 * numsbc, nullptr);
+  DALLOC(bhf, ctx->v.n2, nullptr);
+  IALLOC(sbc_flx, ctx->v.nt, flx_index);
+  IALLOC(sbc_acc, ctx->v.nt, acc_index);
+  return 0;
+}
+int uvic_b200_upload_sbc(uvic_b200_ctx *ctx, const double *sbc, const double *bhf) {
+  DevView &v = ctx->v;
+  if (!v.sbc) return fail(ctx, "upload_sbc: call uvic_b200_sbc_setup first");
+  if (sbc) CK(cudaMemcpyAsync(v.sbc, sbc, (size_t)v.n2 * v.numsbc * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (bhf) CK(cudaMemcpyAsync(v.bhf, bhf, (size_t)v.n2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+int uvic_b200_upload_sbc_slot(uvic_b200_ctx *ctx, int slot, const double *field) {
+  DevView &v = ctx->v;
+  if (!v.sbc || slot < 1 || slot > v.numsbc || !field) return fail(ctx, "upload_sbc_slot: bad slot or no sbc_setup");
+  CK(cudaMemcpyAsync(v.sbc + (size_t)(slot - 1) * v.n2, field, (size_t)v.n2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+int uvic_b200_download_sbc_slot(uvic_b200_ctx *ctx, int slot, double *field) {
+  DevView &v = ctx->v;
+  if (!v.sbc || slot < 1 || slot > v.numsbc || !field) return fail(ctx, "download_sbc_slot: bad slot or no sbc_setup");
+  CK(cudaMemcpyAsync(field, v.sbc + (size_t)(slot - 1) * v.n2, (size_t)v.n2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int uvic_b200_download_sbc(uvic_b200_ctx *ctx, double *sbc) {
+  DevView &v = ctx->v;
+  if (!v.sbc || !sbc) return fail(ctx, "download_sbc: call uvic_b200_sbc_setup first");
+  CK(cudaMemcpyAsync(sbc, v.sbc, (size_t)v.n2 * v.numsbc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int uvic_b200_setvbc(uvic_b200_ctx *ctx) {
+  if (!ctx->v.sbc) return fail(ctx, "setvbc: call uvic_b200_sbc_setup first");
+  launch_setvbc(ctx);
+  CK(cudaGetLastError());
+  return 0;
+}
+int uvic_b200_set_sbc(uvic_b200_ctx *ctx, int eots, int osegs, int osege, int ntspos) {
+  if (!ctx->v.sbc) return fail(ctx, "set_sbc: call uvic_b200_sbc_setup first");
+  if (ntspos < 1) return fail(ctx, "set_sbc: ntspos must be >= 1");
+  launch_set_sbc(ctx, eots, osegs, osege, ntspos);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int uvic_b200_rotate(uvic_b200_ctx *ctx) {
   // tau+1 overwrites the old tau-1 slot next step (source/mom/mom.F:210-212)
   int old_m1 = ctx->lev[0];
@@ -535,9 +590,52 @@ int uvic_b200_tracer_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si, cons
   CK(cudaGetLastError());
   // finished tracer batches stream to the host while the next batch computes (launch_tracer)
   ctx->d2h_dst = t_taup1;
+  ctx->d2h_ntr = ctx->v.nt;
   int rc = uvic_b200_tracer(ctx, si);
   ctx->d2h_dst = nullptr;
   if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->copy_out));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// One ocean step with the surface boundary conditions on the device: what crosses PCIe is what the rest of the model
+// exchanges with the tracer step -- the advective velocities from clinic and (when they changed) the coupler's flux
+// array in; T and S of t(tau+1) for the density in clinic / loadmw every step and the surface accumulators at the end
+// of an ocean segment out.  The other tracers stay resident (uvic_b200_download_tracer fetches them for output steps).
+int uvic_b200_tracer_step_coupled(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si, const double *adv_vet, const double *adv_vnt,
+                                  const double *adv_vbt, const double *sbc_in, const double *bhf, int eots, int osegs, int osege,
+                                  int ntspos, double *ts_taup1, double *sbc_out) {
+  DevView &v = ctx->v;
+  if (!v.sbc) return fail(ctx, "tracer_step_coupled: call uvic_b200_sbc_setup first");
+  if (ntspos < 1) return fail(ctx, "tracer_step_coupled: ntspos must be >= 1");
+  CK(cudaEventRecord(ctx->fork_event, ctx->stream));
+  CK(cudaStreamWaitEvent(ctx->copy_in, ctx->fork_event, 0));
+  if (adv_vet) CK(cudaMemcpyAsync(v.adv_vet, adv_vet, (size_t)v.n3 * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
+  if (adv_vnt) CK(cudaMemcpyAsync(v.adv_vnt, adv_vnt, (size_t)v.n3 * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
+  if (adv_vbt) CK(cudaMemcpyAsync(v.adv_vbt, adv_vbt, (size_t)v.n3z * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
+  if (sbc_in) CK(cudaMemcpyAsync(v.sbc, sbc_in, (size_t)v.n2 * v.numsbc * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
+  if (bhf) CK(cudaMemcpyAsync(v.bhf, bhf, (size_t)v.n2 * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
+  CK(cudaEventRecord(ctx->h2d_event, ctx->copy_in));
+  set_step(ctx, si);
+  begin_mobi(ctx, si);
+  launch_isopyc_coef(ctx);
+  launch_vmixc(ctx);
+  CK(cudaStreamWaitEvent(ctx->stream, ctx->h2d_event, 0));
+  launch_isopyc_vel(ctx);
+  launch_setvbc(ctx);                                  // call setvbc, source/mom/mom.F:360
+  CK(cudaGetLastError());
+  ctx->d2h_dst = ts_taup1;
+  ctx->d2h_ntr = 2;
+  int rc = uvic_b200_tracer(ctx, si);
+  ctx->d2h_dst = nullptr;
+  ctx->d2h_ntr = v.nt;
+  if (rc) return rc;
+  launch_set_sbc(ctx, eots, osegs, osege, ntspos);     // 09/mom/tracer.F:1270-1288
+  CK(cudaGetLastError());
+  if (sbc_out && eots && osege)
+    CK(cudaMemcpyAsync(sbc_out, v.sbc, (size_t)v.n2 * v.numsbc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->copy_out));
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaGetLastError());

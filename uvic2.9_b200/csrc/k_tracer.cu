@@ -660,7 +660,8 @@ void launch_tracer(uvic_b200_ctx *c, const uvic_b200_stepinfo *si) {
   std::vector<std::pair<int, int>> batches;
   if (c->d2h_dst && v.nt > 2) {
     batches.push_back({0, 2});
-    const int rest = v.nt - 2, nb = std::min(rest, std::max(3, (rest + v.ngroup - 1) / v.ngroup));
+    // (the coupled entry point only returns T and S: the other tracers then go in as few batches as possible)
+    const int rest = v.nt - 2, nb = (c->d2h_ntr <= 2) ? 1 : std::min(rest, std::max(3, (rest + v.ngroup - 1) / v.ngroup));
     for (int b = 0; b < nb; b++) {
       const int lo = 2 + (int)((long long)rest * b / nb), hi = 2 + (int)((long long)rest * (b + 1) / nb);
       for (int q = lo; q < hi; q += v.ngroup) batches.push_back({q, std::min(v.ngroup, hi - q)});
@@ -724,7 +725,7 @@ void launch_tracer(uvic_b200_ctx *c, const uvic_b200_stepinfo *si) {
     }
     // Fourier filter of the polar rows + cyclic boundary (09/mom/tracer.F:1245-1262)
     launch_filter(c, nbase, ng);
-    if (c->d2h_dst) {
+    if (c->d2h_dst && nbase < c->d2h_ntr) {
       // this batch of t(tau+1) is final: hand it to the copy stream
       if (nb_done >= c->ev_batch.size()) {
         cudaEvent_t e;
