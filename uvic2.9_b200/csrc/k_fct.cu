@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(32 * MAXW, 1) k_fct_march(const DevView v, int
   }
   __syncthreads();   // row rA0-1 has been read: its slot may be refilled
   // state of the previous row's x / z faces, carried across the barrier to where their neighbours' ratios are visible
-  double c_ae = 0.0, c_loe = 0.0, c_aw = 0.0, c_low = 0.0, c_ad = 0.0, c_lod = 0.0, c_au = 0.0, c_lou = 0.0;
+  double c_ae = 0.0, c_loe = 0.0, c_ad = 0.0, c_lod = 0.0, c_au = 0.0, c_lou = 0.0;
   double c_rxp = 0.0, c_rxm = 0.0, c_rzp = 0.0, c_rzm = 0.0, c_dcfx = 0.0;
 
 #pragma unroll 1
@@ -204,9 +204,10 @@ __global__ void __launch_bounds__(32 * MAXW, 1) k_fct_march(const DevView v, int
     {
       const double *R = sR + ((r - 1) & 1) * (4 * FM_MAXW * 32);
       // east / west faces: Cpos(f) = min(Rpl(f+1),Rmn(f)), Cneg(f) = min(Rpl(f),Rmn(f+1)) (:698-701); no mask (:987)
-      const int le = (lane < 31) ? ro + 1 : ro, lw = (lane > 0) ? ro - 1 : ro;
+      // the west face of a cell is the east face of its western neighbour: one lane over (lane 0 is a halo cell)
+      const int le = (lane < 31) ? ro + 1 : ro;
       const double Fe = delimit(dmin(R[le], c_rxm), dmin(c_rxp, R[FM_MAXW * 32 + le]), c_ae) + c_loe;
-      const double Fw = delimit(dmin(c_rxp, R[FM_MAXW * 32 + lw]), dmin(R[lw], c_rxm), c_aw) + c_low;
+      const double Fw = __shfl_up_sync(0xffffffffu, Fe, 1);
       // bottom / top faces: Cpos(h) = min(Rpl(h),Rmn(h+1)), Cneg(h) = min(Rpl(h+1),Rmn(h)) (:966-969);
       // adv_fb(0), adv_fb(km) are overwritten in tracer (09/mom/tracer.F:1063-1065): level 1 / km carry those in c_lou / c_lod
       const int ld = has_dn ? ro + 32 : ro, lu = has_up ? ro - 32 : ro;
@@ -283,7 +284,7 @@ __global__ void __launch_bounds__(32 * MAXW, 1) k_fct_march(const DevView v, int
       R[FM_MAXW * 32 + ro] = rxm;
       R[2 * FM_MAXW * 32 + ro] = rzp;
       R[3 * FM_MAXW * 32 + ro] = rzm;
-      c_ae = a_e; c_loe = lo_e; c_aw = a_w; c_low = lo_w; c_ad = a_d; c_au = a_u;
+      c_ae = a_e; c_loe = lo_e; c_ad = a_d; c_au = a_u;
       c_lod = (k == km) ? wb_d * Uc : lo_d;           // adv_fb(i,km,j) = adv_vbt(i,km,j)*t(i,km,j,tau)
       c_lou = (k == 1) ? wb_u * (Uc + Uc) : lo_u;     // adv_fb(i,0,j) = adv_vbt(i,0,j)*2*t(i,1,j,tau)
       c_rxp = rxp; c_rxm = rxm; c_rzp = rzp; c_rzm = rzm; c_dcfx = dcfx;

@@ -345,18 +345,37 @@ __global__ void __launch_bounds__(128) k_gm_column(const DevView v) {
       if (gm) store_cyc(v, v.adv_vbtiso, l0, i, 0.0);
       store_cyc(v, v.wb, l0, i, v.adv_vbt[l0 + i - 1] + 0.0);
     }
-    for (int k = 1; k <= v.km; k++) {
-      long long lz = X3Z(1, k, j);
-      double w = 0.0;
-      if (gm && k <= v.km - 1) {
-        double d = v.dzt[k - 1] * v.cstr[j - 1] *
-                   ((v.adv_vetiso[X3(i, k, j)] - v.adv_vetiso[X3(i - 1, k, j)]) * v.dxtr[i - 1] +
-                    (v.adv_vntiso[X3(i, k, j)] - v.adv_vntiso[X3(i, k, j - 1)]) * v.dytr[j - 1]);
-        acc = d + acc;
-        w = (k == kb) ? 0.0 : acc;   // adv_vbtiso(i,kmt,j) = 0 (:1521-1525); the running sum keeps going
+    // loads of 8 levels at a time, ahead of the running sum (few columns per SM: latency, not bandwidth)
+    const double *__restrict__ vet = v.adv_vetiso, *__restrict__ vnt = v.adv_vntiso, *__restrict__ vbt = v.adv_vbt;
+    const int c1 = (int)X3(i, 1, j), sk3 = v.imt, sj3 = v.imt * v.km;
+    const double cstr_j = v.cstr[j - 1], dxtr_i = v.dxtr[i - 1], dytr_j = v.dytr[j - 1];
+    for (int k0 = 1; k0 <= v.km; k0 += 8) {
+      double ec[8], ew[8], nc[8], ns[8], vb[8], dz[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const int k = min(k0 + q, v.km);
+        const int c = c1 + (k - 1) * sk3;
+        vb[q] = vbt[X3Z(1, k, j) + i - 1];
+        dz[q] = v.dzt[k - 1];
+        if (gm) { ec[q] = vet[c]; ew[q] = vet[c - 1]; nc[q] = vnt[c]; ns[q] = vnt[c - sj3]; }
+        else { ec[q] = ew[q] = nc[q] = ns[q] = 0.0; }
       }
-      if (gm) store_cyc(v, v.adv_vbtiso, lz, i, w);
-      store_cyc(v, v.wb, lz, i, v.adv_vbt[lz + i - 1] + w);
+    asm volatile("" ::: "memory");   // keep the chunk's loads together
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const int k = k0 + q;
+        if (k <= v.km) {
+          long long lz = X3Z(1, k, j);
+          double w = 0.0;
+          if (gm && k <= v.km - 1) {
+            double d = dz[q] * cstr_j * ((ec[q] - ew[q]) * dxtr_i + (nc[q] - ns[q]) * dytr_j);
+            acc = d + acc;
+            w = (k == kb) ? 0.0 : acc;   // adv_vbtiso(i,kmt,j) = 0 (:1521-1525); the running sum keeps going
+          }
+          if (gm) store_cyc(v, v.adv_vbtiso, lz, i, w);
+          store_cyc(v, v.wb, lz, i, vb[q] + w);
+        }
+      }
     }
   }
 }

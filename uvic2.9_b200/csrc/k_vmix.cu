@@ -56,30 +56,52 @@ __global__ void __launch_bounds__(128) k_vmix_factor(const DevView v) {
   const int kb = v.kmt[X2(i, j)];
 
   // ---- invtri factorisation (source/mom/invtri.F:55-100) ----
+  // The loads of a chunk of levels are issued together, ahead of the (serial, divide-bound) recurrence: with ~2 warps
+  // per SM on the 100x100 grid the kernel is otherwise one memory round trip per level.
   const double eps = 1.e-30;
+  const double *__restrict__ dcb = v.diff_cbt;
+  double *__restrict__ ta = v.tri_a, *__restrict__ te = v.tri_e, *__restrict__ tb = v.tri_bet;
+  const int c1 = (int)X3(i, 1, j), sk = v.imt;
   double bet = 0.0, cprev = 0.0;
-  for (int k = 1; k <= km; k++) {
-    int km1 = max(1, k - 1), kp1 = min(k + 1, km);
-    double tdt = v.c2dtts * v.dtxcel[k - 1];
-    double factu = v.dztur[k - 1] * tdt * v.aidif;
-    double factl = v.dztlr[k - 1] * tdt * v.aidif;
-    double mk = (kb >= k) ? 1.0 : 0.0, mkp1 = (kb >= kp1) ? 1.0 : 0.0;
-    double a = -v.diff_cbt[X3(i, km1, j)] * factu * mk;
-    double cc = -v.diff_cbt[X3(i, k, j)] * factl * mkp1;
-    if (k == 1) a = 0.0;
-    if (k == km) cc = 0.0;
-    double b = 1.0 - a - cc;
-    double e = 0.0;
-    if (k == 1) {
-      bet = mk / (b + eps);
-    } else {
-      e = cprev * bet;
-      bet = mk / (b - a * e + eps);
+  double dprev = dcb[c1];   // diff_cbt(i,max(1,k-1),j) of level 1
+  for (int k0 = 1; k0 <= km; k0 += 8) {
+    double dq[8], tq[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int k = min(k0 + q, km);
+      dq[q] = dcb[c1 + (k - 1) * sk];
+      tq[q] = v.dtxcel[k - 1];
     }
-    v.tri_a[X3(i, k, j)] = a;
-    v.tri_e[X3(i, k, j)] = e;
-    v.tri_bet[X3(i, k, j)] = bet;
-    cprev = cc;
+    asm volatile("" ::: "memory");   // keep the chunk's loads together
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int k = k0 + q;
+      if (k <= km) {
+        const int kp1 = min(k + 1, km);
+        double tdt = v.c2dtts * tq[q];
+        double factu = v.dztur[k - 1] * tdt * v.aidif;
+        double factl = v.dztlr[k - 1] * tdt * v.aidif;
+        double mk = (kb >= k) ? 1.0 : 0.0, mkp1 = (kb >= kp1) ? 1.0 : 0.0;
+        double a = -dprev * factu * mk;
+        double cc = -dq[q] * factl * mkp1;
+        if (k == 1) a = 0.0;
+        if (k == km) cc = 0.0;
+        double b = 1.0 - a - cc;
+        double e = 0.0;
+        if (k == 1) {
+          bet = mk / (b + eps);
+        } else {
+          e = cprev * bet;
+          bet = mk / (b - a * e + eps);
+        }
+        const int c = c1 + (k - 1) * sk;
+        ta[c] = a;
+        te[c] = e;
+        tb[c] = bet;
+        cprev = cc;
+        dprev = dq[q];
+      }
+    }
   }
 }
 
