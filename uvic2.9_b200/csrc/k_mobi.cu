@@ -245,13 +245,29 @@ __global__ void __launch_bounds__(128) k_mobi_light(const DevView v, double decl
   const double *__restrict__ diat = v.t_m1 + (long long)(ix[IX_TR + V_DIAT] - 1) * n3;
   const double *__restrict__ caco3 = v.t_m1 + (long long)(ix[IX_TR + V_CACO3] - 1) * n3;
   double phin = 0.0, caco3in = 0.0;
-  for (int k = 1; k <= kmx; k++) {
-    const long long c = X3(i, k, j);
-    const double dztk = v.dzt[k - 1];
-    swr = swr * m_exp(-P->kc * phin - P->kc_c * caco3in);
-    phin = fmax(phyt[c], TRCMIN) * dztk + fmax(diaz[c], TRCMIN) * dztk + fmax(diat[c], TRCMIN) * dztk;
-    caco3in = caco3in + caco3[c] * dztk;
-    v.mobi_pre[(long long)PR_GL * n3 + c] = swr * m_exp(P->ztt[k - 1] * rctheta);
+  // the tracer loads of 8 levels are issued together, ahead of the exp chain (one column per thread: latency bound)
+  const long long c1 = X3(i, 1, j);
+  const int sk = v.imt;
+  double *__restrict__ gl_out = v.mobi_pre + (long long)PR_GL * n3;
+  for (int k0 = 1; k0 <= kmx; k0 += 8) {
+    double p_[8], z_[8], d_[8], c_[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const long long c = c1 + (long long)(min(k0 + q, kmx) - 1) * sk;
+      p_[q] = phyt[c]; z_[q] = diaz[c]; d_[q] = diat[c]; c_[q] = caco3[c];
+    }
+    asm volatile("" ::: "memory");
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int k = k0 + q;
+      if (k <= kmx) {
+        const double dztk = v.dzt[k - 1];
+        swr = swr * m_exp(-P->kc * phin - P->kc_c * caco3in);
+        phin = fmax(p_[q], TRCMIN) * dztk + fmax(z_[q], TRCMIN) * dztk + fmax(d_[q], TRCMIN) * dztk;
+        caco3in = caco3in + c_[q] * dztk;
+        gl_out[c1 + (long long)(k - 1) * sk] = swr * m_exp(P->ztt[k - 1] * rctheta);
+      }
+    }
   }
 }
 

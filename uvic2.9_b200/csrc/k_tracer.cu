@@ -516,6 +516,10 @@ __device__ __forceinline__ double dens_f(const DevView &v, double tq, double sq,
 // other tracers can be mixed in parallel.  zsm is recorded, not recomputed, because it is
 // accumulated in the order the levels were discovered.
 __global__ void __launch_bounds__(128) k_convect_ts(const DevView v) {
+  // The T and S columns are fetched once, all levels in flight together, into thread-private shared-memory columns; the
+  // data-dependent search below then runs out of shared memory instead of paying a memory round trip per level it
+  // touches (one column per thread: the kernel is latency bound).  Columns that convected are written back.
+  extern __shared__ double cts[];   // [2][km][128]
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int ni = v.imt - 2;
   int nrow = v.jhi - v.jlo + 1;
@@ -523,12 +527,28 @@ __global__ void __launch_bounds__(128) k_convect_ts(const DevView v) {
   int i = (int)(idx % ni) + 2;
   int j = (int)(idx / ni) + v.jlo;
   const int kbo = v.kmt[X2(i, j)];
-  double *T = v.t_p1, *S = v.t_p1 + v.n3;
+  double *gT = v.t_p1, *gS = v.t_p1 + v.n3;
+  double *T = cts + threadIdx.x, *S = cts + (size_t)v.km * 128 + threadIdx.x;
   const double *dz = v.dztxcl;
   const int c1 = (int)X3(i, 1, j), sk = v.imt;
   const long long col = X2(i, j);
   const int maxreg = v.km / 2 + 1;
-#define TSV(a, k) a[c1 + ((k)-1) * sk]
+  for (int k0 = 1; k0 <= kbo; k0 += 8) {
+    double a_[8], b_[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int k = min(k0 + q, kbo);
+      a_[q] = gT[c1 + (k - 1) * sk];
+      b_[q] = gS[c1 + (k - 1) * sk];
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+      if (k0 + q <= kbo) {
+        T[(k0 + q - 1) * 128] = a_[q];
+        S[(k0 + q - 1) * 128] = b_[q];
+      }
+  }
+#define TSV(a, k) a[((k)-1) * 128]
   int nreg = 0;
   int kt = 1, kb = 2;
   while (kt < kbo) {
@@ -593,12 +613,18 @@ __global__ void __launch_bounds__(128) k_convect_ts(const DevView v) {
     kb = kt + 1;
   }
   v.conv_n[col] = nreg;
-  // cyclic boundary of T and S (09/mom/tracer.F:1199-1203)
-  if (i == 2 || i == v.imt - 1) {
-    int off = (i == 2) ? (v.imt - 2) : -(v.imt - 2);
-    for (int k = 1; k <= v.km; k++) {
-      T[c1 + (k - 1) * sk + off] = TSV(T, k);
-      S[c1 + (k - 1) * sk + off] = TSV(S, k);
+  if (nreg > 0) {
+    // write the adjusted column back, with its cyclic copy (09/mom/tracer.F:1199-1203; untouched columns keep the
+    // copy k_invtri made)
+    const int off = (i == 2) ? (v.imt - 2) : ((i == v.imt - 1) ? -(v.imt - 2) : 0);
+    for (int k = 1; k <= kbo; k++) {
+      const double tq = TSV(T, k), sq = TSV(S, k);
+      gT[c1 + (k - 1) * sk] = tq;
+      gS[c1 + (k - 1) * sk] = sq;
+      if (off) {
+        gT[c1 + (k - 1) * sk + off] = tq;
+        gS[c1 + (k - 1) * sk + off] = sq;
+      }
     }
   }
 #undef TSV
@@ -616,7 +642,7 @@ __global__ void __launch_bounds__(128) k_convect_tr(const DevView v, int nfirst)
   const long long col = X2(i, j);
   const int nreg = v.conv_n[col];
   const bool edge = (i == 2 || i == v.imt - 1);
-  if (nreg == 0 && !edge) return;
+  if (nreg == 0) return;   // untouched column: k_invtri already set its cyclic copy
   double *X = v.t_p1 + (long long)n0 * v.n3;
   const double *dz = v.dztxcl;
   const int c1 = (int)X3(i, 1, j), sk = v.imt;
@@ -716,7 +742,16 @@ void launch_tracer(uvic_b200_ctx *c, const uvic_b200_stepinfo *si) {
       k_invtri<<<cdiv(ncol, 32) * ntq, INV_T, shm, c->stream>>>(v, nbase, ng, ntq);
     }
     if (c->par.fullconvect) {
-      if (nbase == 0) KLAUNCH("k_convect_ts", k_convect_ts, cdiv(ncol, 128), 128, v);
+      if (nbase == 0) {
+        const size_t shm = (size_t)2 * v.km * 128 * sizeof(double);
+        static size_t shm_set = 0;
+        if (shm > 48 * 1024 && shm > shm_set) {
+          cudaFuncSetAttribute(k_convect_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+          shm_set = shm;
+        }
+        ProfScope ps_(c, "k_convect_ts");
+        k_convect_ts<<<cdiv(ncol, 128), 128, shm, c->stream>>>(v);
+      }
       const int nfirst = max(2, nbase), ntr = nbase + ng - nfirst;
       if (ntr > 0) {
         dim3 gt(cdiv(ncol, 128), ntr);
