@@ -49,6 +49,24 @@ struct Carb {
   double bt, st, ft, sit, pt, dic, ta;                // COMMON /species/
 };
 
+// x / y by the compiler's own IEEE divide sequence (reciprocal seed, two Newton steps, quotient, one remainder
+// correction: correctly rounded) without the exponent-range test and the out-of-line slow path behind it.  Valid while
+// x, y and x / y stay well inside the normal range, which holds for every operand of ta_iter ([H+] in [1e-10, 1e-6],
+// equilibrium constants 1e-14 .. 1e-1, their products down to ~1e-60).  ta_iter holds ~30 divides and runs ~10 times
+// per cell: this halves the loop body.
+__device__ __forceinline__ double qdiv(double x, double y) {
+  double r0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(y));
+  r0 = __hiloint2double(__double2hiint(r0), 1);
+  double e = fma(-y, r0, 1.0);
+  e = fma(e, e, e);
+  double r = fma(r0, e, r0);
+  e = fma(-y, r, 1.0);
+  r = fma(r, e, r);
+  const double q = x * r;
+  return fma(r, fma(-y, q, x), q);
+}
+
 // 09/common/co2calc.F:455-526
 __device__ __forceinline__ void ta_iter(const Carb &q, double x, double &fn, double &df) {
   double x2 = x * x;
@@ -56,21 +74,22 @@ __device__ __forceinline__ void ta_iter(const Carb &q, double x, double &fn, dou
   double k12 = q.k1 * q.k2;
   double k12p = q.k1p * q.k2p;
   double k123p = k12p * q.k3p;
-  double c = 1.0 + q.st / q.ks + q.ft / q.kf;
+  double c = 1.0 + qdiv(q.st, q.ks) + qdiv(q.ft, q.kf);
   double a = x3 + q.k1p * x2 + k12p * x + k123p;
   double a2 = a * a;
   double da = 3.0 * x2 + 2.0 * q.k1p * x + k12p;
   double b = x2 + q.k1 * x + k12;
   double b2 = b * b;
   double db = 2.0 * x + q.k1;
-  double xc = x / c;
-  double hs = 1.0 + q.ks / xc, hf = 1.0 + q.kf / xc;
-  double bb = 1.0 + x / q.kb, ss = 1.0 + x / q.ksi;
-  fn = q.k1 * x * q.dic / b + 2.0 * q.dic * k12 / b + q.bt / bb + q.kw / x + q.pt * k12p * x / a + 2.0 * q.pt * k123p / a + q.sit / ss -
-       x / c - q.st / hs - q.ft / hf - q.pt * x3 / a - q.ta;
-  df = ((q.k1 * q.dic * b) - q.k1 * x * q.dic * db) / b2 - 2.0 * q.dic * k12 * db / b2 - q.bt / q.kb / (bb * bb) - q.kw / x2 +
-       (q.pt * k12p * (a - x * da)) / a2 - 2.0 * q.pt * k123p * da / a2 - q.sit / q.ksi / (ss * ss) - 1.0 / c -
-       q.st * (1.0 / (hs * hs)) * (q.ks * c / x2) - q.ft * (1.0 / (hf * hf)) * (q.kf * c / x2) - q.pt * x2 * (3.0 * a - x * da) / a2;
+  double xc = qdiv(x, c);
+  double hs = 1.0 + qdiv(q.ks, xc), hf = 1.0 + qdiv(q.kf, xc);
+  double bb = 1.0 + qdiv(x, q.kb), ss = 1.0 + qdiv(x, q.ksi);
+  fn = qdiv(q.k1 * x * q.dic, b) + qdiv(2.0 * q.dic * k12, b) + qdiv(q.bt, bb) + qdiv(q.kw, x) + qdiv(q.pt * k12p * x, a) +
+       qdiv(2.0 * q.pt * k123p, a) + qdiv(q.sit, ss) - qdiv(x, c) - qdiv(q.st, hs) - qdiv(q.ft, hf) - qdiv(q.pt * x3, a) - q.ta;
+  df = qdiv((q.k1 * q.dic * b) - q.k1 * x * q.dic * db, b2) - qdiv(2.0 * q.dic * k12 * db, b2) - qdiv(qdiv(q.bt, q.kb), bb * bb) -
+       qdiv(q.kw, x2) + qdiv(q.pt * k12p * (a - x * da), a2) - qdiv(2.0 * q.pt * k123p * da, a2) -
+       qdiv(qdiv(q.sit, q.ksi), ss * ss) - qdiv(1.0, c) - q.st * qdiv(1.0, hs * hs) * qdiv(q.ks * c, x2) -
+       q.ft * qdiv(1.0, hf * hf) * qdiv(q.kf * c, x2) - qdiv(q.pt * x2 * (3.0 * a - x * da), a2);
 }
 
 // 09/common/co2calc.F:401-454 (Numerical Recipes rtsafe, error trapping removed).  The reference evaluates ta_iter at
