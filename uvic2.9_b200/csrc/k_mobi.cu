@@ -67,6 +67,8 @@ __device__ __forceinline__ double qdiv(double x, double y) {
   return fma(r, fma(-y, q, x), q);
 }
 
+#define QDIV(a, b) qdiv((a), (b))
+
 // 09/common/co2calc.F:455-526
 __device__ __forceinline__ void ta_iter(const Carb &q, double x, double &fn, double &df) {
   double x2 = x * x;
@@ -406,8 +408,8 @@ __device__ __forceinline__ void mobi_src(const MobiPar *__restrict__ P, int nbio
   const double diazptn = P->diazptn, dfr = P->dfr, pfr = P->pfr, dfrt = P->dfrt, geZ = P->geZ, rfeton = P->rfeton;
   const double bct = io.bct;
   // ratios from the raw inputs (:1781-1784)
-  double ptn_P = b[V_PHYT_PHOS] / b[V_PHYT];
-  double ptn_detr = b[V_DETR_PHOS] / b[V_DETR];
+  double ptn_P = QDIV(b[V_PHYT_PHOS], b[V_PHYT]);
+  double ptn_detr = QDIV(b[V_DETR_PHOS], b[V_DETR]);
   // flags from the raw inputs (:1814-1890), kept as a bit mask: bit m set <=> flag of state m is 1
   unsigned flm = 0u;
 #pragma unroll
@@ -440,42 +442,42 @@ __device__ __forceinline__ void mobi_src(const MobiPar *__restrict__ P, int nbio
     // half-saturation constants and maximum rates (:2150-2166)
     p1 = fmin(biophyt, P->pmax);
     p2 = fmax(0.0, biophyt - P->pmax);
-    double k1n = (P->knmin * p1 + P->knmax * p2) / (p1 + p2);
+    double k1n = QDIV((P->knmin * p1 + P->knmax * p2), (p1 + p2));
     double k1p_P = k1n * ptn_P;
-    kfevar = (P->kfemin * p1 + P->kfemax * p2) / (p1 + p2);
-    deffe = biodfe / (kfevar + biodfe);
+    kfevar = QDIV((P->kfemin * p1 + P->kfemax * p2), (p1 + p2));
+    deffe = QDIV(biodfe, (kfevar + biodfe));
     double jmax = P->abio_P * bct * deffe;
     p1 = fmin(biodiat, P->pmax_Diat);
     p2 = fmax(0.0, biodiat - P->pmax_Diat);
-    kfevar_Diat = (P->kfemin_Diat * p1 + P->kfemax_Diat * p2) / (p1 + p2);
-    double k1n_Diat = (P->knmin_Diat * p1 + P->knmax_Diat * p2) / (p1 + p2);
+    kfevar_Diat = QDIV((P->kfemin_Diat * p1 + P->kfemax_Diat * p2), (p1 + p2));
+    double k1n_Diat = QDIV((P->knmin_Diat * p1 + P->knmax_Diat * p2), (p1 + p2));
     double k1p_Diat = k1n_Diat * redptn;
-    deffe_Diat = biodfe / (kfevar_Diat + biodfe);
+    deffe_Diat = QDIV(biodfe, (kfevar_Diat + biodfe));
     double jmax_Diat = P->abiodiat * bct * deffe_Diat;
-    deffe_D = biodfe / (P->kfe_D + biodfe);
+    deffe_D = QDIV(biodfe, (P->kfe_D + biodfe));
     double jmax_D = fmax(0., P->abio_P * (bct - P->dbct_D) * deffe_D) * P->jdiar;
     // growth rates (:2168-2206)
-    double limP_dop = P->hdop * biodop / (k1p_P + biodop);
-    double limP_po4 = biopo4 / (k1p_P + biopo4);
+    double limP_dop = QDIV(P->hdop * biodop, (k1p_P + biodop));
+    double limP_po4 = QDIV(biopo4, (k1p_P + biopo4));
     double dopupt_flag = 0.5 + fsign(0.5, limP_dop - limP_po4);
     double limP = limP_dop * dopupt_flag + limP_po4 * (1. - dopupt_flag);
     double u_P = fmin(avej, jmax * limP);
-    double limSi = biosil / (5.e-3 + biosil);  // k1si = 5.e-3 (:2181)
-    limP_dop = P->hdop * biodop / (k1p_Diat + biodop);
-    limP_po4 = biopo4 / (k1p_Diat + biopo4);
+    double limSi = QDIV(biosil, (5.e-3 + biosil));  // k1si = 5.e-3 (:2181)
+    limP_dop = QDIV(P->hdop * biodop, (k1p_Diat + biodop));
+    limP_po4 = QDIV(biopo4, (k1p_Diat + biopo4));
     double dopupt_Diat_flag = 0.5 + fsign(0.5, limP_dop - limP_po4);
     double limP_Diat = limP_dop * dopupt_Diat_flag + limP_po4 * (1. - dopupt_Diat_flag);
     double u_Diat = fmin(avej_Diat, jmax_Diat * limSi);
     u_Diat = fmin(u_Diat, jmax_Diat * limP_Diat);
-    u_P = fmin(u_P, jmax * biono3 / (k1n + biono3));
-    u_Diat = fmin(u_Diat, jmax_Diat * biono3 / (k1n_Diat + biono3));
+    u_P = fmin(u_P, QDIV(jmax * biono3, (k1n + biono3)));
+    u_Diat = fmin(u_Diat, QDIV(jmax_Diat * biono3, (k1n_Diat + biono3)));
     double u_D = fmin(avej_D, jmax_D * limP);
     double dopupt_D_flag = dopupt_flag;
     // grazing (:2208-2245)
     double thetaZ = P->zprefP * biophyt + P->zprefDet * biodetr + P->zprefZ * biozoop + P->zprefDiaz * biodiaz + P->kzoo +
                     P->zprefDiat * biodiat;
-    double ing_P = P->zprefP / thetaZ, ing_Det = P->zprefDet / thetaZ, ing_Z = P->zprefZ / thetaZ;
-    double ing_D = P->zprefDiaz / thetaZ, ing_Diat = P->zprefDiat / thetaZ;
+    double ing_P = QDIV(P->zprefP, thetaZ), ing_Det = QDIV(P->zprefDet, thetaZ), ing_Z = QDIV(P->zprefZ, thetaZ);
+    double ing_D = QDIV(P->zprefDiaz, thetaZ), ing_Diat = QDIV(P->zprefDiat, thetaZ);
     double npp = u_P * biophyt;
     double npp_Diat = u_Diat * biodiat;
     double dopupt = npp * dopupt_flag;
@@ -506,9 +508,9 @@ __device__ __forceinline__ void mobi_src(const MobiPar *__restrict__ P, int nbio
     double expoopl = io.wwo * bioopl;
     double remife = io.nud * bct * biodetrfe;
     // iron scavenging (:2262-2283)
-    double ligand = fmax(aou8 / 66. + pow(biodon, 0.8) / 4.8, 0.5) / 1000.;
+    double ligand = QDIV(fmax(QDIV(aou8, 66.) + QDIV(pow(biodon, 0.8), 4.8), 0.5), 1000.);
     double fepa = (1.0 + P->kfeleq * (ligand - biodfe)) * o2flag;
-    double feprime = ((-fepa + sqrt(fepa * fepa + 4.0 * P->kfeleq * biodfe)) / (2.0 * P->kfeleq)) * o2flag;
+    double feprime = (QDIV((-fepa + sqrt(fepa * fepa + 4.0 * P->kfeleq * biodfe)), (2.0 * P->kfeleq))) * o2flag;
     double feorgads = (P->kfeorg * (pow(((biodetr * fl(V_DETR)) * P->mc * redctn), 0.58)) * feprime) * o2flag;
     double fecol = P->kfecol * (feprime * feprime) * o2flag;
     double expofe = io.wwd * biodetrfe;
@@ -551,43 +553,43 @@ __device__ __forceinline__ void mobi_src(const MobiPar *__restrict__ P, int nbio
     double sf_Det_phos = (graz_Det * ptn_detr - dig_Det * redptn);
     const double nr_excr_P = 0.0, nr_excr_detr = 0.0;
     double sf_phos = sf_P_phos + sf_Z * redptn + sf_Det_phos + sf_Diat * redptn;
-    double dig_D = gamma1 * graz_D * (redntp / diazntp);
+    double dig_D = gamma1 * graz_D * (QDIV(redntp, diazntp));
     dig = dig + dig_D;
-    excr = excr + gamma1 * (1 - geZ) * graz_D * (redntp / diazntp);
-    double nr_excr_D = gamma1 * graz_D * (1 - (redntp / diazntp)) + (1 - gamma1) * graz_D * (1 - (redntp / diazntp));
-    double sf_D = (1 - gamma1) * graz_D * (redntp / diazntp);
+    excr = excr + gamma1 * (1 - geZ) * graz_D * (QDIV(redntp, diazntp));
+    double nr_excr_D = gamma1 * graz_D * (1 - (QDIV(redntp, diazntp))) + (1 - gamma1) * graz_D * (1 - (QDIV(redntp, diazntp)));
+    double sf_D = (1 - gamma1) * graz_D * (QDIV(redntp, diazntp));
     sf = sf + sf_D;
     sf_phos = sf_phos + sf_D * redptn;
     // isotope fractionation factors (:2441-2530)
-    double uno3 = fmax(fmin(npp * dtbio / biono3, 0.999), TRCMIN);
-    double rno3 = fmax(fmin(b[V_DIN15] / (biono3 - b[V_DIN15]), 2 * RN15STD), RN15STD / 2.);
-    double bassim = rno3 + P->eps_assim * (1 - uno3) / uno3 * log(1 - uno3) * rno3 / 1000.;
-    double fcassim = bassim / (1 + bassim);
-    double udon = fmax(fmin(recy_don * dtbio / biodon, 0.999), TRCMIN);
-    double rdon = fmax(fmin(b[V_DON15] / (biodon - b[V_DON15]), 2 * RN15STD), RN15STD / 2.);
-    double brecy = rdon + P->eps_recy * (1 - udon) / udon * log(1 - udon) * rdon / 1000.;
-    double fcrecy = brecy / (1 + brecy);
-    double rzoop = fmax(fmin(b[V_ZOOPN15] / (biozoop - b[V_ZOOPN15]), 2. * RN15STD), RN15STD / 2.);
-    double bexcr = rzoop - P->eps_excr * rzoop / 1000.;
-    double fcexcr = bexcr / (1 + bexcr);
-    double bnfix = RN15STD - P->eps_nfix * RN15STD / 1000.;
-    double fcnfix = bnfix / (1 + bnfix);
-    double rtphytn15 = CL15(b[V_PHYTN15] / biophyt);
-    double rtdiatn15 = CL15(b[V_DIATN15] / biodiat);
-    double rtzoopn15 = CL15(b[V_ZOOPN15] / biozoop);
-    double rtdetrn15 = CL15(b[V_DETRN15] / biodetr);
-    double rtdiazn15 = CL15(b[V_DIAZN15] / biodiaz);
-    double rdic13 = fmax(fmin(b[V_DIC13] / (biodic - b[V_DIC13]), 2. * RC13STD), 0.5 * RC13STD);
+    double uno3 = fmax(fmin(QDIV(npp * dtbio, biono3), 0.999), TRCMIN);
+    double rno3 = fmax(fmin(QDIV(b[V_DIN15], (biono3 - b[V_DIN15])), 2 * RN15STD), RN15STD / 2.);
+    double bassim = rno3 + QDIV(QDIV(P->eps_assim * (1 - uno3), uno3) * log(1 - uno3) * rno3, 1000.);
+    double fcassim = QDIV(bassim, (1 + bassim));
+    double udon = fmax(fmin(QDIV(recy_don * dtbio, biodon), 0.999), TRCMIN);
+    double rdon = fmax(fmin(QDIV(b[V_DON15], (biodon - b[V_DON15])), 2 * RN15STD), RN15STD / 2.);
+    double brecy = rdon + QDIV(QDIV(P->eps_recy * (1 - udon), udon) * log(1 - udon) * rdon, 1000.);
+    double fcrecy = QDIV(brecy, (1 + brecy));
+    double rzoop = fmax(fmin(QDIV(b[V_ZOOPN15], (biozoop - b[V_ZOOPN15])), 2. * RN15STD), RN15STD / 2.);
+    double bexcr = rzoop - QDIV(P->eps_excr * rzoop, 1000.);
+    double fcexcr = QDIV(bexcr, (1 + bexcr));
+    double bnfix = RN15STD - QDIV(P->eps_nfix * RN15STD, 1000.);
+    double fcnfix = QDIV(bnfix, (1 + bnfix));
+    double rtphytn15 = CL15(QDIV(b[V_PHYTN15], biophyt));
+    double rtdiatn15 = CL15(QDIV(b[V_DIATN15], biodiat));
+    double rtzoopn15 = CL15(QDIV(b[V_ZOOPN15], biozoop));
+    double rtdetrn15 = CL15(QDIV(b[V_DETRN15], biodetr));
+    double rtdiazn15 = CL15(QDIV(b[V_DIAZN15], biodiaz));
+    double rdic13 = fmax(fmin(QDIV(b[V_DIC13], (biodic - b[V_DIC13])), 2. * RC13STD), 0.5 * RC13STD);
     double bc13npp = io.ac13b * rdic13;
-    double fcnpp = bc13npp / (1 + bc13npp);
-    double rtdic13 = CL13(b[V_DIC13] / biodic);
-    double rtphytc13 = CL13(b[V_PHYTC13] / (biophyt * redctn));
-    double rtdiatc13 = CL13(b[V_DIATC13] / (biodiat * redctn));
-    double rtcaco3c13 = CL13(b[V_CACO3C13] / biocaco3);
-    double rtzoopc13 = CL13(b[V_ZOOPC13] / (biozoop * redctn));
-    double rtdetrc13 = CL13(b[V_DETRC13] / (biodetr * redctn));
-    double rtdoc13 = CL13(b[V_DOC13] / (biodon * redctn));
-    double rtdiazc13 = CL13(b[V_DIAZC13] / (biodiaz * redctn));
+    double fcnpp = QDIV(bc13npp, (1 + bc13npp));
+    double rtdic13 = CL13(QDIV(b[V_DIC13], biodic));
+    double rtphytc13 = CL13(QDIV(b[V_PHYTC13], (biophyt * redctn)));
+    double rtdiatc13 = CL13(QDIV(b[V_DIATC13], (biodiat * redctn)));
+    double rtcaco3c13 = CL13(QDIV(b[V_CACO3C13], biocaco3));
+    double rtzoopc13 = CL13(QDIV(b[V_ZOOPC13], (biozoop * redctn)));
+    double rtdetrc13 = CL13(QDIV(b[V_DETRC13], (biodetr * redctn)));
+    double rtdoc13 = CL13(QDIV(b[V_DOC13], (biodon * redctn)));
+    double rtdiazc13 = CL13(QDIV(b[V_DIAZC13], (biodiaz * redctn)));
     // CaCO3 and opal production (:2532-2548)
     double calpro = ((sf_Z + morz) * io.capr + (sf_P + morp) * io.capr) * redctn * 1.e3;
     double sipr0 = (-0.46204044117647 * tanh(6.9 * biodfe * 1.e3 + -3.673092) + 1.60266544117647);
@@ -596,7 +598,7 @@ __device__ __forceinline__ void mobi_src(const MobiPar *__restrict__ P, int nbio
     expoopl = expoopl * fl(V_OPL);
     double GM15ptc = 0.0060 + 0.0069 * biopo4;
     double GM15ptn = GM15ptc * redctn * 1.e3;
-    const double rnd = redntp / diazntp;
+    const double rnd = QDIV(redntp, diazntp);
 
     // prognostic equations, forward Euler (:2552-2760)
     b[V_PO4] = biopo4 + dtbio * (dopupt * ptn_P - GM15ptn * npp + (1. - dfrt) * morpt * ptn_P + (1. - pfr) * remi * ptn_detr +
@@ -619,8 +621,8 @@ __device__ __forceinline__ void mobi_src(const MobiPar *__restrict__ P, int nbio
     b[V_DIAZ] = biodiaz + dtbio * (npp_D - morp_D - morpt_D - graz_D);
     const double ptn_P_old = ptn_P, ptn_detr_old = ptn_detr;
     (void)ptn_P_old; (void)ptn_detr_old;
-    ptn_P = b[V_PHYT_PHOS] / b[V_PHYT];
-    ptn_detr = b[V_DETR_PHOS] / b[V_DETR];
+    ptn_P = QDIV(b[V_PHYT_PHOS], b[V_PHYT]);
+    ptn_detr = QDIV(b[V_DETR_PHOS], b[V_DETR]);
     b[V_CACO3] = biocaco3 + dtbio * (calpro - dissl - expocaco3 + io.impocaco3);
     b[V_DIAT] = biodiat + dtbio * (npp_Diat - morp_Diat - graz_Diat - morpt_Diat);
     b[V_SIL] = biosil + dtbio * (opldis - oplpro);
@@ -775,20 +777,19 @@ __global__ void __launch_bounds__(32) k_mobi_column(const DevView v, int mi, int
     sg_bdeni = sg_bdeni * (0.5 + lno3) * no3flag * din15flag;
     const double bdeni = sg_bdeni;
     b[V_NO3] = b[V_NO3] + sgb * expo - sg_bdeni;
-    double rno3 = fmax(tdin15, TRCMIN * RN15STD / (1 + RN15STD)) / fmax(tno3 - tdin15, TRCMIN * RN15STD / (1 + RN15STD));
+    double rno3 = QDIV(fmax(tdin15, TRCMIN * RN15STD / (1 + RN15STD)), fmax(tno3 - tdin15, TRCMIN * RN15STD / (1 + RN15STD)));
     rno3 = fmin(rno3, 2. * RN15STD);
     rno3 = fmax(rno3, RN15STD / 2.);
     double eps_bdeni = v.mobi_epsbd[k - 1];
-    double bbdeni = rno3 - eps_bdeni * rno3 / 1000.;
-    b[V_DIN15] = b[V_DIN15] + rn15expo * sgb * expo - bbdeni / (1 + bbdeni) * sg_bdeni;
+    double bbdeni = rno3 - QDIV(eps_bdeni * rno3, 1000.);
+    b[V_DIN15] = b[V_DIN15] + rn15expo * sgb * expo - QDIV(bbdeni, (1 + bbdeni)) * sg_bdeni;
     // sediment carbon oxidation (Flogel 2011 / Somes 2021) and iron release (Dale 2015) (:1076-1110)
     double coxdepth = fmin(fmax(v.zt[k - 1], 50000.), 150000.);
     double oblinc = -1.26e-6 * coxdepth + 0.203;
     double obexpc = -6.e-7 * coxdepth + 1.14;
-    double nburial = (oblinc * pow((expo * sgb * dztk / 100 * 86400. * 365. * redctn * 1000.), obexpc)) /
-                     (86400. * 365. * dztk / 100 * redctn * 1000.);
+    double nburial = QDIV((oblinc * pow((QDIV(expo * sgb * dztk, 100) * 86400. * 365. * redctn * 1000.), obexpc)), (QDIV(86400. * 365. * dztk, 100) * redctn * 1000.));
     double coxsed = expo * sgb - nburial;
-    double fesed = 85. * tanh(coxsed * redctn * 1000 * dztk / 100 * 86400. / o2_in) / (dztk / 100 * 86400 * 1000);
+    double fesed = QDIV(85. * tanh(QDIV(QDIV(coxsed * redctn * 1000 * dztk, 100) * 86400., o2_in)), (QDIV(dztk, 100) * 86400 * 1000));
     b[V_DFE] = b[V_DFE] + fesed;
     b[V_PO4] = b[V_PO4] + sgb * expo_phos;
     b[V_DIC] = b[V_DIC] + sgb * expo * redctn;
@@ -798,10 +799,10 @@ __global__ void __launch_bounds__(32) k_mobi_column(const DevView v, int mi, int
     expo_phos = expo_phos - sgb * expo_phos;
     const double dic_npzd_sms = b[V_DIC];
     // isotope ratios of DIC and CaCO3 for the calcite terms (:1258-1276)
-    double rtdic13 = fmax(clip[V_DIC13], TRCMIN * RC13STD / (1 + RC13STD)) / fmax(dic_in, TRCMIN);
+    double rtdic13 = QDIV(fmax(clip[V_DIC13], TRCMIN * RC13STD / (1 + RC13STD)), fmax(dic_in, TRCMIN));
     rtdic13 = fmin(rtdic13, 2. * RC13STD / (1 + RC13STD));
     rtdic13 = fmax(rtdic13, 0.5 * RC13STD / (1 + RC13STD));
-    double rtcaco3c13 = fmax(clip[V_CACO3C13], TRCMIN * RC13STD / (1 + RC13STD)) / fmax(clip[V_CACO3], TRCMIN);
+    double rtcaco3c13 = QDIV(fmax(clip[V_CACO3C13], TRCMIN * RC13STD / (1 + RC13STD)), fmax(clip[V_CACO3], TRCMIN));
     rtcaco3c13 = fmin(rtcaco3c13, 2. * RC13STD / (1 + RC13STD));
     rtcaco3c13 = fmax(rtcaco3c13, 0.5 * RC13STD / (1 + RC13STD));
     double src_alk = -b[V_DIC] * P->redntc * 1.e-3;
@@ -821,11 +822,11 @@ __global__ void __launch_bounds__(32) k_mobi_column(const DevView v, int mi, int
     double wcdeni = 800. * no3flag * so2 * (1.0 - fo2) * (0.5 + lno3) * din15flag;
     wcdeni = fmax(wcdeni, 0.);
     b[V_NO3] = b[V_NO3] - wcdeni;
-    double uno3 = wcdeni * v.c2dtts / tno3;
+    double uno3 = QDIV(wcdeni * v.c2dtts, tno3);
     uno3 = fmin(uno3, 0.999);
     uno3 = fmax(uno3, TRCMIN);
-    double bwcdeni = rno3 + P->eps_wcdeni * (1 - uno3) / uno3 * log(1 - uno3) * rno3 / 1000.;
-    b[V_DIN15] = b[V_DIN15] - (bwcdeni / (1 + bwcdeni)) * wcdeni;
+    double bwcdeni = rno3 + QDIV(QDIV(P->eps_wcdeni * (1 - uno3), uno3) * log(1 - uno3) * rno3, 1000.);
+    b[V_DIN15] = b[V_DIN15] - (QDIV(bwcdeni, (1 + bwcdeni))) * wcdeni;
     src_alk = src_alk + wcdeni * 1.e-3;
     src_alk = src_alk + bdeni * 1.e-3;
     src_alk = src_alk - nfix * rnbio * 1.e-3;
@@ -843,7 +844,7 @@ __global__ void __launch_bounds__(32) k_mobi_column(const DevView v, int mi, int
       b[V_SIL] = b[V_SIL] + rexpoopl;
     }
     // dust (surface) and hydrothermal iron (tracer.F:536-545)
-    if (k == 1) b[V_DFE] = b[V_DFE] + v.fe_atmdep[X2(i, j) + (long long)(mi - 1) * v.n2] * 1000 / (v.dzt[0] / 100.);
+    if (k == 1) b[V_DFE] = b[V_DFE] + QDIV(v.fe_atmdep[X2(i, j) + (long long)(mi - 1) * v.n2] * 1000, (QDIV(v.dzt[0], 100.)));
     b[V_DFE] = b[V_DFE] + v.fe_hydr[XIJK(i, j, k)];
 
     // scatter into src (mobi.F:1149-1204)
@@ -923,7 +924,7 @@ __global__ void __launch_bounds__(32 * WS_WARPS * G) k_mobi_ws(const DevView v, 
   const long long n3 = v.n3;
   const double gamma1 = P->gamma1, redptn = P->redptn, redctn = P->redctn, redntp = P->redntp, diazntp = P->diazntp;
   const double diazptn = P->diazptn, dfr = P->dfr, pfr = P->pfr, dfrt = P->dfrt, geZ = P->geZ, rfeton = P->rfeton;
-  const double rnd = redntp / diazntp;
+  const double rnd = QDIV(redntp, diazntp);
 #define SB(m) sm.B[m][lane]
 #define SF(m) sm.F[m][lane]
 #define SC(m) sm.C[m][lane]
@@ -966,10 +967,10 @@ __global__ void __launch_bounds__(32 * WS_WARPS * G) k_mobi_ws(const DevView v, 
         SC(m) = cl;
       }
       if (w == 0) {   // states 0..7 include PHYT, PHYT_PHOS, DETR, DETR_PHOS
-        const double ptn_P = raw[V_PHYT_PHOS] / raw[V_PHYT];
+        const double ptn_P = QDIV(raw[V_PHYT_PHOS], raw[V_PHYT]);
         SL(L_ptn_P0) = ptn_P;
         SL(L_sf_P_phosflag) = 0.5 + fsign(0.5, ptn_P - gamma1 * redptn);
-        const double ptn_detr = raw[V_DETR_PHOS] / raw[V_DETR];
+        const double ptn_detr = QDIV(raw[V_DETR_PHOS], raw[V_DETR]);
         SL(L_ptn_detr0) = ptn_detr;
         SL(L_sf_detr_phosflag) = 0.5 + fsign(0.5, ptn_detr - gamma1 * redptn);
       }
@@ -1011,37 +1012,37 @@ __global__ void __launch_bounds__(32 * WS_WARPS * G) k_mobi_ws(const DevView v, 
           // phytoplankton growth (:2150-2206), NO3 assimilation fractionation (:2441-2452)
           const double biophyt = SB(V_PHYT), biodfe = SB(V_DFE), biodop = SB(V_DOP), biopo4 = SB(V_PO4), biono3 = SB(V_NO3);
           double p1 = fmin(biophyt, P->pmax), p2 = fmax(0.0, biophyt - P->pmax);
-          double k1n = (P->knmin * p1 + P->knmax * p2) / (p1 + p2);
+          double k1n = QDIV((P->knmin * p1 + P->knmax * p2), (p1 + p2));
           double k1p_P = k1n * ptn_P;
-          double kfevar = (P->kfemin * p1 + P->kfemax * p2) / (p1 + p2);
-          double deffe = biodfe / (kfevar + biodfe);
+          double kfevar = QDIV((P->kfemin * p1 + P->kfemax * p2), (p1 + p2));
+          double deffe = QDIV(biodfe, (kfevar + biodfe));
           double jmax = P->abio_P * bct * deffe;
-          double limP_dop = P->hdop * biodop / (k1p_P + biodop);
-          double limP_po4 = biopo4 / (k1p_P + biopo4);
+          double limP_dop = QDIV(P->hdop * biodop, (k1p_P + biodop));
+          double limP_po4 = QDIV(biopo4, (k1p_P + biopo4));
           double dopupt_flag = 0.5 + fsign(0.5, limP_dop - limP_po4);
           double limP = limP_dop * dopupt_flag + limP_po4 * (1. - dopupt_flag);
           double u_P = fmin(lc0, jmax * limP);
-          u_P = fmin(u_P, jmax * biono3 / (k1n + biono3));
+          u_P = fmin(u_P, QDIV(jmax * biono3, (k1n + biono3)));
           double npp = u_P * biophyt;
           SR(dopupt) = npp * dopupt_flag;
           npp = npp * SF(V_NO3) * (dopupt_flag * SF(V_DOP) + (1. - dopupt_flag) * SF(V_PO4)) * SF(V_DIN15);
           SR(npp) = npp;
-          double uno3 = fmax(fmin(npp * dtbio / biono3, 0.999), TRCMIN);
-          double rno3 = fmax(fmin(SB(V_DIN15) / (biono3 - SB(V_DIN15)), 2 * RN15STD), RN15STD / 2.);
-          double bassim = rno3 + P->eps_assim * (1 - uno3) / uno3 * log(1 - uno3) * rno3 / 1000.;
-          SR(fcassim) = bassim / (1 + bassim);
+          double uno3 = fmax(fmin(QDIV(npp * dtbio, biono3), 0.999), TRCMIN);
+          double rno3 = fmax(fmin(QDIV(SB(V_DIN15), (biono3 - SB(V_DIN15))), 2 * RN15STD), RN15STD / 2.);
+          double bassim = rno3 + QDIV(QDIV(P->eps_assim * (1 - uno3), uno3) * log(1 - uno3) * rno3, 1000.);
+          SR(fcassim) = QDIV(bassim, (1 + bassim));
         }
         {
           // organic iron adsorption exponent (:2278), excretion / N2-fixation fractionation (:2466-2478), calcite 13C ratios
           const double biozoop = SB(V_ZOOP);
           SR(pw58) = pow(((SB(V_DETR) * SF(V_DETR)) * P->mc * redctn), 0.58);
-          double rzoop = fmax(fmin(SB(V_ZOOPN15) / (biozoop - SB(V_ZOOPN15)), 2. * RN15STD), RN15STD / 2.);
-          double bexcr = rzoop - P->eps_excr * rzoop / 1000.;
-          SR(fcexcr) = bexcr / (1 + bexcr);
-          double bnfix = RN15STD - P->eps_nfix * RN15STD / 1000.;
-          SR(fcnfix) = bnfix / (1 + bnfix);
-          SR(rtdic13) = CL13(SB(V_DIC13) / SB(V_DIC));
-          SR(rtcaco3c13) = CL13(SB(V_CACO3C13) / SB(V_CACO3));
+          double rzoop = fmax(fmin(QDIV(SB(V_ZOOPN15), (biozoop - SB(V_ZOOPN15))), 2. * RN15STD), RN15STD / 2.);
+          double bexcr = rzoop - QDIV(P->eps_excr * rzoop, 1000.);
+          SR(fcexcr) = QDIV(bexcr, (1 + bexcr));
+          double bnfix = RN15STD - QDIV(P->eps_nfix * RN15STD, 1000.);
+          SR(fcnfix) = QDIV(bnfix, (1 + bnfix));
+          SR(rtdic13) = CL13(QDIV(SB(V_DIC13), SB(V_DIC)));
+          SR(rtcaco3c13) = CL13(QDIV(SB(V_CACO3C13), SB(V_CACO3)));
           double GM15ptc = 0.0060 + 0.0069 * SB(V_PO4);
           SR(GM15ptn) = GM15ptc * redctn * 1.e3;
         }
@@ -1061,7 +1062,7 @@ __global__ void __launch_bounds__(32 * WS_WARPS * G) k_mobi_ws(const DevView v, 
           const double nphos = biophyt_phos + dtbio * (npp * GM15ptn - morp * ptn_P - graz * ptn_P - morpt * ptn_P);
           UPD(V_PHYT, nphyt);
           UPD(V_PHYT_PHOS, nphos);
-          SL(L_ptn_P0 + (par ^ 1)) = nphos / nphyt;
+          SL(L_ptn_P0 + (par ^ 1)) = QDIV(nphos, nphyt);
         }
         {
           const double rtphytn15 = SR(rtphytn15), rtdiatn15 = SR(rtdiatn15), rtdiazn15 = SR(rtdiazn15), rtdetrn15 = SR(rtdetrn15);
@@ -1087,19 +1088,19 @@ __global__ void __launch_bounds__(32 * WS_WARPS * G) k_mobi_ws(const DevView v, 
           const double biodiat = SB(V_DIAT), biodfe = SB(V_DFE), biosil = SB(V_SIL), biodop = SB(V_DOP), biopo4 = SB(V_PO4);
           const double biono3 = SB(V_NO3);
           double p1 = fmin(biodiat, P->pmax_Diat), p2 = fmax(0.0, biodiat - P->pmax_Diat);
-          double kfevar_Diat = (P->kfemin_Diat * p1 + P->kfemax_Diat * p2) / (p1 + p2);
-          double k1n_Diat = (P->knmin_Diat * p1 + P->knmax_Diat * p2) / (p1 + p2);
+          double kfevar_Diat = QDIV((P->kfemin_Diat * p1 + P->kfemax_Diat * p2), (p1 + p2));
+          double k1n_Diat = QDIV((P->knmin_Diat * p1 + P->knmax_Diat * p2), (p1 + p2));
           double k1p_Diat = k1n_Diat * redptn;
-          double deffe_Diat = biodfe / (kfevar_Diat + biodfe);
+          double deffe_Diat = QDIV(biodfe, (kfevar_Diat + biodfe));
           double jmax_Diat = P->abiodiat * bct * deffe_Diat;
-          double limSi = biosil / (5.e-3 + biosil);  // k1si = 5.e-3 (:2181)
-          double limP_dop = P->hdop * biodop / (k1p_Diat + biodop);
-          double limP_po4 = biopo4 / (k1p_Diat + biopo4);
+          double limSi = QDIV(biosil, (5.e-3 + biosil));  // k1si = 5.e-3 (:2181)
+          double limP_dop = QDIV(P->hdop * biodop, (k1p_Diat + biodop));
+          double limP_po4 = QDIV(biopo4, (k1p_Diat + biopo4));
           double dopupt_Diat_flag = 0.5 + fsign(0.5, limP_dop - limP_po4);
           double limP_Diat = limP_dop * dopupt_Diat_flag + limP_po4 * (1. - dopupt_Diat_flag);
           double u_Diat = fmin(lc0, jmax_Diat * limSi);
           u_Diat = fmin(u_Diat, jmax_Diat * limP_Diat);
-          u_Diat = fmin(u_Diat, jmax_Diat * biono3 / (k1n_Diat + biono3));
+          u_Diat = fmin(u_Diat, QDIV(jmax_Diat * biono3, (k1n_Diat + biono3)));
           double npp_Diat = u_Diat * biodiat;
           SR(dopupt_Diat) = npp_Diat * dopupt_Diat_flag;
           SR(npp_Diat) = npp_Diat * SF(V_NO3) * (dopupt_Diat_flag * SF(V_DOP) + (1. - dopupt_Diat_flag) * SF(V_PO4)) * SF(V_DIN15);
@@ -1111,16 +1112,16 @@ __global__ void __launch_bounds__(32 * WS_WARPS * G) k_mobi_ws(const DevView v, 
           double recy_don = P->nudon0 * bct * biodon;
           recy_don = recy_don * SF(V_DON) * SF(V_DON15);
           SR(recy_don) = recy_don;
-          double udon = fmax(fmin(recy_don * dtbio / biodon, 0.999), TRCMIN);
-          double rdon = fmax(fmin(SB(V_DON15) / (biodon - SB(V_DON15)), 2 * RN15STD), RN15STD / 2.);
-          double brecy = rdon + P->eps_recy * (1 - udon) / udon * log(1 - udon) * rdon / 1000.;
-          SR(fcrecy) = brecy / (1 + brecy);
-          SR(rtphytn15) = CL15(SB(V_PHYTN15) / SB(V_PHYT));
-          SR(rtdiatn15) = CL15(SB(V_DIATN15) / SB(V_DIAT));
-          SR(rtzoopn15) = CL15(SB(V_ZOOPN15) / SB(V_ZOOP));
-          const double rtdetrn15 = CL15(SB(V_DETRN15) / SB(V_DETR));
+          double udon = fmax(fmin(QDIV(recy_don * dtbio, biodon), 0.999), TRCMIN);
+          double rdon = fmax(fmin(QDIV(SB(V_DON15), (biodon - SB(V_DON15))), 2 * RN15STD), RN15STD / 2.);
+          double brecy = rdon + QDIV(QDIV(P->eps_recy * (1 - udon), udon) * log(1 - udon) * rdon, 1000.);
+          SR(fcrecy) = QDIV(brecy, (1 + brecy));
+          SR(rtphytn15) = CL15(QDIV(SB(V_PHYTN15), SB(V_PHYT)));
+          SR(rtdiatn15) = CL15(QDIV(SB(V_DIATN15), SB(V_DIAT)));
+          SR(rtzoopn15) = CL15(QDIV(SB(V_ZOOPN15), SB(V_ZOOP)));
+          const double rtdetrn15 = CL15(QDIV(SB(V_DETRN15), SB(V_DETR)));
           SR(rtdetrn15) = rtdetrn15;
-          SR(rtdiazn15) = CL15(SB(V_DIAZN15) / SB(V_DIAZ));
+          SR(rtdiazn15) = CL15(QDIV(SB(V_DIAZN15), SB(V_DIAZ)));
           acc0 = acc0 + rtdetrn15;   // rn15expoout
         }
         WS_BAR();
@@ -1135,7 +1136,7 @@ __global__ void __launch_bounds__(32 * WS_WARPS * G) k_mobi_ws(const DevView v, 
                                                            (1. - dfr) * morp_Diat * redptn);
           UPD(V_DETR, ndetr);
           UPD(V_DETR_PHOS, ndphos);
-          SL(L_ptn_detr0 + (par ^ 1)) = ndphos / ndetr;
+          SL(L_ptn_detr0 + (par ^ 1)) = QDIV(ndphos, ndetr);
           UPD(V_ZOOP, SB(V_ZOOP) + dtbio * (SR(dig) - morz - SR(graz_Z) - SR(excr)));
           UPD(V_DIAZ, SB(V_DIAZ) + dtbio * (SR(npp_D) - morp_D - SR(morpt_D) - SR(graz_D)));
           UPD(V_DIAT, SB(V_DIAT) + dtbio * (SR(npp_Diat) - morp_Diat - SR(graz_Diat) - SR(morpt_Diat)));
@@ -1167,8 +1168,8 @@ __global__ void __launch_bounds__(32 * WS_WARPS * G) k_mobi_ws(const DevView v, 
           const double nupt = P->nupt0 * bct, nupt_D = P->nupt0_D * bct, nudt = P->nudt0 * bct;
           double thetaZ = P->zprefP * biophyt + P->zprefDet * biodetr + P->zprefZ * biozoop + P->zprefDiaz * biodiaz + P->kzoo +
                           P->zprefDiat * biodiat;
-          double ing_P = P->zprefP / thetaZ, ing_Det = P->zprefDet / thetaZ, ing_Z = P->zprefZ / thetaZ;
-          double ing_D = P->zprefDiaz / thetaZ, ing_Diat = P->zprefDiat / thetaZ;
+          double ing_P = QDIV(P->zprefP, thetaZ), ing_Det = QDIV(P->zprefDet, thetaZ), ing_Z = QDIV(P->zprefZ, thetaZ);
+          double ing_D = QDIV(P->zprefDiaz, thetaZ), ing_Diat = QDIV(P->zprefDiat, thetaZ);
           double graz_D = gmax * ing_D * biodiaz * biozoop;
           double morpt_D = nupt_D * biodiaz;
           double morp_D = P->nup_D * biodiaz * biodiaz;
@@ -1220,11 +1221,11 @@ __global__ void __launch_bounds__(32 * WS_WARPS * G) k_mobi_ws(const DevView v, 
           double sf_P_phos = (graz * ptn_P - dig_P * redptn);
           double sf_Det_phos = (graz_Det * ptn_detr - dig_Det * redptn);
           double sf_phos = sf_P_phos + sf_Z * redptn + sf_Det_phos + sf_Diat * redptn;
-          double dig_D = gamma1 * graz_D * (redntp / diazntp);
+          double dig_D = gamma1 * graz_D * (QDIV(redntp, diazntp));
           dig = dig + dig_D;
-          excr = excr + gamma1 * (1 - geZ) * graz_D * (redntp / diazntp);
-          double nr_excr_D = gamma1 * graz_D * (1 - (redntp / diazntp)) + (1 - gamma1) * graz_D * (1 - (redntp / diazntp));
-          double sf_D = (1 - gamma1) * graz_D * (redntp / diazntp);
+          excr = excr + gamma1 * (1 - geZ) * graz_D * (QDIV(redntp, diazntp));
+          double nr_excr_D = gamma1 * graz_D * (1 - (QDIV(redntp, diazntp))) + (1 - gamma1) * graz_D * (1 - (QDIV(redntp, diazntp)));
+          double sf_D = (1 - gamma1) * graz_D * (QDIV(redntp, diazntp));
           sf = sf + sf_D;
           sf_phos = sf_phos + sf_D * redptn;
           double calpro = ((sf_Z + morz) * lc3 + (sf_P + morp) * lc3) * redctn * 1.e3;
@@ -1245,13 +1246,13 @@ __global__ void __launch_bounds__(32 * WS_WARPS * G) k_mobi_ws(const DevView v, 
         {
           // 13C fractionation of primary production and ratios of the living pools (:2501-2530)
           const double biodic = SB(V_DIC);
-          double rdic13 = fmax(fmin(SB(V_DIC13) / (biodic - SB(V_DIC13)), 2. * RC13STD), 0.5 * RC13STD);
+          double rdic13 = fmax(fmin(QDIV(SB(V_DIC13), (biodic - SB(V_DIC13))), 2. * RC13STD), 0.5 * RC13STD);
           double bc13npp = lc7 * rdic13;
-          SR(fcnpp) = bc13npp / (1 + bc13npp);
-          SR(rtphytc13) = CL13(SB(V_PHYTC13) / (SB(V_PHYT) * redctn));
-          SR(rtdiatc13) = CL13(SB(V_DIATC13) / (SB(V_DIAT) * redctn));
-          SR(rtzoopc13) = CL13(SB(V_ZOOPC13) / (SB(V_ZOOP) * redctn));
-          SR(rtdetrc13) = CL13(SB(V_DETRC13) / (SB(V_DETR) * redctn));
+          SR(fcnpp) = QDIV(bc13npp, (1 + bc13npp));
+          SR(rtphytc13) = CL13(QDIV(SB(V_PHYTC13), (SB(V_PHYT) * redctn)));
+          SR(rtdiatc13) = CL13(QDIV(SB(V_DIATC13), (SB(V_DIAT) * redctn)));
+          SR(rtzoopc13) = CL13(QDIV(SB(V_ZOOPC13), (SB(V_ZOOP) * redctn)));
+          SR(rtdetrc13) = CL13(QDIV(SB(V_DETRC13), (SB(V_DETR) * redctn)));
         }
         WS_BAR();
         {
@@ -1298,9 +1299,9 @@ __global__ void __launch_bounds__(32 * WS_WARPS * G) k_mobi_ws(const DevView v, 
         {
           // iron speciation and scavenging (:2262-2283)
           const double biodon = SB(V_DON), biodfe = SB(V_DFE), aou8 = lc0, o2flag = lc1;
-          double ligand = fmax(aou8 / 66. + pow(biodon, 0.8) / 4.8, 0.5) / 1000.;
+          double ligand = QDIV(fmax(QDIV(aou8, 66.) + QDIV(pow(biodon, 0.8), 4.8), 0.5), 1000.);
           double fepa = (1.0 + P->kfeleq * (ligand - biodfe)) * o2flag;
-          double feprime = ((-fepa + sqrt(fepa * fepa + 4.0 * P->kfeleq * biodfe)) / (2.0 * P->kfeleq)) * o2flag;
+          double feprime = (QDIV((-fepa + sqrt(fepa * fepa + 4.0 * P->kfeleq * biodfe)), (2.0 * P->kfeleq))) * o2flag;
           double fecol = P->kfecol * (feprime * feprime) * o2flag;
           SR(feprime) = feprime;
           SR(fecol) = fecol * SF(V_DFE);
@@ -1311,12 +1312,12 @@ __global__ void __launch_bounds__(32 * WS_WARPS * G) k_mobi_ws(const DevView v, 
           const double biophyt = SB(V_PHYT), biodfe = SB(V_DFE), biodop = SB(V_DOP), biopo4 = SB(V_PO4), biono3 = SB(V_NO3);
           const double biodiaz = SB(V_DIAZ);
           double p1 = fmin(biophyt, P->pmax), p2 = fmax(0.0, biophyt - P->pmax);
-          double k1n = (P->knmin * p1 + P->knmax * p2) / (p1 + p2);
+          double k1n = QDIV((P->knmin * p1 + P->knmax * p2), (p1 + p2));
           double k1p_P = k1n * ptn_P;
-          double deffe_D = biodfe / (P->kfe_D + biodfe);
+          double deffe_D = QDIV(biodfe, (P->kfe_D + biodfe));
           double jmax_D = fmax(0., P->abio_P * (bct - P->dbct_D) * deffe_D) * P->jdiar;
-          double limP_dop = P->hdop * biodop / (k1p_P + biodop);
-          double limP_po4 = biopo4 / (k1p_P + biopo4);
+          double limP_dop = QDIV(P->hdop * biodop, (k1p_P + biodop));
+          double limP_po4 = QDIV(biopo4, (k1p_P + biopo4));
           double dopupt_flag = 0.5 + fsign(0.5, limP_dop - limP_po4);
           double limP = limP_dop * dopupt_flag + limP_po4 * (1. - dopupt_flag);
           double u_D = fmin(lc2, jmax_D * limP);
@@ -1328,8 +1329,8 @@ __global__ void __launch_bounds__(32 * WS_WARPS * G) k_mobi_ws(const DevView v, 
           SR(npp_D) = npp_D;
           SR(no3upt_D) = no3upt_D;
           acc0 = acc0 + npp_D - no3upt_D;   // nfixout
-          SR(rtdoc13) = CL13(SB(V_DOC13) / (SB(V_DON) * redctn));
-          SR(rtdiazc13) = CL13(SB(V_DIAZC13) / (biodiaz * redctn));
+          SR(rtdoc13) = CL13(QDIV(SB(V_DOC13), (SB(V_DON) * redctn)));
+          SR(rtdiazc13) = CL13(QDIV(SB(V_DIAZC13), (biodiaz * redctn)));
         }
         WS_BAR();
         {
@@ -1442,13 +1443,13 @@ __global__ void __launch_bounds__(32 * WS_WARPS * G) k_mobi_ws(const DevView v, 
           sg_bdeni = fmin(sg_bdeni, sgb * expo);
           sg_bdeni = fmax(sg_bdeni, 0.);
           sg_bdeni = sg_bdeni * (0.5 + lno3) * no3flag * din15flag;
-          double rno3 = fmax(tdin15, TRCMIN * RN15STD / (1 + RN15STD)) / fmax(tno3 - tdin15, TRCMIN * RN15STD / (1 + RN15STD));
+          double rno3 = QDIV(fmax(tdin15, TRCMIN * RN15STD / (1 + RN15STD)), fmax(tno3 - tdin15, TRCMIN * RN15STD / (1 + RN15STD)));
           rno3 = fmin(rno3, 2. * RN15STD);
           rno3 = fmax(rno3, RN15STD / 2.);
           double eps_bdeni = v.mobi_epsbd[k - 1];
-          double bbdeni = rno3 - eps_bdeni * rno3 / 1000.;
+          double bbdeni = rno3 - QDIV(eps_bdeni * rno3, 1000.);
           e3_no3 = SB(V_NO3) + sgb * expo - sg_bdeni;
-          e3_din15 = SB(V_DIN15) + rn15expo * sgb * expo - bbdeni / (1 + bbdeni) * sg_bdeni;
+          e3_din15 = SB(V_DIN15) + rn15expo * sgb * expo - QDIV(bbdeni, (1 + bbdeni)) * sg_bdeni;
           e3_c = c;
           e3_pending = act;
         } break;
@@ -1471,7 +1472,7 @@ __global__ void __launch_bounds__(32 * WS_WARPS * G) k_mobi_ws(const DevView v, 
             sg_bdeni = fmax(sg_bdeni, 0.);
             bdeni = sg_bdeni * (0.5 + lno3a) * no3flag * din15flag;
           }
-          double rno3 = fmax(tdin15, TRCMIN * RN15STD / (1 + RN15STD)) / fmax(tno3 - tdin15, TRCMIN * RN15STD / (1 + RN15STD));
+          double rno3 = QDIV(fmax(tdin15, TRCMIN * RN15STD / (1 + RN15STD)), fmax(tno3 - tdin15, TRCMIN * RN15STD / (1 + RN15STD)));
           rno3 = fmin(rno3, 2. * RN15STD);
           rno3 = fmax(rno3, RN15STD / 2.);
           const double fo2 = PRE(PR_FO2);
@@ -1479,12 +1480,12 @@ __global__ void __launch_bounds__(32 * WS_WARPS * G) k_mobi_ws(const DevView v, 
           double lno3 = PRE(PR_LNO3B);
           double wcdeni = 800. * no3flag * so2 * (1.0 - fo2) * (0.5 + lno3) * din15flag;
           wcdeni = fmax(wcdeni, 0.);
-          double uno3 = wcdeni * v.c2dtts / tno3;
+          double uno3 = QDIV(wcdeni * v.c2dtts, tno3);
           uno3 = fmin(uno3, 0.999);
           uno3 = fmax(uno3, TRCMIN);
-          double bwcdeni = rno3 + P->eps_wcdeni * (1 - uno3) / uno3 * log(1 - uno3) * rno3 / 1000.;
+          double bwcdeni = rno3 + QDIV(QDIV(P->eps_wcdeni * (1 - uno3), uno3) * log(1 - uno3) * rno3, 1000.);
           SL(L_wcdeni) = wcdeni;
-          SL(L_bwfrac) = (bwcdeni / (1 + bwcdeni));
+          SL(L_bwfrac) = (QDIV(bwcdeni, (1 + bwcdeni)));
           src_alk = src_alk + wcdeni * 1.e-3;
           src_alk = src_alk + bdeni * 1.e-3;
           src_alk = src_alk - nfix * rnbio * 1.e-3;
@@ -1511,13 +1512,12 @@ __global__ void __launch_bounds__(32 * WS_WARPS * G) k_mobi_ws(const DevView v, 
           double coxdepth = fmin(fmax(v.zt[k - 1], 50000.), 150000.);
           double oblinc = -1.26e-6 * coxdepth + 0.203;
           double obexpc = -6.e-7 * coxdepth + 1.14;
-          double nburial = (oblinc * pow((expo * sgb * dztk / 100 * 86400. * 365. * redctn * 1000.), obexpc)) /
-                           (86400. * 365. * dztk / 100 * redctn * 1000.);
+          double nburial = QDIV((oblinc * pow((QDIV(expo * sgb * dztk, 100) * 86400. * 365. * redctn * 1000.), obexpc)), (QDIV(86400. * 365. * dztk, 100) * redctn * 1000.));
           double coxsed = expo * sgb - nburial;
-          double fesed = 85. * tanh(coxsed * redctn * 1000 * dztk / 100 * 86400. / o2_in) / (dztk / 100 * 86400 * 1000);
+          double fesed = QDIV(85. * tanh(QDIV(QDIV(coxsed * redctn * 1000 * dztk, 100) * 86400., o2_in)), (QDIV(dztk, 100) * 86400 * 1000));
           double dfe = SB(V_DFE) + fesed;
           if (act) {
-            if (k == 1) dfe = dfe + v.fe_atmdep[X2(i, j) + (long long)(mi - 1) * v.n2] * 1000 / (v.dzt[0] / 100.);
+            if (k == 1) dfe = dfe + QDIV(v.fe_atmdep[X2(i, j) + (long long)(mi - 1) * v.n2] * 1000, (QDIV(v.dzt[0], 100.)));
             dfe = dfe + v.fe_hydr[XIJK(i, j, k)];
             v.src[c + (long long)(ix[IX_SRC + V_DFE] - 1) * n3] = dfe;
           }
@@ -1528,10 +1528,10 @@ __global__ void __launch_bounds__(32 * WS_WARPS * G) k_mobi_ws(const DevView v, 
           const double rexpocaco3 = SL(S_expocaco3) * rnbio;
           const double dic_in = act ? v.t_m1[c + (long long)(ix[IX_TR + V_DIC] - 1) * n3] : 1.0;
           double dic13 = SB(V_DIC13) + rc13expo * sgb * redctn;
-          double rtdic13 = fmax(SC(V_DIC13), TRCMIN * RC13STD / (1 + RC13STD)) / fmax(dic_in, TRCMIN);
+          double rtdic13 = QDIV(fmax(SC(V_DIC13), TRCMIN * RC13STD / (1 + RC13STD)), fmax(dic_in, TRCMIN));
           rtdic13 = fmin(rtdic13, 2. * RC13STD / (1 + RC13STD));
           rtdic13 = fmax(rtdic13, 0.5 * RC13STD / (1 + RC13STD));
-          double rtcaco3c13 = fmax(SC(V_CACO3C13), TRCMIN * RC13STD / (1 + RC13STD)) / fmax(SC(V_CACO3), TRCMIN);
+          double rtcaco3c13 = QDIV(fmax(SC(V_CACO3C13), TRCMIN * RC13STD / (1 + RC13STD)), fmax(SC(V_CACO3), TRCMIN));
           rtcaco3c13 = fmin(rtcaco3c13, 2. * RC13STD / (1 + RC13STD));
           rtcaco3c13 = fmax(rtcaco3c13, 0.5 * RC13STD / (1 + RC13STD));
           if (k < kmx)
