@@ -163,23 +163,23 @@ __device__ void co2calc_sws(double t, double s, double dic_in, double ta_in, dou
   q.dic = dic_in * permil;
   const double pres = depth * 0.1;
   double tk = 273.15 + t;
-  double tk100 = tk / 100.0;
+  double tk100 = QDIV(tk, 100.0);
   double tk1002 = tk100 * tk100;
-  double invtk = 1.0 / tk;
+  double invtk = QDIV(1.0, tk);
   double dlogtk = m_log(tk);
-  double is = 19.924 * s / (1000. - 1.005 * s);
+  double is = QDIV(19.924 * s, (1000. - 1.005 * s));
   double is2 = is * is;
   double sqrtis = sqrt(is);
   double s2 = s * s;
   double t2 = t * t;
   double sqrts = sqrt(s);
   double s15 = m_pow(s, 1.5);
-  double scl = s / 1.80655;
-  double pitkR = pres / tk / 83.15;
+  double scl = QDIV(s, 1.80655);
+  double pitkR = QDIV(QDIV(pres, tk), 83.15);
   double p2itkR = pres * pitkR;
-  q.bt = 0.000232 * scl / 10.811;
-  q.st = 0.14 * scl / 96.062;
-  q.ft = 0.000067 * scl / 18.9984;
+  q.bt = QDIV(0.000232 * scl, 10.811);
+  q.st = QDIV(0.14 * scl, 96.062);
+  q.ft = QDIV(0.000067 * scl, 18.9984);
   (void)tk1002;
 
   q.k1 = m_pow(10., (-1. * (3670.7 * invtk - 62.008 + 9.7944 * dlogtk - 0.0118 * s + 0.000116 * s2))) *
@@ -205,24 +205,24 @@ __device__ void co2calc_sws(double t, double s, double dic_in, double ta_in, dou
          m_exp((9.78 + 9.0e-3 * t + 9.42e-4 * t2) * pitkR + 0.5 * (-3.91e-3 + 5.4e-5 * t) * p2itkR);
   q.kb = m_exp((-8966.90 - 2890.53 * sqrts - 77.942 * s + 1.728 * s15 - 0.0996 * s2) * invtk +
              (148.0248 + 137.1942 * sqrts + 1.62142 * s) + (-24.4344 - 25.085 * sqrts - 0.2474 * s) * dlogtk + 0.053105 * sqrts * tk +
-             m_log((1 + (q.st / q.ks) + (q.ft / q.kf)) / (1 + (q.st / q.ks)))) *
+             m_log(QDIV((1 + (QDIV(q.st, q.ks)) + (QDIV(q.ft, q.kf))), (1 + (QDIV(q.st, q.ks)))))) *
          m_exp((29.48 - 0.1622 * t - 2.608e-3 * t2) * pitkR + 0.5 * (-2.84e-3) * p2itkR);
 
   // [H+] on the seawater scale in [1e-10, 1e-6], xacc = 1e-10 (:343-346)
   double x1 = m_pow(10.0, -6.), x2 = m_pow(10.0, -10.);
   double hSWS = drtsafe(q, x1, x2, 1.e-10);
   double hSWS2 = hSWS * hSWS;
-  double co2star = q.dic * hSWS2 / (hSWS2 + q.k1 * hSWS + q.k1 * q.k2);
-  double CO3 = q.k1 * q.k2 * co2star / hSWS2;
+  double co2star = QDIV(q.dic * hSWS2, (hSWS2 + q.k1 * hSWS + q.k1 * q.k2));
+  double CO3 = QDIV(q.k1 * q.k2 * co2star, hSWS2);
   // calcite solubility product with pressure dependence (:360-388)
-  double Kspc = m_exp(-395.8293 + (6537.773 / tk) + 71.595 * m_log(tk) - 0.17959 * tk +
-                    (-1.78938 + (410.64 / tk) + 0.0065453 * tk) * sqrt(s) - 0.17755 * s + 0.0094979 * s15);
-  double DVc = -65.28 + 0.397 * t - 0.005155 * (t * t) + (19.816 - 0.0441 * t - 0.00017 * (t * t)) * sqrt(s / 35.);
-  double DK = 0.01847 + 0.0001956 * t - 0.000002212 * (t * t) + (-0.03217 - 0.0000711 * t + 0.000002212) * sqrt(s / 35.);
+  double Kspc = m_exp(-395.8293 + (QDIV(6537.773, tk)) + 71.595 * m_log(tk) - 0.17959 * tk +
+                    (-1.78938 + (QDIV(410.64, tk)) + 0.0065453 * tk) * sqrt(s) - 0.17755 * s + 0.0094979 * s15);
+  double DVc = -65.28 + 0.397 * t - 0.005155 * (t * t) + (19.816 - 0.0441 * t - 0.00017 * (t * t)) * sqrt(QDIV(s, 35.));
+  double DK = 0.01847 + 0.0001956 * t - 0.000002212 * (t * t) + (-0.03217 - 0.0000711 * t + 0.000002212) * sqrt(QDIV(s, 35.));
   Kspc = Kspc * m_exp(-DVc * pitkR + 0.5 * DK * p2itkR);
   const double Ca = 10.28E-3;
-  omega_c = Ca * CO3 / Kspc;
-  co2star_out = co2star / permil;
+  omega_c = QDIV(Ca * CO3, Kspc);
+  co2star_out = QDIV(co2star, permil);
 }
 
 // ------------------------------------------------------------------------------------
@@ -251,13 +251,13 @@ __global__ void __launch_bounds__(128) k_mobi_light(const DevView v, double decl
   const MobiPar *__restrict__ P = v.mobi_par;
   const int *__restrict__ ix = v.mobi_idx;
   const double pi = 3.14159265358979323846;  // atan(1.0)*4.0 in FP64
-  const double radian = 360. / (2. * pi);
+  const double radian = QDIV(360., (2. * pi));
   double lat = v.tlat[X2(i, j)];
-  double rctheta = fmax(-1.5, fmin(1.5, lat / radian - declin));
+  double rctheta = fmax(-1.5, fmin(1.5, QDIV(lat, radian) - declin));
   double cr = cos(rctheta);
-  rctheta = P->kw / sqrt(1. - (1. - cr * cr) / (1.33 * 1.33));
-  double dayfrac = fmin(1., -tan(lat / radian) * tan(declin));
-  dayfrac = fmax(1e-12, acos(fmax(-1., dayfrac)) / pi);
+  rctheta = QDIV(P->kw, sqrt(1. - QDIV((1. - cr * cr), (1.33 * 1.33))));
+  double dayfrac = fmin(1., -tan(QDIV(lat, radian)) * tan(declin));
+  dayfrac = fmax(1e-12, QDIV(acos(fmax(-1., dayfrac)), pi));
   double swr = P->tap * v.dnswr[X2(i, j)] * 1e-3 * (1. + v.aice[X2(i, j)] * (m_exp(-P->ki * (v.hice[X2(i, j)] + v.hsno[X2(i, j)])) - 1.));
   v.mobi_day[X2(i, j)] = dayfrac;
   const long long n3 = v.n3;
@@ -294,10 +294,10 @@ __global__ void __launch_bounds__(128) k_mobi_light(const DevView v, double decl
 
 // Evans & Parslow daily-mean light-limited growth (09/mom/mobi.F:1984-2003), one species
 __device__ __forceinline__ double evans_parslow(double gl_x, double gd, double f1, double kirr, double dzt) {
-  double u1 = fmax(gl_x / gd, 1.e-6), u2 = u1 * f1;
-  double phi1 = m_log(u1 + sqrt(1. + u1 * u1)) - (sqrt(1. + u1 * u1) - 1.) / u1;
-  double phi2 = m_log(u2 + sqrt(1. + u2 * u2)) - (sqrt(1. + u2 * u2) - 1.) / u2;
-  return gd * (phi1 - phi2) / (-kirr * dzt);
+  double u1 = fmax(QDIV(gl_x, gd), 1.e-6), u2 = u1 * f1;
+  double phi1 = m_log(u1 + sqrt(1. + u1 * u1)) - QDIV((sqrt(1. + u1 * u1) - 1.), u1);
+  double phi2 = m_log(u2 + sqrt(1. + u2 * u2)) - QDIV((sqrt(1. + u2 * u2) - 1.), u2);
+  return QDIV(gd * (phi1 - phi2), (-kirr * dzt));
 }
 
 // k_mobi_cell: one thread per ocean cell.  co2calc_SWS (09/common/co2calc.F, called from
@@ -326,22 +326,22 @@ __global__ void __launch_bounds__(128, 5) k_mobi_cell(const DevView v) {
   const double o2_in = TIN(IX_IO2) * 1000.;
   double *__restrict__ pre = v.mobi_pre + c;
   double co2star, Omega_c;
-  co2calc_sws(t_in, s_in, dic_in, alk_in, v.zt[k - 1] / 100., co2star, Omega_c);
+  co2calc_sws(t_in, s_in, dic_in, alk_in, QDIV(v.zt[k - 1], 100.), co2star, Omega_c);
   {
     double ac13_DIC_aq = -1.0512994e-4 * t_in + 1.011765;
     double ac13_aq_POC = -0.017 * m_log10(fmin(fmax(co2star * 1000., 2.), 74.)) + 1.0034;
-    pre[(long long)PR_AC13B * n3] = ac13_aq_POC / ac13_DIC_aq;
+    pre[(long long)PR_AC13B * n3] = QDIV(ac13_aq_POC, ac13_DIC_aq);
     pre[(long long)PR_DISSK1 * n3] = P->dissk0 * fmax(0., (1. - Omega_c));
-    pre[(long long)PR_CAPR * n3] = P->caprmax * fmax(0., (Omega_c - 1.) / (P->kcapr + Omega_c - 1.));
+    pre[(long long)PR_CAPR * n3] = P->caprmax * fmax(0., (Omega_c - 1.) / (P->kcapr + Omega_c - 1.));   // singular at Omega_c = 1 - kcapr: the full IEEE divide
   }
   // oxygen saturation -> AOU for the ligand parameterisation
   double aou_in;
   {
-    double f1 = m_log((298.15 - t_in) / (273.15 + t_in));
+    double f1 = m_log(QDIV((298.15 - t_in), (273.15 + t_in)));
     double f2 = f1 * f1, f3 = f2 * f1, f4 = f3 * f1, f5 = f4 * f1;
     double o2sat = m_exp(2.00907 + 3.22014 * f1 + 4.05010 * f2 + 4.94457 * f3 - 2.56847E-1 * f4 + 3.88767 * f5 +
                        s_in * (-6.24523e-3 - 7.37614e-3 * f1 - 1.03410e-2 * f2 - 8.17083E-3 * f3) - 4.88682E-7 * s_in * s_in);
-    o2sat = o2sat / 22391.6 * 1000.0 * 1000.;
+    o2sat = QDIV(o2sat, 22391.6) * 1000.0 * 1000.;
     aou_in = o2sat - o2_in;
   }
   const double bct = m_pow(P->bbio, (P->cbio * t_in));
@@ -365,17 +365,17 @@ __global__ void __launch_bounds__(128, 5) k_mobi_cell(const DevView v) {
     const double bdfe = fmax(TIN(IX_TR + V_DFE), TRCMIN);
     const double gl = pre[(long long)PR_GL * n3], dayfrac = v.mobi_day[X2(i, j)], dzt = v.dzt[k - 1];
     double p1 = fmin(bphyt, P->pmax), p2 = fmax(0.0, bphyt - P->pmax);
-    double kfevar = (P->kfemin * p1 + P->kfemax * p2) / (p1 + p2);
-    double deffe = bdfe / (kfevar + bdfe);
+    double kfevar = QDIV((P->kfemin * p1 + P->kfemax * p2), (p1 + p2));
+    double deffe = QDIV(bdfe, (kfevar + bdfe));
     double thetamax = P->thetamaxlo + (P->thetamaxhi - P->thetamaxlo) * deffe;
     double alpha_O = P->alphamin + (P->alphamax - P->alphamin) * deffe;
     double gl_O = gl * thetamax * alpha_O;
     p1 = fmin(bdiat, P->pmax_Diat);
     p2 = fmax(0.0, bdiat - P->pmax_Diat);
-    double kfevar_Diat = (P->kfemin_Diat * p1 + P->kfemax_Diat * p2) / (p1 + p2);
-    double deffe_Diat = bdfe / (kfevar_Diat + bdfe);
+    double kfevar_Diat = QDIV((P->kfemin_Diat * p1 + P->kfemax_Diat * p2), (p1 + p2));
+    double deffe_Diat = QDIV(bdfe, (kfevar_Diat + bdfe));
     double gl_Diat = gl * (P->thetamaxlo + (P->thetamaxhi - P->thetamaxlo) * deffe_Diat) * (P->alphamin + (P->alphamax - P->alphamin) * deffe_Diat);
-    double deffe_D = bdfe / (P->kfe_D + bdfe);
+    double deffe_D = QDIV(bdfe, (P->kfe_D + bdfe));
     double gl_D = gl * (P->thetamaxlo + (P->thetamaxhi - P->thetamaxlo) * deffe_D) * (P->alphamin + (P->alphamax - P->alphamin) * deffe_D);
     double kirr = -P->kw - P->kc * (bphyt + bdiaz + bdiat) - P->kc_c * bcaco3;
     double f1 = m_exp(kirr * dzt);
