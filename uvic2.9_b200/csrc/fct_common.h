@@ -9,23 +9,8 @@ __device__ __forceinline__ double upw(double totadv, double a, double b) { retur
 __device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
 __device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
 
-// x / y for a positive normal y and a finite x whose quotient neither overflows nor underflows (here y = P + 1e-20 with
-// P >= 0 a flux sum, x = Q >= 0 a tracer difference).  This is the instruction sequence of the compiler's own IEEE
-// divide -- reciprocal seed, two Newton steps, quotient, one remainder correction; correctly rounded -- without the
-// exponent-range test and the out-of-line slow path behind it, which these operands can never need.  x = 0 gives 0.
-__device__ __forceinline__ double fdiv_pos(double x, double y) {
-  double r0;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(y));
-  r0 = __hiloint2double(__double2hiint(r0), 1);
-  double e = fma(-y, r0, 1.0);
-  e = fma(e, e, e);
-  double r = fma(r0, e, r0);
-  e = fma(-y, r, 1.0);
-  r = fma(r, e, r);
-  const double q = x * r;
-  const double rem = fma(-y, q, x);
-  return fma(r, rem, q);
-}
+// the limiter ratios divide Q >= 0 by P + 1e-20 > 0: qdiv (ctx.h) applies
+__device__ __forceinline__ double fdiv_pos(double x, double y) { return qdiv(x, y); }
 
 __device__ __forceinline__ void ratio(double c2dtts, double dcf, double flxlft, double flxrgt, double fxa, double fxb, double tlo,
                                       double m, double &rpl, double &rmn) {

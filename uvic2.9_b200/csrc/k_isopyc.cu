@@ -120,16 +120,16 @@ __global__ void __launch_bounds__(256) k_isocoef(const DevView v) {
         double drodxe = al * DX(i, k, j, 1) + be * DX(i, k, j, 2);
         double drodze = al * DZ(i + ip, k - 1 + kr, j, 1) + be * DZ(i + ip, k - 1 + kr, j, 2);
         double den = drodze + UVIC_EPSLN;
-        double sxe = fabs(div0(drodxe, den));
+        double sxe = fabs(qdiv(drodxe, den));
         double a;
         if (sxe > sc) {
-          double r = sc / (sxe + UVIC_EPSLN);
+          double r = qdiv(sc, sxe + UVIC_EPSLN);
           a = Ai0 * m * me * (r * r);
         } else {
           a = Ai0 * m * me;
         }
         sumz = sumz + v.dzw[k - 1 + kr] * a;
-        v.ce[c + (ip + 2 * kr) * v.n3] = div0(a * drodxe, den);
+        v.ce[c + (ip + 2 * kr) * v.n3] = qdiv(a * drodxe, den);
       }
     v.K11[c] = dzt4r * sumz;
   }
@@ -147,16 +147,16 @@ __global__ void __launch_bounds__(256) k_isocoef(const DevView v) {
         double drodyn = al * DY(i, k, j, 1) + be * DY(i, k, j, 2);
         double drodzn = al * DZ(i, k - 1 + kr, j + jq, 1) + be * DZ(i, k - 1 + kr, j + jq, 2);
         double den = drodzn + UVIC_EPSLN;
-        double syn = fabs(div0(drodyn, den));
+        double syn = fabs(qdiv(drodyn, den));
         double a;
         if (syn > sc) {
-          double r = sc / (syn + UVIC_EPSLN);
+          double r = qdiv(sc, syn + UVIC_EPSLN);
           a = Ai0 * m * mn * (r * r);
         } else {
           a = Ai0 * m * mn;
         }
         sumz = sumz + v.dzw[k - 1 + kr] * a;
-        v.cn[c + (jq + 2 * kr) * v.n3] = div0(a * drodyn, den);
+        v.cn[c + (jq + 2 * kr) * v.n3] = qdiv(a * drodyn, den);
       }
     v.K22[c] = dzt4r * sumz;
   }
@@ -175,16 +175,16 @@ __global__ void __launch_bounds__(256) k_isocoef(const DevView v) {
           double drodxb = al * DX(i - 1 + ip, k + kr, j, 1) + be * DX(i - 1 + ip, k + kr, j, 2);
           double drodzb = al * DZ(i, k, j, 1) + be * DZ(i, k, j, 2);
           double den = drodzb + UVIC_EPSLN;
-          double sxb = fabs(div0(drodxb, den));
+          double sxb = fabs(qdiv(drodxb, den));
           double a;
           if (sxb > sc) {
-            double r = sc / (sxb + UVIC_EPSLN);
+            double r = qdiv(sc, sxb + UVIC_EPSLN);
             a = Ai0 * mb * (r * r);
           } else {
             a = Ai0 * mb;
           }
           sumx = sumx + v.dxu[i - 1 + ip - 1] * a * (sxb * sxb);
-          v.cbx[c + (ip + 2 * kr) * v.n3] = div0(a * v.cstr[j - 1] * drodxb, den);
+          v.cbx[c + (ip + 2 * kr) * v.n3] = qdiv(a * v.cstr[j - 1] * drodxb, den);
         }
 #pragma unroll
       for (int jq = 0; jq <= 1; jq++) {
@@ -195,16 +195,16 @@ __global__ void __launch_bounds__(256) k_isocoef(const DevView v) {
           double drodyb = al * DY(i, k + kr, j - 1 + jq, 1) + be * DY(i, k + kr, j - 1 + jq, 2);
           double drodzb = al * DZ(i, k, j, 1) + be * DZ(i, k, j, 2);
           double den = drodzb + UVIC_EPSLN;
-          double syb = fabs(div0(drodyb, den));
+          double syb = fabs(qdiv(drodyb, den));
           double a;
           if (syb > sc) {
-            double r = sc / (syb + UVIC_EPSLN);
+            double r = qdiv(sc, syb + UVIC_EPSLN);
             a = Ai0 * mb * (r * r);
           } else {
             a = Ai0 * mb;
           }
           sumy = sumy + facty * a * (syb * syb);
-          v.cby[c + (jq + 2 * kr) * v.n3] = div0(a * v.csu[j - 1 + jq - 1] * drodyb, den);
+          v.cby[c + (jq + 2 * kr) * v.n3] = qdiv(a * v.csu[j - 1 + jq - 1] * drodyb, den);
         }
       }
       v.K33[c] = v.dxt4r[i - 1] * sumx + v.dyt4r[j - 1] * v.cstr[j - 1] * sumy;
@@ -260,19 +260,19 @@ __global__ void __launch_bounds__(256) k_gm_faces(const DevView v) {
       tn_z = at * (DZ(i, 1, j, 1) + DZ(i, 1, j + 1, 1)) * 0.5 + bt * (DZ(i, 1, j, 2) + DZ(i, 1, j + 1, 2)) * 0.5;
     }
     double Ath0 = v.athkdf * 0.5 * (v.fisop[XIJK(i, j, k)] + v.fisop[XIJK(i, j + 1, k)]);
-    double stn = div0(-tn_y, tn_z + 0.125 * UVIC_EPSLN);
-    double sbn = div0(-bn_y, bn_z + 0.125 * UVIC_EPSLN);
+    double stn = qdiv(-tn_y, tn_z + 0.125 * UVIC_EPSLN);
+    double sbn = qdiv(-bn_y, bn_z + 0.125 * UVIC_EPSLN);
     double absstn = fabs(stn), abssbn = fabs(sbn);
     double mn = tmask_of(v, i, k, j + 1), mnk1 = tmask_of(v, i, kp1, j + 1);
     double ath_t, ath_b;
     if (absstn > sc) {
-      double r = sc / (absstn + UVIC_EPSLN);
+      double r = qdiv(sc, absstn + UVIC_EPSLN);
       ath_t = Ath0 * m * mn * (r * r);
     } else {
       ath_t = Ath0 * m * mn;
     }
     if (abssbn > sc) {
-      double r = sc / (abssbn + UVIC_EPSLN);
+      double r = qdiv(sc, abssbn + UVIC_EPSLN);
       ath_b = Ath0 * mk1 * mnk1 * (r * r);
     } else {
       ath_b = Ath0 * mk1 * mnk1;
@@ -293,19 +293,19 @@ __global__ void __launch_bounds__(256) k_gm_faces(const DevView v) {
       te_z = at * (DZ(i, 1, j, 1) + DZ(i + 1, 1, j, 1)) * 0.5 + bt * (DZ(i, 1, j, 2) + DZ(i + 1, 1, j, 2)) * 0.5;
     }
     double Ath0 = v.athkdf * 0.5 * (v.fisop[XIJK(i, j, k)] + v.fisop[XIJK(i + 1, j, k)]);
-    double ste = div0(-te_x, te_z + 0.125 * UVIC_EPSLN);
-    double sbe = div0(-be_x, be_z + 0.125 * UVIC_EPSLN);
+    double ste = qdiv(-te_x, te_z + 0.125 * UVIC_EPSLN);
+    double sbe = qdiv(-be_x, be_z + 0.125 * UVIC_EPSLN);
     double absste = fabs(ste), abssbe = fabs(sbe);
     double me = tmask_of(v, i + 1, k, j), mek1 = tmask_of(v, i + 1, kp1, j);
     double ath_t, ath_b;
     if (absste > sc) {
-      double r = sc / (absste + UVIC_EPSLN);
+      double r = qdiv(sc, absste + UVIC_EPSLN);
       ath_t = Ath0 * m * me * (r * r);
     } else {
       ath_t = Ath0 * m * me;
     }
     if (abssbe > sc) {
-      double r = sc / (abssbe + UVIC_EPSLN);
+      double r = qdiv(sc, abssbe + UVIC_EPSLN);
       ath_b = Ath0 * mk1 * mek1 * (r * r);
     } else {
       ath_b = Ath0 * mk1 * mek1;

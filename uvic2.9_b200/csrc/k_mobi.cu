@@ -49,25 +49,6 @@ struct Carb {
   double bt, st, ft, sit, pt, dic, ta;                // COMMON /species/
 };
 
-// x / y by the compiler's own IEEE divide sequence (reciprocal seed, two Newton steps, quotient, one remainder
-// correction: correctly rounded) without the exponent-range test and the out-of-line slow path behind it.  Valid while
-// x, y and x / y stay well inside the normal range, which holds for every operand of ta_iter ([H+] in [1e-10, 1e-6],
-// equilibrium constants 1e-14 .. 1e-1, their products down to ~1e-60).  ta_iter holds ~30 divides and runs ~10 times
-// per cell: this halves the loop body.
-__device__ __forceinline__ double qdiv(double x, double y) {
-  double r0;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(y));
-  r0 = __hiloint2double(__double2hiint(r0), 1);
-  double e = fma(-y, r0, 1.0);
-  e = fma(e, e, e);
-  double r = fma(r0, e, r0);
-  e = fma(-y, r, 1.0);
-  r = fma(r, e, r);
-  const double q = x * r;
-  return fma(r, fma(-y, q, x), q);
-}
-
-#define QDIV(a, b) qdiv((a), (b))
 
 // 09/common/co2calc.F:455-526
 __device__ __forceinline__ void ta_iter(const Carb &q, double x, double &fn, double &df) {

@@ -558,9 +558,9 @@ __global__ void __launch_bounds__(128) k_convect_ts(const DevView v) {
       bool chk_la = true, chk_lb = true;
       double zsm = dz[kt - 1] + dz[kb - 1];
       double tsm1 = TSV(T, kt) * dz[kt - 1] + TSV(T, kb) * dz[kb - 1];
-      double tmx1 = tsm1 / zsm;
+      double tmx1 = qdiv(tsm1, zsm);
       double tsm2 = TSV(S, kt) * dz[kt - 1] + TSV(S, kb) * dz[kb - 1];
-      double tmx2 = tsm2 / zsm;
+      double tmx2 = qdiv(tsm2, zsm);
       while (chk_lb || chk_la) {
         if (kb >= kbo) chk_lb = false;
         while (chk_lb) {
@@ -572,9 +572,9 @@ __global__ void __launch_bounds__(128) k_convect_ts(const DevView v) {
             kb = lb;
             zsm = zsm + dz[kb - 1];
             tsm1 = tsm1 + TSV(T, kb) * dz[kb - 1];
-            tmx1 = tsm1 / zsm;
+            tmx1 = qdiv(tsm1, zsm);
             tsm2 = tsm2 + TSV(S, kb) * dz[kb - 1];
-            tmx2 = tsm2 / zsm;
+            tmx2 = qdiv(tsm2, zsm);
             chk_la = true;
             if (kb < kbo) chk_lb = true;
           }
@@ -590,9 +590,9 @@ __global__ void __launch_bounds__(128) k_convect_ts(const DevView v) {
             kt = la;
             zsm = zsm + dz[kt - 1];
             tsm1 = tsm1 + TSV(T, kt) * dz[kt - 1];
-            tmx1 = tsm1 / zsm;
+            tmx1 = qdiv(tsm1, zsm);
             tsm2 = tsm2 + TSV(S, kt) * dz[kt - 1];
-            tmx2 = tsm2 / zsm;
+            tmx2 = qdiv(tsm2, zsm);
             chk_lb = true;
           }
         }
@@ -652,7 +652,7 @@ __global__ void __launch_bounds__(128) k_convect_tr(const DevView v, int nfirst)
     double zsm = v.conv_zsm[col + (long long)r * v.n2];
     double tsm3 = 0.0;
     for (int k = kt; k <= kb; k++) tsm3 = tsm3 + X[c1 + (k - 1) * sk] * dz[k - 1];
-    double tmx3 = tsm3 / zsm;
+    double tmx3 = qdiv(tsm3, zsm);
     for (int k = kt; k <= kb; k++) X[c1 + (k - 1) * sk] = tmx3;
   }
   if (edge) {

@@ -33,8 +33,8 @@ __global__ void __launch_bounds__(256) k_vmix_cbt(const DevView v) {
       double zn2 = fmax(-v.gravrho0r * drodzb, 1e-8);
       double edr = 0.;
       for (int k1 = k + 1; k1 <= kb; k1++)
-        edr = edr + v.edrsum[c + (long long)(k1 - k) * v.imt] * v.edr_e1[(k - 1) + km * (k1 - 1)] / v.edr_den[k1 - 1];
-      double zkappa = v.ogamma * edr / zn2;
+        edr = edr + qdiv(v.edrsum[c + (long long)(k1 - k) * v.imt] * v.edr_e1[(k - 1) + km * (k1 - 1)], v.edr_den[k1 - 1]);
+      double zkappa = qdiv(v.ogamma * edr, zn2);
       d = fmax(v.kappa_h, fmin(100., zkappa + v.kappa_h));
     } else {
       d = v.kappa_h;
@@ -89,10 +89,10 @@ __global__ void __launch_bounds__(128) k_vmix_factor(const DevView v) {
         double b = 1.0 - a - cc;
         double e = 0.0;
         if (k == 1) {
-          bet = mk / (b + eps);
+          bet = qdiv(mk, b + eps);
         } else {
           e = cprev * bet;
-          bet = mk / (b - a * e + eps);
+          bet = qdiv(mk, b - a * e + eps);
         }
         const int c = c1 + (k - 1) * sk;
         ta[c] = a;
