@@ -44,7 +44,7 @@ def build(force=False, verbose=False, extra=()):
 
     def cc(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [NVCC, *FLAGS, f"-fmad={FMAD.get(src, 'false')}", *extra, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [NVCC, *FLAGS, f"-fmad={FMAD.get(src, 'false')}", *extra, *os.environ.get("UVIC_B200_NVCC_EXTRA", "").split(), "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")

@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(256) k_fct_rfac(const DevView v, int nbase, in
 // fluxes + explicit update, rows jlo..jhi
 // ------------------------------------------------------------------------------------
 #define UPD_T 128   // threads per CTA of k_update
+__device__ __forceinline__ void pf_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // per-thread column of the shared-memory coefficient table: element a lives at p[a*UPD_T]
 struct SmCol {
   double *p;
@@ -216,6 +217,12 @@ __global__ void __launch_bounds__(UPD_T) k_update(const DevView v, int nbase, in
     const double *__restrict__ T = v.t_m1 + (long long)n0 * n3;
     const double *__restrict__ U = v.t_0 + (long long)n0 * n3;
     const double *__restrict__ R = v.Rfac + (long long)g * 6 * n3;
+    if (g + 1 < g1) {
+      // next tracer's neighbourhood: nine cache lines per warp, requested while this tracer is computed
+      const double *__restrict__ Tn1 = T + n3;
+      pf_l2(Tn1 + c); pf_l2(Tn1 + c + sj); pf_l2(Tn1 + c - sj); pf_l2(Tn1 + cu); pf_l2(Tn1 + cd);
+      pf_l2(Tn1 + cu + sj); pf_l2(Tn1 + cu - sj); pf_l2(Tn1 + cd + sj); pf_l2(Tn1 + cd - sj);
+    }
     // t(tau-1): the 15-point neighbourhood
     const double Tc = T[c], Te = T[c + 1], Tw = T[c - 1], Tn = T[c + sj], Ts = T[c - sj], Tu = T[cu], Td = T[cd];
     const double Teu = T[cu + 1], Twu = T[cu - 1], Tnu = T[cu + sj], Tsu = T[cu - sj];
