@@ -253,28 +253,32 @@ __global__ void __launch_bounds__(32 * MAXW, 1) k_fct_march(const DevView v, int
         const double tz = (fb_u - fb_d) * dcfz;
         tlo = Tc - twodt * (tx + ty + tz) * m;
       }
-      double rxp, rxm, rzp, rzm;
+      double rxp = 0.0, rxm = 0.0, rzp = 0.0, rzm = 0.0;
+      // A land cell has tmask = 0 in front of Q+-, so its six ratios are exactly zero whatever the fluxes are
+      // (:688-691, 764-767, 952-955).  Warps whose 32 cells are all land (continents, levels below the bottom) skip the
+      // three limiters -- two thirds of the work of a row -- without diverging; everything else runs as usual.
+      const bool any_ocean = __any_sync(0xffffffffu, kmc >= k);
       // ---- x (:635-694): flxlft = anti_fe(i-1), flxrgt = anti_fe(i) ----
       const double a_w = ue_w * (Uw + Uc) - lo_w;
       const double a_e = ue_c * (Uc + Ue) - lo_e;
-      {
+      if (any_ocean) {
         // mask*(average) + (1-mask)*t_lo with a 0/1 mask is one of the two terms (up to the sign of a zero): select it
         const double fxa = mw_b ? 0.5 * (Uw + Uc) : tlo;
         const double fxb = me_b ? 0.5 * (Uc + Ue) : tlo;
         ratio(c2dtts, dcfx, a_w, a_e, fxa, fxb, tlo, m, rxp, rxm);
       }
       // ---- y (:714-770): flxlft = anti_fn(j-1) (= 0 for row 1, :475), flxrgt = anti_fn(j) ----
-      {
+      a_n = vn_c * (Uc + Un) - lo_n;
+      if (any_ocean) {
         const double fxa = ms_b ? 0.5 * (Um + Uc) : tlo;
         const double fxb = mn_b ? 0.5 * (Uc + Un) : tlo;
-        a_n = vn_c * (Uc + Un) - lo_n;
         ratio(c2dtts, dcfy, a_n_p, a_n, fxa, fxb, tlo, m, ryp, rym);
       }
       // ---- z (:786-958): flxlft = anti_fb(k), flxrgt = anti_fb(k-1) ----
       // anti_fb(i,0,j) = adv_vbt(i,0,j)*c2*t(i,1,j,taum1) (:617); anti_fb(i,km,j) = 0
       const double a_d = wb_d * (Uc + Ud) - lo_d * m;
       const double a_u = wb_u * (Uu + Uc) - lo_u * mu;
-      {
+      if (any_ocean) {
         const double fxa = (k > 1 && kmc >= k - 1) ? 0.5 * (Uu + Uc) : tlo;
         const double fxb = (k < km && kmc >= k + 1) ? 0.5 * (Uc + Ud) : tlo;
         ratio(c2dtts, dcfz, (k == km) ? 0.0 : a_d, (k == 1) ? wb_u * 2.0 * Tc : a_u, fxa, fxb, tlo, m, rzp, rzm);

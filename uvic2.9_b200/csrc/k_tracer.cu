@@ -163,6 +163,13 @@ __global__ void __launch_bounds__(UPD_T) k_update(const DevView v, int nbase, in
   const int cer = (i == v.imt - 1) ? c - (v.imt - 3) : c + 1;   // cell i+1 -> 2
   // masks (09/mom/loadmw.F:60-77)
   const int kb = v.kmt[q.c2];
+  if (MODE == 2 && __all_sync(__activemask(), kb < k)) {
+    // A warp of land cells (continents, levels below the bottom): the implicit solve multiplies the tendency by
+    // tmask = 0 (09/mom/tracer.F:1114-1127), so nothing here can reach t(tau+1).  Leave a clean zero and move on.
+    const int g0z = blockIdx.y * tch, g1z = min(g0z + tch, ng);
+    for (int g = g0z; g < g1z; g++) v.t_p1[(long long)(nbase + g) * n3 + c] = 0.0;
+    return;
+  }
   const double m = (kb >= k) ? 1.0 : 0.0, mu = (kb >= k - 1) ? 1.0 : 0.0;
   const double mw = (v.kmt[q.c2 - 1] >= k) ? 1.0 : 0.0, me = (v.kmt[q.c2 + 1] >= k) ? 1.0 : 0.0;
   const double ms = (v.kmt[q.c2 - v.imt] >= k) ? 1.0 : 0.0, mn = (v.kmt[q.c2 + v.imt] >= k) ? 1.0 : 0.0;
