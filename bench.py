@@ -96,7 +96,7 @@ def kernel_bytes_per_launch(name, case, ctx, ngroup_launch):
         "k_fct_rfac": cells_r * (72 * g + 24),
         "k_fct_apply": cells * (80 * g + 24),
         "k_update": cells * (80 * g + 176),
-        "k_invtri": cells * (32 * g + 24),             # tendency, t(tau-1), source in; t(tau+1) out; a, e, bet
+        "k_invtri": ocean * (24 * g + 24) + cells * 8 * g,   # wet cells: tendency, t(tau-1), source, a, e, bet in; all cells: t(tau+1) out
         "k_convect_ts": cells * 32,                    # T,S read + written (worst case)
         "k_convect_tr": cells * 16 * (case.nt - 2),    # worst case: every other tracer read + written
         "k_mobi_column": ocean * 8 * (37 + 15 + 35),   # 37 tracers + 15 pre-pass fields in; 35 sources out

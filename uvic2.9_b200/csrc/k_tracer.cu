@@ -459,11 +459,14 @@ __global__ void __launch_bounds__(INV_T) k_invtri(const DevView v, int nbase, in
     for (int q = 0; q < INV_KC; q++) {
       const int k = min(k0 + q, km);
       const int c = c1 + (k - 1) * sk;
-      pp[q] = z[c];
-      tt[q] = tm1[c];
-      ss[q] = srcp ? srcp[c] : 0.0;
-      aa[q] = tri_a[c];
-      bb[q] = tri_bet[c];
+      // below the bottom (and on land) bet = tmask/(...) = 0 and f = (...)*tmask = 0: z(k) = 0 whatever the inputs are,
+      // so their loads are not issued
+      const bool wet = k <= kb;
+      pp[q] = wet ? z[c] : 0.0;
+      tt[q] = wet ? tm1[c] : 0.0;
+      ss[q] = (wet && srcp) ? srcp[c] : 0.0;
+      aa[q] = wet ? tri_a[c] : 0.0;
+      bb[q] = wet ? tri_bet[c] : 0.0;
       td[q] = dtx[k - 1];
     }
     asm volatile("" ::: "memory");   // keep the chunk's loads together, ahead of the recurrence
@@ -501,7 +504,7 @@ __global__ void __launch_bounds__(INV_T) k_invtri(const DevView v, int nbase, in
 #pragma unroll
     for (int q = 0; q < INV_KC; q++) {
       const int k = max(k0 - q, 1);
-      ee[q] = tri_e[c1 + k * sk];
+      ee[q] = (k < kb) ? tri_e[c1 + k * sk] : 0.0;   // e(k+1) = c(k)*bet(k) = 0 from the bottom level down
     }
     asm volatile("" ::: "memory");
 #pragma unroll
