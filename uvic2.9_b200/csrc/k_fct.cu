@@ -59,6 +59,9 @@ struct FmGeom {
 template <int MAXW>
 __global__ void __launch_bounds__(32 * MAXW, 1) k_fct_march(const DevView v, int nbase, int ng, FmGeom gm) {
   extern __shared__ __align__(16) unsigned char fm_raw[];
+  // skipping the face-flux phase of land warps and the write of land cells pays where registers are not the limit
+  // (128-register variants); the 96-register variant (columns of <= 20 levels in one tile) is faster without (measured)
+  constexpr bool LAND_SKIP = (MAXW <= 16);
   // ---- which piece of the domain ----
   int bid = blockIdx.x;
   const int g = bid % ng; bid /= ng;
@@ -194,14 +197,15 @@ __global__ void __launch_bounds__(32 * MAXW, 1) k_fct_march(const DevView v, int
   for (int r = rA0; r <= jb + 1; r++) {
     const bool doA = r <= jmt - 1;
     stage(r + 3);
-    const bool will_out = (r - 1 >= ja) && (r - 1 <= jb) && out_cell;
+    // land cells are not written: the implicit solve multiplies the tendency by tmask (09/mom/tracer.F:1114-1127)
+    const bool will_out = (r - 1 >= ja) && (r - 1 <= jb) && out_cell && (!LAND_SKIP || kmc_p >= k);
     const int cj = (r - 1 - v.jbase) * sj + g_own;
     double pd = 0.0;
     if (will_out) pd = P[cj];   // diffusive tendency of row r-1
     // ---- x and z faces of row r-1 (ratios of the neighbours became visible at the last barrier) ----
-    double tx_p, tz_p;
+    double tx_p = 0.0, tz_p = 0.0;
     const double m_p = (kmc_p >= k) ? 1.0 : 0.0;   // tmask(i,k,r-1)
-    {
+    if (!LAND_SKIP || __any_sync(0xffffffffu, kmc_p >= k)) {     // a warp of land cells has no face flux anybody reads
       const double *R = sR + ((r - 1) & 1) * (4 * FM_MAXW * 32);
       // east / west faces: Cpos(f) = min(Rpl(f+1),Rmn(f)), Cneg(f) = min(Rpl(f),Rmn(f+1)) (:698-701); no mask (:987)
       // the west face of a cell is the east face of its western neighbour: one lane over (lane 0 is a halo cell)
