@@ -116,11 +116,6 @@ def kernel_bytes_per_launch(name, case, ctx, ngroup_launch):
 
 PER_TRACER_KERNELS = ("k_fct_march", "k_diffuse", "k_fct_tlo", "k_fct_rfac", "k_fct_apply", "k_update", "k_invtri")
 
-# FP64-pipe instructions per cell*tracer of the flux kernels (thread level; from the committed ncu captures,
-# sm__pipe_fp64_cycles_active x duration: profiles/r01_ncu_*): these kernels are FP64-issue bound, not HBM bound
-DP_INST_PER_UNIT = {"k_fct_march": 309.0, "k_diffuse": 177.0}
-
-
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
 
@@ -395,7 +390,20 @@ def main():
             tt = torch.tensor([ms_e], device=f"cuda:{local}", dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms_e = float(tt.item())
+        # what the link gives: one pinned D2H / H2D copy of the size the step moves, timed alone
+        def link_gbs(dst, src):
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            for _ in range(5):
+                dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            return 5 * src.numel() * 8 / (time.perf_counter() - t1) / 1e9
+
+        d_tmp = torch.empty(h_out.shape, dtype=torch.float64, device=f"cuda:{local}")
+        pcie = {"d2h_gbs": round(link_gbs(h_out, d_tmp), 1), "h2d_gbs": round(link_gbs(d_tmp, h_out), 1)}
+        del d_tmp
         e2e = {"value": units / (ms_e / a.steps * 1e-3) / 1e9, "unit": "G cell*tracer/s", "h2d_bytes_per_step": int(h2d),
+               "pcie": pcie, "d2h_floor_ms": round(d2h / (pcie["d2h_gbs"] * 1e9) * 1e3, 3),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e / a.steps,
                "note": "uvic_b200_tracer_step: adv velocities + stf/btf H2D from pinned memory and the whole t(tau+1) D2H every step, "
                        "copies on their own streams under the kernels; MOBI of step n+1 runs while t(tau+1) of step n travels"}
@@ -486,17 +494,18 @@ def main():
                 "bytes_per_launch": top_bytes, "us_per_launch": top["us_per_launch"],
                 "note": "compulsory bytes of the launch as designed / CUDA-event time; traffic = ncu dram bytes of one launch "
                         "(profiles/r01_ncu_traffic.json)"}
-    # the flux kernels are FP64-issue bound: report them against the FP64 pipe as well (148 SMs x 64 lanes x SM clock)
-    sm_mhz = (clk or {}).get("sm_mhz") or 1965.0
-    fp64_peak = 148 * 64 * sm_mhz * 1e6 / 1e12
-    units_rank = (case.imt - 2) * (ctx.jhi - ctx.jlo + 1) * case.km * case.nt
-    for kq in kern:
-        dp = DP_INST_PER_UNIT.get(kq["kernel"])
-        if dp:
-            ms_step_k = kq["ms_total"] / a.steps
-            kq["fp64_tinst_s"] = round(dp * units_rank / (ms_step_k * 1e-3) / 1e12, 3)
-            kq["fp64_frac"] = round(kq["fp64_tinst_s"] / fp64_peak, 4)
-    roofline["fp64_peak_tinst_s"] = round(fp64_peak, 2)
+    # The flux kernels are FP64-issue bound, not HBM bound: attach what the committed `ncu --set full` capture of this
+    # workload measured for each kernel (FP64-pipe and issue-slot utilisation, DRAM bytes, registers).  Numbers taken
+    # under the profiler, quoted as such; the times above are CUDA events of this run.
+    kpath = os.path.join(ROOT, "profiles", "r01_ncu_kernels.json")
+    if os.path.exists(kpath):
+        nk = json.load(open(kpath)).get(a.workload) or {}
+        for kq in kern:
+            if kq["kernel"] in nk:
+                kq["ncu"] = nk[kq["kernel"]]
+        if top["kernel"] in nk:
+            roofline["fp64_pipe_pct"] = nk[top["kernel"]].get("fp64_pipe_pct")
+            roofline["issue_slot_pct"] = nk[top["kernel"]].get("issue_slot_pct")
     step_bytes = algorithmic_step_bytes(case, w["mobi"]) / world
     step_hbm = {"algorithmic_bytes_per_step": step_bytes, "achieved": step_bytes / (ms_step * 1e-3) / 1e9, "peak": peak,
                 "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak, "unit": "GB/s",

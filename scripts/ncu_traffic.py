@@ -13,10 +13,16 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+OUT2 = os.path.join(ROOT, "profiles", "r01_ncu_kernels.json")
+EXTRA = {"gpu__time_duration.sum": "duration", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active": "fp64_pipe_pct",
+         "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_slot_pct",
+         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct", "launch__registers_per_thread": "registers",
+         "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct", "smsp__inst_executed.sum": "warp_instructions"}
 SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 NAMES = {"k_update<2>": "k_diffuse", "k_update<3>": "k_fct_apply", "k_update<1>": "k_update", "k_update<0>": "k_update"}
 
 out = json.load(open(OUT)) if os.path.exists(OUT) else {}
+out2 = json.load(open(OUT2)) if os.path.exists(OUT2) else {}
 for arg in sys.argv[1:]:
     wl, rep = arg.split("=", 1)
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -31,5 +37,15 @@ for arg in sys.argv[1:]:
         for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             tot += float(r[ix[m]]) * SCALE[units[ix[m]]]
         out.setdefault(wl, {})[short] = int(tot)
+        rec = {"dram_bytes": int(tot)}
+        for m, key in EXTRA.items():
+            if m in ix:
+                val = float(r[ix[m]])
+                if key == "duration":
+                    rec["duration_us"] = round(val * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(units[ix[m]], 1.0), 2)
+                else:
+                    rec[key] = round(val, 2)
+        out2.setdefault(wl, {})[short] = rec
 json.dump(out, open(OUT, "w"), indent=1, sort_keys=True)
+json.dump(out2, open(OUT2, "w"), indent=1, sort_keys=True)
 print(json.dumps(out, indent=1, sort_keys=True))
