@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(32 * MAXW, 1) k_fct_march(const DevView v, int
   const int ig = i0 - 1 + lane;
   const int iw = wrap_i(ig);
   const bool out_cell = lane >= 1 && lane <= FM_TI && ig <= imt - 1 && k >= k0 && k <= k1;
+  const bool halo_k = LAND_SKIP && (k < k0 || k > k1);   // halo level of the k tile: only its R+-z are needed (by the level next to it)
 
   // ---- shared memory ----
   const int plane = gm.nrows * FM_W;                // plane row p <-> level ka_lo - 1 + p
@@ -205,7 +206,7 @@ __global__ void __launch_bounds__(32 * MAXW, 1) k_fct_march(const DevView v, int
     // ---- x and z faces of row r-1 (ratios of the neighbours became visible at the last barrier) ----
     double tx_p = 0.0, tz_p = 0.0;
     const double m_p = (kmc_p >= k) ? 1.0 : 0.0;   // tmask(i,k,r-1)
-    if (!LAND_SKIP || __any_sync(0xffffffffu, kmc_p >= k)) {     // a warp of land cells has no face flux anybody reads
+    if (!halo_k && (!LAND_SKIP || __any_sync(0xffffffffu, kmc_p >= k))) {   // a warp of land cells, or a halo level, has no face flux anybody reads
       const double *R = sR + ((r - 1) & 1) * (4 * FM_MAXW * 32);
       // east / west faces: Cpos(f) = min(Rpl(f+1),Rmn(f)), Cneg(f) = min(Rpl(f),Rmn(f+1)) (:698-701); no mask (:987)
       // the west face of a cell is the east face of its western neighbour: one lane over (lane 0 is a halo cell)
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(32 * MAXW, 1) k_fct_march(const DevView v, int
       // ---- x (:635-694): flxlft = anti_fe(i-1), flxrgt = anti_fe(i) ----
       const double a_w = ue_w * (Uw + Uc) - lo_w;
       const double a_e = ue_c * (Uc + Ue) - lo_e;
-      if (any_ocean) {
+      if (any_ocean && !halo_k) {
         // mask*(average) + (1-mask)*t_lo with a 0/1 mask is one of the two terms (up to the sign of a zero): select it
         const double fxa = mw_b ? 0.5 * (Uw + Uc) : tlo;
         const double fxb = me_b ? 0.5 * (Uc + Ue) : tlo;
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(32 * MAXW, 1) k_fct_march(const DevView v, int
       }
       // ---- y (:714-770): flxlft = anti_fn(j-1) (= 0 for row 1, :475), flxrgt = anti_fn(j) ----
       a_n = vn_c * (Uc + Un) - lo_n;
-      if (any_ocean) {
+      if (any_ocean && !halo_k) {
         const double fxa = ms_b ? 0.5 * (Um + Uc) : tlo;
         const double fxb = mn_b ? 0.5 * (Uc + Un) : tlo;
         ratio(c2dtts, dcfy, a_n_p, a_n, fxa, fxb, tlo, m, ryp, rym);

@@ -286,7 +286,7 @@ __device__ __forceinline__ double evans_parslow(double gl_x, double gd, double f
 // oxygen dependent rate factors (09/mom/mobi.F:775-835), the pre-loop light harvesting and
 // Evans-Parslow integrals of mobi_src (:1928-2003), and the oxygen / nitrate switches of
 // the denitrification terms (:1035-1046, 1301-1322).
-__global__ void __launch_bounds__(128, 5) k_mobi_cell(const DevView v) {
+__global__ void __launch_bounds__(128, 4) k_mobi_cell(const DevView v) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int ni = v.imt - 2, nrow = v.jhi - v.jlo + 1;
   if (idx >= (long long)ni * v.km * nrow) return;
