@@ -494,6 +494,16 @@ def main():
                 "bytes_per_launch": top_bytes, "us_per_launch": top["us_per_launch"],
                 "note": "compulsory bytes of the launch as designed / CUDA-event time; traffic = ncu dram bytes of one launch "
                         "(profiles/r01_ncu_traffic.json)"}
+    # the same roofline arithmetic for the four largest kernels (the top one runs beside the main stream on a third of
+    # the SMs in production; the largest kernel of the main stream is the marching FCT)
+    tr_all = {}
+    if os.path.exists(tpath):
+        tr_all = json.load(open(tpath)).get(a.workload) or {}
+    roofline_top = []
+    for kq in kern[:4]:
+        if kq["gbs"]:
+            roofline_top.append({"kernel": kq["kernel"], "bound": "hbm", "achieved": kq["gbs"], "peak": peak, "unit": "GB/s",
+                                 "frac": round(kq["gbs"] / peak, 4), "traffic": tr_all.get(kq["kernel"]), "share": kq["share"]})
     # The flux kernels are FP64-issue bound, not HBM bound: attach what the committed `ncu --set full` capture of this
     # workload measured for each kernel (FP64-pipe and issue-slot utilisation, DRAM bytes, registers).  Numbers taken
     # under the profiler, quoted as such; the times above are CUDA events of this run.
@@ -538,7 +548,7 @@ def main():
                    "l2": "per-step working set (3 time levels + sources + coefficients + FCT scratch) exceeds the 126 MB L2; no explicit flush",
                    "time_stepping": "leapfrog with a forward mixing step every 16th (run/control.in nmix=16)"},
         "sim_years_per_day": 86400.0 / (292.0 * ms_step * 1e-3),
-        "roofline": roofline, "step_hbm": step_hbm, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "roofline_top": roofline_top, "step_hbm": step_hbm, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": clk, "ms_per_step_serialised_profile_pass": ms_prof / a.steps, "kernels": kern, "inventory_check": {"finite": bool(np.isfinite(inv).all())},
     }
     _emit(line)
