@@ -568,6 +568,11 @@ int uvic_b200_tracer_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si, cons
                           const double *adv_vet, const double *adv_vnt, const double *adv_vbt, const double *stf,
                           const double *btf, double *t_taup1) {
   DevView &v = ctx->v;
+  static const bool trace = getenv("UVIC_B200_E2E_TRACE") != nullptr;   // phase times of the call on stderr (diagnostics)
+  static cudaEvent_t tev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (trace && !tev[0])
+    for (auto &e : tev) cudaEventCreate(&e);
+  if (trace) cudaEventRecord(tev[0], ctx->stream);
   if (t_taum1 && uvic_b200_upload_t(ctx, -1, t_taum1)) return 1;
   if (t_tau && uvic_b200_upload_t(ctx, 0, t_tau)) return 1;
   // velocities and vertical b.c. travel on the input copy stream while the kernels that do not need them
@@ -581,10 +586,12 @@ int uvic_b200_tracer_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si, cons
   if (stf) CK(cudaMemcpyAsync(v.stf, stf, (size_t)v.n2 * v.nt * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
   if (btf) CK(cudaMemcpyAsync(v.btf, btf, (size_t)v.n2 * v.nt * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
   CK(cudaEventRecord(ctx->h2d_event, ctx->copy_in));
+  if (trace) cudaEventRecord(tev[1], ctx->copy_in);
   set_step(ctx, si);
   begin_mobi(ctx, si);
   launch_isopyc_coef(ctx);
   launch_vmixc(ctx);
+  if (trace) cudaEventRecord(tev[2], ctx->stream);
   CK(cudaStreamWaitEvent(ctx->stream, ctx->h2d_event, 0));
   launch_isopyc_vel(ctx);
   CK(cudaGetLastError());
@@ -594,9 +601,16 @@ int uvic_b200_tracer_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si, cons
   int rc = uvic_b200_tracer(ctx, si);
   ctx->d2h_dst = nullptr;
   if (rc) return rc;
+  if (trace) { cudaEventRecord(tev[3], ctx->stream); cudaEventRecord(tev[4], ctx->copy_out); }
   CK(cudaStreamSynchronize(ctx->copy_out));
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaGetLastError());
+  if (trace) {
+    float a = 0, b = 0, c2 = 0, d = 0;
+    cudaEventElapsedTime(&a, tev[0], tev[1]); cudaEventElapsedTime(&b, tev[0], tev[2]);
+    cudaEventElapsedTime(&c2, tev[0], tev[3]); cudaEventElapsedTime(&d, tev[0], tev[4]);
+    fprintf(stderr, "[uvic_b200 e2e] h2d done %.3f ms, coefficients done %.3f, kernels done %.3f, d2h done %.3f\n", a, b, c2, d);
+  }
   return 0;
 }
 

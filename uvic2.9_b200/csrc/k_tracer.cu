@@ -703,11 +703,20 @@ void launch_tracer(uvic_b200_ctx *c, const uvic_b200_stepinfo *si) {
   std::vector<std::pair<int, int>> batches;
   if (c->d2h_dst && v.nt > 2) {
     batches.push_back({0, 2});
-    // (the coupled entry point only returns T and S: the other tracers then go in as few batches as possible)
-    const int rest = v.nt - 2, nb = (c->d2h_ntr <= 2) ? 1 : std::min(rest, std::max(3, (rest + v.ngroup - 1) / v.ngroup));
-    for (int b = 0; b < nb; b++) {
-      const int lo = 2 + (int)((long long)rest * b / nb), hi = 2 + (int)((long long)rest * (b + 1) / nb);
-      for (int q = lo; q < hi; q += v.ngroup) batches.push_back({q, std::min(v.ngroup, hi - q)});
+    if (c->d2h_ntr <= 2) {
+      // the coupled entry point only returns T and S: the other tracers go in as few batches as possible
+      for (int q = 2; q < v.nt; q += v.ngroup) batches.push_back({q, std::min(v.ngroup, v.nt - q)});
+    } else {
+      // Every finished batch streams to the host while the next one computes, and the link (not the kernels) is what
+      // the call waits for: small batches first, so the copy engine starts early and then never runs dry; later
+      // batches grow (kernels are more efficient on many tracers) but stay short enough to keep the tail small.
+      int q = 2, sz = 3;
+      while (q < v.nt) {
+        const int n = std::min(std::min(sz, v.ngroup), v.nt - q);
+        batches.push_back({q, n});
+        q += n;
+        sz = std::min(sz * 2, 10);
+      }
     }
   } else {
     for (int nbase = 0; nbase < v.nt; nbase += v.ngroup) batches.push_back({nbase, std::min(v.ngroup, v.nt - nbase)});
