@@ -392,6 +392,7 @@ def main():
             ms_e = float(tt.item())
         # what the link gives: one pinned D2H / H2D copy of the size the step moves, timed alone
         def link_gbs(dst, src):
+            dst.copy_(src, non_blocking=True)   # untimed first touch
             torch.cuda.synchronize()
             t1 = time.perf_counter()
             for _ in range(5):

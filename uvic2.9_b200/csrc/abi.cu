@@ -82,7 +82,7 @@ int uvic_b200_create(const uvic_b200_dims *d, const uvic_b200_grid *g, const uvi
   ctx->mobi_dtnpzd = 0.0;
   ctx->src_buf[0] = ctx->src_buf[1] = nullptr; ctx->src_cur = 0;
   ctx->hint_valid = ctx->ahead_valid = false; ctx->ahead_tm1 = nullptr; ctx->ahead_buf = 0;
-  ctx->main_done_event = nullptr; ctx->copy_in = ctx->copy_out = nullptr; ctx->h2d_event = nullptr; ctx->d2h_dst = nullptr; ctx->d2h_ntr = 0;
+  ctx->main_done_event = nullptr; ctx->copy_in = ctx->copy_out = nullptr; ctx->h2d_event = nullptr; ctx->h2d_vbc_event = nullptr; ctx->vel_pending = false; ctx->d2h_dst = nullptr; ctx->d2h_ntr = 0;
   DevView &v = ctx->v;
   memset(&v, 0, sizeof v);
   v.imt = d->imt; v.jmt = d->jmt; v.km = d->km; v.nt = d->nt; v.nsrc = d->nsrc;
@@ -229,6 +229,7 @@ int uvic_b200_create(const uvic_b200_dims *d, const uvic_b200_grid *g, const uvi
   }
   CK(cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&ctx->h2d_event, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&ctx->h2d_vbc_event, cudaEventDisableTiming));
   CK(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
   {
@@ -285,6 +286,7 @@ int uvic_b200_destroy(uvic_b200_ctx *ctx) {
   for (auto e : ctx->src_ready) if (e) cudaEventDestroy(e);
   if (ctx->main_done_event) cudaEventDestroy(ctx->main_done_event);
   if (ctx->h2d_event) cudaEventDestroy(ctx->h2d_event);
+  if (ctx->h2d_vbc_event) cudaEventDestroy(ctx->h2d_vbc_event);
   if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
   if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
   for (auto e : ctx->ev_batch) cudaEventDestroy(e);
@@ -580,11 +582,14 @@ int uvic_b200_tracer_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si, cons
   // on the main stream (the previous step still reads these arrays)
   CK(cudaEventRecord(ctx->fork_event, ctx->stream));
   CK(cudaStreamWaitEvent(ctx->copy_in, ctx->fork_event, 0));
+  // the vertical b.c. first (the diffusion pass needs them), then the velocities (only the FCT needs them: launch_tracer
+  // waits for them, and runs the velocity part of isopyc, right before its first advection kernel)
+  if (stf) CK(cudaMemcpyAsync(v.stf, stf, (size_t)v.n2 * v.nt * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
+  if (btf) CK(cudaMemcpyAsync(v.btf, btf, (size_t)v.n2 * v.nt * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
+  CK(cudaEventRecord(ctx->h2d_vbc_event, ctx->copy_in));
   if (adv_vet) CK(cudaMemcpyAsync(v.adv_vet, adv_vet, (size_t)v.n3 * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
   if (adv_vnt) CK(cudaMemcpyAsync(v.adv_vnt, adv_vnt, (size_t)v.n3 * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
   if (adv_vbt) CK(cudaMemcpyAsync(v.adv_vbt, adv_vbt, (size_t)v.n3z * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
-  if (stf) CK(cudaMemcpyAsync(v.stf, stf, (size_t)v.n2 * v.nt * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
-  if (btf) CK(cudaMemcpyAsync(v.btf, btf, (size_t)v.n2 * v.nt * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
   CK(cudaEventRecord(ctx->h2d_event, ctx->copy_in));
   if (trace) cudaEventRecord(tev[1], ctx->copy_in);
   set_step(ctx, si);
@@ -592,8 +597,8 @@ int uvic_b200_tracer_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si, cons
   launch_isopyc_coef(ctx);
   launch_vmixc(ctx);
   if (trace) cudaEventRecord(tev[2], ctx->stream);
-  CK(cudaStreamWaitEvent(ctx->stream, ctx->h2d_event, 0));
-  launch_isopyc_vel(ctx);
+  CK(cudaStreamWaitEvent(ctx->stream, ctx->h2d_vbc_event, 0));
+  ctx->vel_pending = true;
   CK(cudaGetLastError());
   // finished tracer batches stream to the host while the next batch computes (launch_tracer)
   ctx->d2h_dst = t_taup1;
@@ -626,19 +631,20 @@ int uvic_b200_tracer_step_coupled(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *
   if (ntspos < 1) return fail(ctx, "tracer_step_coupled: ntspos must be >= 1");
   CK(cudaEventRecord(ctx->fork_event, ctx->stream));
   CK(cudaStreamWaitEvent(ctx->copy_in, ctx->fork_event, 0));
+  if (sbc_in) CK(cudaMemcpyAsync(v.sbc, sbc_in, (size_t)v.n2 * v.numsbc * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
+  if (bhf) CK(cudaMemcpyAsync(v.bhf, bhf, (size_t)v.n2 * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
+  CK(cudaEventRecord(ctx->h2d_vbc_event, ctx->copy_in));
   if (adv_vet) CK(cudaMemcpyAsync(v.adv_vet, adv_vet, (size_t)v.n3 * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
   if (adv_vnt) CK(cudaMemcpyAsync(v.adv_vnt, adv_vnt, (size_t)v.n3 * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
   if (adv_vbt) CK(cudaMemcpyAsync(v.adv_vbt, adv_vbt, (size_t)v.n3z * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
-  if (sbc_in) CK(cudaMemcpyAsync(v.sbc, sbc_in, (size_t)v.n2 * v.numsbc * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
-  if (bhf) CK(cudaMemcpyAsync(v.bhf, bhf, (size_t)v.n2 * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
   CK(cudaEventRecord(ctx->h2d_event, ctx->copy_in));
   set_step(ctx, si);
   begin_mobi(ctx, si);
   launch_isopyc_coef(ctx);
   launch_vmixc(ctx);
-  CK(cudaStreamWaitEvent(ctx->stream, ctx->h2d_event, 0));
-  launch_isopyc_vel(ctx);
+  CK(cudaStreamWaitEvent(ctx->stream, ctx->h2d_vbc_event, 0));
   launch_setvbc(ctx);                                  // call setvbc, source/mom/mom.F:360
+  ctx->vel_pending = true;                             // velocity part of isopyc: launch_tracer, before the first FCT kernel
   CK(cudaGetLastError());
   ctx->d2h_dst = ts_taup1;
   ctx->d2h_ntr = 2;

@@ -731,12 +731,22 @@ void launch_tracer(uvic_b200_ctx *c, const uvic_b200_stepinfo *si) {
     int tch = (ng + nchunk - 1) / nchunk;
     nchunk = (ng + tch - 1) / tch;
     dim3 gc(cdiv(ncell_c, UPD_T), nchunk);
+    auto velocities = [&]() {
+      // host-buffer entry points: the advective velocities were still travelling while the coefficient kernels and the
+      // diffusion pass ran; the kernels below are the first that need them
+      if (!c->vel_pending) return;
+      cudaStreamWaitEvent(c->stream, c->h2d_event, 0);
+      launch_isopyc_vel(c);
+      c->vel_pending = false;
+    };
     if (v.fct) {
       const int variant = fct_variant();
       if (variant == 0) {
         KLAUNCH("k_diffuse", k_update<2>, gc, UPD_T, v, nbase, ng, tch, v.jlo, nrow_c);
+        velocities();
         launch_fct_march(c, nbase, ng);
       } else {
+        velocities();
         dim3 gr(cdiv(ncell_r, 256), nchunk);
         KLAUNCH("k_fct_rfac", k_fct_rfac, gr, 256, v, nbase, ng, tch, jf_r, nrow_r);
         if (variant == 1) {
@@ -747,6 +757,7 @@ void launch_tracer(uvic_b200_ctx *c, const uvic_b200_stepinfo *si) {
         }
       }
     } else {
+      velocities();
       KLAUNCH("k_update", k_update<0>, gc, UPD_T, v, nbase, ng, tch, v.jlo, nrow_c);
     }
     // the source term enters in k_invtri: the first batch with a sourced tracer waits for MOBI
