@@ -135,6 +135,14 @@ int uvic_b200_setvbc(uvic_b200_ctx *ctx);   /* call setvbc (source/mom/mom.F:360
  * t(tau+1) the last uvic_b200_tracer produced; eots/osegs/osege/ntspos are the switches of source/common/switch.h */
 int uvic_b200_set_sbc(uvic_b200_ctx *ctx, int eots, int osegs, int osege, int ntspos);
 
+/* Time averages of the tracers on the device: the tracer part of avgvar / avgout
+ * (09/mom/timeavgs.F:206-375, 398-420; avgvar is called from 09/mom/diag.F:138-146 with t(tau) on timavgperts steps) on
+ * the default averaging grid of avgset (the whole model grid).  accumulate adds t(tau) and stf (less vflux*gaost(n) for
+ * all tracers but T and S; NULL = no virtual flux) of the owned rows to running sums; fetch returns rnavgt*sum
+ * (avg_t(imt,km,jl,nt), avg_stf(imt,jl,nt); NULL = skip), the step count, and optionally starts a new period. */
+int uvic_b200_tavg_accumulate(uvic_b200_ctx *ctx, const double *vflux, const double *gaost);
+int uvic_b200_tavg_fetch(uvic_b200_ctx *ctx, double *avg_t, double *avg_stf, int32_t *navgts, int reset);
+
 int uvic_b200_rotate(uvic_b200_ctx *ctx);
 
 /* ---- the hot path, one entry per reference call site (device resident) ------------ */

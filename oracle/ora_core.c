@@ -73,6 +73,8 @@ ora_ctx *ora_create(int imt, int jmt, int km, int nt, int nsrc) {
 
   RD(dnswr, ij); RD(aice, ij); RD(hice, ij); RD(hsno, ij);
   RD(sg_bathy, n3); RD(fe_hydr, n3); RD(fe_atmdep, ij * 12);
+  RD(spbuf_t, n3 * nt); RD(avg_t, n3 * nt); RD(spbuf2_stf, ij * nt); RD(avg_stf, ij * nt);
+  RD(vflux, ij); RD(gaost, nt);
   c->numsbc = 2 * nt + 4;
   RD(sbc, ij * c->numsbc); RD(bhf, ij);
   RI(sbc_flx_index, nt); RI(trsbcindex, nt);
@@ -110,7 +112,7 @@ const char *ora_array_name(const ora_ctx *c, int idx) { return c->arr[idx].name;
   X(zetar) X(ogamma) X(gravrho0r) X(relyr) X(co2ccn)
 #define ISCALARS(X) \
   X(fct) X(isopycmix) X(tidal_kv) X(do_convect) X(do_mobi) X(timavgperts) X(do_filter) \
-  X(jfrst) X(jft1) X(jft2) X(jft0) X(eots) X(osegs) X(osege) X(ntspos)
+  X(jfrst) X(jft1) X(jft2) X(jft0) X(eots) X(osegs) X(osege) X(ntspos) X(navgts)
 
 int ora_set_scalar(ora_ctx *c, const char *name, double v) {
 #define X(f) if (strcmp(name, #f) == 0) { c->f = v; return 0; }

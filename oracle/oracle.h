@@ -141,6 +141,12 @@ typedef struct ora_ctx {
   int32_t *trsbcindex;     /* (nt) 1-based sbc slot of tracer n's surface accumulator, 0 = none */
   int eots, osegs, osege, ntspos;   /* source/common/switch.h */
 
+  /* ---- time averages of the tracers (09/mom/timeavgs.F) ---- */
+  double *spbuf_t, *avg_t;       /* (imt,km,jmt,nt) running sums / means of t(tau) */
+  double *spbuf2_stf, *avg_stf;  /* (imt,jmt,nt) running sums / means of the surface tracer flux */
+  double *vflux, *gaost;         /* (imt,jmt) virtual flux, (nt) its tracer factors */
+  int navgts;
+
   /* ---- Fourier filter (source/common/index.h) ---- */
   int do_filter;
   int jfrst, jft1, jft2, jft0;  /* source/common/setcom.F */
@@ -170,6 +176,8 @@ void ora_tracer(ora_ctx *c);                           /* 09/mom/tracer.F:214-13
 void ora_diag_tbar(ora_ctx *c, int n);                 /* 09/mom/tracer.F:1516-1565 */
 void ora_mobi_columns(ora_ctx *c);                     /* 09/mom/tracer.F:310-545,848-867 */
 void ora_filt(ora_ctx *c);                             /* source/common/filt.F */
+void ora_avgvar(ora_ctx *c);                           /* 09/mom/timeavgs.F:206-375 (tracer part) */
+void ora_avgout(ora_ctx *c);                           /* 09/mom/timeavgs.F:398-420 (time means) */
 void ora_setvbc(ora_ctx *c);                           /* 09/mom/setvbc.F:60-140 */
 void ora_set_sbc(ora_ctx *c);                          /* 09/mom/set_sbc.F:36-83 via 09/mom/tracer.F:1270-1288 */
 

@@ -331,3 +331,39 @@ def test_setvbc_and_set_sbc_semantics(pkg):
         assert np.array_equal(got[~ocean], land[~ocean])
     assert np.array_equal(sbc[3 - 1], before[3 - 1])      # a slot nobody owns is untouched
     o.close()
+
+
+def test_time_average_semantics(pkg):
+    """09/mom/timeavgs.F avgvar / avgout, tracer part: running sums of t(tau) and of the surface tracer flux (less the
+    virtual flux for everything but T and S) over rows 2..jmt-1, divided by the number of accumulated steps."""
+    from helpers import make_oracle
+
+    case = pkg.synthetic.make_case(imt=18, jmt=14, km=5, nt=4, names=["temp", "salt", "p0", "p1"], seed=9)
+    o = make_oracle(case)
+    imt, jmt, km, nt = case.imt, case.jmt, case.km, case.nt
+    rng = np.random.default_rng(11)
+    t = o.t()
+    stf = o.arr("stf", (nt, jmt, imt))
+    vflux = o.arr("vflux", (jmt, imt))
+    vflux[...] = rng.standard_normal((jmt, imt))
+    gaost = np.array([9.0, 9.0, 0.5, 2.0])     # the entries of T and S must not be used
+    o.set("gaost", gaost)
+    ts, fs = [], []
+    for step in range(4):
+        t[1] = rng.standard_normal(t[1].shape)
+        stf[...] = rng.standard_normal(stf.shape)
+        ts.append(t[1].copy())
+        fs.append(stf.copy())
+        o.call("ora_avgvar")
+    o.call("ora_avgout")
+    avg_t = o.arr("avg_t", (nt, jmt, km, imt))
+    avg_f = o.arr("avg_stf", (nt, jmt, imt))
+    want_t = 0.25 * (((0.0 + ts[0]) + ts[1]) + ts[2] + ts[3])
+    assert np.array_equal(avg_t[:, 1:-1], want_t[:, 1:-1])
+    assert not avg_t[:, [0, -1]].any()          # rows 1 and jmt are not on the averaging grid
+    for n in range(nt):
+        acc = np.zeros((jmt, imt))
+        for f in fs:
+            acc = acc + f[n] - (vflux * gaost[n] if n >= 2 else 0.0)
+        assert np.array_equal(avg_f[n][1:-1], (0.25 * acc)[1:-1]), n
+    o.close()

@@ -387,3 +387,38 @@ def test_setvbc_and_set_sbc_on_device(pkg):
             assert relerr(got[acc[n] - 1][1:-1, 1:-1], ref[acc[n] - 1][1:-1, 1:-1]) <= TOL, n
     ctx.close()
     o.close()
+
+
+def test_time_averages_on_device(pkg):
+    """the tracer part of avgvar / avgout (09/mom/timeavgs.F:206-375, 398-420) on the device,
+    bit-exact against the oracle for uploaded t(tau) / stf, for one context and for two slabs."""
+    case = _case(pkg, imt=30, jmt=26, km=7, nt=5, seed=4)
+    nt, jmt, km, imt = case.nt, case.jmt, case.km, case.imt
+    rng = np.random.default_rng(5)
+    vflux = rng.standard_normal((jmt, imt))
+    gaost = rng.standard_normal(nt)
+    o = make_oracle(case)
+    o.arr("vflux", (jmt, imt))[...] = vflux
+    o.set("gaost", gaost)
+    ctxs = [_ctx(pkg, case), _ctx(pkg, case, jlo=2, jhi=12), _ctx(pkg, case, jlo=13, jhi=jmt - 1)]
+    for step in range(3):
+        tt = rng.standard_normal((nt, jmt, km, imt))
+        ff = rng.standard_normal((nt, jmt, imt))
+        o.t()[1] = tt
+        o.arr("stf", (nt, jmt, imt))[...] = ff
+        o.call("ora_avgvar")
+        for c in ctxs:
+            sl = slice(c.jbase - 1, c.jbase - 1 + c.jl)
+            c.upload_t(0, tt[:, sl])
+            c._ck(c.L.uvic_b200_upload_vbc(c.h, np.ascontiguousarray(ff[:, sl]).ctypes.data, None))
+            c.tavg_accumulate(vflux[sl], gaost)
+    o.call("ora_avgout")
+    ref_t, ref_f = o.arr("avg_t", (nt, jmt, km, imt)), o.arr("avg_stf", (nt, jmt, imt))
+    for c in ctxs:
+        avg_t, avg_f, n = c.tavg_fetch()
+        assert n == 3
+        lo, hi = c.jlo - c.jbase, c.jhi - c.jbase + 1
+        assert np.array_equal(avg_t[:, lo:hi], ref_t[:, c.jlo - 1:c.jhi])
+        assert np.array_equal(avg_f[:, lo:hi], ref_f[:, c.jlo - 1:c.jhi])
+        c.close()
+    o.close()

@@ -67,6 +67,7 @@ ABI_SYMBOLS = [
     "uvic_b200_hint_next_step", "uvic_b200_pin_host", "uvic_b200_unpin_host",
     "uvic_b200_sbc_setup", "uvic_b200_upload_sbc", "uvic_b200_upload_sbc_slot", "uvic_b200_download_sbc",
     "uvic_b200_download_sbc_slot", "uvic_b200_setvbc", "uvic_b200_set_sbc", "uvic_b200_tracer_step_coupled",
+    "uvic_b200_tavg_accumulate", "uvic_b200_tavg_fetch",
 ]
 
 _lib = None
@@ -125,6 +126,8 @@ def load_library():
     L.uvic_b200_download_sbc_slot.argtypes = [vp, C.c_int, vp]
     L.uvic_b200_setvbc.argtypes = [vp]
     L.uvic_b200_set_sbc.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.uvic_b200_tavg_accumulate.argtypes = [vp, vp, vp]
+    L.uvic_b200_tavg_fetch.argtypes = [vp, vp, vp, _c_int_p, C.c_int]
     L.uvic_b200_tracer_step_coupled.argtypes = [vp, C.POINTER(StepInfo)] + [vp] * 5 + [C.c_int] * 4 + [vp, vp]
     _lib = L
     return L
@@ -334,6 +337,23 @@ class TracerContext:
         self._ck(self.L.uvic_b200_tracer_step_coupled(self.h, C.byref(si), _vp(adv_vet), _vp(adv_vnt), _vp(adv_vbt), _vp(sbc_in),
                                                       _vp(bhf), int(eots), int(osegs), int(osege), int(ntspos), _vp(ts_taup1),
                                                       _vp(sbc_out)))
+
+    # ---- time averages (09/mom/timeavgs.F avgvar / avgout, tracer part) ----
+    def tavg_accumulate(self, vflux_local=None, gaost=None):
+        if vflux_local is not None:
+            vflux_local = np.ascontiguousarray(vflux_local, dtype=np.float64)
+            assert vflux_local.shape == (self.jl, self.imt)
+        if gaost is not None:
+            gaost = np.ascontiguousarray(gaost, dtype=np.float64)
+            assert gaost.shape == (self.nt,)
+        self._ck(self.L.uvic_b200_tavg_accumulate(self.h, _vp(vflux_local), _vp(gaost)))
+
+    def tavg_fetch(self, reset=True):
+        avg_t = np.empty(self.shape_t())
+        avg_stf = np.empty((self.nt, self.jl, self.imt))
+        n = C.c_int(0)
+        self._ck(self.L.uvic_b200_tavg_fetch(self.h, _vp(avg_t), _vp(avg_stf), C.byref(n), int(reset)))
+        return avg_t, avg_stf, n.value
 
     def set_sbc(self, eots=True, osegs=False, osege=False, ntspos=1):
         self._ck(self.L.uvic_b200_set_sbc(self.h, int(eots), int(osegs), int(osege), int(ntspos)))

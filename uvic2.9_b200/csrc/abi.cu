@@ -82,7 +82,8 @@ int uvic_b200_create(const uvic_b200_dims *d, const uvic_b200_grid *g, const uvi
   ctx->mobi_dtnpzd = 0.0;
   ctx->src_buf[0] = ctx->src_buf[1] = nullptr; ctx->src_cur = 0;
   ctx->hint_valid = ctx->ahead_valid = false; ctx->ahead_tm1 = nullptr; ctx->ahead_buf = 0;
-  ctx->main_done_event = nullptr; ctx->copy_in = ctx->copy_out = nullptr; ctx->h2d_event = nullptr; ctx->h2d_vbc_event = nullptr; ctx->vel_pending = false; ctx->d2h_dst = nullptr; ctx->d2h_ntr = 0;
+  ctx->main_done_event = nullptr; ctx->copy_in = ctx->copy_out = nullptr; ctx->h2d_event = nullptr; ctx->h2d_vbc_event = nullptr; ctx->vel_pending = false;
+  ctx->tavg_t = ctx->tavg_stf = ctx->tavg_tmp = ctx->tavg_vflux = ctx->tavg_gaost = nullptr; ctx->navgts = 0; ctx->d2h_dst = nullptr; ctx->d2h_ntr = 0;
   DevView &v = ctx->v;
   memset(&v, 0, sizeof v);
   v.imt = d->imt; v.jmt = d->jmt; v.km = d->km; v.nt = d->nt; v.nsrc = d->nsrc;
@@ -418,6 +419,56 @@ int uvic_b200_set_sbc(uvic_b200_ctx *ctx, int eots, int osegs, int osege, int nt
   if (!ctx->v.sbc) return fail(ctx, "set_sbc: call uvic_b200_sbc_setup first");
   if (ntspos < 1) return fail(ctx, "set_sbc: ntspos must be >= 1");
   launch_set_sbc(ctx, eots, osegs, osege, ntspos);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ---- time averages of the tracers on the device ----
+int uvic_b200_tavg_accumulate(uvic_b200_ctx *ctx, const double *vflux, const double *gaost) {
+  DevView &v = ctx->v;
+  if (!ctx->tavg_t) {
+    CK(cudaMalloc((void **)&ctx->tavg_t, (size_t)v.n3 * v.nt * sizeof(double)));
+    ctx->owned.push_back(ctx->tavg_t);
+    CK(cudaMalloc((void **)&ctx->tavg_stf, (size_t)v.n2 * v.nt * sizeof(double)));
+    ctx->owned.push_back(ctx->tavg_stf);
+    CK(cudaMalloc((void **)&ctx->tavg_tmp, (size_t)v.n3 * sizeof(double)));
+    ctx->owned.push_back(ctx->tavg_tmp);
+    CK(cudaMalloc((void **)&ctx->tavg_vflux, (size_t)v.n2 * sizeof(double)));
+    ctx->owned.push_back(ctx->tavg_vflux);
+    CK(cudaMalloc((void **)&ctx->tavg_gaost, (size_t)v.nt * sizeof(double)));
+    ctx->owned.push_back(ctx->tavg_gaost);
+    CK(cudaMemsetAsync(ctx->tavg_t, 0, (size_t)v.n3 * v.nt * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ctx->tavg_stf, 0, (size_t)v.n2 * v.nt * sizeof(double), ctx->stream));
+    ctx->navgts = 0;
+  }
+  if (vflux) CK(cudaMemcpyAsync(ctx->tavg_vflux, vflux, (size_t)v.n2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (gaost) CK(cudaMemcpyAsync(ctx->tavg_gaost, gaost, (size_t)v.nt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  launch_tavg_accumulate(ctx, vflux ? ctx->tavg_vflux : nullptr, gaost ? ctx->tavg_gaost : nullptr);
+  CK(cudaGetLastError());
+  ctx->navgts += 1;
+  return 0;
+}
+int uvic_b200_tavg_fetch(uvic_b200_ctx *ctx, double *avg_t, double *avg_stf, int32_t *navgts, int reset) {
+  DevView &v = ctx->v;
+  if (!ctx->tavg_t || ctx->navgts < 1) return fail(ctx, "tavg_fetch: nothing accumulated");
+  const double rnavgt = 1.0 / (double)ctx->navgts;   // 09/mom/timeavgs.F:407
+  if (navgts) *navgts = ctx->navgts;
+  if (avg_t)
+    for (int n = 0; n < v.nt; n++) {   // one tracer at a time through a one-field scratch: no second nt-sized array
+      launch_tavg_mean(ctx, ctx->tavg_t + (size_t)n * v.n3, ctx->tavg_tmp, v.n3, rnavgt);
+      CK(cudaMemcpyAsync(avg_t + (size_t)n * v.n3, ctx->tavg_tmp, (size_t)v.n3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+  if (avg_stf)
+    for (int n = 0; n < v.nt; n++) {
+      launch_tavg_mean(ctx, ctx->tavg_stf + (size_t)n * v.n2, ctx->tavg_tmp, v.n2, rnavgt);
+      CK(cudaMemcpyAsync(avg_stf + (size_t)n * v.n2, ctx->tavg_tmp, (size_t)v.n2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+  if (reset) {
+    CK(cudaMemsetAsync(ctx->tavg_t, 0, (size_t)v.n3 * v.nt * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ctx->tavg_stf, 0, (size_t)v.n2 * v.nt * sizeof(double), ctx->stream));
+    ctx->navgts = 0;
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaGetLastError());
   return 0;
 }

@@ -59,3 +59,46 @@ void launch_set_sbc(uvic_b200_ctx *c, int eots, int osegs, int osege, int ntspos
   const long long n = (long long)(v.imt - 2) * (v.jhi - v.jlo + 1);
   KLAUNCH("k_set_sbc", k_set_sbc, cdiv(n, 128), 128, v, eots, osegs, osege, 1.0 / (double)ntspos);
 }
+
+// ---------------------------------------------------------------------------------------
+// Time averages of the tracers: the tracer part of avgvar / avgout
+// (09/mom/timeavgs.F:206-375, 398-420; called from 09/mom/diag.F:138-146 with t(tau)) on the
+// default averaging grid (the whole model grid).  With the sums on the device the host fetches
+// full 3-D fields once per averaging period instead of once per step.
+//   k_tavg_accumulate   spbuf(i,k,j,n) += t(i,k,j,n,tau);
+//                       spbuf2(i,j,n) += stf(i,j,n) [- vflux(i,j)*gaost(n) for all but T and S]
+//   k_tavg_mean         avg = rnavgt * spbuf (rnavgt = 1/navgts)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_tavg_accumulate(const DevView v, double *__restrict__ sum_t, double *__restrict__ sum_stf,
+                                                         const double *__restrict__ vflux, const double *__restrict__ gaost) {
+  const long long per = (long long)v.imt * v.km * (v.jhi - v.jlo + 1);   // cells of the owned rows, all i
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= per) return;
+  const long long row0 = (long long)v.imt * v.km * (v.jlo - v.jbase);
+  const long long c = row0 + idx;
+  for (int n = 0; n < v.nt; n++) sum_t[c + (long long)n * v.n3] = sum_t[c + (long long)n * v.n3] + v.t_0[c + (long long)n * v.n3];
+  // the 2-D part: one thread per (i, j)
+  const long long per2 = (long long)v.imt * (v.jhi - v.jlo + 1);
+  if (idx < per2) {
+    const long long c2 = (long long)v.imt * (v.jlo - v.jbase) + idx;
+    for (int n = 0; n < v.nt; n++) {
+      double s = sum_stf[c2 + (long long)n * v.n2] + v.stf[c2 + (long long)n * v.n2];
+      if (n >= 2) s = s - (vflux ? vflux[c2] : 0.0) * (gaost ? gaost[n] : 0.0);
+      sum_stf[c2 + (long long)n * v.n2] = s;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_tavg_mean(const double *__restrict__ sum, double *__restrict__ avg, long long n, double rnavgt) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n) avg[idx] = rnavgt * sum[idx];
+}
+
+void launch_tavg_accumulate(uvic_b200_ctx *c, const double *vflux_dev, const double *gaost_dev) {
+  DevView &v = c->v;
+  const long long per = (long long)v.imt * v.km * (v.jhi - v.jlo + 1);
+  KLAUNCH("k_tavg_accumulate", k_tavg_accumulate, cdiv(per, 256), 256, v, c->tavg_t, c->tavg_stf, vflux_dev, gaost_dev);
+}
+void launch_tavg_mean(uvic_b200_ctx *c, const double *sum, double *avg, long long n, double rnavgt) {
+  KLAUNCH("k_tavg_mean", k_tavg_mean, cdiv(n, 256), 256, sum, avg, n, rnavgt);
+}
