@@ -367,3 +367,37 @@ def test_time_average_semantics(pkg):
             acc = acc + f[n] - (vflux * gaost[n] if n >= 2 else 0.0)
         assert np.array_equal(avg_f[n][1:-1], (0.25 * acc)[1:-1]), n
     o.close()
+
+
+def test_oracle_reproduces_committed_vectors():
+    """tests/golden/tiny_step.npz was written by tests/golden/make_golden.py from the oracle: the oracle must keep
+    reproducing it bit for bit (a regression pin; the reference itself cannot be run here)."""
+    import importlib.util
+    import os
+
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    got = mg.run_oracle()
+    ref = np.load(os.path.join(here, "tiny_step.npz"))
+    assert set(ref.files) == set(got)
+    for k in ref.files:
+        assert np.array_equal(ref[k], got[k]), k
+
+
+def test_oracle_reproduces_committed_mobi_vectors():
+    """Same pin for the MOBI path (tests/golden/tiny_mobi.npz); libm decides the last bits of exp / log / pow, so the
+    comparison allows 1e-13 of the field maximum instead of bit equality."""
+    import importlib.util
+    import os
+
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    got = mg.run_oracle_mobi()
+    ref = np.load(os.path.join(here, "tiny_mobi.npz"))
+    for k in ref.files:
+        for n in range(ref[k].shape[0]):
+            assert relerr(got[k][n], ref[k][n]) <= 1e-13, (k, n)

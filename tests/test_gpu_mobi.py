@@ -125,3 +125,27 @@ def test_host_buffer_step_with_lookahead_matches_resident_step(pkg):
         ctx.rotate()
     ref.close()
     ctx.close()
+
+
+def test_mobi_matches_committed_vectors(pkg):
+    """The CUDA MOBI path against tests/golden/tiny_mobi.npz (written from the oracle by tests/golden/make_golden.py):
+    sources within 1e-10, t(tau+1) of all 37 tracers within 1e-12."""
+    import importlib.util
+    import os
+
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    ref = np.load(os.path.join(here, "tiny_mobi.npz"))
+    case = pkg.synthetic.make_case(**mg.MOBI_CASE)
+    ctx = pkg.TracerContext(case, mobi=1)
+    ctx.load_state()
+    ctx.step(True)
+    got = ctx.fetch("src", (case.nsrc, case.jmt, case.km, case.imt))
+    for s in range(case.nsrc):
+        assert relerr(got[s][1:-1, :, 1:-1], ref["src"][s][1:-1, :, 1:-1]) <= 1e-10, s
+    gt = ctx.download_t(+1)
+    for n in range(case.nt):
+        assert relerr(gt[n, 1:-1], ref["t_p1"][n, 1:-1]) <= 1e-12, n
+    ctx.close()

@@ -422,3 +422,30 @@ def test_time_averages_on_device(pkg):
         assert np.array_equal(avg_f[:, lo:hi], ref_f[:, c.jlo - 1:c.jhi])
         c.close()
     o.close()
+
+
+def test_cuda_path_matches_committed_vectors(pkg):
+    """The CUDA path against tests/golden/tiny_step.npz (written from the oracle by tests/golden/make_golden.py): masks
+    bit-exact, K33 / diff_cbt bit-exact, t(tau+1) of two leapfrog steps and a mixing step within 1e-12."""
+    import importlib.util
+    import os
+
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    ref = np.load(os.path.join(here, "tiny_step.npz"))
+    case = pkg.synthetic.make_case(**mg.CASE)
+    assert np.array_equal(np.asarray(case["kmt"]), ref["kmt"])
+    ctx = _ctx(pkg, case)
+    for step, lf in enumerate((True, True, False)):
+        ctx.step(leapfrog=lf)
+        got = ctx.download_t(+1)
+        want = ref[f"t_p1_step{step}"]
+        for n in range(case.nt):
+            assert relerr(got[n, 1:-1], want[n, 1:-1]) <= TOL, (step, n)
+        if step == 0:
+            for name in ("K33", "diff_cbt"):
+                assert np.array_equal(ctx.fetch(name, ctx.shape3())[..., 1:-1], ref[name][..., 1:-1]), name
+        ctx.rotate()
+    ctx.close()
