@@ -149,3 +149,43 @@ def test_mobi_matches_committed_vectors(pkg):
     for n in range(case.nt):
         assert relerr(gt[n, 1:-1], ref["t_p1"][n, 1:-1]) <= 1e-12, n
     ctx.close()
+
+
+def test_one_model_year_drift(pkg):
+    """BASELINE.json north_star: basin-mean T / S / DIC within 1e-8 relative after one model year.  292 ocean steps
+    (dtts = 108000 s, run/control.in:3; a mixing step every 16th) of the full 37-tracer MOBI configuration on a small
+    grid, CUDA against the oracle: volume-weighted basin means (the three horizontal regions of mskhr, as `sumbk`
+    forms them, 09/mom/tracer.F:1548-1565) of every tracer, and the whole fields."""
+    case, o, ctx = _mobi_pair(pkg, imt=26, jmt=22, km=8, seed=12)
+    kmt = np.asarray(case["kmt"])
+    msk = np.asarray(case["mskhr"])
+    a = case.arrays
+    vol = (np.asarray(a["dzt"])[None, :, None] * (np.asarray(a["cst"]) * np.asarray(a["dyt"]))[:, None, None] *
+           np.asarray(a["dxt"])[None, None, :])
+    wet = (np.arange(1, case.km + 1)[None, :, None] <= kmt[:, None, :])
+    itt = 0
+    for _ in range(292):
+        itt += 1
+        lf = pkg.timestep.is_leapfrog(itt, 16)
+        oracle_set_step(o, case, lf)
+        o.call("ora_step")
+        ctx.step(leapfrog=lf)
+        oracle_rotate(o)
+        ctx.rotate()
+    gt, rt = ctx.download_t(0), o.t()[1]
+    assert np.isfinite(gt).all()
+    worst = 0.0
+    for n, nm in enumerate(case.tracer_names):
+        for reg in (1, 2, 3):
+            w = (vol * wet * (msk == reg)[:, None, :])[1:-1, :, 1:-1]
+            if w.sum() == 0:
+                continue
+            mg, mr = (gt[n, 1:-1, :, 1:-1] * w).sum() / w.sum(), (rt[n, 1:-1, :, 1:-1] * w).sum() / w.sum()
+            scale = max(abs(mr), np.abs(rt[n]).max() * 1e-6)
+            worst = max(worst, abs(mg - mr) / scale)
+            if nm in ("temp", "salt", "dic"):
+                assert abs(mg - mr) <= 1e-8 * scale, (nm, reg, mg, mr)
+        assert relerr(gt[n, 1:-1], rt[n, 1:-1]) <= 1e-7, (nm, relerr(gt[n, 1:-1], rt[n, 1:-1]))
+    assert worst <= 1e-7, worst
+    ctx.close()
+    o.close()
