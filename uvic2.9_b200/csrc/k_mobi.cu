@@ -1059,6 +1059,14 @@ __global__ void __launch_bounds__(32 * WS_WARPS * G) k_mobi_ws(const DevView v, 
           UPD(V_DON15, SB(V_DON15) + dtbio * (dfr * rtphytn15 * morp + dfr * rtdiatn15 * morp_Diat + dfrt * rtdiatn15 * morpt_Diat +
                                              dfrt * rtphytn15 * morpt + rtdetrn15 * pfr * remi - fcrecy * recy_don));
         }
+        {
+          // 13C of the diazotrophs (taken over from warp 3)
+          const double rtdiazc13 = SR(rtdiazc13);
+          UPD(V_DIAZC13, SB(V_DIAZC13) + dtbio * redctn * (SR(fcnpp) * SR(npp_D) - rtdiazc13 * (SR(morp_D) + SR(graz_D) + SR(morpt_D))));
+          // ... and of the diatoms
+          const double rtdiatc13 = SR(rtdiatc13);
+          UPD(V_DIATC13, SB(V_DIATC13) + dtbio * redctn * (SR(fcnpp) * SR(npp_Diat) - rtdiatc13 * (SR(morp_Diat) + SR(graz_Diat) + SR(morpt_Diat))));
+        }
         WS_BAR();
         }
       } break;
@@ -1097,12 +1105,9 @@ __global__ void __launch_bounds__(32 * WS_WARPS * G) k_mobi_ws(const DevView v, 
           double rdon = fmax(fmin(QDIV(SB(V_DON15), (biodon - SB(V_DON15))), 2 * RN15STD), RN15STD / 2.);
           double brecy = rdon + QDIV(QDIV(P->eps_recy * (1 - udon), udon) * log(1 - udon) * rdon, 1000.);
           SR(fcrecy) = QDIV(brecy, (1 + brecy));
-          SR(rtphytn15) = CL15(QDIV(SB(V_PHYTN15), SB(V_PHYT)));
-          SR(rtdiatn15) = CL15(QDIV(SB(V_DIATN15), SB(V_DIAT)));
-          SR(rtzoopn15) = CL15(QDIV(SB(V_ZOOPN15), SB(V_ZOOP)));
+          // (the 15N ratios of phytoplankton, diatoms, zooplankton and diazotrophs are formed by warp 3: load balance)
           const double rtdetrn15 = CL15(QDIV(SB(V_DETRN15), SB(V_DETR)));
           SR(rtdetrn15) = rtdetrn15;
-          SR(rtdiazn15) = CL15(QDIV(SB(V_DIAZN15), SB(V_DIAZ)));
           acc0 = acc0 + rtdetrn15;   // rn15expoout
         }
         WS_BAR();
@@ -1249,6 +1254,11 @@ __global__ void __launch_bounds__(32 * WS_WARPS * G) k_mobi_ws(const DevView v, 
                                          morpt_D - no3upt_D + recy_don + nr_excr_D + nr_excr_P + nr_excr_detr + morp_D * (1. - rnd)));
           UPD(V_DON, SB(V_DON) + dtbio * (dfr * morp + dfrt * morpt + pfr * remi - recy_don + dfr * morp_Diat + dfrt * morpt_Diat));
           UPD(V_CACO3, SB(V_CACO3) + dtbio * (SR(calpro) - SR(dissl) - SR(expocaco3) + SL(X_expocaco3) * dztrk));
+          {
+            // 13C of calcite (taken over from warp 3)
+            const double rtcaco3c13 = SR(rtcaco3c13), rcaco3c13impo = SL(X_rcaco3c13expo) * dztrk;
+            UPD(V_CACO3C13, SB(V_CACO3C13) + dtbio * (SR(rtdic13) * SR(calpro) - rtcaco3c13 * SR(dissl) - rtcaco3c13 * SR(expocaco3) + rcaco3c13impo));
+          }
         }
         {
           const double rtphytn15 = SR(rtphytn15), rtdiatn15 = SR(rtdiatn15), rtdiazn15 = SR(rtdiazn15), rtdetrn15 = SR(rtdetrn15);
@@ -1312,6 +1322,11 @@ __global__ void __launch_bounds__(32 * WS_WARPS * G) k_mobi_ws(const DevView v, 
           acc0 = acc0 + npp_D - no3upt_D;   // nfixout
           SR(rtdoc13) = CL13(QDIV(SB(V_DOC13), (SB(V_DON) * redctn)));
           SR(rtdiazc13) = CL13(QDIV(SB(V_DIAZC13), (biodiaz * redctn)));
+          // 15N ratios of four organic pools (:2479-2500), taken over from warp 1
+          SR(rtphytn15) = CL15(QDIV(SB(V_PHYTN15), SB(V_PHYT)));
+          SR(rtdiatn15) = CL15(QDIV(SB(V_DIATN15), SB(V_DIAT)));
+          SR(rtzoopn15) = CL15(QDIV(SB(V_ZOOPN15), SB(V_ZOOP)));
+          SR(rtdiazn15) = CL15(QDIV(SB(V_DIAZN15), SB(V_DIAZ)));
         }
         WS_BAR();
         {
@@ -1356,9 +1371,7 @@ __global__ void __launch_bounds__(32 * WS_WARPS * G) k_mobi_ws(const DevView v, 
                                              (rtphytc13 * (1. - dfr) * morp + rtdiatc13 * (1. - dfr) * morp_Diat + rtdiatc13 * sf_Diat +
                                               rtphytc13 * sf_P + rtzoopc13 * sf_Z + rtdetrc13 * sf_Det + rtdiazc13 * sf_D + rtzoopc13 * morz -
                                               rtdetrc13 * remi - rtdetrc13 * graz_Det - rtdetrc13 * expo + rc13impo + rtdiazc13 * morp_D * rnd));
-          UPD(V_DIAZC13, SB(V_DIAZC13) + dtbio * redctn * (fcnpp * npp_D - rtdiazc13 * (morp_D + graz_D + morpt_D)));
-          UPD(V_CACO3C13, SB(V_CACO3C13) + dtbio * (rtdic13 * calpro - rtcaco3c13 * dissl - rtcaco3c13 * expocaco3 + rcaco3c13impo));
-          UPD(V_DIATC13, SB(V_DIATC13) + dtbio * redctn * (fcnpp * npp_Diat - rtdiatc13 * (morp_Diat + graz_Diat + morpt_Diat)));
+          // (DIAZC13, CACO3C13 and DIATC13 are advanced by warps 0, 1 and 2: load balance)
           acc1 = acc1 + rtdetrc13 * expo;            // rc13expoout
           acc2 = acc2 + rtcaco3c13 * expocaco3;      // rcaco3c13expoout
         }
