@@ -78,6 +78,7 @@ int uvic_b200_create(const uvic_b200_dims *d, const uvic_b200_grid *g, const uvi
   ctx->red_partial = ctx->red_out = nullptr;
   ctx->pin_buf = nullptr; ctx->pin_bytes = 0;
   ctx->prof_on = false;
+  ctx->stream3 = nullptr; ctx->ev_elem = ctx->ev_gm = nullptr; ctx->gm_inflight = false;
   ctx->stream2 = nullptr; ctx->fork_event = nullptr; ctx->mobi_event = nullptr; ctx->src_ready[0] = ctx->src_ready[1] = nullptr; ctx->mobi_inflight = false;
   ctx->mobi_dtnpzd = 0.0;
   ctx->src_buf[0] = ctx->src_buf[1] = nullptr; ctx->src_cur = 0;
@@ -229,6 +230,9 @@ int uvic_b200_create(const uvic_b200_dims *d, const uvic_b200_grid *g, const uvi
     CK(cudaEventCreateWithFlags(&ctx->main_done_event, cudaEventDisableTiming));
   }
   CK(cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
+  CK(cudaStreamCreateWithFlags(&ctx->stream3, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&ctx->ev_elem, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&ctx->ev_gm, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&ctx->h2d_event, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&ctx->h2d_vbc_event, cudaEventDisableTiming));
   CK(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
@@ -282,6 +286,9 @@ int uvic_b200_destroy(uvic_b200_ctx *ctx) {
   cudaDeviceSynchronize();
   for (void *p : ctx->owned) cudaFree(p);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+  if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
+  if (ctx->ev_elem) cudaEventDestroy(ctx->ev_elem);
+  if (ctx->ev_gm) cudaEventDestroy(ctx->ev_gm);
   if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
   if (ctx->mobi_event) cudaEventDestroy(ctx->mobi_event);
   for (auto e : ctx->src_ready) if (e) cudaEventDestroy(e);
@@ -301,6 +308,7 @@ int uvic_b200_set_stream(uvic_b200_ctx *ctx, void *s) {
   return 0;
 }
 int uvic_b200_synchronize(uvic_b200_ctx *ctx) {
+  gm_join(ctx);
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaGetLastError());
   return 0;
@@ -646,10 +654,10 @@ int uvic_b200_tracer_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si, cons
   set_step(ctx, si);
   begin_mobi(ctx, si);
   launch_isopyc_coef(ctx);
+  launch_isopyc_vel_after(ctx, ctx->h2d_event);   // on the GM side stream, as soon as the velocities have arrived
   launch_vmixc(ctx);
   if (trace) cudaEventRecord(tev[2], ctx->stream);
   CK(cudaStreamWaitEvent(ctx->stream, ctx->h2d_vbc_event, 0));
-  ctx->vel_pending = true;
   CK(cudaGetLastError());
   // finished tracer batches stream to the host while the next batch computes (launch_tracer)
   ctx->d2h_dst = t_taup1;
@@ -692,10 +700,10 @@ int uvic_b200_tracer_step_coupled(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *
   set_step(ctx, si);
   begin_mobi(ctx, si);
   launch_isopyc_coef(ctx);
+  launch_isopyc_vel_after(ctx, ctx->h2d_event);        // on the GM side stream, as soon as the velocities have arrived
   launch_vmixc(ctx);
   CK(cudaStreamWaitEvent(ctx->stream, ctx->h2d_vbc_event, 0));
   launch_setvbc(ctx);                                  // call setvbc, source/mom/mom.F:360
-  ctx->vel_pending = true;                             // velocity part of isopyc: launch_tracer, before the first FCT kernel
   CK(cudaGetLastError());
   ctx->d2h_dst = ts_taup1;
   ctx->d2h_ntr = 2;
@@ -756,6 +764,7 @@ int uvic_b200_fetch(uvic_b200_ctx *ctx, const char *name, double *host, size_t *
   if (!p) return fail(ctx, std::string("fetch: unknown array ") + name);
   if (nelem) *nelem = n;
   if (!host) return 0;
+  gm_join(ctx);
   for (auto &a : ctx->arrs)
     if (a.name == name && a.is_int) return fail(ctx, "fetch: integer arrays are not fetchable as double");
   CK(cudaMemcpyAsync(host, p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

@@ -380,23 +380,66 @@ __global__ void __launch_bounds__(128) k_gm_column(const DevView v) {
   }
 }
 
+// The GM velocity chain only shares k_elements' output with the Redi coefficients: it runs on its own stream, beside
+// k_isocoef / vmixc / the diffusion pass (none of which fills the GPU on small grids), and the main stream joins it
+// right before the first kernel that reads the total velocities.  In the per-kernel profiling pass everything stays on
+// the launch stream so that every CUDA-event interval is one kernel.
+static bool gm_side(uvic_b200_ctx *c) { return c->stream3 != nullptr && !c->prof_on; }
+
+void gm_join(uvic_b200_ctx *c) {
+  if (!c->gm_inflight) return;
+  cudaStreamWaitEvent(c->stream, c->ev_gm, 0);
+  c->gm_inflight = false;
+}
+
 // the part of isopyc that depends on t(tau-1) only
 void launch_isopyc_coef(uvic_b200_ctx *c) {
   DevView &v = c->v;
   long long ncell = (long long)(v.imt - 2) * v.km * v.jl;
   if (v.isopycmix) {
+    gm_join(c);   // an unread chain of an earlier call still writes the arrays k_gm_faces is about to write
     KLAUNCH("k_elements", k_elements, cdiv(ncell, 256), 256, v);
-    KLAUNCH("k_isocoef", k_isocoef, cdiv(ncell, 256), 256, v);
-    KLAUNCH("k_gm_faces", k_gm_faces, cdiv(ncell, 256), 256, v);
+    if (gm_side(c)) {
+      cudaEventRecord(c->ev_elem, c->stream);
+      cudaStreamWaitEvent(c->stream3, c->ev_elem, 0);
+      cudaStream_t main_stream = c->stream;
+      c->stream = c->stream3;
+      KLAUNCH("k_gm_faces", k_gm_faces, cdiv(ncell, 256), 256, v);
+      c->stream = main_stream;
+      cudaEventRecord(c->ev_gm, c->stream3);
+      c->gm_inflight = true;
+      KLAUNCH("k_isocoef", k_isocoef, cdiv(ncell, 256), 256, v);
+    } else {
+      KLAUNCH("k_isocoef", k_isocoef, cdiv(ncell, 256), 256, v);
+      KLAUNCH("k_gm_faces", k_gm_faces, cdiv(ncell, 256), 256, v);
+    }
   }
 }
-// the part that also needs the resolved advective velocities of this step
-void launch_isopyc_vel(uvic_b200_ctx *c) {
+// the part that also needs the resolved advective velocities of this step; `after` (may be null) is an event the
+// velocities' upload signals
+void launch_isopyc_vel_after(uvic_b200_ctx *c, cudaEvent_t after) {
   DevView &v = c->v;
   long long ncol = (long long)(v.imt - 2) * v.jl;
-  KLAUNCH("k_gm_total", k_gm_total, cdiv(ncol * v.km, 256), 256, v);
-  KLAUNCH("k_gm_column", k_gm_column, cdiv(ncol, 128), 128, v);
+  if (gm_side(c)) {
+    // everything the main stream holds so far (an upload of the velocities on it, the previous step's readers of ue / vn /
+    // wb) comes first
+    cudaEventRecord(c->ev_elem, c->stream);
+    cudaStreamWaitEvent(c->stream3, c->ev_elem, 0);
+    if (after) cudaStreamWaitEvent(c->stream3, after, 0);
+    cudaStream_t main_stream = c->stream;
+    c->stream = c->stream3;
+    KLAUNCH("k_gm_total", k_gm_total, cdiv(ncol * v.km, 256), 256, v);
+    KLAUNCH("k_gm_column", k_gm_column, cdiv(ncol, 128), 128, v);
+    c->stream = main_stream;
+    cudaEventRecord(c->ev_gm, c->stream3);
+    c->gm_inflight = true;
+  } else {
+    if (after) cudaStreamWaitEvent(c->stream, after, 0);
+    KLAUNCH("k_gm_total", k_gm_total, cdiv(ncol * v.km, 256), 256, v);
+    KLAUNCH("k_gm_column", k_gm_column, cdiv(ncol, 128), 128, v);
+  }
 }
+void launch_isopyc_vel(uvic_b200_ctx *c) { launch_isopyc_vel_after(c, nullptr); }
 void launch_isopyc(uvic_b200_ctx *c) {
   launch_isopyc_coef(c);
   launch_isopyc_vel(c);

@@ -734,10 +734,11 @@ void launch_tracer(uvic_b200_ctx *c, const uvic_b200_stepinfo *si) {
     auto velocities = [&]() {
       // host-buffer entry points: the advective velocities were still travelling while the coefficient kernels and the
       // diffusion pass ran; the kernels below are the first that need them
-      if (!c->vel_pending) return;
-      cudaStreamWaitEvent(c->stream, c->h2d_event, 0);
-      launch_isopyc_vel(c);
-      c->vel_pending = false;
+      if (c->vel_pending) {
+        launch_isopyc_vel_after(c, c->h2d_event);
+        c->vel_pending = false;
+      }
+      gm_join(c);   // the total velocities come from the GM chain on its side stream
     };
     if (v.fct) {
       const int variant = fct_variant();
