@@ -327,7 +327,7 @@ static FmGeom fct_geometry(const DevView &v, int ng, int maxw) {
   const int rows = v.jhi - v.jlo + 1;
   int nchunk = std::max(1, (rows + 63) / 64);
   const long long per_chunk = (long long)ng * g.nit * g.nkt;
-  while (per_chunk * nchunk < 148 * 4 && rows / (nchunk + 1) >= 16) nchunk++;
+  while (per_chunk * nchunk < 148 * 4 && rows / (nchunk + 1) >= 8) nchunk++;   // small tracer batches: shorter marches, more CTAs
   g.chunk = (rows + nchunk - 1) / nchunk;
   g.nchunk = (rows + g.chunk - 1) / g.chunk;
   return g;
