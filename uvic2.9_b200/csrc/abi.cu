@@ -83,7 +83,7 @@ int uvic_b200_create(const uvic_b200_dims *d, const uvic_b200_grid *g, const uvi
   ctx->mobi_dtnpzd = 0.0;
   ctx->src_buf[0] = ctx->src_buf[1] = nullptr; ctx->src_cur = 0;
   ctx->hint_valid = ctx->ahead_valid = false; ctx->ahead_tm1 = nullptr; ctx->ahead_buf = 0;
-  ctx->main_done_event = nullptr; ctx->copy_in = ctx->copy_out = nullptr; ctx->h2d_event = nullptr; ctx->h2d_vbc_event = nullptr; ctx->vel_pending = false;
+  ctx->main_done_event = nullptr; ctx->copy_in = ctx->copy_out = nullptr; ctx->h2d_event = nullptr; ctx->h2d_vbc_event = nullptr;
   ctx->tavg_t = ctx->tavg_stf = ctx->tavg_tmp = ctx->tavg_vflux = ctx->tavg_gaost = nullptr; ctx->navgts = 0; ctx->d2h_dst = nullptr; ctx->d2h_ntr = 0;
   DevView &v = ctx->v;
   memset(&v, 0, sizeof v);

@@ -731,15 +731,8 @@ void launch_tracer(uvic_b200_ctx *c, const uvic_b200_stepinfo *si) {
     int tch = (ng + nchunk - 1) / nchunk;
     nchunk = (ng + tch - 1) / tch;
     dim3 gc(cdiv(ncell_c, UPD_T), nchunk);
-    auto velocities = [&]() {
-      // host-buffer entry points: the advective velocities were still travelling while the coefficient kernels and the
-      // diffusion pass ran; the kernels below are the first that need them
-      if (c->vel_pending) {
-        launch_isopyc_vel_after(c, c->h2d_event);
-        c->vel_pending = false;
-      }
-      gm_join(c);   // the total velocities come from the GM chain on its side stream
-    };
+    // the total velocities come from the GM chain on its side stream: the advection kernels below are its first readers
+    auto velocities = [&]() { gm_join(c); };
     if (v.fct) {
       const int variant = fct_variant();
       if (variant == 0) {
