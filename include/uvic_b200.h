@@ -115,6 +115,9 @@ int uvic_b200_upload_adv_vel(uvic_b200_ctx *ctx, const double *adv_vet, const do
 /* or: B-grid velocity u(imt,km,jl,2) at tau, and adv_vel on the device */
 int uvic_b200_upload_u(uvic_b200_ctx *ctx, const double *u_host);
 int uvic_b200_adv_vel(uvic_b200_ctx *ctx);
+/* call state (source/mom/state.F:1-60, from 09/mom/loadmw.F:150-155): rho(imt,km,jl) = dens(T - to(k), S - so(k), k) of the
+ * time level (-1, 0, +1) to the host -- the one 3-D field clinic needs from the tracers every step */
+int uvic_b200_state(uvic_b200_ctx *ctx, int level, double *rho_host);
 /* surface / bottom tracer fluxes from setvbc (09/mom/setvbc.F): stf, btf (imt,jl,nt) */
 int uvic_b200_upload_vbc(uvic_b200_ctx *ctx, const double *stf, const double *btf);
 /* MOBI 2-D forcing: dnswr, aice, hice, hsno (imt,jl) (09/mom/tracer.F:370-390) */

@@ -44,3 +44,13 @@ void ora_adv_vel(ora_ctx *c) {
     ora_setbcx(&c->adv_vbt[I3Z(1, 0, j)], imt, km + 1);
   }
 }
+
+/* source/mom/state.F:1-60 as called from 09/mom/loadmw.F:150-155 with t(tau): the normalised density at T cell centres
+   that clinic differentiates, rho(i,k,j) = dens(t-to(k), s-so(k), k), rows 1..jmt, i = istrt-1..iend+1 = 1..imt */
+void ora_state(ora_ctx *c) {
+  const int imt = c->imt, km = c->km, jmt = c->jmt;
+  for (int j = 1; j <= jmt; j++)
+    for (int k = 1; k <= km; k++)
+      for (int i = 1; i <= imt; i++)
+        c->rho[I3(i, k, j)] = ora_dens(c->eosc, km, c->t[IT(i, k, j, 1, TAU)] - c->to[k - 1], c->t[IT(i, k, j, 2, TAU)] - c->so[k - 1], k);
+}

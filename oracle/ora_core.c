@@ -41,7 +41,7 @@ ora_ctx *ora_create(int imt, int jmt, int km, int nt, int nsrc) {
   RD(duw, imt); RD(due, imt); RD(dus, jmt); RD(dun, jmt);
   RD(eosc, (size_t)km * 9); RD(to, km); RD(so, km);
 
-  RD(t, n3 * nt * 3); RD(u, n3 * 2);
+  RD(t, n3 * nt * 3); RD(u, n3 * 2); RD(rho, n3);
   RD(tmask, n3); RD(umask, n3);
   RD(adv_vet, n3); RD(adv_vnt, n3); RD(adv_vbt, n3z);
   RD(stf, ij * nt); RD(btf, ij * nt);

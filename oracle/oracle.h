@@ -83,6 +83,7 @@ typedef struct ora_ctx {
   /* ---- prognostic + forcing (09/mom/mw.h) ---- */
   double *t;        /* t(imt,km,jmt,nt,-1:1) */
   double *u;        /* u(imt,km,jmt,2) at tau (only for adv_vel) */
+  double *rho;      /* (imt,km,jmt) normalised density of t(tau), source/mom/state.F */
   double *tmask, *umask;    /* (imt,km,jmt) */
   double *adv_vet, *adv_vnt;/* (imt,km,jmt) */
   double *adv_vbt;          /* (imt,0:km,jmt) */
@@ -165,6 +166,7 @@ double ora_get_scalar(ora_ctx *c, const char *name);
 /* hot-path routines (one translation unit per reference file) */
 void ora_make_masks(ora_ctx *c);                       /* 09/mom/loadmw.F:60-77 */
 void ora_adv_vel(ora_ctx *c);                          /* source/mom/adv_vel.F:60-131 */
+void ora_state(ora_ctx *c);                            /* source/mom/state.F:1-60 via 09/mom/loadmw.F:150-155 */
 void ora_isopyc(ora_ctx *c);                           /* 09/mom/isopyc.F:466-557 */
 void ora_vmixc(ora_ctx *c);                            /* 09/mom/vmixc.F:68-188 */
 void ora_adv_flux(ora_ctx *c, int n);                  /* 09/mom/tracer_adv_flx.F */

@@ -449,3 +449,14 @@ def test_cuda_path_matches_committed_vectors(pkg):
                 assert np.array_equal(ctx.fetch(name, ctx.shape3())[..., 1:-1], ref[name][..., 1:-1]), name
         ctx.rotate()
     ctx.close()
+
+
+def test_state_density_bit_exact(pkg):
+    """source/mom/state.F (called from 09/mom/loadmw.F:150-155): rho = dens(T - to, S - so, k) of t(tau), bit-exact."""
+    case = _case(pkg, imt=38, jmt=30, km=9, nt=3, seed=8)
+    o = make_oracle(case)
+    o.call("ora_state")
+    ctx = _ctx(pkg, case)
+    assert np.array_equal(ctx.state(0), o.arr("rho", ctx.shape3()))
+    ctx.close()
+    o.close()

@@ -67,7 +67,7 @@ ABI_SYMBOLS = [
     "uvic_b200_hint_next_step", "uvic_b200_pin_host", "uvic_b200_unpin_host",
     "uvic_b200_sbc_setup", "uvic_b200_upload_sbc", "uvic_b200_upload_sbc_slot", "uvic_b200_download_sbc",
     "uvic_b200_download_sbc_slot", "uvic_b200_setvbc", "uvic_b200_set_sbc", "uvic_b200_tracer_step_coupled",
-    "uvic_b200_tavg_accumulate", "uvic_b200_tavg_fetch",
+    "uvic_b200_tavg_accumulate", "uvic_b200_tavg_fetch", "uvic_b200_state",
 ]
 
 _lib = None
@@ -126,6 +126,7 @@ def load_library():
     L.uvic_b200_download_sbc_slot.argtypes = [vp, C.c_int, vp]
     L.uvic_b200_setvbc.argtypes = [vp]
     L.uvic_b200_set_sbc.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.uvic_b200_state.argtypes = [vp, C.c_int, vp]
     L.uvic_b200_tavg_accumulate.argtypes = [vp, vp, vp]
     L.uvic_b200_tavg_fetch.argtypes = [vp, vp, vp, _c_int_p, C.c_int]
     L.uvic_b200_tracer_step_coupled.argtypes = [vp, C.POINTER(StepInfo)] + [vp] * 5 + [C.c_int] * 4 + [vp, vp]
@@ -296,6 +297,12 @@ class TracerContext:
 
     def adv_vel(self):
         self._ck(self.L.uvic_b200_adv_vel(self.h))
+
+    def state(self, level=0):
+        """rho (jl, km, imt) of a time level: source/mom/state.F."""
+        out = np.empty(self.shape3())
+        self._ck(self.L.uvic_b200_state(self.h, level, _vp(out)))
+        return out
 
     def rotate(self):
         self._ck(self.L.uvic_b200_rotate(self.h))

@@ -84,6 +84,7 @@ int uvic_b200_create(const uvic_b200_dims *d, const uvic_b200_grid *g, const uvi
   ctx->src_buf[0] = ctx->src_buf[1] = nullptr; ctx->src_cur = 0;
   ctx->hint_valid = ctx->ahead_valid = false; ctx->ahead_tm1 = nullptr; ctx->ahead_buf = 0;
   ctx->main_done_event = nullptr; ctx->copy_in = ctx->copy_out = nullptr; ctx->h2d_event = nullptr; ctx->h2d_vbc_event = nullptr;
+  ctx->rho_dev = nullptr;
   ctx->tavg_t = ctx->tavg_stf = ctx->tavg_tmp = ctx->tavg_vflux = ctx->tavg_gaost = nullptr; ctx->navgts = 0; ctx->d2h_dst = nullptr; ctx->d2h_ntr = 0;
   DevView &v = ctx->v;
   memset(&v, 0, sizeof v);
@@ -354,6 +355,21 @@ int uvic_b200_upload_u(uvic_b200_ctx *ctx, const double *u) {
 int uvic_b200_adv_vel(uvic_b200_ctx *ctx) {
   launch_adv_vel(ctx);
   CK(cudaGetLastError());
+  return 0;
+}
+// state (source/mom/state.F) of a time level: rho_host(imt,km,jl) = dens(T - to, S - so, k); the scratch field of the
+// time averages doubles as the device buffer
+int uvic_b200_state(uvic_b200_ctx *ctx, int level, double *rho_host) {
+  DevView &v = ctx->v;
+  if (level < -1 || level > 1 || !rho_host) return fail(ctx, "state: level must be -1, 0 or 1 and rho non-null");
+  if (!ctx->rho_dev) {
+    CK(cudaMalloc((void **)&ctx->rho_dev, (size_t)v.n3 * sizeof(double)));
+    ctx->owned.push_back(ctx->rho_dev);
+  }
+  launch_state(ctx, ctx->t_slot[ctx->lev[level + 1]], ctx->rho_dev);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(rho_host, ctx->rho_dev, (size_t)v.n3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 int uvic_b200_upload_vbc(uvic_b200_ctx *ctx, const double *stf, const double *btf) {

@@ -57,3 +57,21 @@ void launch_adv_vel(uvic_b200_ctx *c) {
   long long ncol = (long long)(v.imt - 2) * v.jl;
   KLAUNCH("k_advvel_column", k_advvel_column, cdiv(ncol, 128), 128, v);
 }
+
+// state (source/mom/state.F:1-60, called from 09/mom/loadmw.F:150-155 with t(tau)): the normalised density clinic
+// differentiates, rho(i,k,j) = dens(t - to(k), s - so(k), k) (source/mom/dens.h:18-19), all local rows, i = 1..imt.
+// With it on the device the host reads one 3-D field per step instead of T and S.
+__global__ void __launch_bounds__(256) k_state(const DevView v, const double *__restrict__ t, double *__restrict__ rho) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= v.n3) return;
+  const int k = (int)((idx / v.imt) % v.km) + 1;
+  const double tq = t[idx] - v.to[k - 1], sq = t[idx + v.n3] - v.so[k - 1];
+#define ECS(m) v.eosc[(k - 1) + v.km * ((m)-1)]
+  rho[idx] = (ECS(1) + (ECS(4) + ECS(7) * sq) * sq + (ECS(3) + ECS(8) * sq + ECS(6) * tq) * tq) * tq + (ECS(2) + (ECS(5) + ECS(9) * sq) * sq) * sq;
+#undef ECS
+}
+
+void launch_state(uvic_b200_ctx *c, const double *t, double *rho) {
+  DevView &v = c->v;
+  KLAUNCH("k_state", k_state, cdiv(v.n3, 256), 256, v, t, rho);
+}
