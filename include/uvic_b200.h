@@ -133,6 +133,16 @@ int uvic_b200_upload_sbc(uvic_b200_ctx *ctx, const double *sbc, const double *bh
 int uvic_b200_upload_sbc_slot(uvic_b200_ctx *ctx, int slot, const double *field);              /* one (imt,jl) slot, async */
 int uvic_b200_download_sbc(uvic_b200_ctx *ctx, double *sbc);
 int uvic_b200_download_sbc_slot(uvic_b200_ctx *ctx, int slot, double *field);
+/* Air-sea gas exchange: the flux loop of gasbc (09/common/gasbc.F:148-266) on the sbc array the device holds: DIC,
+ * DI13C, 14C and O2 fluxes from the segment-mean surface state (the accumulators of uvic_b200_set_sbc), co2calc_SWS at
+ * the surface; land points take the land carbon fluxes when inpp > 0.  Slots are 1-based indices into sbc. */
+typedef struct uvic_b200_gasbc_par {
+  int32_t isst, isss, issdic, issalk, issdic13, issc14, isso2, iws; /* read: SST, SSS, surface DIC, ALK, DI13C, 14C, O2, wind speed */
+  int32_t inpp, isr, iburn;                                         /* read on land: NPP, soil respiration, burning (0 = none) */
+  int32_t idicflx, idic13flx, ic14flx, io2flx;                      /* written */
+  double co2ccn, dc13ccn, dc14ccn;                                  /* atmospheric CO2 (ppmv), delta13C, delta14C (permil) */
+} uvic_b200_gasbc_par;
+int uvic_b200_gasbc(uvic_b200_ctx *ctx, const uvic_b200_gasbc_par *par);
 int uvic_b200_setvbc(uvic_b200_ctx *ctx);   /* call setvbc (source/mom/mom.F:360, 09/mom/setvbc.F:60-140): fills stf, btf */
 /* call set_sbc for every tracer with an accumulator slot (09/mom/tracer.F:1270-1288, 09/mom/set_sbc.F:36-83) on the
  * t(tau+1) the last uvic_b200_tracer produced; eots/osegs/osege/ntspos are the switches of source/common/switch.h */

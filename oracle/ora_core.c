@@ -77,7 +77,7 @@ ora_ctx *ora_create(int imt, int jmt, int km, int nt, int nsrc) {
   RD(vflux, ij); RD(gaost, nt);
   c->numsbc = 2 * nt + 4;
   RD(sbc, ij * c->numsbc); RD(bhf, ij);
-  RI(sbc_flx_index, nt); RI(trsbcindex, nt);
+  RI(sbc_flx_index, nt); RI(trsbcindex, nt); RI(gas_idx, 15);
   c->ntspos = 1;
   RI(mobi_idx, ORA_MOBI_NIDX);
   c->mobi = (ora_mobi_par *)calloc(1, sizeof(ora_mobi_par));
@@ -109,7 +109,7 @@ const char *ora_array_name(const ora_ctx *c, int idx) { return c->arr[idx].name;
 
 #define SCALARS(X) \
   X(dtts) X(c2dtts) X(aidif) X(kappa_h) X(ahisop) X(athkdf) X(slmxr) X(diff_cet) X(diff_cnt) \
-  X(zetar) X(ogamma) X(gravrho0r) X(relyr) X(co2ccn)
+  X(zetar) X(ogamma) X(gravrho0r) X(relyr) X(co2ccn) X(dc13ccn) X(dc14ccn)
 #define ISCALARS(X) \
   X(fct) X(isopycmix) X(tidal_kv) X(do_convect) X(do_mobi) X(timavgperts) X(do_filter) \
   X(jfrst) X(jft1) X(jft2) X(jft0) X(eots) X(osegs) X(osege) X(ntspos) X(navgts)

@@ -141,6 +141,8 @@ typedef struct ora_ctx {
   int32_t *sbc_flx_index;  /* (nt) 1-based sbc slot of tracer n's surface flux, 0 = none */
   int32_t *trsbcindex;     /* (nt) 1-based sbc slot of tracer n's surface accumulator, 0 = none */
   int eots, osegs, osege, ntspos;   /* source/common/switch.h */
+  int32_t *gas_idx;        /* (15) sbc slots of the gas exchange, see ora_gasbc */
+  double dc13ccn, dc14ccn; /* atmospheric delta 13C, delta 14C (09/common/cembm.h) */
 
   /* ---- time averages of the tracers (09/mom/timeavgs.F) ---- */
   double *spbuf_t, *avg_t;       /* (imt,km,jmt,nt) running sums / means of t(tau) */
@@ -181,6 +183,7 @@ void ora_filt(ora_ctx *c);                             /* source/common/filt.F *
 void ora_avgvar(ora_ctx *c);                           /* 09/mom/timeavgs.F:206-375 (tracer part) */
 void ora_avgout(ora_ctx *c);                           /* 09/mom/timeavgs.F:398-420 (time means) */
 void ora_setvbc(ora_ctx *c);                           /* 09/mom/setvbc.F:60-140 */
+void ora_gasbc(ora_ctx *c);                            /* 09/common/gasbc.F:148-266 (gas exchange loop) */
 void ora_set_sbc(ora_ctx *c);                          /* 09/mom/set_sbc.F:36-83 via 09/mom/tracer.F:1270-1288 */
 
 /* one full step as mom.F sequences it: isopyc -> vmixc -> tracer (source/mom/mom.F:340-389) */

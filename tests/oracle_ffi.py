@@ -38,7 +38,7 @@ def lib():
         L.ora_get_scalar.restype = ctypes.c_double
         L.ora_get_scalar.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
         for fn in ("ora_make_masks", "ora_adv_vel", "ora_isopyc", "ora_vmixc", "ora_tracer", "ora_step",
-                   "ora_mobi_columns", "ora_filt", "ora_setvbc", "ora_set_sbc", "ora_avgvar", "ora_avgout", "ora_state"):
+                   "ora_mobi_columns", "ora_filt", "ora_setvbc", "ora_set_sbc", "ora_avgvar", "ora_avgout", "ora_state", "ora_gasbc"):
             getattr(L, fn).argtypes = [ctypes.c_void_p]
             getattr(L, fn).restype = None
         for fn in ("ora_adv_flux", "ora_isoflux", "ora_diag_tbar"):

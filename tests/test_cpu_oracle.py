@@ -401,3 +401,54 @@ def test_oracle_reproduces_committed_mobi_vectors():
     for k in ref.files:
         for n in range(ref[k].shape[0]):
             assert relerr(got[k][n], ref[k][n]) <= 1e-13, (k, n)
+
+
+def test_gasbc_semantics(pkg):
+    """09/common/gasbc.F flux loop: no exchange under full ice cover, fluxes scale with the square of the wind speed,
+    the sign of the CO2 flux follows the air-sea pCO2 difference, land points take the land carbon balance."""
+    from helpers import make_oracle
+
+    case = pkg.synthetic.make_case(imt=16, jmt=12, km=5, nt=37, seed=41)
+    o = make_oracle(case, do_mobi=1)
+    o.call("ora_make_masks")
+    imt, jmt, nt = case.imt, case.jmt, case.nt
+    numsbc = 2 * nt + 4
+    order = ["isst", "isss", "issdic", "issalk", "issdic13", "issc14", "isso2", "iws", "inpp", "isr", "iburn", "idicflx",
+             "idic13flx", "ic14flx", "io2flx"]
+    slots = {k: q + 1 for q, k in enumerate(order)}
+    o.set("gas_idx", np.arange(1, 16, dtype=np.int32))
+    sbc = o.arr("sbc", (numsbc, jmt, imt))
+    ocean = (np.asarray(case["kmt"]) > 0)[1:-1, 1:-1]
+    aice = o.arr("aice", (jmt, imt))
+
+    def run(ws, dic, ice, co2=283.0):
+        sbc[...] = 0.0
+        sbc[slots["isst"] - 1] = 15.0
+        sbc[slots["isss"] - 1] = 0.0             # 35 psu
+        sbc[slots["issdic"] - 1] = dic
+        sbc[slots["issalk"] - 1] = 2.35
+        sbc[slots["issdic13"] - 1] = dic * 0.0111
+        sbc[slots["issc14"] - 1] = dic * 1.1e-12
+        sbc[slots["isso2"] - 1] = 0.25
+        sbc[slots["iws"] - 1] = ws
+        sbc[slots["inpp"] - 1] = 3e-8
+        sbc[slots["isr"] - 1] = 1e-8
+        sbc[slots["iburn"] - 1] = 0.5e-8
+        aice[...] = ice
+        for k, v in (("co2ccn", co2), ("dc13ccn", -6.5), ("dc14ccn", 0.0)):
+            o.set_scalar(k, v)
+        o.call("ora_gasbc")
+        return {k: sbc[slots[k] - 1][1:-1, 1:-1].copy() for k in ("idicflx", "idic13flx", "ic14flx", "io2flx")}
+
+    f1 = run(500.0, 2.0, 0.0)
+    f2 = run(1000.0, 2.0, 0.0)
+    fi = run(500.0, 2.0, 1.0)
+    fh = run(500.0, 2.3, 0.0)
+    for k in f1:
+        assert np.allclose(f2[k][ocean], 4.0 * f1[k][ocean], rtol=1e-12)        # piston velocity ~ wind speed squared
+        assert not fi[k][ocean].any()                                           # ao = 1 - aice = 0
+    assert (f1["idicflx"][ocean] > 0).all() and (fh["idicflx"][ocean] < 0).all()  # uptake at low DIC, outgassing at high
+    land = ~ocean
+    assert np.allclose(f1["idicflx"][land], (3e-8 - 1e-8 - 0.5e-8) * 0.1 / 12.e-6, rtol=1e-14)
+    assert np.array_equal(f1["io2flx"][land], np.zeros(land.sum()))
+    o.close()

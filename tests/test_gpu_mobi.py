@@ -189,3 +189,60 @@ def test_one_model_year_drift(pkg):
     assert worst <= 1e-7, worst
     ctx.close()
     o.close()
+
+
+def _gasbc_setup(case, rng):
+    """a plausible sbc array: surface state from the case's tracers, winds 3-12 m/s, land carbon fluxes"""
+    nt, jmt, imt = case.nt, case.jmt, case.imt
+    numsbc = 2 * nt + 4
+    slots = dict(isst=1, isss=2, issdic=3, issalk=4, issdic13=5, issc14=6, isso2=7, iws=8, inpp=9, isr=10, iburn=11,
+                 idicflx=12, idic13flx=13, ic14flx=14, io2flx=15)
+    t = np.asarray(case.arrays["t"])[1]            # tau
+    name = {n: q for q, n in enumerate(case.tracer_names)}
+    sbc = np.zeros((numsbc, jmt, imt))
+    for key, tr in (("isst", "temp"), ("isss", "salt"), ("issdic", "dic"), ("issalk", "alk"), ("issdic13", "dic13"),
+                    ("issc14", "c14"), ("isso2", "o2")):
+        sbc[slots[key] - 1] = t[name[tr], :, 0, :]
+    sbc[slots["iws"] - 1] = rng.uniform(300.0, 1200.0, (jmt, imt))
+    for key in ("inpp", "isr", "iburn"):
+        sbc[slots[key] - 1] = rng.uniform(0.0, 1e-8, (jmt, imt))
+    for key in ("idicflx", "idic13flx", "ic14flx", "io2flx"):
+        sbc[slots[key] - 1] = 7.0                  # stale values: must be overwritten where the routine writes
+    return numsbc, slots, sbc
+
+
+def test_gasbc_air_sea_exchange(pkg):
+    """the flux loop of gasbc (09/common/gasbc.F:148-266) on the device against the oracle: CO2 /
+    13C / 14C / O2 fluxes within 1e-10 (co2calc_SWS stops its Newton solve at |dx| < 1e-10), land fluxes and the cyclic
+    boundary exact, with and without the land carbon slots."""
+    case, o, ctx = _mobi_pair(pkg, imt=30, jmt=24, km=6, seed=31)
+    rng = np.random.default_rng(2)
+    numsbc, slots, sbc0 = _gasbc_setup(case, rng)
+    o.call("ora_make_masks")
+    order = ["isst", "isss", "issdic", "issalk", "issdic13", "issc14", "isso2", "iws", "inpp", "isr", "iburn", "idicflx",
+             "idic13flx", "ic14flx", "io2flx"]
+    ctx.sbc_setup(numsbc, np.zeros(case.nt, np.int32), np.zeros(case.nt, np.int32))
+    for land in (True, False):
+        sl = dict(slots)
+        if not land:
+            sl["inpp"] = 0
+        o.arr("sbc", (numsbc, case.jmt, case.imt))[...] = sbc0
+        o.set("gas_idx", np.array([sl[k] for k in order], dtype=np.int32))
+        for k, v in (("co2ccn", 283.0), ("dc13ccn", -6.5), ("dc14ccn", 0.0)):
+            o.set_scalar(k, v)
+        o.call("ora_gasbc")
+        ctx.upload_sbc(sbc0, None)
+        ctx.gasbc(sl, 283.0, -6.5, 0.0)
+        got, ref = ctx.download_sbc(), o.arr("sbc", (numsbc, case.jmt, case.imt))
+        ocean = np.asarray(case["kmt"]) > 0
+        for key in ("idicflx", "idic13flx", "ic14flx", "io2flx"):
+            g, r = got[sl[key] - 1], ref[sl[key] - 1]
+            assert relerr(g[1:-1][ocean[1:-1]], r[1:-1][ocean[1:-1]]) <= 1e-10, (land, key)
+            assert np.array_equal(g[1:-1][~ocean[1:-1]], r[1:-1][~ocean[1:-1]]), (land, key)     # land: exact
+            assert np.array_equal(g[1:-1, 0], g[1:-1, -2]) and np.array_equal(g[1:-1, -1], g[1:-1, 1])
+            assert np.abs(r[1:-1][ocean[1:-1]]).max() > 0
+        for m in range(numsbc):                                   # nothing else is touched
+            if m + 1 not in (sl["idicflx"], sl["idic13flx"], sl["ic14flx"], sl["io2flx"]):
+                assert np.array_equal(got[m], sbc0[m]), m
+    ctx.close()
+    o.close()

@@ -55,6 +55,12 @@ class StepInfo(C.Structure):
                 ("co2ccn", C.c_double)]
 
 
+class GasbcPar(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("isst", "isss", "issdic", "issalk", "issdic13", "issc14", "isso2", "iws", "inpp", "isr",
+                                         "iburn", "idicflx", "idic13flx", "ic14flx", "io2flx")] + \
+               [("co2ccn", C.c_double), ("dc13ccn", C.c_double), ("dc14ccn", C.c_double)]
+
+
 # every symbol include/uvic_b200.h declares
 ABI_SYMBOLS = [
     "uvic_b200_create", "uvic_b200_destroy", "uvic_b200_last_error", "uvic_b200_set_stream", "uvic_b200_synchronize",
@@ -67,7 +73,7 @@ ABI_SYMBOLS = [
     "uvic_b200_hint_next_step", "uvic_b200_pin_host", "uvic_b200_unpin_host",
     "uvic_b200_sbc_setup", "uvic_b200_upload_sbc", "uvic_b200_upload_sbc_slot", "uvic_b200_download_sbc",
     "uvic_b200_download_sbc_slot", "uvic_b200_setvbc", "uvic_b200_set_sbc", "uvic_b200_tracer_step_coupled",
-    "uvic_b200_tavg_accumulate", "uvic_b200_tavg_fetch", "uvic_b200_state",
+    "uvic_b200_tavg_accumulate", "uvic_b200_tavg_fetch", "uvic_b200_state", "uvic_b200_gasbc",
 ]
 
 _lib = None
@@ -127,6 +133,7 @@ def load_library():
     L.uvic_b200_setvbc.argtypes = [vp]
     L.uvic_b200_set_sbc.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
     L.uvic_b200_state.argtypes = [vp, C.c_int, vp]
+    L.uvic_b200_gasbc.argtypes = [vp, C.POINTER(GasbcPar)]
     L.uvic_b200_tavg_accumulate.argtypes = [vp, vp, vp]
     L.uvic_b200_tavg_fetch.argtypes = [vp, vp, vp, _c_int_p, C.c_int]
     L.uvic_b200_tracer_step_coupled.argtypes = [vp, C.POINTER(StepInfo)] + [vp] * 5 + [C.c_int] * 4 + [vp, vp]
@@ -331,6 +338,11 @@ class TracerContext:
         out = np.empty((self.numsbc, self.jl, self.imt))
         self._ck(self.L.uvic_b200_download_sbc(self.h, _vp(out)))
         return out
+
+    def gasbc(self, slots, co2ccn, dc13ccn, dc14ccn):
+        """slots: dict of the 15 sbc slot indices (1-based) of GasbcPar; 09/common/gasbc.F flux loop on the device."""
+        gp = GasbcPar(co2ccn=co2ccn, dc13ccn=dc13ccn, dc14ccn=dc14ccn, **{k: int(v) for k, v in slots.items()})
+        self._ck(self.L.uvic_b200_gasbc(self.h, C.byref(gp)))
 
     def setvbc(self):
         self._ck(self.L.uvic_b200_setvbc(self.h))

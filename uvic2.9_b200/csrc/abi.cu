@@ -433,6 +433,20 @@ int uvic_b200_download_sbc(uvic_b200_ctx *ctx, double *sbc) {
   CK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
+int uvic_b200_gasbc(uvic_b200_ctx *ctx, const uvic_b200_gasbc_par *gp) {
+  DevView &v = ctx->v;
+  if (!v.sbc || !gp) return fail(ctx, "gasbc: call uvic_b200_sbc_setup first");
+  if (!ctx->par.mobi || !v.aice) return fail(ctx, "gasbc: needs a context with O_mobi (ice fraction, carbon tracers)");
+  const int32_t rd[] = {gp->isst, gp->isss, gp->issdic, gp->issalk, gp->issdic13, gp->issc14, gp->isso2, gp->iws,
+                        gp->idicflx, gp->idic13flx, gp->ic14flx, gp->io2flx};
+  for (int32_t x : rd)
+    if (x < 1 || x > v.numsbc) return fail(ctx, "gasbc: sbc slot out of range");
+  if (gp->inpp > 0 && (gp->inpp > v.numsbc || gp->isr < 1 || gp->isr > v.numsbc || gp->iburn < 1 || gp->iburn > v.numsbc))
+    return fail(ctx, "gasbc: land carbon slot out of range");
+  launch_gasbc(ctx, gp);
+  CK(cudaGetLastError());
+  return 0;
+}
 int uvic_b200_setvbc(uvic_b200_ctx *ctx) {
   if (!ctx->v.sbc) return fail(ctx, "setvbc: call uvic_b200_sbc_setup first");
   launch_setvbc(ctx);

@@ -21,6 +21,7 @@
 #include "ctx.h"
 #include "mobi_par.h"
 #include <stdlib.h>
+#include <algorithm>
 
 // k_mobi_cell is long straight-line code (~120 KB of SASS when everything is inlined, most of it copies of exp / log /
 // pow / tanh and of ta_iter's divides) and was stalled on instruction fetch; the pre-pass kernels call one out-of-line
@@ -135,7 +136,10 @@ __device__ double drtsafe(const Carb &q, double x1, double x2, double xacc) {
 }
 
 // 09/common/co2calc.F:1-400; returns CO2* (mol m-3) and Omega_calcite, the two outputs MOBI uses
-__device__ void co2calc_sws(double t, double s, double dic_in, double ta_in, double depth, double &co2star_out, double &omega_c) {
+// AIR: also the air-sea difference dco2star = co2*ff*atmpres - co2star (:320-331; only gasbc asks for it)
+template <bool AIR>
+__device__ void co2calc_sws(double t, double s, double dic_in, double ta_in, double depth, double &co2star_out, double &omega_c,
+                            double co2_in = 0.0, double atmpres = 1.0, double *dco2star_out = nullptr) {
   Carb q;
   const double permil = 1.0 / 1024.5;
   q.pt = 0.5125e-3 * permil;   // hard-wired phosphate and silicate (:113-114)
@@ -204,6 +208,14 @@ __device__ void co2calc_sws(double t, double s, double dic_in, double ta_in, dou
   const double Ca = 10.28E-3;
   omega_c = QDIV(Ca * CO3, Kspc);
   co2star_out = QDIV(co2star, permil);
+  if constexpr (AIR) {
+    // solubility ff of Weiss & Price (1980) (:150-153)
+    const double tk100a = tk / 100.0, tk1002a = tk100a * tk100a;
+    const double ff = m_exp(-162.8301 + 218.2968 / tk100a + 90.9241 * m_log(tk100a) - 1.47696 * tk1002a +
+                            s * (.025695 - .025225 * tk100a + 0.0049867 * tk1002a));
+    const double co2starair = (co2_in * 1.e-6) * ff * atmpres;
+    *dco2star_out = (co2starair - co2star) / permil;
+  }
 }
 
 // ------------------------------------------------------------------------------------
@@ -307,7 +319,7 @@ __global__ void __launch_bounds__(128, 4) k_mobi_cell(const DevView v) {
   const double o2_in = TIN(IX_IO2) * 1000.;
   double *__restrict__ pre = v.mobi_pre + c;
   double co2star, Omega_c;
-  co2calc_sws(t_in, s_in, dic_in, alk_in, QDIV(v.zt[k - 1], 100.), co2star, Omega_c);
+  co2calc_sws<false>(t_in, s_in, dic_in, alk_in, QDIV(v.zt[k - 1], 100.), co2star, Omega_c);
   {
     double ac13_DIC_aq = -1.0512994e-4 * t_in + 1.011765;
     double ac13_aq_POC = -0.017 * m_log10(fmin(fmax(co2star * 1000., 2.), 74.)) + 1.0034;
@@ -1557,6 +1569,91 @@ __global__ void __launch_bounds__(32 * WS_WARPS * G) k_mobi_ws(const DevView v, 
 #undef SR
 #undef SL
 #undef UPD
+}
+
+// ------------------------------------------------------------------------------------
+// Air-sea gas exchange: the flux loop of gasbc (09/common/gasbc.F:62-69, 76-80, 148-266), one thread per surface point.
+// Carbon (DIC, DI13C, 14C) and oxygen fluxes from the segment-mean surface state set_sbc left in sbc, with co2calc_SWS
+// at the surface (depth 0, atmpres 1); land points take the land carbon fluxes; then the cyclic boundary of the four
+// flux slots.  (the only other caller of co2calc_SWS.)
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_gasbc(const DevView v, const uvic_b200_gasbc_par gp) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int ni = v.imt - 2;
+  const int jfirst = max(2, v.jbase), jlast = min(v.jmt - 1, v.jbase + v.jl - 1);
+  if (idx >= (long long)ni * (jlast - jfirst + 1)) return;
+  const int i = (int)(idx % ni) + 2;
+  const int j = (int)(idx / ni) + jfirst;
+  const long long c2 = X2(i, j);
+  const long long n2 = v.n2;
+#define GS(slot) v.sbc[c2 + (long long)((slot)-1) * n2]
+  const double rc13std = RC13STD, rc14std = RC14STD, C2K = 273.15;
+  const double ak = 0.99915, aaqg = 0.998764;
+  const double r13a = (gp.dc13ccn * 0.001 + 1.) * rc13std;
+  const double batmc13 = ak * aaqg * r13a;
+  double xconv = 33.7 / 3.6e+05;
+  xconv = xconv * 0.75;
+  double fdic = 0.0, fdic13 = 0.0, fc14 = 0.0, fo2 = 0.0;
+  bool wr_c = false, wr_o = false;
+  if (v.kmt[c2] > 0) {
+    double sss = 1000.0 * GS(gp.isss) + 35.0;
+    double sst = GS(gp.isst);
+    sst = fmin(35., fmax(sst, -2.));
+    sss = fmin(45., fmax(sss, 0.));
+    const double ao = 1. - v.aice[c2];
+    const double dic = GS(gp.issdic);
+    double co2star, Omega_c, dco2star;
+    co2calc_sws<true>(sst, sss, dic, GS(gp.issalk), 0.0, co2star, Omega_c, gp.co2ccn, 1.0, &dco2star);
+    const double scco2 = 2073.1 - 125.62 * sst + 3.6276 * (sst * sst) - 0.043219 * (sst * sst * sst);
+    const double ws = GS(gp.iws) * 0.01;
+    const double ws2 = ws * ws;
+    const double piston_vel = ao * xconv * ws2 * pow(scco2 / 660., -0.5);
+    fdic = piston_vel * dco2star;
+    const double adicg = 1.01051 - 1.05e-4 * sst;
+    const double dic13 = GS(gp.issdic13);
+    double r13dic = dic13 / (dic - dic13);
+    r13dic = fmin(r13dic, 2. * rc13std);
+    r13dic = fmax(r13dic, 0.5 * rc13std);
+    const double bdic13 = ak * aaqg * r13dic / adicg;
+    fdic13 = piston_vel * ((batmc13 / (1 + batmc13)) * (dco2star + co2star) - (bdic13 / (1 + bdic13)) * co2star);
+    fc14 = piston_vel * ((dco2star + co2star) * (1 + gp.dc14ccn * 0.001) * rc14std - co2star * GS(gp.issc14) / dic);
+    const double sco2 = 1638.0 - 81.83 * sst + 1.483 * (sst * sst) - 0.008004 * (sst * sst * sst);
+    const double piston_o2 = ao * xconv * ws2 * pow(sco2 / 660.0, -0.5);
+    const double f1 = log((298.15 - sst) / (C2K + sst));
+    const double f2 = f1 * f1, f3 = f2 * f1, f4 = f3 * f1, f5 = f4 * f1;
+    double o2sat = exp(2.00907 + 3.22014 * f1 + 4.05010 * f2 + 4.94457 * f3 - 2.56847E-1 * f4 + 3.88767 * f5 +
+                       sss * (-6.24523e-3 - 7.37614e-3 * f1 - 1.03410e-2 * f2 - 8.17083E-3 * f3) - 4.88682E-7 * sss * sss);
+    o2sat = o2sat / 22391.6 * 1000.0;
+    fo2 = piston_o2 * (o2sat - GS(gp.isso2));
+    wr_c = wr_o = true;
+  } else if (gp.inpp > 0) {
+    const double f = GS(gp.inpp) - GS(gp.isr) - GS(gp.iburn);
+    fdic = f * 0.1 / 12.e-6;
+    fdic13 = f * 0.1 / 12.e-6 * rc13std / (1 + rc13std);
+    fc14 = f * rc14std * 0.1 / 12.e-6;
+    wr_c = true;
+  }
+  // write, with the cyclic copies (setbcx, :248-266): a(1) = a(imt-1), a(imt) = a(2)
+  const int wrap = (i == 2) ? (v.imt - 2) : ((i == v.imt - 1) ? -(v.imt - 2) : 0);
+  if (wr_c) {
+    GS(gp.idicflx) = fdic; GS(gp.idic13flx) = fdic13; GS(gp.ic14flx) = fc14;
+  }
+  if (wr_o) GS(gp.io2flx) = fo2;
+  if (wrap) {
+    // the boundary copy takes whatever the interior point holds now (written above or left untouched)
+    v.sbc[c2 + wrap + (long long)(gp.idicflx - 1) * n2] = GS(gp.idicflx);
+    v.sbc[c2 + wrap + (long long)(gp.idic13flx - 1) * n2] = GS(gp.idic13flx);
+    v.sbc[c2 + wrap + (long long)(gp.ic14flx - 1) * n2] = GS(gp.ic14flx);
+    v.sbc[c2 + wrap + (long long)(gp.io2flx - 1) * n2] = GS(gp.io2flx);
+  }
+#undef GS
+}
+
+void launch_gasbc(uvic_b200_ctx *c, const uvic_b200_gasbc_par *gp) {
+  DevView &v = c->v;
+  const int jfirst = std::max(2, v.jbase), jlast = std::min(v.jmt - 1, v.jbase + v.jl - 1);
+  const long long n = (long long)(v.imt - 2) * (jlast - jfirst + 1);
+  KLAUNCH("k_gasbc", k_gasbc, cdiv(n, 128), 128, v, *gp);
 }
 
 static int mobi_ws_mode() {
