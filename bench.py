@@ -64,9 +64,11 @@ def load_pkg():
 
 
 def make_case(pkg, wl, world):
+    """One GPU: the named grid.  N GPUs (weak scaling): N copies of that grid's interior rows stacked in latitude, one per
+    GPU (synthetic.stack_bands) -- every slab is the one-GPU problem, neighbours exchange their 2-row halos."""
     w = WORKLOADS[wl]
-    jmt = 2 + w["rows"] * world
-    return pkg.synthetic.make_case(imt=w["imt"], jmt=jmt, km=w["km"], nt=w["nt"])
+    base = pkg.synthetic.make_case(imt=w["imt"], jmt=2 + w["rows"], km=w["km"], nt=w["nt"])
+    return pkg.synthetic.stack_bands(base, world)
 
 
 def units_per_step(case):
@@ -272,16 +274,24 @@ def main():
     w = WORKLOADS[a.workload]
     warmup = max(a.warmup, 3)
     case = make_case(pkg, a.workload, world)
-    parts = pkg.slab.partition_rows(case.jmt, world)
+    # slabs of equal estimated work (wet cells + a share for land), not of equal row counts: the kernels skip land, and the
+    # synthetic geography has polar land caps (UVIC_B200_EQUAL_ROWS=1 restores equal row counts)
+    # the stacked weak-scaling grid gives every slab the same rows and the same work; for a real (uneven) geography
+    # slab.partition_rows_balanced cuts the rows by wet-cell count instead (UVIC_B200_BALANCED=1)
+    if world > 1 and os.environ.get("UVIC_B200_BALANCED") == "1":
+        parts = pkg.slab.partition_rows_balanced(case["kmt"], world, case.km, float(os.environ.get("UVIC_B200_LAND_COST", "0.5")))
+    else:
+        parts = pkg.slab.partition_rows(case.jmt, world)
     jlo, jhi = parts[rank]
     # O_fourfil is on in run/mk.in; the synthetic fine grids skip it (the reference's filter
     # tables are fixed-size, source/common/index.h:34)
-    fourfil = 1 if a.workload.startswith("uvic100") else 0
+    # ... and so does the stacked weak-scaling grid, whose polar rows repeat inside the domain
+    fourfil = 1 if (a.workload.startswith("uvic100") and world == 1) else 0
     ctx = pkg.TracerContext(case, jlo=jlo, jhi=jhi, device=local, mobi=w["mobi"], fourfil=fourfil)
     ctx.load_state()
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
-    halo = pkg.slab.HaloExchanger(case.jmt, rank, world, dist)
+    halo = pkg.slab.HaloExchanger(case.jmt, rank, world, dist, parts=parts)
     tviews = {}
 
     def tp1_tensor():
@@ -292,12 +302,21 @@ def main():
 
     state = {"itt": 0}
 
+    halo_stream = torch.cuda.Stream(device=local) if world > 1 else None
+    halo_sync = os.environ.get("UVIC_B200_HALO_SYNC") == "1"
+
     def one_step():
         state["itt"] += 1
         # the host knows its schedule (mixing step every nmix-th itt, source/mom/mom.F:111-146) and says so: MOBI look-ahead
         ctx.step(leapfrog=pkg.timestep.is_leapfrog(state["itt"], 16), next_leapfrog=pkg.timestep.is_leapfrog(state["itt"] + 1, 16))
-        if world > 1:
-            halo.exchange(tp1_tensor())
+        if world > 1 and halo_sync:
+            halo.exchange(tp1_tensor())        # A/B switch: the exchange in line on the launch stream
+        elif world > 1:
+            # the exchange of t(tau+1) runs on a side stream beside the next step's coefficient / diffusion kernels; the
+            # library waits for it before its first advection kernel (the first reader of the new halo rows)
+            ev = halo.exchange_async(tp1_tensor(), stream, halo_stream)
+            state["halo_ev"] = ev          # keep the event alive until the library has waited for it
+            ctx.wait_before_advection(ev.cuda_event)
         ctx.rotate()
 
     def barrier():
@@ -339,8 +358,12 @@ def main():
     clk = clocks.stop() if rank == 0 else None
     ctx.profile_enable(False)
     prof = ctx.profile()
+    ms_ranks = [ms / a.steps]
     if world > 1:
         tt = torch.tensor([ms], device=f"cuda:{local}", dtype=torch.float64)
+        allms = [torch.zeros_like(tt) for _ in range(world)]
+        dist.all_gather(allms, tt)
+        ms_ranks = [float(x.item()) / a.steps for x in allms]
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
     units = units_per_step(case)
@@ -458,6 +481,23 @@ def main():
     # ---- conservation check on the state the timed steps produced -----------------------
     inv = ctx.inventory(0)
 
+    # ---- load balance: every rank's own step time with the exchange switched off (diagnostic; last, because the
+    # halos go stale) -- what the work-balanced partition is tuned against
+    solo_ranks = None
+    if world > 1:
+        barrier()
+        ev0.record(stream)
+        for _ in range(10):
+            state["itt"] += 1
+            ctx.step(leapfrog=True, next_leapfrog=True)
+            ctx.rotate()
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        tt = torch.tensor([ev0.elapsed_time(ev1) / 10], device=f"cuda:{local}", dtype=torch.float64)
+        allms = [torch.zeros_like(tt) for _ in range(world)]
+        dist.all_gather(allms, tt)
+        solo_ranks = [round(float(x.item()), 4) for x in allms]
+
     if rank != 0:
         ctx.close()
         if world > 1:
@@ -546,11 +586,14 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": a.workload, "desc": w["desc"], "grid": [case.imt, case.jmt, case.km], "nt": case.nt,
                    "nsrc": case.nsrc, "rows_per_gpu": w["rows"], "parallelism": f"latitude slabs x{world}, 2-row NCCL halos",
+                   "rows_per_slab": [int(b - a + 1) for a, b in parts],
+                   "wet_fraction_per_slab": [round(float(np.asarray(case["kmt"])[a - 1:b, 1:-1].sum()) / ((b - a + 1) * (case.imt - 2) * case.km), 3)
+                                             for a, b in parts],
                    "l2": "per-step working set (3 time levels + sources + coefficients + FCT scratch) exceeds the 126 MB L2; no explicit flush",
                    "time_stepping": "leapfrog with a forward mixing step every 16th (run/control.in nmix=16)"},
         "sim_years_per_day": 86400.0 / (292.0 * ms_step * 1e-3),
         "roofline": roofline, "roofline_top": roofline_top, "step_hbm": step_hbm, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-        "clocks": clk, "ms_per_step_serialised_profile_pass": ms_prof / a.steps, "kernels": kern, "inventory_check": {"finite": bool(np.isfinite(inv).all())},
+        "clocks": clk, "ms_per_step_per_rank": [round(x, 4) for x in ms_ranks], "ms_per_step_per_rank_without_exchange": solo_ranks, "ms_per_step_serialised_profile_pass": ms_prof / a.steps, "kernels": kern, "inventory_check": {"finite": bool(np.isfinite(inv).all())},
     }
     _emit(line)
     ctx.close()

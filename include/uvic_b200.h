@@ -172,6 +172,11 @@ int uvic_b200_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si);
  * result is used only if the next call's stepinfo equals the hint bit for bit and no upload_t / upload_forcing came
  * in between; otherwise it is discarded and recomputed.  Results are identical with and without hints. */
 int uvic_b200_hint_next_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *next);
+/* Latitude slabs: `cuda_event` (a cudaEvent_t) marks the end of the halo exchange of the newest time level.  The next
+ * uvic_b200_step lets its coefficient / diffusion kernels (which only read t(tau-1)) run beside the exchange and waits
+ * for the event right before its first advection kernel; a mixing step, or a step driven through the separate
+ * isopyc / vmixc / tracer entry points, waits at once.  The event is consumed by the wait. */
+int uvic_b200_wait_before_advection(uvic_b200_ctx *ctx, void *cuda_event);
 
 /* page-lock / release a host array passed every step (the Fortran COMMON storage), so H2D / D2H copies overlap kernels */
 int uvic_b200_pin_host(void *host, size_t bytes);

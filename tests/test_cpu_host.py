@@ -135,3 +135,32 @@ def test_halo_exchange_two_ranks_gloo(tmp_path):
                         "127.0.0.1", "--master-port", "29731", str(script), ROOT], capture_output=True, text=True, env=env,
                        timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_stacked_weak_scaling_grid_and_balanced_partition(pkg):
+    """synthetic.stack_bands: N copies of the interior rows between one pair of walls, every slab the one-GPU problem;
+    slab.partition_rows_balanced: contiguous slabs of equal estimated work that cover rows 2..jmt-1 with >= 2 rows each."""
+    import numpy as np
+
+    base = pkg.synthetic.make_case(imt=30, jmt=22, km=6, nt=3, names=["temp", "salt", "p0"], seed=3)
+    st = pkg.synthetic.stack_bands(base, 3)
+    assert st.jmt == 2 + 20 * 3
+    kb, ks = np.asarray(base["kmt"]), np.asarray(st["kmt"])
+    for b in range(3):
+        assert np.array_equal(ks[1 + 20 * b:21 + 20 * b], kb[1:21])
+        assert np.array_equal(st["t"][:, :, 1 + 20 * b:21 + 20 * b], base["t"][:, :, 1:21])
+        assert np.array_equal(st["cst"][1 + 20 * b:21 + 20 * b], base["cst"][1:21])
+    assert not ks[0].any() and not ks[-1].any()
+    assert st["adv_vbt"].shape == (st.jmt, base.km + 1, base.imt) and st["fisop"].shape == (base.km, st.jmt, base.imt)
+    assert pkg.slab.partition_rows(st.jmt, 3) == [(2, 21), (22, 41), (42, 61)]
+    # an uneven geography: polar caps of land
+    big = pkg.synthetic.make_case(imt=30, jmt=82, km=6, nt=2, seed=3)
+    kmt = np.asarray(big["kmt"])
+    for n in (2, 3, 5):
+        parts = pkg.slab.partition_rows_balanced(kmt, n, big.km)
+        assert parts[0][0] == 2 and parts[-1][1] == big.jmt - 1
+        assert all(b - a + 1 >= 2 for a, b in parts)
+        assert all(parts[q][1] + 1 == parts[q + 1][0] for q in range(n - 1))
+        work = [kmt[a - 1:b, 1:-1].sum() + 0.5 * 28 * 6 * (b - a + 1) for a, b in parts]
+        eq = [kmt[a - 1:b, 1:-1].sum() + 0.5 * 28 * 6 * (b - a + 1) for a, b in pkg.slab.partition_rows(big.jmt, n)]
+        assert max(work) <= max(eq) + 1e-9

@@ -73,7 +73,7 @@ ABI_SYMBOLS = [
     "uvic_b200_hint_next_step", "uvic_b200_pin_host", "uvic_b200_unpin_host",
     "uvic_b200_sbc_setup", "uvic_b200_upload_sbc", "uvic_b200_upload_sbc_slot", "uvic_b200_download_sbc",
     "uvic_b200_download_sbc_slot", "uvic_b200_setvbc", "uvic_b200_set_sbc", "uvic_b200_tracer_step_coupled",
-    "uvic_b200_tavg_accumulate", "uvic_b200_tavg_fetch", "uvic_b200_state", "uvic_b200_gasbc",
+    "uvic_b200_tavg_accumulate", "uvic_b200_tavg_fetch", "uvic_b200_state", "uvic_b200_gasbc", "uvic_b200_wait_before_advection",
 ]
 
 _lib = None
@@ -132,6 +132,7 @@ def load_library():
     L.uvic_b200_download_sbc_slot.argtypes = [vp, C.c_int, vp]
     L.uvic_b200_setvbc.argtypes = [vp]
     L.uvic_b200_set_sbc.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.uvic_b200_wait_before_advection.argtypes = [vp, vp]
     L.uvic_b200_state.argtypes = [vp, C.c_int, vp]
     L.uvic_b200_gasbc.argtypes = [vp, C.POINTER(GasbcPar)]
     L.uvic_b200_tavg_accumulate.argtypes = [vp, vp, vp]
@@ -313,6 +314,10 @@ class TracerContext:
 
     def rotate(self):
         self._ck(self.L.uvic_b200_rotate(self.h))
+
+    def wait_before_advection(self, cuda_event_handle):
+        """The next step's first advection kernel waits for this cudaEvent_t (end of the halo exchange)."""
+        self._ck(self.L.uvic_b200_wait_before_advection(self.h, C.c_void_p(int(cuda_event_handle))))
 
     # ---- surface boundary conditions on the device (09/mom/setvbc.F, 09/mom/set_sbc.F) ----
     def sbc_setup(self, numsbc, flx_index, acc_index):

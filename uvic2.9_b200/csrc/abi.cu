@@ -85,6 +85,7 @@ int uvic_b200_create(const uvic_b200_dims *d, const uvic_b200_grid *g, const uvi
   ctx->hint_valid = ctx->ahead_valid = false; ctx->ahead_tm1 = nullptr; ctx->ahead_buf = 0;
   ctx->main_done_event = nullptr; ctx->copy_in = ctx->copy_out = nullptr; ctx->h2d_event = nullptr; ctx->h2d_vbc_event = nullptr;
   ctx->rho_dev = nullptr;
+  ctx->halo_event = nullptr;
   ctx->tavg_t = ctx->tavg_stf = ctx->tavg_tmp = ctx->tavg_vflux = ctx->tavg_gaost = nullptr; ctx->navgts = 0; ctx->d2h_dst = nullptr; ctx->d2h_ntr = 0;
   DevView &v = ctx->v;
   memset(&v, 0, sizeof v);
@@ -623,19 +624,38 @@ int uvic_b200_hint_next_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *next)
   return 0;
 }
 
+// The halo rows of the newest time level are first read by the advection kernels of a leapfrog step (t(tau), two rows
+// either side); everything before them works on t(tau-1).  A slab driver can therefore let its exchange of t(tau+1) run
+// beside the coefficient / diffusion kernels of the next step: it hands the event that marks the end of the exchange to
+// the library, which waits for it right before the first advection kernel -- or at once when the step is a mixing
+// step (t(tau-1) := t(tau)) or is driven call site by call site.  The event is consumed by the wait.
+int uvic_b200_wait_before_advection(uvic_b200_ctx *ctx, void *cuda_event) {
+  if (!ctx) return 1;
+  ctx->halo_event = (cudaEvent_t)cuda_event;
+  return 0;
+}
+static void halo_wait_now(uvic_b200_ctx *ctx) {
+  if (!ctx->halo_event) return;
+  cudaStreamWaitEvent(ctx->stream, ctx->halo_event, 0);
+  ctx->halo_event = nullptr;
+}
+
 int uvic_b200_isopyc(uvic_b200_ctx *ctx) {
+  halo_wait_now(ctx);
   launch_isopyc(ctx);
   CK(cudaGetLastError());
   return 0;
 }
 int uvic_b200_vmixc(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
   set_step(ctx, si);
+  if (!si->leapfrog) halo_wait_now(ctx);
   launch_vmixc(ctx);
   CK(cudaGetLastError());
   return 0;
 }
 int uvic_b200_tracer(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
   set_step(ctx, si);
+  if (!si->leapfrog) halo_wait_now(ctx);
   begin_mobi(ctx, si);
   launch_tracer(ctx, si);
   ctx->mobi_inflight = false;
@@ -649,10 +669,12 @@ int uvic_b200_tracer(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
 }
 int uvic_b200_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
   set_step(ctx, si);
+  if (!si->leapfrog || ctx->prof_on) halo_wait_now(ctx);   // a mixing step reads the newest level from its first kernel on
   begin_mobi(ctx, si);
-  if (uvic_b200_isopyc(ctx)) return 1;
+  launch_isopyc(ctx);
+  CK(cudaGetLastError());
   if (uvic_b200_vmixc(ctx, si)) return 1;
-  return uvic_b200_tracer(ctx, si);
+  return uvic_b200_tracer(ctx, si);   // launch_tracer waits for a pending halo event before its first advection kernel
 }
 
 int uvic_b200_tracer_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si, const double *t_taum1, const double *t_tau,
@@ -664,6 +686,7 @@ int uvic_b200_tracer_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si, cons
   if (trace && !tev[0])
     for (auto &e : tev) cudaEventCreate(&e);
   if (trace) cudaEventRecord(tev[0], ctx->stream);
+  halo_wait_now(ctx);
   if (t_taum1 && uvic_b200_upload_t(ctx, -1, t_taum1)) return 1;
   if (t_tau && uvic_b200_upload_t(ctx, 0, t_tau)) return 1;
   // velocities and vertical b.c. travel on the input copy stream while the kernels that do not need them
@@ -718,6 +741,7 @@ int uvic_b200_tracer_step_coupled(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *
   DevView &v = ctx->v;
   if (!v.sbc) return fail(ctx, "tracer_step_coupled: call uvic_b200_sbc_setup first");
   if (ntspos < 1) return fail(ctx, "tracer_step_coupled: ntspos must be >= 1");
+  halo_wait_now(ctx);
   CK(cudaEventRecord(ctx->fork_event, ctx->stream));
   CK(cudaStreamWaitEvent(ctx->copy_in, ctx->fork_event, 0));
   if (sbc_in) CK(cudaMemcpyAsync(v.sbc, sbc_in, (size_t)v.n2 * v.numsbc * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));

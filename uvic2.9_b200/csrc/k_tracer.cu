@@ -732,7 +732,13 @@ void launch_tracer(uvic_b200_ctx *c, const uvic_b200_stepinfo *si) {
     nchunk = (ng + tch - 1) / tch;
     dim3 gc(cdiv(ncell_c, UPD_T), nchunk);
     // the total velocities come from the GM chain on its side stream: the advection kernels below are its first readers
-    auto velocities = [&]() { gm_join(c); };
+    auto velocities = [&]() {
+      gm_join(c);
+      if (c->halo_event) {   // uvic_b200_wait_before_advection: the halo rows of t(tau) are about to be read
+        cudaStreamWaitEvent(c->stream, c->halo_event, 0);
+        c->halo_event = nullptr;
+      }
+    };
     if (v.fct) {
       const int variant = fct_variant();
       if (variant == 0) {

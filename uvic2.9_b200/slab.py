@@ -28,12 +28,38 @@ def partition_rows(jmt: int, nranks: int):
     return out
 
 
-def halo_plan(jmt: int, nranks: int, rank: int):
+def partition_rows_balanced(kmt, nranks: int, km: int, land_cost: float = 0.5):
+    """Contiguous (jlo, jhi) per rank covering rows 2..jmt-1 with equal estimated WORK instead of equal row counts.
+
+    The kernels skip land (continents, levels below the bottom): a row's cost is its wet cells plus `land_cost` of a
+    wet cell for every cell of the row (staging, masks, the parts that are not skipped; fitted to the measured step
+    times of slabs with 5 % to 75 % ocean).  With the polar land caps of the synthetic bathymetry equal row counts leave
+    the equatorial slabs with twice the mean work; equal work keeps the step time of N slabs at the one-slab time.
+    kmt: (jmt, imt) level counts.  Every slab gets at least 2 rows (the halo width)."""
+    kmt = np.asarray(kmt)
+    jmt, imt = kmt.shape
+    nrows = jmt - 2
+    if nranks < 1 or nrows < 2 * nranks:
+        raise ValueError(f"need at least 2 rows per slab: jmt={jmt}, nranks={nranks}")
+    w = kmt[1:-1, 1:-1].sum(axis=1).astype(np.float64) + land_cost * (imt - 2) * km      # rows 2..jmt-1
+    cum = np.concatenate([[0.0], np.cumsum(w)])
+    cuts = [0]
+    for r in range(1, nranks):
+        target = cum[-1] * r / nranks
+        c = int(np.searchsorted(cum, target))
+        c = max(c, cuts[-1] + 2)                       # at least 2 rows in the slab just closed
+        c = min(c, nrows - 2 * (nranks - r))           # and room for 2 rows in every slab still to come
+        cuts.append(c)
+    cuts.append(nrows)
+    return [(2 + cuts[r], 2 + cuts[r + 1] - 1) for r in range(nranks)]
+
+
+def halo_plan(jmt: int, nranks: int, rank: int, parts=None):
     """Local row slices (0-based, into the slab's jl rows) of the four halo pieces.
 
     Returns dict with keys send_up / recv_up (neighbour rank+1) and send_dn / recv_dn
     (neighbour rank-1); each value is a python slice over the local row axis or None."""
-    parts = partition_rows(jmt, nranks)
+    parts = parts if parts is not None else partition_rows(jmt, nranks)
     jlo, jhi = parts[rank]
     jbase = max(1, jlo - 2)
     plan = dict(send_up=None, recv_up=None, send_dn=None, recv_dn=None, jlo=jlo, jhi=jhi, jbase=jbase)
@@ -49,9 +75,9 @@ def halo_plan(jmt: int, nranks: int, rank: int):
 class HaloExchanger:
     """Exchanges the 2-row halos of a (nt, jl, km, imt) torch tensor between neighbouring ranks."""
 
-    def __init__(self, jmt, rank, world, dist=None):
+    def __init__(self, jmt, rank, world, dist=None, parts=None):
         self.rank, self.world = rank, world
-        self.plan = halo_plan(jmt, world, rank)
+        self.plan = halo_plan(jmt, world, rank, parts)
         self.dist = dist
         self._bufs = {}
 
@@ -79,6 +105,21 @@ class HaloExchanger:
             w.wait()
         for key_r, rbuf in recvs:
             t[:, p[key_r]].copy_(rbuf)
+
+    def exchange_async(self, t, main_stream, side_stream):
+        """The same exchange on `side_stream`, behind everything `main_stream` holds so far; returns a torch.cuda.Event
+        that fires when the halo rows are in place (None with one rank).  The caller keeps launching on `main_stream`
+        and makes the first reader of the new halo rows wait for the event (uvic_b200_wait_before_advection)."""
+        if self.world == 1:
+            return None
+        import torch
+
+        side_stream.wait_stream(main_stream)
+        with torch.cuda.stream(side_stream):
+            self.exchange(t)
+            ev = torch.cuda.Event()
+            ev.record(side_stream)
+        return ev
 
     def bytes_per_step(self, nt, km, imt):
         n = sum(1 for k in ("send_up", "send_dn") if self.plan[k] is not None)

@@ -415,3 +415,49 @@ def make_case(imt=102, jmt=102, km=19, nt=2, seed=SEED, names=None, dtts=None, n
         arrays["mobi_par"] = mp.mobi_par_block(case)
         case.has_mobi = True
     return case
+
+
+# arrays with a j extent: axis of j in the C-ordered numpy array (1-D metric arrays of length jmt: axis 0)
+_J_1D = ("dyt", "dyu", "dytr", "dyt2r", "dyt4r", "dyur", "cst", "csu", "cstr", "csur", "cstdytr", "cstdyt2r", "csu_dyur", "dus",
+         "dun", "_yt", "_yu")
+_J_ND = {"kmt": 0, "kmu": 0, "mskhr": 0, "tlat": 0, "tmask": 0, "umask": 0, "fisop": 1, "sg_bathy": 1, "fe_hydr": 1, "fe_atmdep": 1,
+         "addisop": 0, "edrm2": 0, "edrs2": 0, "edrk1": 0, "edro1": 0, "adv_vet": 0, "adv_vnt": 0, "adv_vbt": 0, "stf": 1,
+         "btf": 1, "u": 1, "t": 2, "dnswr": 0, "aice": 0, "hice": 0, "hsno": 0}
+
+
+def stack_bands(case: Case, nbands: int) -> Case:
+    """Weak-scaling grid: `nbands` copies of the interior rows 2..jmt-1 of `case` stacked in latitude between one pair of
+    closed walls (global rows 1 and jmt_new), every copy with the geometry, bathymetry, tracers and velocities of the
+    original.  The polar rows of the synthetic bathymetry are land, so the copies are separate oceans that only exchange
+    land rows: one copy per GPU does exactly the work of the one-GPU case, with the real 2-row halo exchange between
+    neighbours.  (Stretching -89..89 degrees over nbands times as many rows instead would shrink dy by nbands and push the
+    synthetic meridional velocities past the CFL limit of the unchanged time step.)"""
+    if nbands == 1:
+        return case
+    jmt = case.jmt
+    new_jmt = 2 + (jmt - 2) * nbands
+
+    def tile(a, ax):
+        a = np.asarray(a)
+        idx = [slice(None)] * a.ndim
+        parts = []
+        idx[ax] = slice(0, 1)
+        parts.append(a[tuple(idx)])
+        idx[ax] = slice(1, jmt - 1)
+        parts.extend([a[tuple(idx)]] * nbands)
+        idx[ax] = slice(jmt - 1, jmt)
+        parts.append(a[tuple(idx)])
+        return np.ascontiguousarray(np.concatenate(parts, axis=ax))
+
+    arrays = {}
+    for k, v in case.arrays.items():
+        if k in _J_1D:
+            arrays[k] = tile(v, 0)
+        elif k in _J_ND and np.asarray(v).ndim > _J_ND[k] and np.asarray(v).shape[_J_ND[k]] == jmt:
+            arrays[k] = tile(v, _J_ND[k])
+        else:
+            arrays[k] = v
+    out = Case(imt=case.imt, jmt=new_jmt, km=case.km, nt=case.nt, nsrc=case.nsrc, scalars=dict(case.scalars), arrays=arrays,
+               tracer_names=list(case.tracer_names))
+    out.has_mobi = case.has_mobi
+    return out
