@@ -68,7 +68,7 @@ def make_case(pkg, wl, world):
     GPU (synthetic.stack_bands) -- every slab is the one-GPU problem, neighbours exchange their 2-row halos."""
     w = WORKLOADS[wl]
     base = pkg.synthetic.make_case(imt=w["imt"], jmt=2 + w["rows"], km=w["km"], nt=w["nt"])
-    return pkg.synthetic.stack_bands(base, world)
+    return pkg.synthetic.stack_bands(base, world, lazy=True)
 
 
 def units_per_step(case):
@@ -373,7 +373,7 @@ def main():
     # ---- end to end: host buffers through the reference-facing C ABI call ---------------
     e2e = None
     if not a.no_e2e:
-        sl = lambda n: np.ascontiguousarray(pkg.api.slab_slice(n, case[n], ctx.jbase, ctx.jl))
+        sl = lambda n: np.ascontiguousarray(pkg.api.slab_slice(n, case[n], ctx.jbase, ctx.jl, case))
 
         def pinned(x):
             t = torch.empty(x.shape, dtype=torch.float64, pin_memory=True)

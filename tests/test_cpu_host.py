@@ -164,3 +164,22 @@ def test_stacked_weak_scaling_grid_and_balanced_partition(pkg):
         work = [kmt[a - 1:b, 1:-1].sum() + 0.5 * 28 * 6 * (b - a + 1) for a, b in parts]
         eq = [kmt[a - 1:b, 1:-1].sum() + 0.5 * 28 * 6 * (b - a + 1) for a, b in pkg.slab.partition_rows(big.jmt, n)]
         assert max(work) <= max(eq) + 1e-9
+
+
+def test_lazy_stacked_case_gives_the_same_slabs(pkg):
+    """stack_bands(lazy=True) keeps 3-D arrays at the size of one band; every slab gathered through the row map equals
+    the slab cut from the materialised stack."""
+    import numpy as np
+
+    base = pkg.synthetic.make_case(imt=20, jmt=14, km=5, nt=37, seed=6)
+    eager = pkg.synthetic.stack_bands(base, 4)
+    lazy = pkg.synthetic.stack_bands(base, 4, lazy=True)
+    assert lazy.jmt == eager.jmt and lazy["t"].shape[2] == base.jmt and eager["t"].shape[2] == eager.jmt
+    for jlo, jhi in pkg.slab.partition_rows(eager.jmt, 4):
+        jbase, jl = pkg.api.slab_rows(eager.jmt, jlo, jhi)
+        for name in pkg.api._JAXIS:
+            if name not in eager.arrays:
+                continue
+            a = pkg.api.slab_slice(name, eager[name], jbase, jl, eager)
+            b = pkg.api.slab_slice(name, lazy[name], jbase, jl, lazy)
+            assert np.array_equal(a, b), (name, jlo)

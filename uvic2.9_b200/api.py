@@ -169,9 +169,14 @@ def slab_rows(jmt, jlo, jhi):
     return jbase, jtop - jbase + 1
 
 
-def slab_slice(name, arr, jbase, jl):
-    """Rows jbase..jbase+jl-1 (global, 1-based) of a global array."""
+def slab_slice(name, arr, jbase, jl, case=None):
+    """Rows jbase..jbase+jl-1 (global, 1-based) of a global array.  A lazily stacked weak-scaling case
+    (synthetic.stack_bands(..., lazy=True)) keeps its 3-D arrays at the size of one band: their rows are gathered through
+    case.row_map instead of being sliced from a materialised global array."""
     ax = _JAXIS[name]
+    if case is not None and name in getattr(case, "lazy", ()):
+        rows = case.row_map[jbase - 1:jbase - 1 + jl]
+        return np.ascontiguousarray(np.take(np.asarray(arr), rows, axis=ax))
     sl = [slice(None)] * arr.ndim
     sl[ax] = slice(jbase - 1, jbase - 1 + jl)
     return np.ascontiguousarray(arr[tuple(sl)])
@@ -198,7 +203,7 @@ class TracerContext:
             return x
 
         def loc(name):
-            return f64(slab_slice(name, a[name], self.jbase, self.jl))
+            return f64(slab_slice(name, a[name], self.jbase, self.jl, case))
 
         d = Dims(imt, jmt, km, nt, max(nsrc, 0), self.jlo, self.jhi)
         g = Grid()
@@ -286,7 +291,7 @@ class TracerContext:
         """Upload t(tau-1), t(tau), velocities and vertical b.c. of a (global) Case."""
         case = case or self.case
         a = case.arrays
-        sl = lambda n, x: slab_slice(n, x, self.jbase, self.jl)
+        sl = lambda n, x: slab_slice(n, x, self.jbase, self.jl, case)
         self.upload_t(-1, sl("t", a["t"])[0])
         self.upload_t(0, sl("t", a["t"])[1])
         vet, vnt, vbt = (np.ascontiguousarray(sl(n, a[n])) for n in ("adv_vet", "adv_vnt", "adv_vbt"))

@@ -425,13 +425,17 @@ _J_ND = {"kmt": 0, "kmu": 0, "mskhr": 0, "tlat": 0, "tmask": 0, "umask": 0, "fis
          "btf": 1, "u": 1, "t": 2, "dnswr": 0, "aice": 0, "hice": 0, "hsno": 0}
 
 
-def stack_bands(case: Case, nbands: int) -> Case:
+def stack_bands(case: Case, nbands: int, lazy: bool = False) -> Case:
     """Weak-scaling grid: `nbands` copies of the interior rows 2..jmt-1 of `case` stacked in latitude between one pair of
     closed walls (global rows 1 and jmt_new), every copy with the geometry, bathymetry, tracers and velocities of the
     original.  The polar rows of the synthetic bathymetry are land, so the copies are separate oceans that only exchange
     land rows: one copy per GPU does exactly the work of the one-GPU case, with the real 2-row halo exchange between
     neighbours.  (Stretching -89..89 degrees over nbands times as many rows instead would shrink dy by nbands and push the
-    synthetic meridional velocities past the CFL limit of the unchanged time step.)"""
+    synthetic meridional velocities past the CFL limit of the unchanged time step.)
+
+    lazy=True keeps every array with three or more dimensions at the size of ONE band and records the row map instead
+    (out.lazy, out.row_map; api.slab_slice gathers a slab's rows through it): a rank then holds one band on the host,
+    not the whole stack -- what the 0.1 degree grid needs (47 GB per band, 8 bands)."""
     if nbands == 1:
         return case
     jmt = case.jmt
@@ -450,14 +454,24 @@ def stack_bands(case: Case, nbands: int) -> Case:
         return np.ascontiguousarray(np.concatenate(parts, axis=ax))
 
     arrays = {}
+    lazy_names = set()
     for k, v in case.arrays.items():
         if k in _J_1D:
             arrays[k] = tile(v, 0)
         elif k in _J_ND and np.asarray(v).ndim > _J_ND[k] and np.asarray(v).shape[_J_ND[k]] == jmt:
-            arrays[k] = tile(v, _J_ND[k])
+            if lazy and np.asarray(v).ndim >= 3:
+                arrays[k] = v
+                lazy_names.add(k)
+            else:
+                arrays[k] = tile(v, _J_ND[k])
         else:
             arrays[k] = v
     out = Case(imt=case.imt, jmt=new_jmt, km=case.km, nt=case.nt, nsrc=case.nsrc, scalars=dict(case.scalars), arrays=arrays,
                tracer_names=list(case.tracer_names))
     out.has_mobi = case.has_mobi
+    if lazy:
+        out.lazy = lazy_names
+        # global row g (0-based) -> row of the band: the walls map to the band's walls, the interior rows repeat
+        g = np.arange(new_jmt)
+        out.row_map = np.where(g == 0, 0, np.where(g == new_jmt - 1, jmt - 1, 1 + (g - 1) % (jmt - 2)))
     return out
