@@ -421,7 +421,9 @@ __global__ void __launch_bounds__(UPD_T) k_update(const DevView v, int nbase, in
 // back for the substitution: per cell and tracer the kernel moves the tendency, t(tau-1), the source
 // (reads) and t(tau+1) (one write).
 #define INV_T 128
-#define INV_KC 8
+// INV_KC: levels whose loads are in flight together; 8 for deep grids, 4 for km <= 24 (19 levels are 5 chunks of 4 or 3
+// of 8 with 5 idle slots; measured 47 against 54 us on the 100x100x19 grid, 1.87 against 2.33 ms on 0.5 degree x 40 levels)
+template <int INV_KC>
 __global__ void __launch_bounds__(INV_T) k_invtri(const DevView v, int nbase, int ng, int ntq) {
   extern __shared__ double zsm[];   // [km][INV_T]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -713,7 +715,7 @@ void launch_tracer(uvic_b200_ctx *c, const uvic_b200_stepinfo *si) {
       // tracer: batches of six are the smallest that keep the copy engine fed, and the last one leaves a short tail.
       int q = 2;
       while (q < v.nt) {
-        const int n = std::min(std::min(6, v.ngroup), v.nt - q);
+        const int n = std::min(std::min(6, v.ngroup), v.nt - q);   // 5 and 8 measured slower
         batches.push_back({q, n});
         q += n;
       }
@@ -772,11 +774,15 @@ void launch_tracer(uvic_b200_ctx *c, const uvic_b200_stepinfo *si) {
       const size_t shm = (size_t)v.km * INV_T * sizeof(double);
       static size_t shm_set = 0;
       if (shm > 48 * 1024 && shm > shm_set) {
-        cudaFuncSetAttribute(k_invtri, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+        cudaFuncSetAttribute(k_invtri<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+        cudaFuncSetAttribute(k_invtri<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
         shm_set = shm;
       }
       ProfScope ps_(c, "k_invtri");
-      k_invtri<<<cdiv(ncol, 32) * ntq, INV_T, shm, c->stream>>>(v, nbase, ng, ntq);
+      if (v.km <= 24)
+        k_invtri<4><<<cdiv(ncol, 32) * ntq, INV_T, shm, c->stream>>>(v, nbase, ng, ntq);
+      else
+        k_invtri<8><<<cdiv(ncol, 32) * ntq, INV_T, shm, c->stream>>>(v, nbase, ng, ntq);
     }
     if (c->par.fullconvect) {
       if (nbase == 0) {
