@@ -156,6 +156,37 @@ int uvic_b200_set_sbc(uvic_b200_ctx *ctx, int eots, int osegs, int osege, int nt
 int uvic_b200_tavg_accumulate(uvic_b200_ctx *ctx, const double *vflux, const double *gaost);
 int uvic_b200_tavg_fetch(uvic_b200_ctx *ctx, double *avg_t, double *avg_stf, int32_t *navgts, int reset);
 
+/* ---- baroclinic momentum step -----------------------------------------------------------
+ * Replaces `call clinic (joff, jscalc, jecalc, is, ie)` (source/mom/mom.F:390; 09/mom/clinic.F:1-511) together with the
+ * U-cell half of adv_vel (source/mom/adv_vel.F:160-250) and the momentum half of setvbc (09/mom/setvbc.F:163-208), for
+ * the options of run/mk.in: O_consthmix + O_anisotropic_viscosity, O_constvmix, O_stream_function.  The diagnostics
+ * hooks (diagc1 / diagc2), the ice coupling (isbcu / asbcu) and the polar filter of the velocities (filuv) stay with the
+ * caller.  Time-invariant inputs, host pointers copied at setup; 2-D / 3-D arrays cover the context's local rows. */
+typedef struct uvic_b200_clinic_static {
+  const int32_t *kmu;                              /* (imt,jl)    09/common/levind.h */
+  const double *hr;                                /* (imt,jl)    1/depth at U points, 09/mom/setmom.F:1108-1111 */
+  const double *cori;                              /* (imt,jl,2)  09/mom/setmom.F:777-778 */
+  const double *advmet, *am3, *am4;                /* (jmt,2), (jmt), (jmt,2) global, 09/mom/setmom.F:791-802 */
+  const double *dxmetr, *dxu2r;                    /* (imt)       source/common/grids.F:470-530 */
+  const double *dyu2r, *dyu4r, *csudyu2r;          /* (jmt) global */
+  const double *visc_ceu, *amc_north, *amc_south;  /* (imt,km,jl) 09/mom/hmixc.F:62-150 */
+  double kappa_m, cdbot, grav_rho0r;               /* 09/common/UVic_ESCM.F:1682-1684; grav*rho0r */
+} uvic_b200_clinic_static;
+int uvic_b200_clinic_setup(uvic_b200_ctx *ctx, const uvic_b200_clinic_static *cs);
+/* u(imt,km,jl,2) of a time level: upload level -1 or 0 (0 is the field uvic_b200_upload_u sets), download -1, 0 or +1 */
+int uvic_b200_upload_u_level(uvic_b200_ctx *ctx, int level, const double *u_host);
+int uvic_b200_download_u(uvic_b200_ctx *ctx, int level, double *u_host);
+/* surface momentum flux smf(imt,jl,2) when the wind stress does not come from the coupler array on the device */
+int uvic_b200_upload_smf(uvic_b200_ctx *ctx, const double *smf);
+/* One momentum step from the resident u(tau-1), u(tau), t(tau) and T-cell advective velocities (uvic_b200_adv_vel or
+ * uvic_b200_upload_adv_vel): rho = state(t(tau)), smf / bmf, U-cell advective velocities, u(tau+1) with its vertical
+ * mean removed and the cyclic columns set, and zu (the vertical mean of du/dt that forces the barotropic equation).
+ * itaux / itauy: 1-based slots of the wind stress in the coupler array of uvic_b200_sbc_setup, or 0, 0 to keep the smf
+ * of uvic_b200_upload_smf.  Asynchronous on the context's stream. */
+int uvic_b200_clinic(uvic_b200_ctx *ctx, double c2dtuv, int itaux, int itauy);
+int uvic_b200_download_zu(uvic_b200_ctx *ctx, double *zu_host);   /* (imt,jl,2) */
+int uvic_b200_rotate_u(uvic_b200_ctx *ctx);                        /* tau-1 <- tau <- tau+1 */
+
 int uvic_b200_rotate(uvic_b200_ctx *ctx);
 
 /* ---- the hot path, one entry per reference call site (device resident) ------------ */

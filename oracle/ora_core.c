@@ -79,6 +79,15 @@ ora_ctx *ora_create(int imt, int jmt, int km, int nt, int nsrc) {
   RD(sbc, ij * c->numsbc); RD(bhf, ij);
   RI(sbc_flx_index, nt); RI(trsbcindex, nt); RI(gas_idx, 15);
   c->ntspos = 1;
+  RI(kmu, ij); RD(um1, n3 * 2); RD(up1, n3 * 2);
+  RD(adv_veu, n3); RD(adv_vnu, n3); RD(adv_vbu, n3z);
+  RD(smf, ij * 2); RD(bmf, ij * 2); RD(hr, ij); RD(cori, ij * 2);
+  RD(advmet, jmt * 2); RD(am3, jmt); RD(am4, jmt * 2); RD(dxmetr, imt); RD(dxu2r, imt);
+  RD(dyu2r, jmt); RD(dyu4r, jmt); RD(csudyu2r, jmt);
+  RD(visc_ceu, n3); RD(amc_north, n3); RD(amc_south, n3); RD(visc_cbu, n3);
+  RD(grad_p, n3 * 2); RD(zu, ij * 2); RD(baru, ij * 2);
+  RD(csudxur, ij); RD(csudxu2r, ij); RD(am_csudxtr, n3); RD(tempik, n3);
+  c->itaux = 1; c->itauy = 2;
   RI(mobi_idx, ORA_MOBI_NIDX);
   c->mobi = (ora_mobi_par *)calloc(1, sizeof(ora_mobi_par));
   /* the mobi parameter block is exposed as a flat double array for the tests */
@@ -109,10 +118,11 @@ const char *ora_array_name(const ora_ctx *c, int idx) { return c->arr[idx].name;
 
 #define SCALARS(X) \
   X(dtts) X(c2dtts) X(aidif) X(kappa_h) X(ahisop) X(athkdf) X(slmxr) X(diff_cet) X(diff_cnt) \
-  X(zetar) X(ogamma) X(gravrho0r) X(relyr) X(co2ccn) X(dc13ccn) X(dc14ccn)
+  X(zetar) X(ogamma) X(gravrho0r) X(relyr) X(co2ccn) X(dc13ccn) X(dc14ccn) \
+  X(c2dtuv) X(kappa_m) X(cdbot) X(grav_rho0r)
 #define ISCALARS(X) \
   X(fct) X(isopycmix) X(tidal_kv) X(do_convect) X(do_mobi) X(timavgperts) X(do_filter) \
-  X(jfrst) X(jft1) X(jft2) X(jft0) X(eots) X(osegs) X(osege) X(ntspos) X(navgts)
+  X(jfrst) X(jft1) X(jft2) X(jft0) X(eots) X(osegs) X(osege) X(ntspos) X(navgts) X(itaux) X(itauy)
 
 int ora_set_scalar(ora_ctx *c, const char *name, double v) {
 #define X(f) if (strcmp(name, #f) == 0) { c->f = v; return 0; }

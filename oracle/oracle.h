@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ORA_MAXARR 256
+#define ORA_MAXARR 320
 
 typedef struct ora_arr {
   const char *name;
@@ -150,6 +150,26 @@ typedef struct ora_ctx {
   double *vflux, *gaost;         /* (imt,jmt) virtual flux, (nt) its tracer factors */
   int navgts;
 
+  /* ---- baroclinic momentum (09/mom/clinic.F, source/mom/adv_vel.F:160-250, 09/mom/setvbc.F:163-208) ---- */
+  int32_t *kmu;                         /* (imt,jmt) levels at U points, 09/common/levind.h */
+  double *um1, *up1;                    /* u(imt,km,jmt,2) at tau-1 and tau+1 (c->u is tau) */
+  double *adv_veu, *adv_vnu;            /* (imt,km,jmt) */
+  double *adv_vbu;                      /* (imt,0:km,jmt) */
+  double *smf, *bmf;                    /* (imt,jmt,2) surface / bottom momentum flux */
+  double *hr;                           /* (imt,jmt) 1/depth at U points, 09/mom/setmom.F:1108-1111 */
+  double *cori;                         /* (imt,jmt,2) 09/mom/setmom.F:777-778 */
+  double *advmet, *am3, *am4;           /* (jmt,2), (jmt), (jmt,2) 09/mom/setmom.F:791-802 */
+  double *dxmetr, *dxu2r;               /* (imt) source/common/grids.F */
+  double *dyu2r, *dyu4r, *csudyu2r;     /* (jmt) */
+  double *visc_ceu, *amc_north, *amc_south, *visc_cbu; /* (imt,km,jmt) 09/mom/hmixc.F:62-150, 09/mom/vmixc.F:85 */
+  double *grad_p;                       /* (imt,km,jmt,2) */
+  double *zu;                           /* (imt,jmt,2) vertical mean of du/dt, forcing of tropic */
+  double *baru;                         /* (imt,jmt,2) */
+  double *csudxur, *csudxu2r;           /* (imt,jmt) 09/mom/mw.h */
+  double *am_csudxtr, *tempik;          /* (imt,km,jmt) */
+  double c2dtuv, kappa_m, cdbot, grav_rho0r;
+  int itaux, itauy;                     /* 1-based sbc slots of the wind stress */
+
   /* ---- Fourier filter (source/common/index.h) ---- */
   int do_filter;
   int jfrst, jft1, jft2, jft0;  /* source/common/setcom.F */
@@ -185,6 +205,9 @@ void ora_avgout(ora_ctx *c);                           /* 09/mom/timeavgs.F:398-
 void ora_setvbc(ora_ctx *c);                           /* 09/mom/setvbc.F:60-140 */
 void ora_gasbc(ora_ctx *c);                            /* 09/common/gasbc.F:148-266 (gas exchange loop) */
 void ora_set_sbc(ora_ctx *c);                          /* 09/mom/set_sbc.F:36-83 via 09/mom/tracer.F:1270-1288 */
+void ora_adv_vel_u(ora_ctx *c);                        /* source/mom/adv_vel.F:160-250 */
+void ora_setvbc_mom(ora_ctx *c);                       /* 09/mom/setvbc.F:163-208 */
+void ora_clinic(ora_ctx *c);                           /* 09/mom/clinic.F:60-560 (run/mk.in options, without filuv) */
 
 /* one full step as mom.F sequences it: isopyc -> vmixc -> tracer (source/mom/mom.F:340-389) */
 void ora_step(ora_ctx *c);

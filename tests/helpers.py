@@ -43,3 +43,19 @@ def relerr(a, b):
 def interior(x):
     """drop the cyclic boundary columns"""
     return x[..., 1:-1]
+
+
+def oracle_load_momentum(o, case):
+    """wind stress into the coupler slots the oracle's setvbc reads (09/mom/setvbc.F:163-164); slots 1 and 2"""
+    imt, jmt = case.imt, case.jmt
+    sbc = o.arr("sbc").reshape(-1, jmt, imt)
+    sbc[0] = case["taux"]
+    sbc[1] = case["tauy"]
+    o.set_scalar("itaux", 1)
+    o.set_scalar("itauy", 2)
+
+
+def oracle_clinic(o):
+    """adv_vel -> state -> setvbc -> clinic as mom sequences them (source/mom/mom.F:300-390)"""
+    for fn in ("ora_adv_vel", "ora_adv_vel_u", "ora_state", "ora_setvbc_mom", "ora_clinic"):
+        o.call(fn)

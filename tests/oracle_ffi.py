@@ -38,7 +38,8 @@ def lib():
         L.ora_get_scalar.restype = ctypes.c_double
         L.ora_get_scalar.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
         for fn in ("ora_make_masks", "ora_adv_vel", "ora_isopyc", "ora_vmixc", "ora_tracer", "ora_step",
-                   "ora_mobi_columns", "ora_filt", "ora_setvbc", "ora_set_sbc", "ora_avgvar", "ora_avgout", "ora_state", "ora_gasbc"):
+                   "ora_mobi_columns", "ora_filt", "ora_setvbc", "ora_set_sbc", "ora_avgvar", "ora_avgout", "ora_state", "ora_gasbc",
+                   "ora_adv_vel_u", "ora_setvbc_mom", "ora_clinic"):
             getattr(L, fn).argtypes = [ctypes.c_void_p]
             getattr(L, fn).restype = None
         for fn in ("ora_adv_flux", "ora_isoflux", "ora_diag_tbar"):
@@ -112,7 +113,7 @@ class Oracle:
     def load_case(self, case):
         """Copy every array / scalar of a synthetic Case that the oracle knows."""
         for k, v in case.arrays.items():
-            if k.startswith("_") or k == "kmu":
+            if k.startswith("_"):
                 continue
             try:
                 self.set(k, v)

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from conftest import load_pkg
-from helpers import make_oracle, oracle_set_step, relerr
+from helpers import make_oracle, oracle_clinic, oracle_load_momentum, oracle_set_step, relerr
 from oracle_ffi import Oracle
 
 
@@ -452,3 +452,104 @@ def test_gasbc_semantics(pkg):
     assert np.allclose(f1["idicflx"][land], (3e-8 - 1e-8 - 0.5e-8) * 0.1 / 12.e-6, rtol=1e-14)
     assert np.array_equal(f1["io2flx"][land], np.zeros(land.sum()))
     o.close()
+
+
+def _clinic_numpy(case, rho, smf, bmf, veu, vnu, vbu):
+    """Independent vectorised restatement of 09/mom/clinic.F:119-485 + 09/mom/fdifm.h for rows 2..jmt-1, i = 2..imt-1
+    (arrays are (jmt,km,imt); summation order differs from the reference, so agreement is to round-off, not bit-exact)."""
+    a = case.arrays
+    imt, jmt, km = case.imt, case.jmt, case.km
+    sc = case.scalars
+    u0, um = a["u"], a["um1"]
+    umask = a["umask"]
+    J = slice(1, jmt - 1)
+    JN = slice(2, jmt)
+    JS = slice(0, jmt - 2)
+    I = slice(1, imt - 1)
+    IE = slice(2, imt)
+    IW = slice(0, imt - 2)
+    col = lambda x: x[J, None, None]
+    # pressure gradient at U points, i = 1..imt-1 (0-based 0..imt-2), integrated downward
+    g = sc["grav_rho0r"]
+    rbar = np.empty_like(rho)
+    rbar[:, 0] = rho[:, 0]
+    rbar[:, 1:] = rho[:, :-1] + rho[:, 1:]
+    t1 = rbar[JN][:, :, 1:] - rbar[J][:, :, :-1]
+    t2 = rbar[JN][:, :, :-1] - rbar[J][:, :, 1:]
+    dz = np.concatenate([[a["dzw"][0]], 0.5 * a["dzw"][1:km]])
+    gx = g * col(a["csur"]) * (t1 - t2) * dz[None, :, None] * a["dxu2r"][None, None, :-1]
+    gy = g * col(a["dyu2r"]) * (t1 + t2) * dz[None, :, None]
+    gp = np.stack([np.cumsum(gx, axis=1), np.cumsum(gy, axis=1)])     # (2, rows, km, imt-1)
+    csudxur = col(a["csur"]) * a["dxur"][None, None, :]
+    out = np.zeros((2, jmt, km, imt))
+    zu = np.zeros((2, jmt, imt))
+    kmu = a["kmu"]
+    kk = np.arange(km + 1)[None, :, None]
+    for n in range(2):
+        m = 1 - n
+        adv_fe = veu[J][:, :, :-1] * (u0[n][J][:, :, :-1] + u0[n][J][:, :, 1:])
+        diff_fe = a["visc_ceu"][J][:, :, :-1] * col(a["csur"]) * a["dxtr"][None, None, 1:] * (um[n][J][:, :, 1:] - um[n][J][:, :, :-1])
+        adv_fb = np.zeros((jmt - 2, km + 1, imt))
+        diff_fb = np.zeros((jmt - 2, km + 1, imt))
+        adv_fb[:, 1:km] = vbu[J][:, 1:km] * (u0[n][J][:, :-1] + u0[n][J][:, 1:])
+        visc = np.where(np.arange(1, km + 1)[None, :, None] <= a["kmt"][J][:, None, :] - 1, sc["kappa_m"], 0.0)
+        diff_fb[:, 1:km] = visc[:, :km - 1] * a["dzwr"][1:km][None, :, None] * (um[n][J][:, :-1] - um[n][J][:, 1:])
+        adv_fb[:, 0] = vbu[J][:, 0] * 2.0 * u0[n][J][:, 0]
+        adv_fb[:, km] = vbu[J][:, km] * u0[n][J][:, km - 1]
+        diff_fb[:, 0] = smf[n][J]
+        diff_fb = np.where(kk == kmu[J][:, None, :], bmf[n][J][:, None, :], diff_fb)
+        dux = (diff_fe[:, :, 1:] - diff_fe[:, :, :-1]) * csudxur[:, :, I]
+        duy = a["amc_north"][J][:, :, I] * (um[n][JN][:, :, I] - um[n][J][:, :, I]) - a["amc_south"][J][:, :, I] * (um[n][J][:, :, I] - um[n][JS][:, :, I])
+        duz = (diff_fb[:, :-1] - diff_fb[:, 1:])[:, :, I] * a["dztr"][None, :, None]
+        dmet = col(a["am3"]) * um[n][J][:, :, I] + col(a["am4"][n]) * a["dxmetr"][None, None, I] * (um[m][J][:, :, IE] - um[m][J][:, :, IW])
+        aux = (adv_fe[:, :, 1:] - adv_fe[:, :, :-1]) * csudxur[:, :, I] * 0.5
+        auy = (vnu[J][:, :, I] * (u0[n][J][:, :, I] + u0[n][JN][:, :, I]) - vnu[JS][:, :, I] * (u0[n][JS][:, :, I] + u0[n][J][:, :, I])) * col(a["csudyu2r"])
+        auz = (adv_fb[:, :-1] - adv_fb[:, 1:])[:, :, I] * a["dzt2r"][None, :, None]
+        amet = col(a["advmet"][n]) * u0[0][J][:, :, I] * u0[m][J][:, :, I]
+        cor = a["cori"][n][J][:, None, I] * u0[m][J][:, :, I]
+        tend = (dux + duy + duz + dmet - aux - auy - auz + amet - gp[n][:, :, 1:] + cor) * umask[J][:, :, I]
+        zu[n][J, 1:-1] = (tend * a["dzt"][None, :, None]).sum(axis=1) * a["hr"][J, 1:-1]
+        up = um[n][J][:, :, I] + sc["c2dtuv"] * tend
+        bar = (up * a["dzt"][None, :, None]).sum(axis=1) * a["hr"][J, 1:-1]
+        out[n][J, :, 1:-1] = up - umask[J][:, :, I] * bar[:, None, :]
+    out[..., 0] = out[..., -2]
+    out[..., -1] = out[..., 1]
+    return out, zu
+
+
+def test_clinic_against_numpy_and_invariants(pkg):
+    """the baroclinic momentum step.  The oracle's adv_vel (U part), setvbc (momentum part) and
+    clinic agree with an independent vectorised numpy restatement to round-off; u(tau+1) has no depth mean (pure
+    internal mode), vanishes on land and is cyclic; zu is the depth mean of the tendency."""
+    case = pkg.synthetic.make_case(imt=34, jmt=30, km=8, nt=2, seed=33)
+    pkg.synthetic.add_momentum(case)
+    imt, jmt, km = case.imt, case.jmt, case.km
+    o = make_oracle(case)
+    oracle_load_momentum(o, case)
+    oracle_clinic(o)
+    sh3, sh3z = (jmt, km, imt), (jmt, km + 1, imt)
+    up = o.arr("up1", (2,) + sh3).copy()
+    zu = o.arr("zu", (2, jmt, imt)).copy()
+    assert np.isfinite(up).all() and np.abs(up).max() > 0
+    rho = o.arr("rho", sh3).copy()
+    smf, bmf = o.arr("smf", (2, jmt, imt)).copy(), o.arr("bmf", (2, jmt, imt)).copy()
+    a = case.arrays
+    # setvbc: stress masked by the surface U mask, quadratic drag of the deepest U cell
+    assert np.array_equal(smf[0][:, 1:-1], (case["taux"] * a["umask"][:, 0])[:, 1:-1])
+    kz = np.maximum(a["kmu"], 1) - 1
+    jj, ii = np.meshgrid(np.arange(jmt), np.arange(imt), indexing="ij")
+    ub = a["um1"][:, jj, kz, ii]
+    drag = np.where(a["kmu"] > 0, case.scalars["cdbot"] * ub * np.sqrt(ub[0] ** 2 + ub[1] ** 2), 0.0)
+    np.testing.assert_allclose(bmf[:, :, 1:-1], drag[:, :, 1:-1], rtol=1e-14, atol=0)
+    ref, zref = _clinic_numpy(case, rho, smf, bmf, o.arr("adv_veu", sh3), o.arr("adv_vnu", sh3), o.arr("adv_vbu", sh3z))
+    for n in range(2):
+        assert relerr(up[n][1:-1], ref[n][1:-1]) < 1e-12, n
+        assert relerr(zu[n][1:-1, 1:-1], zref[n][1:-1, 1:-1]) < 1e-11, n
+    # invariants
+    assert np.all(up[:, 1:-1][:, :, :, :][..., :] * (1.0 - a["umask"][1:-1])[None] == 0.0)
+    assert np.array_equal(up[..., 0], up[..., -2]) and np.array_equal(up[..., -1], up[..., 1])
+    mean = (up * a["dzt"][None, None, :, None]).sum(axis=2) * a["hr"][None]
+    assert np.abs(mean[:, 1:-1]).max() < 1e-12 * np.abs(up).max()
+    # U-cell advective velocities: the U-cell bottom velocity closes at the bottom like the T-cell one (continuity)
+    vbu = o.arr("adv_vbu", sh3z)
+    assert np.abs(vbu[:, 0]).max() == 0.0

@@ -1,0 +1,130 @@
+"""GPU parity of the baroclinic momentum step: uvic_b200_clinic through the C ABI against the
+oracle's adv_vel (U part) + setvbc (momentum part) + clinic on the same seeded inputs.  The device keeps the reference's
+operation order and is compiled without FMA contraction, so every field is compared bit for bit."""
+import numpy as np
+import pytest
+
+from conftest import load_pkg
+from helpers import make_oracle, oracle_clinic, oracle_load_momentum
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    return load_pkg()
+
+
+def _case(pkg, imt, jmt, km, seed):
+    case = pkg.synthetic.make_case(imt=imt, jmt=jmt, km=km, nt=2, seed=seed)
+    return pkg.synthetic.add_momentum(case)
+
+
+def _sbc_with_stress(case, numsbc):
+    sbc = np.zeros((numsbc, case.jmt, case.imt))
+    sbc[0], sbc[1] = case["taux"], case["tauy"]
+    return sbc
+
+
+def _device_clinic(pkg, case, jlo=None, jhi=None, use_slots=True, smf=None):
+    """one context (optionally a slab), loaded from the global case; returns the context after clinic has run"""
+    ctx = pkg.TracerContext(case, jlo=jlo, jhi=jhi)
+    ctx.load_state()
+    sl = lambda n: pkg.api.slab_slice(n, case[n], ctx.jbase, ctx.jl, case)
+    ctx.upload_u_level(0, sl("u"))
+    ctx.adv_vel()
+    ctx.clinic_setup(case)
+    ctx.upload_u_level(-1, sl("um1"))
+    if use_slots:
+        numsbc = 2 * case.nt + 4
+        ctx.sbc_setup(numsbc, np.zeros(case.nt, dtype=np.int32), np.zeros(case.nt, dtype=np.int32))
+        ctx.upload_sbc(_sbc_with_stress(case, numsbc)[:, ctx.jbase - 1:ctx.jbase - 1 + ctx.jl], None)
+        ctx.clinic(case.scalars["c2dtuv"], 1, 2)
+    else:
+        ctx.upload_smf(smf[:, ctx.jbase - 1:ctx.jbase - 1 + ctx.jl])
+        ctx.clinic(case.scalars["c2dtuv"], 0, 0)
+    ctx.synchronize()
+    return ctx
+
+
+def _oracle_clinic(case):
+    o = make_oracle(case)
+    oracle_load_momentum(o, case)
+    oracle_clinic(o)
+    return o
+
+
+@pytest.mark.parametrize("dims", [(34, 30, 8, 33), (102, 102, 19, 2901)])
+def test_clinic_bit_exact(pkg, dims):
+    imt, jmt, km, seed = dims
+    case = _case(pkg, imt, jmt, km, seed)
+    o = _oracle_clinic(case)
+    ctx = _device_clinic(pkg, case)
+    s3, s3z, s2 = (jmt, km, imt), (jmt, km + 1, imt), (2, jmt, imt)
+    bad = []
+
+    def check(name, got, ref):
+        if not np.array_equal(got, ref):
+            den = max(np.abs(ref).max(), 1e-300)
+            bad.append((name, float(np.abs(got - ref).max() / den), int((got != ref).sum())))
+
+    # U-cell advective velocities: rows the reference computes (adv_vel.F:168,196,226)
+    check("adv_vnu", ctx.fetch("adv_vnu", s3)[0:jmt - 1], o.arr("adv_vnu", s3)[0:jmt - 1])
+    check("adv_veu", ctx.fetch("adv_veu", s3)[1:jmt - 1], o.arr("adv_veu", s3)[1:jmt - 1])
+    check("adv_vbu", ctx.fetch("adv_vbu", s3z)[1:jmt - 1], o.arr("adv_vbu", s3z)[1:jmt - 1])
+    check("smf", ctx.fetch("smf", s2), o.arr("smf", s2))
+    check("bmf", ctx.fetch("bmf", s2), o.arr("bmf", s2))
+    check("rho", ctx.fetch("rho", s3), o.arr("rho", s3))
+    wet = case["umask"][1:-1, :, 1:-1] > 0
+    gp_d = ctx.fetch("grad_p", (2,) + s3)[:, 1:-1, :, 1:-1]
+    gp_o = o.arr("grad_p", (2,) + s3)[:, 1:-1, :, 1:-1]
+    check("grad_p", gp_d * wet[None], gp_o * wet[None])
+    up_d, up_o = ctx.download_u(+1), o.arr("up1", (2,) + s3)
+    check("u(tau+1)", up_d[:, 1:-1], up_o[:, 1:-1])
+    check("zu", ctx.download_zu()[:, 1:-1, 1:-1], o.arr("zu", s2)[:, 1:-1, 1:-1])
+    assert not bad, bad
+    assert np.abs(up_d).max() > 0
+    # size-independent properties of the result: pure internal mode, zero on land, cyclic
+    a = case.arrays
+    mean = (up_d * a["dzt"][None, None, :, None]).sum(axis=2) * a["hr"][None]
+    assert np.abs(mean[:, 1:-1]).max() < 1e-12 * np.abs(up_d).max()
+    assert np.all((up_d[:, 1:-1] - a["um1"][:, 1:-1]) * (1.0 - a["umask"][None, 1:-1]) == 0.0)
+    assert np.array_equal(up_d[..., 0], up_d[..., -2]) and np.array_equal(up_d[..., -1], up_d[..., 1])
+    # the uploaded-smf entry and the time-level rotation
+    ctx2 = _device_clinic(pkg, case, use_slots=False, smf=o.arr("smf", s2))
+    assert np.array_equal(ctx2.download_u(+1)[:, 1:-1], up_d[:, 1:-1])
+    u_tau = ctx2.download_u(0)
+    ctx2.rotate_u()
+    assert np.array_equal(ctx2.download_u(0)[:, 1:-1], up_d[:, 1:-1]) and np.array_equal(ctx2.download_u(-1), u_tau)
+    ctx2.close()
+    ctx.close()
+    o.close()
+
+
+def test_clinic_two_slabs_match_one_context(pkg):
+    """rows 2..jmt-1 split over two contexts with 2-row halos give the single-context result bit for bit"""
+    case = _case(pkg, 34, 30, 8, 33)
+    jmt = case.jmt
+    full = _device_clinic(pkg, case)
+    ref_u, ref_zu = full.download_u(+1), full.download_zu()
+    full.close()
+    mid = 14
+    for jlo, jhi in ((2, mid), (mid + 1, jmt - 1)):
+        ctx = _device_clinic(pkg, case, jlo=jlo, jhi=jhi)
+        u, zu = ctx.download_u(+1), ctx.download_zu()
+        r0 = jlo - ctx.jbase
+        n = jhi - jlo + 1
+        assert np.array_equal(u[:, r0:r0 + n], ref_u[:, jlo - 1:jhi]), (jlo, jhi)
+        assert np.array_equal(zu[:, r0:r0 + n, 1:-1], ref_zu[:, jlo - 1:jhi, 1:-1]), (jlo, jhi)
+        ctx.close()
+
+
+def test_clinic_needs_setup(pkg):
+    case = _case(pkg, 34, 30, 8, 33)
+    ctx = pkg.TracerContext(case)
+    with pytest.raises(pkg.api.UvicError):
+        ctx.clinic(1.0)
+    ctx.clinic_setup(case)
+    with pytest.raises(pkg.api.UvicError):
+        ctx.clinic(1.0, 1, 2)      # wind stress slots without uvic_b200_sbc_setup
+    ctx.close()

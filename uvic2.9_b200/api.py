@@ -61,6 +61,12 @@ class GasbcPar(C.Structure):
                [("co2ccn", C.c_double), ("dc13ccn", C.c_double), ("dc14ccn", C.c_double)]
 
 
+class ClinicStatic(C.Structure):
+    _fields_ = [("kmu", _c_int_p)] + [(n, _c_double_p) for n in (
+        "hr", "cori", "advmet", "am3", "am4", "dxmetr", "dxu2r", "dyu2r", "dyu4r", "csudyu2r", "visc_ceu", "amc_north",
+        "amc_south")] + [(n, C.c_double) for n in ("kappa_m", "cdbot", "grav_rho0r")]
+
+
 # every symbol include/uvic_b200.h declares
 ABI_SYMBOLS = [
     "uvic_b200_create", "uvic_b200_destroy", "uvic_b200_last_error", "uvic_b200_set_stream", "uvic_b200_synchronize",
@@ -74,6 +80,8 @@ ABI_SYMBOLS = [
     "uvic_b200_sbc_setup", "uvic_b200_upload_sbc", "uvic_b200_upload_sbc_slot", "uvic_b200_download_sbc",
     "uvic_b200_download_sbc_slot", "uvic_b200_setvbc", "uvic_b200_set_sbc", "uvic_b200_tracer_step_coupled",
     "uvic_b200_tavg_accumulate", "uvic_b200_tavg_fetch", "uvic_b200_state", "uvic_b200_gasbc", "uvic_b200_wait_before_advection",
+    "uvic_b200_clinic_setup", "uvic_b200_upload_u_level", "uvic_b200_download_u", "uvic_b200_upload_smf", "uvic_b200_clinic",
+    "uvic_b200_download_zu", "uvic_b200_rotate_u",
 ]
 
 _lib = None
@@ -138,6 +146,13 @@ def load_library():
     L.uvic_b200_tavg_accumulate.argtypes = [vp, vp, vp]
     L.uvic_b200_tavg_fetch.argtypes = [vp, vp, vp, _c_int_p, C.c_int]
     L.uvic_b200_tracer_step_coupled.argtypes = [vp, C.POINTER(StepInfo)] + [vp] * 5 + [C.c_int] * 4 + [vp, vp]
+    L.uvic_b200_clinic_setup.argtypes = [vp, C.POINTER(ClinicStatic)]
+    L.uvic_b200_upload_u_level.argtypes = [vp, C.c_int, vp]
+    L.uvic_b200_download_u.argtypes = [vp, C.c_int, vp]
+    L.uvic_b200_upload_smf.argtypes = [vp, vp]
+    L.uvic_b200_clinic.argtypes = [vp, C.c_double, C.c_int, C.c_int]
+    L.uvic_b200_download_zu.argtypes = [vp, vp]
+    L.uvic_b200_rotate_u.argtypes = [vp]
     _lib = L
     return L
 
@@ -160,6 +175,7 @@ _JAXIS = {
     "addisop": 0, "edrm2": 0, "edrs2": 0, "edrk1": 0, "edro1": 0,
     "adv_vet": 0, "adv_vnt": 0, "adv_vbt": 0, "stf": 1, "btf": 1, "u": 1, "t": 2,
     "dnswr": 0, "aice": 0, "hice": 0, "hsno": 0,
+    "kmu": 0, "hr": 0, "cori": 1, "visc_ceu": 0, "amc_north": 0, "amc_south": 0, "um1": 1, "taux": 0, "tauy": 0,
 }
 
 
@@ -366,6 +382,59 @@ class TracerContext:
         self._ck(self.L.uvic_b200_tracer_step_coupled(self.h, C.byref(si), _vp(adv_vet), _vp(adv_vnt), _vp(adv_vbt), _vp(sbc_in),
                                                       _vp(bhf), int(eots), int(osegs), int(osege), int(ntspos), _vp(ts_taup1),
                                                       _vp(sbc_out)))
+
+    # ---- baroclinic momentum step (09/mom/clinic.F) ----
+    def clinic_setup(self, case=None):
+        """Time-invariant inputs of clinic from a Case prepared by synthetic.add_momentum (or any dict-like with the same
+        arrays / scalars)."""
+        case = case or self.case
+        a, s = case.arrays, case.scalars
+        cs = ClinicStatic()
+        keep = []
+        kmu = np.ascontiguousarray(slab_slice("kmu", a["kmu"], self.jbase, self.jl), dtype=np.int32)
+        keep.append(kmu)
+        cs.kmu = kmu.ctypes.data_as(_c_int_p)
+        for n in ("hr", "cori", "visc_ceu", "amc_north", "amc_south"):
+            x = np.ascontiguousarray(slab_slice(n, a[n], self.jbase, self.jl, case), dtype=np.float64)
+            keep.append(x)
+            setattr(cs, n, _dp(x))
+        for n in ("advmet", "am3", "am4", "dxmetr", "dxu2r", "dyu2r", "dyu4r", "csudyu2r"):
+            x = np.ascontiguousarray(a[n], dtype=np.float64)
+            keep.append(x)
+            setattr(cs, n, _dp(x))
+        cs.kappa_m, cs.cdbot, cs.grav_rho0r = float(s["kappa_m"]), float(s["cdbot"]), float(s["grav_rho0r"])
+        self._ck(self.L.uvic_b200_clinic_setup(self.h, C.byref(cs)))
+
+    def shape_u(self):
+        return (2, self.jl, self.km, self.imt)
+
+    def upload_u_level(self, level, u_local):
+        u_local = np.ascontiguousarray(u_local, dtype=np.float64)
+        assert u_local.shape == self.shape_u(), (u_local.shape, self.shape_u())
+        self._ck(self.L.uvic_b200_upload_u_level(self.h, int(level), _vp(u_local)))
+        self.synchronize()
+
+    def download_u(self, level):
+        out = np.empty(self.shape_u())
+        self._ck(self.L.uvic_b200_download_u(self.h, int(level), _vp(out)))
+        return out
+
+    def upload_smf(self, smf_local):
+        smf_local = np.ascontiguousarray(smf_local, dtype=np.float64)
+        assert smf_local.shape == (2, self.jl, self.imt)
+        self._ck(self.L.uvic_b200_upload_smf(self.h, _vp(smf_local)))
+        self.synchronize()
+
+    def clinic(self, c2dtuv, itaux=0, itauy=0):
+        self._ck(self.L.uvic_b200_clinic(self.h, float(c2dtuv), int(itaux), int(itauy)))
+
+    def download_zu(self):
+        out = np.empty((2, self.jl, self.imt))
+        self._ck(self.L.uvic_b200_download_zu(self.h, _vp(out)))
+        return out
+
+    def rotate_u(self):
+        self._ck(self.L.uvic_b200_rotate_u(self.h))
 
     # ---- time averages (09/mom/timeavgs.F avgvar / avgout, tracer part) ----
     def tavg_accumulate(self, vflux_local=None, gaost=None):

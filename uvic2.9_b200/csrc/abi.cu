@@ -86,6 +86,7 @@ int uvic_b200_create(const uvic_b200_dims *d, const uvic_b200_grid *g, const uvi
   ctx->main_done_event = nullptr; ctx->copy_in = ctx->copy_out = nullptr; ctx->h2d_event = nullptr; ctx->h2d_vbc_event = nullptr;
   ctx->rho_dev = nullptr;
   ctx->halo_event = nullptr;
+  ctx->clinic = nullptr;
   ctx->tavg_t = ctx->tavg_stf = ctx->tavg_tmp = ctx->tavg_vflux = ctx->tavg_gaost = nullptr; ctx->navgts = 0; ctx->d2h_dst = nullptr; ctx->d2h_ntr = 0;
   DevView &v = ctx->v;
   memset(&v, 0, sizeof v);
@@ -300,6 +301,7 @@ int uvic_b200_destroy(uvic_b200_ctx *ctx) {
   if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
   if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
   for (auto e : ctx->ev_batch) cudaEventDestroy(e);
+  delete ctx->clinic;
   delete ctx;
   return 0;
 }
@@ -509,6 +511,92 @@ int uvic_b200_tavg_fetch(uvic_b200_ctx *ctx, double *avg_t, double *avg_stf, int
   }
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaGetLastError());
+  return 0;
+}
+
+// ---- baroclinic momentum step on the device (09/mom/clinic.F) ----
+int uvic_b200_clinic_setup(uvic_b200_ctx *ctx, const uvic_b200_clinic_static *cs) {
+  if (!ctx || !cs) return fail(ctx, "clinic_setup: null argument");
+  if (ctx->clinic) return fail(ctx, "clinic_setup: already set up");
+  if (!cs->kmu || !cs->hr || !cs->cori || !cs->advmet || !cs->am3 || !cs->am4 || !cs->dxmetr || !cs->dxu2r || !cs->dyu2r ||
+      !cs->dyu4r || !cs->csudyu2r || !cs->visc_ceu || !cs->amc_north || !cs->amc_south)
+    return fail(ctx, "clinic_setup: every array of uvic_b200_clinic_static is required");
+  DevView &v = ctx->v;
+  for (long long x = 0; x < v.n2; x++)
+    if (cs->kmu[x] < 0 || cs->kmu[x] > v.km) return fail(ctx, "clinic_setup: kmu out of range");
+  ClinicView *cv = new ClinicView();
+  memset(cv, 0, sizeof *cv);
+  ctx->clinic = cv;
+#define CALLOC(field, n, init) \
+  if (dev_alloc(ctx, #field, const_cast<double **>(&cv->field), (size_t)(n), (const double *)(init))) return 1
+  if (dev_alloc(ctx, "kmu", const_cast<int **>(&cv->kmu), (size_t)v.n2, (const int *)cs->kmu)) return 1;
+  CALLOC(hr, v.n2, cs->hr); CALLOC(cori, v.n2 * 2, cs->cori);
+  CALLOC(advmet, v.jmt * 2, cs->advmet); CALLOC(am3, v.jmt, cs->am3); CALLOC(am4, v.jmt * 2, cs->am4);
+  CALLOC(dxmetr, v.imt, cs->dxmetr); CALLOC(dxu2r, v.imt, cs->dxu2r);
+  CALLOC(dyu2r, v.jmt, cs->dyu2r); CALLOC(dyu4r, v.jmt, cs->dyu4r); CALLOC(csudyu2r, v.jmt, cs->csudyu2r);
+  CALLOC(visc_ceu, v.n3, cs->visc_ceu); CALLOC(amc_north, v.n3, cs->amc_north); CALLOC(amc_south, v.n3, cs->amc_south);
+  CALLOC(u_m1, v.n3 * 2, nullptr); CALLOC(u_p1, v.n3 * 2, nullptr);
+  CALLOC(adv_veu, v.n3, nullptr); CALLOC(adv_vnu, v.n3, nullptr); CALLOC(adv_vbu, v.n3z, nullptr);
+  CALLOC(smf, v.n2 * 2, nullptr); CALLOC(bmf, v.n2 * 2, nullptr); CALLOC(zu, v.n2 * 2, nullptr);
+  CALLOC(grad_p, v.n3 * 2, nullptr); CALLOC(rho, v.n3, nullptr);
+#undef CALLOC
+  cv->kappa_m = cs->kappa_m; cv->cdbot = cs->cdbot; cv->grav_rho0r = cs->grav_rho0r;
+  cv->jc0 = std::max(2, v.jlo);
+  cv->jc1 = std::min(v.jmt - 1, v.jhi);
+  return 0;
+}
+int uvic_b200_upload_u_level(uvic_b200_ctx *ctx, int level, const double *u) {
+  if (!ctx || !u) return fail(ctx, "upload_u_level: null argument");
+  double *dst = nullptr;
+  if (level == 0) dst = ctx->v.u;
+  else if (level == -1 && ctx->clinic) dst = ctx->clinic->u_m1;
+  else return fail(ctx, "upload_u_level: level must be 0, or -1 after uvic_b200_clinic_setup");
+  CK(cudaMemcpyAsync(dst, u, (size_t)ctx->v.n3 * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+int uvic_b200_download_u(uvic_b200_ctx *ctx, int level, double *u) {
+  if (!ctx || !u) return fail(ctx, "download_u: null argument");
+  const double *src = nullptr;
+  if (level == 0) src = ctx->v.u;
+  else if (ctx->clinic && (level == -1 || level == 1)) src = level < 0 ? ctx->clinic->u_m1 : ctx->clinic->u_p1;
+  else return fail(ctx, "download_u: level must be 0, or -1 / +1 after uvic_b200_clinic_setup");
+  CK(cudaMemcpyAsync(u, src, (size_t)ctx->v.n3 * 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int uvic_b200_upload_smf(uvic_b200_ctx *ctx, const double *smf) {
+  if (!ctx || !ctx->clinic || !smf) return fail(ctx, "upload_smf: call uvic_b200_clinic_setup first");
+  CK(cudaMemcpyAsync(ctx->clinic->smf, smf, (size_t)ctx->v.n2 * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+int uvic_b200_clinic(uvic_b200_ctx *ctx, double c2dtuv, int itaux, int itauy) {
+  if (!ctx || !ctx->clinic) return fail(ctx, "clinic: call uvic_b200_clinic_setup first");
+  DevView &v = ctx->v;
+  if (itaux != 0 || itauy != 0) {
+    if (!v.sbc) return fail(ctx, "clinic: wind stress slots need uvic_b200_sbc_setup (pass 0, 0 to use uvic_b200_upload_smf)");
+    if (itaux < 1 || itaux > v.numsbc || itauy < 1 || itauy > v.numsbc) return fail(ctx, "clinic: wind stress slot out of range");
+  }
+  ctx->clinic->c2dtuv = c2dtuv;
+  set_levels(ctx, true);
+  launch_state(ctx, v.t_0, ctx->clinic->rho);   // 09/mom/loadmw.F:150-155: rho of t(tau)
+  launch_setvbc_mom(ctx, itaux, itauy);
+  launch_clinic(ctx);
+  CK(cudaGetLastError());
+  return 0;
+}
+int uvic_b200_download_zu(uvic_b200_ctx *ctx, double *zu) {
+  if (!ctx || !ctx->clinic || !zu) return fail(ctx, "download_zu: call uvic_b200_clinic_setup first");
+  CK(cudaMemcpyAsync(zu, ctx->clinic->zu, (size_t)ctx->v.n2 * 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int uvic_b200_rotate_u(uvic_b200_ctx *ctx) {
+  if (!ctx || !ctx->clinic) return fail(ctx, "rotate_u: call uvic_b200_clinic_setup first");
+  ClinicView *cv = ctx->clinic;
+  double *old_m1 = cv->u_m1;
+  cv->u_m1 = ctx->v.u;
+  ctx->v.u = cv->u_p1;
+  cv->u_p1 = old_m1;
   return 0;
 }
 

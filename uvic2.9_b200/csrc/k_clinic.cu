@@ -1,0 +1,258 @@
+// k_clinic.cu -- the baroclinic momentum step on the device, with the options of
+// run/mk.in: O_consthmix + O_anisotropic_viscosity, O_constvmix (explicit vertical viscosity), O_stream_function
+// (explicit Coriolis), no O_biharmonic / O_implicitvmix / O_pressure_gradient_average.
+//
+//   k_clinic_advvel   source/mom/adv_vel.F:160-250   advective velocities on the east / north / bottom faces of U cells
+//   k_setvbc_mom      09/mom/setvbc.F:163-208        surface stress (coupler slots) and quadratic bottom drag
+//   k_clinic_column   09/mom/clinic.F:60-511 + 09/mom/fdifm.h
+//
+// k_clinic_column: one thread per U column (i fastest, so every level is one coalesced row segment), both velocity
+// components at once.  The hydrostatic pressure gradient is the running sum the reference builds in grad_p (:150-177) and
+// stays in two registers; the vertical fluxes through the bottom face of level k are the top-face fluxes of level k+1 and
+// are carried, not recomputed.  Pass 1 writes u(tau-1) + c2dtuv * du/dt and accumulates the two depth sums (zu: forcing
+// of the barotropic equation, :378-397; baru: the vertical mean that is removed, :458-485) in the reference's k order;
+// pass 2 subtracts the mean from the wet levels (the column is L1/L2 resident).  Operation order inside every expression
+// is the reference's (the library is compiled without FMA contraction), so the result is bit-identical to the oracle.
+// The diagnostics hooks (diagc1, diagc2), the ice coupling (isbcu, asbcu) and filuv stay on the host.
+#include "ctx.h"
+
+#define U0(i, k, j, n) v.u[X3(i, k, j) + (long long)((n)-1) * v.n3]
+#define UM(i, k, j, n) cv.u_m1[X3(i, k, j) + (long long)((n)-1) * v.n3]
+#define UP(i, k, j, n) cv.u_p1[X3(i, k, j) + (long long)((n)-1) * v.n3]
+
+// one thread per (i, k = 0..km, j); rows jc0-1..jc1 (adv_vnu) and jc0..jc1 (adv_veu, adv_vbu)
+__global__ void __launch_bounds__(256) k_clinic_advvel(const DevView v, const ClinicView cv) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int ni = v.imt - 2, nk = v.km + 1, nj = cv.jc1 - cv.jc0 + 2;
+  if (idx >= (long long)ni * nk * nj) return;
+  const int i = (int)(idx % ni) + 2;
+  const long long r = idx / ni;
+  const int k = (int)(r % nk);
+  const int j = (int)(r / nk) + cv.jc0 - 1;
+  const bool west = (i == 2), east = (i == v.imt - 1);
+  if (k >= 1) {
+    // adv_vnu = LINEAR_INTRP_Y(WT_AVG_X(adv_vnt)) (:173-186)
+    const double dyr = v.dytr[j];
+    const double val = ((v.adv_vnt[X3(i, k, j)] * v.duw[i - 1] + v.adv_vnt[X3(i + 1, k, j)] * v.due[i - 1]) * v.dus[j] +
+                        (v.adv_vnt[X3(i, k, j + 1)] * v.duw[i - 1] + v.adv_vnt[X3(i + 1, k, j + 1)] * v.due[i - 1]) * v.dun[j - 1]) *
+                       dyr * v.dxur[i - 1];
+    const long long line = X3(1, k, j);
+    cv.adv_vnu[line + i - 1] = val;
+    if (west) cv.adv_vnu[line + v.imt - 1] = val;
+    if (east) cv.adv_vnu[line] = val;
+  }
+  if (j < cv.jc0) return;
+  if (k >= 1) {
+    // adv_veu = LINEAR_INTRP_X(WT_AVG_Y(adv_vet)), cyclic (:200-219)
+    const double dyr = v.dyur[j - 1];
+    const double val = ((v.adv_vet[X3(i, k, j)] * v.dus[j - 1] + v.adv_vet[X3(i, k, j + 1)] * v.dun[j - 1]) * v.duw[i] +
+                        (v.adv_vet[X3(i + 1, k, j)] * v.dus[j - 1] + v.adv_vet[X3(i + 1, k, j + 1)] * v.dun[j - 1]) * v.due[i - 1]) *
+                       dyr * v.dxtr[i];
+    const long long line = X3(1, k, j);
+    cv.adv_veu[line + i - 1] = val;
+    if (west) cv.adv_veu[line + v.imt - 1] = val;
+    if (east) cv.adv_veu[line] = val;
+  }
+  {
+    // bottom face (:226-250)
+    const double dyn = v.dun[j - 1] * v.cst[j];
+    const double dys = v.dus[j - 1] * v.cst[j - 1];
+    const double dyr = v.dyur[j - 1] * v.csur[j - 1];
+    const double asw = v.duw[i - 1] * dys, anw = v.duw[i - 1] * dyn, ase = v.due[i - 1] * dys, ane = v.due[i - 1] * dyn;
+    const double val = dyr * v.dxur[i - 1] *
+                       (v.adv_vbt[X3Z(i, k, j)] * asw + v.adv_vbt[X3Z(i + 1, k, j)] * ase + v.adv_vbt[X3Z(i, k, j + 1)] * anw +
+                        v.adv_vbt[X3Z(i + 1, k, j + 1)] * ane);
+    const long long line = X3Z(1, k, j);
+    cv.adv_vbu[line + i - 1] = val;
+    if (west) cv.adv_vbu[line + v.imt - 1] = val;
+    if (east) cv.adv_vbu[line] = val;
+  }
+}
+
+// 09/mom/setvbc.F:163-208: every local row, i = 2..imt-1 then the cyclic copies.  itaux = 0 keeps an uploaded smf.
+__global__ void __launch_bounds__(128) k_setvbc_mom(const DevView v, const ClinicView cv, int itaux, int itauy) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int ni = v.imt - 2;
+  if (idx >= (long long)ni * v.jl) return;
+  const int i = (int)(idx % ni) + 2;
+  const int j = (int)(idx / ni) + v.jbase;
+  const int kz = cv.kmu[X2(i, j)];
+  double s[2], b[2];
+  if (itaux > 0) {
+    const double um = (kz >= 1) ? 1.0 : 0.0;   // umask(i,1,j)
+    s[0] = v.sbc[X2(i, j) + (long long)(itaux - 1) * v.n2] * um;
+    s[1] = v.sbc[X2(i, j) + (long long)(itauy - 1) * v.n2] * um;
+  }
+  if (cv.cdbot == 0.0 || kz == 0) {
+    b[0] = b[1] = 0.0;
+  } else {
+    const double u1 = UM(i, kz, j, 1), u2 = UM(i, kz, j, 2);
+    const double uvmag = sqrt(u1 * u1 + u2 * u2);
+    b[0] = cv.cdbot * u1 * uvmag;
+    b[1] = cv.cdbot * u2 * uvmag;
+  }
+  for (int n = 0; n < 2; n++) {
+    const long long line = X2(1, j) + (long long)n * v.n2;
+    if (itaux > 0) {
+      cv.smf[line + i - 1] = s[n];
+      if (i == 2) cv.smf[line + v.imt - 1] = s[n];
+      if (i == v.imt - 1) cv.smf[line] = s[n];
+    }
+    cv.bmf[line + i - 1] = b[n];
+    if (i == 2) cv.bmf[line + v.imt - 1] = b[n];
+    if (i == v.imt - 1) cv.bmf[line] = b[n];
+  }
+}
+
+__global__ void __launch_bounds__(128) k_clinic_column(const DevView v, const ClinicView cv) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int ni = v.imt - 2;
+  if (idx >= (long long)ni * (cv.jc1 - cv.jc0 + 1)) return;
+  const int i = (int)(idx % ni) + 2;
+  const int j = (int)(idx / ni) + cv.jc0;
+  const int km = v.km;
+  const bool west = (i == 2), east = (i == v.imt - 1);
+  const int kb = cv.kmu[X2(i, j)];
+  const int kmt_ij = v.kmt[X2(i, j)];          // visc_cbu lives on T-cell levels (09/mom/vmixc.F:84-85)
+  const double hr = cv.hr[X2(i, j)];
+  const double c2dtuv = cv.c2dtuv;
+
+  // row / column constants (09/mom/clinic.F:75-82, 119-147)
+  const double csur = v.csur[j - 1];
+  const double csudxur = csur * v.dxur[i - 1];
+  const double csudxu2r = csur * v.dxur[i - 1] * 0.5;
+  const double csudyu2r = cv.csudyu2r[j - 1];
+  const double dxtr_e = v.dxtr[i], dxtr_w = v.dxtr[i - 1];
+  const double dxu2r = cv.dxu2r[i - 1];
+  const double g = cv.grav_rho0r;
+  const double am3 = cv.am3[j - 1];
+  const double am4d[2] = {cv.am4[j - 1] * cv.dxmetr[i - 1], cv.am4[(j - 1) + v.jmt] * cv.dxmetr[i - 1]};
+  const double advmet[2] = {cv.advmet[j - 1], cv.advmet[(j - 1) + v.jmt]};
+  const double cori[2] = {cv.cori[X2(i, j)], cv.cori[X2(i, j) + v.n2]};
+  const double smf[2] = {cv.smf[X2(i, j)], cv.smf[X2(i, j) + v.n2]};
+  const double bmf[2] = {cv.bmf[X2(i, j)], cv.bmf[X2(i, j) + v.n2]};
+
+  double gp[2] = {0.0, 0.0};          // grad_p(i,k,j,:) integrated downward
+  double rp[4] = {0.0, 0.0, 0.0, 0.0};   // rho of the level above at (i,j) (i+1,j) (i,j+1) (i+1,j+1)
+  double afb_up[2], dfb_up[2];        // fluxes through the top face of the current level
+  double zu[2] = {0.0, 0.0}, bar[2] = {0.0, 0.0};
+
+  for (int k = 1; k <= km; k++) {
+    double tend[2] = {0.0, 0.0};
+    if (k <= kb) {
+      // ---- pressure gradient at this level ----
+      const double r00 = cv.rho[X3(i, k, j)], r10 = cv.rho[X3(i + 1, k, j)], r01 = cv.rho[X3(i, k, j + 1)], r11 = cv.rho[X3(i + 1, k, j + 1)];
+      if (k == 1) {
+        const double fxa = g * v.dzw[0] * csur, fxb = g * v.dzw[0] * cv.dyu2r[j - 1];
+        const double t1 = r11 - r00, t2 = r01 - r10;
+        gp[0] = (t1 - t2) * fxa * dxu2r;
+        gp[1] = (t1 + t2) * fxb;
+      } else {
+        const double fxa = g * csur * 0.5, fxb = g * cv.dyu4r[j - 1];
+        const double e00 = rp[0] + r00, e10 = rp[1] + r10, e01 = rp[2] + r01, e11 = rp[3] + r11;   // tempik (:150-157)
+        const double t1 = e11 - e00, t2 = e01 - e10;
+        gp[0] = gp[0] + fxa * (t1 - t2) * v.dzw[k - 1] * dxu2r;
+        gp[1] = gp[1] + fxb * (t1 + t2) * v.dzw[k - 1];
+      }
+      rp[0] = r00; rp[1] = r10; rp[2] = r01; rp[3] = r11;
+      if (cv.grad_p) {
+        cv.grad_p[X3(i, k, j)] = gp[0];
+        cv.grad_p[X3(i, k, j) + v.n3] = gp[1];
+      }
+      // ---- operands ----
+      double u0c[2], u0e[2], u0w[2], u0n[2], u0s[2], u0d[2], umc[2], ume[2], umw[2], umn[2], ums[2], umd[2];
+      const int kd = (k < km) ? k + 1 : km;
+#pragma unroll
+      for (int n = 0; n < 2; n++) {
+        u0c[n] = U0(i, k, j, n + 1); u0e[n] = U0(i + 1, k, j, n + 1); u0w[n] = U0(i - 1, k, j, n + 1);
+        u0n[n] = U0(i, k, j + 1, n + 1); u0s[n] = U0(i, k, j - 1, n + 1); u0d[n] = U0(i, kd, j, n + 1);
+        umc[n] = UM(i, k, j, n + 1); ume[n] = UM(i + 1, k, j, n + 1); umw[n] = UM(i - 1, k, j, n + 1);
+        umn[n] = UM(i, k, j + 1, n + 1); ums[n] = UM(i, k, j - 1, n + 1); umd[n] = UM(i, kd, j, n + 1);
+      }
+      const double veu_e = cv.adv_veu[X3(i, k, j)], veu_w = cv.adv_veu[X3(i - 1, k, j)];
+      const double vnu_n = cv.adv_vnu[X3(i, k, j)], vnu_s = cv.adv_vnu[X3(i, k, j - 1)];
+      const double vbu_lo = cv.adv_vbu[X3Z(i, k, j)];
+      const double amx_e = cv.visc_ceu[X3(i, k, j)] * csur * dxtr_e;      // am_csudxtr(i,k,j)   (:80)
+      const double amx_w = cv.visc_ceu[X3(i - 1, k, j)] * csur * dxtr_w;  // am_csudxtr(i-1,k,j)
+      const double amcn = cv.amc_north[X3(i, k, j)], amcs = cv.amc_south[X3(i, k, j)];
+      const double visc_lo = (k <= kmt_ij - 1) ? cv.kappa_m : 0.0;
+#pragma unroll
+      for (int n = 0; n < 2; n++) {
+        const int o = 1 - n;
+        if (k == 1) {
+          // surface b.c. (:309-313)
+          dfb_up[n] = smf[n];
+          afb_up[n] = cv.adv_vbu[X3Z(i, 0, j)] * (u0c[n] + u0c[n]);
+        }
+        // bottom face of level k (:283-293, 310-314)
+        double afb_lo, dfb_lo;
+        if (k < km) {
+          afb_lo = vbu_lo * (u0c[n] + u0d[n]);
+          dfb_lo = visc_lo * v.dzwr[k] * (umc[n] - umd[n]);
+        } else {
+          afb_lo = vbu_lo * u0c[n];
+          dfb_lo = 0.0;                 // diff_fb(i,km,j) is only ever set through kb = km
+        }
+        const double dfb_reg = dfb_lo;
+        if (k == kb) dfb_lo = bmf[n];
+        const double afe_e = veu_e * (u0c[n] + u0e[n]), afe_w = veu_w * (u0w[n] + u0c[n]);
+        const double dfe_e = amx_e * (ume[n] - umc[n]), dfe_w = amx_w * (umc[n] - umw[n]);
+        // 09/mom/fdifm.h
+        const double DIFF_Ux = (dfe_e - dfe_w) * csudxur;
+        const double DIFF_Uy = amcn * (umn[n] - umc[n]) - amcs * (umc[n] - ums[n]);
+        const double DIFF_Uz = (dfb_up[n] - dfb_lo) * v.dztr[k - 1];
+        const double DIFF_metric = am3 * umc[n] + am4d[n] * (ume[o] - umw[o]);
+        const double ADV_Ux = (afe_e - afe_w) * csudxu2r;
+        const double ADV_Uy = (vnu_n * (u0c[n] + u0n[n]) - vnu_s * (u0s[n] + u0c[n])) * csudyu2r;
+        const double ADV_Uz = (afb_up[n] - afb_lo) * v.dzt2r[k - 1];
+        const double ADV_metric = advmet[n] * u0c[0] * u0c[o];
+        const double CORIOLIS = cori[n] * u0c[o];
+        tend[n] = DIFF_Ux + DIFF_Uy + DIFF_Uz + DIFF_metric - ADV_Ux - ADV_Uy - ADV_Uz + ADV_metric - gp[n] + CORIOLIS;
+        afb_up[n] = afb_lo;
+        dfb_up[n] = dfb_reg;
+      }
+    }
+    // ---- tau+1 before the mean is removed (:444-451), depth sums in the reference's order ----
+#pragma unroll
+    for (int n = 0; n < 2; n++) {
+      zu[n] = zu[n] + tend[n] * v.dzt[k - 1];
+      const double up = UM(i, k, j, n + 1) + c2dtuv * tend[n];
+      bar[n] = bar[n] + up * v.dzt[k - 1];
+      UP(i, k, j, n + 1) = up;
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < 2; n++) {
+    cv.zu[X2(i, j) + (long long)n * v.n2] = zu[n] * hr;
+    bar[n] = bar[n] * hr;
+  }
+  // ---- pure internal modes (:476-485) and the cyclic boundary ----
+  for (int k = 1; k <= km; k++) {
+#pragma unroll
+    for (int n = 0; n < 2; n++) {
+      double up = UP(i, k, j, n + 1);
+      if (k <= kb) {
+        up = up - bar[n];
+        UP(i, k, j, n + 1) = up;
+      }
+      if (west) UP(v.imt, k, j, n + 1) = up;
+      if (east) UP(1, k, j, n + 1) = up;
+    }
+  }
+}
+
+void launch_setvbc_mom(uvic_b200_ctx *c, int itaux, int itauy) {
+  DevView &v = c->v;
+  const ClinicView &cv = *c->clinic;
+  const long long ncol = (long long)(v.imt - 2) * v.jl;
+  KLAUNCH("k_setvbc_mom", k_setvbc_mom, cdiv(ncol, 128), 128, v, cv, itaux, itauy);
+}
+
+void launch_clinic(uvic_b200_ctx *c) {
+  DevView &v = c->v;
+  const ClinicView &cv = *c->clinic;
+  const long long ncell = (long long)(v.imt - 2) * (v.km + 1) * (cv.jc1 - cv.jc0 + 2);
+  KLAUNCH("k_clinic_advvel", k_clinic_advvel, cdiv(ncell, 256), 256, v, cv);
+  const long long ncol = (long long)(v.imt - 2) * (cv.jc1 - cv.jc0 + 1);
+  KLAUNCH("k_clinic_column", k_clinic_column, cdiv(ncol, 128), 128, v, cv);
+}

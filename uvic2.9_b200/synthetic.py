@@ -417,6 +417,73 @@ def make_case(imt=102, jmt=102, km=19, nt=2, seed=SEED, names=None, dtts=None, n
     return case
 
 
+def add_momentum(case: Case, seed=SEED, am=1.5e9, kappa_m=10.0, cdbot=1.3e-3, dtuv=None) -> Case:
+    """Inputs of the baroclinic momentum step (09/mom/clinic.F) for a case made by make_case: u(tau-1), wind stress,
+    the Coriolis / metric factors of setmom (09/mom/setmom.F:777-802), the grid reciprocals of grids.F:470-530, 1/depth at
+    U points (09/mom/setmom.F:1108-1111) and the anisotropic viscosity coefficients in the shape hmixc leaves them
+    (09/mom/hmixc.F:62-150: Large et al. 2001 in the tropics above 550 m, `am` elsewhere).  Synthetic inputs only: the
+    oracle and the device read these arrays, neither derives them."""
+    a = case.arrays
+    imt, jmt, km = case.imt, case.jmt, case.km
+    rng = _rng("momentum", seed)
+    radius = 6370.0e5
+    pi = case.scalars["pi"]
+    radian = case.scalars["radian"]
+    omega = pi / 43082.0                                        # 09/common/UVic_ESCM.F: earth's rotation rate
+    xu, yu, xt, yt = a["_xu"], a["_yu"], a["_xt"], a["_yt"]
+    phi = yu / radian
+    sine, csu = np.sin(phi), a["csu"]
+    tng = sine / csu
+    cor1 = np.broadcast_to((2.0 * omega * sine)[:, None], (jmt, imt))
+    a["cori"] = np.stack([cor1, -cor1]).copy()
+    a["advmet"] = np.stack([tng / radius, -(tng / radius)])
+    a["am3"] = am * (1.0 - tng * tng) / (radius ** 2)
+    am41 = -am * 2.0 * sine / (radius * csu * csu)
+    a["am4"] = np.stack([am41, -am41])
+    dxt, dxu, dyu = a["dxt"], a["dxu"], a["dyu"]
+    dxmetr = np.empty(imt)
+    dxmetr[:-1] = 1.0 / (dxt[:-1] + dxt[1:])
+    dxmetr[-1] = dxmetr[1]
+    a["dxmetr"] = dxmetr
+    a["dxu2r"] = 0.5 / dxu
+    a["dyu2r"] = 0.5 / dyu
+    a["dyu4r"] = 0.25 / dyu
+    a["csudyu2r"] = 0.5 / (csu * dyu)
+    kmu, zw = a["kmu"], a["zw"]
+    a["hr"] = np.where(kmu > 0, 1.0 / zw[np.maximum(kmu, 1) - 1], 0.0)
+    # anisotropic viscosity
+    tropics = (np.abs(yu) <= 20.0)[:, None, None] & (zw <= 55000.0)[None, :, None]
+    dlam = 360.0 / (imt - 2)
+    dphi = 178.0 / jmt
+    coslat = np.abs(np.cos(pi / 180.0 * yu))
+    beddy = 1.0e7 * (1.0 + 24.5 * (1.0 - np.abs(np.cos(2.0 * pi / 180.0 * yu))))
+    delx = dlam * 1.11e7 * coslat
+    bmunk = 0.2 * (0.0228e-11 * coslat) * delx ** 3
+    cnu = np.where(tropics, np.maximum(bmunk, beddy)[:, None, None], am) * np.ones((jmt, km, imt))
+    gridlen = np.maximum(delx, dphi * 1.1e7)
+    ceu = np.where(tropics, (0.5 * 100.0 * gridlen)[:, None, None], am) * np.ones((jmt, km, imt))
+    cst, dytr, csur, dyur = a["cst"], a["dytr"], a["csur"], a["dyur"]
+    jp1 = np.minimum(np.arange(jmt) + 1, jmt - 1)
+    a["visc_ceu"] = ceu
+    a["amc_north"] = cnu * (cst[jp1] * dytr[jp1] * csur * dyur)[:, None, None]
+    a["amc_south"] = cnu * (cst * dytr * csur * dyur)[:, None, None]
+    # u(tau-1): u(tau) plus a masked perturbation (the vertical mean is not removed: clinic itself does that for tau+1)
+    u = a["u"]
+    pert = np.stack([_smooth2d(rng, imt, jmt, xu, yu)[:, None, :] * np.cos(pi * a["zt"] / a["zt"][-1])[None, :, None] for _ in range(2)])
+    um1 = (0.97 * u + 0.4 * pert) * a["umask"][None]
+    um1[..., 0] = um1[..., -2]
+    um1[..., -1] = um1[..., 1]
+    a["um1"] = um1
+    # wind stress (dyn cm-2): trades / westerlies plus noise
+    taux = -0.8 * np.cos(3.0 * phi)[:, None] * np.ones((jmt, imt)) + 0.2 * _smooth2d(rng, imt, jmt, xu, yu)
+    tauy = 0.2 * _smooth2d(rng, imt, jmt, xu, yu)
+    a["taux"], a["tauy"] = taux, tauy
+    if dtuv is None:
+        dtuv = case.scalars["dtts"] / 96.0                       # run/control.in:3: dtts=108000, dtuv=1125
+    case.scalars.update(c2dtuv=2.0 * dtuv, kappa_m=kappa_m, cdbot=cdbot, grav_rho0r=980.6 * (1.0 / 1.035))
+    return case
+
+
 # arrays with a j extent: axis of j in the C-ordered numpy array (1-D metric arrays of length jmt: axis 0)
 _J_1D = ("dyt", "dyu", "dytr", "dyt2r", "dyt4r", "dyur", "cst", "csu", "cstr", "csur", "cstdytr", "cstdyt2r", "csu_dyur", "dus",
          "dun", "_yt", "_yu")
