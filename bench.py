@@ -478,6 +478,65 @@ def main():
                           "note": "uvic_b200_tracer_step_coupled: setvbc / set_sbc on the device; velocities in and T,S out every "
                                   "step, the sbc array in / out once per 4-step ocean segment; other tracers resident"}
 
+    # ---- the next row of SURVEY 8(f): the baroclinic momentum step (uvic_b200_clinic) on the same grid, device resident,
+    # timed on its own (one GPU): rho = state(t(tau)), smf / bmf, U-cell advective velocities, u(tau+1), zu
+    clinic = None
+    if world == 1 and not a.workload.startswith("tenth") and os.environ.get("UVIC_B200_BENCH_CLINIC", "1") == "1":
+        pkg.synthetic.add_momentum(case)
+        slc = lambda n: np.ascontiguousarray(pkg.api.slab_slice(n, case[n], ctx.jbase, ctx.jl, case))
+        ctx.clinic_setup(case)
+        ctx.upload_u_level(0, slc("u"))
+        ctx.upload_u_level(-1, slc("um1"))
+        ctx.adv_vel()
+        ctx.upload_smf(np.stack([slc("taux"), slc("tauy")]) * slc("umask")[None, :, 0, :])
+        c2dtuv = float(case.scalars["c2dtuv"])
+        for _ in range(3):
+            ctx.clinic(c2dtuv)
+        ctx.profile_reset()
+        barrier()
+        nck = max(a.steps, 20)
+        ev0.record(stream)
+        for _ in range(nck):
+            ctx.clinic(c2dtuv)
+        ev1.record(stream)
+        barrier()
+        ms_ck = ev0.elapsed_time(ev1) / nck
+        ctx.profile_enable(True)
+        for _ in range(nck):
+            ctx.clinic(c2dtuv)
+        barrier()
+        ctx.profile_enable(False)
+        pk = {k: round(1e3 * v[0] / max(v[1], 1), 2) for k, v in ctx.profile().items() if k in ("k_clinic_column", "k_clinic_advvel", "k_setvbc_mom", "k_state")}
+        ctx.profile_reset()
+        kmu = np.asarray(case["kmu"])[1:-1, 1:-1]
+        wet_u = int(kmu.sum())
+        all_u = kmu.size * case.km
+        # compulsory bytes of k_clinic_column: per wet U cell u(tau) 2 + u(tau-1) 2 + rho 1 + adv_veu/vnu/vbu 3 + visc_ceu,
+        # amc_north, amc_south 3 reads and u(tau+1) 2 writes; per masked cell u(tau-1) 2 reads and u(tau+1) 2 writes
+        col_bytes = 8 * (13 * wet_u + 4 * (all_u - wet_u))
+        pkh = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0)) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+        col_us = pk.get("k_clinic_column")
+        clinic = {"ms_per_step": ms_ck, "steps": nck, "value": 2 * all_u / (ms_ck * 1e-3) / 1e9, "unit": "G U-cell*component/s",
+                  "kernels_us": pk,
+                  "roofline": {"bound": "hbm", "kernel": "k_clinic_column", "bytes_per_launch": col_bytes, "us_per_launch": col_us,
+                               "achieved": (col_bytes / (col_us * 1e-6) / 1e9) if col_us else None, "peak": pkh, "unit": "GB/s",
+                               "frac": (col_bytes / (col_us * 1e-6) / 1e9 / pkh) if col_us else None},
+                  "note": "uvic_b200_clinic (09/mom/clinic.F with run/mk.in options, without filuv), resident fields, CUDA events"}
+        if not a.no_cpu_baseline:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            os.environ["UVIC_ORACLE_VARIANT"] = "o3"
+            import helpers
+            oc = helpers.make_oracle(case)
+            helpers.oracle_load_momentum(oc, case)
+            helpers.oracle_clinic(oc)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                helpers.oracle_clinic(oc)
+            cpu_ms = (time.perf_counter() - t0) / 3 * 1e3
+            oc.close()
+            clinic["cpu_baseline"] = {"ms_per_step": cpu_ms, "value": 2 * all_u / (cpu_ms * 1e-3) / 1e9, "unit": "G U-cell*component/s",
+                                      "cores": 1, "kind": "port", "sample": "3 calls of the oracle's adv_vel + state + setvbc + clinic on the same grid"}
+
     # ---- conservation check on the state the timed steps produced -----------------------
     inv = ctx.inventory(0)
 
@@ -594,6 +653,7 @@ def main():
         "sim_years_per_day": 86400.0 / (292.0 * ms_step * 1e-3),
         "roofline": roofline, "roofline_top": roofline_top, "step_hbm": step_hbm, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": clk, "ms_per_step_per_rank": [round(x, 4) for x in ms_ranks], "ms_per_step_per_rank_without_exchange": solo_ranks, "ms_per_step_serialised_profile_pass": ms_prof / a.steps, "kernels": kern, "inventory_check": {"finite": bool(np.isfinite(inv).all())},
+        "next_rows": {"clinic": clinic},
     }
     _emit(line)
     ctx.close()

@@ -176,6 +176,7 @@ _JAXIS = {
     "adv_vet": 0, "adv_vnt": 0, "adv_vbt": 0, "stf": 1, "btf": 1, "u": 1, "t": 2,
     "dnswr": 0, "aice": 0, "hice": 0, "hsno": 0,
     "kmu": 0, "hr": 0, "cori": 1, "visc_ceu": 0, "amc_north": 0, "amc_south": 0, "um1": 1, "taux": 0, "tauy": 0,
+    "umask": 0, "tmask": 0,
 }
 
 
