@@ -160,8 +160,8 @@ int uvic_b200_tavg_fetch(uvic_b200_ctx *ctx, double *avg_t, double *avg_stf, int
  * Replaces `call clinic (joff, jscalc, jecalc, is, ie)` (source/mom/mom.F:390; 09/mom/clinic.F:1-511) together with the
  * U-cell half of adv_vel (source/mom/adv_vel.F:160-250) and the momentum half of setvbc (09/mom/setvbc.F:163-208), for
  * the options of run/mk.in: O_consthmix + O_anisotropic_viscosity, O_constvmix, O_stream_function.  The diagnostics
- * hooks (diagc1 / diagc2), the ice coupling (isbcu / asbcu) and the polar filter of the velocities (filuv) stay with the
- * caller.  Time-invariant inputs, host pointers copied at setup; 2-D / 3-D arrays cover the context's local rows. */
+ * hooks (diagc1 / diagc2) and the ice coupling (isbcu / asbcu) stay with the caller; the polar filter of the velocities
+ * (filuv, source/common/filuv.F) runs on the device when `fourfil` is set.  Time-invariant inputs, host pointers copied at setup; 2-D / 3-D arrays cover the context's local rows. */
 typedef struct uvic_b200_clinic_static {
   const int32_t *kmu;                              /* (imt,jl)    09/common/levind.h */
   const double *hr;                                /* (imt,jl)    1/depth at U points, 09/mom/setmom.F:1108-1111 */
@@ -171,6 +171,10 @@ typedef struct uvic_b200_clinic_static {
   const double *dyu2r, *dyu4r, *csudyu2r;          /* (jmt) global */
   const double *visc_ceu, *amc_north, *amc_south;  /* (imt,km,jl) 09/mom/hmixc.F:62-150 */
   double kappa_m, cdbot, grav_rho0r;               /* 09/common/UVic_ESCM.F:1682-1684; grav*rho0r */
+  int32_t fourfil;                                 /* O_fourfil: run filuv (source/common/filuv.F) on u(tau+1) */
+  int32_t jfrst, jfu0, jfu1, jfu2;                 /* filter rows (global), source/common/setcom.F:75-83 */
+  const double *spsin, *spcos;                     /* (imt) source/common/setcom.F:56-71; may be NULL without fourfil */
+  const double *phi;                               /* (jmt) latitude of the U rows in radians (coord.h); may be NULL without fourfil */
 } uvic_b200_clinic_static;
 int uvic_b200_clinic_setup(uvic_b200_ctx *ctx, const uvic_b200_clinic_static *cs);
 /* u(imt,km,jl,2) of a time level: upload level -1 or 0 (0 is the field uvic_b200_upload_u sets), download -1, 0 or +1 */

@@ -7,8 +7,8 @@
  *   ora_clinic      09/mom/clinic.F:60-560 with the statement functions of 09/mom/fdifm.h
  * Called as mom does with the memory window fully open: adv_vel(js=1, je=jmt), setvbc(js=1, je=jmt),
  * clinic(js=2, je=jmt-1), istrt=2, iend=imt-1 (source/mom/mom.F:300-390).
- * The diagnostics hooks (diagc1, diagc2), the ice coupling (isbcu, asbcu) and the velocity filter (filuv) are not
- * part of this restatement.
+ * The velocity filter filuv (ora_filt.c) runs when do_filter is set (O_fourfil).  The diagnostics hooks (diagc1, diagc2)
+ * and the ice coupling (isbcu, asbcu) are not part of this restatement.
  * TEST INFRASTRUCTURE ONLY (see oracle.h).
  */
 #include "oracle.h"
@@ -257,6 +257,8 @@ void ora_clinic(ora_ctx *c) {
       ora_setbcx(&UP(1, 1, j, n), imt, km);
     }
   }
+  /* polar filter of the velocities (:494-507) */
+  if (c->do_filter) ora_filuv(c);
   /* (:508-511) */
   for (int j = js; j <= je; j++) {
     ora_setbcx(&UP(1, 1, j, 1), imt, km);

@@ -88,6 +88,7 @@ ora_ctx *ora_create(int imt, int jmt, int km, int nt, int nsrc) {
   RD(grad_p, n3 * 2); RD(zu, ij * 2); RD(baru, ij * 2);
   RD(csudxur, ij); RD(csudxu2r, ij); RD(am_csudxtr, n3); RD(tempik, n3);
   c->itaux = 1; c->itauy = 2;
+  RD(spsin, imt); RD(spcos, imt); RD(phi, jmt);
   RI(mobi_idx, ORA_MOBI_NIDX);
   c->mobi = (ora_mobi_par *)calloc(1, sizeof(ora_mobi_par));
   /* the mobi parameter block is exposed as a flat double array for the tests */
@@ -101,6 +102,7 @@ void ora_destroy(ora_ctx *c) {
   if (!c) return;
   for (int a = 0; a < c->narr; a++) free(c->arr[a].ptr);
   free(c->filt_state);
+  free(c->filtu_state);
   free(c);
 }
 
@@ -122,7 +124,7 @@ const char *ora_array_name(const ora_ctx *c, int idx) { return c->arr[idx].name;
   X(c2dtuv) X(kappa_m) X(cdbot) X(grav_rho0r)
 #define ISCALARS(X) \
   X(fct) X(isopycmix) X(tidal_kv) X(do_convect) X(do_mobi) X(timavgperts) X(do_filter) \
-  X(jfrst) X(jft1) X(jft2) X(jft0) X(eots) X(osegs) X(osege) X(ntspos) X(navgts) X(itaux) X(itauy)
+  X(jfrst) X(jft1) X(jft2) X(jft0) X(eots) X(osegs) X(osege) X(ntspos) X(navgts) X(itaux) X(itauy) X(jfu0) X(jfu1) X(jfu2)
 
 int ora_set_scalar(ora_ctx *c, const char *name, double v) {
 #define X(f) if (strcmp(name, #f) == 0) { c->f = v; return 0; }

@@ -30,10 +30,10 @@ typedef struct {
 #define IETF(jj, l, k) fs->ietf[((jj)-1) + (size_t)fs->jjmax * (((l)-1) + (size_t)fs->lsegf * ((k)-1))]
 
 /* source/common/findex.F:17-93 with O_cyclic */
-static void findex(ora_ctx *c, filt_state *fs, int jf1, int jf2) {
+static void findex(ora_ctx *c, filt_state *fs, const int32_t *kxx, int jf1, int jf2) {
   const int imt = c->imt, jmt = c->jmt, imax = c->imt, kmax = c->km, lsegf = fs->lsegf;
   int *iis = (int *)calloc(lsegf + 3, sizeof(int)), *iie = (int *)calloc(lsegf + 3, sizeof(int));
-#define KXX(i, j) c->kmt[I2(i, j)]
+#define KXX(i, j) kxx[I2(i, j)]
   int jj = 0;
   for (int jrow = c->jfrst; jrow <= jmt - 1; jrow++) {
     if (jrow <= jf1 || jrow >= jf2) {
@@ -222,13 +222,18 @@ static void filtr(filt_state *fs, double *s /* 1-based: s[1..im] */, int im, int
   for (int i = 1; i <= im; i++) s[i] = ssm + sprime[i];
 }
 
+static filt_state *make_state(ora_ctx *c, const int32_t *kxx, int jf1, int jf2);
 static filt_state *get_state(ora_ctx *c) {
   if (c->filt_state) return (filt_state *)c->filt_state;
+  c->filt_state = make_state(c, c->kmt, c->jft1, c->jft2);
+  return (filt_state *)c->filt_state;
+}
+static filt_state *make_state(ora_ctx *c, const int32_t *kxx, int jf1, int jf2) {
   filt_state *fs = (filt_state *)calloc(1, sizeof(filt_state));
   const int imt = c->imt, km = c->km;
   fs->imt = imt;
   fs->km = km;
-  fs->jjmax = (c->jft1 - c->jfrst + 1) + (c->jmt - 1 - c->jft2 + 1);
+  fs->jjmax = (jf1 - c->jfrst + 1) + (c->jmt - 1 - jf2 + 1);
   if (fs->jjmax < 1) fs->jjmax = 1;
   fs->lsegf = imt / 2 + 2;
   size_t nt = (size_t)fs->jjmax * fs->lsegf * km;
@@ -248,8 +253,7 @@ static filt_state *get_state(ora_ctx *c) {
   fs->cosine = (double *)calloc((size_t)imt * 8 + 2, sizeof(double));
   fs->denom = (double *)calloc((size_t)imt * 4 + 2, sizeof(double));
   fs->sprime = (double *)calloc(imt + 2, sizeof(double));
-  findex(c, fs, c->jft1, c->jft2);
-  c->filt_state = fs;
+  findex(c, fs, kxx, jf1, jf2);
   return fs;
 }
 
@@ -309,5 +313,104 @@ void ora_filt(ora_ctx *c) {
   }
   free(tempik);
 #undef T
+#undef TEMPIK
+}
+
+/* source/common/filuv.F:1-205 (O_fourfil, O_cyclic): polar filter of the baroclinic velocities u(tau+1), called from
+   clinic as filuv(joff=0, js=2, je=jmt-1) (09/mom/clinic.F:494-507).  Strips come from findex on kmu with jfu1, jfu2
+   (source/common/setcom.F:158); the components are rotated to polar stereographic ones (spsin, spcos: setcom.F:56-71),
+   filtered with m = 2 (land-bounded strip) or m = 3 (full cyclic row), rotated back; on every row that had a strip the
+   vertical mean is removed again and the result masked. */
+void ora_filuv(ora_ctx *c) {
+  const int imt = c->imt, km = c->km, jmt = c->jmt;
+  const int js = 2, je = jmt - 1, imtm1 = imt - 1, imtm2 = imt - 2;
+  if (!c->filtu_state) c->filtu_state = make_state(c, c->kmu, c->jfu1, c->jfu2);
+  filt_state *fs = (filt_state *)c->filtu_state;
+  const int jskpu = c->jfu2 - c->jfu1;
+  double *tempik = (double *)calloc((size_t)(imt + 2) * (km + 1) * 2, sizeof(double));
+#define UP(i, k, j, n) c->up1[I4(i, k, j, n)]
+#define TEMPIK(i, k, q) tempik[(i) + (size_t)(imt + 2) * ((k) + (size_t)(km + 1) * ((q)-1))]
+  for (int n = 1; n <= 2; n++)
+    for (int j = js; j <= je; j++) ora_setbcx(&UP(1, 1, j, n), imt, km);
+  for (int j = js; j <= je; j++) {
+    int jrow = j;
+    if ((jrow > c->jfu1 && jrow < c->jfu2) || jrow < c->jfrst) continue;
+    int jj = jrow - c->jfrst + 1;
+    if (jrow >= c->jfu2) jj = jj - jskpu + 1;
+    double fx = -1.0;
+    if (c->phi[jrow - 1] > 0.0) fx = 1.0;
+    int isave = 0, ieave = 0, im = 0, m = 0, n = 0;
+    for (int l = 1; l <= fs->lsegf; l++)
+      for (int k = 1; k <= km; k++)
+        if (ISTF(jj, l, k) != 0) {
+          int is = ISTF(jj, l, k), ie = IETF(jj, l, k);
+          int iredo = 1;
+          if (is != isave || ie != ieave) {
+            iredo = 0;
+            im = ie - is + 1;
+            isave = is;
+            ieave = ie;
+            if (im != imtm2) {
+              m = 2;
+              n = (int)round((double)im * c->csu[jrow - 1] * c->csur[c->jfu0 - 1]);
+            } else {
+              m = 3;
+              n = (int)round((double)im * c->csu[jrow - 1] * c->csur[c->jfu0 - 1] * 0.5);
+            }
+          }
+          int ism1 = is - 1;
+          int iea = ie;
+          if (ie >= imt) iea = imtm1;
+          for (int i = is; i <= iea; i++) {
+            TEMPIK(i - ism1, k, 1) = -fx * UP(i, k, j, 1) * c->spsin[i - 1] - UP(i, k, j, 2) * c->spcos[i - 1];
+            TEMPIK(i - ism1, k, 2) = fx * UP(i, k, j, 1) * c->spcos[i - 1] - UP(i, k, j, 2) * c->spsin[i - 1];
+          }
+          int ieb = 0, ii = 0;
+          if (ie >= imt) {
+            ieb = ie - imtm2;
+            ii = imtm1 - is;
+            for (int i = 2; i <= ieb; i++) {
+              TEMPIK(i + ii, k, 1) = -fx * UP(i, k, j, 1) * c->spsin[i - 1] - UP(i, k, j, 2) * c->spcos[i - 1];
+              TEMPIK(i + ii, k, 2) = fx * UP(i, k, j, 1) * c->spcos[i - 1] - UP(i, k, j, 2) * c->spsin[i - 1];
+            }
+          }
+          filtr(fs, &TEMPIK(0, k, 1), im, m, n, iredo);
+          filtr(fs, &TEMPIK(0, k, 2), im, m, n, 1);
+          for (int i = is; i <= iea; i++) {
+            UP(i, k, j, 1) = fx * (-TEMPIK(i - ism1, k, 1) * c->spsin[i - 1] + TEMPIK(i - ism1, k, 2) * c->spcos[i - 1]);
+            UP(i, k, j, 2) = -TEMPIK(i - ism1, k, 1) * c->spcos[i - 1] - TEMPIK(i - ism1, k, 2) * c->spsin[i - 1];
+          }
+          if (ie >= imt)
+            for (int i = 2; i <= ieb; i++) {
+              UP(i, k, j, 1) = fx * (-TEMPIK(i + ii, k, 1) * c->spsin[i - 1] + TEMPIK(i + ii, k, 2) * c->spcos[i - 1]);
+              UP(i, k, j, 2) = -TEMPIK(i + ii, k, 1) * c->spcos[i - 1] - TEMPIK(i + ii, k, 2) * c->spsin[i - 1];
+            }
+        }
+    if (isave != 0 && ieave != 0) {
+      /* :140-166: remove the vertical mean of the filtered row, then mask */
+      for (int i = 1; i <= imt; i++) { TEMPIK(i, 1, 1) = 0.0; TEMPIK(i, 1, 2) = 0.0; }
+      for (int k = 1; k <= km; k++)
+        for (int i = 1; i <= imt; i++) {
+          TEMPIK(i, 1, 1) = TEMPIK(i, 1, 1) + UP(i, k, j, 1) * c->dzt[k - 1];
+          TEMPIK(i, 1, 2) = TEMPIK(i, 1, 2) + UP(i, k, j, 2) * c->dzt[k - 1];
+        }
+      for (int i = 1; i <= imt; i++) {
+        TEMPIK(i, 1, 1) = TEMPIK(i, 1, 1) * c->hr[I2(i, jrow)];
+        TEMPIK(i, 1, 2) = TEMPIK(i, 1, 2) * c->hr[I2(i, jrow)];
+      }
+      for (int k = 1; k <= km; k++)
+        for (int i = 1; i <= imt; i++) {
+          UP(i, k, j, 1) = UP(i, k, j, 1) - TEMPIK(i, 1, 1);
+          UP(i, k, j, 2) = UP(i, k, j, 2) - TEMPIK(i, 1, 2);
+        }
+      for (int k = 1; k <= km; k++)
+        for (int i = 1; i <= imt; i++) {
+          UP(i, k, j, 1) = UP(i, k, j, 1) * c->umask[I3(i, k, j)];
+          UP(i, k, j, 2) = UP(i, k, j, 2) * c->umask[I3(i, k, j)];
+        }
+    }
+  }
+  free(tempik);
+#undef UP
 #undef TEMPIK
 }

@@ -174,6 +174,10 @@ typedef struct ora_ctx {
   int do_filter;
   int jfrst, jft1, jft2, jft0;  /* source/common/setcom.F */
   void *filt_state;
+  int jfu0, jfu1, jfu2;         /* source/common/setcom.F:79-81 */
+  double *spsin, *spcos;        /* (imt) source/common/setcom.F:56-71 */
+  double *phi;                  /* (jmt) latitude of U rows in radians, source/common/coord.h */
+  void *filtu_state;
 } ora_ctx;
 
 /* context management (ora_core.c) */
@@ -200,6 +204,7 @@ void ora_tracer(ora_ctx *c);                           /* 09/mom/tracer.F:214-13
 void ora_diag_tbar(ora_ctx *c, int n);                 /* 09/mom/tracer.F:1516-1565 */
 void ora_mobi_columns(ora_ctx *c);                     /* 09/mom/tracer.F:310-545,848-867 */
 void ora_filt(ora_ctx *c);                             /* source/common/filt.F */
+void ora_filuv(ora_ctx *c);                            /* source/common/filuv.F */
 void ora_avgvar(ora_ctx *c);                           /* 09/mom/timeavgs.F:206-375 (tracer part) */
 void ora_avgout(ora_ctx *c);                           /* 09/mom/timeavgs.F:398-420 (time means) */
 void ora_setvbc(ora_ctx *c);                           /* 09/mom/setvbc.F:60-140 */
@@ -207,7 +212,7 @@ void ora_gasbc(ora_ctx *c);                            /* 09/common/gasbc.F:148-
 void ora_set_sbc(ora_ctx *c);                          /* 09/mom/set_sbc.F:36-83 via 09/mom/tracer.F:1270-1288 */
 void ora_adv_vel_u(ora_ctx *c);                        /* source/mom/adv_vel.F:160-250 */
 void ora_setvbc_mom(ora_ctx *c);                       /* 09/mom/setvbc.F:163-208 */
-void ora_clinic(ora_ctx *c);                           /* 09/mom/clinic.F:60-560 (run/mk.in options, without filuv) */
+void ora_clinic(ora_ctx *c);                           /* 09/mom/clinic.F:60-560 (run/mk.in options; filuv when do_filter) */
 
 /* one full step as mom.F sequences it: isopyc -> vmixc -> tracer (source/mom/mom.F:340-389) */
 void ora_step(ora_ctx *c);

@@ -553,3 +553,73 @@ def test_clinic_against_numpy_and_invariants(pkg):
     # U-cell advective velocities: the U-cell bottom velocity closes at the bottom like the T-cell one (continuity)
     vbu = o.arr("adv_vbu", sh3z)
     assert np.abs(vbu[:, 0]).max() == 0.0
+
+
+def test_filuv_properties_and_sine_series(pkg):
+    """source/common/filuv.F: rows between jfu1 and jfu2 are untouched; on filtered rows u(tau+1) is again a pure internal
+    mode and masked; a land-bounded strip (m = 2) is the truncated sine series of the rotated components
+    (filtr.F: s'(j) = 2/(im+1) sum_i s(i) sum_{w=1..n} sin(pi w i/(im+1)) sin(pi w j/(im+1)))."""
+    case = _filter_case(pkg)
+    pkg.synthetic.add_momentum(case)
+    s, a = case.scalars, case.arrays
+    imt, jmt, km = case.imt, case.jmt, case.km
+    assert 1 <= s["jfrst"] <= s["jfu1"] < s["jfu2"] <= jmt
+    o = make_oracle(case)
+    rng = np.random.default_rng(5)
+    up = (a["um1"] + 0.5 * rng.standard_normal(a["um1"].shape)) * a["umask"][None]
+    up[..., 0], up[..., -1] = up[..., -2], up[..., 1]
+    o.arr("up1", up.shape)[...] = up
+    o.call("ora_filuv")
+    after = o.arr("up1", up.shape).copy()
+    rows = np.arange(1, jmt + 1)
+    unfiltered = ((rows > s["jfu1"]) & (rows < s["jfu2"])) | (rows < s["jfrst"])
+    unfiltered[0] = unfiltered[-1] = True
+    assert np.array_equal(after[:, unfiltered], up[:, unfiltered])
+    wetrow = (a["kmu"][:, 1:-1] > 0).any(axis=1)
+    polar = ~unfiltered & wetrow
+    assert polar.sum() >= 4 and np.abs(after[:, polar] - up[:, polar]).max() > 1e-3
+    mean = (after * a["dzt"][None, None, :, None]).sum(axis=2) * a["hr"][None]
+    assert np.abs(mean[:, polar][..., 1:-1]).max() < 1e-12 * np.abs(after).max()
+    assert np.all(after[:, polar] * (1.0 - a["umask"][polar])[None] == 0.0)
+    # one land-bounded strip at the surface, before the mean removal: reproduce filtr's m = 2 by the sine series
+    checked = 0
+    for j in np.nonzero(polar)[0]:
+        wet = a["kmu"][j, 1:-1] >= 1
+        if wet.all():
+            continue
+        # strips of the surface level (1-based i = 2..imt-1)
+        idx = np.nonzero(wet)[0] + 2
+        runs = np.split(idx, np.nonzero(np.diff(idx) > 1)[0] + 1)
+        runs = [r for r in runs if len(r) >= 3 and r[0] > 2 and r[-1] < imt - 1]
+        if not runs:
+            continue
+        r = runs[0]
+        im = len(r)
+        n = int(round(im * a["csu"][j] * a["csur"][s["jfu0"] - 1]))
+        fx = 1.0 if a["phi"][j] > 0 else -1.0
+        ii = r - 1
+        u1, u2 = up[0, j, 0, ii], up[1, j, 0, ii]
+        t1 = -fx * u1 * a["spsin"][ii] - u2 * a["spcos"][ii]
+        t2 = fx * u1 * a["spcos"][ii] - u2 * a["spsin"][ii]
+        p = np.arange(1, im + 1)
+        S = np.sin(np.pi * np.outer(np.arange(1, n + 1), p) / (im + 1))     # (n, im)
+        P = (2.0 / (im + 1)) * S.T @ S
+        f1, f2 = P @ t1, P @ t2
+        v1 = fx * (-f1 * a["spsin"][ii] + f2 * a["spcos"][ii])
+        v2 = -f1 * a["spcos"][ii] - f2 * a["spsin"][ii]
+        # undo the oracle's vertical-mean removal at the surface level for the comparison
+        kb = a["kmu"][j, ii]
+        o2 = make_oracle(case)
+        col = up.copy()
+        o2.arr("up1", up.shape)[...] = col
+        o2.arr("hr")[...] = 0.0                   # hr = 0: the mean that is removed vanishes
+        o2.call("ora_filuv")
+        raw = o2.arr("up1", up.shape)
+        assert np.abs(raw[0, j, 0, ii] - v1).max() < 1e-10 * max(np.abs(v1).max(), 1.0)
+        assert np.abs(raw[1, j, 0, ii] - v2).max() < 1e-10 * max(np.abs(v2).max(), 1.0)
+        o2.close()
+        checked += 1
+        if checked >= 2:
+            break
+    assert checked >= 1
+    o.close()

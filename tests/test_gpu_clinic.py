@@ -26,14 +26,14 @@ def _sbc_with_stress(case, numsbc):
     return sbc
 
 
-def _device_clinic(pkg, case, jlo=None, jhi=None, use_slots=True, smf=None):
+def _device_clinic(pkg, case, jlo=None, jhi=None, use_slots=True, smf=None, fourfil=False):
     """one context (optionally a slab), loaded from the global case; returns the context after clinic has run"""
     ctx = pkg.TracerContext(case, jlo=jlo, jhi=jhi)
     ctx.load_state()
     sl = lambda n: pkg.api.slab_slice(n, case[n], ctx.jbase, ctx.jl, case)
     ctx.upload_u_level(0, sl("u"))
     ctx.adv_vel()
-    ctx.clinic_setup(case)
+    ctx.clinic_setup(case, fourfil=fourfil)
     ctx.upload_u_level(-1, sl("um1"))
     if use_slots:
         numsbc = 2 * case.nt + 4
@@ -117,6 +117,38 @@ def test_clinic_two_slabs_match_one_context(pkg):
         assert np.array_equal(u[:, r0:r0 + n], ref_u[:, jlo - 1:jhi]), (jlo, jhi)
         assert np.array_equal(zu[:, r0:r0 + n, 1:-1], ref_zu[:, jlo - 1:jhi, 1:-1]), (jlo, jhi)
         ctx.close()
+
+
+def test_clinic_with_polar_filter(pkg):
+    """O_fourfil: filuv (source/common/filuv.F) after the momentum step -- rotation to polar stereographic components,
+    m = 2 strips and m = 3 full rows, vertical mean removed again, mask.  One context and two slabs, against the oracle."""
+    case = pkg.synthetic.make_case(imt=42, jmt=48, km=6, nt=2, seed=31, land_lat=86.0)
+    pkg.synthetic.add_momentum(case)
+    jmt = case.jmt
+    o = make_oracle(case)
+    o.set_scalar("do_filter", 1)
+    oracle_load_momentum(o, case)
+    oracle_clinic(o)
+    ref = o.arr("up1", (2, jmt, case.km, case.imt)).copy()
+    o.set_scalar("do_filter", 0)
+    oracle_clinic(o)
+    plain = o.arr("up1", ref.shape).copy()
+    changed = np.nonzero(np.abs(ref - plain).max(axis=(0, 2, 3)) > 0)[0]
+    assert len(changed) >= 6, changed            # the filter did something on both polar caps
+    assert changed.min() < jmt // 2 < changed.max()
+    ctx = _device_clinic(pkg, case, fourfil=True)
+    got = ctx.download_u(+1)
+    ctx.close()
+    rel = np.abs(got[:, 1:-1] - ref[:, 1:-1]).max() / np.abs(ref).max()
+    assert np.array_equal(got[:, 1:-1], ref[:, 1:-1]), rel
+    mid = jmt // 2
+    for jlo, jhi in ((2, mid), (mid + 1, jmt - 1)):
+        ctx = _device_clinic(pkg, case, jlo=jlo, jhi=jhi, fourfil=True)
+        u = ctx.download_u(+1)
+        r0 = jlo - ctx.jbase
+        assert np.array_equal(u[:, r0:r0 + jhi - jlo + 1], ref[:, jlo - 1:jhi]), (jlo, jhi)
+        ctx.close()
+    o.close()
 
 
 def test_clinic_needs_setup(pkg):

@@ -64,7 +64,8 @@ class GasbcPar(C.Structure):
 class ClinicStatic(C.Structure):
     _fields_ = [("kmu", _c_int_p)] + [(n, _c_double_p) for n in (
         "hr", "cori", "advmet", "am3", "am4", "dxmetr", "dxu2r", "dyu2r", "dyu4r", "csudyu2r", "visc_ceu", "amc_north",
-        "amc_south")] + [(n, C.c_double) for n in ("kappa_m", "cdbot", "grav_rho0r")]
+        "amc_south")] + [(n, C.c_double) for n in ("kappa_m", "cdbot", "grav_rho0r")] + \
+        [(n, C.c_int32) for n in ("fourfil", "jfrst", "jfu0", "jfu1", "jfu2")] + [(n, _c_double_p) for n in ("spsin", "spcos", "phi")]
 
 
 # every symbol include/uvic_b200.h declares
@@ -385,7 +386,7 @@ class TracerContext:
                                                       _vp(sbc_out)))
 
     # ---- baroclinic momentum step (09/mom/clinic.F) ----
-    def clinic_setup(self, case=None):
+    def clinic_setup(self, case=None, fourfil=False):
         """Time-invariant inputs of clinic from a Case prepared by synthetic.add_momentum (or any dict-like with the same
         arrays / scalars)."""
         case = case or self.case
@@ -404,6 +405,13 @@ class TracerContext:
             keep.append(x)
             setattr(cs, n, _dp(x))
         cs.kappa_m, cs.cdbot, cs.grav_rho0r = float(s["kappa_m"]), float(s["cdbot"]), float(s["grav_rho0r"])
+        if fourfil:
+            cs.fourfil = 1
+            cs.jfrst, cs.jfu0, cs.jfu1, cs.jfu2 = (int(s[n]) for n in ("jfrst", "jfu0", "jfu1", "jfu2"))
+            for n in ("spsin", "spcos", "phi"):
+                x = np.ascontiguousarray(a[n], dtype=np.float64)
+                keep.append(x)
+                setattr(cs, n, _dp(x))
         self._ck(self.L.uvic_b200_clinic_setup(self.h, C.byref(cs)))
 
     def shape_u(self):

@@ -87,6 +87,7 @@ int uvic_b200_create(const uvic_b200_dims *d, const uvic_b200_grid *g, const uvi
   ctx->rho_dev = nullptr;
   ctx->halo_event = nullptr;
   ctx->clinic = nullptr;
+  ctx->filtu_items = nullptr; ctx->filtu_mats = nullptr; ctx->filtu_rows = nullptr; ctx->filtu_nitems = ctx->filtu_maxim = ctx->filtu_nrows = 0;
   ctx->tavg_t = ctx->tavg_stf = ctx->tavg_tmp = ctx->tavg_vflux = ctx->tavg_gaost = nullptr; ctx->navgts = 0; ctx->d2h_dst = nullptr; ctx->d2h_ntr = 0;
   DevView &v = ctx->v;
   memset(&v, 0, sizeof v);
@@ -543,6 +544,24 @@ int uvic_b200_clinic_setup(uvic_b200_ctx *ctx, const uvic_b200_clinic_static *cs
   cv->kappa_m = cs->kappa_m; cv->cdbot = cs->cdbot; cv->grav_rho0r = cs->grav_rho0r;
   cv->jc0 = std::max(2, v.jlo);
   cv->jc1 = std::min(v.jmt - 1, v.jhi);
+  if (cs->fourfil) {
+    // O_fourfil: filuv (source/common/filuv.F) on the rows poleward of jfu1 / jfu2
+    if (!cs->spsin || !cs->spcos || !cs->phi) return fail(ctx, "clinic_setup: fourfil needs spsin, spcos and phi");
+    if (cs->jfrst < 1 || cs->jfu0 < 1 || cs->jfu0 > v.jmt || cs->jfu1 < 1 || cs->jfu2 > v.jmt || cs->jfu1 >= cs->jfu2)
+      return fail(ctx, "clinic_setup: bad filter rows jfrst / jfu0 / jfu1 / jfu2");
+    {
+      double *p = nullptr;
+      if (dev_alloc(ctx, "spsin", &p, (size_t)v.imt, cs->spsin)) return 1;
+      cv->spsin = p;
+      if (dev_alloc(ctx, "spcos", &p, (size_t)v.imt, cs->spcos)) return 1;
+      cv->spcos = p;
+    }
+    std::vector<double> csu(v.jmt), csur(v.jmt);
+    CK(cudaMemcpy(csu.data(), v.csu, sizeof(double) * v.jmt, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(csur.data(), v.csur, sizeof(double) * v.jmt, cudaMemcpyDeviceToHost));
+    if (filuv_setup(ctx, cs->kmu, csu.data(), csur.data(), cs->phi, cs->jfrst, cs->jfu0, cs->jfu1, cs->jfu2, cv->jc0, cv->jc1))
+      return fail(ctx, "clinic_setup: filuv_setup failed (device allocation)");
+  }
   return 0;
 }
 int uvic_b200_upload_u_level(uvic_b200_ctx *ctx, int level, const double *u) {

@@ -91,6 +91,7 @@ struct FiltItem {
   int wrap_split;           // number of strip elements before the cyclic wrap (== im when none)
   long long fofs;           // offset of the matrix in filt_mats
   double fnorm;
+  double fx;                // filuv only: -1 south, +1 north (filuv.F:46-47)
 };
 
 // host: walk the strips exactly as filt does (filt.F:56-112) and record one item per (row, strip, level)
@@ -253,4 +254,233 @@ void launch_filter(uvic_b200_ctx *c, int nbase, int ng) {
   size_t smem = (size_t)(2 * c->filt_maxim + 4) * sizeof(double);
   ProfScope ps(c, "k_filter");
   k_filter<<<grid, 128, smem, c->stream>>>(v, (const FiltItem *)c->filt_items, c->filt_mats, nbase);
+}
+
+
+// ================================================================================================================
+// filuv (source/common/filuv.F): polar filter of the baroclinic velocities u(tau+1), called from clinic
+// (09/mom/clinic.F:494-507).  Strips come from findex on kmu with jfu1 / jfu2 (setcom.F:158); a land-bounded strip is
+// filtered with m = 2 (sine series, no mean handling, fnorm = 2/(im+1)), a full cyclic row with m = 3; the wave number is
+// n = nint(im*csu(j)/csu(jfu0)) (halved for m = 3).  item modes: 1 = m 3 matrix, 2 = m 2 matrix, 3 = m 2 with n = 0
+// (strip set to zero, filtr.F:261-266).
+// ================================================================================================================
+int filuv_setup(uvic_b200_ctx *c, const int *kmu_h, const double *csu, const double *csur, const double *phi, int jfrst,
+                int jfu0, int jfu1, int jfu2, int jc0, int jc1) {
+  DevView &v = c->v;
+  const int imt = v.imt, km = v.km, imtm1 = imt - 1, imtm2 = imt - 2;
+  std::vector<FiltItem> items;
+  std::vector<double> mats;
+  std::vector<int> rows;
+  std::map<std::tuple<int, int, int>, long long> seen;
+  auto KXX = [&](int i, int jrow) { return kmu_h[(i - 1) + (size_t)imt * (jrow - v.jbase)]; };
+  for (int jrow = jc0; jrow <= jc1; jrow++) {
+    if ((jrow > jfu1 && jrow < jfu2) || jrow < jfrst) continue;
+    std::vector<std::vector<std::pair<int, int>>> strips(km + 1);
+    size_t lmax = 0;
+    for (int k = 1; k <= km; k++) {
+      std::vector<int> iis(imt + 3, 0), iie(imt + 3, 0);
+      int l = 1;
+      if (KXX(2, jrow) >= k) iis[1] = 2;
+      for (int i = 2; i <= imt - 1; i++) {
+        if (KXX(i - 1, jrow) < k && KXX(i, jrow) >= k) iis[l] = i;
+        if (KXX(i, jrow) >= k && KXX(i + 1, jrow) < k) {
+          if (i != iis[l] || (i == 2 && KXX(1, jrow) >= k)) {
+            iie[l] = i;
+            l = l + 1;
+          } else {
+            iis[l] = 0;
+          }
+        }
+      }
+      if (KXX(imt - 1, jrow) >= k && KXX(imt, jrow) >= k) {
+        iie[l] = imt - 1;
+        l = l + 1;
+      }
+      int lm = l - 1;
+      if (lm > 1 && iis[1] == 2 && iie[lm] == imt - 1 && KXX(1, jrow) >= k) {
+        iis[1] = iis[lm];
+        iie[1] = iie[1] + imt - 2;
+        iis[lm] = 0;
+        iie[lm] = 0;
+        lm = lm - 1;
+      }
+      for (int q = 1; q <= lm; q++) strips[k].push_back({iis[q], iie[q]});
+      lmax = std::max(lmax, strips[k].size());
+    }
+    const double fx = (phi[jrow - 1] > 0.0) ? 1.0 : -1.0;
+    int isave = 0, ieave = 0, im = 0, m = 0, n = 0;
+    for (size_t l = 0; l < lmax; l++)
+      for (int k = 1; k <= km; k++) {
+        if (l >= strips[k].size() || strips[k][l].first == 0) continue;
+        int is = strips[k][l].first, ie = strips[k][l].second;
+        if (is != isave || ie != ieave) {
+          isave = is;
+          ieave = ie;
+          im = ie - is + 1;
+          if (im != imtm2) {
+            m = 2;
+            n = (int)round((double)im * csu[jrow - 1] * csur[jfu0 - 1]);
+          } else {
+            m = 3;
+            n = (int)round((double)im * csu[jrow - 1] * csur[jfu0 - 1] * 0.5);
+          }
+        }
+        FiltItem it;
+        it.j = jrow; it.k = k; it.is = is; it.im = im; it.fx = fx;
+        it.wrap_split = (ie >= imt) ? (imtm1 - is + 1) : im;
+        it.fnorm = (m == 2) ? 2.0 / (double)(im + 1) : 2.0 / (double)im;   // filtr.F:279-285
+        it.fofs = 0;
+        if (m == 2 && n == 0) {
+          it.mode = 3;
+        } else {
+          it.mode = (m == 2) ? 2 : 1;
+          auto key = std::make_tuple(im, m, n);
+          auto f = seen.find(key);
+          if (f == seen.end()) {
+            std::vector<double> F = build_ftarr(im, m, n);
+            long long ofs = (long long)mats.size();
+            mats.insert(mats.end(), F.begin(), F.end());
+            seen[key] = ofs;
+            it.fofs = ofs;
+          } else {
+            it.fofs = f->second;
+          }
+        }
+        items.push_back(it);
+      }
+    if (isave != 0 && ieave != 0) rows.push_back(jrow);   // filuv.F:140: rows whose vertical mean is removed again
+  }
+  c->filtu_nitems = (int)items.size();
+  c->filtu_nrows = (int)rows.size();
+  c->filtu_maxim = 0;
+  for (auto &it : items) c->filtu_maxim = std::max(c->filtu_maxim, it.im);
+  if (items.empty()) return 0;
+  if (cudaMalloc((void **)&c->filtu_items, items.size() * sizeof(FiltItem)) != cudaSuccess) return 1;
+  cudaMemcpy(c->filtu_items, items.data(), items.size() * sizeof(FiltItem), cudaMemcpyHostToDevice);
+  c->owned.push_back(c->filtu_items);
+  if (cudaMalloc((void **)&c->filtu_mats, std::max<size_t>(mats.size(), 1) * sizeof(double)) != cudaSuccess) return 1;
+  cudaMemcpy(c->filtu_mats, mats.data(), mats.size() * sizeof(double), cudaMemcpyHostToDevice);
+  c->owned.push_back(c->filtu_mats);
+  if (cudaMalloc((void **)&c->filtu_rows, rows.size() * sizeof(int)) != cudaSuccess) return 1;
+  cudaMemcpy(c->filtu_rows, rows.data(), rows.size() * sizeof(int), cudaMemcpyHostToDevice);
+  c->owned.push_back(c->filtu_rows);
+  return 0;
+}
+
+// one CTA per (row, strip, level): rotate both components, filter both with the same array, rotate back.
+// dynamic smem: s1[im], s2[im], sp1[im], sp2[im], 6 scalars
+__global__ void __launch_bounds__(128) k_filuv(const DevView v, double *__restrict__ up, const FiltItem *items, const double *mats,
+                                               const double *__restrict__ spsin, const double *__restrict__ spcos) {
+  extern __shared__ double sh[];
+  const FiltItem it = items[blockIdx.x];
+  const int im = it.im;
+  double *s[2] = {sh, sh + im};
+  double *sp[2] = {sh + 2 * im, sh + 3 * im};
+  double *sc = sh + 4 * im;
+  const double fx = it.fx;
+  const long long line = X3(1, it.k, it.j);
+  for (int p = threadIdx.x; p < im; p += blockDim.x) {
+    const int i = (p < it.wrap_split) ? it.is + p : p - it.wrap_split + 2;
+    const double u1 = up[line + i - 1], u2 = up[line + i - 1 + v.n3];
+    s[0][p] = -fx * u1 * spsin[i - 1] - u2 * spcos[i - 1];     // filuv.F:75-78
+    s[1][p] = fx * u1 * spcos[i - 1] - u2 * spsin[i - 1];
+  }
+  __syncthreads();
+  if (it.mode == 3) {
+    for (int p = threadIdx.x; p < im; p += blockDim.x) sp[0][p] = sp[1][p] = 0.0;
+  } else {
+    const double fimr = 1.0 / (double)im;
+    if (it.mode == 1) {
+      // m = 3: remove the strip mean first (filtr.F:292-309)
+      if (threadIdx.x < 2) {
+        const int q = threadIdx.x;
+        double ssum = 0.0;
+        for (int p = 0; p < im; p++) ssum = ssum + s[q][p];
+        sc[q] = ssum;
+        sc[2 + q] = ssum * fimr;
+      }
+      __syncthreads();
+      for (int p = threadIdx.x; p < im; p += blockDim.x) {
+        s[0][p] = s[0][p] - sc[2];
+        s[1][p] = s[1][p] - sc[3];
+      }
+      __syncthreads();
+    }
+    const double *F = mats + it.fofs;
+    for (int jx = threadIdx.x; jx < im; jx += blockDim.x) {
+      double a0 = 0.0, a1 = 0.0;
+      for (int p = 0; p < im; p++) {
+        const double f = F[(size_t)p * im + jx];
+        a0 = a0 + s[0][p] * f;
+        a1 = a1 + s[1][p] * f;
+      }
+      sp[0][jx] = it.fnorm * a0;
+      sp[1][jx] = it.fnorm * a1;
+    }
+    __syncthreads();
+    if (it.mode == 1) {
+      // restore the strip sum (filtr.F:411-420)
+      if (threadIdx.x < 2) {
+        const int q = threadIdx.x;
+        double ssm = 0.0;
+        for (int p = 0; p < im; p++) ssm = ssm + sp[q][p];
+        sc[4 + q] = (sc[q] - ssm) * fimr;
+      }
+      __syncthreads();
+      for (int p = threadIdx.x; p < im; p += blockDim.x) {
+        sp[0][p] = sc[4] + sp[0][p];
+        sp[1][p] = sc[5] + sp[1][p];
+      }
+    }
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < im; p += blockDim.x) {
+    const int i = (p < it.wrap_split) ? it.is + p : p - it.wrap_split + 2;
+    const double t1 = sp[0][p], t2 = sp[1][p];
+    up[line + i - 1] = fx * (-t1 * spsin[i - 1] + t2 * spcos[i - 1]);      // filuv.F:124-128
+    up[line + i - 1 + v.n3] = -t1 * spcos[i - 1] - t2 * spsin[i - 1];
+  }
+}
+
+// filuv.F:140-166 on the rows that had a strip: remove the vertical mean again, mask; then clinic's setbcx (:508-511)
+__global__ void __launch_bounds__(128) k_filuv_mean(const DevView v, double *__restrict__ up, const int *__restrict__ rows, int nrows,
+                                                    const int *__restrict__ kmu, const double *__restrict__ hr) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int ni = v.imt - 2;
+  if (idx >= (long long)ni * nrows) return;
+  const int i = (int)(idx % ni) + 2;
+  const int j = rows[idx / ni];
+  const int kb = kmu[X2(i, j)];
+  const double h = hr[X2(i, j)];
+  for (int n = 0; n < 2; n++) {
+    double *u = up + (long long)n * v.n3;
+    double bar = 0.0;
+    for (int k = 1; k <= v.km; k++) bar = bar + u[X3(i, k, j)] * v.dzt[k - 1];
+    bar = bar * h;
+    for (int k = 1; k <= v.km; k++) {
+      const long long line = X3(1, k, j);
+      const double val = (k <= kb) ? (u[line + i - 1] - bar) : 0.0;
+      u[line + i - 1] = val;
+      if (i == 2) u[line + v.imt - 1] = val;
+      if (i == v.imt - 1) u[line] = val;
+    }
+  }
+}
+
+void launch_filuv(uvic_b200_ctx *c, double *up, const double *spsin, const double *spcos, const int *kmu, const double *hr) {
+  if (c->filtu_nitems == 0) return;
+  DevView &v = c->v;
+  {
+    size_t smem = (size_t)(4 * c->filtu_maxim + 8) * sizeof(double);
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+      cudaFuncSetAttribute(k_filuv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      smem_set = smem;
+    }
+    ProfScope ps(c, "k_filuv");
+    k_filuv<<<c->filtu_nitems, 128, smem, c->stream>>>(v, up, (const FiltItem *)c->filtu_items, c->filtu_mats, spsin, spcos);
+  }
+  const long long n = (long long)(v.imt - 2) * c->filtu_nrows;
+  ProfScope ps(c, "k_filuv_mean");
+  k_filuv_mean<<<cdiv(n, 128), 128, 0, c->stream>>>(v, up, c->filtu_rows, c->filtu_nrows, kmu, hr);
 }

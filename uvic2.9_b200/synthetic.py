@@ -478,6 +478,15 @@ def add_momentum(case: Case, seed=SEED, am=1.5e9, kappa_m=10.0, cdbot=1.3e-3, dt
     taux = -0.8 * np.cos(3.0 * phi)[:, None] * np.ones((jmt, imt)) + 0.2 * _smooth2d(rng, imt, jmt, xu, yu)
     tauy = 0.2 * _smooth2d(rng, imt, jmt, xu, yu)
     a["taux"], a["tauy"] = taux, tauy
+    # polar filter of the velocities (source/common/setcom.F:41-43,56-71,79-81)
+    fxa = dxt[0] / radius
+    ang = fxa * (np.arange(1, imt + 1) - 2.0)
+    spsin, spcos = np.sin(ang), np.cos(ang)
+    spsin[np.abs(spsin) < 1.0e-10] = 0.0
+    spcos[np.abs(spcos) < 1.0e-10] = 0.0
+    spsin[0] = spcos[0] = spsin[-1] = spcos[-1] = 0.0
+    a["spsin"], a["spcos"], a["phi"] = spsin, spcos, phi
+    case.scalars.update(jfu0=indp(-68.4, yu), jfu1=indp(-70.2, yu), jfu2=indp(70.2, yu))
     if dtuv is None:
         dtuv = case.scalars["dtts"] / 96.0                       # run/control.in:3: dtts=108000, dtuv=1125
     case.scalars.update(c2dtuv=2.0 * dtuv, kappa_m=kappa_m, cdbot=cdbot, grav_rho0r=980.6 * (1.0 / 1.035))
