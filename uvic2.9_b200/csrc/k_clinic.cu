@@ -6,9 +6,10 @@
 //   k_setvbc_mom      09/mom/setvbc.F:163-208        surface stress (coupler slots) and quadratic bottom drag
 //   k_clinic_column   09/mom/clinic.F:60-511 + 09/mom/fdifm.h
 //
-// k_clinic_column: one thread per U column and velocity component (i fastest, so every level is one coalesced row
-// segment; the component is blockIdx.y).  The hydrostatic pressure gradient is the running sum the reference builds in grad_p (:150-177) and
-// stays in a register; the vertical fluxes through the bottom face of level k are the top-face fluxes of level k+1 and
+// k_clinic_column: one thread per U column (i fastest, so every level is one coalesced row segment), both velocity
+// components at once (one thread per column AND component was measured slower, 947 against 592 us on 0.5 degree: the
+// kernel is bound by L1/L2 load traffic, and the split repeats the rho / velocity / viscosity loads).  The hydrostatic pressure gradient is the running sum the reference builds in grad_p (:150-177) and
+// stays in two registers; the vertical fluxes through the bottom face of level k are the top-face fluxes of level k+1 and
 // are carried, not recomputed.  Pass 1 writes u(tau-1) + c2dtuv * du/dt and accumulates the two depth sums (zu: forcing
 // of the barotropic equation, :378-397; baru: the vertical mean that is removed, :458-485) in the reference's k order;
 // pass 2 subtracts the mean from the wet levels (the column is L1/L2 resident).  Operation order inside every expression
@@ -105,23 +106,19 @@ __global__ void __launch_bounds__(128) k_setvbc_mom(const DevView v, const Clini
   }
 }
 
-// one thread per (U column, velocity component): blockIdx.y is the component n, so every branch on n is uniform
-__global__ void __launch_bounds__(128) k_clinic_column(const DevView v, const ClinicView cv) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int ni = v.imt - 2;
-  if (idx >= (long long)ni * (cv.jc1 - cv.jc0 + 1)) return;
-  const int i = (int)(idx % ni) + 2;
-  const int j = (int)(idx / ni) + cv.jc0;
-  const int n = blockIdx.y, o = 1 - n;         // this thread's component (0-based) and the other one
+// CTA = 32 columns in i x CL_TJ rows: the north / south neighbours of the inner rows are lines the CTA's other warps load
+// at the same level, so they come from L1 instead of L2
+#define CL_TJ 4
+__global__ void __launch_bounds__(32 * CL_TJ) k_clinic_column(const DevView v, const ClinicView cv) {
+  const int i = blockIdx.x * 32 + (threadIdx.x & 31) + 2;
+  const int j = blockIdx.y * CL_TJ + (threadIdx.x >> 5) + cv.jc0;
+  if (i > v.imt - 1 || j > cv.jc1) return;
   const int km = v.km;
   const bool west = (i == 2), east = (i == v.imt - 1);
   const int kb = cv.kmu[X2(i, j)];
   const int kmt_ij = v.kmt[X2(i, j)];          // visc_cbu lives on T-cell levels (09/mom/vmixc.F:84-85)
   const double hr = cv.hr[X2(i, j)];
   const double c2dtuv = cv.c2dtuv;
-  const double *__restrict__ u0 = v.u + (long long)n * v.n3, *__restrict__ u0o = v.u + (long long)o * v.n3;
-  const double *__restrict__ um = cv.u_m1 + (long long)n * v.n3, *__restrict__ umo = cv.u_m1 + (long long)o * v.n3;
-  double *__restrict__ up = cv.u_p1 + (long long)n * v.n3;
 
   // row / column constants (09/mom/clinic.F:75-82, 119-147)
   const double csur = v.csur[j - 1];
@@ -132,101 +129,129 @@ __global__ void __launch_bounds__(128) k_clinic_column(const DevView v, const Cl
   const double dxu2r = cv.dxu2r[i - 1];
   const double g = cv.grav_rho0r;
   const double am3 = cv.am3[j - 1];
-  const double am4d = cv.am4[(j - 1) + n * v.jmt] * cv.dxmetr[i - 1];
-  const double advmet = cv.advmet[(j - 1) + n * v.jmt];
-  const double cori = cv.cori[X2(i, j) + (long long)n * v.n2];
-  const double smf = cv.smf[X2(i, j) + (long long)n * v.n2];
-  const double bmf = cv.bmf[X2(i, j) + (long long)n * v.n2];
-  // pressure gradient factors: level 1 (:135-147) and levels below (:160-170)
-  const double fx1 = (n == 0) ? g * v.dzw[0] * csur : g * v.dzw[0] * cv.dyu2r[j - 1];
-  const double fxk = (n == 0) ? g * csur * 0.5 : g * cv.dyu4r[j - 1];
+  const double am4d[2] = {cv.am4[j - 1] * cv.dxmetr[i - 1], cv.am4[(j - 1) + v.jmt] * cv.dxmetr[i - 1]};
+  const double advmet[2] = {cv.advmet[j - 1], cv.advmet[(j - 1) + v.jmt]};
+  const double cori[2] = {cv.cori[X2(i, j)], cv.cori[X2(i, j) + v.n2]};
+  const double smf[2] = {cv.smf[X2(i, j)], cv.smf[X2(i, j) + v.n2]};
+  const double bmf[2] = {cv.bmf[X2(i, j)], cv.bmf[X2(i, j) + v.n2]};
 
-  double gp = 0.0;                       // grad_p(i,k,j,n) integrated downward
-  double rp0 = 0.0, rp1 = 0.0, rp2 = 0.0, rp3 = 0.0;   // rho of the level above at (i,j) (i+1,j) (i,j+1) (i+1,j+1)
-  double afb_up = 0.0, dfb_up = 0.0;     // fluxes through the top face of the current level
-  double zu = 0.0, bar = 0.0;
+  double gp[2] = {0.0, 0.0};          // grad_p(i,k,j,:) integrated downward
+  double rp[4] = {0.0, 0.0, 0.0, 0.0};   // rho of the level above at (i,j) (i+1,j) (i,j+1) (i+1,j+1)
+  double afb_up[2], dfb_up[2];        // fluxes through the top face of the current level
+  double zu[2] = {0.0, 0.0}, bar[2] = {0.0, 0.0};
+  double u0d_prev[2] = {0.0, 0.0}, umd_prev[2] = {0.0, 0.0};
+  double um_k[2];
 
   for (int k = 1; k <= km; k++) {
-    double tend = 0.0;
-    const long long x = X3(i, k, j);
-    const double umc = um[x];
+    double tend[2] = {0.0, 0.0};
     if (k <= kb) {
-      const long long lev = (long long)v.imt, jst = (long long)v.imt * v.km;   // strides of k and j
       // ---- pressure gradient at this level ----
-      const double r00 = cv.rho[x], r10 = cv.rho[x + 1], r01 = cv.rho[x + jst], r11 = cv.rho[x + jst + 1];
+      const double r00 = cv.rho[X3(i, k, j)], r10 = cv.rho[X3(i + 1, k, j)], r01 = cv.rho[X3(i, k, j + 1)], r11 = cv.rho[X3(i + 1, k, j + 1)];
       if (k == 1) {
+        const double fxa = g * v.dzw[0] * csur, fxb = g * v.dzw[0] * cv.dyu2r[j - 1];
         const double t1 = r11 - r00, t2 = r01 - r10;
-        gp = (n == 0) ? (t1 - t2) * fx1 * dxu2r : (t1 + t2) * fx1;
+        gp[0] = (t1 - t2) * fxa * dxu2r;
+        gp[1] = (t1 + t2) * fxb;
       } else {
-        const double e00 = rp0 + r00, e10 = rp1 + r10, e01 = rp2 + r01, e11 = rp3 + r11;   // tempik (:150-157)
+        const double fxa = g * csur * 0.5, fxb = g * cv.dyu4r[j - 1];
+        const double e00 = rp[0] + r00, e10 = rp[1] + r10, e01 = rp[2] + r01, e11 = rp[3] + r11;   // tempik (:150-157)
         const double t1 = e11 - e00, t2 = e01 - e10;
-        gp = (n == 0) ? gp + fxk * (t1 - t2) * v.dzw[k - 1] * dxu2r : gp + fxk * (t1 + t2) * v.dzw[k - 1];
+        gp[0] = gp[0] + fxa * (t1 - t2) * v.dzw[k - 1] * dxu2r;
+        gp[1] = gp[1] + fxb * (t1 + t2) * v.dzw[k - 1];
       }
-      rp0 = r00; rp1 = r10; rp2 = r01; rp3 = r11;
-      cv.grad_p[x + (long long)n * v.n3] = gp;
+      rp[0] = r00; rp[1] = r10; rp[2] = r01; rp[3] = r11;
+      if (cv.grad_p) {
+        cv.grad_p[X3(i, k, j)] = gp[0];
+        cv.grad_p[X3(i, k, j) + v.n3] = gp[1];
+      }
       // ---- operands ----
-      const long long xd = (k < km) ? x + lev : x;
-      const double u0c = u0[x], u0e = u0[x + 1], u0w = u0[x - 1], u0n = u0[x + jst], u0s = u0[x - jst], u0d = u0[xd];
-      const double ume = um[x + 1], umw = um[x - 1], umn = um[x + jst], ums = um[x - jst], umd = um[xd];
-      const double u0co = u0o[x], umeo = umo[x + 1], umwo = umo[x - 1];
-      const double veu_e = cv.adv_veu[x], veu_w = cv.adv_veu[x - 1];
-      const double vnu_n = cv.adv_vnu[x], vnu_s = cv.adv_vnu[x - jst];
+      double u0c[2], u0e[2], u0w[2], u0n[2], u0s[2], u0d[2], umc[2], ume[2], umw[2], umn[2], ums[2], umd[2];
+      const int kd = (k < km) ? k + 1 : km;
+#pragma unroll
+      for (int n = 0; n < 2; n++) {
+        // the centre values of level k are the "level below" values of level k-1 (both wet): carried, not reloaded
+        u0c[n] = (k == 1) ? U0(i, k, j, n + 1) : u0d_prev[n];
+        umc[n] = (k == 1) ? UM(i, k, j, n + 1) : umd_prev[n];
+        u0e[n] = U0(i + 1, k, j, n + 1); u0w[n] = U0(i - 1, k, j, n + 1);
+        u0n[n] = U0(i, k, j + 1, n + 1); u0s[n] = U0(i, k, j - 1, n + 1); u0d[n] = U0(i, kd, j, n + 1);
+        ume[n] = UM(i + 1, k, j, n + 1); umw[n] = UM(i - 1, k, j, n + 1);
+        umn[n] = UM(i, k, j + 1, n + 1); ums[n] = UM(i, k, j - 1, n + 1); umd[n] = UM(i, kd, j, n + 1);
+        u0d_prev[n] = u0d[n]; umd_prev[n] = umd[n];
+      }
+      const double veu_e = cv.adv_veu[X3(i, k, j)], veu_w = cv.adv_veu[X3(i - 1, k, j)];
+      const double vnu_n = cv.adv_vnu[X3(i, k, j)], vnu_s = cv.adv_vnu[X3(i, k, j - 1)];
       const double vbu_lo = cv.adv_vbu[X3Z(i, k, j)];
-      const double amx_e = cv.visc_ceu[x] * csur * dxtr_e;      // am_csudxtr(i,k,j)   (:80)
-      const double amx_w = cv.visc_ceu[x - 1] * csur * dxtr_w;  // am_csudxtr(i-1,k,j)
-      const double amcn = cv.amc_north[x], amcs = cv.amc_south[x];
+      const double amx_e = cv.visc_ceu[X3(i, k, j)] * csur * dxtr_e;      // am_csudxtr(i,k,j)   (:80)
+      const double amx_w = cv.visc_ceu[X3(i - 1, k, j)] * csur * dxtr_w;  // am_csudxtr(i-1,k,j)
+      const double amcn = cv.amc_north[X3(i, k, j)], amcs = cv.amc_south[X3(i, k, j)];
       const double visc_lo = (k <= kmt_ij - 1) ? cv.kappa_m : 0.0;
-      if (k == 1) {
-        // surface b.c. (:309-313)
-        dfb_up = smf;
-        afb_up = cv.adv_vbu[X3Z(i, 0, j)] * (u0c + u0c);
+#pragma unroll
+      for (int n = 0; n < 2; n++) {
+        const int o = 1 - n;
+        if (k == 1) {
+          // surface b.c. (:309-313)
+          dfb_up[n] = smf[n];
+          afb_up[n] = cv.adv_vbu[X3Z(i, 0, j)] * (u0c[n] + u0c[n]);
+        }
+        // bottom face of level k (:283-293, 310-314)
+        double afb_lo, dfb_lo;
+        if (k < km) {
+          afb_lo = vbu_lo * (u0c[n] + u0d[n]);
+          dfb_lo = visc_lo * v.dzwr[k] * (umc[n] - umd[n]);
+        } else {
+          afb_lo = vbu_lo * u0c[n];
+          dfb_lo = 0.0;                 // diff_fb(i,km,j) is only ever set through kb = km
+        }
+        const double dfb_reg = dfb_lo;
+        if (k == kb) dfb_lo = bmf[n];
+        const double afe_e = veu_e * (u0c[n] + u0e[n]), afe_w = veu_w * (u0w[n] + u0c[n]);
+        const double dfe_e = amx_e * (ume[n] - umc[n]), dfe_w = amx_w * (umc[n] - umw[n]);
+        // 09/mom/fdifm.h
+        const double DIFF_Ux = (dfe_e - dfe_w) * csudxur;
+        const double DIFF_Uy = amcn * (umn[n] - umc[n]) - amcs * (umc[n] - ums[n]);
+        const double DIFF_Uz = (dfb_up[n] - dfb_lo) * v.dztr[k - 1];
+        const double DIFF_metric = am3 * umc[n] + am4d[n] * (ume[o] - umw[o]);
+        const double ADV_Ux = (afe_e - afe_w) * csudxu2r;
+        const double ADV_Uy = (vnu_n * (u0c[n] + u0n[n]) - vnu_s * (u0s[n] + u0c[n])) * csudyu2r;
+        const double ADV_Uz = (afb_up[n] - afb_lo) * v.dzt2r[k - 1];
+        const double ADV_metric = advmet[n] * u0c[0] * u0c[o];
+        const double CORIOLIS = cori[n] * u0c[o];
+        tend[n] = DIFF_Ux + DIFF_Uy + DIFF_Uz + DIFF_metric - ADV_Ux - ADV_Uy - ADV_Uz + ADV_metric - gp[n] + CORIOLIS;
+        um_k[n] = umc[n];
+        afb_up[n] = afb_lo;
+        dfb_up[n] = dfb_reg;
       }
-      // bottom face of level k (:283-293, 310-314)
-      double afb_lo, dfb_lo;
-      if (k < km) {
-        afb_lo = vbu_lo * (u0c + u0d);
-        dfb_lo = visc_lo * v.dzwr[k] * (umc - umd);
-      } else {
-        afb_lo = vbu_lo * u0c;
-        dfb_lo = 0.0;                 // diff_fb(i,km,j) is only ever set through kb = km
-      }
-      const double dfb_reg = dfb_lo;
-      if (k == kb) dfb_lo = bmf;
-      const double afe_e = veu_e * (u0c + u0e), afe_w = veu_w * (u0w + u0c);
-      const double dfe_e = amx_e * (ume - umc), dfe_w = amx_w * (umc - umw);
-      // 09/mom/fdifm.h
-      const double DIFF_Ux = (dfe_e - dfe_w) * csudxur;
-      const double DIFF_Uy = amcn * (umn - umc) - amcs * (umc - ums);
-      const double DIFF_Uz = (dfb_up - dfb_lo) * v.dztr[k - 1];
-      const double DIFF_metric = am3 * umc + am4d * (umeo - umwo);
-      const double ADV_Ux = (afe_e - afe_w) * csudxu2r;
-      const double ADV_Uy = (vnu_n * (u0c + u0n) - vnu_s * (u0s + u0c)) * csudyu2r;
-      const double ADV_Uz = (afb_up - afb_lo) * v.dzt2r[k - 1];
-      const double u0_1 = (n == 0) ? u0c : u0co;   // u(i,k,j,1,tau)
-      const double ADV_metric = advmet * u0_1 * u0co;
-      const double CORIOLIS = cori * u0co;
-      tend = DIFF_Ux + DIFF_Uy + DIFF_Uz + DIFF_metric - ADV_Ux - ADV_Uy - ADV_Uz + ADV_metric - gp + CORIOLIS;
-      afb_up = afb_lo;
-      dfb_up = dfb_reg;
+    }
+    if (k > kb) {
+      um_k[0] = UM(i, k, j, 1);
+      um_k[1] = UM(i, k, j, 2);
     }
     // ---- tau+1 before the mean is removed (:444-451), depth sums in the reference's order ----
-    zu = zu + tend * v.dzt[k - 1];
-    const double upk = umc + c2dtuv * tend;
-    bar = bar + upk * v.dzt[k - 1];
-    up[x] = upk;
+#pragma unroll
+    for (int n = 0; n < 2; n++) {
+      zu[n] = zu[n] + tend[n] * v.dzt[k - 1];
+      const double up = um_k[n] + c2dtuv * tend[n];
+      bar[n] = bar[n] + up * v.dzt[k - 1];
+      UP(i, k, j, n + 1) = up;
+    }
   }
-  cv.zu[X2(i, j) + (long long)n * v.n2] = zu * hr;
-  bar = bar * hr;
+#pragma unroll
+  for (int n = 0; n < 2; n++) {
+    cv.zu[X2(i, j) + (long long)n * v.n2] = zu[n] * hr;
+    bar[n] = bar[n] * hr;
+  }
   // ---- pure internal modes (:476-485) and the cyclic boundary ----
   for (int k = 1; k <= km; k++) {
-    const long long line = X3(1, k, j);
-    double upk = up[line + i - 1];
-    if (k <= kb) {
-      upk = upk - bar;
-      up[line + i - 1] = upk;
+#pragma unroll
+    for (int n = 0; n < 2; n++) {
+      double up = UP(i, k, j, n + 1);
+      if (k <= kb) {
+        up = up - bar[n];
+        UP(i, k, j, n + 1) = up;
+      }
+      if (west) UP(v.imt, k, j, n + 1) = up;
+      if (east) UP(1, k, j, n + 1) = up;
     }
-    if (west) up[line + v.imt - 1] = upk;
-    if (east) up[line] = upk;
   }
 }
 
@@ -242,10 +267,9 @@ void launch_clinic(uvic_b200_ctx *c) {
   const ClinicView &cv = *c->clinic;
   const long long ncell = (long long)(v.imt - 2) * (v.km + 1) * (cv.jc1 - cv.jc0 + 2);
   KLAUNCH("k_clinic_advvel", k_clinic_advvel, cdiv(ncell, 256), 256, v, cv);
-  const long long ncol = (long long)(v.imt - 2) * (cv.jc1 - cv.jc0 + 1);
   {
     ProfScope ps_(c, "k_clinic_column");
-    k_clinic_column<<<dim3(cdiv(ncol, 128), 2), 128, 0, c->stream>>>(v, cv);
+    k_clinic_column<<<dim3(cdiv(v.imt - 2, 32), cdiv(cv.jc1 - cv.jc0 + 1, CL_TJ)), 32 * CL_TJ, 0, c->stream>>>(v, cv);
   }
   // O_fourfil: filuv on the polar rows (09/mom/clinic.F:494-507), including the final setbcx of those rows
   launch_filuv(c, cv.u_p1, cv.spsin, cv.spcos, cv.kmu, cv.hr);
