@@ -16,6 +16,7 @@
 // is the reference's (the library is compiled without FMA contraction), so the result is bit-identical to the oracle.
 // The polar filter of the velocities (filuv, k_filter.cu) follows when the context was set up with fourfil.  The
 // diagnostics hooks (diagc1, diagc2) and the ice coupling (isbcu, asbcu) stay on the host.
+#include <stdlib.h>
 #include "ctx.h"
 
 #define U0(i, k, j, n) v.u[X3(i, k, j) + (long long)((n)-1) * v.n3]
@@ -23,14 +24,12 @@
 #define UP(i, k, j, n) cv.u_p1[X3(i, k, j) + (long long)((n)-1) * v.n3]
 
 // one thread per (i, k = 0..km, j); rows jc0-1..jc1 (adv_vnu) and jc0..jc1 (adv_veu, adv_vbu)
-__global__ void __launch_bounds__(256) k_clinic_advvel(const DevView v, const ClinicView cv) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int ni = v.imt - 2, nk = v.km + 1, nj = cv.jc1 - cv.jc0 + 2;
-  if (idx >= (long long)ni * nk * nj) return;
-  const int i = (int)(idx % ni) + 2;
-  const long long r = idx / ni;
-  const int k = (int)(r % nk);
-  const int j = (int)(r / nk) + cv.jc0 - 1;
+__global__ void __launch_bounds__(128) k_clinic_advvel(const DevView v, const ClinicView cv) {
+  // grid: x over i, y = level 0..km, z = row jc0-1..jc1 (no index division)
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
+  if (i > v.imt - 1) return;
+  const int k = blockIdx.y;
+  const int j = blockIdx.z + cv.jc0 - 1;
   const bool west = (i == 2), east = (i == v.imt - 1);
   if (k >= 1) {
     // adv_vnu = LINEAR_INTRP_Y(WT_AVG_X(adv_vnt)) (:173-186)
@@ -109,7 +108,8 @@ __global__ void __launch_bounds__(128) k_setvbc_mom(const DevView v, const Clini
 // CTA = 32 columns in i x CL_TJ rows: the north / south neighbours of the inner rows are lines the CTA's other warps load
 // at the same level, so they come from L1 instead of L2
 #define CL_TJ 4
-__global__ void __launch_bounds__(32 * CL_TJ) k_clinic_column(const DevView v, const ClinicView cv) {
+template <int MINB>
+__global__ void __launch_bounds__(32 * CL_TJ, MINB) k_clinic_column(const DevView v, const ClinicView cv) {
   const int i = blockIdx.x * 32 + (threadIdx.x & 31) + 2;
   const int j = blockIdx.y * CL_TJ + (threadIdx.x >> 5) + cv.jc0;
   if (i > v.imt - 1 || j > cv.jc1) return;
@@ -265,11 +265,21 @@ void launch_setvbc_mom(uvic_b200_ctx *c, int itaux, int itauy) {
 void launch_clinic(uvic_b200_ctx *c) {
   DevView &v = c->v;
   const ClinicView &cv = *c->clinic;
-  const long long ncell = (long long)(v.imt - 2) * (v.km + 1) * (cv.jc1 - cv.jc0 + 2);
-  KLAUNCH("k_clinic_advvel", k_clinic_advvel, cdiv(ncell, 256), 256, v, cv);
+  {
+    ProfScope ps_(c, "k_clinic_advvel");
+    k_clinic_advvel<<<dim3(cdiv(v.imt - 2, 128), v.km + 1, cv.jc1 - cv.jc0 + 2), 128, 0, c->stream>>>(v, cv);
+  }
   {
     ProfScope ps_(c, "k_clinic_column");
-    k_clinic_column<<<dim3(cdiv(v.imt - 2, 32), cdiv(cv.jc1 - cv.jc0 + 1, CL_TJ)), 32 * CL_TJ, 0, c->stream>>>(v, cv);
+    // resident CTAs per SM the register allocation is capped for: 2 = 240 registers, 3 = 166, 4 = 128 (with 144 B of spills)
+    // Measured (whole clinic call): 0.5 degree x 40 levels 0.713 / 0.699 / 0.673 ms, 100x100x19 (80 CTAs, less than one
+    // per SM) 0.049 / 0.057 / 0.062 ms -- so the cap follows the grid size.
+    const dim3 grid(cdiv(v.imt - 2, 32), cdiv(cv.jc1 - cv.jc0 + 1, CL_TJ));
+    static const int occ_env = getenv("UVIC_B200_CLINIC_OCC") ? atoi(getenv("UVIC_B200_CLINIC_OCC")) : 0;
+    const int occ = occ_env ? occ_env : ((long long)grid.x * grid.y >= 4 * 148 ? 4 : 2);
+    if (occ <= 2) k_clinic_column<2><<<grid, 32 * CL_TJ, 0, c->stream>>>(v, cv);
+    else if (occ == 3) k_clinic_column<3><<<grid, 32 * CL_TJ, 0, c->stream>>>(v, cv);
+    else k_clinic_column<4><<<grid, 32 * CL_TJ, 0, c->stream>>>(v, cv);
   }
   // O_fourfil: filuv on the polar rows (09/mom/clinic.F:494-507), including the final setbcx of those rows
   launch_filuv(c, cv.u_p1, cv.spsin, cv.spcos, cv.kmu, cv.hr);
