@@ -484,7 +484,7 @@ def main():
     if world == 1 and not a.workload.startswith("tenth") and os.environ.get("UVIC_B200_BENCH_CLINIC", "1") == "1":
         pkg.synthetic.add_momentum(case)
         slc = lambda n: np.ascontiguousarray(pkg.api.slab_slice(n, case[n], ctx.jbase, ctx.jl, case))
-        ctx.clinic_setup(case)
+        ctx.clinic_setup(case, fourfil=bool(fourfil))
         ctx.upload_u_level(0, slc("u"))
         ctx.upload_u_level(-1, slc("um1"))
         ctx.adv_vel()
@@ -521,7 +521,7 @@ def main():
                   "roofline": {"bound": "hbm", "kernel": "k_clinic_column", "bytes_per_launch": col_bytes, "us_per_launch": col_us,
                                "achieved": (col_bytes / (col_us * 1e-6) / 1e9) if col_us else None, "peak": pkh, "unit": "GB/s",
                                "frac": (col_bytes / (col_us * 1e-6) / 1e9 / pkh) if col_us else None},
-                  "note": "uvic_b200_clinic (09/mom/clinic.F with run/mk.in options, without filuv), resident fields, CUDA events"}
+                  "note": "uvic_b200_clinic (09/mom/clinic.F with run/mk.in options; filuv as O_fourfil of the workload says), resident fields, CUDA events"}
         if not a.no_cpu_baseline:
             sys.path.insert(0, os.path.join(ROOT, "tests"))
             os.environ["UVIC_ORACLE_VARIANT"] = "o3"
