@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256) k_elements(const DevView v) {
   // gradients at the bottom face (:408-422)
   int kp1 = min(k + 1, v.km);
   double mkp1 = tmask_of(v, i, kp1, j);
-  long long cz = X3Z(i, k, j), linez = X3Z(1, k, j);
+  long long linez = X3Z(1, k, j);
   long long ckp1 = X3(i, kp1, j);
   store_cyc(v, v.ddzt, linez, i, mkp1 * v.dzwr[k] * (T[c] - T[ckp1]));
   store_cyc(v, v.ddzt + v.n3z, linez, i, mkp1 * v.dzwr[k] * (S[c] - S[ckp1]));
@@ -73,7 +73,6 @@ __global__ void __launch_bounds__(256) k_elements(const DevView v) {
     store_cyc(v, v.ddzt, l0, i, 0.0);
     store_cyc(v, v.ddzt + v.n3z, l0, i, 0.0);
   }
-  (void)cz;
   double m = tmask_of(v, i, k, j);
   // gradients at the eastern face (:428-440), rows max(js-1,2)..je-1
   if (j >= 2 && j <= v.jmt - 1) {

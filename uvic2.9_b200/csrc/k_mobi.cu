@@ -1363,15 +1363,14 @@ __global__ void __launch_bounds__(32 * WS_WARPS * G) k_mobi_ws(const DevView v, 
         }
         {
           const double rtphytc13 = SR(rtphytc13), rtzoopc13 = SR(rtzoopc13), rtdiazc13 = SR(rtdiazc13), rtdetrc13 = SR(rtdetrc13);
-          const double rtdiatc13 = SR(rtdiatc13), rtdoc13 = SR(rtdoc13), fcnpp = SR(fcnpp), rtdic13 = SR(rtdic13);
+          const double rtdiatc13 = SR(rtdiatc13), rtdoc13 = SR(rtdoc13), fcnpp = SR(fcnpp);
           const double rtcaco3c13 = SR(rtcaco3c13);
           const double morp = SR(morp), morp_Diat = SR(morp_Diat), morpt_Diat = SR(morpt_Diat), morpt = SR(morpt), remi = SR(remi);
           const double recy_don = SR(recy_don), npp = SR(npp), graz = SR(graz), morz = SR(morz), graz_Z = SR(graz_Z), excr = SR(excr);
           const double sf_Diat = SR(sf_Diat), sf_P = SR(sf_P), sf_Z = SR(sf_Z), sf_Det = SR(sf_Det), sf_D = SR(sf_D);
-          const double graz_Det = SR(graz_Det), expo = SR(expo), morp_D = SR(morp_D), npp_D = SR(npp_D), graz_D = SR(graz_D);
-          const double morpt_D = SR(morpt_D), calpro = SR(calpro), dissl = SR(dissl), expocaco3 = SR(expocaco3);
-          const double npp_Diat = SR(npp_Diat), graz_Diat = SR(graz_Diat);
-          const double rc13impo = SL(X_rc13expo) * dztrk, rcaco3c13impo = SL(X_rcaco3c13expo) * dztrk;
+          const double graz_Det = SR(graz_Det), expo = SR(expo), morp_D = SR(morp_D);
+          const double expocaco3 = SR(expocaco3);
+          const double rc13impo = SL(X_rc13expo) * dztrk;
           UPD(V_DOC13, SB(V_DOC13) + dtbio * redctn *
                                          (dfr * rtphytc13 * morp + rtdiatc13 * (dfr * morp_Diat + dfrt * morpt_Diat) + rtphytc13 * dfrt * morpt +
                                           rtdetrc13 * pfr * remi - rtdoc13 * recy_don));

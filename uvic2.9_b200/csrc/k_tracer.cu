@@ -188,7 +188,6 @@ __global__ void __launch_bounds__(UPD_T) k_update(const DevView v, int nbase, in
   const double dzt2r = v.dzt2r[k - 1], dztr = v.dztr[k - 1], dzt4r = 0.5 * v.dzt2r[k - 1];
   const double csu_dzt4r_n = v.csu[j - 1] * 0.5 * v.dzt2r[k - 1], csu_dzt4r_s = v.csu[j - 2] * 0.5 * v.dzt2r[k - 1];
   const double dxt4r = v.dxt4r[i - 1], dyt4r_cstr = v.dyt4r[j - 1] * cstr;
-  const double twodt = v.c2dtts * v.dtxcel[k - 1];
   const double one_m_aidif = 1.0 - v.aidif;
   // tracer-independent coefficients of the six faces
   const SmCol ce_e{&sco[0][tid]}, ce_w{&sco[4][tid]}, cn_n{&sco[8][tid]}, cn_s{&sco[12][tid]};
