@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from conftest import load_pkg
-from helpers import make_oracle, oracle_clinic, oracle_load_momentum
+from helpers import make_oracle, oracle_clinic, oracle_load_momentum, oracle_rotate, oracle_set_step, relerr
 
 pytestmark = pytest.mark.gpu
 
@@ -148,6 +148,53 @@ def test_clinic_with_polar_filter(pkg):
         r0 = jlo - ctx.jbase
         assert np.array_equal(u[:, r0:r0 + jhi - jlo + 1], ref[:, jlo - 1:jhi]), (jlo, jhi)
         ctx.close()
+    o.close()
+
+
+def test_ocean_steps_tracer_and_clinic_together(pkg):
+    """Four ocean steps as mom sequences them (without the barotropic solver): adv_vel from u(tau), isopyc / vmixc /
+    tracer, clinic, both sets of time levels rotated -- the device keeps u and t resident throughout.  The tracer step is
+    within 1e-12 of the oracle per step (not bit-exact), its density feeds the pressure gradient, so u is compared to
+    1e-11 of its maximum."""
+    case = pkg.synthetic.make_case(imt=42, jmt=36, km=8, nt=3, names=["temp", "salt", "passive0"], seed=77)
+    pkg.synthetic.add_momentum(case)
+    jmt, km, imt = case.jmt, case.km, case.imt
+    o = make_oracle(case)
+    oracle_load_momentum(o, case)
+    ctx = pkg.TracerContext(case)
+    ctx.load_state()
+    ctx.upload_u_level(0, case["u"])
+    ctx.clinic_setup(case)
+    ctx.upload_u_level(-1, case["um1"])
+    numsbc = 2 * case.nt + 4
+    ctx.sbc_setup(numsbc, np.zeros(case.nt, dtype=np.int32), np.zeros(case.nt, dtype=np.int32))
+    ctx.upload_sbc(_sbc_with_stress(case, numsbc), None)
+    c2dtuv = case.scalars["c2dtuv"]
+    shu = (2, jmt, km, imt)
+    for step in range(4):
+        oracle_set_step(o, case, True)
+        o.call("ora_adv_vel")
+        o.call("ora_step")
+        oracle_clinic(o)
+        ctx.adv_vel()
+        ctx.step(leapfrog=True)
+        ctx.clinic(c2dtuv, 1, 2)
+        t_d, u_d = ctx.download_t(+1), ctx.download_u(+1)
+        t_o, u_o = o.t()[2], o.arr("up1", shu)
+        for n in range(case.nt):
+            assert relerr(t_d[n][1:-1], t_o[n][1:-1]) < 1e-11, (step, n)
+        for n in range(2):
+            assert relerr(u_d[n][1:-1], u_o[n][1:-1]) < 1e-11, (step, n)
+        assert np.isfinite(u_d).all()
+        # tau-1 <- tau <- tau+1 for both
+        oracle_rotate(o)
+        o.arr("um1", shu)[...] = o.arr("u", shu)
+        o.arr("u", shu)[...] = o.arr("up1", shu)
+        ctx.rotate()
+        ctx.rotate_u()
+    # the velocities moved: this was not a fixed point
+    assert np.abs(ctx.download_u(0) - case["u"]).max() > 1e-3
+    ctx.close()
     o.close()
 
 
