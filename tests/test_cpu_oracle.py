@@ -623,3 +623,48 @@ def test_filuv_properties_and_sine_series(pkg):
             break
     assert checked >= 1
     o.close()
+
+
+def test_adv_vel_and_state_against_numpy(pkg, small):
+    """source/mom/adv_vel.F:60-131 against the vectorised numpy version that builds the synthetic inputs (independent
+    code, same operation order: bit-exact), the U-cell velocities of :160-250 through the properties the scheme is
+    built on (a uniform T-cell field averages to itself; the U-cell vertical velocity vanishes at the surface), and
+    state (source/mom/state.F) against the cubic of dens.h evaluated in numpy."""
+    case = small
+    imt, jmt, km = case.imt, case.jmt, case.km
+    o = make_oracle(case)
+    o.call("ora_adv_vel")
+    vet, vnt, vbt = pkg.synthetic.adv_vel_numpy(imt, jmt, km, case.arrays)
+    s3, s3z = (jmt, km, imt), (jmt, km + 1, imt)
+    assert np.array_equal(o.arr("adv_vnt", s3), vnt)
+    assert np.array_equal(o.arr("adv_vet", s3)[1:], vet[1:])
+    assert np.array_equal(o.arr("adv_vbt", s3z)[1:], vbt[1:])
+    # continuity closes at the bottom of every T column to round-off (the synthetic u has no depth mean)
+    kmt = case["kmt"]
+    jj, ii = np.nonzero(kmt[1:-1, 1:-1] > 0)
+    wb = o.arr("adv_vbt", s3z)[jj + 1, kmt[jj + 1, ii + 1], ii + 1]
+    assert np.abs(wb).max() < 1e-9 * np.abs(o.arr("adv_vbt", s3z)).max()
+    # U-cell averages: constants are reproduced
+    pkg.synthetic.add_momentum(case)
+    o2 = make_oracle(case)
+    o2.arr("adv_vnt", s3)[...] = 3.0
+    o2.arr("adv_vet", s3)[...] = -2.0
+    o2.arr("adv_vbt", s3z)[...] = 0.5
+    o2.call("ora_adv_vel_u")
+    a = case.arrays
+    # LINEAR_INTRP weights: (duw + due) * dxur = 1 and (dus(j+1) + dun(j)) * dytr(j+1) = 1 on the uniform synthetic grid
+    np.testing.assert_allclose(o2.arr("adv_vnu", s3)[0:jmt - 1, :, 1:-1], 3.0, rtol=1e-13)
+    np.testing.assert_allclose(o2.arr("adv_veu", s3)[1:jmt - 1, :, 1:-1], -2.0, rtol=1e-13)
+    wgt = ((a["dus"][1:jmt - 1] * a["cst"][1:jmt - 1] + a["dun"][1:jmt - 1] * a["cst"][2:jmt]) * a["dyur"][1:jmt - 1] * a["csur"][1:jmt - 1])
+    np.testing.assert_allclose(o2.arr("adv_vbu", s3z)[1:jmt - 1, :, 1:-1], 0.5 * wgt[:, None, None] * np.ones((1, km + 1, imt - 2)), rtol=1e-13)
+    # state
+    o.call("ora_state")
+    t = case["t"][1]
+    c = case["eosc"].reshape(9, km)          # c(km,9) column-major
+    tq = t[0] - case["to"][None, :, None]
+    sq = t[1] - case["so"][None, :, None]
+    C = lambda m: c[m - 1][None, :, None]
+    rho = (C(1) + (C(4) + C(7) * sq) * sq + (C(3) + C(8) * sq + C(6) * tq) * tq) * tq + (C(2) + (C(5) + C(9) * sq) * sq) * sq
+    assert np.array_equal(o.arr("rho", s3), rho)
+    o.close()
+    o2.close()
