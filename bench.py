@@ -506,21 +506,26 @@ def main():
             ctx.clinic(c2dtuv)
         barrier()
         ctx.profile_enable(False)
-        pk = {k: round(1e3 * v[0] / max(v[1], 1), 2) for k, v in ctx.profile().items() if k in ("k_clinic_column", "k_clinic_advvel", "k_setvbc_mom", "k_state")}
+        pk = {k: round(1e3 * v[0] / max(v[1], 1), 2) for k, v in ctx.profile().items()
+              if k.startswith("k_clinic") or k in ("k_setvbc_mom", "k_state", "k_filuv", "k_filuv_mean")}
         ctx.profile_reset()
         kmu = np.asarray(case["kmu"])[1:-1, 1:-1]
         wet_u = int(kmu.sum())
         all_u = kmu.size * case.km
-        # compulsory bytes of k_clinic_column: per wet U cell u(tau) 2 + u(tau-1) 2 + rho 1 + adv_veu/vnu/vbu 3 + visc_ceu,
-        # amc_north, amc_south 3 reads and u(tau+1) 2 writes; per masked cell u(tau-1) 2 reads and u(tau+1) 2 writes
-        col_bytes = 8 * (13 * wet_u + 4 * (all_u - wet_u))
+        # compulsory bytes of the tendency kernel per wet U cell: u(tau) 2 + u(tau-1) 2 + adv_veu/vnu/vbu 3 + visc_ceu,
+        # amc_north, amc_south 3 + grad_p 2 reads and du/dt 2 writes (k_clinic_tend); the single marching kernel
+        # (k_clinic_column) reads rho instead of grad_p and also carries the masked cells: u(tau-1) 2 reads, u(tau+1) 2 writes
+        if "k_clinic_tend" in pk:
+            rk, rbytes = "k_clinic_tend", 8 * 14 * wet_u
+        else:
+            rk, rbytes = "k_clinic_column", 8 * (13 * wet_u + 4 * (all_u - wet_u))
         pkh = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0)) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-        col_us = pk.get("k_clinic_column")
+        r_us = pk.get(rk)
         clinic = {"ms_per_step": ms_ck, "steps": nck, "value": 2 * all_u / (ms_ck * 1e-3) / 1e9, "unit": "G U-cell*component/s",
                   "kernels_us": pk,
-                  "roofline": {"bound": "hbm", "kernel": "k_clinic_column", "bytes_per_launch": col_bytes, "us_per_launch": col_us,
-                               "achieved": (col_bytes / (col_us * 1e-6) / 1e9) if col_us else None, "peak": pkh, "unit": "GB/s",
-                               "frac": (col_bytes / (col_us * 1e-6) / 1e9 / pkh) if col_us else None},
+                  "roofline": {"bound": "hbm", "kernel": rk, "bytes_per_launch": rbytes, "us_per_launch": r_us,
+                               "achieved": (rbytes / (r_us * 1e-6) / 1e9) if r_us else None, "peak": pkh, "unit": "GB/s",
+                               "frac": (rbytes / (r_us * 1e-6) / 1e9 / pkh) if r_us else None},
                   "note": "uvic_b200_clinic (09/mom/clinic.F with run/mk.in options; filuv as O_fourfil of the workload says), resident fields, CUDA events"}
         if not a.no_cpu_baseline:
             sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -6,6 +6,7 @@
 //   k_setvbc_mom      09/mom/setvbc.F:163-208        surface stress (coupler slots) and quadratic bottom drag
 //   k_clinic_column   09/mom/clinic.F:60-511 + 09/mom/fdifm.h
 //
+// Two variants of the step itself (launch_clinic): three kernels with a cell-parallel tendency (default, see below), or
 // k_clinic_column: one thread per U column (i fastest, so every level is one coalesced row segment), both velocity
 // components at once (one thread per column AND component was measured slower, 947 against 592 us on 0.5 degree: the
 // kernel is bound by L1/L2 load traffic, and the split repeats the rho / velocity / viscosity loads).  The hydrostatic pressure gradient is the running sum the reference builds in grad_p (:150-177) and
@@ -255,6 +256,145 @@ __global__ void __launch_bounds__(32 * CL_TJ, MINB) k_clinic_column(const DevVie
   }
 }
 
+
+// ---- the cell-parallel variant (UVIC_B200_CLINIC=cell): the same arithmetic in three kernels -----------------------
+// k_clinic_gradp  column threads, 4 loads per level: the downward integral of the pressure gradient into grad_p
+// k_clinic_tend   one thread per wet U cell (no serial chain): du/dt of both components into u_p1; the vertical face
+//                 fluxes are evaluated from their definitions (the same expressions the column kernel carries)
+// k_clinic_finish column threads: zu, u(tau-1) + c2dtuv du/dt, the vertical mean and its removal, cyclic columns
+__global__ void __launch_bounds__(128) k_clinic_gradp(const DevView v, const ClinicView cv) {
+  const int i = blockIdx.x * 32 + (threadIdx.x & 31) + 2;
+  const int j = blockIdx.y * 4 + (threadIdx.x >> 5) + cv.jc0;
+  if (i > v.imt - 1 || j > cv.jc1) return;
+  const int kb = cv.kmu[X2(i, j)];
+  const double *__restrict__ rho = cv.rho;
+  double *__restrict__ gpo = cv.grad_p;
+  const double csur = v.csur[j - 1], dxu2r = cv.dxu2r[i - 1], g = cv.grav_rho0r;
+  const long long jst = (long long)v.imt * v.km;
+  double gp0 = 0.0, gp1 = 0.0, rp0 = 0.0, rp1 = 0.0, rp2 = 0.0, rp3 = 0.0;
+  for (int k = 1; k <= kb; k++) {
+    const long long x = X3(i, k, j);
+    const double r00 = rho[x], r10 = rho[x + 1], r01 = rho[x + jst], r11 = rho[x + jst + 1];
+    if (k == 1) {
+      const double fxa = g * v.dzw[0] * csur, fxb = g * v.dzw[0] * cv.dyu2r[j - 1];
+      const double t1 = r11 - r00, t2 = r01 - r10;
+      gp0 = (t1 - t2) * fxa * dxu2r;
+      gp1 = (t1 + t2) * fxb;
+    } else {
+      const double fxa = g * csur * 0.5, fxb = g * cv.dyu4r[j - 1];
+      const double e00 = rp0 + r00, e10 = rp1 + r10, e01 = rp2 + r01, e11 = rp3 + r11;
+      const double t1 = e11 - e00, t2 = e01 - e10;
+      gp0 = gp0 + fxa * (t1 - t2) * v.dzw[k - 1] * dxu2r;
+      gp1 = gp1 + fxb * (t1 + t2) * v.dzw[k - 1];
+    }
+    rp0 = r00; rp1 = r10; rp2 = r01; rp3 = r11;
+    gpo[x] = gp0;
+    gpo[x + v.n3] = gp1;
+  }
+}
+
+__global__ void __launch_bounds__(128) k_clinic_tend(const DevView v, const ClinicView cv) {
+  // grid: x over i, y = level 1..km, z = row jc0..jc1
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 2;
+  if (i > v.imt - 1) return;
+  const int k = blockIdx.y + 1;
+  const int j = blockIdx.z + cv.jc0;
+  const int kb = cv.kmu[X2(i, j)];
+  if (k > kb) return;
+  const int km = v.km;
+  const int kmt_ij = v.kmt[X2(i, j)];
+  const long long x = X3(i, k, j), lev = (long long)v.imt, jst = (long long)v.imt * v.km;
+  const double csur = v.csur[j - 1];
+  const double csudxur = csur * v.dxur[i - 1];
+  const double csudxu2r = csur * v.dxur[i - 1] * 0.5;
+  const double csudyu2r = cv.csudyu2r[j - 1];
+  const double am3 = cv.am3[j - 1];
+  const double veu_e = cv.adv_veu[x], veu_w = cv.adv_veu[x - 1];
+  const double vnu_n = cv.adv_vnu[x], vnu_s = cv.adv_vnu[x - jst];
+  const double vbu_lo = cv.adv_vbu[X3Z(i, k, j)], vbu_up = cv.adv_vbu[X3Z(i, k - 1, j)];
+  const double amx_e = cv.visc_ceu[x] * csur * v.dxtr[i];
+  const double amx_w = cv.visc_ceu[x - 1] * csur * v.dxtr[i - 1];
+  const double amcn = cv.amc_north[x], amcs = cv.amc_south[x];
+  const double visc_lo = (k <= kmt_ij - 1) ? cv.kappa_m : 0.0;
+  const double visc_up = (k - 1 <= kmt_ij - 1) ? cv.kappa_m : 0.0;
+  const long long xd = (k < km) ? x + lev : x, xu = (k > 1) ? x - lev : x;
+  double u0c[2], u0e[2], u0w[2], u0n[2], u0s[2], u0d[2], u0u[2], umc[2], ume[2], umw[2], umn[2], ums[2], umd[2], umu[2];
+#pragma unroll
+  for (int n = 0; n < 2; n++) {
+    const double *__restrict__ u0 = v.u + (long long)n * v.n3;
+    const double *__restrict__ um = cv.u_m1 + (long long)n * v.n3;
+    u0c[n] = u0[x]; u0e[n] = u0[x + 1]; u0w[n] = u0[x - 1]; u0n[n] = u0[x + jst]; u0s[n] = u0[x - jst]; u0d[n] = u0[xd]; u0u[n] = u0[xu];
+    umc[n] = um[x]; ume[n] = um[x + 1]; umw[n] = um[x - 1]; umn[n] = um[x + jst]; ums[n] = um[x - jst]; umd[n] = um[xd]; umu[n] = um[xu];
+  }
+#pragma unroll
+  for (int n = 0; n < 2; n++) {
+    const int o = 1 - n;
+    // top face (:283-293 for the face k-1; :309-313 at the surface)
+    double afb_up, dfb_up;
+    if (k == 1) {
+      dfb_up = cv.smf[X2(i, j) + (long long)n * v.n2];
+      afb_up = vbu_up * (u0c[n] + u0c[n]);
+    } else {
+      afb_up = vbu_up * (u0u[n] + u0c[n]);
+      dfb_up = visc_up * v.dzwr[k - 1] * (umu[n] - umc[n]);
+    }
+    // bottom face
+    double afb_lo, dfb_lo;
+    if (k < km) {
+      afb_lo = vbu_lo * (u0c[n] + u0d[n]);
+      dfb_lo = visc_lo * v.dzwr[k] * (umc[n] - umd[n]);
+    } else {
+      afb_lo = vbu_lo * u0c[n];
+      dfb_lo = 0.0;
+    }
+    if (k == kb) dfb_lo = cv.bmf[X2(i, j) + (long long)n * v.n2];
+    const double afe_e = veu_e * (u0c[n] + u0e[n]), afe_w = veu_w * (u0w[n] + u0c[n]);
+    const double dfe_e = amx_e * (ume[n] - umc[n]), dfe_w = amx_w * (umc[n] - umw[n]);
+    const double DIFF_Ux = (dfe_e - dfe_w) * csudxur;
+    const double DIFF_Uy = amcn * (umn[n] - umc[n]) - amcs * (umc[n] - ums[n]);
+    const double DIFF_Uz = (dfb_up - dfb_lo) * v.dztr[k - 1];
+    const double DIFF_metric = am3 * umc[n] + cv.am4[(j - 1) + n * v.jmt] * cv.dxmetr[i - 1] * (ume[o] - umw[o]);
+    const double ADV_Ux = (afe_e - afe_w) * csudxu2r;
+    const double ADV_Uy = (vnu_n * (u0c[n] + u0n[n]) - vnu_s * (u0s[n] + u0c[n])) * csudyu2r;
+    const double ADV_Uz = (afb_up - afb_lo) * v.dzt2r[k - 1];
+    const double ADV_metric = cv.advmet[(j - 1) + n * v.jmt] * u0c[0] * u0c[o];
+    const double CORIOLIS = cv.cori[X2(i, j) + (long long)n * v.n2] * u0c[o];
+    cv.u_p1[x + (long long)n * v.n3] = DIFF_Ux + DIFF_Uy + DIFF_Uz + DIFF_metric - ADV_Ux - ADV_Uy - ADV_Uz + ADV_metric -
+                                       cv.grad_p[x + (long long)n * v.n3] + CORIOLIS;
+  }
+}
+
+__global__ void __launch_bounds__(128) k_clinic_finish(const DevView v, const ClinicView cv) {
+  const int i = blockIdx.x * 32 + (threadIdx.x & 31) + 2;
+  const int j = blockIdx.y * 4 + (threadIdx.x >> 5) + cv.jc0;
+  if (i > v.imt - 1 || j > cv.jc1) return;
+  const int n = blockIdx.z;
+  const int kb = cv.kmu[X2(i, j)];
+  const double hr = cv.hr[X2(i, j)], c2dtuv = cv.c2dtuv;
+  const double *__restrict__ um = cv.u_m1 + (long long)n * v.n3;
+  double *up = cv.u_p1 + (long long)n * v.n3;
+  const bool west = (i == 2), east = (i == v.imt - 1);
+  double zu = 0.0, bar = 0.0;
+  for (int k = 1; k <= v.km; k++) {
+    const long long x = X3(i, k, j);
+    const double tend = (k <= kb) ? up[x] : 0.0;
+    zu = zu + tend * v.dzt[k - 1];
+    const double upk = um[x] + c2dtuv * tend;
+    bar = bar + upk * v.dzt[k - 1];
+  }
+  cv.zu[X2(i, j) + (long long)n * v.n2] = zu * hr;
+  bar = bar * hr;
+  for (int k = 1; k <= v.km; k++) {
+    const long long line = X3(1, k, j);
+    const double tend = (k <= kb) ? up[line + i - 1] : 0.0;
+    double upk = um[line + i - 1] + c2dtuv * tend;
+    if (k <= kb) upk = upk - bar;
+    up[line + i - 1] = upk;
+    if (west) up[line + v.imt - 1] = upk;
+    if (east) up[line] = upk;
+  }
+}
+
 void launch_setvbc_mom(uvic_b200_ctx *c, int itaux, int itauy) {
   DevView &v = c->v;
   const ClinicView &cv = *c->clinic;
@@ -269,7 +409,18 @@ void launch_clinic(uvic_b200_ctx *c) {
     ProfScope ps_(c, "k_clinic_advvel");
     k_clinic_advvel<<<dim3(cdiv(v.imt - 2, 128), v.km + 1, cv.jc1 - cv.jc0 + 2), 128, 0, c->stream>>>(v, cv);
   }
-  {
+  // default: the cell-parallel variant (whole call 0.623 against 0.674 ms on 0.5 degree x 40 levels, 0.044 against 0.048 ms
+  // on 100x100x19); UVIC_B200_CLINIC=column selects the single marching kernel.  Both are bit-identical to the oracle.
+  static const bool cell_variant = !(getenv("UVIC_B200_CLINIC") && std::string(getenv("UVIC_B200_CLINIC")) == "column");
+  if (cell_variant) {
+    const dim3 cols(cdiv(v.imt - 2, 32), cdiv(cv.jc1 - cv.jc0 + 1, 4));
+    { ProfScope ps_(c, "k_clinic_gradp"); k_clinic_gradp<<<cols, 128, 0, c->stream>>>(v, cv); }
+    {
+      ProfScope ps_(c, "k_clinic_tend");
+      k_clinic_tend<<<dim3(cdiv(v.imt - 2, 128), v.km, cv.jc1 - cv.jc0 + 1), 128, 0, c->stream>>>(v, cv);
+    }
+    { ProfScope ps_(c, "k_clinic_finish"); k_clinic_finish<<<dim3(cols.x, cols.y, 2), 128, 0, c->stream>>>(v, cv); }
+  } else {
     ProfScope ps_(c, "k_clinic_column");
     // resident CTAs per SM the register allocation is capped for: 2 = 240 registers, 3 = 166, 4 = 128 (with 144 B of spills)
     // Measured (whole clinic call): 0.5 degree x 40 levels 0.713 / 0.699 / 0.673 ms, 100x100x19 (80 CTAs, less than one
