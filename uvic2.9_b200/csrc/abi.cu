@@ -596,8 +596,9 @@ int uvic_b200_clinic(uvic_b200_ctx *ctx, double c2dtuv, int itaux, int itauy) {
     if (itaux < 1 || itaux > v.numsbc || itauy < 1 || itauy > v.numsbc) return fail(ctx, "clinic: wind stress slot out of range");
   }
   ctx->clinic->c2dtuv = c2dtuv;
-  set_levels(ctx, true);
-  launch_state(ctx, v.t_0, ctx->clinic->rho);   // 09/mom/loadmw.F:150-155: rho of t(tau)
+  // 09/mom/loadmw.F:150-155: rho of t(tau).  The tau slot is addressed directly: the time-level view of the tracer step
+  // (which maps tau-1 onto tau on mixing steps) is left as the tracer entry points set it
+  launch_state(ctx, ctx->t_slot[ctx->lev[1]], ctx->clinic->rho);
   launch_setvbc_mom(ctx, itaux, itauy);
   launch_clinic(ctx);
   CK(cudaGetLastError());
