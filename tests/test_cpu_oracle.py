@@ -668,3 +668,22 @@ def test_adv_vel_and_state_against_numpy(pkg, small):
     assert np.array_equal(o.arr("rho", s3), rho)
     o.close()
     o2.close()
+
+
+def test_oracle_reproduces_committed_clinic_vectors():
+    """tests/golden/tiny_clinic.npz (one momentum step without and with filuv, written from the oracle)."""
+    import importlib.util
+    import os
+
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    got = mg.run_oracle_clinic()
+    ref = np.load(os.path.join(here, "tiny_clinic.npz"))
+    assert set(ref.files) == set(got)
+    for k in ref.files:
+        assert np.array_equal(ref[k], got[k]), k
+    # the fixture exercises the filter on both polar caps
+    rows = np.nonzero(np.abs(ref["u_p1"] - ref["u_p1_filuv"]).max(axis=(0, 2, 3)) > 0)[0]
+    assert rows.min() < 10 and rows.max() > 30

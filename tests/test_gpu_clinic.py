@@ -198,6 +198,30 @@ def test_ocean_steps_tracer_and_clinic_together(pkg):
     o.close()
 
 
+def test_clinic_against_committed_vectors(pkg):
+    """The device against tests/golden/tiny_clinic.npz (written from the oracle by tests/golden/make_golden.py): u(tau+1)
+    without and with the polar filter, zu and the pressure gradient, bit for bit."""
+    import importlib.util
+    import os
+
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    ref = np.load(os.path.join(here, "tiny_clinic.npz"))
+    case = mg.clinic_case()
+    assert np.array_equal(np.asarray(case["kmu"]), ref["kmu"])
+    s3 = (case.jmt, case.km, case.imt)
+    for tag, filt in (("", False), ("_filuv", True)):
+        ctx = _device_clinic(pkg, case, fourfil=filt)
+        assert np.array_equal(ctx.download_u(+1)[:, 1:-1], ref["u_p1" + tag][:, 1:-1]), tag
+        if not filt:
+            assert np.array_equal(ctx.download_zu()[:, 1:-1, 1:-1], ref["zu"][:, 1:-1, 1:-1])
+            gp = ctx.fetch("grad_p", (2,) + s3) * np.asarray(case["umask"])[None]
+            assert np.array_equal(gp[:, 1:-1, :, 1:-1], ref["grad_p"][:, 1:-1, :, 1:-1])
+        ctx.close()
+
+
 def test_clinic_needs_setup(pkg):
     case = _case(pkg, 34, 30, 8, 33)
     ctx = pkg.TracerContext(case)
