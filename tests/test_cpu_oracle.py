@@ -687,3 +687,47 @@ def test_oracle_reproduces_committed_clinic_vectors():
     # the fixture exercises the filter on both polar caps
     rows = np.nonzero(np.abs(ref["u_p1"] - ref["u_p1_filuv"]).max(axis=(0, 2, 3)) > 0)[0]
     assert rows.min() < 10 and rows.max() > 30
+
+
+def test_filuv_full_rows_are_fourier_truncation(pkg):
+    """filuv on a fully wet polar row (m = 3, filtr.F): the rotated components keep the waves 0..n of the cyclic row,
+    n = nint(im*csu(j)/csu(jfu0)/2) -- checked against an FFT truncation for the rows with 2n < im."""
+    case = pkg.synthetic.make_case(imt=26, jmt=44, km=5, nt=2, seed=12, land_lat=86.0, land_frac=0.04)
+    pkg.synthetic.add_momentum(case)
+    s, a = case.scalars, case.arrays
+    kmu = np.asarray(a["kmu"])
+    jmt, imt = kmu.shape
+    rng = np.random.default_rng(1)
+    up = (a["um1"] + 0.5 * rng.standard_normal(a["um1"].shape)) * a["umask"][None]
+    up[..., 0], up[..., -1] = up[..., -2], up[..., 1]
+    o = make_oracle(case)
+    o.arr("up1", up.shape)[...] = up
+    o.arr("hr")[...] = 0.0                        # no vertical-mean removal: the raw filter output stays visible
+    o.call("ora_filuv")
+    raw = o.arr("up1", up.shape)
+    im, ii = imt - 2, np.arange(1, imt - 1)
+    checked = 0
+    for j in range(1, jmt - 1):
+        jrow = j + 1
+        if (s["jfu1"] < jrow < s["jfu2"]) or jrow < s["jfrst"] or not (kmu[j, 1:-1] >= 1).all():
+            continue
+        n = int(round(im * a["csu"][j] * a["csur"][s["jfu0"] - 1] * 0.5))
+        if 2 * n >= im:
+            continue
+        fx = 1.0 if a["phi"][j] > 0 else -1.0
+        u1, u2 = up[0, j, 0, ii], up[1, j, 0, ii]
+        t1 = -fx * u1 * a["spsin"][ii] - u2 * a["spcos"][ii]
+        t2 = fx * u1 * a["spcos"][ii] - u2 * a["spsin"][ii]
+
+        def trunc(x):
+            F = np.fft.rfft(x)
+            F[n + 1:] = 0
+            return np.fft.irfft(F, im)
+
+        f1, f2 = trunc(t1), trunc(t2)
+        v1 = fx * (-f1 * a["spsin"][ii] + f2 * a["spcos"][ii])
+        v2 = -f1 * a["spcos"][ii] - f2 * a["spsin"][ii]
+        assert np.abs(raw[0, j, 0, ii] - v1).max() < 1e-12 and np.abs(raw[1, j, 0, ii] - v2).max() < 1e-12, jrow
+        checked += 1
+    assert checked >= 2
+    o.close()

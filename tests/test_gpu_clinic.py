@@ -119,10 +119,13 @@ def test_clinic_two_slabs_match_one_context(pkg):
         ctx.close()
 
 
-def test_clinic_with_polar_filter(pkg):
+@pytest.mark.parametrize("geo", [dict(imt=42, jmt=48, km=6, seed=31, land_lat=86.0),
+                                 dict(imt=26, jmt=44, km=5, seed=12, land_lat=86.0, land_frac=0.04)])
+def test_clinic_with_polar_filter(pkg, geo):
     """O_fourfil: filuv (source/common/filuv.F) after the momentum step -- rotation to polar stereographic components,
-    m = 2 strips and m = 3 full rows, vertical mean removed again, mask.  One context and two slabs, against the oracle."""
-    case = pkg.synthetic.make_case(imt=42, jmt=48, km=6, nt=2, seed=31, land_lat=86.0)
+    land-bounded strips (m = 2, also across the cyclic seam) and, on the second geography, full cyclic rows (m = 3);
+    vertical mean removed again, mask.  One context and two slabs, against the oracle."""
+    case = pkg.synthetic.make_case(nt=2, **geo)
     pkg.synthetic.add_momentum(case)
     jmt = case.jmt
     o = make_oracle(case)
@@ -134,7 +137,7 @@ def test_clinic_with_polar_filter(pkg):
     oracle_clinic(o)
     plain = o.arr("up1", ref.shape).copy()
     changed = np.nonzero(np.abs(ref - plain).max(axis=(0, 2, 3)) > 0)[0]
-    assert len(changed) >= 6, changed            # the filter did something on both polar caps
+    assert len(changed) >= 4, changed            # the filter did something on both polar caps
     assert changed.min() < jmt // 2 < changed.max()
     ctx = _device_clinic(pkg, case, fourfil=True)
     got = ctx.download_u(+1)

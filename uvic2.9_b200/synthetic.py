@@ -332,14 +332,14 @@ def filter_rows(yt):
 
 
 def make_case(imt=102, jmt=102, km=19, nt=2, seed=SEED, names=None, dtts=None, noise=1.0,
-              with_static_mobi=True, land_lat=72.0) -> Case:
+              with_static_mobi=True, land_lat=72.0, land_frac=0.30) -> Case:
     """Build one complete synthetic configuration."""
     names = list(names) if names is not None else default_tracer_names(nt)
     assert len(names) == nt
     arrays: dict = {}
     scalars: dict = {}
     make_grid(imt, jmt, km, arrays, scalars)
-    make_bathymetry(imt, jmt, km, arrays, seed, land_lat=land_lat)
+    make_bathymetry(imt, jmt, km, arrays, seed, land_lat=land_lat, land_frac=land_frac)
     make_eos(km, arrays)
     make_velocity(imt, jmt, km, arrays, seed)
     vet, vnt, vbt = adv_vel_numpy(imt, jmt, km, arrays)
