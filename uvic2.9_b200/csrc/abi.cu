@@ -516,7 +516,18 @@ int uvic_b200_tavg_fetch(uvic_b200_ctx *ctx, double *avg_t, double *avg_stf, int
 }
 
 // ---- baroclinic momentum step on the device (09/mom/clinic.F) ----
+static int clinic_setup_impl(uvic_b200_ctx *ctx, const uvic_b200_clinic_static *cs);
 int uvic_b200_clinic_setup(uvic_b200_ctx *ctx, const uvic_b200_clinic_static *cs) {
+  const int rc = clinic_setup_impl(ctx, cs);
+  if (rc != 0 && ctx && ctx->clinic && ctx->err.find("already set up") == std::string::npos) {
+    // a half-built momentum state must not be usable: the device arrays stay owned by the context (freed at destroy)
+    delete ctx->clinic;
+    ctx->clinic = nullptr;
+    ctx->filtu_nitems = ctx->filtu_nrows = 0;
+  }
+  return rc;
+}
+static int clinic_setup_impl(uvic_b200_ctx *ctx, const uvic_b200_clinic_static *cs) {
   if (!ctx || !cs) return fail(ctx, "clinic_setup: null argument");
   if (ctx->clinic) return fail(ctx, "clinic_setup: already set up");
   if (!cs->kmu || !cs->hr || !cs->cori || !cs->advmet || !cs->am3 || !cs->am4 || !cs->dxmetr || !cs->dxu2r || !cs->dyu2r ||
