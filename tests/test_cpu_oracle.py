@@ -731,3 +731,27 @@ def test_filuv_full_rows_are_fourier_truncation(pkg):
         checked += 1
     assert checked >= 2
     o.close()
+
+
+def test_step_is_affine_equivariant(pkg):
+    """A passive tracer started as 2*p + 3 stays 2*p' + 3 through leapfrog and mixing steps: advection by a
+    non-divergent flow (FCT included: its limiters only see differences and ratios), isopycnal and vertical diffusion,
+    the implicit solve and convection are all shift invariant and homogeneous of degree one.  Holds to the closure of
+    the synthetic velocity's continuity at the bottom (~1e-9), far below any indexing error."""
+    names = ["temp", "salt", "passive0", "passive1"]
+    case = pkg.synthetic.make_case(imt=34, jmt=30, km=8, nt=4, names=names, seed=21)
+    t = case["t"]
+    t[:, 3] = (2.0 * t[:, 2] + 3.0) * case["tmask"][None]
+    o = make_oracle(case)
+    for step, lf in enumerate((True, True, False, True)):
+        oracle_set_step(o, case, lf)
+        o.call("ora_step")
+        tp = o.t()[2]
+        d = (tp[3] - (2.0 * tp[2] + 3.0)) * case["tmask"]
+        assert np.abs(d[1:-1, :, 1:-1]).max() < 1e-6 * np.abs(tp[3]).max(), step
+        # ... and it is not a fixed point
+        assert np.abs(tp[2] - o.t()[1][2]).max() > 1e-4
+        t_ = o.t()
+        t_[0] = t_[1]
+        t_[1] = t_[2]
+    o.close()
