@@ -183,3 +183,37 @@ def test_lazy_stacked_case_gives_the_same_slabs(pkg):
             a = pkg.api.slab_slice(name, eager[name], jbase, jl, eager)
             b = pkg.api.slab_slice(name, lazy[name], jbase, jl, lazy)
             assert np.array_equal(a, b), (name, jlo)
+
+
+def test_stacked_grid_carries_the_momentum_inputs(pkg):
+    """stack_bands also tiles the inputs of the momentum step: on a two-band stack the oracle's clinic gives every band
+    the single-band result bit for bit (the bands are separated by land rows), through the eager and the lazy stack."""
+    import numpy as np
+    from helpers import make_oracle, oracle_clinic, oracle_load_momentum
+
+    base = pkg.synthetic.add_momentum(pkg.synthetic.make_case(imt=26, jmt=20, km=6, nt=2, seed=5))
+    o = make_oracle(base)
+    oracle_load_momentum(o, base)
+    oracle_clinic(o)
+    ref = o.arr("up1", (2, base.jmt, base.km, base.imt)).copy()
+    zref = o.arr("zu", (2, base.jmt, base.imt)).copy()
+    o.close()
+    st = pkg.synthetic.stack_bands(base, 2)
+    nb = base.jmt - 2
+    assert st["um1"].shape == (2, st.jmt, base.km, base.imt) and st["am4"].shape == (2, st.jmt) and st["hr"].shape == (st.jmt, base.imt)
+    o = make_oracle(st)
+    oracle_load_momentum(o, st)
+    oracle_clinic(o)
+    got = o.arr("up1", (2, st.jmt, st.km, st.imt))
+    zgot = o.arr("zu", (2, st.jmt, st.imt))
+    for b in range(2):
+        assert np.array_equal(got[:, 1 + nb * b:1 + nb * (b + 1)], ref[:, 1:-1]), b
+        assert np.array_equal(zgot[:, 1 + nb * b:1 + nb * (b + 1), 1:-1], zref[:, 1:-1, 1:-1]), b
+    o.close()
+    lazy = pkg.synthetic.stack_bands(base, 2, lazy=True)
+    for jlo, jhi in pkg.slab.partition_rows(st.jmt, 2):
+        jbase, jl = pkg.api.slab_rows(st.jmt, jlo, jhi)
+        for name in ("um1", "visc_ceu", "amc_north", "amc_south", "cori", "hr", "kmu"):
+            a = pkg.api.slab_slice(name, st[name], jbase, jl, st)
+            b = pkg.api.slab_slice(name, lazy[name], jbase, jl, lazy)
+            assert np.array_equal(a, b), (name, jlo)

@@ -495,10 +495,12 @@ def add_momentum(case: Case, seed=SEED, am=1.5e9, kappa_m=10.0, cdbot=1.3e-3, dt
 
 # arrays with a j extent: axis of j in the C-ordered numpy array (1-D metric arrays of length jmt: axis 0)
 _J_1D = ("dyt", "dyu", "dytr", "dyt2r", "dyt4r", "dyur", "cst", "csu", "cstr", "csur", "cstdytr", "cstdyt2r", "csu_dyur", "dus",
-         "dun", "_yt", "_yu")
+         "dun", "_yt", "_yu", "am3", "dyu2r", "dyu4r", "csudyu2r", "phi")
 _J_ND = {"kmt": 0, "kmu": 0, "mskhr": 0, "tlat": 0, "tmask": 0, "umask": 0, "fisop": 1, "sg_bathy": 1, "fe_hydr": 1, "fe_atmdep": 1,
          "addisop": 0, "edrm2": 0, "edrs2": 0, "edrk1": 0, "edro1": 0, "adv_vet": 0, "adv_vnt": 0, "adv_vbt": 0, "stf": 1,
-         "btf": 1, "u": 1, "t": 2, "dnswr": 0, "aice": 0, "hice": 0, "hsno": 0}
+         "btf": 1, "u": 1, "t": 2, "dnswr": 0, "aice": 0, "hice": 0, "hsno": 0,
+         # inputs of the momentum step (add_momentum)
+         "um1": 1, "hr": 0, "cori": 1, "visc_ceu": 0, "amc_north": 0, "amc_south": 0, "taux": 0, "tauy": 0, "advmet": 1, "am4": 1}
 
 
 def stack_bands(case: Case, nbands: int, lazy: bool = False) -> Case:
