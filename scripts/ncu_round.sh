@@ -14,4 +14,7 @@ H="python bench.py --workload half_deg_40 --steps 1 --warmup 3 --no-cpu-baseline
 $H > $O/plain_half.json 2> $O/plain_half.err &&
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_fct_march|k_update|k_invtri|k_mobi_column|k_mobi_cell" -s 10 -c 5 -f -o $O/prof_half $H > $O/ncu_h.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_fct_march|k_update|k_invtri|k_mobi_ws|k_mobi_cell" -s 10 -c 5 -f -o $O/prof_uvic $B > $O/ncu_w.log 2>&1
+# the momentum step on the 0.5 degree grid (k_clinic_*, k_filuv*)
+python scripts/clinic_once.py > $O/clinic_once.log 2>&1 &&
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:"k_clinic|k_filuv" -s 8 -c 5 -f -o $O/prof_clinic python scripts/clinic_once.py > $O/ncu_c.log 2>&1
 ls -la $O | tail -20
