@@ -172,13 +172,14 @@ void ora_co2calc_SWS(double t, double s, double dic_in, double ta_in, double co2
   double dpCO2 = pCO2 - co2starair;
   double CO3 = q.k1 * q.k2 * co2star / hSWS2;
 
+  /* :343-365: the five x**0.5 stay pow(x, 0.5), as written and as in oracle/_ref (see ora_mobi.c header) */
   double Kspc = exp(-395.8293 + (6537.773 / tk) + 71.595 * log(tk) - 0.17959 * tk +
-                    (-1.78938 + (410.64 / tk) + 0.0065453 * tk) * sqrt(s) - 0.17755 * s + 0.0094979 * s15);
+                    (-1.78938 + (410.64 / tk) + 0.0065453 * tk) * pow(s, 0.5) - 0.17755 * s + 0.0094979 * s15);
   double Kspa = exp(-395.9180 + (6685.079 / tk) + 71.595 * log(tk) - 0.17959 * tk +
-                    (-0.157481 + (202.938 / tk) + 0.0039780 * tk) * sqrt(s) - 0.23067 * s + 0.0136808 * s15);
-  double DVc = -65.28 + 0.397 * t - 0.005155 * (t * t) + (19.816 - 0.0441 * t - 0.00017 * (t * t)) * sqrt(s / 35.);
-  double DVa = -65.50 + 0.397 * t - 0.005155 * (t * t) + (19.82 - 0.0441 * t - 0.00017 * (t * t)) * sqrt(s / 35.);
-  double DK = 0.01847 + 0.0001956 * t - 0.000002212 * (t * t) + (-0.03217 - 0.0000711 * t + 0.000002212) * sqrt(s / 35.);
+                    (-0.157481 + (202.938 / tk) + 0.0039780 * tk) * pow(s, 0.5) - 0.23067 * s + 0.0136808 * s15);
+  double DVc = -65.28 + 0.397 * t - 0.005155 * (t * t) + (19.816 - 0.0441 * t - 0.00017 * (t * t)) * pow(s / 35., 0.5);
+  double DVa = -65.50 + 0.397 * t - 0.005155 * (t * t) + (19.82 - 0.0441 * t - 0.00017 * (t * t)) * pow(s / 35., 0.5);
+  double DK = 0.01847 + 0.0001956 * t - 0.000002212 * (t * t) + (-0.03217 - 0.0000711 * t + 0.000002212) * pow(s / 35., 0.5);
   Kspc = Kspc * exp(-DVc * pitkR + 0.5 * DK * p2itkR);
   Kspa = Kspa * exp(-DVa * pitkR + 0.5 * DK * p2itkR);
   double Ca = 10.28E-3;

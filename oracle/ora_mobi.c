@@ -6,8 +6,10 @@
  *   mobi_driver       one water column                09/mom/mobi.F:519-1483
  *   mobi_src          the ecosystem ODE per cell      09/mom/mobi.F:1485-3313
  * COMMON-block quantities the reference rewrites per cell (ptn_P, k1n, k1p_P,
- * alpha_Diat, sipr0, capr) are locals here.  Real exponents with
- * the literal values 2. and 0.5 are evaluated as x*x and sqrt(x).
+ * alpha_Diat, sipr0, capr) are locals here.  A real exponent with
+ * the literal value 2. is evaluated as x*x (what gcc / gfortran make of pow(x, 2.0) at
+ * every optimisation level); x**(0.5) stays pow(x, 0.5), as in oracle/_ref (the pin
+ * decided: glibc's pow(x, 0.5) differs from sqrt(x) by one ulp for 0.08 % of arguments).
  * TEST INFRASTRUCTURE ONLY (see oracle.h).
  */
 #include <math.h>
@@ -214,7 +216,7 @@ static void mobi_src(const ora_mobi_par *P, int nbio, double dtbio, double capr,
     double o2flag = tanh(dmax(o2, 0.));
     double ligand = dmax(pow(dmax(aou, 40.), 0.8) / 66. + pow(biodon, 0.8) / 4.8, 0.5) / 1000.;
     double fepa = (1.0 + P->kfeleq * (ligand - biodfe)) * o2flag;
-    double feprime = ((-fepa + sqrt(fepa * fepa + 4.0 * P->kfeleq * biodfe)) / (2.0 * P->kfeleq)) * o2flag;
+    double feprime = ((-fepa + pow(fepa * fepa + 4.0 * P->kfeleq * biodfe, 0.5)) / (2.0 * P->kfeleq)) * o2flag;   /* :2217-2219 */
     double feorgads = (P->kfeorg * (pow(((biodetr * detrflag) * P->mc * redctn), 0.58)) * feprime) * o2flag;
     double fecol = P->kfecol * (feprime * feprime) * o2flag;
     double expofe = wwd * biodetrfe;
@@ -626,6 +628,20 @@ static void mobi_driver(const ora_ctx *c, int kmx, double twodt, double rctheta,
 #undef TN
 #undef SRC
 #undef ISM
+}
+
+/* Test entry point (tests/test_cpu_refpin.py): one call of mobi_src with explicit arguments, so that the restatement can
+ * be driven with the same random cells as the translated reference routine.  in[24] = gl, bct, impo, dzt, impo_phos,
+ * dayfrac, wwd, nud, impocaco3, wwc, dissk1, impoopl, wwo, opl_disk1, nudop, nudon, bctz, rn15impo, rc13impo, ac13b,
+ * rcaco3c13impo, impofe, o2, aou; out[12] = nfix, expo, expo_phos, calpro, dissl, expocaco3, expoopl, rn15expo, rc13expo,
+ * rcaco3c13expo, expofe, remife. */
+void ora_test_mobi_src(ora_ctx *c, int nbio, double dtbio, double capr, double *bioin, const double *in, double *bioout, double *out) {
+  src_out so;
+  mobi_src(c->mobi, nbio, dtbio, capr, bioin, in[0], in[1], in[2], in[3], in[4], in[5], in[6], in[7], in[8], in[9], in[10], in[11],
+           in[12], in[13], in[14], in[15], in[16], in[17], in[18], in[19], in[20], in[21], in[22], in[23], bioout, &so);
+  out[0] = so.nfix; out[1] = so.expo; out[2] = so.expo_phos; out[3] = so.calpro; out[4] = so.dissl; out[5] = so.expocaco3;
+  out[6] = so.expoopl; out[7] = so.rn15expo; out[8] = so.rc13expo; out[9] = so.rcaco3c13expo; out[10] = so.expofe;
+  out[11] = so.remife;
 }
 
 /* 09/mom/tracer.F:310-545 (column prologue + mobi_driver) and :848-867 (c14 source) */
