@@ -207,6 +207,16 @@ int uvic_b200_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si);
  * result is used only if the next call's stepinfo equals the hint bit for bit and no upload_t / upload_forcing came
  * in between; otherwise it is discarded and recomputed.  Results are identical with and without hints. */
 int uvic_b200_hint_next_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *next);
+/* How often the sources computed ahead were adopted (hit) or had to be recomputed because the step that came was not the
+ * step that was hinted (miss: relyr, co2ccn, dtts, leapfrog or the t(tau-1) slot differ).  `next` of the hint must carry
+ * the NEXT step's relyr / co2ccn -- a driver advances relyr every step (source/mom/mom.F). */
+int uvic_b200_lookahead_stats(uvic_b200_ctx *ctx, int64_t *hits, int64_t *misses);
+/* Drop sources computed ahead: required after writing t, the forcing or the vertical b.c. through raw device pointers
+ * (uvic_b200_t_ptr / uvic_b200_device_ptr); the upload_* entry points do it themselves. */
+int uvic_b200_invalidate_lookahead(uvic_b200_ctx *ctx);
+/* Orders the context's launch stream behind its side streams (look-ahead MOBI, GM velocities), so that an event the caller
+ * records next covers all the work issued so far. */
+int uvic_b200_join_streams(uvic_b200_ctx *ctx);
 /* Latitude slabs: `cuda_event` (a cudaEvent_t) marks the end of the halo exchange of the newest time level.  The next
  * uvic_b200_step lets its coefficient / diffusion kernels (which only read t(tau-1)) run beside the exchange and waits
  * for the event right before its first advection kernel; a mixing step, or a step driven through the separate
@@ -253,6 +263,11 @@ void *uvic_b200_device_ptr(uvic_b200_ctx *ctx, const char *name, size_t *nelem);
 /* device pointer of t at a time level: t(imt,km,jl,nt) */
 void *uvic_b200_t_ptr(uvic_b200_ctx *ctx, int level);
 /* number of kernels this context has launched so far */
+/* Measurement helper (bench.py): the FP64 instruction rates of this device -- thread-level DFMA, DADD, DMUL per second from
+ * dependent-chain kernels with no memory traffic, best of three launches -- the roof the MOBI and flux kernels are measured
+ * against ("reported against both roofs").  Not part of the reference interface. */
+int uvic_b200_measure_fp64_peak(int device, double *dfma_per_s, double *dadd_per_s, double *dmul_per_s, double *sm_clock_mhz);
+
 int64_t uvic_b200_kernel_launches(const uvic_b200_ctx *ctx);
 /* per-kernel device time, measured with CUDA events on the launch stream while enabled */
 int uvic_b200_profile_enable(uvic_b200_ctx *ctx, int on);

@@ -5,9 +5,13 @@
  * library, bench.py's GPU arm) may include, link or call this code; only tests/,
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs do.
  *
- * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures, and it
- * cannot be compiled in this environment (no Fortran compiler, no libnetcdf, no input
- * data set), so this restatement is the pin.  Every routine follows the reference's
+ * PARITY PINNED against the reference's own code: the reference ships no tests, golden vectors or
+ * fixtures and no Fortran compiler exists here, so oracle/refgen cpp-expands the reference sources
+ * exactly as `mk` does and translates them to C MECHANICALLY (f2c.py, no hand editing) into
+ * oracle/_ref/libref_<tag>.so; tests/test_cpu_refpin.py drives that library and this restatement
+ * with the same inputs and requires BITWISE equality (isopyc, vmixc, adv_flux, isoflux, mobi_init,
+ * mobi_src on 10^4 random cells, co2calc_SWS, state, adv_vel, diagt1, filt/filtr/findex, and whole
+ * `tracer` steps with MOBI over leapfrog and mixing steps).  Every routine follows the reference's
  * array shapes, index ranges, loop order and operation order, and cites the
  * reference file:line it restates (paths relative to /root/reference; "09/" means
  * updates/09/source/, the update level run/mk.in:204 selects).

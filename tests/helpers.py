@@ -59,3 +59,14 @@ def oracle_clinic(o):
     """adv_vel -> state -> setvbc -> clinic as mom sequences them (source/mom/mom.F:300-390)"""
     for fn in ("ora_adv_vel", "ora_adv_vel_u", "ora_state", "ora_setvbc_mom", "ora_clinic"):
         o.call(fn)
+
+
+def pointwise_relerr(a, b, rel_floor=1e-3):
+    """max over cells of |a-b| / |b|, taken over the cells with |b| > rel_floor * max|b| (a point-wise relative
+    difference has no meaning where the field passes through zero: sums of opposite-signed flux terms).
+    Reported beside `relerr`, the field-normalised metric."""
+    den = np.abs(b)
+    big = den > rel_floor * (den.max() if den.size else 0.0)
+    if not big.any():
+        return 0.0
+    return float((np.abs(a - b)[big] / den[big]).max())

@@ -18,7 +18,7 @@ REFERENCE = "/root/reference"
 # the variants the tests use: tag -> size.h overrides (nt = 37, nsrc = 35 come from the options of run/mk.in)
 VARIANTS = {
     "s": {"imt": 34, "jmt": 26, "km": 8},
-    "m": {"imt": 42, "jmt": 34, "km": 10},
+    "t": {"imt": 20, "jmt": 16, "km": 6},      # tests/golden/ref_step_t.npz is made from this one
 }
 
 

@@ -388,3 +388,19 @@ def test_diagt1_inventories_bitwise(pkg, ref):
         a, b = o.arr("sumbk", (case.nt, case.km, 3))[n - 1], ref.view("sumbk")[n - 1]
         assert np.array_equal(a, b), ("sumbk", n, np.abs(a - b).max())
     o.close()
+
+
+def test_oracle_reproduces_reference_golden_vectors(pkg):
+    """tests/golden/ref_step_t.npz was written by the reference's own (translated) code (tests/golden/make_ref_golden.py);
+    the hand-written oracle reproduces it bit for bit.  Needs neither /root/reference nor oracle/_ref."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_step_t.npz"))
+    case = pkg.synthetic.make_case(imt=20, jmt=16, km=6, nt=37, seed=int(g["seed"]))
+    assert np.array_equal(case["kmt"], g["kmt"])
+    o = make_oracle(case, do_mobi=1)
+    o.set_scalar("do_filter", 0)
+    for itt, lf in enumerate(g["schedule"]):
+        oracle_set_step(o, case, bool(lf))
+        o.call("ora_step")
+        assert np.array_equal(o.t()[2][:, 1:-1], g[f"t_p1_step{itt}"][:, 1:-1]), itt
+        oracle_rotate(o)
+    o.close()

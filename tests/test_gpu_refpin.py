@@ -1,0 +1,64 @@
+"""The CUDA path against the REFERENCE'S OWN CODE: against the golden vectors the translated reference wrote
+(tests/golden/ref_step_t.npz) and, when the built library travelled to this box, against oracle/_ref/libref_s.so run side
+by side (stress case: convection in a third of the columns, concentrations below trcmin, surface fluxes)."""
+import os
+
+import numpy as np
+import pytest
+
+import reflib
+from conftest import load_pkg
+from helpers import pointwise_relerr, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    return load_pkg()
+
+
+def test_cuda_step_matches_reference_golden_vectors(pkg):
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_step_t.npz"))
+    case = pkg.synthetic.make_case(imt=20, jmt=16, km=6, nt=37, seed=int(g["seed"]))
+    ctx = pkg.TracerContext(case, mobi=1, fourfil=0)
+    ctx.load_state()
+    for itt, lf in enumerate(g["schedule"]):
+        ctx.step(leapfrog=bool(lf))
+        got, ref = ctx.download_t(+1), g[f"t_p1_step{itt}"]
+        assert np.array_equal(got[:, 1:-1] == 0, ref[:, 1:-1] == 0), "land / below-bottom cells"      # mask rule, bit exact
+        for n, nm in enumerate(case.tracer_names):
+            assert relerr(got[n, 1:-1], ref[n, 1:-1]) <= 1e-12, (itt, nm, relerr(got[n, 1:-1], ref[n, 1:-1]))
+        ctx.rotate()
+    ctx.close()
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(reflib.REFDIR, "libref_s.so")), reason="oracle/_ref/libref_s.so did not travel")
+def test_cuda_step_matches_translated_reference_side_by_side(pkg):
+    import test_cpu_refpin as T
+
+    ref = reflib.RefLib("s")
+    case, o = T.setup_pair(pkg, ref, seed=11, fourfil=True)
+    T._stress(case, o, ref, np.random.default_rng(11))
+    # the stressed state into the case the CUDA context loads
+    case.arrays["t"] = o.t()[:2].copy()
+    case.arrays["stf"] = o.arr("stf").reshape(case.nt, case.jmt, case.imt).copy()
+    case.arrays["btf"] = o.arr("btf").reshape(case.nt, case.jmt, case.imt).copy()
+    ctx = pkg.TracerContext(case, mobi=1, fourfil=1)
+    ctx.load_state()
+    worst = 0.0
+    for itt, lf in enumerate((True, True, False, True)):
+        T.ref_set_step(ref, o, case, lf)
+        ref.set("first", 1 if itt == 0 else 0)
+        T.ref_step(ref)
+        ctx.step(leapfrog=lf)
+        got, want = ctx.download_t(+1), ref.view("t")[2]
+        for n, nm in enumerate(case.tracer_names):
+            e = relerr(got[n, 1:-1], want[n, 1:-1])
+            worst = max(worst, e)
+            assert e <= 1e-12, (itt, nm, e)
+        T.ref_rotate(ref)
+        ctx.rotate()
+    print(f"CUDA vs translated reference, 4 steps, 37 tracers: worst normalised difference {worst:.2e}")
+    ctx.close()
+    o.close()

@@ -83,6 +83,7 @@ ABI_SYMBOLS = [
     "uvic_b200_tavg_accumulate", "uvic_b200_tavg_fetch", "uvic_b200_state", "uvic_b200_gasbc", "uvic_b200_wait_before_advection",
     "uvic_b200_clinic_setup", "uvic_b200_upload_u_level", "uvic_b200_download_u", "uvic_b200_upload_smf", "uvic_b200_clinic",
     "uvic_b200_download_zu", "uvic_b200_rotate_u",
+    "uvic_b200_lookahead_stats", "uvic_b200_invalidate_lookahead", "uvic_b200_join_streams", "uvic_b200_measure_fp64_peak",
 ]
 
 _lib = None
@@ -117,6 +118,10 @@ def load_library():
         getattr(L, "uvic_b200_" + fn).argtypes = [vp, C.POINTER(StepInfo)]
     L.uvic_b200_tracer_step.argtypes = [vp, C.POINTER(StepInfo)] + [vp] * 8
     L.uvic_b200_hint_next_step.argtypes = [vp, C.POINTER(StepInfo)]
+    L.uvic_b200_lookahead_stats.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.uvic_b200_invalidate_lookahead.argtypes = [vp]
+    L.uvic_b200_join_streams.argtypes = [vp]
+    L.uvic_b200_measure_fp64_peak.argtypes = [C.c_int] + [C.POINTER(C.c_double)] * 4
     L.uvic_b200_pin_host.argtypes = [vp, C.c_size_t]
     L.uvic_b200_unpin_host.argtypes = [vp]
     L.uvic_b200_inventory.argtypes = [vp, C.c_int, vp]
@@ -156,6 +161,16 @@ def load_library():
     L.uvic_b200_rotate_u.argtypes = [vp]
     _lib = L
     return L
+
+
+def measure_fp64_peak(device=0):
+    """thread-level FP64 instruction rates of the device (dependent DFMA / DADD / DMUL chains, no memory traffic)"""
+    L = load_library()
+    a, b, c, clk = C.c_double(), C.c_double(), C.c_double(), C.c_double()
+    if L.uvic_b200_measure_fp64_peak(int(device), C.byref(a), C.byref(b), C.byref(c), C.byref(clk)) != 0:
+        raise RuntimeError("uvic_b200_measure_fp64_peak failed")
+    return {"dfma_per_s": a.value, "dadd_per_s": b.value, "dmul_per_s": c.value, "sm_clock_mhz_nominal": clk.value,
+            "tflops_fma": 2.0 * a.value / 1e12}
 
 
 class UvicError(RuntimeError):
@@ -264,6 +279,7 @@ class TracerContext:
         self.dtts = float(s["dtts"])
         self.relyr = float(s.get("relyr", 0.0))
         self.co2ccn = float(s.get("co2ccn", 280.0))
+        self.relyr_next = self.co2ccn_next = None
 
     # ---- plumbing ----------------------------------------------------------------
     def _ck(self, rc):
@@ -478,9 +494,30 @@ class TracerContext:
         self._ck(self.L.uvic_b200_tracer(self.h, C.byref(si)))
 
     def hint_next_step(self, leapfrog=True):
-        """Tell the library what the step after the next one looks like (MOBI look-ahead); None-safe."""
+        """Tell the library what the step AFTER the next call looks like (MOBI look-ahead): its leapfrog flag and ITS model
+        time / CO2 (`set_time(relyr, relyr_next)`; a driver advances relyr every step, source/mom/mom.F)."""
         si = self.stepinfo(leapfrog)
+        si.relyr = self.relyr_next if self.relyr_next is not None else self.relyr
+        si.co2ccn = self.co2ccn_next if self.co2ccn_next is not None else self.co2ccn
         self._ck(self.L.uvic_b200_hint_next_step(self.h, C.byref(si)))
+
+    def set_time(self, relyr, relyr_next=None, co2ccn=None, co2ccn_next=None):
+        """Model time (years) and atmospheric CO2 of the next step call, and of the step after it (for the look-ahead hint)."""
+        self.relyr, self.relyr_next = float(relyr), (None if relyr_next is None else float(relyr_next))
+        if co2ccn is not None:
+            self.co2ccn = float(co2ccn)
+        self.co2ccn_next = None if co2ccn_next is None else float(co2ccn_next)
+
+    def lookahead_stats(self):
+        h, m = C.c_int64(), C.c_int64()
+        self._ck(self.L.uvic_b200_lookahead_stats(self.h, C.byref(h), C.byref(m)))
+        return h.value, m.value
+
+    def invalidate_lookahead(self):
+        self._ck(self.L.uvic_b200_invalidate_lookahead(self.h))
+
+    def join_side_streams(self):
+        self._ck(self.L.uvic_b200_join_streams(self.h))
 
     def step(self, leapfrog=True, diag=False, next_leapfrog=None):
         if next_leapfrog is not None:

@@ -52,13 +52,30 @@ static void set_levels(uvic_b200_ctx *c, bool leapfrog) {
 
 extern "C" {
 
+static void halo_wait_now(uvic_b200_ctx *ctx);
+
 const char *uvic_b200_version(void) { return "uvic_b200 0.1 (sm_100a)"; }
 
 const char *uvic_b200_last_error(const uvic_b200_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
+static int create_impl(const uvic_b200_dims *d, const uvic_b200_grid *g, const uvic_b200_params *par, const uvic_b200_static *st,
+                       int device, uvic_b200_ctx **out, uvic_b200_ctx *&ctx);
 int uvic_b200_create(const uvic_b200_dims *d, const uvic_b200_grid *g, const uvic_b200_params *par, const uvic_b200_static *st,
                      int device, uvic_b200_ctx **out) {
   uvic_b200_ctx *ctx = nullptr;
+  if (out) *out = nullptr;
+  const int rc = create_impl(d, g, par, st, device, out, ctx);
+  if (rc != 0 && ctx) {
+    // a failed create leaves nothing behind: the cause goes to the create-error slot (uvic_b200_last_error(NULL)), the
+    // device memory, streams and events of the half-built context are released
+    g_create_err = ctx->err;
+    if (out) *out = nullptr;
+    uvic_b200_destroy(ctx);
+  }
+  return rc;
+}
+static int create_impl(const uvic_b200_dims *d, const uvic_b200_grid *g, const uvic_b200_params *par, const uvic_b200_static *st,
+                       int device, uvic_b200_ctx **out, uvic_b200_ctx *&ctx) {
   if (!d || !g || !par || !st || !out) return fail(nullptr, "uvic_b200_create: null argument");
   if (d->imt < 4 || d->jmt < 4 || d->km < 2 || d->nt < 2) return fail(nullptr, "uvic_b200_create: bad dims");
   if (d->jrow_lo < 2 || d->jrow_hi > d->jmt - 1 || d->jrow_lo > d->jrow_hi)
@@ -308,11 +325,13 @@ int uvic_b200_destroy(uvic_b200_ctx *ctx) {
 }
 
 int uvic_b200_set_stream(uvic_b200_ctx *ctx, void *s) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   if (!ctx) return 1;
   ctx->stream = (cudaStream_t)s;
   return 0;
 }
 int uvic_b200_synchronize(uvic_b200_ctx *ctx) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   gm_join(ctx);
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaGetLastError());
@@ -322,6 +341,7 @@ int uvic_b200_synchronize(uvic_b200_ctx *ctx) {
 static int lev_index(int level) { return level + 1; }
 
 int uvic_b200_upload_t(uvic_b200_ctx *ctx, int level, const double *h) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   if (level < -1 || level > 1) return fail(ctx, "upload_t: level must be -1, 0 or 1");
   if (ctx->ahead_valid) {   // a look-ahead MOBI may be reading this slot; its result is void now
     CK(cudaStreamWaitEvent(ctx->stream, ctx->mobi_event, 0));
@@ -332,6 +352,7 @@ int uvic_b200_upload_t(uvic_b200_ctx *ctx, int level, const double *h) {
   return 0;
 }
 int uvic_b200_download_t(uvic_b200_ctx *ctx, int level, double *h) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   if (level < -1 || level > 1) return fail(ctx, "download_t: level must be -1, 0 or 1");
   CK(cudaMemcpyAsync(h, ctx->t_slot[ctx->lev[lev_index(level)]], (size_t)ctx->v.n3 * ctx->v.nt * sizeof(double),
                      cudaMemcpyDeviceToHost, ctx->stream));
@@ -339,6 +360,7 @@ int uvic_b200_download_t(uvic_b200_ctx *ctx, int level, double *h) {
   return 0;
 }
 int uvic_b200_download_tracer(uvic_b200_ctx *ctx, int level, int n, double *h) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   if (level < -1 || level > 1 || n < 1 || n > ctx->v.nt) return fail(ctx, "download_tracer: bad level or tracer index");
   CK(cudaMemcpyAsync(h, ctx->t_slot[ctx->lev[lev_index(level)]] + (size_t)(n - 1) * ctx->v.n3, (size_t)ctx->v.n3 * sizeof(double),
                      cudaMemcpyDeviceToHost, ctx->stream));
@@ -346,6 +368,7 @@ int uvic_b200_download_tracer(uvic_b200_ctx *ctx, int level, int n, double *h) {
   return 0;
 }
 int uvic_b200_upload_adv_vel(uvic_b200_ctx *ctx, const double *vet, const double *vnt, const double *vbt) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   DevView &v = ctx->v;
   if (vet) CK(cudaMemcpyAsync(v.adv_vet, vet, (size_t)v.n3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   if (vnt) CK(cudaMemcpyAsync(v.adv_vnt, vnt, (size_t)v.n3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -353,10 +376,12 @@ int uvic_b200_upload_adv_vel(uvic_b200_ctx *ctx, const double *vet, const double
   return 0;
 }
 int uvic_b200_upload_u(uvic_b200_ctx *ctx, const double *u) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   CK(cudaMemcpyAsync(ctx->v.u, u, (size_t)ctx->v.n3 * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   return 0;
 }
 int uvic_b200_adv_vel(uvic_b200_ctx *ctx) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   launch_adv_vel(ctx);
   CK(cudaGetLastError());
   return 0;
@@ -364,12 +389,14 @@ int uvic_b200_adv_vel(uvic_b200_ctx *ctx) {
 // state (source/mom/state.F) of a time level: rho_host(imt,km,jl) = dens(T - to, S - so, k); the scratch field of the
 // time averages doubles as the device buffer
 int uvic_b200_state(uvic_b200_ctx *ctx, int level, double *rho_host) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   DevView &v = ctx->v;
   if (level < -1 || level > 1 || !rho_host) return fail(ctx, "state: level must be -1, 0 or 1 and rho non-null");
   if (!ctx->rho_dev) {
     CK(cudaMalloc((void **)&ctx->rho_dev, (size_t)v.n3 * sizeof(double)));
     ctx->owned.push_back(ctx->rho_dev);
   }
+  if (level >= 0) halo_wait_now(ctx);
   launch_state(ctx, ctx->t_slot[ctx->lev[level + 1]], ctx->rho_dev);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(rho_host, ctx->rho_dev, (size_t)v.n3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -377,12 +404,14 @@ int uvic_b200_state(uvic_b200_ctx *ctx, int level, double *rho_host) {
   return 0;
 }
 int uvic_b200_upload_vbc(uvic_b200_ctx *ctx, const double *stf, const double *btf) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   DevView &v = ctx->v;
   if (stf) CK(cudaMemcpyAsync(v.stf, stf, (size_t)v.n2 * v.nt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   if (btf) CK(cudaMemcpyAsync(v.btf, btf, (size_t)v.n2 * v.nt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   return 0;
 }
 int uvic_b200_upload_forcing(uvic_b200_ctx *ctx, const double *dnswr, const double *aice, const double *hice, const double *hsno) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   DevView &v = ctx->v;
   if (!ctx->par.mobi) return fail(ctx, "upload_forcing: context was created without O_mobi");
   if (ctx->ahead_valid) {
@@ -398,6 +427,7 @@ int uvic_b200_upload_forcing(uvic_b200_ctx *ctx, const double *dnswr, const doub
 }
 // ---- surface boundary conditions on the device ----
 int uvic_b200_sbc_setup(uvic_b200_ctx *ctx, int numsbc, const int32_t *flx_index, const int32_t *acc_index) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   if (!ctx || numsbc < 1 || !flx_index || !acc_index) return fail(ctx, "sbc_setup: bad argument");
   if (ctx->v.sbc) return fail(ctx, "sbc_setup: already set up");
   for (int n = 0; n < ctx->v.nt; n++)
@@ -411,6 +441,7 @@ int uvic_b200_sbc_setup(uvic_b200_ctx *ctx, int numsbc, const int32_t *flx_index
   return 0;
 }
 int uvic_b200_upload_sbc(uvic_b200_ctx *ctx, const double *sbc, const double *bhf) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   DevView &v = ctx->v;
   if (!v.sbc) return fail(ctx, "upload_sbc: call uvic_b200_sbc_setup first");
   if (sbc) CK(cudaMemcpyAsync(v.sbc, sbc, (size_t)v.n2 * v.numsbc * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -418,12 +449,14 @@ int uvic_b200_upload_sbc(uvic_b200_ctx *ctx, const double *sbc, const double *bh
   return 0;
 }
 int uvic_b200_upload_sbc_slot(uvic_b200_ctx *ctx, int slot, const double *field) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   DevView &v = ctx->v;
   if (!v.sbc || slot < 1 || slot > v.numsbc || !field) return fail(ctx, "upload_sbc_slot: bad slot or no sbc_setup");
   CK(cudaMemcpyAsync(v.sbc + (size_t)(slot - 1) * v.n2, field, (size_t)v.n2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   return 0;
 }
 int uvic_b200_download_sbc_slot(uvic_b200_ctx *ctx, int slot, double *field) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   DevView &v = ctx->v;
   if (!v.sbc || slot < 1 || slot > v.numsbc || !field) return fail(ctx, "download_sbc_slot: bad slot or no sbc_setup");
   CK(cudaMemcpyAsync(field, v.sbc + (size_t)(slot - 1) * v.n2, (size_t)v.n2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -431,6 +464,7 @@ int uvic_b200_download_sbc_slot(uvic_b200_ctx *ctx, int slot, double *field) {
   return 0;
 }
 int uvic_b200_download_sbc(uvic_b200_ctx *ctx, double *sbc) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   DevView &v = ctx->v;
   if (!v.sbc || !sbc) return fail(ctx, "download_sbc: call uvic_b200_sbc_setup first");
   CK(cudaMemcpyAsync(sbc, v.sbc, (size_t)v.n2 * v.numsbc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -438,6 +472,7 @@ int uvic_b200_download_sbc(uvic_b200_ctx *ctx, double *sbc) {
   return 0;
 }
 int uvic_b200_gasbc(uvic_b200_ctx *ctx, const uvic_b200_gasbc_par *gp) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   DevView &v = ctx->v;
   if (!v.sbc || !gp) return fail(ctx, "gasbc: call uvic_b200_sbc_setup first");
   if (!ctx->par.mobi || !v.aice) return fail(ctx, "gasbc: needs a context with O_mobi (ice fraction, carbon tracers)");
@@ -452,12 +487,14 @@ int uvic_b200_gasbc(uvic_b200_ctx *ctx, const uvic_b200_gasbc_par *gp) {
   return 0;
 }
 int uvic_b200_setvbc(uvic_b200_ctx *ctx) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   if (!ctx->v.sbc) return fail(ctx, "setvbc: call uvic_b200_sbc_setup first");
   launch_setvbc(ctx);
   CK(cudaGetLastError());
   return 0;
 }
 int uvic_b200_set_sbc(uvic_b200_ctx *ctx, int eots, int osegs, int osege, int ntspos) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   if (!ctx->v.sbc) return fail(ctx, "set_sbc: call uvic_b200_sbc_setup first");
   if (ntspos < 1) return fail(ctx, "set_sbc: ntspos must be >= 1");
   launch_set_sbc(ctx, eots, osegs, osege, ntspos);
@@ -467,6 +504,7 @@ int uvic_b200_set_sbc(uvic_b200_ctx *ctx, int eots, int osegs, int osege, int nt
 
 // ---- time averages of the tracers on the device ----
 int uvic_b200_tavg_accumulate(uvic_b200_ctx *ctx, const double *vflux, const double *gaost) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   DevView &v = ctx->v;
   if (!ctx->tavg_t) {
     CK(cudaMalloc((void **)&ctx->tavg_t, (size_t)v.n3 * v.nt * sizeof(double)));
@@ -491,6 +529,7 @@ int uvic_b200_tavg_accumulate(uvic_b200_ctx *ctx, const double *vflux, const dou
   return 0;
 }
 int uvic_b200_tavg_fetch(uvic_b200_ctx *ctx, double *avg_t, double *avg_stf, int32_t *navgts, int reset) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   DevView &v = ctx->v;
   if (!ctx->tavg_t || ctx->navgts < 1) return fail(ctx, "tavg_fetch: nothing accumulated");
   const double rnavgt = 1.0 / (double)ctx->navgts;   // 09/mom/timeavgs.F:407
@@ -518,8 +557,11 @@ int uvic_b200_tavg_fetch(uvic_b200_ctx *ctx, double *avg_t, double *avg_stf, int
 // ---- baroclinic momentum step on the device (09/mom/clinic.F) ----
 static int clinic_setup_impl(uvic_b200_ctx *ctx, const uvic_b200_clinic_static *cs);
 int uvic_b200_clinic_setup(uvic_b200_ctx *ctx, const uvic_b200_clinic_static *cs) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
+  const size_t narrs = ctx ? ctx->arrs.size() : 0;
   const int rc = clinic_setup_impl(ctx, cs);
   if (rc != 0 && ctx && ctx->clinic && ctx->err.find("already set up") == std::string::npos) {
+    ctx->arrs.resize(narrs);   // their slots point into the ClinicView deleted below (uvic_b200_device_ptr / _fetch by name)
     // a half-built momentum state must not be usable: the device arrays stay owned by the context (freed at destroy)
     delete ctx->clinic;
     ctx->clinic = nullptr;
@@ -576,6 +618,7 @@ static int clinic_setup_impl(uvic_b200_ctx *ctx, const uvic_b200_clinic_static *
   return 0;
 }
 int uvic_b200_upload_u_level(uvic_b200_ctx *ctx, int level, const double *u) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   if (!ctx || !u) return fail(ctx, "upload_u_level: null argument");
   double *dst = nullptr;
   if (level == 0) dst = ctx->v.u;
@@ -585,6 +628,7 @@ int uvic_b200_upload_u_level(uvic_b200_ctx *ctx, int level, const double *u) {
   return 0;
 }
 int uvic_b200_download_u(uvic_b200_ctx *ctx, int level, double *u) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   if (!ctx || !u) return fail(ctx, "download_u: null argument");
   const double *src = nullptr;
   if (level == 0) src = ctx->v.u;
@@ -595,11 +639,13 @@ int uvic_b200_download_u(uvic_b200_ctx *ctx, int level, double *u) {
   return 0;
 }
 int uvic_b200_upload_smf(uvic_b200_ctx *ctx, const double *smf) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   if (!ctx || !ctx->clinic || !smf) return fail(ctx, "upload_smf: call uvic_b200_clinic_setup first");
   CK(cudaMemcpyAsync(ctx->clinic->smf, smf, (size_t)ctx->v.n2 * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   return 0;
 }
 int uvic_b200_clinic(uvic_b200_ctx *ctx, double c2dtuv, int itaux, int itauy) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   if (!ctx || !ctx->clinic) return fail(ctx, "clinic: call uvic_b200_clinic_setup first");
   DevView &v = ctx->v;
   if (itaux != 0 || itauy != 0) {
@@ -607,6 +653,7 @@ int uvic_b200_clinic(uvic_b200_ctx *ctx, double c2dtuv, int itaux, int itauy) {
     if (itaux < 1 || itaux > v.numsbc || itauy < 1 || itauy > v.numsbc) return fail(ctx, "clinic: wind stress slot out of range");
   }
   ctx->clinic->c2dtuv = c2dtuv;
+  halo_wait_now(ctx);   // rho and grad_p read the halo rows of t(tau): a pending asynchronous exchange must have landed
   // 09/mom/loadmw.F:150-155: rho of t(tau).  The tau slot is addressed directly: the time-level view of the tracer step
   // (which maps tau-1 onto tau on mixing steps) is left as the tracer entry points set it
   launch_state(ctx, ctx->t_slot[ctx->lev[1]], ctx->clinic->rho);
@@ -616,12 +663,14 @@ int uvic_b200_clinic(uvic_b200_ctx *ctx, double c2dtuv, int itaux, int itauy) {
   return 0;
 }
 int uvic_b200_download_zu(uvic_b200_ctx *ctx, double *zu) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   if (!ctx || !ctx->clinic || !zu) return fail(ctx, "download_zu: call uvic_b200_clinic_setup first");
   CK(cudaMemcpyAsync(zu, ctx->clinic->zu, (size_t)ctx->v.n2 * 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 int uvic_b200_rotate_u(uvic_b200_ctx *ctx) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   if (!ctx || !ctx->clinic) return fail(ctx, "rotate_u: call uvic_b200_clinic_setup first");
   ClinicView *cv = ctx->clinic;
   double *old_m1 = cv->u_m1;
@@ -632,6 +681,7 @@ int uvic_b200_rotate_u(uvic_b200_ctx *ctx) {
 }
 
 int uvic_b200_rotate(uvic_b200_ctx *ctx) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   // tau+1 overwrites the old tau-1 slot next step (source/mom/mom.F:210-212)
   int old_m1 = ctx->lev[0];
   ctx->lev[0] = ctx->lev[1];
@@ -666,6 +716,7 @@ static void begin_mobi_now(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
   if (ctx->ahead_valid) {
     const bool hit = !ctx->prof_on && same_step(*si, ctx->ahead_si) && ctx->ahead_tm1 == ctx->v.t_m1;
     ctx->ahead_valid = false;
+    if (!ctx->prof_on) (hit ? ctx->la_hits : ctx->la_misses)++;
     if (hit) {
       ctx->src_cur = ctx->ahead_buf;
       ctx->v.src = ctx->src_buf[ctx->src_cur];
@@ -736,7 +787,31 @@ static void set_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
   set_levels(ctx, si->leapfrog != 0);
 }
 
+int uvic_b200_lookahead_stats(uvic_b200_ctx *ctx, int64_t *hits, int64_t *misses) {
+  if (!ctx) return 1;
+  if (hits) *hits = ctx->la_hits;
+  if (misses) *misses = ctx->la_misses;
+  return 0;
+}
+// A driver that writes t, the forcing or the vertical b.c. through raw device pointers (uvic_b200_t_ptr,
+// uvic_b200_device_ptr) after a step calls this: sources computed ahead from the old contents are dropped.
+int uvic_b200_invalidate_lookahead(uvic_b200_ctx *ctx) {
+  if (!ctx) return 1;
+  if (ctx->ahead_valid && ctx->mobi_event) CK(cudaStreamWaitEvent(ctx->stream, ctx->mobi_event, 0));
+  ctx->ahead_valid = false;
+  ctx->hint_valid = false;
+  return 0;
+}
+// Orders the caller's stream behind everything the library has queued on its side streams (the look-ahead MOBI, the GM
+// velocities): an event recorded on the launch stream afterwards covers ALL the work of the steps issued so far.
+int uvic_b200_join_streams(uvic_b200_ctx *ctx) {
+  if (!ctx) return 1;
+  if (ctx->mobi_event) CK(cudaStreamWaitEvent(ctx->stream, ctx->mobi_event, 0));
+  if (ctx->ev_gm) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_gm, 0));
+  return 0;
+}
 int uvic_b200_hint_next_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *next) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   if (!ctx) return 1;
   ctx->hint_valid = next != nullptr;
   if (next) ctx->hint_si = *next;
@@ -749,6 +824,7 @@ int uvic_b200_hint_next_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *next)
 // the library, which waits for it right before the first advection kernel -- or at once when the step is a mixing
 // step (t(tau-1) := t(tau)) or is driven call site by call site.  The event is consumed by the wait.
 int uvic_b200_wait_before_advection(uvic_b200_ctx *ctx, void *cuda_event) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   if (!ctx) return 1;
   ctx->halo_event = (cudaEvent_t)cuda_event;
   return 0;
@@ -760,12 +836,14 @@ static void halo_wait_now(uvic_b200_ctx *ctx) {
 }
 
 int uvic_b200_isopyc(uvic_b200_ctx *ctx) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   halo_wait_now(ctx);
   launch_isopyc(ctx);
   CK(cudaGetLastError());
   return 0;
 }
 int uvic_b200_vmixc(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   set_step(ctx, si);
   if (!si->leapfrog) halo_wait_now(ctx);
   launch_vmixc(ctx);
@@ -773,6 +851,7 @@ int uvic_b200_vmixc(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
   return 0;
 }
 int uvic_b200_tracer(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   set_step(ctx, si);
   if (!si->leapfrog) halo_wait_now(ctx);
   begin_mobi(ctx, si);
@@ -787,6 +866,7 @@ int uvic_b200_tracer(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
   return lookahead_mobi(ctx);
 }
 int uvic_b200_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   set_step(ctx, si);
   if (!si->leapfrog || ctx->prof_on) halo_wait_now(ctx);   // a mixing step reads the newest level from its first kernel on
   begin_mobi(ctx, si);
@@ -799,11 +879,12 @@ int uvic_b200_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
 int uvic_b200_tracer_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si, const double *t_taum1, const double *t_tau,
                           const double *adv_vet, const double *adv_vnt, const double *adv_vbt, const double *stf,
                           const double *btf, double *t_taup1) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   DevView &v = ctx->v;
   static const bool trace = getenv("UVIC_B200_E2E_TRACE") != nullptr;   // phase times of the call on stderr (diagnostics)
-  static cudaEvent_t tev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t *tev = ctx->trace_ev;      // per context: events belong to one device
   if (trace && !tev[0])
-    for (auto &e : tev) cudaEventCreate(&e);
+    for (int q = 0; q < 5; q++) cudaEventCreate(&tev[q]);
   if (trace) cudaEventRecord(tev[0], ctx->stream);
   halo_wait_now(ctx);
   if (t_taum1 && uvic_b200_upload_t(ctx, -1, t_taum1)) return 1;
@@ -857,6 +938,7 @@ int uvic_b200_tracer_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si, cons
 int uvic_b200_tracer_step_coupled(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si, const double *adv_vet, const double *adv_vnt,
                                   const double *adv_vbt, const double *sbc_in, const double *bhf, int eots, int osegs, int osege,
                                   int ntspos, double *ts_taup1, double *sbc_out) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   DevView &v = ctx->v;
   if (!v.sbc) return fail(ctx, "tracer_step_coupled: call uvic_b200_sbc_setup first");
   if (ntspos < 1) return fail(ctx, "tracer_step_coupled: ntspos must be >= 1");
@@ -904,6 +986,7 @@ int uvic_b200_pin_host(void *host, size_t bytes) {
 int uvic_b200_unpin_host(void *host) { return cudaHostUnregister(host) == cudaSuccess ? 0 : 1; }
 
 int uvic_b200_inventory(uvic_b200_ctx *ctx, int level, double *out) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   if (level < -1 || level > 1) return fail(ctx, "inventory: bad level");
   launch_inventory(ctx, ctx->t_slot[ctx->lev[lev_index(level)]], ctx->red_out);
   CK(cudaGetLastError());
@@ -912,18 +995,21 @@ int uvic_b200_inventory(uvic_b200_ctx *ctx, int level, double *out) {
   return 0;
 }
 int uvic_b200_tbar(uvic_b200_ctx *ctx, double *h) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   size_t n = (size_t)ctx->v.km * ctx->v.nt * (ctx->v.jhi - ctx->v.jlo + 1);
   CK(cudaMemcpyAsync(h, ctx->tbar, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 int uvic_b200_sumbk(uvic_b200_ctx *ctx, double *h) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   CK(cudaMemcpyAsync(h, ctx->sumbk, (size_t)3 * ctx->v.km * ctx->v.nt * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 
 void *uvic_b200_device_ptr(uvic_b200_ctx *ctx, const char *name, size_t *nelem) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   for (auto &a : ctx->arrs)
     if (a.name == name) {
       if (nelem) *nelem = a.nelem;
@@ -932,6 +1018,7 @@ void *uvic_b200_device_ptr(uvic_b200_ctx *ctx, const char *name, size_t *nelem) 
   return nullptr;
 }
 int uvic_b200_fetch(uvic_b200_ctx *ctx, const char *name, double *host, size_t *nelem) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   size_t n = 0;
   void *p = uvic_b200_device_ptr(ctx, name, &n);
   if (!p) return fail(ctx, std::string("fetch: unknown array ") + name);
@@ -945,12 +1032,14 @@ int uvic_b200_fetch(uvic_b200_ctx *ctx, const char *name, double *host, size_t *
   return 0;
 }
 void *uvic_b200_t_ptr(uvic_b200_ctx *ctx, int level) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   if (level < -1 || level > 1) return nullptr;
   return ctx->t_slot[ctx->lev[lev_index(level)]];
 }
 int64_t uvic_b200_kernel_launches(const uvic_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 int uvic_b200_profile_enable(uvic_b200_ctx *ctx, int on) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   if (!ctx) return 1;
   ctx->prof_on = on != 0;
   return 0;
@@ -970,10 +1059,12 @@ static int prof_drain(uvic_b200_ctx *ctx) {
   return 0;
 }
 int uvic_b200_profile_count(uvic_b200_ctx *ctx) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   if (!ctx || prof_drain(ctx)) return -1;
   return (int)ctx->prof_names.size();
 }
 int uvic_b200_profile_get(uvic_b200_ctx *ctx, int idx, char *name, int name_len, double *total_ms, int64_t *count) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   if (!ctx || idx < 0 || idx >= (int)ctx->prof_names.size()) return 1;
   if (name && name_len > 0) {
     strncpy(name, ctx->prof_names[idx].c_str(), name_len - 1);
@@ -984,12 +1075,14 @@ int uvic_b200_profile_get(uvic_b200_ctx *ctx, int idx, char *name, int name_len,
   return 0;
 }
 int uvic_b200_profile_reset(uvic_b200_ctx *ctx) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   if (!ctx || prof_drain(ctx)) return 1;
   for (auto &x : ctx->prof_ms) x = 0.0;
   for (auto &x : ctx->prof_count) x = 0;
   return 0;
 }
 int uvic_b200_local_rows(const uvic_b200_ctx *ctx, int32_t *jbase, int32_t *jl) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   if (!ctx) return 1;
   if (jbase) *jbase = ctx->v.jbase;
   if (jl) *jl = ctx->v.jl;

@@ -339,11 +339,7 @@ static void fct_launch_t(uvic_b200_ctx *c, int nbase, int ng) {
   const FmGeom g = fct_geometry(v, ng, MAXW);
   const size_t plane = (size_t)g.nrows * FM_W;
   const size_t shm = (5 * FM_NSLOT * plane + 8 * FM_MAXW * 32) * sizeof(double) + FM_NSLOT * FM_W * sizeof(int);
-  static size_t shm_set = 0;
-  if (shm > shm_set) {
-    cudaFuncSetAttribute(k_fct_march<MAXW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
-    shm_set = shm;
-  }
+  ensure_dyn_smem(c, (const void *)k_fct_march<MAXW>, shm);
   const int nwarp = (g.nkt == 1) ? v.km : std::min(MAXW, g.TK + (g.nkt == 2 ? 1 : 2));   // most levels any k tile needs ratios for
   const long long nblk = (long long)ng * g.nit * g.nkt * g.nchunk;
   ProfScope ps_(c, "k_fct_march");

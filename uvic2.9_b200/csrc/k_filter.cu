@@ -472,11 +472,7 @@ void launch_filuv(uvic_b200_ctx *c, double *up, const double *spsin, const doubl
   DevView &v = c->v;
   {
     size_t smem = (size_t)(4 * c->filtu_maxim + 8) * sizeof(double);
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-      cudaFuncSetAttribute(k_filuv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      smem_set = smem;
-    }
+    ensure_dyn_smem(c, (const void *)k_filuv, smem);
     ProfScope ps(c, "k_filuv");
     k_filuv<<<c->filtu_nitems, 128, smem, c->stream>>>(v, up, (const FiltItem *)c->filtu_items, c->filtu_mats, spsin, spcos);
   }

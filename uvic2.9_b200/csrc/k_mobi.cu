@@ -1684,13 +1684,9 @@ void launch_mobi(uvic_b200_ctx *c, const DevView &v, const uvic_b200_stepinfo *s
   // fill the machine either way and the one-thread-per-column kernel issues fewer instructions in total.
   bool ws = (mode < 0) ? (ngroups <= 148 * 8) : (mode != 0);
   if (ws) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(k_mobi_ws<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WsSm));
-      cudaFuncSetAttribute(k_mobi_ws<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)sizeof(WsSm));
-      cudaFuncSetAttribute(k_mobi_ws<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (int)sizeof(WsSm));
-      attr_set = true;
-    }
+    ensure_dyn_smem(c, (const void *)k_mobi_ws<1>, sizeof(WsSm));
+    ensure_dyn_smem(c, (const void *)k_mobi_ws<2>, 2 * sizeof(WsSm));
+    ensure_dyn_smem(c, (const void *)k_mobi_ws<4>, 4 * sizeof(WsSm));
     // G = 4 confines MOBI to a quarter of the SMs it would otherwise touch (48 of 148 on the 100x100 grid), leaving the
     // rest to the kernels of the main stream it overlaps with; measured best for the whole step.
     int G = 4;

@@ -771,12 +771,8 @@ void launch_tracer(uvic_b200_ctx *c, const uvic_b200_stepinfo *si) {
     {
       const int ntq = (ng + 3) / 4;
       const size_t shm = (size_t)v.km * INV_T * sizeof(double);
-      static size_t shm_set = 0;
-      if (shm > 48 * 1024 && shm > shm_set) {
-        cudaFuncSetAttribute(k_invtri<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
-        cudaFuncSetAttribute(k_invtri<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
-        shm_set = shm;
-      }
+      ensure_dyn_smem(c, (const void *)k_invtri<8>, shm);
+      ensure_dyn_smem(c, (const void *)k_invtri<4>, shm);
       ProfScope ps_(c, "k_invtri");
       if (v.km <= 24)
         k_invtri<4><<<cdiv(ncol, 32) * ntq, INV_T, shm, c->stream>>>(v, nbase, ng, ntq);
@@ -786,11 +782,7 @@ void launch_tracer(uvic_b200_ctx *c, const uvic_b200_stepinfo *si) {
     if (c->par.fullconvect) {
       if (nbase == 0) {
         const size_t shm = (size_t)2 * v.km * 128 * sizeof(double);
-        static size_t shm_set = 0;
-        if (shm > 48 * 1024 && shm > shm_set) {
-          cudaFuncSetAttribute(k_convect_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
-          shm_set = shm;
-        }
+        ensure_dyn_smem(c, (const void *)k_convect_ts, shm);
         ProfScope ps_(c, "k_convect_ts");
         k_convect_ts<<<cdiv(ncol, 128), 128, shm, c->stream>>>(v);
       }
