@@ -263,6 +263,32 @@ void *uvic_b200_device_ptr(uvic_b200_ctx *ctx, const char *name, size_t *nelem);
 /* device pointer of t at a time level: t(imt,km,jl,nt) */
 void *uvic_b200_t_ptr(uvic_b200_ctx *ctx, int level);
 /* number of kernels this context has launched so far */
+/* ---- several devices, ONE host thread ------------------------------------------------------------------------------
+ * The reference's host is a single serial process (source/mom/mom.F:289-407; SURVEY.md 8b "one process, 8 devices").  A
+ * group holds one context per device, each owning a latitude slab of equal estimated work (rows 2..jmt-1 cut by wet-cell
+ * count).  Every array argument is the GLOBAL array exactly as the COMMON blocks hold it (j extent jmt; `tlat`, `kmt`, ...
+ * of uvic_b200_grid / uvic_b200_static likewise): the library slices it.  group_step queues one ocean step on every device and
+ * then lets every device pull the 2-row halos of t(tau+1) from its neighbours' memory (peer copies over NVLink, ordered
+ * by events; the consumer waits right before its first advection kernel).  Inventories are per-device partial sums added
+ * on the host in device order (fixed order).  Calls are asynchronous unless they return data. */
+typedef struct uvic_b200_group uvic_b200_group;
+int uvic_b200_group_create(const uvic_b200_dims *dims, const uvic_b200_grid *grid, const uvic_b200_params *par,
+                           const uvic_b200_static *st, int ndev, const int32_t *devices /* NULL: 0..ndev-1 */, uvic_b200_group **out);
+int uvic_b200_group_destroy(uvic_b200_group *g);
+const char *uvic_b200_group_last_error(const uvic_b200_group *g);   /* g may be NULL: last create error */
+int uvic_b200_group_size(const uvic_b200_group *g);
+uvic_b200_ctx *uvic_b200_group_ctx(uvic_b200_group *g, int r);      /* the r-th context, for the per-context entry points */
+int uvic_b200_group_rows(const uvic_b200_group *g, int r, int32_t *jrow_lo, int32_t *jrow_hi);
+int uvic_b200_group_upload_t(uvic_b200_group *g, int level, const double *t_global);       /* t(imt,km,jmt,nt) */
+int uvic_b200_group_download_t(uvic_b200_group *g, int level, double *t_global);           /* synchronous */
+int uvic_b200_group_upload_adv_vel(uvic_b200_group *g, const double *adv_vet, const double *adv_vnt, const double *adv_vbt);
+int uvic_b200_group_upload_vbc(uvic_b200_group *g, const double *stf, const double *btf);  /* (imt,jmt,nt) */
+int uvic_b200_group_upload_forcing(uvic_b200_group *g, const double *dnswr, const double *aice, const double *hice, const double *hsno);
+int uvic_b200_group_step(uvic_b200_group *g, const uvic_b200_stepinfo *si, const uvic_b200_stepinfo *next /* may be NULL */);
+int uvic_b200_group_rotate(uvic_b200_group *g);
+int uvic_b200_group_inventory(uvic_b200_group *g, int level, double *out_nt);              /* synchronous */
+int uvic_b200_group_synchronize(uvic_b200_group *g);
+
 /* Measurement helper (bench.py): the FP64 instruction rates of this device -- thread-level DFMA, DADD, DMUL per second from
  * dependent-chain kernels with no memory traffic, best of three launches -- the roof the MOBI and flux kernels are measured
  * against ("reported against both roofs").  Not part of the reference interface. */

@@ -2,6 +2,6 @@
 from . import synthetic  # noqa: F401
 from . import timestep  # noqa: F401
 from . import api  # noqa: F401
-from .api import TracerContext, UvicError, load_library  # noqa: F401
+from .api import TracerContext, TracerGroup, UvicError, load_library  # noqa: F401
 from . import slab  # noqa: F401
 from . import mobi_params  # noqa: F401

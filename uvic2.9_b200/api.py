@@ -14,7 +14,9 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libuvic_b200.so")
+# UVIC_B200_LIB selects another build of the same library (A/B experiments: scripts/build_variants.py); the default is the
+# in-tree product build
+LIB_PATH = os.environ.get("UVIC_B200_LIB") or os.path.join(HERE, "libuvic_b200.so")
 
 _c_double_p = C.POINTER(C.c_double)
 _c_int_p = C.POINTER(C.c_int32)
@@ -84,6 +86,10 @@ ABI_SYMBOLS = [
     "uvic_b200_clinic_setup", "uvic_b200_upload_u_level", "uvic_b200_download_u", "uvic_b200_upload_smf", "uvic_b200_clinic",
     "uvic_b200_download_zu", "uvic_b200_rotate_u",
     "uvic_b200_lookahead_stats", "uvic_b200_invalidate_lookahead", "uvic_b200_join_streams", "uvic_b200_measure_fp64_peak",
+    "uvic_b200_group_create", "uvic_b200_group_destroy", "uvic_b200_group_last_error", "uvic_b200_group_size", "uvic_b200_group_ctx",
+    "uvic_b200_group_rows", "uvic_b200_group_upload_t", "uvic_b200_group_download_t", "uvic_b200_group_upload_adv_vel",
+    "uvic_b200_group_upload_vbc", "uvic_b200_group_upload_forcing", "uvic_b200_group_step", "uvic_b200_group_rotate",
+    "uvic_b200_group_inventory", "uvic_b200_group_synchronize",
 ]
 
 _lib = None
@@ -122,6 +128,21 @@ def load_library():
     L.uvic_b200_invalidate_lookahead.argtypes = [vp]
     L.uvic_b200_join_streams.argtypes = [vp]
     L.uvic_b200_measure_fp64_peak.argtypes = [C.c_int] + [C.POINTER(C.c_double)] * 4
+    L.uvic_b200_group_create.argtypes = [C.POINTER(Dims), C.POINTER(Grid), C.POINTER(Params), C.POINTER(Static), C.c_int, vp, C.POINTER(vp)]
+    L.uvic_b200_group_last_error.restype = C.c_char_p
+    L.uvic_b200_group_last_error.argtypes = [vp]
+    L.uvic_b200_group_ctx.restype = vp
+    L.uvic_b200_group_ctx.argtypes = [vp, C.c_int]
+    L.uvic_b200_group_rows.argtypes = [vp, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    for fn in ("destroy", "size", "rotate", "synchronize"):
+        getattr(L, "uvic_b200_group_" + fn).argtypes = [vp]
+    L.uvic_b200_group_upload_t.argtypes = [vp, C.c_int, vp]
+    L.uvic_b200_group_download_t.argtypes = [vp, C.c_int, vp]
+    L.uvic_b200_group_upload_adv_vel.argtypes = [vp, vp, vp, vp]
+    L.uvic_b200_group_upload_vbc.argtypes = [vp, vp, vp]
+    L.uvic_b200_group_upload_forcing.argtypes = [vp, vp, vp, vp, vp]
+    L.uvic_b200_group_step.argtypes = [vp, C.POINTER(StepInfo), C.POINTER(StepInfo)]
+    L.uvic_b200_group_inventory.argtypes = [vp, C.c_int, vp]
     L.uvic_b200_pin_host.argtypes = [vp, C.c_size_t]
     L.uvic_b200_unpin_host.argtypes = [vp]
     L.uvic_b200_inventory.argtypes = [vp, C.c_int, vp]
@@ -590,3 +611,110 @@ class TracerContext:
 
     def shape3z(self):
         return (self.jl, self.km + 1, self.imt)
+
+
+class TracerGroup:
+    """Several devices driven by one host thread (uvic_b200_group_*): the mode the serial Fortran host uses.  Takes the GLOBAL
+    arrays of a Case; the library cuts the latitude slabs, exchanges the halos with peer copies and sums the inventories."""
+
+    def __init__(self, case, devices, fct=1, isopycmix=1, tidal_kv=1, fullconvect=1, mobi=0, fourfil=0):
+        self.L = load_library()
+        self.case = case
+        imt, jmt, km, nt, nsrc = case.imt, case.jmt, case.km, case.nt, case.nsrc
+        self.imt, self.jmt, self.km, self.nt = imt, jmt, km, nt
+        a, s = case.arrays, case.scalars
+        self._keep = []
+
+        def f64(x):
+            x = np.ascontiguousarray(x, dtype=np.float64)
+            self._keep.append(x)
+            return x
+
+        d = Dims(imt, jmt, km, nt, max(nsrc, 0), 2, jmt - 1)
+        g = Grid()
+        for n in _GRID_FIELDS:
+            setattr(g, n, _dp(f64(a[n])))
+        p = Params()
+        for n in ("aidif", "kappa_h", "ahisop", "athkdf", "slmxr", "diff_cet", "diff_cnt", "zetar", "ogamma", "gravrho0r"):
+            setattr(p, n, float(s[n]))
+        p.fct, p.isopycmix, p.tidal_kv, p.fullconvect, p.mobi, p.fourfil = fct, isopycmix, tidal_kv, fullconvect, mobi, fourfil
+        if fourfil:
+            p.jfrst, p.jft0, p.jft1, p.jft2 = (int(s[n]) for n in ("jfrst", "jft0", "jft1", "jft2"))
+        itrc = np.ascontiguousarray(a["itrc"], dtype=np.int32)
+        self._keep.append(itrc)
+        p.itrc = itrc.ctypes.data_as(_c_int_p)
+        if mobi:
+            midx = np.ascontiguousarray(a["mobi_idx"], dtype=np.int32)
+            mpar = f64(a["mobi_par"])
+            self._keep.append(midx)
+            p.mobi_index = midx.ctypes.data_as(_c_int_p)
+            p.mobi_par = _dp(mpar)
+            p.n_mobi_index, p.n_mobi_par = midx.size, mpar.size
+        self.mobi = bool(mobi)
+        st = Static()
+        kmt = np.ascontiguousarray(a["kmt"], dtype=np.int32)
+        msk = np.ascontiguousarray(a["mskhr"], dtype=np.int32)
+        self._keep += [kmt, msk]
+        st.kmt = kmt.ctypes.data_as(_c_int_p)
+        st.mskhr = msk.ctypes.data_as(_c_int_p)
+        for n in ("fisop", "addisop", "edrm2", "edrs2", "edrk1", "edro1", "sg_bathy", "fe_hydr", "fe_atmdep"):
+            if n in a:
+                setattr(st, n, _dp(f64(a[n])))
+        devs = np.ascontiguousarray(devices, dtype=np.int32)
+        h = C.c_void_p()
+        rc = self.L.uvic_b200_group_create(C.byref(d), C.byref(g), C.byref(p), C.byref(st), len(devs), devs.ctypes.data, C.byref(h))
+        if rc != 0:
+            raise UvicError(self.L.uvic_b200_group_last_error(None).decode())
+        self.h = h
+        self.n = len(devs)
+        self.dtts = float(s["dtts"])
+        self.relyr = float(s.get("relyr", 0.0))
+        self.co2ccn = float(s.get("co2ccn", 280.0))
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise UvicError(self.L.uvic_b200_group_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.uvic_b200_group_destroy(self.h)
+            self.h = None
+
+    def rows(self, r):
+        lo, hi = C.c_int32(), C.c_int32()
+        self._ck(self.L.uvic_b200_group_rows(self.h, r, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def load_state(self):
+        a = self.case.arrays
+        t = np.ascontiguousarray(a["t"], dtype=np.float64)
+        self._ck(self.L.uvic_b200_group_upload_t(self.h, -1, _vp(t[0])))
+        self._ck(self.L.uvic_b200_group_upload_t(self.h, 0, _vp(t[1])))
+        vet, vnt, vbt = (np.ascontiguousarray(a[n], dtype=np.float64) for n in ("adv_vet", "adv_vnt", "adv_vbt"))
+        self._ck(self.L.uvic_b200_group_upload_adv_vel(self.h, _vp(vet), _vp(vnt), _vp(vbt)))
+        stf, btf = np.ascontiguousarray(a["stf"], dtype=np.float64), np.ascontiguousarray(a["btf"], dtype=np.float64)
+        self._ck(self.L.uvic_b200_group_upload_vbc(self.h, _vp(stf), _vp(btf)))
+        if self.mobi:
+            f = [np.ascontiguousarray(a[n], dtype=np.float64) for n in ("dnswr", "aice", "hice", "hsno")]
+            self._ck(self.L.uvic_b200_group_upload_forcing(self.h, *[_vp(x) for x in f]))
+        self._ck(self.L.uvic_b200_group_synchronize(self.h))
+
+    def step(self, leapfrog=True, next_leapfrog=None):
+        si = StepInfo(self.dtts, 1 if leapfrog else 0, 0, self.relyr, self.co2ccn)
+        nx = None
+        if next_leapfrog is not None:
+            nx = StepInfo(self.dtts, 1 if next_leapfrog else 0, 0, self.relyr, self.co2ccn)
+        self._ck(self.L.uvic_b200_group_step(self.h, C.byref(si), C.byref(nx) if nx is not None else None))
+
+    def rotate(self):
+        self._ck(self.L.uvic_b200_group_rotate(self.h))
+
+    def download_t(self, level):
+        out = np.zeros((self.nt, self.jmt, self.km, self.imt))
+        self._ck(self.L.uvic_b200_group_download_t(self.h, level, _vp(out)))
+        return out
+
+    def inventory(self, level):
+        out = np.empty(self.nt)
+        self._ck(self.L.uvic_b200_group_inventory(self.h, level, _vp(out)))
+        return out

@@ -36,15 +36,20 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False, extra=()):
-    if not force and not needs_build():
+def build(force=False, verbose=False, extra=(), fmad=None, out=None, objdir_name="build", defines=()):
+    """fmad: {file: "true"} overrides; out: another library path (experiment builds keep the product library untouched)"""
+    global FMAD
+    lib = out or LIB
+    if fmad is not None:
+        FMAD = dict(fmad)
+    if not force and not needs_build() and out is None:
         return LIB
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, objdir_name)
     os.makedirs(objdir, exist_ok=True)
 
     def cc(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [NVCC, *FLAGS, f"-fmad={FMAD.get(src, 'false')}", *extra, *os.environ.get("UVIC_B200_NVCC_EXTRA", "").split(), "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [NVCC, *FLAGS, f"-fmad={FMAD.get(src, 'false')}", *extra, *defines, *os.environ.get("UVIC_B200_NVCC_EXTRA", "").split(), "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
@@ -54,11 +59,11 @@ def build(force=False, verbose=False, extra=()):
 
     with ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(cc, sources()))
-    r = subprocess.run([NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"],
+    r = subprocess.run([NVCC, "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a"],
                        capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
