@@ -39,6 +39,8 @@ WORKLOADS = {
                         desc="synthetic 0.5 deg grid 720x360x40, 40 tracers (37 MOBI + 3 passive), isopyc + GM + FCT + invtri (BASELINE config 4)"),
     "uvic100_mobi37": dict(imt=102, rows=100, km=19, nt=37, mobi=1, fourfil=1,
                            desc="UVic 2.9 100x100x19, isopycnal mixing + GM + FCT + full MOBI tracer set with isotopes (run/mk.in), nt=37 (BASELINE config 3)"),
+    "uvic100_mobi21": dict(imt=102, rows=100, km=19, nt=21, mobi=1, fourfil=1, options=(),
+                           desc="UVic 2.9 100x100x19, isopycnal mixing + GM + FCT + full MOBI tracer set WITHOUT isotopes (O_carbon_13/14, O_mobi_nitrogen_15 off), nt=21 (BASELINE config 2)"),
     "uvic100_ts": dict(imt=102, rows=100, km=19, nt=2, mobi=0, fourfil=1, desc="UVic 2.9 100x100x19, T,S only, isopyc + GM + FCT (BASELINE config 1 physics)"),
     "one_deg_37": dict(imt=362, rows=180, km=30, nt=37, mobi=1, fourfil=0,
                        desc="synthetic 1 deg 360x180x30, full MOBI tracer set (profiling size)"),
@@ -80,7 +82,8 @@ def make_case(pkg, wl, world):
             raise SystemExit(f"bench.py: workload {wl} is {bands} slabs of {w['rows'] // bands} rows: run it with --gpus {bands}")
         base = pkg.synthetic.make_case(imt=w["imt"], jmt=2 + w["rows"] // bands, km=w["km"], nt=w["nt"])
         return pkg.synthetic.stack_bands(base, bands, lazy=True)
-    return pkg.synthetic.make_case(imt=w["imt"], jmt=2 + w["rows"], km=w["km"], nt=w["nt"])
+    names = pkg.mobi_params.tracer_names_for(options=w["options"]) if "options" in w else None
+    return pkg.synthetic.make_case(imt=w["imt"], jmt=2 + w["rows"], km=w["km"], nt=w["nt"], names=names)
 
 
 def partition(pkg, case, wl, world):
@@ -256,7 +259,8 @@ def cpu_sample(pkg, wl, budget_s):
     rows = w["rows"] // w.get("bands", 1)
     t_est = (w["imt"] - 2) * rows * w["km"] * w["nt"] / CPU_RATE
     rows_s = rows if t_est <= budget_s else max(8, int(rows * budget_s / t_est))
-    case = pkg.synthetic.make_case(imt=w["imt"], jmt=2 + rows_s, km=w["km"], nt=w["nt"])
+    names = pkg.mobi_params.tracer_names_for(options=w["options"]) if "options" in w else None
+    case = pkg.synthetic.make_case(imt=w["imt"], jmt=2 + rows_s, km=w["km"], nt=w["nt"], names=names)
     what = "the whole grid" if rows_s == rows else f"a {rows_s}-row latitude sub-slab of the grid (same imt, km, nt), throughput per cell"
     return case, what
 

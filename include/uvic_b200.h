@@ -71,7 +71,10 @@ typedef struct uvic_b200_params {
   int32_t fourfil;              /* O_fourfil */
   int32_t jfrst, jft0, jft1, jft2; /* Fourier-filter rows (global), source/common/setcom.F:37-40,75-85 */
   const int32_t *itrc;          /* (nt) source slot per tracer, 0 = none (09/mom/mw.h:125-221) */
-  const int32_t *mobi_index;    /* tracer / source index maps for MOBI, see uvic_b200_mobi.h; may be NULL */
+  const int32_t *mobi_index;    /* tracer / source index maps for MOBI (layout: uvic2.9_b200/csrc/mobi_par.h); may be NULL.  The
+                                 * isotope options are selected independently, as in run/mk.in: the tracers of O_carbon_13,
+                                 * O_carbon_14, O_mobi_nitrogen_15 that a build does not carry (09/common/size.h:31-144) have
+                                 * index 0 here -- e.g. nt = 21, nsrc = 19 for "full MOBI, no isotopes" */
   const double *mobi_par;       /* MOBI parameter block after mobi_init's unit conversion; may be NULL */
   int32_t n_mobi_index, n_mobi_par;
 } uvic_b200_params;
@@ -111,6 +114,11 @@ int uvic_b200_upload_t(uvic_b200_ctx *ctx, int level, const double *t_host);
 int uvic_b200_download_t(uvic_b200_ctx *ctx, int level, double *t_host);
 int uvic_b200_download_tracer(uvic_b200_ctx *ctx, int level, int n, double *field_host); /* lazy D2H of one tracer (1-based n) */
 /* advective velocities from adv_vel (source/mom/adv_vel.F:60-131): (imt,km,jl),(imt,km,jl),(imt,0:km,jl) */
+/* The reference dimensions the advective velocities (imt,km,jsmw:jmw) and (imt,0:km,jsmw:jmw) (09/mom/mw.h:246-263): with
+ * the fully opened memory window jsmw = 2, so the COMMON arrays have NO row 1.  A host that passes c_loc of those arrays
+ * says so once: every host velocity pointer (uvic_b200_upload_adv_vel, _tracer_step, _tracer_step_coupled) is then read as
+ * starting at global row jrow_first (the device row before it keeps its zeros: row 1 is a closed wall).  Default 1. */
+int uvic_b200_set_host_window(uvic_b200_ctx *ctx, int jrow_first);
 int uvic_b200_upload_adv_vel(uvic_b200_ctx *ctx, const double *adv_vet, const double *adv_vnt, const double *adv_vbt);
 /* or: B-grid velocity u(imt,km,jl,2) at tau, and adv_vel on the device */
 int uvic_b200_upload_u(uvic_b200_ctx *ctx, const double *u_host);

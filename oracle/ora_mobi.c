@@ -451,7 +451,13 @@ static void mobi_driver(const ora_ctx *c, int kmx, double twodt, double rctheta,
                         double rnbio) {
   const ora_mobi_par *P = c->mobi;
   const int km = c->km, nsrc = c->nsrc;
-  const int32_t *ix = c->mobi_idx;
+  /* option subsets (O_carbon_13 / O_carbon_14 / O_mobi_nitrogen_15 off): a source slot of 0 means "absent"; its source
+   * goes to the scratch slot nsrc + 1 of the column buffer (the caller sizes it), which nothing reads */
+  int32_t ixl[ORA_MOBI_NIDX];
+  for (int q = 0; q < ORA_MOBI_NIDX; q++) ixl[q] = c->mobi_idx[q];
+  for (int q = MI_SRC; q < MI_SRC + ORA_MOBI_NVAR; q++) if (ixl[q] == 0) ixl[q] = nsrc + 1;
+  for (int q = MI_ISALK; q < MI_N; q++) if (ixl[q] == 0) ixl[q] = nsrc + 1;
+  const int32_t *ix = ixl;
   const double redctn = P->redctn;
 #define TN(k, m) tnpzd[(size_t)(m)*km + ((k)-1)]
 #define SRC(k, s) src[(size_t)((s)-1) * km + ((k)-1)]
@@ -463,7 +469,7 @@ static void mobi_driver(const ora_ctx *c, int kmx, double twodt, double rctheta,
   double rn15impo = 0.0, rn15expo = 0.0, rc13impo = 0.0, rc13expo = 0.0, prca13 = 0.0, rcaco3c13impo = 0.0, rcaco3c13expo = 0.0;
   double expofe = 0.0, impofe = 0.0, calpro = 0.0, caco3in = 0.0, dissl = 0.0, impocaco3 = 0.0, expocaco3 = 0.0, dissk1 = 0.0;
   double expoopl = 0.0, impoopl = 0.0;
-  memset(src, 0, sizeof(double) * (size_t)km * nsrc);
+  memset(src, 0, sizeof(double) * (size_t)km * (nsrc + 1));
   memset(snpzd, 0, sizeof snpzd);
   for (int k = 0; k <= km; k++) { rcalpro[k] = rdissl[k] = rexpocaco3[k] = rexpoopl[k] = 0.0; nfix[k] = bdeni[k] = 0.0; }
 
@@ -665,7 +671,7 @@ void ora_mobi_columns(ora_ctx *c) {
   double rnbio = 1. / nbio;
 
   double tnpzd[ORA_MOBI_NVAR * km], t_in[km], o2_in[km], aou_in[km], s_in[km], dic_in[km], alk_in[km], sgb_in[km];
-  double srccol[(size_t)km * nsrc];
+  double srccol[(size_t)km * (nsrc + 1)];   /* + the scratch slot of an option subset */
   for (int j = js; j <= je; j++) {
     int jrow = j;
     for (int i = is; i <= ie; i++) {
@@ -679,8 +685,10 @@ void ora_mobi_columns(ora_ctx *c) {
         dayfrac = dmax(1e-12, acos(dmax(-1., dayfrac)) / pi);
         double swr = P->tap * c->dnswr[I2(i, jrow)] * 1e-3 * (1. + ai * (exp(-P->ki * (hi + hs)) - 1.));
         /* gather (:393-503) */
+        /* an absent isotope tracer (index 0) reads as 1: its equations are computed and discarded, and no equation of a
+         * present variable reads an isotope variable */
         for (int m = 0; m < ORA_MOBI_NVAR; m++)
-          for (int k = 1; k <= km; k++) tnpzd[(size_t)m * km + (k - 1)] = T(i, k, j, ix[MI_TR + m], TAUM1);
+          for (int k = 1; k <= km; k++) tnpzd[(size_t)m * km + (k - 1)] = ix[MI_TR + m] ? T(i, k, j, ix[MI_TR + m], TAUM1) : 1.0;
         for (int k = 1; k <= km; k++) {
           t_in[k - 1] = T(i, k, j, ix[MI_ITEMP], TAUM1);
           o2_in[k - 1] = T(i, k, j, ix[MI_IO2], TAUM1) * 1000.;
@@ -714,6 +722,7 @@ void ora_mobi_columns(ora_ctx *c) {
     }
   }
   /* source for c14 (:848-867) */
+  if (ix[MI_IC14] == 0) return;   /* O_carbon_14 off */
   for (int j = js; j <= je; j++) {
     int jrow = j;
     for (int i = is; i <= ie; i++)

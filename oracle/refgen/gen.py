@@ -140,8 +140,8 @@ def read_namelists(ref):
     return out
 
 
-def generate(ref, overrides, only_files=None):
-    opts = mk_options(ref)
+def generate(ref, overrides, only_files=None, undef=()):
+    opts = [o for o in mk_options(ref) if o[2:] not in set(undef)]
     tr = f2c.Translator(skip_calls=SKIP_CALLS, overrides=overrides, stub_calls=STUB_CALLS)
     wanted = set()
     for fn, units in UNITS.items():
@@ -166,6 +166,7 @@ def main():
     ap.add_argument("--set", nargs="*", default=[], help="override size.h parameters, e.g. imt=34 jmt=26 km=8")
     ap.add_argument("--tag", default=None, help="output name: oracle/_ref/libref_<tag>.so (default: libref.so)")
     ap.add_argument("--files", nargs="*", default=None)
+    ap.add_argument("--undef", nargs="*", default=[], help="options of run/mk.in to leave out, e.g. O_carbon_13 O_carbon_14 O_mobi_nitrogen_15")
     ap.add_argument("--keep-going", action="store_true")
     a = ap.parse_args()
     if not os.path.isdir(a.ref):
@@ -175,7 +176,7 @@ def main():
     for kv in a.set:
         k, v = kv.split("=")
         overrides[k.strip().lower()] = int(v)
-    tr, opts = generate(a.ref, overrides, a.files)
+    tr, opts = generate(a.ref, overrides, a.files, a.undef)
     csrc = tr.emit()
     os.makedirs(OUT, exist_ok=True)
     suffix = f"_{a.tag}" if a.tag else ""

@@ -19,7 +19,11 @@ REFERENCE = "/root/reference"
 VARIANTS = {
     "s": {"imt": 34, "jmt": 26, "km": 8},
     "t": {"imt": 20, "jmt": 16, "km": 6},      # tests/golden/ref_step_t.npz is made from this one
+    # BASELINE config 2: "full MOBI tracer set, no isotopes" -- the reference built WITHOUT O_carbon_13, O_carbon_14,
+    # O_mobi_nitrogen_15 (nt = 21)
+    "n": {"imt": 34, "jmt": 26, "km": 8},
 }
+UNDEF = {"n": ["O_carbon_13", "O_carbon_14", "O_mobi_nitrogen_15"]}
 
 
 def build_variant(tag, force=False):
@@ -29,7 +33,8 @@ def build_variant(tag, force=False):
     stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
     if (force or stale) and os.path.isdir(REFERENCE):
         sets = [f"{k}={v}" for k, v in VARIANTS[tag].items()]
-        r = subprocess.run([sys.executable, GEN, "--tag", tag, "--set", *sets], capture_output=True, text=True)
+        undef = ["--undef", *UNDEF[tag]] if tag in UNDEF else []
+        r = subprocess.run([sys.executable, GEN, "--tag", tag, "--set", *sets, *undef], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("oracle/refgen/gen.py failed:\n" + r.stdout[-2000:] + r.stderr[-4000:])
     return so if os.path.exists(so) else None

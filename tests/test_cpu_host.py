@@ -217,3 +217,56 @@ def test_stacked_grid_carries_the_momentum_inputs(pkg):
             a = pkg.api.slab_slice(name, st[name], jbase, jl, st)
             b = pkg.api.slab_slice(name, lazy[name], jbase, jl, lazy)
             assert np.array_equal(a, b), (name, jlo)
+
+
+def test_fortran_shim_names_match_the_reference_common_blocks():
+    """uvic2.9_b200/fortran/tracer_gpu.F cannot be compiled here (no Fortran compiler).  What can be checked mechanically: every
+    COMMON array it hands to the library with c_loc, and every COMMON scalar it copies into the parameter / index blocks,
+    exists in the reference's own declarations (the manifest oracle/refgen extracts from the cpp-expanded include files), and
+    the arrays passed straight through have the shape include/uvic_b200.h documents (first row = global row 1)."""
+    import json
+
+    man_path = os.path.join(ROOT, "oracle", "_ref", "ref_gen_s.json")
+    if not os.path.exists(man_path):
+        pytest.skip("oracle/_ref not built")
+    com = json.load(open(man_path))["commons"]
+    src = open(os.path.join(ROOT, "uvic2.9_b200", "fortran", "tracer_gpu.F")).read().lower()
+    local = {"mobi_par", "mobi_idx", "flx_index", "acc_index", "addisop_f", "tbar_f"}
+    imt, jmt, km = 34, 26, 8
+    seen = set()
+    for m in re.finditer(r"c_loc\(([a-z0-9_]+)", src):
+        name = m.group(1)
+        if name in local:
+            continue
+        assert name in com, f"c_loc({name}): not a COMMON member of the reference"
+        seen.add(name)
+    # shapes the header expects, rows from 1: (imt,km,jmt) / (imt,jmt,km) / (imt,jmt) / (jmt) / (km) ...
+    def dims(n):
+        return [tuple(d) for d in com[n][0]["dims"]]
+    for n in ("edrm2", "edrs2", "edrk1", "edro1"):
+        assert dims(n) == [(1, imt), (1, km), (1, jmt)], n
+    for n in ("fisop", "sg_bathy", "fe_hydr"):
+        assert dims(n) == [(1, imt), (1, jmt), (1, km)], n
+    assert dims("kmt") == [(1, imt), (1, jmt)] and dims("mskhr") == [(1, imt), (1, jmt)] and dims("tlat") == [(1, imt), (1, jmt)]
+    assert dims("t")[:4] == [(1, imt), (1, km), (1, jmt), (1, 37)] and dims("t")[4] == (-1, 3)
+    assert dims("c") == [(1, km), (1, 9)] and dims("dzw") == [(0, km + 1)]
+    assert dims("sbc")[:2] == [(1, imt), (1, jmt)] and dims("bhf") == [(1, imt), (1, jmt)] and dims("dnswr") == [(1, imt), (1, jmt)]
+    assert dims("aice") == [(1, imt), (1, jmt), (1, 2)]
+    # the arrays the reference dimensions from row jsmw = 2: the shim must not pass them as if they started at row 1
+    assert dims("addisop")[2][0] == 2 and "addisop_f(:,:,jsmw:jemw) = addisop(:,:,jsmw:jemw)" in src
+    assert dims("adv_vet")[2][0] == 2 and dims("adv_vbt")[2][0] == 2 and "uvic_b200_set_host_window (ctx, jsmw)" in src
+    assert dims("tbar") == [(0, km + 1), (1, 37), (1, jmt)] and "tbar(k,n,jrow) = tbar(k,n,jrow) + tbar_f(k,n,jrow-1)" in src
+    # scalars / index variables copied into the parameter and index blocks
+    for m in re.finditer(r"^\s+(?:mobi_par\(\d+\)|mobi_idx\(\d+\)|flx_index\([a-z0-9_]+\)|p%[a-z0-9_]+)\s*=\s*([a-z_][a-z0-9_]*)\s*$", src, re.M):
+        name = m.group(1)
+        if name in ("n_mobi_idx", "n_mobi_par"):
+            continue
+        assert name in com, f"{m.group(0).strip()}: {name} is not a COMMON member of the reference"
+        seen.add(name)
+    for m in re.finditer(r"flx_index\(([a-z0-9_]+)\)", src):
+        assert m.group(1) in com or m.group(1) in (":", "nt"), m.group(1)
+    assert len(seen) > 200
+    # every C function the shim binds is declared in the header
+    hdr = open(os.path.join(ROOT, "include", "uvic_b200.h")).read()
+    for m in re.finditer(r"bind\(c, name='([a-z0-9_]+)'\)", src):
+        assert m.group(1) == "strlen" or re.search(r"\b" + m.group(1) + r"\s*\(", hdr), m.group(1)

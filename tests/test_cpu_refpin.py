@@ -36,12 +36,13 @@ def oget(o, n):
     return o.L.ora_get_scalar(o.h, n.encode())
 
 
-def setup_pair(pkg, ref, seed=3, mobi=1, fourfil=False, **kw):
+def setup_pair(pkg, ref, seed=3, mobi=1, fourfil=False, names=None, **kw):
     """one synthetic case in the oracle and in the translated reference's COMMON blocks"""
     from uvic29_b200 import mobi_params as mp
 
     d = ref.dims
-    case = pkg.synthetic.make_case(imt=d["imt"], jmt=d["jmt"], km=d["km"], nt=37, seed=seed, **kw)
+    names = names or mp.tracer_names_for()
+    case = pkg.synthetic.make_case(imt=d["imt"], jmt=d["jmt"], km=d["km"], nt=len(names), names=names, seed=seed, **kw)
     o = make_oracle(case, do_mobi=mobi)
     o.set_scalar("do_filter", 1 if fourfil else 0)
     imt, jmt, km = d["imt"], d["jmt"], d["km"]
@@ -66,7 +67,7 @@ def setup_pair(pkg, ref, seed=3, mobi=1, fourfil=False, **kw):
     # tracer / source index maps: what tracer_init assigns (09/common/UVic_ESCM.F:1282-1483)
     for n, nm in enumerate(case.tracer_names):
         ref.set({"temp": "itemp", "salt": "isalt"}.get(nm, "i" + nm), n + 1)
-    for s, nm in enumerate(mp.SOURCE_ORDER):
+    for s, nm in enumerate([q for q in mp.SOURCE_ORDER if q in case.tracer_names]):
         ref.set("is" + nm, s + 1)
     for nm in ("aice", "hice", "hsno"):                       # (imt,jmt,2): the tracer step reads time level 2
         ref.view(nm)[1] = o.arr(nm).reshape(jmt, imt)
@@ -403,4 +404,32 @@ def test_oracle_reproduces_reference_golden_vectors(pkg):
         o.call("ora_step")
         assert np.array_equal(o.t()[2][:, 1:-1], g[f"t_p1_step{itt}"][:, 1:-1]), itt
         oracle_rotate(o)
+    o.close()
+
+
+def test_no_isotope_configuration_bitwise(pkg):
+    """BASELINE config 2 (full MOBI tracer set, no isotopes, nt = 21): the reference built WITHOUT O_carbon_13, O_carbon_14 and
+    O_mobi_nitrogen_15 (oracle/_ref/libref_n.so) against the oracle run with the isotope tracers marked absent (index 0 in the
+    MOBI maps): whole tracer steps, all 21 tracers bit for bit"""
+    from uvic29_b200 import mobi_params as mp
+
+    ref = reflib.RefLib("n")
+    assert "-DO_carbon_13" not in ref.man["cpp_options"] and "-DO_mobi" in ref.man["cpp_options"]
+    names = mp.tracer_names_for(options=())
+    assert len(names) == 21 and ref.view("t").shape[1] == 21
+    case, o = setup_pair(pkg, ref, seed=17, names=names)
+    assert case.nsrc == 19 and (np.asarray(case["mobi_idx"])[:64] == 0).sum() == 2 * 15
+    _stress(case, o, ref, np.random.default_rng(17))
+    for itt, lf in enumerate((True, True, False, True)):
+        oracle_set_step(o, case, lf)
+        ref_set_step(ref, o, case, lf)
+        o.call("ora_step")
+        ref_step(ref)
+        to, tr = o.t()[2], ref.view("t")[2]
+        for n, nm in enumerate(case.tracer_names):
+            nd = int((to[n, 1:-1] != tr[n, 1:-1]).sum())
+            assert nd == 0, (itt, nm, nd, float(np.abs(to[n, 1:-1] - tr[n, 1:-1]).max()))
+        assert np.isfinite(tr).all()
+        oracle_rotate(o)
+        ref_rotate(ref)
     o.close()

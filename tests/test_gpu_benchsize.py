@@ -150,3 +150,31 @@ def test_inventory_conserved_to_1e14_per_step(pkg):
     print(f"worst relative inventory change per step: {worst:.2e}")
     assert worst <= 1e-14, worst
     ctx.close()
+
+
+@pytest.mark.parametrize("options", [(), ("O_carbon_13",), ("O_carbon_14", "O_mobi_nitrogen_15")])
+def test_mobi_option_subsets(pkg, options):
+    """BASELINE config 2 and the other subsets run/mk.in can select: MOBI without (some of) the isotope options.  The oracle in
+    the same subset mode is bitwise equal to the reference BUILT without the options (tests/test_cpu_refpin.py)."""
+    from uvic29_b200 import mobi_params as mp
+
+    names = mp.tracer_names_for(options=options)
+    case = pkg.synthetic.make_case(imt=42, jmt=34, km=10, nt=len(names), names=names, seed=23)
+    assert case.has_mobi and case.nsrc == len(names) - 2
+    if not options:
+        assert case.nt == 21
+    o = make_oracle(case, do_mobi=1)
+    ctx = pkg.TracerContext(case, mobi=1)
+    ctx.load_state()
+    for itt, lf in enumerate((True, True, False, True)):
+        oracle_set_step(o, case, lf)
+        o.call("ora_step")
+        ctx.step(leapfrog=lf, next_leapfrog=(True, False, True, True)[itt])
+        got, ref = ctx.download_t(+1), o.t()[2]
+        for n, nm in enumerate(case.tracer_names):
+            e = relerr(got[n, 1:-1], ref[n, 1:-1])
+            assert e <= 1e-12, (itt, nm, e)
+        oracle_rotate(o)
+        ctx.rotate()
+    ctx.close()
+    o.close()

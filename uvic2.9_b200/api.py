@@ -85,7 +85,7 @@ ABI_SYMBOLS = [
     "uvic_b200_tavg_accumulate", "uvic_b200_tavg_fetch", "uvic_b200_state", "uvic_b200_gasbc", "uvic_b200_wait_before_advection",
     "uvic_b200_clinic_setup", "uvic_b200_upload_u_level", "uvic_b200_download_u", "uvic_b200_upload_smf", "uvic_b200_clinic",
     "uvic_b200_download_zu", "uvic_b200_rotate_u",
-    "uvic_b200_lookahead_stats", "uvic_b200_invalidate_lookahead", "uvic_b200_join_streams", "uvic_b200_measure_fp64_peak",
+    "uvic_b200_set_host_window", "uvic_b200_lookahead_stats", "uvic_b200_invalidate_lookahead", "uvic_b200_join_streams", "uvic_b200_measure_fp64_peak",
     "uvic_b200_group_create", "uvic_b200_group_destroy", "uvic_b200_group_last_error", "uvic_b200_group_size", "uvic_b200_group_ctx",
     "uvic_b200_group_rows", "uvic_b200_group_upload_t", "uvic_b200_group_download_t", "uvic_b200_group_upload_adv_vel",
     "uvic_b200_group_upload_vbc", "uvic_b200_group_upload_forcing", "uvic_b200_group_step", "uvic_b200_group_rotate",
@@ -126,6 +126,7 @@ def load_library():
     L.uvic_b200_hint_next_step.argtypes = [vp, C.POINTER(StepInfo)]
     L.uvic_b200_lookahead_stats.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.uvic_b200_invalidate_lookahead.argtypes = [vp]
+    L.uvic_b200_set_host_window.argtypes = [vp, C.c_int]
     L.uvic_b200_join_streams.argtypes = [vp]
     L.uvic_b200_measure_fp64_peak.argtypes = [C.c_int] + [C.POINTER(C.c_double)] * 4
     L.uvic_b200_group_create.argtypes = [C.POINTER(Dims), C.POINTER(Grid), C.POINTER(Params), C.POINTER(Static), C.c_int, vp, C.POINTER(vp)]
@@ -528,6 +529,10 @@ class TracerContext:
         if co2ccn is not None:
             self.co2ccn = float(co2ccn)
         self.co2ccn_next = None if co2ccn_next is None else float(co2ccn_next)
+
+    def set_host_window(self, jrow_first):
+        """host velocity arrays start at global row `jrow_first` (2 for the reference's (imt,km,jsmw:jmw) COMMON arrays)"""
+        self._ck(self.L.uvic_b200_set_host_window(self.h, int(jrow_first)))
 
     def lookahead_stats(self):
         h, m = C.c_int64(), C.c_int64()

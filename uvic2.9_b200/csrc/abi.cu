@@ -50,6 +50,15 @@ static void set_levels(uvic_b200_ctx *c, bool leapfrog) {
   c->v.t_m1 = leapfrog ? c->t_slot[c->lev[0]] : c->t_slot[c->lev[1]];
 }
 
+
+// H2D copy of a host velocity array whose first row is global row ctx->host_jfirst (uvic_b200_set_host_window): the
+// reference dimensions adv_vet / adv_vnt / adv_vbt (imt,km,jsmw:jmw), 09/mom/mw.h:246-263, i.e. WITHOUT row 1
+#define H2D_VEL(dst, src, rowelems, total, strm)                                                                       \
+  do {                                                                                                                 \
+    const long long skip_ = (long long)std::max(0, ctx->host_jfirst - ctx->v.jbase) * (long long)(rowelems);          \
+    CK(cudaMemcpyAsync((dst) + skip_, (src), ((size_t)(total) - (size_t)skip_) * sizeof(double), cudaMemcpyHostToDevice, strm)); \
+  } while (0)
+
 extern "C" {
 
 static void halo_wait_now(uvic_b200_ctx *ctx);
@@ -128,7 +137,7 @@ static int create_impl(const uvic_b200_dims *d, const uvic_b200_grid *g, const u
     int jglob = v.jbase + jj;
     if (jglob == 1 || jglob == jmt)
       for (int i = 0; i < imt; i++)
-        if (st->kmt[i + (size_t)imt * jj] != 0) { delete ctx; return fail(nullptr, "uvic_b200_create: rows 1 and jmt must be land (kmt=0)"); }
+        if (st->kmt[i + (size_t)imt * jj] != 0) { return fail(ctx, "uvic_b200_create: rows 1 and jmt must be land (kmt=0)"); }
   }
 
   // ---- grid ----
@@ -162,7 +171,7 @@ static int create_impl(const uvic_b200_dims *d, const uvic_b200_grid *g, const u
   ctx->itrc_h.assign(nt, 0);
   if (par->itrc) for (int n = 0; n < nt; n++) ctx->itrc_h[n] = par->itrc[n];
   for (int n = 0; n < nt; n++)
-    if (ctx->itrc_h[n] < 0 || ctx->itrc_h[n] > v.nsrc) { delete ctx; return fail(nullptr, "uvic_b200_create: itrc out of range"); }
+    if (ctx->itrc_h[n] < 0 || ctx->itrc_h[n] > v.nsrc) { return fail(ctx, "uvic_b200_create: itrc out of range"); }
   IALLOC(itrc, nt, ctx->itrc_h.data());
   DALLOC(fisop, v.n3, st->fisop);
   DALLOC(addisop, v.n3, st->addisop);
@@ -185,10 +194,24 @@ static int create_impl(const uvic_b200_dims *d, const uvic_b200_grid *g, const u
     DALLOC(edrsum, v.n3, es.data());
   }
   // ---- state and work arrays ----
+  // MOBI option subsets (O_carbon_13 / O_carbon_14 / O_mobi_nitrogen_15 off in run/mk.in: BASELINE config 2, nt = 21): an
+  // index of 0 in the MOBI maps says "this tracer does not exist".  The kernels keep their 32-variable state vector; the
+  // absent variables are read from one scratch field behind the nt tracers of every time level (constant 1, so every
+  // isotope ratio stays finite) and their sources land in one scratch slot behind the nsrc sources that nothing reads.
+  // The equations of the present variables never read an isotope variable (09/mom/mobi.F: isotope terms only appear in
+  // the isotope equations), so the present tracers are those of the reference built without the options.
+  bool subset = false;
+  if (par->mobi && par->mobi_index)
+    for (int m = 0; m < IX_N && m < par->n_mobi_index; m++) subset = subset || par->mobi_index[m] == 0;
+  const int nt_alloc = nt + (subset ? 1 : 0);
   for (int s = 0; s < 3; s++) {
     double *p = nullptr;
-    CK(cudaMalloc((void **)&p, (size_t)v.n3 * nt * sizeof(double)));
-    CK(cudaMemset(p, 0, (size_t)v.n3 * nt * sizeof(double)));
+    CK(cudaMalloc((void **)&p, (size_t)v.n3 * nt_alloc * sizeof(double)));
+    CK(cudaMemset(p, 0, (size_t)v.n3 * nt_alloc * sizeof(double)));
+    if (subset) {
+      std::vector<double> ones((size_t)v.n3, 1.0);
+      CK(cudaMemcpy(p + (size_t)v.n3 * nt, ones.data(), (size_t)v.n3 * sizeof(double), cudaMemcpyHostToDevice));
+    }
     ctx->t_slot[s] = p;
     ctx->owned.push_back(p);
     ctx->lev[s] = s;
@@ -204,26 +227,38 @@ static int create_impl(const uvic_b200_dims *d, const uvic_b200_grid *g, const u
   DALLOC(K11, v.n3, nullptr); DALLOC(K22, v.n3, nullptr); DALLOC(K33, v.n3, nullptr);
   DALLOC(diff_cbt, v.n3, nullptr); DALLOC(tri_a, v.n3, nullptr); DALLOC(tri_e, v.n3, nullptr); DALLOC(tri_bet, v.n3, nullptr);
   DALLOC(stf, v.n2 * nt, nullptr); DALLOC(btf, v.n2 * nt, nullptr);
-  DALLOC(src, v.n3 * std::max(v.nsrc, 1), nullptr);
+  DALLOC(src, v.n3 * (std::max(v.nsrc, 1) + (subset ? 1 : 0)), nullptr);
   ctx->src_buf[0] = v.src;
   if (par->mobi) {
     if (!par->mobi_par || !par->mobi_index || par->n_mobi_par < (int)(sizeof(MobiPar) / sizeof(double)) || par->n_mobi_index < IX_N ||
         !st->sg_bathy || !st->fe_hydr || !st->fe_atmdep) {
-      delete ctx;
-      return fail(nullptr, "uvic_b200_create: O_mobi needs mobi_par, mobi_index, sg_bathy, fe_hydr and fe_atmdep");
+      return fail(ctx, "uvic_b200_create: O_mobi needs mobi_par, mobi_index, sg_bathy, fe_hydr and fe_atmdep");
     }
-    if (km > MOBI_KMAX) { delete ctx; return fail(nullptr, "uvic_b200_create: km exceeds MOBI_KMAX"); }
+    if (km > MOBI_KMAX) { return fail(ctx, "uvic_b200_create: km exceeds MOBI_KMAX"); }
     for (int m = 0; m < IX_N; m++) {
       int x = par->mobi_index[m];
       bool is_src = (m >= IX_SRC && m < IX_SRC + MOBI_NVAR) || m >= IX_ISALK;
-      if (x < 1 || x > (is_src ? v.nsrc : nt)) { delete ctx; return fail(nullptr, "uvic_b200_create: MOBI index map out of range"); }
+      if (x < 0 || x > (is_src ? v.nsrc : nt)) { return fail(ctx, "uvic_b200_create: MOBI index map out of range"); }
+      // the variables every MOBI configuration has (09/mom/mobi.h:104-142 with O_mobi alone)
+      const bool required = m == IX_TR + V_PO4 || m == IX_TR + V_PHYT || m == IX_TR + V_ZOOP || m == IX_TR + V_DETR || m == IX_TR + V_DIC ||
+                            m == IX_ITEMP || m == IX_ISALT || m == IX_IALK || m == IX_IO2;
+      if (x == 0 && required) { return fail(ctx, "uvic_b200_create: MOBI index map: a required tracer is marked absent"); }
     }
     double *mp = nullptr;
     if (dev_alloc(ctx, "mobi_par", &mp, sizeof(MobiPar) / sizeof(double), par->mobi_par)) return 1;
     v.mobi_par = (const MobiPar *)mp;
     ctx->mobi_dtnpzd = ((const MobiPar *)par->mobi_par)->dtnpzd;
     IALLOC(mobi_idx, MOBI_NIDX, nullptr);
-    CK(cudaMemcpy(const_cast<int *>(v.mobi_idx), par->mobi_index, sizeof(int) * std::min(par->n_mobi_index, MOBI_NIDX), cudaMemcpyHostToDevice));
+    {
+      // absent entries -> the scratch tracer (nt + 1) / the scratch source slot (nsrc + 1)
+      std::vector<int> mi(MOBI_NIDX, 0);
+      for (int m = 0; m < std::min(par->n_mobi_index, MOBI_NIDX); m++) mi[m] = par->mobi_index[m];
+      for (int m = 0; m < IX_N; m++) {
+        const bool is_src = (m >= IX_SRC && m < IX_SRC + MOBI_NVAR) || m >= IX_ISALK;
+        if (mi[m] == 0) mi[m] = is_src ? v.nsrc + 1 : nt + 1;
+      }
+      CK(cudaMemcpy(const_cast<int *>(v.mobi_idx), mi.data(), sizeof(int) * MOBI_NIDX, cudaMemcpyHostToDevice));
+    }
     DALLOC(sg_bathy, v.n3, st->sg_bathy);
     DALLOC(fe_hydr, v.n3, st->fe_hydr);
     DALLOC(fe_atmdep, v.n2 * 12, st->fe_atmdep);
@@ -291,8 +326,7 @@ static int create_impl(const uvic_b200_dims *d, const uvic_b200_grid *g, const u
   ctx->filt_items = nullptr; ctx->filt_mats = nullptr; ctx->filt_nitems = 0; ctx->filt_maxim = 0;
   if (par->fourfil) {
     if (par->jfrst < 1 || par->jft0 < 1 || par->jft0 > jmt || par->jft1 < par->jfrst || par->jft2 <= par->jft1 || par->jft2 > jmt) {
-      delete ctx;
-      return fail(nullptr, "uvic_b200_create: O_fourfil needs 1 <= jfrst <= jft1 < jft2 <= jmt and a valid jft0");
+      return fail(ctx, "uvic_b200_create: O_fourfil needs 1 <= jfrst <= jft1 < jft2 <= jmt and a valid jft0");
     }
     if (filter_setup(ctx, st->kmt, g->cst, g->cstr)) return fail(ctx, "uvic_b200_create: filter set-up failed");
   }
@@ -370,9 +404,9 @@ int uvic_b200_download_tracer(uvic_b200_ctx *ctx, int level, int n, double *h) {
 int uvic_b200_upload_adv_vel(uvic_b200_ctx *ctx, const double *vet, const double *vnt, const double *vbt) {
   if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   DevView &v = ctx->v;
-  if (vet) CK(cudaMemcpyAsync(v.adv_vet, vet, (size_t)v.n3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  if (vnt) CK(cudaMemcpyAsync(v.adv_vnt, vnt, (size_t)v.n3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  if (vbt) CK(cudaMemcpyAsync(v.adv_vbt, vbt, (size_t)v.n3z * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (vet) H2D_VEL(v.adv_vet, vet, (long long)v.imt * v.km, v.n3, ctx->stream);
+  if (vnt) H2D_VEL(v.adv_vnt, vnt, (long long)v.imt * v.km, v.n3, ctx->stream);
+  if (vbt) H2D_VEL(v.adv_vbt, vbt, (long long)v.imt * (v.km + 1), v.n3z, ctx->stream);
   return 0;
 }
 int uvic_b200_upload_u(uvic_b200_ctx *ctx, const double *u) {
@@ -753,8 +787,8 @@ static int lookahead_mobi(uvic_b200_ctx *ctx) {
   if (!ctx->par.mobi || ctx->prof_on) return 0;
   if (!ctx->src_buf[1]) {
     double *p = nullptr;
-    CK(cudaMalloc((void **)&p, (size_t)ctx->v.n3 * std::max(ctx->v.nsrc, 1) * sizeof(double)));
-    CK(cudaMemsetAsync(p, 0, (size_t)ctx->v.n3 * std::max(ctx->v.nsrc, 1) * sizeof(double), ctx->stream2));
+    CK(cudaMalloc((void **)&p, (size_t)ctx->v.n3 * (std::max(ctx->v.nsrc, 1) + 1) * sizeof(double)));   // + the scratch slot of a MOBI subset
+    CK(cudaMemsetAsync(p, 0, (size_t)ctx->v.n3 * (std::max(ctx->v.nsrc, 1) + 1) * sizeof(double), ctx->stream2));
     ctx->src_buf[1] = p;
     ctx->owned.push_back(p);
   }
@@ -787,6 +821,12 @@ static void set_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
   set_levels(ctx, si->leapfrog != 0);
 }
 
+int uvic_b200_set_host_window(uvic_b200_ctx *ctx, int jrow_first) {
+  if (!ctx) return 1;
+  if (jrow_first < 1 || jrow_first > ctx->v.jbase + 2) return fail(ctx, "set_host_window: the host arrays must start at global row 1 or jsmw = 2");
+  ctx->host_jfirst = jrow_first;
+  return 0;
+}
 int uvic_b200_lookahead_stats(uvic_b200_ctx *ctx, int64_t *hits, int64_t *misses) {
   if (!ctx) return 1;
   if (hits) *hits = ctx->la_hits;
@@ -899,9 +939,9 @@ int uvic_b200_tracer_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si, cons
   if (stf) CK(cudaMemcpyAsync(v.stf, stf, (size_t)v.n2 * v.nt * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
   if (btf) CK(cudaMemcpyAsync(v.btf, btf, (size_t)v.n2 * v.nt * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
   CK(cudaEventRecord(ctx->h2d_vbc_event, ctx->copy_in));
-  if (adv_vet) CK(cudaMemcpyAsync(v.adv_vet, adv_vet, (size_t)v.n3 * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
-  if (adv_vnt) CK(cudaMemcpyAsync(v.adv_vnt, adv_vnt, (size_t)v.n3 * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
-  if (adv_vbt) CK(cudaMemcpyAsync(v.adv_vbt, adv_vbt, (size_t)v.n3z * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
+  if (adv_vet) H2D_VEL(v.adv_vet, adv_vet, (long long)v.imt * v.km, v.n3, ctx->copy_in);
+  if (adv_vnt) H2D_VEL(v.adv_vnt, adv_vnt, (long long)v.imt * v.km, v.n3, ctx->copy_in);
+  if (adv_vbt) H2D_VEL(v.adv_vbt, adv_vbt, (long long)v.imt * (v.km + 1), v.n3z, ctx->copy_in);
   CK(cudaEventRecord(ctx->h2d_event, ctx->copy_in));
   if (trace) cudaEventRecord(tev[1], ctx->copy_in);
   set_step(ctx, si);
@@ -948,9 +988,9 @@ int uvic_b200_tracer_step_coupled(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *
   if (sbc_in) CK(cudaMemcpyAsync(v.sbc, sbc_in, (size_t)v.n2 * v.numsbc * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
   if (bhf) CK(cudaMemcpyAsync(v.bhf, bhf, (size_t)v.n2 * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
   CK(cudaEventRecord(ctx->h2d_vbc_event, ctx->copy_in));
-  if (adv_vet) CK(cudaMemcpyAsync(v.adv_vet, adv_vet, (size_t)v.n3 * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
-  if (adv_vnt) CK(cudaMemcpyAsync(v.adv_vnt, adv_vnt, (size_t)v.n3 * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
-  if (adv_vbt) CK(cudaMemcpyAsync(v.adv_vbt, adv_vbt, (size_t)v.n3z * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
+  if (adv_vet) H2D_VEL(v.adv_vet, adv_vet, (long long)v.imt * v.km, v.n3, ctx->copy_in);
+  if (adv_vnt) H2D_VEL(v.adv_vnt, adv_vnt, (long long)v.imt * v.km, v.n3, ctx->copy_in);
+  if (adv_vbt) H2D_VEL(v.adv_vbt, adv_vbt, (long long)v.imt * (v.km + 1), v.n3z, ctx->copy_in);
   CK(cudaEventRecord(ctx->h2d_event, ctx->copy_in));
   set_step(ctx, si);
   begin_mobi(ctx, si);

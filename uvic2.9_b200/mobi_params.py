@@ -134,21 +134,44 @@ MI_TR, MI_SRC, MI_ITEMP, MI_ISALT, MI_IALK, MI_IO2, MI_IC14, MI_ISALK, MI_ISO2, 
 N_IDX = 128
 
 
+# the option groups of run/mk.in that add MOBI state variables (09/mom/mobi.h:104-142, 09/common/size.h:31-144)
+ISOTOPE_GROUPS = {
+    "O_carbon_13": ["dic13", "phytc13", "zoopc13", "detrc13", "doc13", "diazc13", "diatc13", "caco3c13"],
+    "O_carbon_14": ["c14"],
+    "O_mobi_nitrogen_15": ["din15", "don15", "phytn15", "zoopn15", "detrn15", "diazn15", "diatn15"],
+}
+OPTIONAL = {nm for g in ISOTOPE_GROUPS.values() for nm in g}
+
+
+def tracer_names_for(options=("O_carbon_13", "O_carbon_14", "O_mobi_nitrogen_15")):
+    """tracer order of tracer_init with the given isotope options on: all three -> the 37 tracers of the
+    shipped run/mk.in (BASELINE config 3); none -> the 21 tracers of "full MOBI, no isotopes" (config 2)"""
+    from .synthetic import MOBI_TRACERS_37
+    off = {nm for opt, g in ISOTOPE_GROUPS.items() if opt not in options for nm in g}
+    return [nm for nm in MOBI_TRACERS_37 if nm not in off]
+
+
 def mobi_index_maps(tracer_names):
     """(itrc(nt), mobi_idx(128), nsrc): tracer -> source slot, and the MOBI gather/scatter maps
-    (09/mom/tracer.F:393-447, 09/mom/mobi.F:1149-1204)."""
+    (09/mom/tracer.F:393-447, 09/mom/mobi.F:1149-1204).  Isotope tracers that are not in `tracer_names` (options
+    O_carbon_13 / O_carbon_14 / O_mobi_nitrogen_15 off) get index 0 = absent; an option group is all or nothing."""
     pos = {nm: n + 1 for n, nm in enumerate(tracer_names)}
-    missing = [s for s in MOBI_STATE + ["temp", "salt", "alk", "o2", "c14"] if s not in pos]
+    missing = [s for s in MOBI_STATE + ["temp", "salt", "alk", "o2", "c14"] if s not in pos and s not in OPTIONAL]
     if missing:
-        raise ValueError(f"MOBI with the shipped options needs tracers {missing}")
-    slot = {nm: s + 1 for s, nm in enumerate(SOURCE_ORDER)}
+        raise ValueError(f"MOBI needs tracers {missing}")
+    for opt, g in ISOTOPE_GROUPS.items():
+        have = [nm in pos for nm in g]
+        if any(have) and not all(have):
+            raise ValueError(f"{opt}: its tracers {g} must be all present or all absent")
+    order = [nm for nm in SOURCE_ORDER if nm in pos]
+    slot = {nm: s + 1 for s, nm in enumerate(order)}
     itrc = np.zeros(len(tracer_names), dtype=np.int32)
     for nm, s in slot.items():
         itrc[pos[nm] - 1] = s
     idx = np.zeros(N_IDX, dtype=np.int32)
     for m, nm in enumerate(MOBI_STATE):
-        idx[MI_TR + m] = pos[nm]
-        idx[MI_SRC + m] = slot[nm]
-    idx[MI_ITEMP], idx[MI_ISALT], idx[MI_IALK], idx[MI_IO2], idx[MI_IC14] = pos["temp"], pos["salt"], pos["alk"], pos["o2"], pos["c14"]
-    idx[MI_ISALK], idx[MI_ISO2], idx[MI_ISC14] = slot["alk"], slot["o2"], slot["c14"]
-    return itrc, idx, len(SOURCE_ORDER)
+        idx[MI_TR + m] = pos.get(nm, 0)
+        idx[MI_SRC + m] = slot.get(nm, 0)
+    idx[MI_ITEMP], idx[MI_ISALT], idx[MI_IALK], idx[MI_IO2], idx[MI_IC14] = pos["temp"], pos["salt"], pos["alk"], pos["o2"], pos.get("c14", 0)
+    idx[MI_ISALK], idx[MI_ISO2], idx[MI_ISC14] = slot["alk"], slot["o2"], slot.get("c14", 0)
+    return itrc, idx, len(order)

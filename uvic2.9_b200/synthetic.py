@@ -407,7 +407,7 @@ def make_case(imt=102, jmt=102, km=19, nt=2, seed=SEED, names=None, dtts=None, n
     arrays["itrc"] = itrc
     case = Case(imt=imt, jmt=jmt, km=km, nt=nt, nsrc=nsrc, scalars=scalars, arrays=arrays, tracer_names=names)
     from . import mobi_params as mp
-    if all(s in names for s in mp.MOBI_STATE + ["alk", "o2", "c14"]):
+    if all(s in names for s in mp.MOBI_STATE + ["alk", "o2", "c14"] if s not in mp.OPTIONAL):
         # full MOBI tracer set: source slots in tracer_init's order, gather/scatter maps, parameters
         itrc, idx, nsrc = mp.mobi_index_maps(names)
         arrays["itrc"], arrays["mobi_idx"] = itrc, idx
