@@ -39,6 +39,7 @@ def test_step_parity_at_benchmark_depths_40_tracers(pkg, imt, jmt, km):
             e = relerr(got[n, 1:-1], ref[n, 1:-1])
             worst, worst_pw = max(worst, e), max(worst_pw, pointwise_relerr(got[n, 1:-1], ref[n, 1:-1]))
             assert e <= 1e-12, (itt, nm, e)
+        ctx.upload_t(+1, ref)      # per-step gate (north_star): the next step starts from the oracle's state on both sides
         oracle_rotate(o)
         ctx.rotate()
     print(f"{imt}x{jmt}x{km} nt=40: worst normalised {worst:.2e}, worst point-wise relative (|ref| > 1e-3 max) {worst_pw:.2e}")
@@ -174,6 +175,7 @@ def test_mobi_option_subsets(pkg, options):
         for n, nm in enumerate(case.tracer_names):
             e = relerr(got[n, 1:-1], ref[n, 1:-1])
             assert e <= 1e-12, (itt, nm, e)
+        ctx.upload_t(+1, ref)
         oracle_rotate(o)
         ctx.rotate()
     ctx.close()

@@ -29,6 +29,7 @@ def test_cuda_step_matches_reference_golden_vectors(pkg):
         assert np.array_equal(got[:, 1:-1] == 0, ref[:, 1:-1] == 0), "land / below-bottom cells"      # mask rule, bit exact
         for n, nm in enumerate(case.tracer_names):
             assert relerr(got[n, 1:-1], ref[n, 1:-1]) <= 1e-12, (itt, nm, relerr(got[n, 1:-1], ref[n, 1:-1]))
+        ctx.upload_t(+1, np.ascontiguousarray(ref))     # per-step gate: continue from the reference's state
         ctx.rotate()
     ctx.close()
 
@@ -57,6 +58,7 @@ def test_cuda_step_matches_translated_reference_side_by_side(pkg):
             e = relerr(got[n, 1:-1], want[n, 1:-1])
             worst = max(worst, e)
             assert e <= 1e-12, (itt, nm, e)
+        ctx.upload_t(+1, np.ascontiguousarray(want))    # per-step gate: continue from the reference's state
         T.ref_rotate(ref)
         ctx.rotate()
     print(f"CUDA vs translated reference, 4 steps, 37 tracers: worst normalised difference {worst:.2e}")

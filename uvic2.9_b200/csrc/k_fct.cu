@@ -33,6 +33,9 @@
 #include "fct_common.h"
 #include <algorithm>
 #include <stdlib.h>
+#include <string.h>
+#include <array>
+#include <cuda.h>   // CUtensorMap (the encode function itself is fetched through cudaGetDriverEntryPoint: no -lcuda)
 
 #define FM_TI 30      // interior cells in i per CTA
 #define FM_W 34       // staged row width: i0-2 .. i0+31
@@ -51,14 +54,59 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// ---- TMA staging (interior i tiles of grids with an even imt): one elected thread issues five tensor copies per row
+// (t(tau-1), t(tau), the three face velocities: boxes of 34 x nrows doubles, out-of-range levels zero filled) that complete
+// on the mbarrier of the ring slot; the 512 threads no longer compute 6-8 global addresses each per row ----
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned mb, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mb, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mb, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "FM_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra FM_DONE;\n"
+      "bra FM_WAIT;\n"
+      "FM_DONE:\n"
+      "}\n" ::"r"(mb), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, unsigned mb) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+               "l"(map), "r"(mb), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, int c3, unsigned mb) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+               "l"(map), "r"(mb), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
+struct FmMaps {
+  CUtensorMap tm1, t0, ue, vn, wb;   // t(tau-1), t(tau) as (imt,km,jl,nt); ue, vn (imt,km,jl); wb (imt,km+1,jl)
+};
+
+// staged plane: MAXW + 4 rows of FM_W doubles, padded to a multiple of 128 bytes (TMA destination alignment); a
+// compile-time constant, so that every shared-memory access of the march is base register + immediate
+template <int MAXW>
+struct FmCfg {
+  static constexpr int PLANE = (((MAXW + 4) * 34 + 15) / 16) * 16;
+};
+
 struct FmGeom {
   int nit, nkt, TK, nchunk, chunk;   // i tiles, k tiles, levels per k tile, row chunks, rows per chunk
   int nrows;                         // staged levels per row: TK + 4
+  int tma;                           // 1: interior i tiles stage their rows with TMA
 };
 
 template <int MAXW>
-__global__ void __launch_bounds__(32 * MAXW, 1) k_fct_march(const DevView v, int nbase, int ng, FmGeom gm) {
-  extern __shared__ __align__(16) unsigned char fm_raw[];
+__global__ void __launch_bounds__(32 * MAXW, 1) k_fct_march(const DevView v, int nbase, int ng, FmGeom gm, const __grid_constant__ FmMaps maps) {
+  extern __shared__ __align__(128) unsigned char fm_raw[];
+  constexpr int plane = FmCfg<MAXW>::PLANE;         // plane row p <-> level ka_lo - 1 + p
   // skipping the face-flux phase of land warps and the write of land cells pays where registers are not the limit
   // (128-register variants); the 96-register variant (columns of <= 20 levels in one tile) is faster without (measured)
   constexpr bool LAND_SKIP = (MAXW <= 16);
@@ -78,6 +126,7 @@ __global__ void __launch_bounds__(32 * MAXW, 1) k_fct_march(const DevView v, int
   const int rA0 = max(2, ja - 1);
   if (w >= nA) {
     // a warp without a level in this k tile only keeps the barrier count
+    if (gm.tma && it > 0 && it < gm.nit - 1) __syncthreads();
     __syncthreads();
     __syncthreads();
     for (int r = rA0; r <= jb + 1; r++) __syncthreads();
@@ -98,14 +147,22 @@ __global__ void __launch_bounds__(32 * MAXW, 1) k_fct_march(const DevView v, int
   const bool halo_k = LAND_SKIP && (k < k0 || k > k1);   // halo level of the k tile: only its R+-z are needed (by the level next to it)
 
   // ---- shared memory ----
-  const int plane = gm.nrows * FM_W;                // plane row p <-> level ka_lo - 1 + p
   double *sT = reinterpret_cast<double *>(fm_raw);  // [FM_NSLOT][nrows][FM_W]
   double *sU = sT + FM_NSLOT * plane;
   double *sUe = sU + FM_NSLOT * plane;              // east-face velocity
   double *sVn = sUe + FM_NSLOT * plane;             // north-face velocity
   double *sWb = sVn + FM_NSLOT * plane;             // bottom-face velocity, plane row p <-> face ka_lo - 1 + p
-  double *sR = sWb + FM_NSLOT * plane;              // [2][4][FM_MAXW][32]: R+x, R-x, R+z, R-z, double buffered over rows
-  int *sK = reinterpret_cast<int *>(sR + 2 * 4 * FM_MAXW * 32);   // [FM_NSLOT][FM_W] kmt
+  double *sR = sWb + FM_NSLOT * plane;              // [2][4][MAXW][32]: R+x, R-x, R+z, R-z, double buffered over rows
+  unsigned long long *sMb = reinterpret_cast<unsigned long long *>(sR + 2 * 4 * MAXW * 32);   // [FM_NSLOT] mbarriers (TMA staging)
+  int *sK = reinterpret_cast<int *>(sMb + FM_NSLOT);                                         // [FM_NSLOT][FM_W] kmt
+  // TMA staging for the i tiles whose 34-wide window lies inside 1..imt (no cyclic wrap); the two edge tiles keep cp.async
+  const bool tma = gm.tma && it > 0 && it < gm.nit - 1;
+  const unsigned mb0 = smem_u32(sMb);
+  const unsigned tx_bytes = 5u * FM_W * (unsigned)gm.nrows * 8u;
+  if (tma && threadIdx.x == 0) {
+    for (int q = 0; q < FM_NSLOT; q++) mbar_init(mb0 + 8 * q, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
 
   const double *__restrict__ T = v.t_m1 + (long long)(nbase + g) * v.n3;
   const double *__restrict__ U = v.t_0 + (long long)(nbase + g) * v.n3;
@@ -127,9 +184,30 @@ __global__ void __launch_bounds__(32 * MAXW, 1) k_fct_march(const DevView v, int
   const int g_k = iw - 1, g_kh = ie2 - 1;
   const double *__restrict__ gUe = v.ue, *__restrict__ gVn = v.vn, *__restrict__ gWb = v.wb;
   const int *__restrict__ gK = v.kmt;
+  const int first_row = max(2, ja - 1) - 1;   // the first staged row: use q of a ring slot holds row first_row + (slot offset) + 4 q
   auto stage = [&](int rr) {
     const int so = (rr & (FM_NSLOT - 1)) * plane;
     const int jloc = min(max(rr, v.jbase), jtop) - v.jbase;
+    if (tma) {
+      if (threadIdx.x == 0) {
+        const unsigned mb = mb0 + 8 * (rr & (FM_NSLOT - 1));
+        mbar_expect_tx(mb, tx_bytes);
+        // element e of a staged row <-> i = i0 - 2 + e (0-based i0 - 3 + e); plane row p <-> level ka_lo - 1 + p
+        // (0-based ka_lo - 2 + p; -1 and km are out of range: zero filled), face ka_lo - 1 + p for the bottom-face velocity
+        tma_load_4d(&sT[so], &maps.tm1, i0 - 3, ka_lo - 2, jloc, nbase + g, mb);
+        tma_load_4d(&sU[so], &maps.t0, i0 - 3, ka_lo - 2, jloc, nbase + g, mb);
+        tma_load_3d(&sUe[so], &maps.ue, i0 - 3, ka_lo - 2, jloc, mb);
+        tma_load_3d(&sVn[so], &maps.vn, i0 - 3, ka_lo - 2, jloc, mb);
+        tma_load_3d(&sWb[so], &maps.wb, i0 - 3, ka_lo - 1, jloc, mb);
+      }
+      if (w == 0) {
+        const int sko = (rr & (FM_NSLOT - 1)) * FM_W;
+        cp_async4(&sK[sko + lane + 1], gK + (jloc * imt + g_k));
+        if (lane < 2) cp_async4(&sK[sko + e2], gK + (jloc * imt + g_kh));
+      }
+      cp_async_commit();
+      return;
+    }
     const int o3 = jloc * sj, o3z = jloc * sjz;
     cp_async8(&sT[so + s_own], T + (o3 + g_own));
     cp_async8(&sU[so + s_own], U + (o3 + g_own));
@@ -168,11 +246,20 @@ __global__ void __launch_bounds__(32 * MAXW, 1) k_fct_march(const DevView v, int
   const bool has_up = (w >= 1);
 
   // ---- prologue: rows rA0-1 .. rA0+2 ----
+  // row rr landed?  (slot rr & 3, its use number (rr - first_row) >> 2 gives the mbarrier phase)
+  auto wait_row = [&](int rr) {
+    if (tma) mbar_wait(mb0 + 8 * (rr & (FM_NSLOT - 1)), ((rr - first_row) >> 2) & 1);
+  };
+  if (tma) __syncthreads();   // the mbarriers are initialised before anybody waits on them
   stage(rA0 - 1);
   stage(rA0);
   stage(rA0 + 1);
   stage(rA0 + 2);
   cp_async_wait<0>();
+  wait_row(rA0 - 1);
+  wait_row(rA0);
+  wait_row(rA0 + 1);
+  wait_row(rA0 + 2);
   __syncthreads();
   double Tc, Uc, Um, lo_n_p, a_n_p;
   int kmc_p;
@@ -207,18 +294,18 @@ __global__ void __launch_bounds__(32 * MAXW, 1) k_fct_march(const DevView v, int
     double tx_p = 0.0, tz_p = 0.0;
     const double m_p = (kmc_p >= k) ? 1.0 : 0.0;   // tmask(i,k,r-1)
     if (!halo_k && (!LAND_SKIP || __any_sync(0xffffffffu, kmc_p >= k))) {   // a warp of land cells, or a halo level, has no face flux anybody reads
-      const double *R = sR + ((r - 1) & 1) * (4 * FM_MAXW * 32);
+      const double *R = sR + ((r - 1) & 1) * (4 * MAXW * 32);
       // east / west faces: Cpos(f) = min(Rpl(f+1),Rmn(f)), Cneg(f) = min(Rpl(f),Rmn(f+1)) (:698-701); no mask (:987)
       // the west face of a cell is the east face of its western neighbour: one lane over (lane 0 is a halo cell)
       const int le = (lane < 31) ? ro + 1 : ro;
-      const double Fe = delimit(dmin(R[le], c_rxm), dmin(c_rxp, R[FM_MAXW * 32 + le]), c_ae) + c_loe;
+      const double Fe = delimit(dmin(R[le], c_rxm), dmin(c_rxp, R[MAXW * 32 + le]), c_ae) + c_loe;
       const double Fw = __shfl_up_sync(0xffffffffu, Fe, 1);
       // bottom / top faces: Cpos(h) = min(Rpl(h),Rmn(h+1)), Cneg(h) = min(Rpl(h+1),Rmn(h)) (:966-969);
       // adv_fb(0), adv_fb(km) are overwritten in tracer (09/mom/tracer.F:1063-1065): level 1 / km carry those in c_lou / c_lod
       const int ld = has_dn ? ro + 32 : ro, lu = has_up ? ro - 32 : ro;
       const double mu_p = (kmc_p >= k - 1) ? 1.0 : 0.0;
-      double Fb = (delimit(dmin(c_rzp, R[3 * FM_MAXW * 32 + ld]), dmin(R[2 * FM_MAXW * 32 + ld], c_rzm), c_ad) + c_lod) * m_p;
-      double Fu = (delimit(dmin(R[2 * FM_MAXW * 32 + lu], c_rzm), dmin(c_rzp, R[3 * FM_MAXW * 32 + lu]), c_au) + c_lou) * mu_p;
+      double Fb = (delimit(dmin(c_rzp, R[3 * MAXW * 32 + ld]), dmin(R[2 * MAXW * 32 + ld], c_rzm), c_ad) + c_lod) * m_p;
+      double Fu = (delimit(dmin(R[2 * MAXW * 32 + lu], c_rzm), dmin(c_rzp, R[3 * MAXW * 32 + lu]), c_au) + c_lou) * mu_p;
       if (k == km) Fb = c_lod;
       if (k == 1) Fu = c_lou;
       tx_p = (Fe - Fw) * c_dcfx;
@@ -288,11 +375,11 @@ __global__ void __launch_bounds__(32 * MAXW, 1) k_fct_march(const DevView v, int
         const double fxb = (k < km && kmc >= k + 1) ? 0.5 * (Uc + Ud) : tlo;
         ratio(c2dtts, dcfz, (k == km) ? 0.0 : a_d, (k == 1) ? wb_u * 2.0 * Tc : a_u, fxa, fxb, tlo, m, rzp, rzm);
       }
-      double *R = sR + (r & 1) * (4 * FM_MAXW * 32);
+      double *R = sR + (r & 1) * (4 * MAXW * 32);
       R[ro] = rxp;
-      R[FM_MAXW * 32 + ro] = rxm;
-      R[2 * FM_MAXW * 32 + ro] = rzp;
-      R[3 * FM_MAXW * 32 + ro] = rzm;
+      R[MAXW * 32 + ro] = rxm;
+      R[2 * MAXW * 32 + ro] = rzp;
+      R[3 * MAXW * 32 + ro] = rzm;
       c_ae = a_e; c_loe = lo_e; c_ad = a_d; c_au = a_u;
       c_lod = (k == km) ? wb_d * Uc : lo_d;           // adv_fb(i,km,j) = adv_vbt(i,km,j)*t(i,km,j,tau)
       c_lou = (k == 1) ? wb_u * (Uc + Uc) : lo_u;     // adv_fb(i,0,j) = adv_vbt(i,0,j)*2*t(i,1,j,tau)
@@ -310,9 +397,11 @@ __global__ void __launch_bounds__(32 * MAXW, 1) k_fct_march(const DevView v, int
     lo_n_p = lo_n; a_n_p = a_n; ryp_p = ryp; rym_p = rym; kmc_p = kmc;
     Um = Uc; Uc = Un; Tc = Tn;
     cp_async_wait<1>();   // everything but the copies issued in this iteration has landed: rows <= r+2
+    wait_row(r + 2);
     __syncthreads();      // ... and, like the ratios of row r, is visible to every thread
   }
   cp_async_wait<0>();
+  wait_row(jb + 4);       // the last row staged ahead: no copy may be in flight when the CTA retires
 }
 
 // launch geometry: a CTA has at most maxw warps (one per level whose ratios it needs); latitude chunks sized to give
@@ -333,17 +422,69 @@ static FmGeom fct_geometry(const DevView &v, int ng, int maxw) {
   return g;
 }
 
+// ---- tensor maps (host): built once per device pointer and box height, cached in the context ----
+typedef CUresult (*FmEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                               const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                               CUtensorMapFloatOOBfill);
+static FmEncodeFn fm_encode_fn() {
+  static FmEncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (FmEncodeFn)p;
+  }
+  return fn;
+}
+// (imt, nlev, jl[, nt]) doubles, box 34 x nrows x 1 [x 1], no swizzle, zero fill outside
+static bool fm_map(uvic_b200_ctx *c, const double *ptr, int imt, int nlev, int jl, int nt4, int nrows, CUtensorMap *out) {
+  auto key = std::make_pair((const void *)ptr, nrows * 8 + (nt4 > 0 ? 1 : 0));
+  auto it = c->tma_maps.find(key);
+  if (it != c->tma_maps.end()) {
+    memcpy(out, it->second.data(), sizeof(CUtensorMap));
+    return true;
+  }
+  FmEncodeFn enc = fm_encode_fn();
+  if (!enc) return false;
+  const int rank = nt4 > 0 ? 4 : 3;
+  cuuint64_t dims[4] = {(cuuint64_t)imt, (cuuint64_t)nlev, (cuuint64_t)jl, (cuuint64_t)std::max(nt4, 1)};
+  cuuint64_t strides[3] = {(cuuint64_t)imt * 8, (cuuint64_t)imt * nlev * 8, (cuuint64_t)imt * nlev * jl * 8};
+  cuuint32_t box[4] = {FM_W, (cuuint32_t)nrows, 1, 1}, es[4] = {1, 1, 1, 1};
+  CUtensorMap m;
+  if (enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, rank, (void *)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+          CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  std::array<unsigned char, 128> blob;
+  memcpy(blob.data(), &m, sizeof(CUtensorMap));
+  c->tma_maps[key] = blob;
+  *out = m;
+  return true;
+}
+
 template <int MAXW>
 static void fct_launch_t(uvic_b200_ctx *c, int nbase, int ng) {
   DevView &v = c->v;
-  const FmGeom g = fct_geometry(v, ng, MAXW);
-  const size_t plane = (size_t)g.nrows * FM_W;
-  const size_t shm = (5 * FM_NSLOT * plane + 8 * FM_MAXW * 32) * sizeof(double) + FM_NSLOT * FM_W * sizeof(int);
+  FmGeom g = fct_geometry(v, ng, MAXW);
+  constexpr size_t plane = FmCfg<MAXW>::PLANE;
+  const size_t shm = (5 * FM_NSLOT * plane + 8 * MAXW * 32) * sizeof(double) + FM_NSLOT * sizeof(unsigned long long) + FM_NSLOT * FM_W * sizeof(int);
   ensure_dyn_smem(c, (const void *)k_fct_march<MAXW>, shm);
+  // TMA staging needs 16-byte multiples for the row strides (imt even) and at least one interior i tile
+  static const bool tma_env = !(getenv("UVIC_B200_FCT_TMA") && atoi(getenv("UVIC_B200_FCT_TMA")) == 0);
+  FmMaps maps;
+  memset(&maps, 0, sizeof maps);
+  g.tma = 0;
+  if (tma_env && (v.imt % 2) == 0 && g.nit >= 3 && g.nrows <= 256) {
+    const bool ok = fm_map(c, v.t_m1, v.imt, v.km, v.jl, v.nt, g.nrows, &maps.tm1) && fm_map(c, v.t_0, v.imt, v.km, v.jl, v.nt, g.nrows, &maps.t0) &&
+                    fm_map(c, v.ue, v.imt, v.km, v.jl, 0, g.nrows, &maps.ue) && fm_map(c, v.vn, v.imt, v.km, v.jl, 0, g.nrows, &maps.vn) &&
+                    fm_map(c, v.wb, v.imt, v.km + 1, v.jl, 0, g.nrows, &maps.wb);
+    g.tma = ok ? 1 : 0;
+  }
   const int nwarp = (g.nkt == 1) ? v.km : std::min(MAXW, g.TK + (g.nkt == 2 ? 1 : 2));   // most levels any k tile needs ratios for
   const long long nblk = (long long)ng * g.nit * g.nkt * g.nchunk;
   ProfScope ps_(c, "k_fct_march");
-  k_fct_march<MAXW><<<(unsigned)nblk, 32 * nwarp, shm, c->stream>>>(v, nbase, ng, g);
+  k_fct_march<MAXW><<<(unsigned)nblk, 32 * nwarp, shm, c->stream>>>(v, nbase, ng, g, maps);
 }
 
 void launch_fct_march(uvic_b200_ctx *c, int nbase, int ng) {
