@@ -38,7 +38,9 @@
 #include <cuda.h>   // CUtensorMap (the encode function itself is fetched through cudaGetDriverEntryPoint: no -lcuda)
 
 #define FM_TI 30      // interior cells in i per CTA
-#define FM_W 34       // staged row width: i0-2 .. i0+31
+#define FM_W 36       // staged row width: element E <-> i = i0 - 3 + E; E = 1..34 (i0-2 .. i0+31) are used, E = 0 and 35 only make
+                      // the row start 16-byte aligned in global memory (i0 - 4 is even, 0-based) and its size a multiple of 16: TMA
+#define FM_E 2        // element of lane 0 is FM_E - 1: a lane's own element is lane + FM_E
 #define FM_MAXW 21    // most warps per CTA (shared-memory layout of the ratio planes)
 #define FM_NSLOT 4    // rows r-1, r, r+1 in use, r+2 in flight
 
@@ -94,7 +96,7 @@ struct FmMaps {
 // compile-time constant, so that every shared-memory access of the march is base register + immediate
 template <int MAXW>
 struct FmCfg {
-  static constexpr int PLANE = (((MAXW + 4) * 34 + 15) / 16) * 16;
+  static constexpr int PLANE = (((MAXW + 4) * FM_W + 15) / 16) * 16;
 };
 
 struct FmGeom {
@@ -170,17 +172,17 @@ __global__ void __launch_bounds__(32 * MAXW, 1) k_fct_march(const DevView v, int
   const int sj = imt * km, sjz = imt * (km + 1);
 
   // ---- staging: per-thread element offsets, fixed for the whole march ----
-  // element e of a staged row <-> i = i0 - 2 + e; this thread copies e = lane + 1, lanes 0 / 1 also e = 0 / 33;
+  // element E of a staged row <-> i = i0 - 3 + E; this thread copies E = lane + 2, lanes 0 / 1 also E = 1 / 34;
   // the first / last warp also copies the level above / below the tile's ratio levels
-  const int e2 = (lane == 0) ? 0 : FM_W - 1;
-  const int ie2 = wrap_i(i0 - 2 + e2);
+  const int e2 = (lane == 0) ? 1 : FM_W - 2;
+  const int ie2 = wrap_i(i0 - 3 + e2);
   const int g_own = (iw - 1) + imt * (k - 1), gz_own = (iw - 1) + imt * k;
   const int g_h = (ie2 - 1) + imt * (k - 1);
-  const int s_own = (w + 1) * FM_W + lane + 1, s_h = (w + 1) * FM_W + e2;
+  const int s_own = (w + 1) * FM_W + lane + FM_E, s_h = (w + 1) * FM_W + e2;
   const int kx = (w == 0) ? ka_lo - 1 : ((w == nA - 1) ? ka_hi + 1 : -1);
   const bool x_w = kx >= 0 && kx <= km, x_t = kx >= 1 && kx <= km;
   const int g_x = (iw - 1) + imt * (kx - 1), gz_x = (iw - 1) + imt * kx;
-  const int s_x = ((w == 0) ? 0 : nA + 1) * FM_W + lane + 1;
+  const int s_x = ((w == 0) ? 0 : nA + 1) * FM_W + lane + FM_E;
   const int g_k = iw - 1, g_kh = ie2 - 1;
   const double *__restrict__ gUe = v.ue, *__restrict__ gVn = v.vn, *__restrict__ gWb = v.wb;
   const int *__restrict__ gK = v.kmt;
@@ -192,17 +194,18 @@ __global__ void __launch_bounds__(32 * MAXW, 1) k_fct_march(const DevView v, int
       if (threadIdx.x == 0) {
         const unsigned mb = mb0 + 8 * (rr & (FM_NSLOT - 1));
         mbar_expect_tx(mb, tx_bytes);
-        // element e of a staged row <-> i = i0 - 2 + e (0-based i0 - 3 + e); plane row p <-> level ka_lo - 1 + p
+        // element E of a staged row <-> i = i0 - 3 + E (0-based i0 - 4 + E: an even start, 16-byte aligned -- a box whose
+        // first byte is not 16-byte aligned raises `illegal instruction`); plane row p <-> level ka_lo - 1 + p
         // (0-based ka_lo - 2 + p; -1 and km are out of range: zero filled), face ka_lo - 1 + p for the bottom-face velocity
-        tma_load_4d(&sT[so], &maps.tm1, i0 - 3, ka_lo - 2, jloc, nbase + g, mb);
-        tma_load_4d(&sU[so], &maps.t0, i0 - 3, ka_lo - 2, jloc, nbase + g, mb);
-        tma_load_3d(&sUe[so], &maps.ue, i0 - 3, ka_lo - 2, jloc, mb);
-        tma_load_3d(&sVn[so], &maps.vn, i0 - 3, ka_lo - 2, jloc, mb);
-        tma_load_3d(&sWb[so], &maps.wb, i0 - 3, ka_lo - 1, jloc, mb);
+        tma_load_4d(&sT[so], &maps.tm1, i0 - 4, ka_lo - 2, jloc, nbase + g, mb);
+        tma_load_4d(&sU[so], &maps.t0, i0 - 4, ka_lo - 2, jloc, nbase + g, mb);
+        tma_load_3d(&sUe[so], &maps.ue, i0 - 4, ka_lo - 2, jloc, mb);
+        tma_load_3d(&sVn[so], &maps.vn, i0 - 4, ka_lo - 2, jloc, mb);
+        tma_load_3d(&sWb[so], &maps.wb, i0 - 4, ka_lo - 1, jloc, mb);
       }
       if (w == 0) {
         const int sko = (rr & (FM_NSLOT - 1)) * FM_W;
-        cp_async4(&sK[sko + lane + 1], gK + (jloc * imt + g_k));
+        cp_async4(&sK[sko + lane + FM_E], gK + (jloc * imt + g_k));
         if (lane < 2) cp_async4(&sK[sko + e2], gK + (jloc * imt + g_kh));
       }
       cp_async_commit();
@@ -226,7 +229,7 @@ __global__ void __launch_bounds__(32 * MAXW, 1) k_fct_march(const DevView v, int
     }
     if (w == 0) {
       const int sko = (rr & (FM_NSLOT - 1)) * FM_W;
-      cp_async4(&sK[sko + lane + 1], gK + (jloc * imt + g_k));
+      cp_async4(&sK[sko + lane + FM_E], gK + (jloc * imt + g_k));
       if (lane < 2) cp_async4(&sK[sko + e2], gK + (jloc * imt + g_kh));
     }
     cp_async_commit();
@@ -238,7 +241,7 @@ __global__ void __launch_bounds__(32 * MAXW, 1) k_fct_march(const DevView v, int
   const double c2dtts = v.c2dtts;
   const double twodt = c2dtts * v.dtxcel[k - 1];
   const double *__restrict__ cstr = v.cstr, *__restrict__ cstdyt2r = v.cstdyt2r;
-  const int o_c = (w + 1) * FM_W + lane + 1;                 // own element in a staged plane
+  const int o_c = (w + 1) * FM_W + lane + FM_E;              // own element in a staged plane
   const int o_u = (k > 1) ? o_c - FM_W : o_c;                // clamped k-1 (Tu = Tc at k = 1)
   const int o_d = (k < km) ? o_c + FM_W : o_c;               // clamped k+1
   const int ro = w * 32 + lane;
@@ -274,7 +277,7 @@ __global__ void __launch_bounds__(32 * MAXW, 1) k_fct_march(const DevView v, int
     // north face of row rA0-1: low-order flux and antidiffusive flux (anti_fn(row 1) = 0, :475)
     lo_n_p = upw(vn_m, Tm, Tc);
     a_n_p = (rA0 - 1 < 2) ? 0.0 : vn_m * (Um + Uc) - lo_n_p;
-    kmc_p = sK[((rA0 - 1) & 3) * FM_W + lane + 1];
+    kmc_p = sK[((rA0 - 1) & 3) * FM_W + lane + FM_E];
   }
   __syncthreads();   // row rA0-1 has been read: its slot may be refilled
   // state of the previous row's x / z faces, carried across the barrier to where their neighbours' ratios are visible
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(32 * MAXW, 1) k_fct_march(const DevView v, int
     int kmc = 0;
     if (doA) {
       const int so = (r & 3) * plane, sn = ((r + 1) & 3) * plane;
-      const int sko = (r & 3) * FM_W + lane + 1;
+      const int sko = (r & 3) * FM_W + lane + FM_E;
       const double Te = sT[so + o_c + 1], Tw = sT[so + o_c - 1], Tu = sT[so + o_u], Td = sT[so + o_d];
       const double Ue = sU[so + o_c + 1], Uw = sU[so + o_c - 1], Uu = sU[so + o_u], Ud = sU[so + o_d];
       Tn = sT[sn + o_c];
@@ -326,7 +329,7 @@ __global__ void __launch_bounds__(32 * MAXW, 1) k_fct_march(const DevView v, int
       const double m = (kmc >= k) ? 1.0 : 0.0;
       const double mu = (kmc >= k - 1) ? 1.0 : 0.0;
       const bool mw_b = sK[sko - 1] >= k, me_b = sK[sko + 1] >= k;
-      const bool ms_b = kmc_p >= k, mn_b = sK[((r + 1) & 3) * FM_W + lane + 1] >= k;
+      const bool ms_b = kmc_p >= k, mn_b = sK[((r + 1) & 3) * FM_W + lane + FM_E] >= k;
       const double dcfx = cstr[r - 1] * dxtr_i * 0.5;
       const double dcfy = cstdyt2r[r - 1];
       // low-order fluxes of the six faces and the low-order solution (:496-580)
