@@ -206,9 +206,15 @@ def _stress(case, o, ref, rng):
             t[0, n][z] = 0.0
     t[0] *= case["tmask"][None]
     t[1] *= case["tmask"][None]
+    # the cyclic boundary columns are copies of the interior (setbcx, source/common/util.F:789-812): keep them consistent
+    t[..., 0] = t[..., -2]
+    t[..., -1] = t[..., 1]
     stf, btf = o.arr("stf").reshape(nt, jmt, imt), o.arr("btf").reshape(nt, jmt, imt)
     stf[:] = 1e-7 * rng.standard_normal(stf.shape) * (case["kmt"] > 0)
     btf[:] = 1e-8 * rng.standard_normal(btf.shape) * (case["kmt"] > 0)
+    for f in (stf, btf):
+        f[..., 0] = f[..., -2]
+        f[..., -1] = f[..., 1]
     reflib.oracle_to_ref(o, ref, only=["t", "stf", "btf"])
 
 

@@ -65,8 +65,9 @@ def test_mobi_multi_step_with_mixing(pkg, ws, monkeypatch):
 
 
 def test_mobi_kernels_agree_bitwise(pkg, monkeypatch):
-    """The warp-specialised kernel evaluates the same expressions in the same order as the
-    one-thread-per-column kernel: the source fields must be identical to the last bit."""
+    """The warp-specialised kernel evaluates the same expressions in the same order as the one-thread-per-column kernel.
+    With FMA contraction (round 2: the gate is the oracle at 1e-10 / 1e-12, not bit equality) the compiler fuses
+    differently in the two kernels: sources agree to 1e-12, tracers to 1e-13 of the field maximum."""
     case = pkg.synthetic.make_case(nt=37, imt=50, jmt=40, km=12, seed=11)
     out = []
     for ws in ("0", "1"):
@@ -76,8 +77,10 @@ def test_mobi_kernels_agree_bitwise(pkg, monkeypatch):
         ctx.step(True)
         out.append((ctx.fetch("src", (case.nsrc, case.jmt, case.km, case.imt)).copy(), ctx.download_t(+1).copy()))
         ctx.close()
-    assert np.array_equal(out[0][0], out[1][0])
-    assert np.array_equal(out[0][1], out[1][1])
+    for q in range(case.nsrc):
+        assert relerr(out[1][0][q], out[0][0][q]) <= 1e-12, (q, relerr(out[1][0][q], out[0][0][q]))
+    for n in range(case.nt):
+        assert relerr(out[1][1][n], out[0][1][n]) <= 1e-13, (n, relerr(out[1][1][n], out[0][1][n]))
 
 
 def test_mobi_lookahead_is_bitwise_neutral(pkg):

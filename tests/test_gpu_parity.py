@@ -295,9 +295,11 @@ def test_fourier_filter_parity(pkg):
 def test_fct_variants_agree_bitwise(pkg, shape, monkeypatch):
     """The marching FCT kernel (k_fct_march: shared-memory staged rows, every face flux formed once),
     the two-pass version (k_fct_rfac + k_update<3>, ratios through HBM) and the merged k_update<1>
-    evaluate every expression with the same operands in the same order; t(tau+1) must be identical to
-    the last bit on leapfrog and mixing steps, for one and for several k tiles / row chunks, and for a
-    two-slab decomposition of the same grid."""
+    evaluate every expression with the same operands in the same order.  Since round 2 the flux kernels are
+    compiled with FMA contraction (the gate is 1e-12 against the oracle, not bit equality), and the compiler
+    contracts differently in different kernels: the three variants agree to 1e-13 of the field maximum on
+    leapfrog and mixing steps, for one and for several k tiles / row chunks.  What must stay BITWISE is the
+    same kernel on a two-slab decomposition of the same grid."""
     case = pkg.synthetic.make_case(nt=4, names=["temp", "salt", "p0", "p1"], seed=3, **shape)
     out = {}
     for mode in ("merged", "split", "march"):
@@ -312,8 +314,8 @@ def test_fct_variants_agree_bitwise(pkg, shape, monkeypatch):
         out[mode] = res
         ctx.close()
     for a, b, c in zip(out["merged"], out["split"], out["march"]):
-        assert np.array_equal(a, b)
-        assert np.array_equal(a, c)
+        for n in range(case.nt):
+            assert relerr(b[n], a[n]) <= 1e-13 and relerr(c[n], a[n]) <= 1e-13, (n, relerr(b[n], a[n]), relerr(c[n], a[n]))
     # slabs: rows 2..jm and jm+1..jmt-1 computed by two contexts from the same state
     jm = case.jmt // 2
     ref = out["march"][0]

@@ -11,17 +11,20 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libuvic_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
-# -fmad=false: no FMA contraction, so the operation order written in the kernels (which
-# follows the reference's Fortran) is what executes -- the CPU oracle is built the same way
-# (-ffp-contract=off) and the stencil kernels then agree with it to the last bit wherever
-# the operation order was kept.  The kernels are bandwidth / FP64-issue bound, not FMA bound.
+# -fmad=false (the default for a translation unit): no FMA contraction, so the operation order written in the kernels
+# (which follows the reference's Fortran) is what executes -- the CPU oracle is built the same way (-ffp-contract=off)
+# and the coefficient kernels (elements, Redi / GM coefficients, vmixc, adv_vel, state, clinic) agree with it to the last
+# bit.  The three FP64-issue bound translation units -- the FCT, the diffusion / implicit solve and MOBI -- are compiled
+# WITH contraction since round 2: their gate is 1e-12 (tracers) / 1e-10 (MOBI sources) against the oracle, which they
+# keep, and a*b+c costs one FP64 issue slot instead of two (measured on B200, 0.5 degree x 40 tracers: march 11.35 ->
+# 11.08 ms, MOBI column 6.63 -> 5.96 ms, diffusion 3.88 -> 3.57 ms, step 28.5 -> 27.2 ms).
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
 ]
-# Per-file override of -fmad.  FMA contraction was measured on k_mobi.cu (the FP64-issue bound
-# kernel): 5-6 % faster only, so every translation unit keeps -fmad=false.
-FMAD = {f: "true" for f in os.environ.get("UVIC_B200_FMAD", "").split(",") if f}   # experiment switch
+FMAD = {"k_fct.cu": "true", "k_tracer.cu": "true", "k_mobi.cu": "true"}
+if "UVIC_B200_FMAD" in os.environ:   # experiment switch: the comma separated list replaces the default ("" = none)
+    FMAD = {f: "true" for f in os.environ["UVIC_B200_FMAD"].split(",") if f}
 
 
 def sources():
