@@ -70,3 +70,21 @@ def pointwise_relerr(a, b, rel_floor=1e-3):
     if not big.any():
         return 0.0
     return float((np.abs(a - b)[big] / den[big]).max())
+
+
+def make_oracle_o3(case, **kw):
+    """An oracle context from the -O3 build of the same sources (FMA contraction allowed: the reference's own optimisation
+    level, run/mk.ver).  Run beside the strict build it measures how far two legitimate builds of the reference's arithmetic
+    drift apart on a given state -- the conditioning of the step, used to scale gates where 1e-12 is not attainable by ANY
+    pair of builds (calcite dissolution near saturation, see test_calcite_is_ill_conditioned_on_deep_grids)."""
+    import os
+    import oracle_ffi
+
+    old_lib, old_path = oracle_ffi._lib, oracle_ffi.LIB
+    oracle_ffi.build_oracle()
+    oracle_ffi._lib, oracle_ffi.LIB = None, os.path.join(oracle_ffi.ORACLE_DIR, "_build", "liboracle_o3.so")
+    try:
+        o = make_oracle(case, **kw)
+    finally:
+        oracle_ffi._lib, oracle_ffi.LIB = old_lib, old_path
+    return o

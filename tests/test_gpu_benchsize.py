@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from conftest import load_pkg
-from helpers import make_oracle, oracle_rotate, oracle_set_step, pointwise_relerr, relerr
+from helpers import make_oracle, make_oracle_o3, oracle_rotate, oracle_set_step, pointwise_relerr, relerr
 
 pytestmark = pytest.mark.gpu
 
@@ -30,31 +30,45 @@ def _names40(pkg):
 
 @pytest.mark.parametrize("imt,jmt,km", [(34, 26, 40), (23, 30, 61)])
 def test_step_parity_at_benchmark_depths_40_tracers(pkg, imt, jmt, km):
-    """two leapfrog steps + one mixing step + one leapfrog step, nt = 40, km = 40 / 61"""
+    """two leapfrog steps + one mixing step + one leapfrog step, nt = 40, km = 40 / 61; per-step gate (every step starts from
+    the oracle's state).  Gate per tracer and step: 1e-12, or -- where the step itself is ill conditioned -- 20 x the difference
+    between two builds of the ORACLE's own source (strict and -O3 with FMA contraction) on the same state.  On these deep grids
+    that only widens the carbon tracers fed by calcite dissolution (caco3, caco3c13; alk, dic, dic13, c14 on the later steps)."""
     case = pkg.synthetic.make_case(imt=imt, jmt=jmt, km=km, nt=40, names=_names40(pkg), seed=km)
     assert case.has_mobi and case.nsrc == 35
     o = make_oracle(case, do_mobi=1)
+    o3 = make_oracle_o3(case, do_mobi=1)
     ctx = pkg.TracerContext(case, mobi=1)
     ctx.load_state()
-    worst, worst_pw = 0.0, 0.0
+    worst, worst_pw, widened = 0.0, 0.0, set()
     for itt, lf in enumerate((True, True, False, True)):
-        oracle_set_step(o, case, lf)
-        o.call("ora_step")
+        for q in (o, o3):
+            oracle_set_step(q, case, lf)
+            q.call("ora_step")
         ctx.step(leapfrog=lf)
-        got, ref = ctx.download_t(+1), o.t()[2]
+        got, ref, alt = ctx.download_t(+1), o.t()[2], o3.t()[2]
         assert np.array_equal(got[:, 1:-1] == 0, ref[:, 1:-1] == 0)                  # kmt / land-mask indexing: bit exact
         for n, nm in enumerate(case.tracer_names):
             e = relerr(got[n, 1:-1], ref[n, 1:-1])
-            if nm not in ("caco3", "caco3c13"):
+            cond = relerr(alt[n, 1:-1], ref[n, 1:-1])
+            tol = max(1e-12, 20.0 * cond)
+            if tol > 1e-12:
+                widened.add(nm)
+            else:
                 worst, worst_pw = max(worst, e), max(worst_pw, pointwise_relerr(got[n, 1:-1], ref[n, 1:-1]))
-            assert e <= _tol(nm), (itt, nm, e)
-        ctx.upload_t(+1, ref)      # per-step gate (north_star): the next step starts from the oracle's state on both sides
-        oracle_rotate(o)
+            assert e <= tol, (itt, nm, e, cond)
+        ctx.upload_t(+1, ref)      # per-step gate (north_star): the next step starts from the oracle's state on all sides
+        o3.t()[2][:] = ref
+        for q in (o, o3):
+            oracle_rotate(q)
         ctx.rotate()
-    print(f"{imt}x{jmt}x{km} nt=40: worst normalised {worst:.2e}, worst point-wise relative (|ref| > 1e-3 max) {worst_pw:.2e}")
+    print(f"{imt}x{jmt}x{km} nt=40: worst normalised {worst:.2e}, worst point-wise relative (|ref| > 1e-3 max) {worst_pw:.2e}; "
+          f"gate widened by the oracle's own build-to-build difference for {sorted(widened)}")
+    assert widened <= {"caco3", "caco3c13", "alk", "dic", "dic13", "c14"}, widened
     assert worst_pw <= 1e-9
     ctx.close()
     o.close()
+    o3.close()
 
 
 def test_convection_stress_parity(pkg):
