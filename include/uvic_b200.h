@@ -260,6 +260,9 @@ int uvic_b200_inventory(uvic_b200_ctx *ctx, int level, double *out_nt);
 /* tbar(km,nt,jl): sum_i t(tau)*dzt*dxt*cst*dyt*tmask per level, tracer and row */
 int uvic_b200_tbar(uvic_b200_ctx *ctx, double *tbar_host);
 /* basin sums sumbk(3,km,nt) by mskhr */
+/* travar(k,n,jrow) = sum_i t(tau)^2 dV and dtabs(k,n,jrow) = sum_i |t(tau+1)-t(tau-1)| dV / (c2dtts dtxcel(k)) of the last step made
+ * with diag = 1 (09/mom/tracer.F:1521-1536), shaped like uvic_b200_tbar's output; either pointer may be NULL */
+int uvic_b200_travar_dtabs(uvic_b200_ctx *ctx, double *travar_host, double *dtabs_host);
 int uvic_b200_sumbk(uvic_b200_ctx *ctx, double *sumbk_host);
 
 /* ---- introspection (tests, halo exchange, profiling) ---------------------------------- */

@@ -14,6 +14,6 @@ os.makedirs(os.path.join(ROOT, "uvic2.9_b200", "variants"), exist_ok=True)
 for arg in sys.argv[1:]:
     name, files = arg.split("=", 1)
     defines = [f for f in files.split(",") if f.startswith("-D")]
-    fm = {f: "true" for f in files.split(",") if f and not f.startswith("-D")}
+    fm = {f: "true" for f in files.split(",") if f and not f.startswith("-D")} or None   # no file named: the default FMA set
     out = os.path.join(ROOT, "uvic2.9_b200", "variants", f"libuvic_b200_{name}.so")
     print(b.build(force=True, fmad=fm, out=out, objdir_name=f"build_{name}", defines=defines))

@@ -121,9 +121,14 @@ def test_tbar_sumbk_against_oracle(pkg):
     ctx.load_state()
     ctx.step(True, diag=True)
     tb, sb = ctx.tbar(), ctx.sumbk()
+    tv, da = ctx.travar_dtabs()
     for n in range(1, case.nt + 1):
         o.call("ora_diag_tbar", n)
     ref_tb = o.arr("tbar", (case.jmt, case.nt, case.km))[1:-1]
+    ref_tv, ref_da = o.arr("travar", (case.jmt, case.nt, case.km))[1:-1], o.arr("dtabs", (case.jmt, case.nt, case.km))[1:-1]
+    assert np.abs(ref_tv).max() > 0 and np.abs(ref_da).max() > 0
+    for n in range(case.nt):
+        assert relerr(tv[:, n], ref_tv[:, n]) <= 1e-13 and relerr(da[:, n], ref_da[:, n]) <= 1e-13, (n, relerr(tv[:, n], ref_tv[:, n]), relerr(da[:, n], ref_da[:, n]))
     ref_sb = o.arr("sumbk", (case.nt, case.km, 3))
     assert np.abs(ref_tb).max() > 0 and np.abs(ref_sb).max() > 0
     for n in range(case.nt):

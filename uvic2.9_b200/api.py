@@ -85,7 +85,7 @@ ABI_SYMBOLS = [
     "uvic_b200_tavg_accumulate", "uvic_b200_tavg_fetch", "uvic_b200_state", "uvic_b200_gasbc", "uvic_b200_wait_before_advection",
     "uvic_b200_clinic_setup", "uvic_b200_upload_u_level", "uvic_b200_download_u", "uvic_b200_upload_smf", "uvic_b200_clinic",
     "uvic_b200_download_zu", "uvic_b200_rotate_u",
-    "uvic_b200_set_host_window", "uvic_b200_lookahead_stats", "uvic_b200_invalidate_lookahead", "uvic_b200_join_streams", "uvic_b200_measure_fp64_peak",
+    "uvic_b200_travar_dtabs", "uvic_b200_set_host_window", "uvic_b200_lookahead_stats", "uvic_b200_invalidate_lookahead", "uvic_b200_join_streams", "uvic_b200_measure_fp64_peak",
     "uvic_b200_group_create", "uvic_b200_group_destroy", "uvic_b200_group_last_error", "uvic_b200_group_size", "uvic_b200_group_ctx",
     "uvic_b200_group_rows", "uvic_b200_group_upload_t", "uvic_b200_group_download_t", "uvic_b200_group_upload_adv_vel",
     "uvic_b200_group_upload_vbc", "uvic_b200_group_upload_forcing", "uvic_b200_group_step", "uvic_b200_group_rotate",
@@ -148,6 +148,7 @@ def load_library():
     L.uvic_b200_unpin_host.argtypes = [vp]
     L.uvic_b200_inventory.argtypes = [vp, C.c_int, vp]
     L.uvic_b200_tbar.argtypes = [vp, vp]
+    L.uvic_b200_travar_dtabs.argtypes = [vp, vp, vp]
     L.uvic_b200_sumbk.argtypes = [vp, vp]
     L.uvic_b200_fetch.argtypes = [vp, C.c_char_p, vp, C.POINTER(C.c_size_t)]
     L.uvic_b200_device_ptr.restype = vp
@@ -569,6 +570,12 @@ class TracerContext:
         out = np.empty((self.jhi - self.jlo + 1, self.nt, self.km))
         self._ck(self.L.uvic_b200_tbar(self.h, _vp(out)))
         return out
+
+    def travar_dtabs(self):
+        shp = (self.jhi - self.jlo + 1, self.nt, self.km)
+        a, b = np.empty(shp), np.empty(shp)
+        self._ck(self.L.uvic_b200_travar_dtabs(self.h, _vp(a), _vp(b)))
+        return a, b
 
     def sumbk(self):
         out = np.empty((self.nt, self.km, 3))

@@ -318,6 +318,12 @@ static int create_impl(const uvic_b200_dims *d, const uvic_b200_grid *g, const u
     CK(cudaMalloc((void **)&ctx->tbar, ntb * sizeof(double)));
     CK(cudaMemset(ctx->tbar, 0, ntb * sizeof(double)));
     ctx->owned.push_back(ctx->tbar);
+    CK(cudaMalloc((void **)&ctx->travar, ntb * sizeof(double)));
+    CK(cudaMalloc((void **)&ctx->dtabs, ntb * sizeof(double)));
+    CK(cudaMemset(ctx->travar, 0, ntb * sizeof(double)));
+    CK(cudaMemset(ctx->dtabs, 0, ntb * sizeof(double)));
+    ctx->owned.push_back(ctx->travar);
+    ctx->owned.push_back(ctx->dtabs);
     CK(cudaMalloc((void **)&ctx->sumbk, (size_t)3 * km * nt * sizeof(double)));
     ctx->owned.push_back(ctx->sumbk);
     CK(cudaMalloc((void **)&ctx->red_out, (size_t)nt * sizeof(double)));
@@ -900,6 +906,7 @@ int uvic_b200_tracer(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si) {
   CK(cudaGetLastError());
   if (si->diag) {
     launch_tbar(ctx);
+    launch_travar_dtabs(ctx, ctx->travar, ctx->dtabs);
     if (ctx->v.mskhr) launch_sumbk(ctx);
     CK(cudaGetLastError());
   }
@@ -1038,6 +1045,14 @@ int uvic_b200_tbar(uvic_b200_ctx *ctx, double *h) {
   if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
   size_t n = (size_t)ctx->v.km * ctx->v.nt * (ctx->v.jhi - ctx->v.jlo + 1);
   CK(cudaMemcpyAsync(h, ctx->tbar, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int uvic_b200_travar_dtabs(uvic_b200_ctx *ctx, double *travar_host, double *dtabs_host) {
+  if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
+  size_t n = (size_t)ctx->v.km * ctx->v.nt * (ctx->v.jhi - ctx->v.jlo + 1);
+  if (travar_host) CK(cudaMemcpyAsync(travar_host, ctx->travar, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (dtabs_host) CK(cudaMemcpyAsync(dtabs_host, ctx->dtabs, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }

@@ -106,7 +106,7 @@ struct FmGeom {
 };
 
 template <int MAXW>
-__global__ void __launch_bounds__(32 * MAXW, 1) k_fct_march(const DevView v, int nbase, int ng, FmGeom gm, const __grid_constant__ FmMaps maps) {
+__global__ void __launch_bounds__(32 * MAXW, (MAXW <= 8) ? 2 : 1) k_fct_march(const DevView v, int nbase, int ng, FmGeom gm, const __grid_constant__ FmMaps maps) {
   extern __shared__ __align__(128) unsigned char fm_raw[];
   constexpr int plane = FmCfg<MAXW>::PLANE;         // plane row p <-> level ka_lo - 1 + p
   // skipping the face-flux phase of land warps and the write of land cells pays where registers are not the limit
@@ -496,7 +496,8 @@ void launch_fct_march(uvic_b200_ctx *c, int nbase, int ng) {
   // (measured on B200, profiles/).  UVIC_B200_FCT_MAXW overrides the choice (experiments).
   int maxw = (c->v.km <= 20) ? 20 : 16;
   if (const char *e = getenv("UVIC_B200_FCT_MAXW")) maxw = atoi(e);
-  if (maxw <= 12) fct_launch_t<12>(c, nbase, ng);
+  if (maxw <= 8) fct_launch_t<8>(c, nbase, ng);        // two CTAs per SM (experiment: UVIC_B200_FCT_MAXW=8)
+  else if (maxw <= 12) fct_launch_t<12>(c, nbase, ng);
   else if (maxw <= 16) fct_launch_t<16>(c, nbase, ng);
   else if (maxw <= 20) fct_launch_t<20>(c, nbase, ng);
   else fct_launch_t<21>(c, nbase, ng);

@@ -36,6 +36,37 @@ __global__ void __launch_bounds__(256) k_tbar(const DevView v, const double *t, 
   if (lane == 0) out[warp] = s;
 }
 
+// travar(k,n,jloc) = sum_i t(tau)^2 darea and dtabs(k,n,jloc) = sum_i |t(tau+1) - t(tau-1)| darea fx, fx = 1/(c2dtts dtxcel(k))
+// (09/mom/tracer.F:1521-1536); same line ownership and summation tree as k_tbar
+__global__ void __launch_bounds__(256) k_travar_dtabs(const DevView v, double *travar, double *dtabs) {
+  int warp = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  int lane = threadIdx.x & 31;
+  int nrow = v.jhi - v.jlo + 1;
+  long long nline = (long long)v.km * v.nt * nrow;
+  if (warp >= nline) return;
+  int k = warp % v.km + 1;
+  int n0 = (warp / v.km) % v.nt;
+  int j = warp / (v.km * v.nt) + v.jlo;
+  const double cosdyt = v.cst[j - 1] * v.dyt[j - 1];
+  const double r2dt = 1.0 / v.c2dtts;
+  const double fx = r2dt / v.dtxcel[k - 1];
+  const double *t0 = v.t_0 + (long long)n0 * v.n3, *tp = v.t_p1 + (long long)n0 * v.n3, *tm = v.t_m1 + (long long)n0 * v.n3;
+  double s1 = 0.0, s2 = 0.0;
+  for (int i = 2 + lane; i <= v.imt - 1; i += 32) {
+    const double m = (v.kmt[X2(i, j)] >= k) ? 1.0 : 0.0;
+    const double darea = v.dzt[k - 1] * v.dxt[i - 1] * cosdyt * m;
+    const double tc = t0[X3(i, k, j)];
+    s1 += tc * tc * darea;
+    s2 += fabs(tp[X3(i, k, j)] - tm[X3(i, k, j)]) * darea * fx;
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if (lane == 0) {
+    travar[warp] = s1;
+    dtabs[warp] = s2;
+  }
+}
+
 // inv(n) = sum over (row, level) of tbar(k,n,row), fixed order, one block per tracer
 __global__ void __launch_bounds__(256) k_inventory(const DevView v, const double *tbar, double *inv) {
   __shared__ double sh[256];
@@ -94,6 +125,11 @@ void launch_tbar(uvic_b200_ctx *c) {
   DevView &v = c->v;
   long long nline = (long long)v.km * v.nt * (v.jhi - v.jlo + 1);
   KLAUNCH("k_tbar", k_tbar, cdiv(nline * 32, 256), 256, v, v.t_0, c->tbar);
+}
+void launch_travar_dtabs(uvic_b200_ctx *c, double *travar, double *dtabs) {
+  DevView &v = c->v;
+  long long nline = (long long)v.km * v.nt * (v.jhi - v.jlo + 1);
+  KLAUNCH("k_travar_dtabs", k_travar_dtabs, cdiv(nline * 32, 256), 256, v, travar, dtabs);
 }
 void launch_sumbk(uvic_b200_ctx *c) {
   DevView &v = c->v;

@@ -422,8 +422,11 @@ __global__ void __launch_bounds__(UPD_T) k_update(const DevView v, int nbase, in
 #define INV_T 128
 // INV_KC: levels whose loads are in flight together; 8 for deep grids, 4 for km <= 24 (19 levels are 5 chunks of 4 or 3
 // of 8 with 5 idle slots; measured 47 against 54 us on the 100x100x19 grid, 1.87 against 2.33 ms on 0.5 degree x 40 levels)
+#ifndef UVIC_INV_MINBLOCKS
+#define UVIC_INV_MINBLOCKS 1   // experiment knob (scripts/build_variants.py inv6=-DUVIC_INV_MINBLOCKS=6): resident CTAs per SM
+#endif
 template <int INV_KC>
-__global__ void __launch_bounds__(INV_T) k_invtri(const DevView v, int nbase, int ng, int ntq) {
+__global__ void __launch_bounds__(INV_T, UVIC_INV_MINBLOCKS) k_invtri(const DevView v, int nbase, int ng, int ntq) {
   extern __shared__ double zsm[];   // [km][INV_T]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int tq = blockIdx.x % ntq, cb = blockIdx.x / ntq;
