@@ -354,6 +354,15 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the tracer step has no CPU fallback")
     torch.cuda.set_device(local)
     dist = None
+    if world > 1 and os.environ.get("UVIC_B200_BENCH_AFFINITY", "1") == "1":
+        # one slice of the host cores per rank, in device order: the pinned host buffers of the host-buffer legs are then
+        # first-touched on the socket next to the rank's GPU instead of all on one NUMA node
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            os.sched_setaffinity(0, set(cores[local * per:(local + 1) * per]) or set(cores))
+        except (AttributeError, OSError):
+            pass
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))

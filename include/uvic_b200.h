@@ -216,7 +216,7 @@ int uvic_b200_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si);
  * in between; otherwise it is discarded and recomputed.  Results are identical with and without hints. */
 int uvic_b200_hint_next_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *next);
 /* How often the sources computed ahead were adopted (hit) or had to be recomputed because the step that came was not the
- * step that was hinted (miss: relyr, co2ccn, dtts, leapfrog or the t(tau-1) slot differ).  `next` of the hint must carry
+ * step that was hinted (miss: relyr by more than 1e-9 years, co2ccn, dtts, leapfrog or the t(tau-1) slot differ).  `next` of the hint must carry
  * the NEXT step's relyr / co2ccn -- a driver advances relyr every step (source/mom/mom.F). */
 int uvic_b200_lookahead_stats(uvic_b200_ctx *ctx, int64_t *hits, int64_t *misses);
 /* Drop sources computed ahead: required after writing t, the forcing or the vertical b.c. through raw device pointers

@@ -89,7 +89,7 @@ def test_one_model_year_against_translated_reference(pkg):
         ref.set("first", 0)
         T.ref_step(ref)
         T.ref_rotate(ref)
-        ctx.set_time(ry, ry + dty)
+        ctx.set_time(ry, ry + dty)      # the hint's time is formed like the Fortran shim forms it: not bit-equal to the next ry
         ctx.step(leapfrog=lf, next_leapfrog=pkg.timestep.is_leapfrog(itt + 1, 16))
         ctx.rotate()
     gt, rt = ctx.download_t(0), ref.view("t")[1]

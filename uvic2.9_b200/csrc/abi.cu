@@ -732,7 +732,10 @@ int uvic_b200_rotate(uvic_b200_ctx *ctx) {
 }
 
 static bool same_step(const uvic_b200_stepinfo &a, const uvic_b200_stepinfo &b) {
-  return a.dtts == b.dtts && a.leapfrog == b.leapfrog && a.relyr == b.relyr && a.co2ccn == b.co2ccn;
+  // relyr: a host that forms "the next step's model time" itself (relyr + dtts / year length) and the model's own clock
+  // differ in the last bits; 1e-9 years = 0.03 s of a 1.25 day step is the same step (the sources are then those of the
+  // hinted time: the declination differs by 1e-9 relative, far below the 1e-10 gate of the sources)
+  return a.dtts == b.dtts && a.leapfrog == b.leapfrog && fabs(a.relyr - b.relyr) <= 1e-9 && a.co2ccn == b.co2ccn;
 }
 
 // MOBI of this step.  If the look-ahead of the previous step already produced the sources for exactly this step
