@@ -250,8 +250,12 @@ int uvic_b200_tracer_step(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si, cons
  * velocities (every step) and, when they changed, the coupler's sbc array and the bottom heat flux (NULL = keep).
  * Device -> host: T and S of t(tau+1), ts_taup1(imt,km,jl,2), for the density in clinic / loadmw (NULL = skip), and the
  * whole sbc array with the averaged surface accumulators when this step ends an ocean segment (eots && osege).  All
- * other tracers stay resident; output steps fetch them with uvic_b200_download_tracer.  Synchronous like the call
- * sites it replaces (setvbc source/mom/mom.F:360, isopyc :340, vmixc :347, tracer :389). */
+ * other tracers stay resident; output steps fetch them with uvic_b200_download_tracer.  On return the host velocity
+ * buffers have been read and every requested output is on the host ("complete for the outputs requested");
+ * the resident tracers of t(tau+1) may still be in flight -- every later call on the context is ordered behind them --
+ * so the host's work between two tracer steps overlaps the rest of this one, and the next step's velocity upload starts
+ * as soon as this step has formed its total velocities.  Replaces setvbc source/mom/mom.F:360, isopyc :340, vmixc :347,
+ * tracer :389. */
 int uvic_b200_tracer_step_coupled(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *si, const double *adv_vet,
                                   const double *adv_vnt, const double *adv_vbt, const double *sbc_in, const double *bhf,
                                   int eots, int osegs, int osege, int ntspos, double *ts_taup1, double *sbc_out);

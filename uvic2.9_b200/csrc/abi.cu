@@ -289,6 +289,7 @@ static int create_impl(const uvic_b200_dims *d, const uvic_b200_grid *g, const u
   CK(cudaStreamCreateWithFlags(&ctx->stream3, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&ctx->ev_elem, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&ctx->ev_gm, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&ctx->vel_free, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&ctx->h2d_event, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&ctx->h2d_vbc_event, cudaEventDisableTiming));
   CK(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
@@ -350,6 +351,7 @@ int uvic_b200_destroy(uvic_b200_ctx *ctx) {
   if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
   if (ctx->ev_elem) cudaEventDestroy(ctx->ev_elem);
   if (ctx->ev_gm) cudaEventDestroy(ctx->ev_gm);
+  if (ctx->vel_free) cudaEventDestroy(ctx->vel_free);
   if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
   if (ctx->mobi_event) cudaEventDestroy(ctx->mobi_event);
   for (auto e : ctx->src_ready) if (e) cudaEventDestroy(e);
@@ -422,6 +424,7 @@ int uvic_b200_upload_u(uvic_b200_ctx *ctx, const double *u) {
 }
 int uvic_b200_adv_vel(uvic_b200_ctx *ctx) {
   if (ctx) cudaSetDevice(ctx->device);   // one host thread may drive several devices
+  if (ctx) ctx->vel_free_valid = false;
   launch_adv_vel(ctx);
   CK(cudaGetLastError());
   return 0;
@@ -693,6 +696,7 @@ int uvic_b200_clinic(uvic_b200_ctx *ctx, double c2dtuv, int itaux, int itauy) {
     if (itaux < 1 || itaux > v.numsbc || itauy < 1 || itauy > v.numsbc) return fail(ctx, "clinic: wind stress slot out of range");
   }
   ctx->clinic->c2dtuv = c2dtuv;
+  ctx->vel_free_valid = false;   // the U-cell advective velocities below read adv_vet / adv_vnt / adv_vbt
   halo_wait_now(ctx);   // rho and grad_p read the halo rows of t(tau): a pending asynchronous exchange must have landed
   // 09/mom/loadmw.F:150-155: rho of t(tau).  The tau slot is addressed directly: the time-level view of the tracer step
   // (which maps tau-1 onto tau on mixing steps) is left as the tracer entry points set it
@@ -993,8 +997,18 @@ int uvic_b200_tracer_step_coupled(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *
   if (!v.sbc) return fail(ctx, "tracer_step_coupled: call uvic_b200_sbc_setup first");
   if (ntspos < 1) return fail(ctx, "tracer_step_coupled: ntspos must be >= 1");
   halo_wait_now(ctx);
-  CK(cudaEventRecord(ctx->fork_event, ctx->stream));
-  CK(cudaStreamWaitEvent(ctx->copy_in, ctx->fork_event, 0));
+  // The coupler's array and the bottom heat flux are read by setvbc / written by set_sbc until the end of the previous
+  // step: their upload (start of an ocean segment only) waits for everything queued so far.  The velocities do not:
+  // with the FCT their device copies are free as soon as the previous step formed its total velocities (vel_free), so
+  // this step's upload runs while the previous step's tracer kernels are still at work.
+  const bool early_vel = ctx->vel_free_valid && v.fct && !sbc_in && !bhf;
+  if (early_vel) {
+    CK(cudaStreamWaitEvent(ctx->copy_in, ctx->vel_free, 0));
+  } else {
+    CK(cudaEventRecord(ctx->fork_event, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->copy_in, ctx->fork_event, 0));
+  }
+  ctx->vel_free_valid = false;
   if (sbc_in) CK(cudaMemcpyAsync(v.sbc, sbc_in, (size_t)v.n2 * v.numsbc * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
   if (bhf) CK(cudaMemcpyAsync(v.bhf, bhf, (size_t)v.n2 * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_in));
   CK(cudaEventRecord(ctx->h2d_vbc_event, ctx->copy_in));
@@ -1018,10 +1032,16 @@ int uvic_b200_tracer_step_coupled(uvic_b200_ctx *ctx, const uvic_b200_stepinfo *
   if (rc) return rc;
   launch_set_sbc(ctx, eots, osegs, osege, ntspos);     // 09/mom/tracer.F:1270-1288
   CK(cudaGetLastError());
-  if (sbc_out && eots && osege)
-    CK(cudaMemcpyAsync(sbc_out, v.sbc, (size_t)v.n2 * v.numsbc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  // Complete for the outputs requested on return: the host buffers of the velocities have been read, T and S
+  // of t(tau+1) are on the host; the coupler's array too on the step that returns it.  The tracers that stay resident may
+  // still be in flight -- every later call is ordered behind them on the context's stream -- so the host's own work between
+  // two tracer steps (clinic, tropic, the coupler) and the next step's upload overlap the rest of this step.
+  CK(cudaEventSynchronize(ctx->h2d_event));
   CK(cudaStreamSynchronize(ctx->copy_out));
-  CK(cudaStreamSynchronize(ctx->stream));
+  if (sbc_out && eots && osege) {
+    CK(cudaMemcpyAsync(sbc_out, v.sbc, (size_t)v.n2 * v.numsbc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
   CK(cudaGetLastError());
   return 0;
 }

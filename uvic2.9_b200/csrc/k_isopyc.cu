@@ -432,10 +432,14 @@ void launch_isopyc_vel_after(uvic_b200_ctx *c, cudaEvent_t after) {
     c->stream = main_stream;
     cudaEventRecord(c->ev_gm, c->stream3);
     c->gm_inflight = true;
+    // with the FCT the advection kernels read the TOTAL velocities ue / vn / wb only: from here on the device copies of
+    // adv_vet / adv_vnt / adv_vbt may be overwritten by the next step's upload (uvic_b200_tracer_step_coupled)
+    if (c->vel_free && v.fct) { cudaEventRecord(c->vel_free, c->stream3); c->vel_free_valid = true; }
   } else {
     if (after) cudaStreamWaitEvent(c->stream, after, 0);
     KLAUNCH("k_gm_total", k_gm_total, cdiv(ncol * v.km, 256), 256, v);
     KLAUNCH("k_gm_column", k_gm_column, cdiv(ncol, 128), 128, v);
+    if (c->vel_free && v.fct) { cudaEventRecord(c->vel_free, c->stream); c->vel_free_valid = true; }
   }
 }
 void launch_isopyc_vel(uvic_b200_ctx *c) { launch_isopyc_vel_after(c, nullptr); }
