@@ -422,11 +422,15 @@ __global__ void __launch_bounds__(UPD_T) k_update(const DevView v, int nbase, in
 #define INV_T 128
 // INV_KC: levels whose loads are in flight together; 8 for deep grids, 4 for km <= 24 (19 levels are 5 chunks of 4 or 3
 // of 8 with 5 idle slots; measured 47 against 54 us on the 100x100x19 grid, 1.87 against 2.33 ms on 0.5 degree x 40 levels)
-#ifndef UVIC_INV_MINBLOCKS
-#define UVIC_INV_MINBLOCKS 4   // 4 CTAs = 128 registers (measured best; 5 / 6 CTAs: 2.95 / 3.49 ms against 1.85); knob (scripts/build_variants.py inv6=-DUVIC_INV_MINBLOCKS=6): resident CTAs per SM
+// resident CTAs per SM: left to the compiler (it settles on 128 registers = 4 CTAs for the deep-grid variant); forcing 5 / 6
+// CTAs (scripts/build_variants.py inv5=-DUVIC_INV_MINBLOCKS=5) measured 2.95 / 3.49 ms against 1.85 on 0.5 degree x 40 levels
+#ifdef UVIC_INV_MINBLOCKS
+#define INV_BOUNDS __launch_bounds__(INV_T, UVIC_INV_MINBLOCKS)
+#else
+#define INV_BOUNDS __launch_bounds__(INV_T)
 #endif
 template <int INV_KC>
-__global__ void __launch_bounds__(INV_T, UVIC_INV_MINBLOCKS) k_invtri(const DevView v, int nbase, int ng, int ntq) {
+__global__ void INV_BOUNDS k_invtri(const DevView v, int nbase, int ng, int ntq) {
   extern __shared__ double zsm[];   // [km][INV_T]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int tq = blockIdx.x % ntq, cb = blockIdx.x / ntq;
