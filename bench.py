@@ -153,21 +153,26 @@ def kernel_bytes_per_launch(name, case, ctx, ngroup_launch):
     return table.get(name)
 
 
-def kernel_fp64_instr_per_launch(name, case, ctx, ngroup_launch):
-    """Thread-level FP64 instructions (DFMA + DADD + DMUL + DSETP ...) one launch of a MOBI kernel executes, per the committed
-    ncu capture (smsp__sass_thread_inst_executed_op_fp64_pred_on.sum, profiles/<tag>_ncu_kernels.json, scaled by the ocean
-    cells of this launch); None for the kernels measured against HBM or when no capture exists for the workload."""
-    if not name.startswith("k_mobi"):
-        return None
+def kernel_fp64_instr_per_launch(name, case, ctx, ngroup_launch, workload=None):
+    """Thread-level FP64 instructions (DFMA + DADD + DMUL + DSETP ...) one launch of a kernel executes, per the committed ncu
+    capture (smsp__sass_thread_inst_executed_op_fp64_pred_on.sum, profiles/<tag>_ncu_kernels.json).  MOBI kernels: the count
+    per ocean cell of any captured workload, scaled by the ocean cells of this launch.  Other kernels: the count of one launch
+    of the SAME workload on one GPU (same launch shape), scaled by this context's share of the rows.  None without a capture."""
     tag = os.environ.get("UVIC_B200_NCU_TAG", "r02")
     kp = os.path.join(ROOT, "profiles", f"{tag}_ncu_kernels.json")
     if not os.path.exists(kp):
         return None
-    for wl, ks in json.load(open(kp)).items():
-        e = ks.get(name) if isinstance(ks, dict) else None
-        if e and e.get("fp64_thread_instr_per_ocean_cell"):
-            ocean = float((case["kmt"][ctx.jlo - 1:ctx.jhi, 1:-1]).sum())
-            return e["fp64_thread_instr_per_ocean_cell"] * ocean
+    allk = json.load(open(kp))
+    if name.startswith("k_mobi"):
+        for wl, ks in allk.items():
+            e = ks.get(name) if isinstance(ks, dict) else None
+            if e and e.get("fp64_thread_instr_per_ocean_cell"):
+                ocean = float((case["kmt"][ctx.jlo - 1:ctx.jhi, 1:-1]).sum())
+                return e["fp64_thread_instr_per_ocean_cell"] * ocean
+        return None
+    e = (allk.get(workload) or {}).get(name)
+    if e and e.get("fp64_thread_instr"):
+        return e["fp64_thread_instr"] * (ctx.jhi - ctx.jlo + 1) / float(case.jmt - 2)
     return None
 
 
@@ -677,7 +682,7 @@ def main():
                "us_per_launch": round(1e3 * per_launch_ms, 2), "bytes_per_launch": b,
                "gbs": round(b / (per_launch_ms * 1e-3) / 1e9, 1) if b else None,
                "hbm_frac": round(b / (per_launch_ms * 1e-3) / 1e9 / peak, 4) if b else None}
-        fi = kernel_fp64_instr_per_launch(name, case, ctx, ng)
+        fi = kernel_fp64_instr_per_launch(name, case, ctx, ng, a.workload)
         if fi:
             row["fp64_instr_per_launch"] = fi
             row["fp64_frac"] = round(fi / (per_launch_ms * 1e-3) / fp64["dfma_per_s"], 4)
@@ -689,12 +694,14 @@ def main():
     def roof(kq):
         """one kernel against the roof that bounds it: HBM for the stencil / solve kernels, the measured FP64 issue rate for
         MOBI (arithmetic intensity 13 flop/B, above the machine balance)"""
-        if kq["kernel"].startswith("k_mobi") and kq.get("fp64_instr_per_launch"):
+        # the binding resource is the one the kernel uses the larger fraction of
+        if kq.get("fp64_instr_per_launch") and (kq.get("fp64_frac") or 0.0) > (kq.get("hbm_frac") or 0.0):
             ach = kq["fp64_instr_per_launch"] / (kq["us_per_launch"] * 1e-6) / 1e12
             return {"bound": "fp64", "kernel": kq["kernel"], "achieved": ach, "peak": fp64["dfma_per_s"] / 1e12, "unit": "T FP64 instr/s",
                     "frac": ach / (fp64["dfma_per_s"] / 1e12), "traffic": tr_all.get(kq["kernel"]), "share": kq["share"],
-                    "us_per_launch": kq["us_per_launch"], "hbm_frac": kq["hbm_frac"],
-                    "peak_source": "measured in this run: uvic_b200_measure_fp64_peak (dependent DFMA chains, thread-level instr/s)"}
+                    "us_per_launch": kq["us_per_launch"], "hbm_frac": kq["hbm_frac"], "hbm_gbs": kq["gbs"], "bytes_per_launch": kq["bytes_per_launch"],
+                    "peak_source": "measured in this run: uvic_b200_measure_fp64_peak (dependent DFMA chains, thread-level instr/s); "
+                                   "instruction count of the launch from the committed ncu capture"}
         if not kq["gbs"]:
             return None
         return {"bound": "hbm", "kernel": kq["kernel"], "achieved": kq["gbs"], "peak": peak, "unit": "GB/s", "frac": round(kq["gbs"] / peak, 4),
