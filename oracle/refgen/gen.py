@@ -51,7 +51,7 @@ UNITS = {
     "findex.F": ["findex"],
     "set_sbc.F": ["set_sbc"],
     "setvbc.F": ["setvbc"],
-    "clinic.F": ["clinic", "asbcu", "isbcu"],
+    "clinic.F": ["clinic", "diagc1", "diagc2", "asbcu", "isbcu"],
     "filuv.F": ["filuv"],
 }
 
@@ -61,7 +61,7 @@ SKIP_CALLS = {"getunit", "relunit", "openfile", "closefile", "getvara", "getvars
 
 
 # diagnostics behind run-time switches that the pin tests leave off (gyrets, trmbts, ...): a call aborts if ever reached
-STUB_CALLS = {"gyre", "ttb1", "ttb2", "ge1", "ge2", "utb1", "utb2", "diagc1", "diagc2"}
+STUB_CALLS = {"gyre", "ttb1", "ttb2", "ge1", "ge2", "utb1", "utb2"}
 
 
 def find(ref, name):

@@ -36,13 +36,15 @@ def oget(o, n):
     return o.L.ora_get_scalar(o.h, n.encode())
 
 
-def setup_pair(pkg, ref, seed=3, mobi=1, fourfil=False, names=None, **kw):
+def setup_pair(pkg, ref, seed=3, mobi=1, fourfil=False, names=None, momentum=False, **kw):
     """one synthetic case in the oracle and in the translated reference's COMMON blocks"""
     from uvic29_b200 import mobi_params as mp
 
     d = ref.dims
     names = names or mp.tracer_names_for()
     case = pkg.synthetic.make_case(imt=d["imt"], jmt=d["jmt"], km=d["km"], nt=len(names), names=names, seed=seed, **kw)
+    if momentum:
+        pkg.synthetic.add_momentum(case)
     o = make_oracle(case, do_mobi=mobi)
     o.set_scalar("do_filter", 1 if fourfil else 0)
     imt, jmt, km = d["imt"], d["jmt"], d["km"]
@@ -225,12 +227,23 @@ def test_full_tracer_step_bitwise(pkg, ref, seed, stress, fourfil):
     case, o = setup_pair(pkg, ref, seed=seed, fourfil=fourfil)
     if stress:
         _stress(case, o, ref, np.random.default_rng(seed))
+    # the segment accumulators for the atmosphere (09/mom/set_sbc.F, called at the end of the reference's `tracer`,
+    # 09/mom/tracer.F:1270-1288): every tracer owns slot n of the coupler array; a four-step segment
+    nt, jmt, imt = case.nt, case.jmt, case.imt
+    o.set("trsbcindex", np.arange(1, nt + 1, dtype=np.int32))
+    ref.view("trsbcindex")[...] = np.arange(1, nt + 1)
+    o.set_scalar("ntspos", 4), ref.set("ntspos", 4)
     for itt, lf in enumerate((True, True, False, True)):
         oracle_set_step(o, case, lf)
         ref_set_step(ref, o, case, lf)
         ref.set("first", 1 if itt == 0 else 0)                   # source/common/switch.h: filtr builds its tables when `first`
+        for k, v in (("eots", 1), ("osegs", int(itt == 0)), ("osege", int(itt == 3))):
+            o.set_scalar(k, v), ref.set(k, v)
         o.call("ora_step")
+        o.call("ora_set_sbc")
         ref_step(ref)
+        osbc, rsbc = o.arr("sbc").reshape(-1, jmt, imt)[:nt], ref.view("sbc")[:nt]
+        assert np.array_equal(osbc[..., 1:-1], rsbc[..., 1:-1]) and np.abs(osbc[8]).max() > 0, itt
         to, tr = o.t()[2], ref.view("t")[2]
         for n, nm in enumerate(case.tracer_names):
             nd = int((to[n, 1:-1] != tr[n, 1:-1]).sum())
@@ -438,4 +451,92 @@ def test_no_isotope_configuration_bitwise(pkg):
         assert np.isfinite(tr).all()
         oracle_rotate(o)
         ref_rotate(ref)
+    o.close()
+
+
+def _ref_momentum_inputs(ref, o, case):
+    """the inputs of setvbc / clinic the by-name copy cannot place: time levels of u, the coupler's stress slots, scalars"""
+    imt, jmt = case.imt, case.jmt
+    u = ref.view("u")                                              # u(imt,km,jmw,2,-1:...): tau-1, tau are slots 0, 1
+    u[0], u[1] = case["um1"], case["u"]
+    sbc = ref.view("sbc")
+    sbc[0], sbc[1] = case["taux"], case["tauy"]
+    ref.set("itaux", 1), ref.set("itauy", 2)
+    for n in ("c2dtuv", "kappa_m", "cdbot"):
+        ref.set(n, oget(o, n))
+    ref.set("grav", 980.6), ref.set("rho0r", 1.0 / 1.035)          # source/common/pconst.h; clinic forms grav*rho0r itself
+
+
+def _ref_clinic(ref, case):
+    imt, jmt = case.imt, case.jmt
+    ref.call("adv_vel", 0, 1, jmt, 1, imt)                         # source/mom/mom.F:300-390
+    t = ref.view("t")
+    ref.call("state", np.ascontiguousarray(t[1, 0]), np.ascontiguousarray(t[1, 1]), ref.view("rho"), 2, jmt, 1, imt)
+    ref.call("vmixc", 0, 1, jmt, 1, imt)
+    ref.call("setvbc", 0, 1, jmt, 1, imt)
+    ref.call("clinic", 0, 2, jmt - 1, 1, imt)
+
+
+@pytest.mark.parametrize("fourfil", [False, True])
+def test_setvbc_and_clinic_bitwise(pkg, ref, fourfil):
+    """§8 rows f-2 / f-4: the reference's setvbc (09/mom/setvbc.F) and clinic (09/mom/clinic.F, with filuv and the ice
+    coupling hooks it calls) against ora_setvbc / ora_setvbc_mom / ora_clinic / ora_filuv on the same inputs."""
+    from helpers import oracle_clinic, oracle_load_momentum
+
+    case, o = setup_pair(pkg, ref, seed=13, fourfil=fourfil, momentum=True)
+    imt, jmt, km, nt = case.imt, case.jmt, case.km, case.nt
+    rng = np.random.default_rng(5)
+    oracle_load_momentum(o, case)
+    _ref_momentum_inputs(ref, o, case)
+    # ---- tracer surface fluxes: one coupler slot per tracer (slots 3..nt+2), random fluxes, a bottom heat flux
+    osbc = o.arr("sbc").reshape(-1, jmt, imt)
+    rsbc = ref.view("sbc")
+    flx = o.raw("sbc_flx_index")
+    for n, nm in enumerate(case.tracer_names):
+        slot = n + 3
+        f = rng.standard_normal((jmt, imt)) * 1e-5
+        osbc[slot - 1] = f
+        rsbc[slot - 1] = f
+        flx[n] = slot
+        fname = "i" + nm[:-5] + "flx_phos" if nm.endswith("_phos") else "i" + nm + "flx"   # 09/common/csbc.h
+        ref.set({"temp": "ihflx", "salt": "isflx"}.get(nm, fname), slot)
+    bhf = rng.standard_normal((jmt, imt)) * 1e-6
+    o.raw("bhf")[:] = bhf.ravel()
+    ref.view("bhf")[...] = bhf
+    o.call("ora_setvbc")
+    if fourfil:
+        for n in ("jfu0", "jfu1", "jfu2"):
+            ref.set(n, int(oget(o, n)))
+        ref.set("jskpu", int(oget(o, "jfu2")) - int(oget(o, "jfu1")))     # source/common/setcom.F:84
+        ref.call("findex", ref.view("kmu"), 50, km, int(oget(o, "jfu1")), int(oget(o, "jfu2")), imt, ref.view("isuf"), ref.view("ieuf"))
+    else:
+        ref.set("jfu1", 0), ref.set("jfu2", jmt + 10)
+    ref.set("first", 1)                                           # source/common/switch.h: filtr builds its tables when `first`
+    oracle_clinic(o)
+    _ref_clinic(ref, case)
+    # setvbc: interior columns (the reference also sets the cyclic columns of stf/btf, which nothing reads)
+    ostf, obtf = o.arr("stf", (nt, jmt, imt)), o.arr("btf", (nt, jmt, imt))
+    assert np.array_equal(ostf[..., 1:-1], ref.view("stf")[..., 1:-1]) and np.abs(ostf).max() > 0
+    assert np.array_equal(obtf[..., 1:-1], ref.view("btf")[..., 1:-1]) and np.abs(obtf[0]).max() > 0
+    assert np.array_equal(o.arr("smf", (2, jmt, imt)), ref.view("smf"))
+    assert np.array_equal(o.arr("bmf", (2, jmt, imt)), ref.view("bmf")) and np.abs(ref.view("bmf")).max() > 0
+    # adv_vel on U cells, density, pressure gradient
+    assert np.array_equal(o.arr("adv_veu", (jmt, km, imt))[1:-1], ref.view("adv_veu"))
+    assert np.array_equal(o.arr("adv_vnu", (jmt, km, imt))[:-1], ref.view("adv_vnu"))
+    assert np.array_equal(o.arr("adv_vbu", (jmt, km + 1, imt))[1:-1], ref.view("adv_vbu")[:, :km + 1])
+    assert np.array_equal(o.arr("rho", (jmt, km, imt))[1:], ref.view("rho"))
+    assert np.array_equal(o.arr("grad_p", (2, jmt, km, imt))[:, 1:-1], ref.view("grad_p"))
+    # the step itself: u(tau+1) (internal mode) and the forcing of the barotropic equation
+    up1, rup1 = o.arr("up1", (2, jmt, km, imt)), ref.view("u")[2]
+    assert np.array_equal(up1[:, 1:-1], rup1[:, 1:-1]), np.abs(up1 - rup1).max()
+    assert np.abs(up1).max() > 0
+    assert np.array_equal(o.arr("zu", (2, jmt, imt))[:, 1:-1, 1:-1], ref.view("zu")[:, 1:-1, 1:-1])
+    if fourfil:
+        # the filter did act on the polar rows
+        o2 = make_oracle(case, do_mobi=0)
+        o2.set_scalar("do_filter", 0)
+        oracle_load_momentum(o2, case)
+        oracle_clinic(o2)
+        assert np.abs(o2.arr("up1", (2, jmt, km, imt)) - up1).max() > 0
+        o2.close()
     o.close()
