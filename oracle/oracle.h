@@ -11,7 +11,7 @@
  * oracle/_ref/libref_<tag>.so; tests/test_cpu_refpin.py drives that library and this restatement
  * with the same inputs and requires BITWISE equality (isopyc, vmixc, adv_flux, isoflux, mobi_init,
  * mobi_src on 10^4 random cells, co2calc_SWS, state, adv_vel, diagt1, filt/filtr/findex, whole
- * `tracer` steps with MOBI over leapfrog and mixing steps, set_sbc, setvbc, clinic + filuv).  Every routine follows the reference's
+ * `tracer` steps with MOBI over leapfrog and mixing steps, set_sbc, setvbc, gasbc's flux loop, clinic + filuv).  Every routine follows the reference's
  * array shapes, index ranges, loop order and operation order, and cites the
  * reference file:line it restates (paths relative to /root/reference; "09/" means
  * updates/09/source/, the update level run/mk.in:204 selects).

@@ -499,6 +499,7 @@ class Unit:
 class Translator:
     def __init__(self, skip_calls=(), overrides=None, known_units=(), stub_calls=()):
         self.skip_calls = set(skip_calls)
+        self.skip_why = dict(skip_calls) if isinstance(skip_calls, dict) else {}   # name -> reason recorded in the manifest
         self.stub_calls = set(stub_calls)   # diagnostics not translated: reaching one aborts
         self.overrides = dict(overrides or {})   # parameter name -> integer value (grid sizes)
         self.units: list[Unit] = []
@@ -537,8 +538,10 @@ class Translator:
             base = {"integer": "int", "real": "real", "double precision": "real", "logical": "logical", "character": "char"}[m.group(1)]
             rest = m.group(4)
             if base != "char" and m.group(2) and m.group(2).strip().startswith("("):
-                # `real (kind=8) x` does not occur; `real(x)` as an expression is excluded above
-                raise TranslateError("unsupported kind selector: " + s)
+                # `real(kind=8) x`: double precision, what every real is in this build (mk passes -r8); `real(x)` as an
+                # expression is excluded above
+                if not (base == "real" and re.fullmatch(r"\(\s*kind\s*=\s*8\s*\)", m.group(2).strip())):
+                    raise TranslateError("unsupported kind selector: " + s)
             if rest.startswith("function "):
                 return False
             for item in _split_top(rest):
@@ -1213,7 +1216,7 @@ class Translator:
             if name in self.skip_calls or name not in self.known_units:
                 if name not in self.skip_calls:
                     raise TranslateError(f"{u.name}: call of untranslated routine {name}")
-                return self._drop(u, s, "I/O helper")
+                return self._drop(u, s, self.skip_why.get(name, "I/O helper"))
             args = []
             if m.group(3) and m.group(3).strip():
                 p = Parser(tokenize(m.group(3)))

@@ -44,7 +44,7 @@ UNITS = {
     "tracer_adv_flx.F": ["adv_flux"],
     "vmixc.F": ["vmixc"],
     "adv_vel.F": ["adv_vel"],
-    "util.F": ["setbcx"],
+    "util.F": ["setbcx", "areaavg"],
     "tracer.F": ["tracer", "diagt1", "diagt2", "ivdift"],
     "filt.F": ["filt"],
     "filtr.F": ["filtr"],
@@ -53,11 +53,17 @@ UNITS = {
     "setvbc.F": ["setvbc"],
     "clinic.F": ["clinic", "diagc1", "diagc2", "asbcu", "isbcu"],
     "filuv.F": ["filuv"],
+    "gasbc.F": ["gasbc"],
 }
 
 # I/O helpers of the reference (unit management, netCDF reads, name mangling): calls are dropped, not translated
-SKIP_CALLS = {"getunit", "relunit", "openfile", "closefile", "getvara", "getvars", "putvara", "putvars", "defvar", "defdim",
-              "new_file_name", "file_names", "opennew", "opennext", "redef", "enddef"}
+SKIP_CALLS = {n: "I/O helper" for n in (
+    "getunit", "relunit", "openfile", "closefile", "getvara", "getvars", "putvara", "putvars", "defvar", "defdim",
+    "new_file_name", "file_names", "opennew", "opennext", "redef", "enddef")}
+# gasbc (09/common/gasbc.F) is the atmosphere's coupling routine: its air-sea gas exchange loop is on the path (the other
+# caller of co2calc_SWS); the forcing-data readers and the atmosphere's own physics it also calls are not
+SKIP_CALLS.update({n: "forcing data reader" for n in ("solardata", "co2ccndata", "data")})
+SKIP_CALLS.update({n: "atmosphere model (outside the path)" for n in ("decl", "zenith", "co2forc", "ta_embm_tavg", "ta_embm_tsi")})
 
 
 # diagnostics behind run-time switches that the pin tests leave off (gyrets, trmbts, ...): a call aborts if ever reached

@@ -116,9 +116,9 @@ def test_translation_manifest(ref):
     rt = ref.man["routines"]
     for r in ("tracer", "adv_flux", "isoflux", "ivdift", "invtri", "convct2", "elements", "ai_east", "ai_north", "ai_bottom",
               "isopyc_adv", "vmixc", "mobi_init", "mobi_driver", "mobi_src", "co2calc_sws", "drtsafe", "ta_iter_sws", "state",
-              "adv_vel", "setbcx", "filt", "filtr", "findex", "diagt1"):
+              "adv_vel", "setbcx", "filt", "filtr", "findex", "diagt1", "set_sbc", "setvbc", "clinic", "filuv", "gasbc", "areaavg"):
         assert r in rt, r
-    assert all(d["why"] in ("I/O", "I/O helper", "CHARACTER assignment", "CHARACTER expression") for d in ref.man["dropped"])
+    assert all(d["why"] in ("I/O", "I/O helper", "CHARACTER assignment", "CHARACTER expression") for d in ref.man["dropped"] if d["unit"] != "gasbc")
     assert "-DO_mobi" in ref.man["cpp_options"] and "-DO_fct" in ref.man["cpp_options"] and "-DO_isopycmix" in ref.man["cpp_options"]
 
 
@@ -539,4 +539,50 @@ def test_setvbc_and_clinic_bitwise(pkg, ref, fourfil):
         oracle_clinic(o2)
         assert np.abs(o2.arr("up1", (2, jmt, km, imt)) - up1).max() > 0
         o2.close()
+    o.close()
+
+
+def test_gasbc_flux_loop_bitwise(pkg, ref):
+    """§8 row f-2: the air-sea gas exchange of 09/common/gasbc.F (the other caller of co2calc_SWS) against ora_gasbc.
+    The reference routine is the atmosphere's coupling step: its forcing-data readers and the atmosphere's own physics
+    are dropped by the translation (listed in the manifest), the flux loop, the land carbon fluxes, setbcx and areaavg run."""
+    case, o = setup_pair(pkg, ref, seed=21)
+    imt, jmt, nt = case.imt, case.jmt, case.nt
+    rng = np.random.default_rng(8)
+    order = ["isst", "isss", "issdic", "issalk", "issdic13", "issc14", "isso2", "iws", "inpp", "isr", "iburn", "idicflx",
+             "idic13flx", "ic14flx", "io2flx"]
+    # every slot index of csbc.h gets a valid slot (gasbc zeroes ~50 flux slots by name); the 15 the flux loop uses are 1..15
+    q = 0
+    for nm, ents in ref.man["commons"].items():
+        if ents[0]["block"] == "csbc_i" and ents[0]["dims"] is None and nm.startswith("i") and nm not in order:
+            ref.set(nm, 16 + q % 87)
+            q += 1
+    for s, nm in enumerate(order):
+        ref.set(nm, s + 1)
+    o.set("gas_idx", np.arange(1, 16, dtype=np.int32))
+    osbc, rsbc = o.arr("sbc").reshape(-1, jmt, imt), ref.view("sbc")
+    ocean = np.asarray(case["kmt"]) > 0
+    vals = {"isst": rng.uniform(-3.0, 36.0, (jmt, imt)),                   # beyond the clamps at -2 and 35 (:152)
+            "isss": rng.uniform(-0.006, 0.004, (jmt, imt)),                # (S-35)/1000
+            "issdic": rng.uniform(1.8, 2.4, (jmt, imt)), "issalk": rng.uniform(2.2, 2.5, (jmt, imt)),
+            "isso2": rng.uniform(0.0, 0.4, (jmt, imt)), "iws": rng.uniform(0.0, 2000.0, (jmt, imt)),
+            "inpp": rng.uniform(0, 5e-8, (jmt, imt)), "isr": rng.uniform(0, 3e-8, (jmt, imt)), "iburn": rng.uniform(0, 1e-8, (jmt, imt))}
+    vals["issdic13"] = vals["issdic"] * rng.uniform(0.004, 0.03, (jmt, imt))    # both clamps of r13dic are reached (:170-171)
+    vals["issc14"] = vals["issdic"] * rng.uniform(0.8e-12, 1.3e-12, (jmt, imt))
+    for s, nm in enumerate(order[:11]):
+        osbc[s], rsbc[s] = vals[nm], vals[nm]
+    ice = np.clip(rng.uniform(-0.5, 1.2, (jmt, imt)), 0.0, 1.0)
+    o.arr("aice", (jmt, imt))[...] = ice
+    ref.view("aice")[1] = ice
+    ref.view("tmsk")[...] = ocean.astype(np.float64)
+    for k, v in (("co2ccn", 283.0), ("dc13ccn", -6.5), ("dc14ccn", 12.0)):
+        o.set_scalar(k, v), ref.set(k, v)
+    o.call("ora_gasbc")
+    ref.call("gasbc", 1, imt, 1, jmt)
+    for s in range(11, 15):
+        assert np.array_equal(osbc[s][1:-1], rsbc[s][1:-1]), order[s]
+        assert np.abs(osbc[s][1:-1][ocean[1:-1]]).max() > 0
+    assert np.isfinite(rsbc[11:15]).all()
+    dropped = {d["why"] for d in ref.man["dropped"] if d["unit"] == "gasbc"}
+    assert dropped <= {"forcing data reader", "atmosphere model (outside the path)", "I/O"}
     o.close()
