@@ -298,7 +298,10 @@ __device__ __forceinline__ double evans_parslow(double gl_x, double gd, double f
 // oxygen dependent rate factors (09/mom/mobi.F:775-835), the pre-loop light harvesting and
 // Evans-Parslow integrals of mobi_src (:1928-2003), and the oxygen / nitrate switches of
 // the denitrification terms (:1035-1046, 1301-1322).
-__global__ void __launch_bounds__(128, 4) k_mobi_cell(const DevView v) {
+#ifndef MOBI_CELL_MINB
+#define MOBI_CELL_MINB 4
+#endif
+__global__ void __launch_bounds__(128, MOBI_CELL_MINB) k_mobi_cell(const DevView v) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int ni = v.imt - 2, nrow = v.jhi - v.jlo + 1;
   if (idx >= (long long)ni * v.km * nrow) return;
@@ -686,7 +689,12 @@ __device__ __forceinline__ void mobi_src(const MobiPar *__restrict__ P, int nbio
 #undef fl
 }
 
-__global__ void __launch_bounds__(32) k_mobi_column(const DevView v, int mi, int nbio, double dtbio, double rdtts, double rnbio) {
+#ifdef MOBI_COL_MINB   // experiment builds: resident CTAs (= warps) per SM the register allocation must allow
+#define MOBI_COL_BOUNDS __launch_bounds__(32, MOBI_COL_MINB)
+#else
+#define MOBI_COL_BOUNDS __launch_bounds__(32)
+#endif
+__global__ void MOBI_COL_BOUNDS k_mobi_column(const DevView v, int mi, int nbio, double dtbio, double rdtts, double rnbio) {
   // ocean columns of the owned rows, sorted by depth so that the 32 columns of a warp run
   // the same number of levels
   int idx = blockIdx.x * blockDim.x + threadIdx.x;

@@ -147,7 +147,12 @@ struct SmCol {
 // 2: diffusive tendency only; 3: FCT advection only, subtracted from the tendency MODE 2 left in t(tau+1).
 // 2 followed by 3 performs the operations of 1 in the same order with half the registers each.
 template <int MODE>
-__global__ void __launch_bounds__(UPD_T) k_update(const DevView v, int nbase, int ng, int tch, int jfirst, int nrow) {
+#ifdef UPD_MINB   // experiment builds: resident CTAs per SM the register allocation must allow
+#define UPD_BOUNDS __launch_bounds__(UPD_T, UPD_MINB)
+#else
+#define UPD_BOUNDS __launch_bounds__(UPD_T)
+#endif
+__global__ void UPD_BOUNDS k_update(const DevView v, int nbase, int ng, int tch, int jfirst, int nrow) {
   // The 36 tracer-independent Redi coefficients of a cell's six faces are parked in shared
   // memory (thread-private slots, conflict free) instead of registers: 36 KB per 128-thread CTA
   // buys ~70 registers per thread, i.e. three CTAs per SM instead of one 256-thread CTA.
