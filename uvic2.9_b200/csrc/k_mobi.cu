@@ -298,8 +298,11 @@ __device__ __forceinline__ double evans_parslow(double gl_x, double gd, double f
 // oxygen dependent rate factors (09/mom/mobi.F:775-835), the pre-loop light harvesting and
 // Evans-Parslow integrals of mobi_src (:1928-2003), and the oxygen / nitrate switches of
 // the denitrification terms (:1035-1046, 1301-1322).
+// Twelve resident CTAs per SM (40 registers, ~380 bytes of spills that stay in L1) beat four at 128 registers: the kernel
+// is FP64-issue bound and short of warps to cover the pipe latency.  Measured on B200, 0.5 degree x 40 levels:
+// 160 registers 2.72 ms, 128: 2.49, 96: 2.48, 80: 2.44, 64: 2.35, 48: 2.32, 40: 2.29.
 #ifndef MOBI_CELL_MINB
-#define MOBI_CELL_MINB 4
+#define MOBI_CELL_MINB 12
 #endif
 __global__ void __launch_bounds__(128, MOBI_CELL_MINB) k_mobi_cell(const DevView v) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -63,6 +63,36 @@ __device__ __forceinline__ bool decode_cell(const DevView &v, long long idx, int
   return true;
 }
 
+// The same cell record for a CTA that owns a tile of 32 consecutive i x (blockDim.x / 32) consecutive levels of one row
+// (warp = level): the rows k-1, k, k+1 a warp reads are the rows its neighbour warps read, so they are fetched from L2
+// once per CTA instead of once per warp.  Grid: upd_tiles(v) * nrow CTAs.
+__device__ __forceinline__ bool decode_cell_tiled(const DevView &v, int jfirst, int nrow, int tiled, Cell &q) {
+  // tiled = 1: all warps of the CTA stacked in k; 2: pairs of warps in k, the pairs side by side in j (experiment)
+  const int nwj = (tiled == 2) ? 2 : 1;
+  const int ni = v.imt - 2, nit = (ni + 31) >> 5, nw = (blockDim.x >> 5) / nwj, nkt = (v.km + nw - 1) / nw;
+  unsigned b = blockIdx.x;
+  const unsigned it = b % (unsigned)nit;
+  b /= (unsigned)nit;
+  const unsigned kt = b % (unsigned)nkt;
+  const int w = threadIdx.x >> 5;
+  const unsigned jj = (b / (unsigned)nkt) * nwj + (w / nw);
+  q.i = 2 + (int)it * 32 + (threadIdx.x & 31);
+  q.k = 1 + (int)kt * nw + (w % nw);
+  q.j = (int)jj + jfirst;
+  if ((int)jj >= nrow || q.i > v.imt - 1 || q.k > v.km) return false;
+  const int jloc = q.j - v.jbase;
+  q.sk = v.imt;
+  q.sj = v.imt * v.km;
+  q.c = (q.i - 1) + v.imt * ((q.k - 1) + v.km * jloc);
+  q.cz = q.c + v.imt * (jloc + 1);
+  q.c2 = (q.i - 1) + v.imt * jloc;
+  return true;
+}
+static long long upd_tiles(const DevView &v, int threads, int tiled) {
+  const int nw = threads / 32 / ((tiled == 2) ? 2 : 1);
+  return (long long)((v.imt - 2 + 31) / 32) * ((v.km + nw - 1) / nw);
+}
+
 // ------------------------------------------------------------------------------------
 // t_lo and R+-x, R+-y, R+-z, rows max(2,jlo-1) .. min(jmt-1,jhi+1)
 // ------------------------------------------------------------------------------------
@@ -135,7 +165,9 @@ __global__ void __launch_bounds__(256) k_fct_rfac(const DevView v, int nbase, in
 // ------------------------------------------------------------------------------------
 // fluxes + explicit update, rows jlo..jhi
 // ------------------------------------------------------------------------------------
+#ifndef UPD_T
 #define UPD_T 128   // threads per CTA of k_update
+#endif
 __device__ __forceinline__ void pf_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // per-thread column of the shared-memory coefficient table: element a lives at p[a*UPD_T]
 struct SmCol {
@@ -152,13 +184,17 @@ template <int MODE>
 #else
 #define UPD_BOUNDS __launch_bounds__(UPD_T)
 #endif
-__global__ void UPD_BOUNDS k_update(const DevView v, int nbase, int ng, int tch, int jfirst, int nrow) {
+__global__ void UPD_BOUNDS k_update(const DevView v, int nbase, int ng, int tch, int jfirst, int nrow, int tiled) {
   // The 36 tracer-independent Redi coefficients of a cell's six faces are parked in shared
   // memory (thread-private slots, conflict free) instead of registers: 36 KB per 128-thread CTA
   // buys ~70 registers per thread, i.e. three CTAs per SM instead of one 256-thread CTA.
   __shared__ double sco[36][UPD_T];
   Cell q;
-  if (!decode_cell(v, (long long)blockIdx.x * blockDim.x + threadIdx.x, jfirst, nrow, q)) return;
+  if (tiled) {
+    if (!decode_cell_tiled(v, jfirst, nrow, tiled, q)) return;
+  } else if (!decode_cell(v, (long long)blockIdx.x * blockDim.x + threadIdx.x, jfirst, nrow, q)) {
+    return;
+  }
   const int tid = threadIdx.x;
   const int km = v.km, k = q.k, c = q.c, i = q.i, j = q.j, sk = q.sk, sj = q.sj;
   const long long n3 = v.n3;
@@ -743,7 +779,12 @@ void launch_tracer(uvic_b200_ctx *c, const uvic_b200_stepinfo *si) {
     int nchunk = (int)min((long long)ng, max(1LL, (148LL * 2048 * 2 + ncell_c - 1) / ncell_c));
     int tch = (ng + nchunk - 1) / nchunk;
     nchunk = (ng + tch - 1) / tch;
-    dim3 gc(cdiv(ncell_c, UPD_T), nchunk);
+    // CTA = 32 i x 4 levels where that tiling wastes few threads (imt - 2 close to a multiple of 32, km to one of 4): the
+    // kernel is bound by L2 -> L1 traffic and the tile halves it.  UVIC_B200_UPD_TILE=0/1 overrides (experiments).
+    static const int tile_env = getenv("UVIC_B200_UPD_TILE") ? atoi(getenv("UVIC_B200_UPD_TILE")) : -1;
+    const int tiled = (tile_env >= 0) ? tile_env : ((double)upd_tiles(v, UPD_T, 1) * UPD_T <= 1.08 * (double)(v.imt - 2) * v.km ? 1 : 0);
+    const long long ntile = upd_tiles(v, UPD_T, tiled);
+    dim3 gc(tiled ? (unsigned)(ntile * (tiled == 2 ? (nrow_c + 1) / 2 : nrow_c)) : cdiv(ncell_c, UPD_T), nchunk);
     // the total velocities come from the GM chain on its side stream: the advection kernels below are its first readers
     auto velocities = [&]() {
       gm_join(c);
@@ -755,7 +796,7 @@ void launch_tracer(uvic_b200_ctx *c, const uvic_b200_stepinfo *si) {
     if (v.fct) {
       const int variant = fct_variant();
       if (variant == 0) {
-        KLAUNCH("k_diffuse", k_update<2>, gc, UPD_T, v, nbase, ng, tch, v.jlo, nrow_c);
+        KLAUNCH("k_diffuse", k_update<2>, gc, UPD_T, v, nbase, ng, tch, v.jlo, nrow_c, tiled);
         velocities();
         launch_fct_march(c, nbase, ng);
       } else {
@@ -763,15 +804,15 @@ void launch_tracer(uvic_b200_ctx *c, const uvic_b200_stepinfo *si) {
         dim3 gr(cdiv(ncell_r, 256), nchunk);
         KLAUNCH("k_fct_rfac", k_fct_rfac, gr, 256, v, nbase, ng, tch, jf_r, nrow_r);
         if (variant == 1) {
-          KLAUNCH("k_diffuse", k_update<2>, gc, UPD_T, v, nbase, ng, tch, v.jlo, nrow_c);
-          KLAUNCH("k_fct_apply", k_update<3>, gc, UPD_T, v, nbase, ng, tch, v.jlo, nrow_c);
+          KLAUNCH("k_diffuse", k_update<2>, gc, UPD_T, v, nbase, ng, tch, v.jlo, nrow_c, tiled);
+          KLAUNCH("k_fct_apply", k_update<3>, gc, UPD_T, v, nbase, ng, tch, v.jlo, nrow_c, tiled);
         } else {
-          KLAUNCH("k_update", k_update<1>, gc, UPD_T, v, nbase, ng, tch, v.jlo, nrow_c);
+          KLAUNCH("k_update", k_update<1>, gc, UPD_T, v, nbase, ng, tch, v.jlo, nrow_c, tiled);
         }
       }
     } else {
       velocities();
-      KLAUNCH("k_update", k_update<0>, gc, UPD_T, v, nbase, ng, tch, v.jlo, nrow_c);
+      KLAUNCH("k_update", k_update<0>, gc, UPD_T, v, nbase, ng, tch, v.jlo, nrow_c, tiled);
     }
     // the source term enters in k_invtri: the first batch with a sourced tracer waits for MOBI
     bool sourced = false;
