@@ -18,4 +18,5 @@ FP="smsp__sass_thread_inst_executed_op_fp64_pred_on.sum,smsp__sass_thread_inst_e
 timeout 1200 ncu --set full --metrics $FP --clock-control none --import-source on -k regex:"k_fct_march|k_update|k_invtri|k_mobi_column|k_mobi_cell|k_isocoef" -s 12 -c 8 -f -o $O/${P}_prof_half $B > $O/${P}_ncu_h.log 2>&1
 U="python bench.py --workload uvic100_mobi37 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --min-seconds 0"
 timeout 600 ncu --set full --metrics $FP --clock-control none --import-source on -k regex:"k_fct_march|k_update|k_invtri|k_mobi_ws|k_mobi_cell" -s 12 -c 8 -f -o $O/${P}_prof_uvic $U > $O/${P}_ncu_u.log 2>&1
-ls -la $O | grep " e_" | wc -l
+UVIC_B200_FCT_CHUNK=360 python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-e2e --min-seconds 0.3 > $O/${P}_chunk360.json 2> $O/${P}_chunk360.err
+ls -la $O | grep " ${P}_" | wc -l

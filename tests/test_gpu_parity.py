@@ -462,3 +462,34 @@ def test_state_density_bit_exact(pkg):
     assert np.array_equal(ctx.state(0), o.arr("rho", ctx.shape3()))
     ctx.close()
     o.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [dict(imt=34, jmt=26, km=8), dict(imt=70, jmt=37, km=19), dict(imt=95, jmt=45, km=45)])
+def test_launch_geometry_does_not_change_a_bit(pkg, shape, monkeypatch):
+    """The CTA tile of the diffusion kernel (linear cell order, 32 i x 4 levels, 32 i x 2 levels x 2 rows) and the length
+    of the march's row chunks (warm-up rows recomputed per chunk) are launch geometry: t(tau+1) must be bit-identical
+    whatever they are, over leapfrog and mixing steps with isopycnal mixing and the FCT."""
+    case = pkg.synthetic.make_case(nt=4, names=["temp", "salt", "p0", "p1"], seed=17, **shape)
+
+    def run(env):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        ctx = pkg.TracerContext(case)
+        ctx.load_state()
+        res = []
+        for lf in (True, False, True):
+            ctx.step(leapfrog=lf)
+            res.append(ctx.download_t(+1).copy())
+            ctx.rotate()
+        ctx.close()
+        for k in env:
+            monkeypatch.delenv(k)
+        return res
+
+    base = run({"UVIC_B200_UPD_TILE": "0", "UVIC_B200_FCT_CHUNK": "64"})
+    assert np.abs(base[-1]).max() > 0
+    for env in ({"UVIC_B200_UPD_TILE": "1"}, {"UVIC_B200_UPD_TILE": "2"}, {"UVIC_B200_FCT_CHUNK": "8"}, {"UVIC_B200_FCT_CHUNK": "1000"}, {}):
+        got = run(env)
+        for a, b in zip(base, got):
+            assert np.array_equal(a, b), env

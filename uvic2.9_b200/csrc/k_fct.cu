@@ -420,7 +420,7 @@ static FmGeom fct_geometry(const DevView &v, int ng, int maxw) {
   // rows per chunk: every chunk recomputes the ratios of the two rows before its first (warm-up), so long chunks win as
   // long as the grid keeps many CTAs per SM -- measured on B200, 0.5 degree x 40 tracers (358 rows): 64 rows 11.06 ms,
   // 96: 10.86, 128: 10.76, 180: 10.68.  UVIC_B200_FCT_CHUNK overrides (experiments).
-  static const int chunk_rows = getenv("UVIC_B200_FCT_CHUNK") ? std::max(8, atoi(getenv("UVIC_B200_FCT_CHUNK"))) : 192;
+  const int chunk_rows = getenv("UVIC_B200_FCT_CHUNK") ? std::max(8, atoi(getenv("UVIC_B200_FCT_CHUNK"))) : 192;
   int nchunk = std::max(1, (rows + chunk_rows - 1) / chunk_rows);
   const long long per_chunk = (long long)ng * g.nit * g.nkt;
   while (per_chunk * nchunk < 148 * 4 && rows / (nchunk + 1) >= 8) nchunk++;   // small tracer batches: shorter marches, more CTAs

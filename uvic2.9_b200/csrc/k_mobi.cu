@@ -298,13 +298,16 @@ __device__ __forceinline__ double evans_parslow(double gl_x, double gd, double f
 // oxygen dependent rate factors (09/mom/mobi.F:775-835), the pre-loop light harvesting and
 // Evans-Parslow integrals of mobi_src (:1928-2003), and the oxygen / nitrate switches of
 // the denitrification terms (:1035-1046, 1301-1322).
-// Twelve resident CTAs per SM (40 registers, ~380 bytes of spills that stay in L1) beat four at 128 registers: the kernel
-// is FP64-issue bound and short of warps to cover the pipe latency.  Measured on B200, 0.5 degree x 40 levels:
-// 160 registers 2.72 ms, 128: 2.49, 96: 2.48, 80: 2.44, 64: 2.35, 48: 2.32, 40: 2.29.
+// Two register allocations of the same body.  On a large grid (many waves of CTAs) twelve resident CTAs per SM at 40
+// registers, with ~380 bytes of spills that stay in L1, beat four at 128 registers: the kernel is FP64-issue bound and
+// short of warps to cover the pipe latency (measured on B200, 0.5 degree x 40 levels: 160 registers 2.72 ms, 128: 2.49,
+// 96: 2.48, 80: 2.44, 64: 2.35, 48: 2.32, 40: 2.29, 32: 2.30).  On a small grid, where every CTA is resident at once
+// anyway, the spills only lengthen each thread: 100x100x19 takes 83 us at 128 registers and 101 us at 40.
 #ifndef MOBI_CELL_MINB
 #define MOBI_CELL_MINB 12
 #endif
-__global__ void __launch_bounds__(128, MOBI_CELL_MINB) k_mobi_cell(const DevView v) {
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_mobi_cell(const DevView v) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int ni = v.imt - 2, nrow = v.jhi - v.jlo + 1;
   if (idx >= (long long)ni * v.km * nrow) return;
@@ -1688,7 +1691,11 @@ void launch_mobi(uvic_b200_ctx *c, const DevView &v, const uvic_b200_stepinfo *s
   long long ncol = (long long)(v.imt - 2) * (v.jhi - v.jlo + 1);
   if (v.mobi_ncols <= 0) return;
   KLAUNCH("k_mobi_light", k_mobi_light, cdiv(ncol, 128), 128, v, declin);
-  KLAUNCH("k_mobi_cell", k_mobi_cell, cdiv(ncell, 128), 128, v);
+  if (cdiv(ncell, 128) >= 148LL * MOBI_CELL_MINB * 3) {   // at least three full waves at the high occupancy
+    KLAUNCH("k_mobi_cell", k_mobi_cell<MOBI_CELL_MINB>, cdiv(ncell, 128), 128, v);
+  } else {
+    KLAUNCH("k_mobi_cell", k_mobi_cell<4>, cdiv(ncell, 128), 128, v);
+  }
   const int ngroups = (v.mobi_ncols + 31) / 32;
   int mode = mobi_ws_mode();
   // Few column groups: the chain latency of a column dominates and the warp-specialised kernel wins; many groups

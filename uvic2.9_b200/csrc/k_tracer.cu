@@ -781,7 +781,7 @@ void launch_tracer(uvic_b200_ctx *c, const uvic_b200_stepinfo *si) {
     nchunk = (ng + tch - 1) / tch;
     // CTA = 32 i x 4 levels where that tiling wastes few threads (imt - 2 close to a multiple of 32, km to one of 4): the
     // kernel is bound by L2 -> L1 traffic and the tile halves it.  UVIC_B200_UPD_TILE=0/1 overrides (experiments).
-    static const int tile_env = getenv("UVIC_B200_UPD_TILE") ? atoi(getenv("UVIC_B200_UPD_TILE")) : -1;
+    const int tile_env = getenv("UVIC_B200_UPD_TILE") ? atoi(getenv("UVIC_B200_UPD_TILE")) : -1;   // read per call: the tests toggle it
     const int tiled = (tile_env >= 0) ? tile_env : ((double)upd_tiles(v, UPD_T, 1) * UPD_T <= 1.08 * (double)(v.imt - 2) * v.km ? 1 : 0);
     const long long ntile = upd_tiles(v, UPD_T, tiled);
     dim3 gc(tiled ? (unsigned)(ntile * (tiled == 2 ? (nrow_c + 1) / 2 : nrow_c)) : cdiv(ncell_c, UPD_T), nchunk);
