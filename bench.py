@@ -316,13 +316,25 @@ def run_reference(a):
               f"{'the whole grid' if rows_s == w['rows'] else f'a {rows_s}-row latitude sub-slab of the grid (same imt, km, nt; throughput per cell)'}; "
               f"oracle/ C restatement (bitwise equal to the translated reference, tests/test_cpu_refpin.py), gcc -O3 -march=x86-64-v3 "
               f"(the reference builds with -O3, run/mk.ver); single-replica step {1e3 * min(p[0] for p in per):.0f}-{1e3 * tmax:.0f} ms; wall {wall:.0f} s")
+    # Is the port a fair stand-in for the reference's own code?  Where the mechanically translated reference travelled with
+    # the snapshot (oracle/_ref/libref_s.so), time one `tracer` step of it and of the port on its 34x26x8 grid, same flags.
+    check = None
+    try:
+        import subprocess
+
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "time_ref_vs_oracle.py"), "--json"], capture_output=True, text=True, timeout=240)
+        if r.returncode == 0 and r.stdout.strip():
+            check = json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:   # the check is evidence, not the measurement
+        check = {"unavailable": str(e)[:200]}
     line = {
         "impl": "reference", "metric": "tracer cell-updates/sec", "value": value, "unit": "G cell*tracer/s", "n_gpus": a.gpus,
         "steps": nsteps, "warmup": warm, "steps_requested": a.steps, "warmup_requested": a.warmup,
         "ms_per_step": 1e3 * units_per_step(gcase) / (value * 1e9), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_dict(a, w, gcase, world, parts, np),
-        "cpu_baseline": {"value": value, "unit": "G cell*tracer/s", "cores": nrep, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "G cell*tracer/s", "cores": nrep, "kind": "port", "sample": sample,
+                         "port_vs_translated_reference": check},
         "e2e": {"value": value, "unit": "G cell*tracer/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     _emit(line)
