@@ -136,8 +136,7 @@ def kernel_bytes_per_launch(name, case, ctx, ngroup_launch):
         "k_fct_apply": cells * (80 * g + 24),
         "k_update": cells * (80 * g + 176),
         "k_invtri": ocean * (24 * g + 24) + cells * 8 * g,   # wet cells: tendency, t(tau-1), source, a, e, bet in; all cells: t(tau+1) out
-        "k_convect_ts": cells * 32,                    # T,S read + written (worst case)
-        "k_convect_tr": cells * 16 * (case.nt - 2),    # worst case: every other tracer read + written
+        # k_convect_ts / k_convect_tr: data dependent (only the columns that convect are touched): no algorithmic figure
         "k_mobi_column": ocean * 8 * (37 + 15 + 35),   # 37 tracers + 15 pre-pass fields in; 35 sources out
         "k_mobi_ws": ocean * 8 * (37 + 15 + 35),
         "k_mobi_cell": ocean * 8 * (11 + 1 + 15),      # 11 tracers + light in; 15 pre-pass fields out
