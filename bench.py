@@ -719,7 +719,9 @@ def main():
                 "traffic": tr_all.get(kq["kernel"]), "share": kq["share"], "us_per_launch": kq["us_per_launch"],
                 "bytes_per_launch": kq["bytes_per_launch"], "peak_source": peak_src}
 
-    roofline = roof(top)
+    # the dominant kernel that has a roofline figure (the data-dependent convection kernels have none)
+    roofline = next((r for r in (roof(kq) for kq in kern) if r), None) or {"bound": "hbm", "kernel": top["kernel"], "achieved": None, "peak": peak,
+                                                                             "unit": "GB/s", "frac": None, "traffic": None}
     roofline["note"] = ("dominant kernel of the per-kernel profile pass; achieved = algorithmic bytes (or FP64 instructions) of one launch / its "
                         f"CUDA-event time; traffic = ncu dram bytes of one launch (profiles/{ncu_tag}_ncu_traffic.json)")
     roofline_top = [r for r in (roof(kq) for kq in kern[:6]) if r]
