@@ -220,7 +220,8 @@ def _stress(case, o, ref, rng):
     reflib.oracle_to_ref(o, ref, only=["t", "stf", "btf"])
 
 
-@pytest.mark.parametrize("seed,stress,fourfil", [(3, False, False), (11, True, False), (4, True, True)])
+@pytest.mark.parametrize("seed,stress,fourfil", [(3, False, False), (11, True, False), (4, True, True), (7, True, True), (23, True, False),
+                                                 (31, False, True)])
 def test_full_tracer_step_bitwise(pkg, ref, seed, stress, fourfil):
     """isopyc -> vmixc -> tracer (MOBI, FCT, isoflux, ivdift/invtri, convct2, filt) as mom sequences them: leapfrog, leapfrog,
     mixing step, leapfrog -- all 37 tracers of t(tau+1) bit for bit after every step"""
