@@ -915,9 +915,9 @@ class Translator:
             else:
                 if self._declare(u, s) and not s.startswith("data"):
                     continue
-            m = re.match(r"entry\s+([a-z0-9_]+)\s*\((.*)\)$", s)
+            m = re.match(r"entry\s+([a-z0-9_]+)\s*(?:\((.*)\))?$", s)
             if m:
-                eargs = [a.strip() for a in m.group(2).split(",") if a.strip()]
+                eargs = [a.strip() for a in (m.group(2) or "").split(",") if a.strip()]
                 for a in eargs:
                     u.sym(a).kind = "arg"
                 u.entries.append((m.group(1), eargs, len(execs)))
