@@ -25,7 +25,9 @@ def build(src, units):
     tr.known_units |= set(units)
     tr.load(f2c.read_fixed_form(src), only=set(units))
     csrc = tr.emit()
-    d = tempfile.mkdtemp(prefix="f2c_")
+    base = os.path.join(ROOT, "oracle", "_ref", "f2c_tests")          # git-ignored build area of the translated code
+    os.makedirs(base, exist_ok=True)
+    d = tempfile.mkdtemp(prefix="t_", dir=base)
     cp, so = os.path.join(d, "t.c"), os.path.join(d, "t.so")
     open(cp, "w").write(csrc)
     r = subprocess.run(["gcc", "-O2", "-fno-fast-math", "-ffp-contract=off", "-fPIC", "-std=gnu11", "-w", "-shared", "-o", so, cp, "-lm"],
