@@ -8,6 +8,7 @@ values are computed in Python by the Fortran rules.  TEST INFRASTRUCTURE (needs 
 import ctypes
 import math
 import os
+import shutil
 import subprocess
 import sys
 import tempfile
@@ -33,7 +34,9 @@ def build(src, units):
     r = subprocess.run(["gcc", "-O2", "-fno-fast-math", "-ffp-contract=off", "-fPIC", "-std=gnu11", "-w", "-shared", "-o", so, cp, "-lm"],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[:3000] + "\n" + csrc[-3000:]
-    return ctypes.CDLL(so), csrc
+    lib = ctypes.CDLL(so)
+    shutil.rmtree(d, ignore_errors=True)                              # the mapping stays valid
+    return lib, csrc
 
 
 def dptr(a):
